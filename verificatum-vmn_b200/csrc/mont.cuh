@@ -1,0 +1,138 @@
+// mont.cuh -- thread-per-element Montgomery multiplication (CIOS, two rows per loop trip).
+//
+// One thread owns one N-limb residue: `a` (N registers) and the running CIOS accumulator
+// `t` (N+2 registers) stay in registers; the second operand is streamed one 32-bit word per
+// row; the modulus is read straight from the kernel-parameter constant bank (no registers).
+//
+// Why two rows per trip and an "odd block": IMAD.WIDE needs an even-aligned (lo,hi) register
+// pair.  A product a[j]*b[i] lands on columns (i+j, i+j+1); half of the products of every row
+// are therefore mis-aligned with respect to a fixed accumulator.  We call products on an even
+// absolute column E-class (fused straight into `t`) and the others O-class.  O-class products
+// of a row PAIR (i, i+1) all fall on the same pairs (1,2),(3,4),..; they are accumulated --
+// fused, with carry chains -- into a small separate block `o` of 2*PB registers that is
+// aligned on its own, and folded into `t` with one add chain per block.  The last E chain of
+// the trip writes its results two registers lower, which implements the CIOS right shift by
+// two words for free (no MOVs).  Result: 4*N IMAD.WIDE + ~1.1*N IADD3 per trip.
+//
+// Algorithmic unit: 1 modmul = 2N^2+N word MACs; this kernel executes exactly
+// 2N^2 IMAD.WIDE + N mul.lo for it.
+#pragma once
+#include "ptx_arith.cuh"
+
+namespace vmx {
+
+template <int N>
+struct MontParams {
+  uint32_t n[N];    // modulus, little-endian limbs
+  uint32_t n0inv;   // -n^{-1} mod 2^32
+};
+
+constexpr int kPairBlock = 8;  // O-class pairs per block (16 columns)
+
+// One trip = rows (i, i+1).  t holds relative columns 0..N+1 on entry and on exit (exit
+// columns are entry columns 2..N+3).
+template <int N>
+VMX_DEV void mont_rowpair(uint32_t (&t)[N + 2], const uint32_t (&a)[N], uint32_t b0, uint32_t b1,
+                          const MontParams<N>& M) {
+  static_assert(N % (2 * kPairBlock) == 0, "N must be a multiple of 16");
+  constexpr int PB = kPairBlock;
+  uint32_t top2 = 0;  // column N+2
+
+  // E-class, row 0: a[even j] * b0 on pairs (j, j+1)
+  mad_wide_cc(t[0], t[1], a[0], b0);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) madc_wide_cc(t[j], t[j + 1], a[j], b0);
+  addc_cc(t[N], t[N], 0);
+  addc(t[N + 1], t[N + 1], 0);
+
+  const uint32_t m0 = t[0] * M.n0inv;
+
+  // E-class, row 0 reduction: n[even j] * m0
+  mad_wide_cc(t[0], t[1], M.n[0], m0);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) madc_wide_cc(t[j], t[j + 1], M.n[j], m0);
+  addc_cc(t[N], t[N], 0);
+  addc(t[N + 1], t[N + 1], 0);
+
+  // E-class, row 1: a[odd j] * b1 on pairs (1+j, 2+j)
+  mad_wide_cc(t[2], t[3], a[1], b1);
+#pragma unroll
+  for (int j = 3; j < N; j += 2) madc_wide_cc(t[j + 1], t[j + 2], a[j], b1);
+  addc(top2, top2, 0);
+
+  // O-class: pair q sits on columns (c, c+1), c = 2q+1, and receives
+  //   a[c]*b0 + n[c]*m0 + a[c-1]*b1 + n[c-1]*m1
+  uint32_t m1 = 0;
+  uint32_t cw = 0;  // carry word handed from one block to the next
+#pragma unroll
+  for (int kb = 0; kb < N / 2 / PB; kb++) {
+    uint32_t o[2 * PB];
+    uint32_t oc;
+    const int c0 = 2 * kb * PB + 1;
+    // chain A (no carries between pairs; the first pair absorbs the incoming carry word)
+    mad_wide_cc3(o[0], o[1], a[c0], b0, cw, 0);
+#pragma unroll
+    for (int r = 1; r < PB; r++) mul_wide(o[2 * r], o[2 * r + 1], a[c0 + 2 * r], b0);
+    // chain B
+    mad_wide_cc(o[0], o[1], M.n[c0], m0);
+#pragma unroll
+    for (int r = 1; r < PB; r++) madc_wide_cc(o[2 * r], o[2 * r + 1], M.n[c0 + 2 * r], m0);
+    addc(oc, 0, 0);
+    // chain C
+    mad_wide_cc(o[0], o[1], a[c0 - 1], b1);
+#pragma unroll
+    for (int r = 1; r < PB; r++) madc_wide_cc(o[2 * r], o[2 * r + 1], a[c0 - 1 + 2 * r], b1);
+    addc(oc, oc, 0);
+    if (kb == 0) m1 = (t[1] + o[0]) * M.n0inv;
+    // chain D
+    mad_wide_cc(o[0], o[1], M.n[c0 - 1], m1);
+#pragma unroll
+    for (int r = 1; r < PB; r++) madc_wide_cc(o[2 * r], o[2 * r + 1], M.n[c0 - 1 + 2 * r], m1);
+    addc(oc, oc, 0);
+    // fold the block into t
+    add_cc(t[c0], t[c0], o[0]);
+#pragma unroll
+    for (int r = 1; r < 2 * PB; r++) addc_cc(t[c0 + r], t[c0 + r], o[r]);
+    addc(cw, oc, 0);
+  }
+  add_cc(t[N + 1], t[N + 1], cw);
+  addc(top2, top2, 0);
+
+  // E-class, row 1 reduction: n[odd j] * m1 on pairs (1+j, 2+j), written two columns lower.
+  mad_wide_cc3(t[0], t[1], M.n[1], m1, t[2], t[3]);
+#pragma unroll
+  for (int j = 3; j < N; j += 2) madc_wide_cc3(t[j - 1], t[j], M.n[j], m1, t[j + 1], t[j + 2]);
+  addc_cc(t[N], top2, 0);
+  addc(t[N + 1], 0, 0);
+}
+
+// r = t - n if t >= n else t, where t has N+1 significant words (t < 2n).
+template <int N>
+VMX_DEV void mont_final_sub(uint32_t (&r)[N], const uint32_t (&t)[N + 2], const MontParams<N>& M) {
+  uint32_t d[N];
+  uint32_t top;
+  sub_cc(d[0], t[0], M.n[0]);
+#pragma unroll
+  for (int j = 1; j < N; j++) subc_cc(d[j], t[j], M.n[j]);
+  subc(top, t[N], 0);
+  // top == 0  -> t >= n (no borrow out of the N+1 word subtraction): take d; else keep t
+  const bool keep = (top != 0);
+#pragma unroll
+  for (int j = 0; j < N; j++) r[j] = keep ? t[j] : d[j];
+}
+
+// a <- a * b * R^{-1} mod n, with b streamed through `ld(i)` (any callable returning word i).
+template <int N, typename Loader>
+VMX_DEV void mont_mul(uint32_t (&a)[N], Loader ld, const MontParams<N>& M) {
+  uint32_t t[N + 2];
+#pragma unroll
+  for (int i = 0; i < N + 2; i++) t[i] = 0;
+#pragma unroll 1
+  for (int i = 0; i < N; i += 2) {
+    const uint32_t b0 = ld(i), b1 = ld(i + 1);
+    mont_rowpair<N>(t, a, b0, b1, M);
+  }
+  mont_final_sub<N>(a, t, M);
+}
+
+}  // namespace vmx
