@@ -15,7 +15,7 @@ template <int N> int run() {
   for (;;) {
     for (int i = 0; i < N; i++) if (scanf("%x", &a[i]) != 1) return 0;
     for (int i = 0; i < N; i++) if (scanf("%x", &b[i]) != 1) return 1;
-    vmx::mont_mul<N>(a, [&](int i) { return b[i]; }, M);
+    vmx::mont_mul<N>(a, [&](int i) { return vmx::Word2{b[i], b[i + 1]}; }, M);
     for (int i = 0; i < N; i++) printf("%08x ", a[i]);
     printf("\n");
   }

@@ -1,0 +1,321 @@
+// kernels_elem.cuh -- element-wise (thread-per-element) kernels: codec, mul, exponentiations.
+//
+// Every kernel keeps one residue per thread in registers (see mont.cuh) and streams the other
+// operand.  Grids are sized in 128-thread blocks; with 254 registers (N=96) two blocks are
+// resident per SM (8 warps, 2 per scheduler), which saturates the half-rate IMAD.WIDE pipe.
+#pragma once
+#include "layout.cuh"
+
+namespace vmx {
+
+constexpr int kThreads = 128;
+template <int N> struct Occ { static constexpr int kMinBlocks = (N > 64) ? 2 : 3; };
+#define VMX_KERNEL(N) __global__ void __launch_bounds__(kThreads, Occ<N>::kMinBlocks)
+
+// error flag bits
+enum { kErrRange = 1, kErrZero = 2, kErrPad = 4, kErrMember = 8 };
+
+// ------------------------------------------------------------------ byte codec
+// raw: n elements of `eb` big-endian bytes (eb >= 4N; leading eb-4N bytes must be zero).
+// mode 0: group element -> range check 0 < x < mod, to Montgomery form (x * R).
+// mode 1: ring element  -> range check 0 <= x < mod, stays canonical.
+template <int N>
+VMX_KERNEL(N) k_from_bytes(const uint8_t* __restrict__ raw, size_t n, int eb, int mode, uint32_t* __restrict__ out,
+                           size_t cap, const uint32_t* __restrict__ r2, int* __restrict__ err,
+                           const __grid_constant__ MontParams<N> M) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* src = raw + i * (size_t)eb;
+  uint32_t a[N];
+  int bad = 0;
+  const int pad = eb - 4 * N;
+  for (int k = 0; k < pad; k++) if (src[k] != 0) bad |= kErrPad;
+  src += pad;
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    const uint8_t* q = src + 4 * (N - 1 - j);
+    a[j] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+  }
+  // x < mod ?
+  uint32_t d, brw;
+  sub_cc(d, a[0], M.n[0]);
+#pragma unroll
+  for (int j = 1; j < N; j++) subc_cc(d, a[j], M.n[j]);
+  subc(brw, 0, 0);
+  if (brw == 0) bad |= kErrRange;
+  if (mode == 0) {
+    uint32_t nz = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) nz |= a[j];
+    if (nz == 0) bad |= kErrZero;
+    if (!bad) mont_mul<N>(a, GlobalLoader(r2, 4, 0), M);
+  }
+  if (bad) atomicOr(err, bad);
+  store_elem<N>(a, out, cap, i);
+}
+
+// mode 0: group element (Montgomery -> canonical first); mode 1: ring element.
+template <int N>
+VMX_KERNEL(N) k_to_bytes(const uint32_t* __restrict__ in, size_t cap, size_t n, int eb, int mode,
+                         uint8_t* __restrict__ raw, const __grid_constant__ MontParams<N> M) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t a[N];
+  load_elem<N>(a, in, cap, i);
+  if (mode == 0) mont_mul<N>(a, OneLoader{}, M);
+  uint8_t* dst = raw + i * (size_t)eb;
+  const int pad = eb - 4 * N;
+  for (int k = 0; k < pad; k++) dst[k] = 0;
+  dst += pad;
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    uint8_t* q = dst + 4 * (N - 1 - j);
+    q[0] = (uint8_t)(a[j] >> 24); q[1] = (uint8_t)(a[j] >> 16); q[2] = (uint8_t)(a[j] >> 8); q[3] = (uint8_t)a[j];
+  }
+}
+
+// raw unsigned integers of `width` bytes (big-endian), masked to `bitlen` bits (0 = all),
+// reduced mod q.  Handles width*8 up to 2*32N bits.
+template <int N>
+VMX_KERNEL(N) k_ring_from_raw(const uint8_t* __restrict__ raw, size_t n, int width, int bitlen,
+                              uint32_t* __restrict__ out, size_t cap, const uint32_t* __restrict__ r2,
+                              int need_reduce, const __grid_constant__ MontParams<N> M) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* src = raw + i * (size_t)width;
+  const int totalbits = bitlen ? bitlen : 8 * width;
+  auto word = [&](int j) -> uint32_t {  // little-endian word j of the masked integer
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int byte = 4 * j + k;  // little-endian byte index
+      if (byte < width) {
+        uint32_t b = src[width - 1 - byte];
+        const int hb = totalbits - 8 * byte;  // valid bits in this byte
+        if (hb <= 0) b = 0; else if (hb < 8) b &= (1u << hb) - 1u;
+        v |= b << (8 * k);
+      }
+    }
+    return v;
+  };
+  uint32_t lo[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) lo[j] = word(j);
+  if (need_reduce) {
+    // x = hi * 2^(32N) + lo ;  x mod q = hi*R mod q + lo mod q
+    const GlobalLoader R2(r2, 4, 0);
+    mont_mul<N>(lo, R2, M);          // lo * R
+    mont_mul<N>(lo, OneLoader{}, M); // lo mod q
+    if (8 * width > 32 * N) {
+      uint32_t hi[N];
+#pragma unroll
+      for (int j = 0; j < N; j++) hi[j] = word(N + j);
+      mont_mul<N>(hi, R2, M);        // hi * R mod q
+      // lo = lo + hi mod q
+      uint32_t c;
+      add_cc(lo[0], lo[0], hi[0]);
+#pragma unroll
+      for (int j = 1; j < N; j++) addc_cc(lo[j], lo[j], hi[j]);
+      addc(c, 0, 0);
+      uint32_t d[N], brw;
+      sub_cc(d[0], lo[0], M.n[0]);
+#pragma unroll
+      for (int j = 1; j < N; j++) subc_cc(d[j], lo[j], M.n[j]);
+      subc(brw, c, 0);
+      const bool keep = (brw != 0);
+#pragma unroll
+      for (int j = 0; j < N; j++) lo[j] = keep ? lo[j] : d[j];
+    }
+  }
+  store_elem<N>(lo, out, cap, i);
+}
+
+// ------------------------------------------------------------------ out[i] = a[i] * b[i]
+template <int N>
+VMX_KERNEL(N) k_mul(const uint32_t* __restrict__ a_, size_t acap, const uint32_t* __restrict__ b_, size_t bcap,
+                    uint32_t* __restrict__ out, size_t ocap, size_t n, const __grid_constant__ MontParams<N> M) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t a[N];
+  load_elem<N>(a, a_, acap, i);
+  mont_mul<N>(a, GlobalLoader(b_, bcap, i), M);
+  store_elem<N>(a, out, ocap, i);
+}
+
+// out[i] = a[i] * b[i]^iters  (benchmark of the raw modmul path)
+template <int N>
+VMX_KERNEL(N) k_mul_iter(const uint32_t* __restrict__ a_, const uint32_t* __restrict__ b_, uint32_t* __restrict__ out,
+                         size_t cap, size_t n, int iters, const __grid_constant__ MontParams<N> M) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t a[N];
+  load_elem<N>(a, a_, cap, i);
+  const GlobalLoader B(b_, cap, i);
+  for (int it = 0; it < iters; it++) mont_mul<N>(a, B, M);
+  store_elem<N>(a, out, cap, i);
+}
+
+// ------------------------------------------------------------------ fixed-base exponentiation
+// table: nwin * 2^w entries, entry (k, d) = base^(d * 2^(w*k)) in Montgomery form (d = 0 -> one).
+// Work item = (element i, window range part): part p of `parts` multiplies windows
+// [p*nwin/parts, (p+1)*nwin/parts) and writes to out element p*n + i (parts > 1 -> combined later).
+template <int N>
+VMX_KERNEL(N) k_exp_fixed(const uint32_t* __restrict__ table, size_t tcap, int w, int nwin,
+                          const uint32_t* __restrict__ e_, size_t ecap, size_t n, int parts,
+                          uint32_t* __restrict__ out, size_t ocap, const __grid_constant__ MontParams<N> M) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * (size_t)parts) return;
+  const size_t i = t % n;
+  const int p = (int)(t / n);
+  const int k0 = (int)((long long)nwin * p / parts), k1 = (int)((long long)nwin * (p + 1) / parts);
+  uint32_t a[N];
+  {
+    const uint32_t d = window_bits<N>(e_, ecap, i, k0 * w, w);
+    load_elem<N>(a, table, tcap, ((size_t)k0 << w) + d);
+  }
+  uint32_t dn = (k0 + 1 < k1) ? window_bits<N>(e_, ecap, i, (k0 + 1) * w, w) : 0;
+  for (int k = k0 + 1; k < k1; k++) {
+    const GlobalLoader B(table, tcap, ((size_t)k << w) + dn);
+    if (k + 1 < k1) dn = window_bits<N>(e_, ecap, i, (k + 1) * w, w);
+    mont_mul<N>(a, B, M);
+  }
+  store_elem<N>(a, out, ocap, t);
+}
+
+// out[i] = prod_{p < parts} in[p*n + i]
+template <int N>
+VMX_KERNEL(N) k_combine_parts(const uint32_t* __restrict__ in, size_t icap, size_t n, int parts,
+                              uint32_t* __restrict__ out, size_t ocap, const __grid_constant__ MontParams<N> M) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t a[N];
+  load_elem<N>(a, in, icap, i);
+  for (int p = 1; p < parts; p++) mont_mul<N>(a, GlobalLoader(in, icap, (size_t)p * n + i), M);
+  store_elem<N>(a, out, ocap, i);
+}
+
+// Squaring chain Q[m] = base^(2^m), m = 0..len-1 (single thread; latency-bound, run once per base).
+template <int N>
+VMX_KERNEL(N) k_sqr_chain(const uint32_t* __restrict__ base, size_t bcap, size_t bidx, uint32_t* __restrict__ Q,
+                          size_t qcap, int len, const __grid_constant__ MontParams<N> M) {
+  extern __shared__ uint2 smem[];
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint32_t a[N];
+  load_elem<N>(a, base, bcap, bidx);
+  store_elem<N>(a, Q, qcap, 0);
+  for (int m = 1; m < len; m++) {
+    mont_sqr<N>(a, smem, 1, M);
+    store_elem<N>(a, Q, qcap, m);
+  }
+}
+
+// Table level j: T[k][2^j + r] = Q[w*k + j] * T[k][r], r in [0, 2^j); T[k][0] = one.
+// Work item t -> (k, r).
+template <int N>
+VMX_KERNEL(N) k_table_level(uint32_t* __restrict__ table, size_t tcap, int w, int nwin, int j, int qlen,
+                            const uint32_t* __restrict__ Q, size_t qcap, const uint32_t* __restrict__ one,
+                            const __grid_constant__ MontParams<N> M) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per = (size_t)1 << j;
+  if (t >= per * nwin) return;
+  const int k = (int)(t >> j);
+  const size_t r = t & (per - 1);
+  const int m = w * k + j;
+  uint32_t a[N];
+  const size_t dst = ((size_t)k << w) + per + r;
+  if (m >= qlen) {  // beyond the exponent range: never addressed, keep defined
+    load_elem<N>(a, one, 4, 1);
+    store_elem<N>(a, table, tcap, dst);
+    return;
+  }
+  if (r == 0) {
+    load_elem<N>(a, Q, qcap, m);
+    if (j == 0) {  // also write entry 0 = one
+      uint32_t o[N];
+      load_elem<N>(o, one, 4, 1);
+      store_elem<N>(o, table, tcap, (size_t)k << w);
+    }
+  } else {
+    load_elem<N>(a, table, tcap, ((size_t)k << w) + r);
+    mont_mul<N>(a, GlobalLoader(Q, qcap, m), M);
+  }
+  store_elem<N>(a, table, tcap, dst);
+}
+
+// ------------------------------------------------------------------ variable-base exponentiation
+// out[i] = a[i]^{e[i]} (escalar = 0) or a[i]^{e[0]} (escalar = 1); fixed w-bit windows, top-down.
+// tab: scratch for per-thread tables, (2^w) * n elements, entry d of element i at d*n + i.
+template <int N>
+VMX_KERNEL(N) k_exp_var(const uint32_t* __restrict__ a_, size_t acap, const uint32_t* __restrict__ e_, size_t ecap,
+                        int escalar, int ebits, int w, size_t n, uint32_t* __restrict__ tab, size_t tabcap,
+                        const uint32_t* __restrict__ one, uint32_t* __restrict__ out, size_t ocap,
+                        const __grid_constant__ MontParams<N> M) {
+  extern __shared__ uint2 smem[];
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint2* sc = smem + threadIdx.x;
+  const unsigned ss = blockDim.x;
+  const size_t ei = escalar ? 0 : i;
+  uint32_t a[N];
+  // table: tab[0] = 1, tab[1] = base, tab[d] = tab[d-1] * base
+  load_elem<N>(a, one, 4, 1);
+  store_elem<N>(a, tab, tabcap, i);
+  load_elem<N>(a, a_, acap, i);
+  store_elem<N>(a, tab, tabcap, n + i);
+  const GlobalLoader Bse(a_, acap, i);
+  for (int d = 2; d < (1 << w); d++) {
+    mont_mul<N>(a, Bse, M);
+    store_elem<N>(a, tab, tabcap, (size_t)d * n + i);
+  }
+  const int nwin = (ebits + w - 1) / w;
+  {
+    const uint32_t d = window_bits<N>(e_, ecap, ei, (nwin - 1) * w, w);
+    load_elem<N>(a, tab, tabcap, (size_t)d * n + i);
+  }
+  for (int k = nwin - 2; k >= 0; k--) {
+    const uint32_t d = window_bits<N>(e_, ecap, ei, k * w, w);
+    for (int s = 0; s < w; s++) mont_sqr<N>(a, sc, ss, M);
+    mont_mul<N>(a, GlobalLoader(tab, tabcap, (size_t)d * n + i), M);
+  }
+  store_elem<N>(a, out, ocap, i);
+}
+
+// ------------------------------------------------------------------ data movement (uint4 granularity)
+// out[dst(i)] = in[src(i)] for plane-wise copies; one thread per (plane, element).
+__global__ void k_gather(const uint4* __restrict__ in, size_t icap, uint4* __restrict__ out, size_t ocap, size_t n,
+                         int planes, const uint32_t* __restrict__ src_idx, const uint32_t* __restrict__ dst_idx,
+                         long long src_off, long long dst_off) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * (size_t)planes) return;
+  const size_t i = t % n, g = t / n;
+  const size_t s = src_idx ? src_idx[i] : (size_t)((long long)i + src_off);
+  const size_t d = dst_idx ? dst_idx[i] : (size_t)((long long)i + dst_off);
+  out[g * ocap + d] = in[g * icap + s];
+}
+
+// *diff |= any word differs
+__global__ void k_equal(const uint4* __restrict__ a, size_t acap, const uint4* __restrict__ b, size_t bcap, size_t n,
+                        int planes, int* __restrict__ diff) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * (size_t)planes) return;
+  const size_t i = t % n, g = t / n;
+  const uint4 x = a[g * acap + i], y = b[g * bcap + i];
+  if (x.x != y.x || x.y != y.y || x.z != y.z || x.w != y.w) atomicOr(diff, 1);
+}
+
+// max bit length over the array -> atomicMax(bits)
+template <int N>
+__global__ void k_bitlen(const uint32_t* __restrict__ d, size_t cap, size_t n, unsigned* __restrict__ bits) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned b = 0;
+  if (i < n) {
+    for (int j = N - 1; j >= 0; j--) {
+      const uint32_t v = d[((size_t)(j >> 2) * cap + i) * 4 + (j & 3)];
+      if (v) { b = 32u * j + (32u - __clz(v)); break; }
+    }
+  }
+  b = __reduce_max_sync(0xffffffffu, b);
+  if ((threadIdx.x & 31) == 0 && b) atomicMax(bits, b);
+}
+
+}  // namespace vmx

@@ -121,16 +121,19 @@ VMX_DEV void mont_final_sub(uint32_t (&r)[N], const uint32_t (&t)[N + 2], const 
   for (int j = 0; j < N; j++) r[j] = keep ? t[j] : d[j];
 }
 
-// a <- a * b * R^{-1} mod n, with b streamed through `ld(i)` (any callable returning word i).
+struct Word2 { uint32_t x, y; };
+
+// a <- a * b * R^{-1} mod n, with b streamed through `ld2(i)` (any callable returning the
+// word pair (b[i], b[i+1]) for even i).  Result fully reduced to [0, n).
 template <int N, typename Loader>
-VMX_DEV void mont_mul(uint32_t (&a)[N], Loader ld, const MontParams<N>& M) {
+VMX_DEV void mont_mul(uint32_t (&a)[N], Loader ld2, const MontParams<N>& M) {
   uint32_t t[N + 2];
 #pragma unroll
   for (int i = 0; i < N + 2; i++) t[i] = 0;
 #pragma unroll 1
   for (int i = 0; i < N; i += 2) {
-    const uint32_t b0 = ld(i), b1 = ld(i + 1);
-    mont_rowpair<N>(t, a, b0, b1, M);
+    const Word2 b = ld2(i);
+    mont_rowpair<N>(t, a, b.x, b.y, M);
   }
   mont_final_sub<N>(a, t, M);
 }
