@@ -62,6 +62,9 @@ void vmx_ctx_destroy(vmx_ctx* ctx);
 size_t vmx_ctx_elem_bytes(const vmx_ctx* ctx); /* bytelen(p) = bits/8 + 1 */
 size_t vmx_ctx_ring_bytes(const vmx_ctx* ctx); /* bytelen(q)              */
 int vmx_ctx_sync(vmx_ctx* ctx);                /* wait for all queued work */
+void* vmx_ctx_stream(vmx_ctx* ctx);            /* the cudaStream_t all work of this ctx is queued on */
+/* Window width of fixed-base tables built from now on (0 = choose from the array size). */
+int vmx_ctx_set_fixed_window(vmx_ctx* ctx, int w);
 
 /* ---------------------------------------------------------------- group arrays: I/O */
 /* PGroup.toElementArray(size, ByteTreeReader) (hvzk/PoSBasicTW.java:507,787-789;
@@ -69,6 +72,10 @@ int vmx_ctx_sync(vmx_ctx* ctx);                /* wait for all queued work */
  * satisfy 0 < x < p and, if check_membership != 0, x^q = 1 (Legendre symbol 1 for safe primes).
  * On violation returns VMX_EFORMAT and *out = NULL. */
 int vmx_garr_from_bytes(vmx_ctx* ctx, size_t n, const uint8_t* be, int check_membership, vmx_garr** out);
+/* PGroup.randomElementArray(size, prg, statDist) for ModPGroup (distr/IndependentGeneratorsRO.java:129):
+ * element i = (t_i mod p)^((p-1)/q), t_i = the i-th `width`-byte big-endian integer masked to
+ * `bitlen` bits.  The bytes come from the caller's PRG; reduction and cofactor power run here. */
+int vmx_garr_from_raw(vmx_ctx* ctx, size_t n, const uint8_t* be, size_t width, unsigned bitlen, vmx_garr** out);
 /* PGroupElementArray.toByteTree() payload (hvzk/PoSBasicTW.java:694-699). */
 int vmx_garr_to_bytes(const vmx_garr* a, uint8_t* be_out);
 /* PGroup.toElementArray(size, PGroupElement): n copies of one element (hvzk/PoSBasicTW.java:805). */
@@ -81,6 +88,9 @@ size_t vmx_garr_size(const vmx_garr* a);
  * (mixnet/ShufflerElGamalSession.java:407; hvzk/PoSBasicTW.java:447,606,608,644,646,1030).
  * The window table for `base` is built on first use and cached in the ctx. */
 int vmx_exp_fixed(vmx_ctx* ctx, const uint8_t* base_be, const vmx_rarr* e, vmx_garr** out);
+/* Build (or resize) the table of `base` ahead of time for arrays of about n_hint exponents:
+ * the analogue of VMG.fpowm_precomp in the reference's native seam. */
+int vmx_fixed_precompute(vmx_ctx* ctx, const uint8_t* base_be, size_t n_hint);
 /* PGroupElementArray.exp(PRingElementArray): out[i] = a[i]^{e[i]} (hvzk/PoSBasicTW.java:1032). */
 int vmx_exp_var(const vmx_garr* a, const vmx_rarr* e, vmx_garr** out);
 /* PGroupElementArray.exp(PRingElement): out[i] = a[i]^{e} (hvzk/PoSBasicTW.java:1028;
@@ -137,6 +147,7 @@ int vmx_rarr_bitlen(const vmx_rarr* a, unsigned* bits);
 
 int vmx_radd(const vmx_rarr* a, const vmx_rarr* b, vmx_rarr** out);             /* hvzk/PoSBasicTW.java:643 */
 int vmx_rneg(const vmx_rarr* a, vmx_rarr** out);
+int vmx_rsub(const vmx_rarr* a, const vmx_rarr* b, vmx_rarr** out);
 int vmx_rmul(const vmx_rarr* a, const vmx_rarr* b, vmx_rarr** out);             /* :642,645 */
 /* PRingElementArray.mulAdd(scalar, arr): out[i] = a[i]*s + b[i] (:874,877). */
 int vmx_rmuladd(const vmx_rarr* a, const uint8_t* s_be, const vmx_rarr* b, vmx_rarr** out);

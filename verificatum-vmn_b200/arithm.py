@@ -1,0 +1,1006 @@
+"""GPU-backed mirror of the `com.verificatum.arithm` array API the mix-net hot path calls.
+
+Same class and method names as verificatum-vcr 3.1.0 (camelCase kept on purpose, so the
+protocol code in hvzk.py / mixnet.py reads like the Java it mirrors and the Java call sites in
+/root/reference map one to one):
+
+    ModPGroup, PPGroup, PGroupElement, PPGroupElement, PGroupElementArray, PPGroupElementArray,
+    PField (Z_q), PPRing, PFieldElement, PPRingElement, PRingElementArray, PPRingElementArray,
+    LargeIntegerArray, Permutation
+
+Arrays are opaque DEVICE handles of the C ABI (include/vmx.h); every array method is one C-ABI
+call (or one per component of a product group).  Single elements are host values (Python ints),
+exactly as single `PGroupElement`s are JVM-side `LargeInteger`s in the reference; their
+exponentiations are routed through the engine as one-element arrays so that no group
+arithmetic is ever done on the CPU.  Every temporary must be `free()`d, as in the reference.
+
+Semantics that live in the un-vendored VCR jar ([VCR-mem] in SURVEY.md §8c) and are fixed here:
+  * `permute(pi)`:  result[pi.map(i)] = this[i]
+  * `Z_q.randomElementArray(n, rs, statDist)`: ceil((|q|+statDist)/8) bytes per element, masked
+    to |q|+statDist bits, reduced mod q
+  * `LargeIntegerArray.random(n, bits, rs)`: ceil(bits/8) bytes per element, masked to `bits`
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as nat
+from .eio import (ByteTreeBasic, ByteTreeContainer, ByteTreeLeaf, ByteTreeLeafArray, ByteTreeReader, EIOException,
+                  int_to_bytes)
+
+ArithmFormatException = nat.ArithmFormatError
+
+
+class ArithmError(RuntimeError):
+    pass
+
+
+def _ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _be(x: int, width: int) -> bytes:
+    return x.to_bytes(width, "big")
+
+
+# ====================================================================== permutations
+class Permutation:
+    """com.verificatum.arithm.Permutation (table form)."""
+
+    def __init__(self, table: Sequence[int]):
+        self.table = np.ascontiguousarray(np.asarray(table, dtype=np.uint32))
+
+    @staticmethod
+    def identity(size: int) -> "Permutation":
+        return Permutation(np.arange(size, dtype=np.uint32))
+
+    @staticmethod
+    def random(size: int, randomSource, statDist: int) -> "Permutation":
+        """Sort-based sampling: `size` integers of ceil(log2 size)+statDist bits, stable argsort."""
+        bits = max(1, (size - 1).bit_length()) + statDist
+        nbytes = (bits + 7) // 8
+        raw = np.frombuffer(randomSource.getBytes(size * nbytes), dtype=np.uint8).reshape(size, nbytes).copy()
+        raw[:, 0] &= 0xFF >> ((8 - bits % 8) % 8)
+        keys = [bytes(r) for r in raw]
+        order = sorted(range(size), key=lambda i: (keys[i], i))
+        table = np.empty(size, dtype=np.uint32)
+        table[np.asarray(order, dtype=np.int64)] = np.arange(size, dtype=np.uint32)
+        return Permutation(table)
+
+    def size(self) -> int:
+        return int(self.table.shape[0])
+
+    def map(self, i: int) -> int:
+        return int(self.table[i])
+
+    def inv(self) -> "Permutation":
+        inv = np.empty_like(self.table)
+        inv[self.table] = np.arange(self.table.shape[0], dtype=np.uint32)
+        return Permutation(inv)
+
+    def free(self) -> None:
+        pass
+
+
+# ====================================================================== rings
+class PRing:
+    pass
+
+
+class PField(PRing):
+    """Z_q, the exponent ring of a prime-order group."""
+
+    def __init__(self, group: "ModPGroup"):
+        self.group = group
+        self.order = group.q
+        self.byte_len = group.ring_bytes
+
+    # -- elements
+    def getZERO(self) -> "PFieldElement":
+        return PFieldElement(self, 0)
+
+    def getONE(self) -> "PFieldElement":
+        return PFieldElement(self, 1)
+
+    def getPField(self) -> "PField":
+        return self
+
+    def toElement(self, x) -> "PFieldElement":
+        if isinstance(x, ByteTreeReader):
+            if not x.isLeaf() or x.getRemaining() != self.byte_len:
+                raise ArithmFormatException(nat.VMX_EFORMAT, "ring element of wrong length")
+            v = int.from_bytes(x.read(), "big", signed=True)
+            if not 0 <= v < self.order:
+                raise ArithmFormatException(nat.VMX_EFORMAT, "ring element out of range")
+            return PFieldElement(self, v)
+        return PFieldElement(self, int(x) % self.order)
+
+    def randomElement(self, randomSource, statDist: int) -> "PFieldElement":
+        bits = self.order.bit_length() + statDist
+        raw = randomSource.getBytes((bits + 7) // 8)
+        return PFieldElement(self, (int.from_bytes(raw, "big") & ((1 << bits) - 1)) % self.order)
+
+    # -- arrays
+    def randomElementArray(self, size: int, randomSource, statDist: int) -> "PRingElementArray":
+        bits = self.order.bit_length() + statDist
+        width = (bits + 7) // 8
+        raw = np.frombuffer(randomSource.getBytes(size * width), dtype=np.uint8)
+        return self._from_raw(size, raw, width, bits)
+
+    def _from_raw(self, size, raw: np.ndarray, width: int, bits: int) -> "PRingElementArray":
+        lib = nat.load()
+        h = C.c_void_p()
+        nat.check(lib.vmx_rarr_from_raw(self.group.ctx, size, _ptr(raw), width, bits, C.byref(h)))
+        return PRingElementArray(self, h)
+
+    def toElementArray(self, *args) -> "PRingElementArray":
+        """(size, ByteTreeReader) | (LargeIntegerArray) | (size, element) | (list of elements)."""
+        lib = nat.load()
+        if len(args) == 1 and isinstance(args[0], LargeIntegerArray):
+            return args[0]._to_ring(self)
+        if len(args) == 1:
+            vals = [int(e.value) for e in args[0]]
+            m = np.frombuffer(b"".join(_be(v, self.byte_len) for v in vals), dtype=np.uint8)
+            h = C.c_void_p()
+            nat.check(lib.vmx_rarr_from_bytes(self.group.ctx, len(vals), _ptr(m), C.byref(h)))
+            return PRingElementArray(self, h)
+        size, src = args
+        h = C.c_void_p()
+        if isinstance(src, ByteTreeReader):
+            try:
+                m = src.leaf_matrix(size, self.byte_len)
+            except EIOException as e:
+                raise ArithmFormatException(nat.VMX_EFORMAT, str(e))
+            nat.check(lib.vmx_rarr_from_bytes(self.group.ctx, size, _ptr(m), C.byref(h)))
+        else:
+            nat.check(lib.vmx_rarr_fill(self.group.ctx, size, _be(src.value, self.byte_len), C.byref(h)))
+        return PRingElementArray(self, h)
+
+    unsafeToElementArray = toElementArray
+
+    def __eq__(self, o):
+        return isinstance(o, PField) and o.order == self.order
+
+    def __hash__(self):
+        return hash(self.order)
+
+
+class PFieldElement:
+    def __init__(self, ring: PField, value: int):
+        self.ring = ring
+        self.value = value % ring.order
+
+    def getPRing(self):
+        return self.ring
+
+    def add(self, o):
+        return PFieldElement(self.ring, self.value + o.value)
+
+    def sub(self, o):
+        return PFieldElement(self.ring, self.value - o.value)
+
+    def mul(self, o):
+        return PFieldElement(self.ring, self.value * o.value)
+
+    def neg(self):
+        return PFieldElement(self.ring, -self.value)
+
+    def mulAdd(self, v, b):
+        """this * v + b (hvzk/PoSBasicTW.java:873-878)."""
+        return PFieldElement(self.ring, self.value * v.value + b.value)
+
+    def toLargeInteger(self) -> int:
+        return self.value
+
+    def toByteTree(self) -> ByteTreeBasic:
+        return ByteTreeLeaf(int_to_bytes(self.value, self.ring.byte_len))
+
+    def equals(self, o) -> bool:
+        return isinstance(o, PFieldElement) and o.ring == self.ring and o.value == self.value
+
+    __eq__ = equals
+
+    def __hash__(self):
+        return hash(self.value)
+
+
+class PRingElementArray:
+    """Device-resident array over Z_q."""
+
+    def __init__(self, ring: PField, handle):
+        self.ring = ring
+        self.h = handle
+        self._lib = nat.load()
+
+    # -- bookkeeping
+    def getPRing(self):
+        return self.ring
+
+    def size(self) -> int:
+        return int(self._lib.vmx_rarr_size(self.h))
+
+    def free(self) -> None:
+        if self.h is not None and self.h.value:
+            self._lib.vmx_rarr_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def _new(self, h) -> "PRingElementArray":
+        return PRingElementArray(self.ring, h)
+
+    def _scalar_out(self, fn, *args) -> PFieldElement:
+        buf = np.empty(self.ring.byte_len, dtype=np.uint8)
+        nat.check(fn(*args, _ptr(buf)))
+        return PFieldElement(self.ring, int.from_bytes(buf.tobytes(), "big"))
+
+    # -- algebra
+    def add(self, o):
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_radd(self.h, o.h, C.byref(h)))
+        return self._new(h)
+
+    def neg(self):
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_rneg(self.h, C.byref(h)))
+        return self._new(h)
+
+    def mul(self, o):
+        h = C.c_void_p()
+        if isinstance(o, PFieldElement):
+            zero = self.ring.toElementArray(self.size(), self.ring.getZERO())
+            try:
+                return self.mulAdd(o, zero)
+            finally:
+                zero.free()
+        nat.check(self._lib.vmx_rmul(self.h, o.h, C.byref(h)))
+        return self._new(h)
+
+    def mulAdd(self, scalar: PFieldElement, o: "PRingElementArray"):
+        """this[i] * scalar + o[i] (hvzk/PoSBasicTW.java:874,877)."""
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_rmuladd(self.h, _be(scalar.value, self.ring.byte_len), o.h, C.byref(h)))
+        return self._new(h)
+
+    def innerProduct(self, o) -> PFieldElement:
+        return self._scalar_out(self._lib.vmx_rinner, self.h, o.h)
+
+    def sum(self) -> PFieldElement:
+        return self._scalar_out(self._lib.vmx_rsum, self.h)
+
+    def prod(self) -> PFieldElement:
+        return self._scalar_out(self._lib.vmx_rprod, self.h)
+
+    def prods(self):
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_rprods(self.h, C.byref(h)))
+        return self._new(h)
+
+    def recLin(self, e: "PRingElementArray"):
+        """x[0] = this[0], x[i] = x[i-1]*e[i] + this[i]; returns (x, x[n-1]) (PoSBasicTW.java:583-598)."""
+        h = C.c_void_p()
+        buf = np.empty(self.ring.byte_len, dtype=np.uint8)
+        nat.check(self._lib.vmx_rreclin(self.h, e.h, C.byref(h), _ptr(buf)))
+        return self._new(h), PFieldElement(self.ring, int.from_bytes(buf.tobytes(), "big"))
+
+    # -- data movement
+    def permute(self, pi: Permutation):
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_rpermute(self.h, _ptr(pi.table), C.byref(h)))
+        return self._new(h)
+
+    def shiftPush(self, el: PFieldElement):
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_rshift_push(self.h, _be(el.value, self.ring.byte_len), C.byref(h)))
+        return self._new(h)
+
+    def copyOfRange(self, a: int, b: int):
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_rslice(self.h, a, b, C.byref(h)))
+        return self._new(h)
+
+    def get(self, i: int) -> PFieldElement:
+        return self._scalar_out(lambda hh, ii, out: self._lib.vmx_rget(hh, ii, out), self.h, i)
+
+    def equals(self, o) -> bool:
+        eq = C.c_int()
+        nat.check(self._lib.vmx_requals(self.h, o.h, C.byref(eq)))
+        return bool(eq.value)
+
+    def bitLength(self) -> int:
+        b = C.c_uint()
+        nat.check(self._lib.vmx_rarr_bitlen(self.h, C.byref(b)))
+        return int(b.value)
+
+    # -- I/O
+    def to_matrix(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        n, w = self.size(), self.ring.byte_len
+        m = out if out is not None else np.empty((n, w), dtype=np.uint8)
+        nat.check(self._lib.vmx_rarr_to_bytes(self.h, _ptr(m)))
+        return m
+
+    def toByteTree(self) -> ByteTreeBasic:
+        return ByteTreeLeafArray(self.to_matrix())
+
+    def elements(self) -> List[PFieldElement]:
+        return [PFieldElement(self.ring, int.from_bytes(r.tobytes(), "big")) for r in self.to_matrix()]
+
+    @staticmethod
+    def free_(a) -> None:
+        if a is not None:
+            a.free()
+
+
+class LargeIntegerArray:
+    """Non-negative integers of bounded bit length, device-resident (already < q here)."""
+
+    def __init__(self, field: PField, handle):
+        self.field = field
+        self.h = handle
+
+    @staticmethod
+    def random(size: int, bitLength: int, randomSource, field: PField) -> "LargeIntegerArray":
+        """LargeIntegerArray.random(size, bitLength, randomSource) (PoSBasicTW.java:472-474,535-536).
+
+        With a PRGHeuristic(SHA-256) source the expansion runs on the device (counter mode);
+        any other source hands its bytes over."""
+        from .crypto import PRGHeuristic
+        lib = nat.load()
+        h = C.c_void_p()
+        width = (bitLength + 7) // 8
+        if (isinstance(randomSource, PRGHeuristic) and randomSource.hf.name == "SHA-256"
+                and randomSource.counter == 0 and not randomSource.buf and bitLength < field.order.bit_length()):
+            nat.check(lib.vmx_rarr_prg_sha256(field.group.ctx, randomSource.seed, len(randomSource.seed), size,
+                                              bitLength, C.byref(h)))
+            # keep the host-side PRG state consistent with the bytes consumed on the device
+            full, rem = divmod(size * width, 32)
+            randomSource.counter = full
+            randomSource.buf = bytearray()
+            if rem:
+                randomSource.getBytes(rem)
+            return LargeIntegerArray(field, h)
+        raw = np.frombuffer(randomSource.getBytes(size * width), dtype=np.uint8)
+        nat.check(lib.vmx_rarr_from_raw(field.group.ctx, size, _ptr(raw), width, bitLength, C.byref(h)))
+        return LargeIntegerArray(field, h)
+
+    def _to_ring(self, field: PField) -> PRingElementArray:
+        h, self.h = self.h, None
+        return PRingElementArray(field, h)
+
+    def free(self) -> None:
+        if self.h is not None and self.h.value:
+            nat.load().vmx_rarr_free(self.h)
+        self.h = None
+
+
+# ====================================================================== groups
+class PGroup:
+    pass
+
+
+class ModPGroup(PGroup):
+    """Subgroup of order q of Z_p^* with generator g (com.verificatum.arithm.ModPGroup)."""
+
+    def __init__(self, p: int, q: int, g: int, device: int = 0):
+        lib = nat.load()
+        self.p, self.q, self.g = p, q, g
+        nbytes = (p.bit_length() + 7) // 8
+        ctx = C.c_void_p()
+        nat.check(lib.vmx_ctx_create_modp(_be(p, nbytes), _be(q, nbytes), _be(g, nbytes), nbytes, device,
+                                          C.byref(ctx)))
+        self.ctx = ctx
+        self._lib = lib
+        self.elem_bytes = int(lib.vmx_ctx_elem_bytes(ctx))
+        self.ring_bytes = int(lib.vmx_ctx_ring_bytes(ctx))
+        self.pRing = PField(self)
+
+    def __del__(self):
+        # arrays keep a reference to their group, so the context outlives every handle
+        try:
+            if self.ctx is not None:
+                self._lib.vmx_ctx_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    # -- structure
+    def getPRing(self) -> PField:
+        return self.pRing
+
+    def getg(self) -> "PGroupElement":
+        return PGroupElement(self, self.g)
+
+    def getONE(self) -> "PGroupElement":
+        return PGroupElement(self, 1)
+
+    def getElementOrder(self) -> int:
+        return self.q
+
+    def basic(self) -> List["ModPGroup"]:
+        return [self]
+
+    def launch_count(self) -> int:
+        return int(self._lib.vmx_ctx_launch_count(self.ctx))
+
+    def modmul_count(self) -> int:
+        return int(self._lib.vmx_ctx_modmul_count(self.ctx))
+
+    def sync(self) -> None:
+        nat.check(self._lib.vmx_ctx_sync(self.ctx))
+
+    def precomputeFixedBase(self, el: "PGroupElement", size_hint: int) -> None:
+        nat.check(self._lib.vmx_fixed_precompute(self.ctx, _be(el.value, self.elem_bytes), size_hint))
+
+    # -- elements
+    def toElement(self, x) -> "PGroupElement":
+        if isinstance(x, ByteTreeReader):
+            if not x.isLeaf() or x.getRemaining() != self.elem_bytes:
+                raise ArithmFormatException(nat.VMX_EFORMAT, "group element of wrong length")
+            v = int.from_bytes(x.read(), "big", signed=True)
+        else:
+            v = int(x)
+        if not 0 < v < self.p:
+            raise ArithmFormatException(nat.VMX_EFORMAT, "group element out of range")
+        # membership through the engine (one-element array, Euler criterion on the device)
+        m = np.frombuffer(_be(v, self.elem_bytes), dtype=np.uint8)
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_garr_from_bytes(self.ctx, 1, _ptr(m), 1, C.byref(h)))
+        self._lib.vmx_garr_free(h)
+        return PGroupElement(self, v)
+
+    # -- arrays
+    def toElementArray(self, *args, check_membership: bool = True) -> "PGroupElementArray":
+        """(size, ByteTreeReader) | (size, PGroupElement) | (list of PGroupElement)."""
+        lib = self._lib
+        h = C.c_void_p()
+        if len(args) == 1:
+            vals = [e.value for e in args[0]]
+            m = np.frombuffer(b"".join(_be(v, self.elem_bytes) for v in vals), dtype=np.uint8)
+            nat.check(lib.vmx_garr_from_bytes(self.ctx, len(vals), _ptr(m), 0, C.byref(h)))
+            return PGroupElementArray(self, h)
+        size, src = args
+        if isinstance(src, ByteTreeReader):
+            try:
+                m = src.leaf_matrix(size, self.elem_bytes)
+            except EIOException as e:
+                raise ArithmFormatException(nat.VMX_EFORMAT, str(e))
+            nat.check(lib.vmx_garr_from_bytes(self.ctx, size, _ptr(m), 1 if check_membership else 0, C.byref(h)))
+        elif isinstance(src, np.ndarray):
+            nat.check(lib.vmx_garr_from_bytes(self.ctx, size, _ptr(src), 1 if check_membership else 0, C.byref(h)))
+        else:
+            nat.check(lib.vmx_garr_fill(self.ctx, size, _be(src.value, self.elem_bytes), C.byref(h)))
+        return PGroupElementArray(self, h)
+
+    def unsafeToElementArray(self, *args) -> "PGroupElementArray":
+        return self.toElementArray(*args, check_membership=False)
+
+    def randomElementArray(self, size: int, randomSource, statDist: int) -> "PGroupElementArray":
+        """t_i = next ceil((|p|+statDist)/8) bytes mod 2^(|p|+statDist); h_i = t_i^((p-1)/q) mod p
+        (distr/IndependentGeneratorsRO.java:129).  The reduction mod p and the cofactor power run
+        on the device."""
+        bits = self.p.bit_length() + statDist
+        width = (bits + 7) // 8
+        raw = np.frombuffer(randomSource.getBytes(size * width), dtype=np.uint8)
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_garr_from_raw(self.ctx, size, _ptr(raw), width, bits, C.byref(h)))
+        return PGroupElementArray(self, h)
+
+    def expProd(self, bases: Sequence["PGroupElementArray"], integers: Sequence[int], bitLength: int):
+        """Element-wise prod_j bases[j][i]^integers[j] (elgamal/DistrElGamalSessionBasic.java:502)."""
+        t = len(bases)
+        arr = (C.c_void_p * t)(*[b.h for b in bases])
+        ints = (C.c_int64 * t)(*[int(x) for x in integers])
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_expprod_cols(arr, t, ints, C.byref(h)))
+        return PGroupElementArray(self, h)
+
+    def __eq__(self, o):
+        return isinstance(o, ModPGroup) and (o.p, o.q, o.g) == (self.p, self.q, self.g)
+
+    def __hash__(self):
+        return hash((self.p, self.g))
+
+
+class PGroupElement:
+    """A single group element: host value; exponentiations go through the engine."""
+
+    def __init__(self, group: ModPGroup, value: int):
+        self.group = group
+        self.value = value
+
+    def getPGroup(self):
+        return self.group
+
+    def _be(self) -> bytes:
+        return _be(self.value, self.group.elem_bytes)
+
+    def _single(self, h) -> "PGroupElement":
+        lib = self.group._lib
+        buf = np.empty(self.group.elem_bytes, dtype=np.uint8)
+        try:
+            nat.check(lib.vmx_get(h, 0, _ptr(buf)))
+        finally:
+            lib.vmx_garr_free(h)
+        return PGroupElement(self.group, int.from_bytes(buf.tobytes(), "big"))
+
+    def _as_array(self):
+        h = C.c_void_p()
+        nat.check(self.group._lib.vmx_garr_fill(self.group.ctx, 1, self._be(), C.byref(h)))
+        return h
+
+    def exp(self, e):
+        """exp(PRingElementArray) -> fixed-base array exponentiation (ShufflerElGamalSession.java:407;
+        PoSBasicTW.java:447,606,608,644,646,1030); exp(PRingElement) -> single element."""
+        lib = self.group._lib
+        if isinstance(e, PRingElementArray):
+            h = C.c_void_p()
+            nat.check(lib.vmx_exp_fixed(self.group.ctx, self._be(), e.h, C.byref(h)))
+            return PGroupElementArray(self.group, h)
+        if isinstance(e, int):
+            e = self.group.pRing.toElement(e)
+        a = self._as_array()
+        try:
+            h = C.c_void_p()
+            nat.check(lib.vmx_exp_scalar(a, _be(e.value, self.group.ring_bytes), C.byref(h)))
+        finally:
+            lib.vmx_garr_free(a)
+        return self._single(h)
+
+    def mul(self, o: "PGroupElement") -> "PGroupElement":
+        lib = self.group._lib
+        a, b = self._as_array(), o._as_array()
+        try:
+            h = C.c_void_p()
+            nat.check(lib.vmx_mul(a, b, C.byref(h)))
+        finally:
+            lib.vmx_garr_free(a)
+            lib.vmx_garr_free(b)
+        return self._single(h)
+
+    def inv(self) -> "PGroupElement":
+        lib = self.group._lib
+        a = self._as_array()
+        try:
+            h = C.c_void_p()
+            nat.check(lib.vmx_inv(a, C.byref(h)))
+        finally:
+            lib.vmx_garr_free(a)
+        return self._single(h)
+
+    def div(self, o: "PGroupElement") -> "PGroupElement":
+        return self.mul(o.inv())
+
+    def expMul(self, e: PFieldElement, b: "PGroupElement") -> "PGroupElement":
+        """this^e * b (PoSBasicTW.java:1021,1048,1055,1063)."""
+        return self.exp(e).mul(b)
+
+    def equals(self, o) -> bool:
+        return isinstance(o, PGroupElement) and o.group == self.group and o.value == self.value
+
+    __eq__ = equals
+
+    def __hash__(self):
+        return hash(self.value)
+
+    def toByteTree(self) -> ByteTreeBasic:
+        return ByteTreeLeaf(int_to_bytes(self.value, self.group.elem_bytes))
+
+
+class PGroupElementArray:
+    """Device-resident array of ModPGroup elements (Montgomery form, limb-major)."""
+
+    def __init__(self, group: ModPGroup, handle):
+        self.group = group
+        self.h = handle
+        self._lib = group._lib
+
+    def getPGroup(self):
+        return self.group
+
+    def size(self) -> int:
+        return int(self._lib.vmx_garr_size(self.h))
+
+    def free(self) -> None:
+        if self.h is not None and self.h.value:
+            self._lib.vmx_garr_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def _new(self, h):
+        return PGroupElementArray(self.group, h)
+
+    def basic(self) -> List["PGroupElementArray"]:
+        return [self]
+
+    # -- algebra
+    def mul(self, o: "PGroupElementArray"):
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_mul(self.h, o.h, C.byref(h)))
+        return self._new(h)
+
+    def inv(self):
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_inv(self.h, C.byref(h)))
+        return self._new(h)
+
+    def exp(self, e):
+        """exp(PRingElementArray): per-element exponents (PoSBasicTW.java:1032);
+        exp(PRingElement): one exponent for all (PoSBasicTW.java:1028; DistrElGamalSession.java:384)."""
+        h = C.c_void_p()
+        if isinstance(e, PRingElementArray):
+            nat.check(self._lib.vmx_exp_var(self.h, e.h, C.byref(h)))
+        else:
+            nat.check(self._lib.vmx_exp_scalar(self.h, _be(e.value, self.group.ring_bytes), C.byref(h)))
+        return self._new(h)
+
+    def expProd(self, e: PRingElementArray) -> PGroupElement:
+        """prod_i this[i]^e[i] (PoSBasicTW.java:408-409,481,690,1021,1063)."""
+        return expProdMany([self], e)[0]
+
+    def prod(self) -> PGroupElement:
+        buf = np.empty(self.group.elem_bytes, dtype=np.uint8)
+        nat.check(self._lib.vmx_prod(self.h, _ptr(buf)))
+        return PGroupElement(self.group, int.from_bytes(buf.tobytes(), "big"))
+
+    # -- data movement
+    def permute(self, pi: Permutation):
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_permute(self.h, _ptr(pi.table), C.byref(h)))
+        return self._new(h)
+
+    def shiftPush(self, el: PGroupElement):
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_shift_push(self.h, el._be(), C.byref(h)))
+        return self._new(h)
+
+    def extract(self, keep: Sequence[bool]):
+        k = np.ascontiguousarray(np.asarray(keep, dtype=np.uint8))
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_extract(self.h, k.ctypes.data_as(C.c_char_p), C.byref(h)))
+        return self._new(h)
+
+    def copyOfRange(self, a: int, b: int):
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_slice(self.h, a, b, C.byref(h)))
+        return self._new(h)
+
+    def get(self, i: int) -> PGroupElement:
+        buf = np.empty(self.group.elem_bytes, dtype=np.uint8)
+        nat.check(self._lib.vmx_get(self.h, i, _ptr(buf)))
+        return PGroupElement(self.group, int.from_bytes(buf.tobytes(), "big"))
+
+    def equals(self, o) -> bool:
+        eq = C.c_int()
+        nat.check(self._lib.vmx_equals(self.h, o.h, C.byref(eq)))
+        return bool(eq.value)
+
+    # -- I/O
+    def to_matrix(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        n, w = self.size(), self.group.elem_bytes
+        m = out if out is not None else np.empty((n, w), dtype=np.uint8)
+        nat.check(self._lib.vmx_garr_to_bytes(self.h, _ptr(m)))
+        return m
+
+    def toByteTree(self) -> ByteTreeBasic:
+        return ByteTreeLeafArray(self.to_matrix())
+
+    def elements(self) -> List[PGroupElement]:
+        return [PGroupElement(self.group, int.from_bytes(r.tobytes(), "big")) for r in self.to_matrix()]
+
+    @staticmethod
+    def free_(a) -> None:
+        if a is not None:
+            a.free()
+
+
+def expProdMany(arrays: Sequence[PGroupElementArray], e: PRingElementArray) -> List[PGroupElement]:
+    """expProd of several arrays that share one exponent array: the engine sorts the exponent
+    digits once (the components of a product-group array, PoSBasicTW.java:409,690,1063)."""
+    group = arrays[0].group
+    k = len(arrays)
+    arr = (C.c_void_p * k)(*[a.h for a in arrays])
+    buf = np.empty((k, group.elem_bytes), dtype=np.uint8)
+    nat.check(group._lib.vmx_expprod(arr, k, e.h, _ptr(buf)))
+    return [PGroupElement(group, int.from_bytes(buf[i].tobytes(), "big")) for i in range(k)]
+
+
+# ====================================================================== product groups / rings
+class PPRing(PRing):
+    """Product ring (exponents of wide ciphertexts): `width` copies of Z_q."""
+
+    def __init__(self, ring: PField, width: int):
+        self.ring = ring
+        self.width = width
+
+    def getPField(self):
+        return self.ring
+
+    def randomElement(self, randomSource, statDist):
+        return PPRingElement(self, [self.ring.randomElement(randomSource, statDist) for _ in range(self.width)])
+
+    def randomElementArray(self, size, randomSource, statDist):
+        return PPRingElementArray(self, [self.ring.randomElementArray(size, randomSource, statDist)
+                                         for _ in range(self.width)])
+
+    def toElement(self, btr: ByteTreeReader):
+        if btr.isLeaf() or btr.getRemaining() != self.width:
+            raise ArithmFormatException(nat.VMX_EFORMAT, "product ring element of wrong arity")
+        return PPRingElement(self, [self.ring.toElement(btr.getNextChild()) for _ in range(self.width)])
+
+    def __eq__(self, o):
+        return isinstance(o, PPRing) and o.ring == self.ring and o.width == self.width
+
+    def __hash__(self):
+        return hash((self.ring, self.width))
+
+
+class PPRingElement:
+    def __init__(self, ring: PPRing, comps):
+        self.ring = ring
+        self.comps = list(comps)
+
+    def getPRing(self):
+        return self.ring
+
+    def neg(self):
+        return PPRingElement(self.ring, [c.neg() for c in self.comps])
+
+    def add(self, o):
+        return PPRingElement(self.ring, [a.add(b) for a, b in zip(self.comps, o.comps)])
+
+    def mulAdd(self, v, b):
+        return PPRingElement(self.ring, [a.mulAdd(v, bb) for a, bb in zip(self.comps, b.comps)])
+
+    def toByteTree(self):
+        return ByteTreeContainer(*[c.toByteTree() for c in self.comps])
+
+    def equals(self, o):
+        return isinstance(o, PPRingElement) and all(a.equals(b) for a, b in zip(self.comps, o.comps))
+
+
+class PPRingElementArray:
+    def __init__(self, ring: PPRing, comps):
+        self.ring = ring
+        self.comps = list(comps)
+
+    def getPRing(self):
+        return self.ring
+
+    def size(self):
+        return self.comps[0].size()
+
+    def innerProduct(self, o):
+        """Component-wise inner product with a Z_q array (PoSBasicTW.java:863)."""
+        if isinstance(o, PPRingElementArray):
+            return PPRingElement(self.ring, [a.innerProduct(b) for a, b in zip(self.comps, o.comps)])
+        return PPRingElement(self.ring, [a.innerProduct(o) for a in self.comps])
+
+    def free(self):
+        for c in self.comps:
+            c.free()
+
+    def toByteTree(self):
+        return ByteTreeContainer(*[c.toByteTree() for c in self.comps])
+
+
+class PPGroup(PGroup):
+    """Product group: PPGroup(G, k) = G^k, or a product of given factors."""
+
+    def __init__(self, factors, width: Optional[int] = None):
+        if width is not None:
+            factors = [factors] * width
+        self.factors = list(factors)
+
+    def project(self, i: int) -> PGroup:
+        return self.factors[i]
+
+    def getWidth(self) -> int:
+        return len(self.factors)
+
+    def getPRing(self):
+        f = self.factors[0]
+        r = f.getPRing()
+        # exponents act per factor when the factors are themselves products of the same shape
+        return r if all(x == f for x in self.factors) and not isinstance(f, PPGroup) else PPRingOf(self)
+
+    def product(self, *els):
+        if len(els) == 1 and not isinstance(els[0], (PGroupElementArray, PPGroupElementArray)):
+            els = [els[0]] * len(self.factors)
+        if isinstance(els[0], (PGroupElementArray, PPGroupElementArray)):
+            return PPGroupElementArray(self, list(els))
+        return PPGroupElement(self, list(els))
+
+    def getONE(self):
+        return PPGroupElement(self, [f.getONE() for f in self.factors])
+
+    def getg(self):
+        return PPGroupElement(self, [f.getg() for f in self.factors])
+
+    def basic(self) -> List[ModPGroup]:
+        out = []
+        for f in self.factors:
+            out += f.basic()
+        return out
+
+    def toElement(self, btr: ByteTreeReader):
+        if btr.isLeaf() or btr.getRemaining() != len(self.factors):
+            raise ArithmFormatException(nat.VMX_EFORMAT, "product element of wrong arity")
+        return PPGroupElement(self, [f.toElement(btr.getNextChild()) for f in self.factors])
+
+    def toElementArray(self, size: int, src, check_membership: bool = True):
+        if isinstance(src, ByteTreeReader):
+            if src.isLeaf() or src.getRemaining() != len(self.factors):
+                raise ArithmFormatException(nat.VMX_EFORMAT, "product array of wrong arity")
+            comps = []
+            try:
+                for f in self.factors:
+                    comps.append(f.toElementArray(size, src.getNextChild(), check_membership=check_membership)
+                                 if isinstance(f, ModPGroup) else f.toElementArray(size, src.getNextChild(),
+                                                                                    check_membership))
+            except Exception:
+                for c in comps:
+                    c.free()
+                raise
+            return PPGroupElementArray(self, comps)
+        return PPGroupElementArray(self, [f.toElementArray(size, c) for f, c in zip(self.factors, src.comps)])
+
+    def __eq__(self, o):
+        return isinstance(o, PPGroup) and o.factors == self.factors
+
+    def __hash__(self):
+        return hash(tuple(self.factors))
+
+
+def PPRingOf(group: PPGroup) -> PRing:
+    f = group.factors[0]
+    if isinstance(f, PPGroup):
+        return PPRing(f.factors[0].getPRing(), len(f.factors))
+    return f.getPRing()
+
+
+def _exp_dispatch(comp, e):
+    return comp.exp(e)
+
+
+class PPGroupElement:
+    def __init__(self, group: PPGroup, comps):
+        self.group = group
+        self.comps = list(comps)
+
+    def getPGroup(self):
+        return self.group
+
+    def project(self, i: int):
+        return self.comps[i]
+
+    def _split(self, e):
+        """Exponent per component: a product-ring exponent of matching arity acts component-wise,
+        anything else is applied to every component."""
+        if isinstance(e, (PPRingElement, PPRingElementArray)) and len(e.comps) == len(self.comps) \
+                and not isinstance(self.comps[0], PPGroupElement):
+            return e.comps
+        if isinstance(e, (PPRingElement, PPRingElementArray)) and isinstance(self.comps[0], PPGroupElement) \
+                and len(e.comps) != len(self.comps):
+            return [e] * len(self.comps)
+        return [e] * len(self.comps)
+
+    def exp(self, e):
+        parts = [c.exp(x) for c, x in zip(self.comps, self._split(e))]
+        if isinstance(parts[0], (PGroupElementArray, PPGroupElementArray)):
+            return PPGroupElementArray(self.group, parts)
+        return PPGroupElement(self.group, parts)
+
+    def mul(self, o):
+        return PPGroupElement(self.group, [a.mul(b) for a, b in zip(self.comps, o.comps)])
+
+    def inv(self):
+        return PPGroupElement(self.group, [a.inv() for a in self.comps])
+
+    def div(self, o):
+        return self.mul(o.inv())
+
+    def expMul(self, e, b):
+        return self.exp(e).mul(b)
+
+    def equals(self, o):
+        return isinstance(o, PPGroupElement) and len(o.comps) == len(self.comps) and \
+            all(a.equals(b) for a, b in zip(self.comps, o.comps))
+
+    __eq__ = equals
+
+    def __hash__(self):
+        return hash(tuple(self.comps))
+
+    def toByteTree(self):
+        return ByteTreeContainer(*[c.toByteTree() for c in self.comps])
+
+
+class PPGroupElementArray:
+    """Array over a product group, stored column-wise: one device array per factor
+    (elgamal/ProtocolElGamalInterfaceRaw.java:53-56)."""
+
+    def __init__(self, group: PPGroup, comps):
+        self.group = group
+        self.comps = list(comps)
+
+    def getPGroup(self):
+        return self.group
+
+    def size(self):
+        return self.comps[0].size()
+
+    def project(self, i: int):
+        return self.comps[i]
+
+    def basic(self) -> List[PGroupElementArray]:
+        out = []
+        for c in self.comps:
+            out += c.basic()
+        return out
+
+    def free(self):
+        for c in self.comps:
+            c.free()
+
+    def _map(self, fn, *others):
+        return PPGroupElementArray(self.group, [fn(c, *[o.comps[i] for o in others])
+                                                for i, c in enumerate(self.comps)])
+
+    def mul(self, o):
+        return self._map(lambda a, b: a.mul(b), o)
+
+    def inv(self):
+        return self._map(lambda a: a.inv())
+
+    def exp(self, e):
+        if isinstance(e, (PPRingElement, PPRingElementArray)) and len(e.comps) == len(self.comps) \
+                and not isinstance(self.comps[0], PPGroupElementArray):
+            return PPGroupElementArray(self.group, [c.exp(x) for c, x in zip(self.comps, e.comps)])
+        return self._map(lambda a: a.exp(e))
+
+    def expProd(self, e) -> PPGroupElement:
+        flat = self.basic()
+        res = expProdMany(flat, e)
+        it = iter(res)
+
+        def rebuild(arr):
+            if isinstance(arr, PPGroupElementArray):
+                return PPGroupElement(arr.group, [rebuild(c) for c in arr.comps])
+            return next(it)
+        return rebuild(self)
+
+    def prod(self):
+        return PPGroupElement(self.group, [c.prod() for c in self.comps])
+
+    def permute(self, pi):
+        return self._map(lambda a: a.permute(pi))
+
+    def shiftPush(self, el):
+        return PPGroupElementArray(self.group, [c.shiftPush(x) for c, x in zip(self.comps, el.comps)])
+
+    def extract(self, keep):
+        return self._map(lambda a: a.extract(keep))
+
+    def copyOfRange(self, a, b):
+        return self._map(lambda c: c.copyOfRange(a, b))
+
+    def get(self, i):
+        return PPGroupElement(self.group, [c.get(i) for c in self.comps])
+
+    def equals(self, o):
+        return all(a.equals(b) for a, b in zip(self.comps, o.comps))
+
+    def toByteTree(self):
+        return ByteTreeContainer(*[c.toByteTree() for c in self.comps])

@@ -1,0 +1,112 @@
+"""Host-side hashing: PRG, random oracle, random sources.
+
+Mirror of `com.verificatum.crypto.{PRGHeuristic, RandomOracle, HashfunctionHeuristic,
+RandomSource}` (verificatum-vcr 3.1.0) as used by hvzk/ChallengerRO.java:96-116,
+hvzk/PoSBasicTW.java:533-538 and distr/IndependentGeneratorsRO.java:110-130.  Fiat-Shamir
+hashing is a single SHA-256 stream per challenge and stays on the host (SURVEY.md §8a row
+a18); array-sized PRG expansions run on the device (`vmx_rarr_prg_sha256`).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import struct
+
+
+class HashfunctionHeuristic:
+    def __init__(self, name: str = "SHA-256"):
+        self.name = name
+        self._py = name.lower().replace("-", "")
+        self.output_bits = hashlib.new(self._py).digest_size * 8
+
+    def getDigest(self):
+        return hashlib.new(self._py)
+
+    def hash(self, *parts: bytes) -> bytes:
+        h = self.getDigest()
+        for p in parts:
+            h.update(p)
+        return h.digest()
+
+
+class RandomSource:
+    def getBytes(self, n: int) -> bytes:
+        raise NotImplementedError
+
+
+class RandomDevice(RandomSource):
+    """/dev/urandom (com.verificatum.crypto.RandomDevice)."""
+
+    def getBytes(self, n: int) -> bytes:
+        return os.urandom(n)
+
+
+class PRGHeuristic(RandomSource):
+    """PRG(H): H(seed || be32(0)) || H(seed || be32(1)) || ..."""
+
+    def __init__(self, hashfunction: HashfunctionHeuristic | None = None):
+        self.hf = hashfunction or HashfunctionHeuristic("SHA-256")
+        self.seed = None
+        self.counter = 0
+        self.buf = bytearray()
+
+    def minNoSeedBytes(self) -> int:
+        return self.hf.output_bits // 8
+
+    def setSeed(self, seed: bytes) -> None:
+        if len(seed) < self.minNoSeedBytes():
+            raise ValueError("seed too short")
+        self.seed = bytes(seed)
+        self.counter = 0
+        self.buf = bytearray()
+
+    def getBytes(self, n: int) -> bytes:
+        blocks = []
+        have = len(self.buf)
+        while have < n:
+            blocks.append(self.hf.hash(self.seed, struct.pack(">I", self.counter)))
+            self.counter += 1
+            have += len(blocks[-1])
+        if blocks:
+            self.buf += b"".join(blocks)
+        out = bytes(self.buf[:n])
+        del self.buf[:n]
+        return out
+
+
+class RandomOracleDigest:
+    def __init__(self, hf: HashfunctionHeuristic, out_bits: int):
+        self.hf = hf
+        self.out_bits = out_bits
+        self.h = hf.getDigest()
+        self.h.update(struct.pack(">I", out_bits))
+        self.nbytes = 4
+
+    def update(self, data) -> None:
+        self.h.update(data)
+        self.nbytes += len(data) if not hasattr(data, "nbytes") else data.nbytes
+
+    def digest(self) -> bytes:
+        prg = PRGHeuristic(self.hf)
+        prg.setSeed(self.h.digest())
+        out = bytearray(prg.getBytes((self.out_bits + 7) // 8))
+        extra = (8 - self.out_bits % 8) % 8
+        if extra:
+            out[0] &= 0xFF >> extra
+        return bytes(out)
+
+
+class RandomOracle:
+    """RO(H, n_out)(d) = leading n_out bits of PRG_H(H(be32(n_out) || d))."""
+
+    def __init__(self, hashfunction: HashfunctionHeuristic, out_bits: int):
+        self.hf = hashfunction
+        self.out_bits = out_bits
+
+    def getDigest(self) -> RandomOracleDigest:
+        return RandomOracleDigest(self.hf, self.out_bits)
+
+    def hash(self, data: bytes) -> bytes:
+        d = self.getDigest()
+        d.update(data)
+        return d.digest()

@@ -16,9 +16,21 @@ template <int N> struct Occ { static constexpr int kMinBlocks = (N > 64) ? 2 : 3
 enum { kErrRange = 1, kErrZero = 2, kErrPad = 4, kErrMember = 8 };
 
 // ------------------------------------------------------------------ byte codec
-// raw: n elements of `eb` big-endian bytes (eb >= 4N; leading eb-4N bytes must be zero).
+// raw: n elements of `eb` big-endian bytes each (the fixed-width two's-complement leaf payload
+// of the byte tree; values are non-negative).  Bytes beyond 4N must be zero.
 // mode 0: group element -> range check 0 < x < mod, to Montgomery form (x * R).
 // mode 1: ring element  -> range check 0 <= x < mod, stays canonical.
+template <int N>
+VMX_DEV uint32_t be_word(const uint8_t* src, int eb, int j) {  // little-endian word j of a big-endian string
+  uint32_t v = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int b = 4 * j + k;
+    if (b < eb) v |= (uint32_t)src[eb - 1 - b] << (8 * k);
+  }
+  return v;
+}
+
 template <int N>
 VMX_KERNEL(N) k_from_bytes(const uint8_t* __restrict__ raw, size_t n, int eb, int mode, uint32_t* __restrict__ out,
                            size_t cap, const uint32_t* __restrict__ r2, int* __restrict__ err,
@@ -28,14 +40,9 @@ VMX_KERNEL(N) k_from_bytes(const uint8_t* __restrict__ raw, size_t n, int eb, in
   const uint8_t* src = raw + i * (size_t)eb;
   uint32_t a[N];
   int bad = 0;
-  const int pad = eb - 4 * N;
-  for (int k = 0; k < pad; k++) if (src[k] != 0) bad |= kErrPad;
-  src += pad;
+  for (int k = 0; k < eb - 4 * N; k++) if (src[k] != 0) bad |= kErrPad;
 #pragma unroll
-  for (int j = 0; j < N; j++) {
-    const uint8_t* q = src + 4 * (N - 1 - j);
-    a[j] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
-  }
+  for (int j = 0; j < N; j++) a[j] = be_word<N>(src, eb, j);
   // x < mod ?
   uint32_t d, brw;
   sub_cc(d, a[0], M.n[0]);
@@ -64,13 +71,14 @@ VMX_KERNEL(N) k_to_bytes(const uint32_t* __restrict__ in, size_t cap, size_t n, 
   load_elem<N>(a, in, cap, i);
   if (mode == 0) mont_mul<N>(a, OneLoader{}, M);
   uint8_t* dst = raw + i * (size_t)eb;
-  const int pad = eb - 4 * N;
-  for (int k = 0; k < pad; k++) dst[k] = 0;
-  dst += pad;
+  for (int k = 0; k < eb - 4 * N; k++) dst[k] = 0;
 #pragma unroll
   for (int j = 0; j < N; j++) {
-    uint8_t* q = dst + 4 * (N - 1 - j);
-    q[0] = (uint8_t)(a[j] >> 24); q[1] = (uint8_t)(a[j] >> 16); q[2] = (uint8_t)(a[j] >> 8); q[3] = (uint8_t)a[j];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int b = 4 * j + k;
+      if (b < eb) dst[eb - 1 - b] = (uint8_t)(a[j] >> (8 * k));
+    }
   }
 }
 
@@ -198,7 +206,7 @@ VMX_KERNEL(N) k_combine_parts(const uint32_t* __restrict__ in, size_t icap, size
 template <int N>
 VMX_KERNEL(N) k_sqr_chain(const uint32_t* __restrict__ base, size_t bcap, size_t bidx, uint32_t* __restrict__ Q,
                           size_t qcap, int len, const __grid_constant__ MontParams<N> M) {
-  extern __shared__ uint2 smem[];
+  VMX_DYN_SMEM(uint2, smem);
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   uint32_t a[N];
   load_elem<N>(a, base, bcap, bidx);
@@ -250,7 +258,7 @@ VMX_KERNEL(N) k_exp_var(const uint32_t* __restrict__ a_, size_t acap, const uint
                         int escalar, int ebits, int w, size_t n, uint32_t* __restrict__ tab, size_t tabcap,
                         const uint32_t* __restrict__ one, uint32_t* __restrict__ out, size_t ocap,
                         const __grid_constant__ MontParams<N> M) {
-  extern __shared__ uint2 smem[];
+  VMX_DYN_SMEM(uint2, smem);
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint2* sc = smem + threadIdx.x;
@@ -282,13 +290,14 @@ VMX_KERNEL(N) k_exp_var(const uint32_t* __restrict__ a_, size_t acap, const uint
 
 // ------------------------------------------------------------------ data movement (uint4 granularity)
 // out[dst(i)] = in[src(i)] for plane-wise copies; one thread per (plane, element).
+// bcast != 0: every destination receives source element `bidx` (fill).
 __global__ void k_gather(const uint4* __restrict__ in, size_t icap, uint4* __restrict__ out, size_t ocap, size_t n,
                          int planes, const uint32_t* __restrict__ src_idx, const uint32_t* __restrict__ dst_idx,
-                         long long src_off, long long dst_off) {
+                         long long src_off, long long dst_off, int bcast, size_t bidx) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * (size_t)planes) return;
   const size_t i = t % n, g = t / n;
-  const size_t s = src_idx ? src_idx[i] : (size_t)((long long)i + src_off);
+  const size_t s = bcast ? bidx : (src_idx ? src_idx[i] : (size_t)((long long)i + src_off));
   const size_t d = dst_idx ? dst_idx[i] : (size_t)((long long)i + dst_off);
   out[g * ocap + d] = in[g * icap + s];
 }
@@ -314,8 +323,24 @@ __global__ void k_bitlen(const uint32_t* __restrict__ d, size_t cap, size_t n, u
       if (v) { b = 32u * j + (32u - __clz(v)); break; }
     }
   }
+#ifndef VMX_HOST_EMUL
   b = __reduce_max_sync(0xffffffffu, b);
   if ((threadIdx.x & 31) == 0 && b) atomicMax(bits, b);
+#else
+  if (b) atomicMax(bits, b);
+#endif
+}
+
+// *diff |= 1 if any of the n elements differs from element `cidx` of c_ (e.g. the Montgomery one)
+template <int N>
+__global__ void k_differs_from_const(const uint32_t* __restrict__ a_, size_t acap, size_t n,
+                                     const uint32_t* __restrict__ c_, size_t ccap, size_t cidx, int* __restrict__ diff) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x = 0;
+  for (int j = 0; j < N; j++)
+    x |= a_[((size_t)(j >> 2) * acap + i) * 4 + (j & 3)] ^ c_[((size_t)(j >> 2) * ccap + cidx) * 4 + (j & 3)];
+  if (x) atomicOr(diff, 1);
 }
 
 }  // namespace vmx

@@ -17,6 +17,7 @@
 // Algorithmic unit: 1 modmul = 2N^2+N word MACs; this kernel executes exactly
 // 2N^2 IMAD.WIDE + N mul.lo for it.
 #pragma once
+#include "cuda_compat.cuh"
 #include "ptx_arith.cuh"
 
 namespace vmx {
@@ -130,10 +131,14 @@ VMX_DEV void mont_mul(uint32_t (&a)[N], Loader ld2, const MontParams<N>& M) {
   uint32_t t[N + 2];
 #pragma unroll
   for (int i = 0; i < N + 2; i++) t[i] = 0;
+  // the operand words of trip i+1 are requested before trip i is computed (the loads are
+  // gathers from L2/HBM tables in the exponentiation kernels; one trip hides their latency)
+  Word2 b = ld2(0);
 #pragma unroll 1
   for (int i = 0; i < N; i += 2) {
-    const Word2 b = ld2(i);
+    const Word2 nb = ld2(i + 2 < N ? i + 2 : i);
     mont_rowpair<N>(t, a, b.x, b.y, M);
+    b = nb;
   }
   mont_final_sub<N>(a, t, M);
 }

@@ -2,12 +2,13 @@
 // Three small kernels (block scan, scan of block sums, add-back); sizes here are <= a few
 // million entries, so this is launch-latency bound and deliberately simple.
 #pragma once
-#include <cstdint>
+#include "cuda_compat.cuh"
 
 namespace vmx {
 
 constexpr int kScanBlock = 1024;
 
+#ifndef VMX_HOST_EMUL
 // in-place exclusive scan of each block of 1024 entries; block totals to sums[blockIdx]
 __global__ void k_scan_block(uint32_t* __restrict__ d, size_t n, uint32_t* __restrict__ sums) {
   __shared__ uint32_t warp_tot[32];
@@ -36,6 +37,17 @@ __global__ void k_scan_block(uint32_t* __restrict__ d, size_t n, uint32_t* __res
   if (i < n) d[i] = base + x - v;
   if (threadIdx.x == kScanBlock - 1 && sums) sums[blockIdx.x] = base + x;
 }
+
+#else
+// sequential stand-in (tests/host_emul only): thread 0 of each block scans its 1024 entries
+inline void k_scan_block(uint32_t* d, size_t n, uint32_t* sums) {
+  if (threadIdx.x != 0) return;
+  const size_t b0 = (size_t)blockIdx.x * kScanBlock;
+  uint32_t acc = 0;
+  for (size_t i = b0; i < b0 + kScanBlock && i < n; i++) { const uint32_t v = d[i]; d[i] = acc; acc += v; }
+  if (sums) sums[blockIdx.x] = acc;
+}
+#endif
 
 __global__ void k_scan_add(uint32_t* __restrict__ d, size_t n, const uint32_t* __restrict__ sums) {
   const size_t i = (size_t)blockIdx.x * kScanBlock + threadIdx.x;

@@ -1,0 +1,1565 @@
+// vmx.cu -- host side of the C ABI declared in include/vmx.h: handle management, kernel
+// orchestration (window tables, Pippenger plan, segmented products, scans) and accounting.
+// All arithmetic runs in the sm_100a kernels of kernels_*.cuh; there is no CPU path.
+#include "vmx_internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <memory>
+
+#ifdef VMX_HOST_EMUL
+namespace vmx_emul {
+thread_local dim3 threadIdx_, blockIdx_, blockDim_, gridDim_;
+thread_local unsigned char* dyn_smem = nullptr;
+}  // namespace vmx_emul
+#endif
+
+namespace vmx {
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+#define VMX_DISPATCH(nl, ...)                                                  \
+  switch (nl) {                                                                \
+    case 16: { constexpr int N = 16; __VA_ARGS__; } break;                     \
+    case 32: { constexpr int N = 32; __VA_ARGS__; } break;                     \
+    case 64: { constexpr int N = 64; __VA_ARGS__; } break;                     \
+    case 96: { constexpr int N = 96; __VA_ARGS__; } break;                     \
+    default: set_error("unsupported limb count %d", (int)(nl)); return VMX_EARG; \
+  }
+
+#define VMX_CHECK_LAUNCH() VMX_CU(cudaGetLastError())
+
+static inline unsigned nblocks(size_t n, int per = kThreads) { return (unsigned)((n + per - 1) / per); }
+static inline size_t cap_for(size_t n) { return std::max<size_t>(8, (n + 7) & ~(size_t)7); }
+
+// ------------------------------------------------------------------ tiny host bignum (setup only)
+// little-endian 32-bit limbs; used for R mod n, R^2 mod n, n0inv, p-2: O(bits) shifts at
+// context creation.  No group arithmetic is ever done on the host.
+static bool be_to_limbs(const uint8_t* be, size_t nbytes, uint32_t* out, int N) {
+  for (int j = 0; j < N; j++) out[j] = 0;
+  for (size_t b = 0; b < nbytes; b++) {
+    const uint8_t v = be[nbytes - 1 - b];
+    if (b / 4 >= (size_t)N) { if (v) return false; continue; }
+    out[b / 4] |= (uint32_t)v << (8 * (b % 4));
+  }
+  return true;
+}
+static int limbs_bits(const uint32_t* a, int N) {
+  for (int j = N - 1; j >= 0; j--) if (a[j]) return 32 * j + (32 - __builtin_clz(a[j]));
+  return 0;
+}
+static int limbs_cmp(const uint32_t* a, const uint32_t* b, int N) {
+  for (int j = N - 1; j >= 0; j--) if (a[j] != b[j]) return a[j] < b[j] ? -1 : 1;
+  return 0;
+}
+static void limbs_sub(uint32_t* a, const uint32_t* b, int N) {
+  uint64_t brw = 0;
+  for (int j = 0; j < N; j++) { const uint64_t d = (uint64_t)a[j] - b[j] - brw; a[j] = (uint32_t)d; brw = (d >> 32) & 1; }
+}
+// r = 2^k mod n
+static void pow2_mod(uint32_t* r, int k, const uint32_t* n, int N) {
+  for (int j = 0; j < N; j++) r[j] = 0;
+  r[0] = 1;
+  for (int s = 0; s < k; s++) {
+    uint32_t c = 0;
+    for (int j = 0; j < N; j++) { const uint32_t nc = r[j] >> 31; r[j] = (r[j] << 1) | c; c = nc; }
+    if (c || limbs_cmp(r, n, N) >= 0) limbs_sub(r, n, N);
+  }
+}
+static uint32_t neg_inv32(uint32_t n0) {
+  uint32_t x = n0;  // n0 * x = 1 mod 2^3
+  for (int i = 0; i < 5; i++) x *= 2u - n0 * x;
+  return 0u - x;
+}
+// element `idx` of a limb-major host image with capacity `cap`
+static void image_put(std::vector<uint32_t>& img, size_t cap, size_t idx, const uint32_t* limbs, int N) {
+  for (int j = 0; j < N; j++) img[((size_t)(j >> 2) * cap + idx) * 4 + (j & 3)] = limbs[j];
+}
+
+// ------------------------------------------------------------------ device memory helpers
+struct DevBuf {  // stream-ordered temporary
+  vmx_ctx* c = nullptr;
+  void* p = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { reset(); }
+  void reset() { if (p) cudaFreeAsync(p, c->stream); p = nullptr; }
+  int alloc(vmx_ctx* ctx, size_t bytes) {
+    reset();
+    c = ctx;
+    if (cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream) != cudaSuccess) {
+      p = nullptr;
+      (void)cudaGetLastError();
+      set_error("device allocation of %zu bytes failed", bytes);
+      return VMX_ENOMEM;
+    }
+    return VMX_OK;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// a limb-major element array used as a temporary
+struct ElemBuf : DevBuf {
+  size_t cap = 0;
+  int alloc_elems(vmx_ctx* ctx, size_t n) { cap = cap_for(n); return alloc(ctx, cap * ctx->nl * 4); }
+  uint32_t* d() const { return as<uint32_t>(); }
+};
+
+static int new_garr(vmx_ctx* c, size_t n, vmx_garr** out) {
+  *out = nullptr;
+  auto* a = new (std::nothrow) vmx_garr{c, n, cap_for(n), nullptr};
+  if (!a) return VMX_ENOMEM;
+  void* p = nullptr;
+  if (cudaMallocAsync(&p, a->cap * c->nl * 4, c->stream) != cudaSuccess) {
+    (void)cudaGetLastError();
+    delete a;
+    set_error("device allocation of %zu bytes failed", a->cap * c->nl * 4);
+    return VMX_ENOMEM;
+  }
+  a->d = (uint32_t*)p;
+  *out = a;
+  return VMX_OK;
+}
+static int new_rarr(vmx_ctx* c, size_t n, vmx_rarr** out) {
+  *out = nullptr;
+  auto* a = new (std::nothrow) vmx_rarr{c, n, cap_for(n), nullptr, -1};
+  if (!a) return VMX_ENOMEM;
+  void* p = nullptr;
+  if (cudaMallocAsync(&p, a->cap * c->nl * 4, c->stream) != cudaSuccess) {
+    (void)cudaGetLastError();
+    delete a;
+    set_error("device allocation of %zu bytes failed", a->cap * c->nl * 4);
+    return VMX_ENOMEM;
+  }
+  a->d = (uint32_t*)p;
+  *out = a;
+  return VMX_OK;
+}
+
+static int enter_(const vmx_ctx* c) {
+  if (!c) { set_error("null context"); return VMX_EARG; }
+  VMX_CU(cudaSetDevice(c->device));
+  return VMX_OK;
+}
+// API entry: select the device and serialise host threads on the context (all work of a
+// context is queued on its one stream anyway; the flag scratch is shared).
+#define VMX_ENTER(c)    \
+  VMX_TRY(enter_(c)); \
+  std::unique_lock<std::recursive_mutex> _api_lock(const_cast<vmx_ctx*>(c)->api)
+
+// read back ctx->d_flag[0..k) (synchronises the stream)
+static int read_flags(vmx_ctx* c, int k) {
+  VMX_CU(cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int) * k, cudaMemcpyDeviceToHost, c->stream));
+  VMX_CU(cudaStreamSynchronize(c->stream));
+  return VMX_OK;
+}
+
+// ------------------------------------------------------------------ exclusive scan (uint32)
+static int exclusive_scan(vmx_ctx* c, uint32_t* d, size_t n) {
+  if (n == 0) return VMX_OK;
+  const size_t nb = (n + kScanBlock - 1) / kScanBlock;
+  if (nb == 1) {
+    VMX_LAUNCH(c, k_scan_block, 1, kScanBlock, 0, d, n, (uint32_t*)nullptr);
+    VMX_CHECK_LAUNCH();
+    return VMX_OK;
+  }
+  DevBuf sums;
+  VMX_TRY(sums.alloc(c, nb * 4));
+  VMX_LAUNCH(c, k_scan_block, nb, kScanBlock, 0, d, n, sums.as<uint32_t>());
+  VMX_CHECK_LAUNCH();
+  VMX_TRY(exclusive_scan(c, sums.as<uint32_t>(), nb));
+  VMX_LAUNCH(c, k_scan_add, nb, kScanBlock, 0, d, n, sums.as<uint32_t>());
+  VMX_CHECK_LAUNCH();
+  return VMX_OK;
+}
+
+// ------------------------------------------------------------------ segmented products
+// out[s] = prod_{k in [seg_off[s], seg_off[s+1])} V[idx ? idx[k] : k]  (empty -> one) for
+// s < nseg.  `total_bound` >= seg_off[nseg].  Runs chunked rounds (K terms per thread).
+template <int N>
+static int seg_product(vmx_ctx* c, const Modulus& Mod, const uint32_t* V, size_t vcap, const uint32_t* idx,
+                       const uint32_t* seg_off, size_t nseg, size_t total_bound, int K, uint32_t* out, size_t ocap) {
+  const MontParams<N> M = Mod.params<N>();
+  DevBuf off_keep;   // seg_off of the current round when it is one of ours
+  ElemBuf val_keep;  // partial products feeding the current round
+  const uint32_t* cur_V = V;
+  size_t cur_vcap = vcap;
+  const uint32_t* cur_idx = idx;
+  const uint32_t* cur_off = seg_off;
+  size_t cur_total = total_bound;
+  for (int round = 0; round < 64; round++) {
+    const size_t nch_bound = nseg + cur_total / K + 1;
+    DevBuf chunk_off, chunks;
+    VMX_TRY(chunk_off.alloc(c, (nseg + 1) * 4));
+    VMX_TRY(chunks.alloc(c, nch_bound * sizeof(Chunk)));
+    VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
+    VMX_LAUNCH(c, k_chunk_count, nblocks(nseg + 1, 256), 256, 0, cur_off, nseg, K, chunk_off.as<uint32_t>(),
+               reinterpret_cast<uint32_t*>(c->d_flag));
+    VMX_CHECK_LAUNCH();
+    VMX_TRY(exclusive_scan(c, chunk_off.as<uint32_t>(), nseg + 1));
+    VMX_LAUNCH(c, k_chunk_fill, nblocks(nseg, 256), 256, 0, cur_off, chunk_off.as<uint32_t>(), nseg,
+               chunks.as<Chunk>());
+    VMX_CHECK_LAUNCH();
+    VMX_TRY(read_flags(c, 1));
+    const bool last = (c->h_flag[0] == 0);  // every segment fits one chunk: chunk id == segment id
+    const uint32_t* nch_dev = chunk_off.as<uint32_t>() + nseg;
+    if (last) {
+      VMX_LAUNCH(c, k_seg_prod<N>, nblocks(nseg), kThreads, 0, cur_V, cur_vcap, cur_idx, chunks.as<Chunk>(), nch_dev,
+                 out, ocap, Mod.consts, M);
+      VMX_CHECK_LAUNCH();
+      c->modmuls += cur_total;
+      return VMX_OK;
+    }
+    ElemBuf part;
+    VMX_TRY(part.alloc_elems(c, nch_bound));
+    VMX_LAUNCH(c, k_seg_prod<N>, nblocks(nch_bound), kThreads, 0, cur_V, cur_vcap, cur_idx, chunks.as<Chunk>(),
+               nch_dev, part.d(), part.cap, Mod.consts, M);
+    VMX_CHECK_LAUNCH();
+    c->modmuls += cur_total;
+    // next round: values = partial products, segments = chunk ranges
+    std::swap(val_keep.p, part.p); std::swap(val_keep.c, part.c); std::swap(val_keep.cap, part.cap);
+    std::swap(off_keep.p, chunk_off.p); std::swap(off_keep.c, chunk_off.c);
+    cur_V = val_keep.d();
+    cur_vcap = val_keep.cap;
+    cur_idx = nullptr;
+    cur_off = off_keep.as<uint32_t>();
+    cur_total = nch_bound;
+  }
+  set_error("segmented product did not converge");
+  return VMX_ECUDA;
+}
+
+// ------------------------------------------------------------------ constants on the device
+static int upload_consts(vmx_ctx* c, Modulus& Mod) {
+  const int N = c->nl;
+  std::vector<uint32_t> img((size_t)4 * N, 0), r(N), r2(N), one(N, 0);
+  pow2_mod(r.data(), 32 * N, Mod.n, N);
+  pow2_mod(r2.data(), 64 * N, Mod.n, N);
+  one[0] = 1;
+  image_put(img, 4, 0, r2.data(), N);
+  image_put(img, 4, 1, r.data(), N);
+  image_put(img, 4, 2, one.data(), N);
+  void* p = nullptr;
+  VMX_CU(cudaMallocAsync(&p, img.size() * 4, c->stream));
+  Mod.consts = (uint32_t*)p;
+  VMX_CU(cudaMemcpyAsync(p, img.data(), img.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  VMX_CU(cudaStreamSynchronize(c->stream));
+  return VMX_OK;
+}
+
+// upload one element given as big-endian bytes into a fresh 1-element (cap 8) temporary,
+// group: to Montgomery form with range check; ring: canonical with range check.
+static int upload_one(vmx_ctx* c, const uint8_t* be, bool group, ElemBuf& buf) {
+  const size_t eb = group ? c->eb : c->rb;
+  DevBuf raw;
+  VMX_TRY(raw.alloc(c, eb));
+  VMX_CU(cudaMemcpyAsync(raw.p, be, eb, cudaMemcpyHostToDevice, c->stream));
+  VMX_TRY(buf.alloc_elems(c, 1));
+  VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
+  const Modulus& Mod = group ? c->P : c->Q;
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, 1, kThreads, 0, raw.as<uint8_t>(), (size_t)1, (int)eb,
+                                 group ? 0 : 1, buf.d(), buf.cap, Mod.consts, c->d_flag, Mod.params<N>()));
+  VMX_CHECK_LAUNCH();
+  VMX_TRY(read_flags(c, 1));
+  if (c->h_flag[0]) { set_error("element out of range (flags %d)", c->h_flag[0]); return VMX_EFORMAT; }
+  return VMX_OK;
+}
+
+// download element `idx` of a limb-major array as big-endian bytes (synchronises)
+static int download_one(vmx_ctx* c, const uint32_t* d, size_t cap, size_t idx, bool group, uint8_t* out_be) {
+  const size_t eb = group ? c->eb : c->rb;
+  DevBuf raw;
+  VMX_TRY(raw.alloc(c, eb));
+  const Modulus& Mod = group ? c->P : c->Q;
+  // k_to_bytes addresses element i = thread index: shift the base so that thread 0 -> idx
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, 1, kThreads, 0, d + 4 * idx, cap, (size_t)1, (int)eb,
+                                 group ? 0 : 1, raw.as<uint8_t>(), Mod.params<N>()));
+  VMX_CHECK_LAUNCH();
+  c->modmuls += group ? 1 : 0;
+  VMX_CU(cudaMemcpyAsync(out_be, raw.p, eb, cudaMemcpyDeviceToHost, c->stream));
+  VMX_CU(cudaStreamSynchronize(c->stream));
+  return VMX_OK;
+}
+
+static int rarr_bitlen(const vmx_rarr* a, int* bits) {
+  if (a->bits < 0) {
+    vmx_ctx* c = a->ctx;
+    VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
+    if (a->n) {
+      VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_bitlen<N>, nblocks(a->n, 256), 256, 0, a->d, a->cap, a->n,
+                                     reinterpret_cast<unsigned*>(c->d_flag)));
+      VMX_CHECK_LAUNCH();
+    }
+    VMX_TRY(read_flags(c, 1));
+    a->bits = c->h_flag[0];
+  }
+  *bits = a->bits;
+  return VMX_OK;
+}
+
+// number of resident threads one "wave" of the thread-per-element kernels fills
+static size_t wave_threads(const vmx_ctx* c) {
+  return (size_t)c->sm_count * kThreads * (c->nl > 64 ? 2 : 3);
+}
+
+// ------------------------------------------------------------------ fixed-base tables
+static int choose_fixed_window(const vmx_ctx* c, size_t n, int ebits) {
+  if (c->fixed_window) return c->fixed_window;
+  double best = 1e300;
+  int bw = 4;
+  for (int w = 4; w <= 16; w++) {
+    const double nwin = (ebits + w - 1) / w;
+    const double entries = nwin * (double)(1u << w);
+    if (entries * c->nl * 4 > 8e9) break;
+    const double cost = nwin * (3.0 * (double)n + (double)(1u << w));
+    if (cost < best) { best = cost; bw = w; }
+  }
+  return bw;
+}
+static double fixed_cost(int w, size_t n, int ebits) {
+  const double nwin = (ebits + w - 1) / w;
+  return nwin * (3.0 * (double)n + (double)(1u << w));
+}
+
+template <int N>
+static int build_table(vmx_ctx* c, const uint32_t* base, size_t bcap, int w, FixedTable& T) {
+  const MontParams<N> M = c->P.params<N>();
+  const int ebits = c->Q.bits;  // exponents are ring elements < q
+  T.w = w;
+  T.nwin = (ebits + w - 1) / w;
+  const size_t entries = (size_t)T.nwin << w;
+  T.cap = cap_for(entries);
+  void* p = nullptr;
+  if (cudaMallocAsync(&p, T.cap * N * 4, c->stream) != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("fixed-base table allocation failed (%zu bytes)", T.cap * N * 4);
+    return VMX_ENOMEM;
+  }
+  T.d = (uint32_t*)p;
+  const int qlen = T.nwin * w;
+  ElemBuf Q;
+  VMX_TRY(Q.alloc_elems(c, qlen));
+  VMX_LAUNCH(c, k_sqr_chain<N>, 1, 32, N * 4, base, bcap, (size_t)0, Q.d(), Q.cap, qlen, M);
+  VMX_CHECK_LAUNCH();
+  c->modmuls += qlen;
+  for (int j = 0; j < w; j++) {
+    const size_t items = (size_t)T.nwin << j;
+    VMX_LAUNCH(c, k_table_level<N>, nblocks(items), kThreads, 0, T.d, T.cap, w, T.nwin, j, qlen, Q.d(), Q.cap,
+               c->P.consts, M);
+    VMX_CHECK_LAUNCH();
+    c->modmuls += items;
+  }
+  return VMX_OK;
+}
+
+// find or build the table for `base_be`, sized for n exponents
+static int get_table(vmx_ctx* c, const uint8_t* base_be, size_t n, FixedTable* out) {
+  const std::string key(reinterpret_cast<const char*>(base_be), c->eb);
+  const int ebits = c->Q.bits;
+  const int wbest = choose_fixed_window(c, n, ebits);
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto it = c->tables.find(key);
+  if (it != c->tables.end()) {
+    if (fixed_cost(it->second.w, n, ebits) <= 1.3 * fixed_cost(wbest, n, ebits)) { *out = it->second; return VMX_OK; }
+    cudaFreeAsync(it->second.d, c->stream);
+    c->tables.erase(it);
+  }
+  ElemBuf base;
+  VMX_TRY(upload_one(c, base_be, true, base));
+  FixedTable T;
+  VMX_DISPATCH(c->nl, VMX_TRY(build_table<N>(c, base.d(), base.cap, wbest, T)));
+  c->tables[key] = T;
+  *out = T;
+  return VMX_OK;
+}
+
+template <int N>
+static int exp_fixed_run(vmx_ctx* c, const FixedTable& T, const vmx_rarr* e, int ebits, uint32_t* out, size_t ocap) {
+  const MontParams<N> M = c->P.params<N>();
+  const size_t n = e->n;
+  int nwin = std::min(T.nwin, std::max(1, (ebits + T.w - 1) / T.w));
+  // split the windows of one exponent over `parts` threads when that fills the waves better
+  const size_t wave = wave_threads(c);
+  int parts = 1;
+  if (nwin >= 8) {
+    double best_eff = 0;
+    for (int p = 1; p <= 64 && p * 4 <= nwin; p++) {
+      const double waves = (double)n * p / wave;
+      const double time = std::ceil(waves) * ((double)nwin / p) + (p > 1 ? std::ceil((double)n / wave) * p : 0);
+      const double eff = ((double)n * nwin / wave) / time;                 // useful / spent
+      if (eff > best_eff * 1.02) { best_eff = eff; parts = p; }
+    }
+  }
+  if (parts == 1) {
+    VMX_LAUNCH(c, k_exp_fixed<N>, nblocks(n), kThreads, 0, T.d, T.cap, T.w, nwin, e->d, e->cap, n, 1, out, ocap, M);
+    VMX_CHECK_LAUNCH();
+    c->modmuls += (uint64_t)n * (nwin - 1);
+    return VMX_OK;
+  }
+  ElemBuf tmp;
+  VMX_TRY(tmp.alloc_elems(c, n * parts));
+  VMX_LAUNCH(c, k_exp_fixed<N>, nblocks(n * parts), kThreads, 0, T.d, T.cap, T.w, nwin, e->d, e->cap, n, parts,
+             tmp.d(), tmp.cap, M);
+  VMX_CHECK_LAUNCH();
+  VMX_LAUNCH(c, k_combine_parts<N>, nblocks(n), kThreads, 0, tmp.d(), tmp.cap, n, parts, out, ocap, M);
+  VMX_CHECK_LAUNCH();
+  c->modmuls += (uint64_t)n * (nwin - 1);
+  return VMX_OK;
+}
+
+// ------------------------------------------------------------------ variable-base
+static int choose_var_window(int ebits) {
+  int bw = 1;
+  double best = 1e300;
+  for (int w = 1; w <= 6; w++) {
+    const double cost = (double)(1 << w) + ebits + (double)ebits / w;
+    if (cost < best) { best = cost; bw = w; }
+  }
+  return bw;
+}
+
+// out[i] = a[i]^{E[i or 0]} where E is a limb-major exponent array (capacity ecap)
+template <int N>
+static int exp_var_run(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32_t* E, size_t ecap, bool escalar,
+                       int ebits, size_t n, uint32_t* out, size_t ocap) {
+  const MontParams<N> M = c->P.params<N>();
+  if (n == 0) return VMX_OK;
+  if (ebits == 0) {  // everything to the power 0: fill with one
+    VMX_LAUNCH(c, k_gather, nblocks(n * (N / 4), 256), 256, 0, reinterpret_cast<const uint4*>(c->P.consts), (size_t)4,
+               reinterpret_cast<uint4*>(out), ocap, n, N / 4, (const uint32_t*)nullptr, (const uint32_t*)nullptr,
+               (long long)0, (long long)0, 1, (size_t)1);
+    VMX_CHECK_LAUNCH();
+    return VMX_OK;
+  }
+  const int w = choose_var_window(ebits);
+  // bound the per-thread table scratch (2^w entries per element) to ~6 GB, in whole waves
+  const size_t wave = wave_threads(c);
+  size_t chunk = (size_t)(6e9 / ((double)(1u << w) * N * 4));
+  chunk = std::max(wave, chunk / wave * wave);
+  chunk = std::min(chunk, n);
+  ElemBuf tab;
+  VMX_TRY(tab.alloc_elems(c, chunk << w));
+  const int nwin = (ebits + w - 1) / w;
+  for (size_t i0 = 0; i0 < n; i0 += chunk) {
+    const size_t m = std::min(chunk, n - i0);
+    VMX_LAUNCH(c, k_exp_var<N>, nblocks(m), kThreads, kThreads * N * 4, a + 4 * i0, acap,
+               escalar ? E : E + 4 * i0, ecap, escalar ? 1 : 0, ebits, w, m, tab.d(), tab.cap, c->P.consts,
+               out + 4 * i0, ocap, M);
+    VMX_CHECK_LAUNCH();
+    c->modmuls += (uint64_t)m * ((1u << w) - 2 + (uint64_t)(nwin - 1) * (w + 1));
+  }
+  return VMX_OK;
+}
+
+// ------------------------------------------------------------------ Pippenger
+struct MexpPlan {
+  int c = 0, W = 0, J = 0;
+  size_t nb = 0;       // W << c bucket segments
+  DevBuf seg_off, idx; // bucket accumulation lists
+  DevBuf seg2_off, idx2;  // static sub-digit lists
+  size_t nseg2 = 0, total2 = 0;
+};
+
+static int choose_mexp_window(size_t n, int L) {
+  int bc = 4;
+  double best = 1e300;
+  for (int c = 4; c <= 16; c += 4) {
+    const double W = (L + c - 1) / c;
+    const double cost = W * ((double)n + (double)(1u << c) * (c / 4) + 60.0 * 30);  // + latency-ish term
+    if (cost < best) { best = cost; bc = c; }
+  }
+  return bc;
+}
+
+template <int N>
+static int mexp_plan(vmx_ctx* c, const vmx_rarr* e, int L, MexpPlan& P) {
+  const size_t n = e->n;
+  P.c = choose_mexp_window(n, L);
+  P.W = (L + P.c - 1) / P.c;
+  P.J = P.c / kSubDigit;
+  P.nb = (size_t)P.W << P.c;
+  const size_t items = n * (size_t)P.W;
+  if (items >= 0xffffffffull) { set_error("expProd too large"); return VMX_ESIZE; }
+  VMX_TRY(P.seg_off.alloc(c, (P.nb + 1) * 4));
+  VMX_TRY(P.idx.alloc(c, items * 4));
+  VMX_CU(cudaMemsetAsync(P.seg_off.p, 0, (P.nb + 1) * 4, c->stream));
+  VMX_LAUNCH(c, k_digit_hist<N>, nblocks(items, 256), 256, 0, e->d, e->cap, n, P.c, P.W, P.seg_off.as<uint32_t>());
+  VMX_CHECK_LAUNCH();
+  VMX_TRY(exclusive_scan(c, P.seg_off.as<uint32_t>(), P.nb + 1));
+  DevBuf cursor;
+  VMX_TRY(cursor.alloc(c, (P.nb + 1) * 4));
+  VMX_CU(cudaMemcpyAsync(cursor.p, P.seg_off.p, (P.nb + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
+  VMX_LAUNCH(c, k_digit_scatter<N>, nblocks(items, 256), 256, 0, e->d, e->cap, n, P.c, P.W, cursor.as<uint32_t>(),
+             P.idx.as<uint32_t>());
+  VMX_CHECK_LAUNCH();
+  // static sub-digit lists
+  const size_t cnt = (size_t)1 << (P.c - kSubDigit);
+  P.nseg2 = (size_t)P.W * P.J * kSubVals;
+  P.total2 = P.nseg2 * cnt;
+  VMX_TRY(P.seg2_off.alloc(c, (P.nseg2 + 1) * 4));
+  VMX_TRY(P.idx2.alloc(c, P.total2 * 4));
+  VMX_LAUNCH(c, k_uniform_offsets, nblocks(P.nseg2 + 1, 256), 256, 0, P.seg2_off.as<uint32_t>(), P.nseg2,
+             (uint32_t)cnt);
+  VMX_CHECK_LAUNCH();
+  VMX_LAUNCH(c, k_subdigit_lists, P.nseg2, 128, 0, P.c, P.J, P.idx2.as<uint32_t>());
+  VMX_CHECK_LAUNCH();
+  return VMX_OK;
+}
+
+// result element written to out[oidx] (Montgomery form)
+template <int N>
+static int mexp_run(vmx_ctx* c, const MexpPlan& P, const vmx_garr* a, size_t n_terms, uint32_t* out, size_t ocap,
+                    size_t oidx) {
+  const MontParams<N> M = c->P.params<N>();
+  ElemBuf buckets, X, Y, R;
+  VMX_TRY(buckets.alloc_elems(c, P.nb));
+  VMX_TRY(seg_product<N>(c, c->P, a->d, a->cap, P.idx.as<uint32_t>(), P.seg_off.as<uint32_t>(), P.nb,
+                         n_terms * (size_t)P.W, 32, buckets.d(), buckets.cap));
+  VMX_TRY(X.alloc_elems(c, P.nseg2));
+  VMX_TRY(seg_product<N>(c, c->P, buckets.d(), buckets.cap, P.idx2.as<uint32_t>(), P.seg2_off.as<uint32_t>(),
+                         P.nseg2, P.total2, 8, X.d(), X.cap));
+  const size_t ngroups = (size_t)P.W * P.J;
+  VMX_TRY(Y.alloc_elems(c, ngroups));
+  VMX_TRY(R.alloc_elems(c, ngroups));
+  VMX_LAUNCH(c, k_weighted_small<N>, nblocks(ngroups, 32), 32, 0, X.d(), X.cap, ngroups, Y.d(), Y.cap, R.d(), R.cap,
+             M);
+  VMX_CHECK_LAUNCH();
+  VMX_LAUNCH(c, k_horner<N>, 1, 32, N * 4, Y.d(), Y.cap, (int)ngroups, out, ocap, oidx, M);
+  VMX_CHECK_LAUNCH();
+  c->modmuls += ngroups * 28 + (ngroups - 1) * 5;
+  return VMX_OK;
+}
+
+// ------------------------------------------------------------------ ring helpers
+// out[i] = a[i] * (element cidx of carr, Montgomery form) [+ addend[i]]   (mod q)
+template <int N>
+static int ring_mul_const(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32_t* carr, size_t ccap, size_t cidx,
+                          const uint32_t* addend, size_t dcap, uint32_t* out, size_t ocap, size_t n) {
+  if (!n) return VMX_OK;
+  VMX_LAUNCH(c, k_mul_const<N>, nblocks(n), kThreads, 0, a, acap, carr, ccap, cidx, addend, dcap, out, ocap, n,
+             c->Q.params<N>());
+  VMX_CHECK_LAUNCH();
+  c->modmuls += n;
+  return VMX_OK;
+}
+
+// total = sum_i a[i] (b == null) or sum_i a[i]*b[i] (canonical), written to out (1 element buf)
+template <int N>
+static int ring_reduce_sum(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32_t* b, size_t bcap, size_t n,
+                           ElemBuf& out) {
+  const MontParams<N> M = c->Q.params<N>();
+  const int K = 16;
+  ElemBuf cur, nxt, tmp;
+  const uint32_t* src = a;
+  size_t scap = acap, m = n;
+  const uint32_t* bb = b;
+  bool first = true;
+  while (first || m > 1) {
+    const size_t nch = (m + K - 1) / K;
+    VMX_TRY(nxt.alloc_elems(c, nch));
+    if (bb) VMX_TRY(tmp.alloc_elems(c, nch));
+    VMX_LAUNCH(c, k_chunk_sum<N>, nblocks(nch), kThreads, 0, src, scap, bb, bcap, m, K, nxt.d(), nxt.cap,
+               bb ? tmp.d() : (uint32_t*)nullptr, bb ? tmp.cap : (size_t)0, M);
+    VMX_CHECK_LAUNCH();
+    if (bb) c->modmuls += m;
+    std::swap(cur.p, nxt.p); std::swap(cur.c, nxt.c); std::swap(cur.cap, nxt.cap);
+    src = cur.d(); scap = cur.cap; m = nch; bb = nullptr; first = false;
+  }
+  VMX_TRY(out.alloc_elems(c, 1));
+  if (b) {  // sum of a*b*R^-1 -> multiply by R^2
+    VMX_TRY(ring_mul_const<N>(c, cur.d(), cur.cap, c->Q.consts, 4, 0, nullptr, 0, out.d(), out.cap, 1));
+  } else {
+    VMX_LAUNCH(c, k_gather, nblocks(N / 4, 32), 32, 0, reinterpret_cast<const uint4*>(cur.d()), cur.cap,
+               reinterpret_cast<uint4*>(out.d()), out.cap, (size_t)1, N / 4, (const uint32_t*)nullptr,
+               (const uint32_t*)nullptr, (long long)0, (long long)0, 0, (size_t)0);
+    VMX_CHECK_LAUNCH();
+  }
+  return VMX_OK;
+}
+
+// Affine scan.  eM = e in Montgomery form (n elements).  want_y = 0: out = recLin(b, e);
+// want_y = 1: out = prods(e) (b unused).
+template <int N>
+static int ring_scan(vmx_ctx* c, const uint32_t* eM, size_t ecap, const uint32_t* b, size_t bcap, size_t n,
+                     int want_y, uint32_t* out, size_t ocap) {
+  const MontParams<N> M = c->Q.params<N>();
+  const int K = 32;
+  const size_t nch = (n + K - 1) / K;
+  if (nch <= 1) {
+    VMX_LAUNCH(c, k_scan_phaseB<N>, 1, kThreads, 0, eM, ecap, b, bcap, n, K, (const uint32_t*)nullptr, (size_t)0,
+               (const uint32_t*)nullptr, (size_t)0, want_y, out, ocap, M);
+    VMX_CHECK_LAUNCH();
+    c->modmuls += n;
+    return VMX_OK;
+  }
+  ElemBuf A, B, AM, IA, IB;
+  VMX_TRY(A.alloc_elems(c, nch));
+  if (!want_y) VMX_TRY(B.alloc_elems(c, nch));
+  VMX_LAUNCH(c, k_scan_phaseA<N>, nblocks(nch), kThreads, 0, eM, ecap, want_y ? (const uint32_t*)nullptr : b, bcap, n,
+             K, A.d(), A.cap, want_y ? (uint32_t*)nullptr : B.d(), want_y ? (size_t)0 : B.cap, c->Q.consts, M);
+  VMX_CHECK_LAUNCH();
+  c->modmuls += (want_y ? 1 : 2) * n;
+  // chunk maps compose by the same recurrence: IA = prods(A), IB = recLin(B, A)
+  VMX_TRY(AM.alloc_elems(c, nch));
+  VMX_TRY(ring_mul_const<N>(c, A.d(), A.cap, c->Q.consts, 4, 0, nullptr, 0, AM.d(), AM.cap, nch));
+  if (want_y) {
+    VMX_TRY(IA.alloc_elems(c, nch));
+    VMX_TRY(ring_scan<N>(c, AM.d(), AM.cap, nullptr, 0, nch, 1, IA.d(), IA.cap));
+  } else {
+    VMX_TRY(IB.alloc_elems(c, nch));
+    VMX_TRY(ring_scan<N>(c, AM.d(), AM.cap, B.d(), B.cap, nch, 0, IB.d(), IB.cap));
+  }
+  VMX_LAUNCH(c, k_scan_phaseB<N>, nblocks(nch), kThreads, 0, eM, ecap, b, bcap, n, K,
+             want_y ? IA.d() : (const uint32_t*)nullptr, want_y ? IA.cap : (size_t)0,
+             want_y ? (const uint32_t*)nullptr : IB.d(), want_y ? (size_t)0 : IB.cap, want_y, out, ocap, M);
+  VMX_CHECK_LAUNCH();
+  c->modmuls += n;
+  return VMX_OK;
+}
+
+// generic plane-wise copy out[dst(i)] = in[src(i)]
+static int gather(vmx_ctx* c, const uint32_t* in, size_t icap, uint32_t* out, size_t ocap, size_t n,
+                  const uint32_t* src_idx, const uint32_t* dst_idx, long long src_off, long long dst_off) {
+  if (!n) return VMX_OK;
+  const int planes = c->nl / 4;
+  VMX_LAUNCH(c, k_gather, nblocks(n * planes, 256), 256, 0, reinterpret_cast<const uint4*>(in), icap,
+             reinterpret_cast<uint4*>(out), ocap, n, planes, src_idx, dst_idx, src_off, dst_off, 0, (size_t)0);
+  VMX_CHECK_LAUNCH();
+  return VMX_OK;
+}
+
+static int same_ctx(const void* a, const void* b) {
+  if (a != b) { set_error("operands belong to different contexts"); return VMX_EARG; }
+  return VMX_OK;
+}
+
+}  // namespace vmx
+
+using namespace vmx;
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char* vmx_last_error(void) { return g_err; }
+int vmx_version(void) { return 100; }
+
+int vmx_ctx_create_modp(const uint8_t* p_be, const uint8_t* q_be, const uint8_t* g_be, size_t nbytes, int device,
+                        vmx_ctx** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!p_be || !q_be || !nbytes) { set_error("null modulus"); return VMX_EARG; }
+  (void)g_be;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    (void)cudaGetLastError();
+    set_error("no CUDA device: this engine has no CPU path");
+    return VMX_ECUDA;
+  }
+  if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return VMX_EARG; }
+  std::unique_ptr<vmx_ctx> c(new vmx_ctx);
+  c->device = device;
+  uint32_t tmp[kMaxLimbs];
+  if (!be_to_limbs(p_be, nbytes, tmp, kMaxLimbs)) { set_error("modulus larger than 3072 bits"); return VMX_EARG; }
+  const int pbits = limbs_bits(tmp, kMaxLimbs);
+  c->nl = pbits <= 512 ? 16 : pbits <= 1024 ? 32 : pbits <= 2048 ? 64 : 96;
+  if (pbits < 64 || !(tmp[0] & 1)) { set_error("modulus must be odd and >= 64 bits"); return VMX_EARG; }
+  std::memcpy(c->P.n, tmp, sizeof tmp);
+  c->P.bits = pbits;
+  c->P.n0inv = neg_inv32(c->P.n[0]);
+  if (!be_to_limbs(q_be, nbytes, tmp, kMaxLimbs)) { set_error("bad group order"); return VMX_EARG; }
+  std::memcpy(c->Q.n, tmp, sizeof tmp);
+  c->Q.bits = limbs_bits(tmp, kMaxLimbs);
+  if (c->Q.bits < 8 || !(tmp[0] & 1) || limbs_cmp(c->Q.n, c->P.n, kMaxLimbs) >= 0) {
+    set_error("group order must be odd and smaller than the modulus");
+    return VMX_EARG;
+  }
+  c->Q.n0inv = neg_inv32(c->Q.n[0]);
+  c->eb = (size_t)pbits / 8 + 1;
+  c->rb = (size_t)c->Q.bits / 8 + 1;
+  c->pm2.assign(c->P.n, c->P.n + c->nl);
+  { uint32_t two[kMaxLimbs] = {2}; limbs_sub(c->pm2.data(), two, c->nl); }
+  VMX_CU(cudaSetDevice(device));
+#ifndef VMX_HOST_EMUL
+  {
+    cudaDeviceProp prop;
+    VMX_CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+      set_error("device %d is sm_%d%d; this engine is built for sm_100a only", device, prop.major, prop.minor);
+      return VMX_ECUDA;
+    }
+    cudaMemPool_t pool;
+    VMX_CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = ~0ull;  // keep freed blocks cached in the pool
+    VMX_CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  }
+#endif
+  VMX_CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  void* p = nullptr;
+  VMX_CU(cudaMallocAsync(&p, sizeof(int) * 4, c->stream));
+  c->d_flag = (int*)p;
+  VMX_CU(cudaMallocHost(&p, sizeof(int) * 4));
+  c->h_flag = (int*)p;
+  VMX_TRY(upload_consts(c.get(), c->P));
+  VMX_TRY(upload_consts(c.get(), c->Q));
+  *out = c.release();
+  return VMX_OK;
+}
+
+void vmx_ctx_destroy(vmx_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& kv : c->tables) cudaFreeAsync(kv.second.d, c->stream);
+  cudaFreeAsync(c->P.consts, c->stream);
+  cudaFreeAsync(c->Q.consts, c->stream);
+  cudaFreeAsync(c->d_flag, c->stream);
+  cudaStreamSynchronize(c->stream);
+  cudaFreeHost(c->h_flag);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+size_t vmx_ctx_elem_bytes(const vmx_ctx* c) { return c ? c->eb : 0; }
+size_t vmx_ctx_ring_bytes(const vmx_ctx* c) { return c ? c->rb : 0; }
+int vmx_ctx_sync(vmx_ctx* c) {
+  VMX_ENTER(c);
+  VMX_CU(cudaStreamSynchronize(c->stream));
+  return VMX_OK;
+}
+void* vmx_ctx_stream(vmx_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int vmx_ctx_set_fixed_window(vmx_ctx* c, int w) {
+  if (!c || w < 0 || w > 16) return VMX_EARG;
+  c->fixed_window = w;
+  return VMX_OK;
+}
+uint64_t vmx_ctx_launch_count(const vmx_ctx* c) { return c ? c->launches.load() : 0; }
+uint64_t vmx_ctx_modmul_count(const vmx_ctx* c) { return c ? c->modmuls.load() : 0; }
+
+// ---------------------------------------------------------------- group arrays: I/O
+static int garr_check_members(vmx_ctx* c, const vmx_garr* a, int* ok);
+
+int vmx_garr_from_bytes(vmx_ctx* c, size_t n, const uint8_t* be, int check_membership, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  VMX_ENTER(c);
+  if (n && !be) return VMX_EARG;
+  vmx_garr* a = nullptr;
+  VMX_TRY(new_garr(c, n, &a));
+  std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(a, vmx_garr_free);
+  if (n) {
+    DevBuf raw;
+    VMX_TRY(raw.alloc(c, n * c->eb));
+    VMX_CU(cudaMemcpyAsync(raw.p, be, n * c->eb, cudaMemcpyHostToDevice, c->stream));
+    VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n), kThreads, 0, raw.as<uint8_t>(), n, (int)c->eb, 0,
+                                   a->d, a->cap, c->P.consts, c->d_flag, c->P.params<N>()));
+    VMX_CHECK_LAUNCH();
+    c->modmuls += n;
+    VMX_TRY(read_flags(c, 1));
+    if (c->h_flag[0]) { set_error("group element out of range (flags %d)", c->h_flag[0]); return VMX_EFORMAT; }
+    if (check_membership) {
+      int ok = 0;
+      VMX_TRY(garr_check_members(c, a, &ok));
+      if (!ok) { set_error("element not in the order-q subgroup"); return VMX_EFORMAT; }
+    }
+  }
+  *out = guard.release();
+  return VMX_OK;
+}
+
+static int exp_scalar_limbs(vmx_ctx* c, const vmx_garr* a, const uint32_t* x, vmx_garr** out);
+
+int vmx_garr_from_raw(vmx_ctx* c, size_t n, const uint8_t* be, size_t width, unsigned bitlen, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  VMX_ENTER(c);
+  if ((n && !be) || !width || width > (size_t)8 * c->nl) { set_error("from_raw: bad width %zu", width); return VMX_EARG; }
+  if (bitlen > 8 * width) bitlen = 0;
+  // cofactor (p-1)/q must be a small integer: find it by repeated addition of q (setup-size host work)
+  uint32_t cof = 0;
+  {
+    std::vector<uint32_t> acc(c->nl + 1, 0), pm1(c->P.n, c->P.n + c->nl);
+    pm1.push_back(0);
+    pm1[0] -= 1;  // p is odd
+    for (cof = 1; cof <= 1u << 20; cof++) {
+      uint64_t carry = 0;
+      for (int j = 0; j <= c->nl; j++) {
+        const uint64_t s = (uint64_t)acc[j] + (j < c->nl ? c->Q.n[j] : 0) + carry;
+        acc[j] = (uint32_t)s; carry = s >> 32;
+      }
+      if (acc == pm1) break;
+    }
+    if (cof > 1u << 20) { set_error("from_raw: cofactor (p-1)/q is not a small integer"); return VMX_EARG; }
+  }
+  vmx_garr* t = nullptr;
+  VMX_TRY(new_garr(c, n, &t));
+  std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(t, vmx_garr_free);
+  if (!n) { *out = guard.release(); return VMX_OK; }
+  {
+    DevBuf raw;
+    ElemBuf can;
+    VMX_TRY(raw.alloc(c, n * width));
+    VMX_TRY(can.alloc_elems(c, n));
+    VMX_CU(cudaMemcpyAsync(raw.p, be, n * width, cudaMemcpyHostToDevice, c->stream));
+    VMX_DISPATCH(c->nl, {
+      VMX_LAUNCH(c, k_ring_from_raw<N>, nblocks(n), kThreads, 0, raw.as<uint8_t>(), n, (int)width, (int)bitlen, can.d(),
+                 can.cap, c->P.consts, 1, c->P.params<N>());
+      VMX_CHECK_LAUNCH();
+      // canonical -> Montgomery form
+      VMX_LAUNCH(c, k_mul_const<N>, nblocks(n), kThreads, 0, can.d(), can.cap, c->P.consts, (size_t)4, (size_t)0,
+                 (const uint32_t*)nullptr, (size_t)0, t->d, t->cap, n, c->P.params<N>());
+      VMX_CHECK_LAUNCH();
+    });
+    c->modmuls += 4 * n;
+    VMX_CU(cudaStreamSynchronize(c->stream));  // `be` is borrowed for the call only
+  }
+  uint32_t x[kMaxLimbs] = {cof};
+  return exp_scalar_limbs(c, t, x, out);
+}
+
+int vmx_garr_to_bytes(const vmx_garr* a, uint8_t* be_out) {
+  if (!a) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  if (!a->n) return VMX_OK;
+  DevBuf raw;
+  VMX_TRY(raw.alloc(c, a->n * c->eb));
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, a->n, (int)c->eb, 0,
+                                 raw.as<uint8_t>(), c->P.params<N>()));
+  VMX_CHECK_LAUNCH();
+  c->modmuls += a->n;
+  VMX_CU(cudaMemcpyAsync(be_out, raw.p, a->n * c->eb, cudaMemcpyDeviceToHost, c->stream));
+  VMX_CU(cudaStreamSynchronize(c->stream));
+  return VMX_OK;
+}
+
+int vmx_garr_fill(vmx_ctx* c, size_t n, const uint8_t* elem_be, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  VMX_ENTER(c);
+  ElemBuf one;
+  VMX_TRY(upload_one(c, elem_be, true, one));
+  vmx_garr* a = nullptr;
+  VMX_TRY(new_garr(c, n, &a));
+  if (n) {
+    const int planes = c->nl / 4;
+    VMX_LAUNCH(c, k_gather, nblocks(n * planes, 256), 256, 0, reinterpret_cast<const uint4*>(one.d()), one.cap,
+               reinterpret_cast<uint4*>(a->d), a->cap, n, planes, (const uint32_t*)nullptr, (const uint32_t*)nullptr,
+               (long long)0, (long long)0, 1, (size_t)0);
+    if (cudaGetLastError() != cudaSuccess) { vmx_garr_free(a); set_error("fill launch failed"); return VMX_ECUDA; }
+  }
+  *out = a;
+  return VMX_OK;
+}
+
+void vmx_garr_free(vmx_garr* a) {
+  if (!a) return;
+  cudaSetDevice(a->ctx->device);
+  if (a->d) cudaFreeAsync(a->d, a->ctx->stream);
+  delete a;
+}
+size_t vmx_garr_size(const vmx_garr* a) { return a ? a->n : 0; }
+
+// ---------------------------------------------------------------- group arrays: algebra
+int vmx_exp_fixed(vmx_ctx* c, const uint8_t* base_be, const vmx_rarr* e, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  VMX_ENTER(c);
+  if (!e || !base_be) return VMX_EARG;
+  VMX_TRY(same_ctx(e->ctx, c));
+  FixedTable T;
+  VMX_TRY(get_table(c, base_be, e->n, &T));
+  int ebits = 0;
+  VMX_TRY(rarr_bitlen(e, &ebits));
+  vmx_garr* r = nullptr;
+  VMX_TRY(new_garr(c, e->n, &r));
+  std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(r, vmx_garr_free);
+  if (e->n) VMX_DISPATCH(c->nl, VMX_TRY(exp_fixed_run<N>(c, T, e, ebits, r->d, r->cap)));
+  *out = guard.release();
+  return VMX_OK;
+}
+
+int vmx_fixed_precompute(vmx_ctx* c, const uint8_t* base_be, size_t n_hint) {
+  VMX_ENTER(c);
+  FixedTable T;
+  return get_table(c, base_be, n_hint, &T);
+}
+
+int vmx_exp_var(const vmx_garr* a, const vmx_rarr* e, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a || !e) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  VMX_TRY(same_ctx(e->ctx, c));
+  if (a->n != e->n) { set_error("exp: size mismatch %zu vs %zu", a->n, e->n); return VMX_ESIZE; }
+  int ebits = 0;
+  VMX_TRY(rarr_bitlen(e, &ebits));
+  vmx_garr* r = nullptr;
+  VMX_TRY(new_garr(c, a->n, &r));
+  std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(r, vmx_garr_free);
+  VMX_DISPATCH(c->nl, VMX_TRY(exp_var_run<N>(c, a->d, a->cap, e->d, e->cap, false, ebits, a->n, r->d, r->cap)));
+  *out = guard.release();
+  return VMX_OK;
+}
+
+int vmx_exp_scalar(const vmx_garr* a, const uint8_t* e_be, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a || !e_be) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  ElemBuf e;
+  VMX_TRY(upload_one(c, e_be, false, e));
+  uint32_t limbs[kMaxLimbs];
+  if (!be_to_limbs(e_be, c->rb, limbs, kMaxLimbs)) return VMX_EFORMAT;
+  const int ebits = limbs_bits(limbs, kMaxLimbs);
+  vmx_garr* r = nullptr;
+  VMX_TRY(new_garr(c, a->n, &r));
+  std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(r, vmx_garr_free);
+  VMX_DISPATCH(c->nl, VMX_TRY(exp_var_run<N>(c, a->d, a->cap, e.d(), e.cap, true, ebits, a->n, r->d, r->cap)));
+  *out = guard.release();
+  return VMX_OK;
+}
+
+// a[i]^x for a host-side limb exponent (internal: membership test, inversion)
+static int exp_scalar_limbs(vmx_ctx* c, const vmx_garr* a, const uint32_t* x, vmx_garr** out) {
+  std::vector<uint32_t> img((size_t)8 * c->nl, 0);
+  image_put(img, 8, 0, x, c->nl);
+  ElemBuf e;
+  VMX_TRY(e.alloc_elems(c, 1));
+  VMX_CU(cudaMemcpyAsync(e.p, img.data(), img.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  VMX_CU(cudaStreamSynchronize(c->stream));  // img is a stack-lifetime buffer
+  const int ebits = limbs_bits(x, c->nl);
+  vmx_garr* r = nullptr;
+  VMX_TRY(new_garr(c, a->n, &r));
+  std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(r, vmx_garr_free);
+  VMX_DISPATCH(c->nl, VMX_TRY(exp_var_run<N>(c, a->d, a->cap, e.d(), e.cap, true, ebits, a->n, r->d, r->cap)));
+  *out = guard.release();
+  return VMX_OK;
+}
+
+// Euler criterion x^q == 1 for every element (exact; a Jacobi-symbol kernel is the planned
+// replacement).
+static int garr_check_members(vmx_ctx* c, const vmx_garr* a, int* ok) {
+  vmx_garr* t = nullptr;
+  VMX_TRY(exp_scalar_limbs(c, a, c->Q.n, &t));
+  std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(t, vmx_garr_free);
+  VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_differs_from_const<N>, nblocks(a->n, 256), 256, 0, t->d, t->cap, a->n,
+                                 c->P.consts, (size_t)4, (size_t)1, c->d_flag));
+  VMX_CHECK_LAUNCH();
+  VMX_TRY(read_flags(c, 1));
+  *ok = c->h_flag[0] == 0;
+  return VMX_OK;
+}
+
+int vmx_expprod(const vmx_garr* const* a, size_t k, const vmx_rarr* e, uint8_t* out_be) {
+  if (!a || !k || !e || !out_be) return VMX_EARG;
+  vmx_ctx* c = e->ctx;
+  VMX_ENTER(c);
+  for (size_t l = 0; l < k; l++) {
+    if (!a[l]) return VMX_EARG;
+    VMX_TRY(same_ctx(a[l]->ctx, c));
+    if (a[l]->n != e->n) { set_error("expProd: size mismatch %zu vs %zu", a[l]->n, e->n); return VMX_ESIZE; }
+  }
+  int L = 0;
+  VMX_TRY(rarr_bitlen(e, &L));
+  ElemBuf res;
+  VMX_TRY(res.alloc_elems(c, k));
+  if (e->n == 0 || L == 0) {
+    for (size_t l = 0; l < k; l++) VMX_TRY(gather(c, c->P.consts, 4, res.d(), res.cap, 1, nullptr, nullptr, 1, (long long)l));
+  } else {
+    VMX_DISPATCH(c->nl, {
+      MexpPlan P;
+      VMX_TRY(mexp_plan<N>(c, e, L, P));
+      for (size_t l = 0; l < k; l++) VMX_TRY(mexp_run<N>(c, P, a[l], e->n, res.d(), res.cap, l));
+    });
+  }
+  DevBuf raw;
+  VMX_TRY(raw.alloc(c, k * c->eb));
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, 1, kThreads, 0, res.d(), res.cap, k, (int)c->eb, 0,
+                                 raw.as<uint8_t>(), c->P.params<N>()));
+  VMX_CHECK_LAUNCH();
+  VMX_CU(cudaMemcpyAsync(out_be, raw.p, k * c->eb, cudaMemcpyDeviceToHost, c->stream));
+  VMX_CU(cudaStreamSynchronize(c->stream));
+  return VMX_OK;
+}
+
+int vmx_mul(const vmx_garr* a, const vmx_garr* b, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a || !b) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  VMX_TRY(same_ctx(b->ctx, c));
+  if (a->n != b->n) { set_error("mul: size mismatch %zu vs %zu", a->n, b->n); return VMX_ESIZE; }
+  vmx_garr* r = nullptr;
+  VMX_TRY(new_garr(c, a->n, &r));
+  if (a->n) {
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_mul<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, b->d, b->cap, r->d, r->cap,
+                                   a->n, c->P.params<N>()));
+    if (cudaGetLastError() != cudaSuccess) { vmx_garr_free(r); set_error("mul launch failed"); return VMX_ECUDA; }
+    c->modmuls += a->n;
+  }
+  *out = r;
+  return VMX_OK;
+}
+
+int vmx_inv(const vmx_garr* a, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  return exp_scalar_limbs(c, a, c->pm2.data(), out);
+}
+
+int vmx_prod(const vmx_garr* a, uint8_t* out_be) {
+  if (!a || !out_be) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  ElemBuf res;
+  VMX_TRY(res.alloc_elems(c, 1));
+  DevBuf off;
+  VMX_TRY(off.alloc(c, 8));
+  const uint32_t h[2] = {0, (uint32_t)a->n};
+  VMX_CU(cudaMemcpyAsync(off.p, h, 8, cudaMemcpyHostToDevice, c->stream));
+  VMX_CU(cudaStreamSynchronize(c->stream));
+  // K scales with n so that the first round still fills the machine
+  const int K = (int)std::min<size_t>(64, std::max<size_t>(2, a->n / wave_threads(c)));
+  VMX_DISPATCH(c->nl, VMX_TRY(seg_product<N>(c, c->P, a->d, a->cap, nullptr, off.as<uint32_t>(), 1, a->n, K, res.d(),
+                                             res.cap)));
+  return download_one(c, res.d(), res.cap, 0, true, out_be);
+}
+
+static int upload_u32(vmx_ctx* c, const uint32_t* h, size_t n, DevBuf& buf) {
+  VMX_TRY(buf.alloc(c, n * 4));
+  if (n) {
+    VMX_CU(cudaMemcpyAsync(buf.p, h, n * 4, cudaMemcpyHostToDevice, c->stream));
+    VMX_CU(cudaStreamSynchronize(c->stream));
+  }
+  return VMX_OK;
+}
+
+int vmx_permute(const vmx_garr* a, const uint32_t* perm, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a || (!perm && a->n)) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  for (size_t i = 0; i < a->n; i++) if (perm[i] >= a->n) { set_error("permutation entry out of range"); return VMX_EARG; }
+  DevBuf p;
+  VMX_TRY(upload_u32(c, perm, a->n, p));
+  vmx_garr* r = nullptr;
+  VMX_TRY(new_garr(c, a->n, &r));
+  const int s = gather(c, a->d, a->cap, r->d, r->cap, a->n, nullptr, p.as<uint32_t>(), 0, 0);
+  if (s != VMX_OK) { vmx_garr_free(r); return s; }
+  *out = r;
+  return VMX_OK;
+}
+
+int vmx_shift_push(const vmx_garr* a, const uint8_t* elem_be, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a || !elem_be) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  ElemBuf el;
+  VMX_TRY(upload_one(c, elem_be, true, el));
+  vmx_garr* r = nullptr;
+  VMX_TRY(new_garr(c, a->n, &r));
+  std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(r, vmx_garr_free);
+  if (a->n) {
+    VMX_TRY(gather(c, a->d, a->cap, r->d, r->cap, a->n - 1, nullptr, nullptr, 0, 1));
+    VMX_TRY(gather(c, el.d(), el.cap, r->d, r->cap, 1, nullptr, nullptr, 0, 0));
+  }
+  *out = guard.release();
+  return VMX_OK;
+}
+
+int vmx_extract(const vmx_garr* a, const uint8_t* keep, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a || (!keep && a->n)) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  std::vector<uint32_t> src;
+  for (size_t i = 0; i < a->n; i++) if (keep[i]) src.push_back((uint32_t)i);
+  DevBuf p;
+  VMX_TRY(upload_u32(c, src.data(), src.size(), p));
+  vmx_garr* r = nullptr;
+  VMX_TRY(new_garr(c, src.size(), &r));
+  const int s = gather(c, a->d, a->cap, r->d, r->cap, src.size(), p.as<uint32_t>(), nullptr, 0, 0);
+  if (s != VMX_OK) { vmx_garr_free(r); return s; }
+  *out = r;
+  return VMX_OK;
+}
+
+int vmx_slice(const vmx_garr* a, size_t begin, size_t end, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a) return VMX_EARG;
+  if (begin > end || end > a->n) { set_error("slice [%zu,%zu) out of range %zu", begin, end, a->n); return VMX_ESIZE; }
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  vmx_garr* r = nullptr;
+  VMX_TRY(new_garr(c, end - begin, &r));
+  const int s = gather(c, a->d, a->cap, r->d, r->cap, end - begin, nullptr, nullptr, (long long)begin, 0);
+  if (s != VMX_OK) { vmx_garr_free(r); return s; }
+  *out = r;
+  return VMX_OK;
+}
+
+static int arrays_equal(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32_t* b, size_t bcap, size_t n, int* eq) {
+  VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
+  if (n) {
+    const int planes = c->nl / 4;
+    VMX_LAUNCH(c, k_equal, nblocks(n * planes, 256), 256, 0, reinterpret_cast<const uint4*>(a), acap,
+               reinterpret_cast<const uint4*>(b), bcap, n, planes, c->d_flag);
+    VMX_CHECK_LAUNCH();
+  }
+  VMX_TRY(read_flags(c, 1));
+  *eq = c->h_flag[0] == 0;
+  return VMX_OK;
+}
+
+int vmx_equals(const vmx_garr* a, const vmx_garr* b, int* equal) {
+  if (!a || !b || !equal) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  VMX_TRY(same_ctx(b->ctx, c));
+  if (a->n != b->n) { *equal = 0; return VMX_OK; }
+  return arrays_equal(c, a->d, a->cap, b->d, b->cap, a->n, equal);
+}
+
+int vmx_get(const vmx_garr* a, size_t i, uint8_t* out_be) {
+  if (!a || !out_be) return VMX_EARG;
+  if (i >= a->n) { set_error("index %zu out of range %zu", i, a->n); return VMX_ESIZE; }
+  VMX_ENTER(a->ctx);
+  return download_one(a->ctx, a->d, a->cap, i, true, out_be);
+}
+
+int vmx_expprod_cols(const vmx_garr* const* bases, size_t t, const int64_t* ints, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!bases || !t || !ints) return VMX_EARG;
+  vmx_ctx* c = bases[0]->ctx;
+  VMX_ENTER(c);
+  const size_t n = bases[0]->n;
+  vmx_garr* acc = nullptr;
+  for (size_t j = 0; j < t; j++) {
+    if (bases[j]->ctx != c || bases[j]->n != n) { if (acc) vmx_garr_free(acc); set_error("expProd: size mismatch"); return VMX_ESIZE; }
+    // term = bases[j]^{|ints[j]|}, inverted if negative
+    uint32_t x[kMaxLimbs] = {0};
+    const uint64_t mag = ints[j] < 0 ? (uint64_t)(-(ints[j] + 1)) + 1 : (uint64_t)ints[j];
+    x[0] = (uint32_t)mag; x[1] = (uint32_t)(mag >> 32);
+    vmx_garr* term = nullptr;
+    int s = exp_scalar_limbs(c, bases[j], x, &term);
+    if (s == VMX_OK && ints[j] < 0) {
+      vmx_garr* inv = nullptr;
+      s = vmx_inv(term, &inv);
+      vmx_garr_free(term);
+      term = inv;
+    }
+    if (s != VMX_OK) { if (acc) vmx_garr_free(acc); return s; }
+    if (!acc) { acc = term; continue; }
+    vmx_garr* prod = nullptr;
+    s = vmx_mul(acc, term, &prod);
+    vmx_garr_free(acc);
+    vmx_garr_free(term);
+    if (s != VMX_OK) return s;
+    acc = prod;
+  }
+  *out = acc;
+  return VMX_OK;
+}
+
+// ---------------------------------------------------------------- ring arrays
+int vmx_rarr_from_bytes(vmx_ctx* c, size_t n, const uint8_t* be, vmx_rarr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  VMX_ENTER(c);
+  if (n && !be) return VMX_EARG;
+  vmx_rarr* a = nullptr;
+  VMX_TRY(new_rarr(c, n, &a));
+  std::unique_ptr<vmx_rarr, void (*)(vmx_rarr*)> guard(a, vmx_rarr_free);
+  if (n) {
+    DevBuf raw;
+    VMX_TRY(raw.alloc(c, n * c->rb));
+    VMX_CU(cudaMemcpyAsync(raw.p, be, n * c->rb, cudaMemcpyHostToDevice, c->stream));
+    VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n), kThreads, 0, raw.as<uint8_t>(), n, (int)c->rb, 1,
+                                   a->d, a->cap, c->Q.consts, c->d_flag, c->Q.params<N>()));
+    VMX_CHECK_LAUNCH();
+    VMX_TRY(read_flags(c, 1));
+    if (c->h_flag[0]) { set_error("ring element out of range (flags %d)", c->h_flag[0]); return VMX_EFORMAT; }
+  }
+  *out = guard.release();
+  return VMX_OK;
+}
+
+int vmx_rarr_from_raw(vmx_ctx* c, size_t n, const uint8_t* be, size_t width, unsigned bitlen, vmx_rarr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  VMX_ENTER(c);
+  if ((n && !be) || !width || width > (size_t)8 * c->nl) { set_error("from_raw: bad width %zu", width); return VMX_EARG; }
+  if (bitlen > 8 * width) bitlen = 0;
+  vmx_rarr* a = nullptr;
+  VMX_TRY(new_rarr(c, n, &a));
+  std::unique_ptr<vmx_rarr, void (*)(vmx_rarr*)> guard(a, vmx_rarr_free);
+  if (n) {
+    DevBuf raw;
+    VMX_TRY(raw.alloc(c, n * width));
+    VMX_CU(cudaMemcpyAsync(raw.p, be, n * width, cudaMemcpyHostToDevice, c->stream));
+    const int totalbits = bitlen ? (int)bitlen : (int)(8 * width);
+    const int need_reduce = totalbits >= c->Q.bits;
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_ring_from_raw<N>, nblocks(n), kThreads, 0, raw.as<uint8_t>(), n, (int)width,
+                                   (int)bitlen, a->d, a->cap, c->Q.consts, need_reduce, c->Q.params<N>()));
+    VMX_CHECK_LAUNCH();
+    if (need_reduce) c->modmuls += 3 * n;
+    VMX_CU(cudaStreamSynchronize(c->stream));  // `be` is borrowed for the call only
+  }
+  *out = guard.release();
+  return VMX_OK;
+}
+
+int vmx_rarr_prg_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, size_t n, unsigned bitlen, vmx_rarr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  VMX_ENTER(c);
+  if (!seed || seedlen < 32 || seedlen > 48) { set_error("PRG seed must be 32..48 bytes"); return VMX_EARG; }
+  if (!bitlen || (int)bitlen >= c->Q.bits) { set_error("PRG bit length %u must be below |q|", bitlen); return VMX_EARG; }
+  const size_t wbytes = (bitlen + 7) / 8;
+  if (n * wbytes / 32 >= 0xffffffffull) { set_error("PRG stream too long"); return VMX_ESIZE; }
+  PrgSeed s;
+  std::memset(&s, 0, sizeof s);
+  std::memcpy(s.bytes, seed, seedlen);
+  s.len = (int)seedlen;
+  vmx_rarr* a = nullptr;
+  VMX_TRY(new_rarr(c, n, &a));
+  if (n) {
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_prg_expand<N>, nblocks(n, 128), 128, 0, s, n, (int)bitlen, a->d, a->cap));
+    if (cudaGetLastError() != cudaSuccess) { vmx_rarr_free(a); set_error("prg launch failed"); return VMX_ECUDA; }
+  }
+  *out = a;
+  return VMX_OK;
+}
+
+int vmx_rarr_to_bytes(const vmx_rarr* a, uint8_t* be_out) {
+  if (!a) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  if (!a->n) return VMX_OK;
+  DevBuf raw;
+  VMX_TRY(raw.alloc(c, a->n * c->rb));
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, a->n, (int)c->rb, 1,
+                                 raw.as<uint8_t>(), c->Q.params<N>()));
+  VMX_CHECK_LAUNCH();
+  VMX_CU(cudaMemcpyAsync(be_out, raw.p, a->n * c->rb, cudaMemcpyDeviceToHost, c->stream));
+  VMX_CU(cudaStreamSynchronize(c->stream));
+  return VMX_OK;
+}
+
+int vmx_rarr_fill(vmx_ctx* c, size_t n, const uint8_t* elem_be, vmx_rarr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  VMX_ENTER(c);
+  ElemBuf one;
+  VMX_TRY(upload_one(c, elem_be, false, one));
+  vmx_rarr* a = nullptr;
+  VMX_TRY(new_rarr(c, n, &a));
+  if (n) {
+    const int planes = c->nl / 4;
+    VMX_LAUNCH(c, k_gather, nblocks(n * planes, 256), 256, 0, reinterpret_cast<const uint4*>(one.d()), one.cap,
+               reinterpret_cast<uint4*>(a->d), a->cap, n, planes, (const uint32_t*)nullptr, (const uint32_t*)nullptr,
+               (long long)0, (long long)0, 1, (size_t)0);
+    if (cudaGetLastError() != cudaSuccess) { vmx_rarr_free(a); set_error("fill launch failed"); return VMX_ECUDA; }
+  }
+  *out = a;
+  return VMX_OK;
+}
+
+void vmx_rarr_free(vmx_rarr* a) {
+  if (!a) return;
+  cudaSetDevice(a->ctx->device);
+  if (a->d) cudaFreeAsync(a->d, a->ctx->stream);
+  delete a;
+}
+size_t vmx_rarr_size(const vmx_rarr* a) { return a ? a->n : 0; }
+int vmx_rarr_bitlen(const vmx_rarr* a, unsigned* bits) {
+  if (!a || !bits) return VMX_EARG;
+  VMX_ENTER(a->ctx);
+  int b = 0;
+  VMX_TRY(rarr_bitlen(a, &b));
+  *bits = (unsigned)b;
+  return VMX_OK;
+}
+
+static int ring_binary(const vmx_rarr* a, const vmx_rarr* b, int op, vmx_rarr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a || (op != 1 && !b)) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  if (b) {
+    VMX_TRY(same_ctx(b->ctx, c));
+    if (a->n != b->n) { set_error("ring op: size mismatch %zu vs %zu", a->n, b->n); return VMX_ESIZE; }
+  }
+  vmx_rarr* r = nullptr;
+  VMX_TRY(new_rarr(c, a->n, &r));
+  if (a->n) {
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_ring_addsub<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, b ? b->d : a->d,
+                                   b ? b->cap : a->cap, r->d, r->cap, a->n, op, c->Q.params<N>()));
+    if (cudaGetLastError() != cudaSuccess) { vmx_rarr_free(r); set_error("ring launch failed"); return VMX_ECUDA; }
+  }
+  *out = r;
+  return VMX_OK;
+}
+int vmx_radd(const vmx_rarr* a, const vmx_rarr* b, vmx_rarr** out) { return ring_binary(a, b, 0, out); }
+int vmx_rneg(const vmx_rarr* a, vmx_rarr** out) { return ring_binary(a, nullptr, 1, out); }
+int vmx_rsub(const vmx_rarr* a, const vmx_rarr* b, vmx_rarr** out) { return ring_binary(a, b, 2, out); }
+
+int vmx_rmul(const vmx_rarr* a, const vmx_rarr* b, vmx_rarr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a || !b) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  VMX_TRY(same_ctx(b->ctx, c));
+  if (a->n != b->n) { set_error("ring mul: size mismatch %zu vs %zu", a->n, b->n); return VMX_ESIZE; }
+  vmx_rarr* r = nullptr;
+  VMX_TRY(new_rarr(c, a->n, &r));
+  std::unique_ptr<vmx_rarr, void (*)(vmx_rarr*)> guard(r, vmx_rarr_free);
+  if (a->n) {
+    // r = a*b*R^-1 ; r = r * R^2 * R^-1 = a*b
+    VMX_DISPATCH(c->nl, {
+      ElemBuf t;
+      VMX_TRY(t.alloc_elems(c, a->n));
+      VMX_LAUNCH(c, k_mul<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, b->d, b->cap, t.d(), t.cap, a->n,
+                 c->Q.params<N>());
+      VMX_CHECK_LAUNCH();
+      c->modmuls += a->n;
+      VMX_TRY(ring_mul_const<N>(c, t.d(), t.cap, c->Q.consts, 4, 0, nullptr, 0, r->d, r->cap, a->n));
+    });
+  }
+  *out = guard.release();
+  return VMX_OK;
+}
+
+int vmx_rmuladd(const vmx_rarr* a, const uint8_t* s_be, const vmx_rarr* b, vmx_rarr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a || !b || !s_be) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  VMX_TRY(same_ctx(b->ctx, c));
+  if (a->n != b->n) { set_error("mulAdd: size mismatch %zu vs %zu", a->n, b->n); return VMX_ESIZE; }
+  ElemBuf s, sM;
+  VMX_TRY(upload_one(c, s_be, false, s));
+  VMX_TRY(sM.alloc_elems(c, 1));
+  vmx_rarr* r = nullptr;
+  VMX_TRY(new_rarr(c, a->n, &r));
+  std::unique_ptr<vmx_rarr, void (*)(vmx_rarr*)> guard(r, vmx_rarr_free);
+  VMX_DISPATCH(c->nl, {
+    VMX_TRY(ring_mul_const<N>(c, s.d(), s.cap, c->Q.consts, 4, 0, nullptr, 0, sM.d(), sM.cap, 1));
+    VMX_TRY(ring_mul_const<N>(c, a->d, a->cap, sM.d(), sM.cap, 0, b->d, b->cap, r->d, r->cap, a->n));
+  });
+  *out = guard.release();
+  return VMX_OK;
+}
+
+int vmx_rinner(const vmx_rarr* a, const vmx_rarr* b, uint8_t* out_be) {
+  if (!a || !b || !out_be) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  VMX_TRY(same_ctx(b->ctx, c));
+  if (a->n != b->n) { set_error("innerProduct: size mismatch %zu vs %zu", a->n, b->n); return VMX_ESIZE; }
+  if (!a->n) { std::memset(out_be, 0, c->rb); return VMX_OK; }
+  ElemBuf res;
+  VMX_DISPATCH(c->nl, VMX_TRY(ring_reduce_sum<N>(c, a->d, a->cap, b->d, b->cap, a->n, res)));
+  return download_one(c, res.d(), res.cap, 0, false, out_be);
+}
+
+int vmx_rsum(const vmx_rarr* a, uint8_t* out_be) {
+  if (!a || !out_be) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  if (!a->n) { std::memset(out_be, 0, c->rb); return VMX_OK; }
+  ElemBuf res;
+  VMX_DISPATCH(c->nl, VMX_TRY(ring_reduce_sum<N>(c, a->d, a->cap, nullptr, 0, a->n, res)));
+  return download_one(c, res.d(), res.cap, 0, false, out_be);
+}
+
+int vmx_rprod(const vmx_rarr* a, uint8_t* out_be) {
+  if (!a || !out_be) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  ElemBuf aM, res, can;
+  VMX_TRY(aM.alloc_elems(c, a->n));
+  VMX_TRY(res.alloc_elems(c, 1));
+  VMX_TRY(can.alloc_elems(c, 1));
+  DevBuf off;
+  const uint32_t h[2] = {0, (uint32_t)a->n};
+  VMX_TRY(upload_u32(c, h, 2, off));
+  const int K = (int)std::min<size_t>(64, std::max<size_t>(2, a->n / wave_threads(c)));
+  VMX_DISPATCH(c->nl, {
+    VMX_TRY(ring_mul_const<N>(c, a->d, a->cap, c->Q.consts, 4, 0, nullptr, 0, aM.d(), aM.cap, a->n));
+    VMX_TRY(seg_product<N>(c, c->Q, aM.d(), aM.cap, nullptr, off.as<uint32_t>(), 1, a->n, K, res.d(), res.cap));
+    VMX_LAUNCH(c, k_from_mont<N>, 1, kThreads, 0, res.d(), res.cap, can.d(), can.cap, (size_t)1, c->Q.params<N>());
+    VMX_CHECK_LAUNCH();
+  });
+  return download_one(c, can.d(), can.cap, 0, false, out_be);
+}
+
+static int ring_scan_api(const vmx_rarr* b, const vmx_rarr* e, int want_y, vmx_rarr** out, uint8_t* last_be) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!e || (!want_y && !b)) return VMX_EARG;
+  vmx_ctx* c = e->ctx;
+  VMX_ENTER(c);
+  if (b) {
+    VMX_TRY(same_ctx(b->ctx, c));
+    if (b->n != e->n) { set_error("recLin: size mismatch %zu vs %zu", b->n, e->n); return VMX_ESIZE; }
+  }
+  const size_t n = e->n;
+  vmx_rarr* r = nullptr;
+  VMX_TRY(new_rarr(c, n, &r));
+  std::unique_ptr<vmx_rarr, void (*)(vmx_rarr*)> guard(r, vmx_rarr_free);
+  if (n) {
+    ElemBuf eM;
+    VMX_TRY(eM.alloc_elems(c, n));
+    VMX_DISPATCH(c->nl, {
+      VMX_TRY(ring_mul_const<N>(c, e->d, e->cap, c->Q.consts, 4, 0, nullptr, 0, eM.d(), eM.cap, n));
+      VMX_TRY(ring_scan<N>(c, eM.d(), eM.cap, b ? b->d : nullptr, b ? b->cap : 0, n, want_y, r->d, r->cap));
+    });
+    if (last_be) VMX_TRY(download_one(c, r->d, r->cap, n - 1, false, last_be));
+  } else if (last_be) {
+    std::memset(last_be, 0, c->rb);
+  }
+  *out = guard.release();
+  return VMX_OK;
+}
+int vmx_rprods(const vmx_rarr* a, vmx_rarr** out) { return ring_scan_api(nullptr, a, 1, out, nullptr); }
+int vmx_rreclin(const vmx_rarr* b, const vmx_rarr* e, vmx_rarr** out, uint8_t* last_be) {
+  return ring_scan_api(b, e, 0, out, last_be);
+}
+
+int vmx_rpermute(const vmx_rarr* a, const uint32_t* perm, vmx_rarr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a || (!perm && a->n)) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  for (size_t i = 0; i < a->n; i++) if (perm[i] >= a->n) { set_error("permutation entry out of range"); return VMX_EARG; }
+  DevBuf p;
+  VMX_TRY(upload_u32(c, perm, a->n, p));
+  vmx_rarr* r = nullptr;
+  VMX_TRY(new_rarr(c, a->n, &r));
+  const int s = gather(c, a->d, a->cap, r->d, r->cap, a->n, nullptr, p.as<uint32_t>(), 0, 0);
+  if (s != VMX_OK) { vmx_rarr_free(r); return s; }
+  r->bits = a->bits;
+  *out = r;
+  return VMX_OK;
+}
+
+int vmx_rshift_push(const vmx_rarr* a, const uint8_t* elem_be, vmx_rarr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a || !elem_be) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  ElemBuf el;
+  VMX_TRY(upload_one(c, elem_be, false, el));
+  vmx_rarr* r = nullptr;
+  VMX_TRY(new_rarr(c, a->n, &r));
+  std::unique_ptr<vmx_rarr, void (*)(vmx_rarr*)> guard(r, vmx_rarr_free);
+  if (a->n) {
+    VMX_TRY(gather(c, a->d, a->cap, r->d, r->cap, a->n - 1, nullptr, nullptr, 0, 1));
+    VMX_TRY(gather(c, el.d(), el.cap, r->d, r->cap, 1, nullptr, nullptr, 0, 0));
+  }
+  *out = guard.release();
+  return VMX_OK;
+}
+
+int vmx_rslice(const vmx_rarr* a, size_t begin, size_t end, vmx_rarr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a) return VMX_EARG;
+  if (begin > end || end > a->n) { set_error("slice [%zu,%zu) out of range %zu", begin, end, a->n); return VMX_ESIZE; }
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  vmx_rarr* r = nullptr;
+  VMX_TRY(new_rarr(c, end - begin, &r));
+  const int s = gather(c, a->d, a->cap, r->d, r->cap, end - begin, nullptr, nullptr, (long long)begin, 0);
+  if (s != VMX_OK) { vmx_rarr_free(r); return s; }
+  *out = r;
+  return VMX_OK;
+}
+
+int vmx_rget(const vmx_rarr* a, size_t i, uint8_t* out_be) {
+  if (!a || !out_be) return VMX_EARG;
+  if (i >= a->n) { set_error("index %zu out of range %zu", i, a->n); return VMX_ESIZE; }
+  VMX_ENTER(a->ctx);
+  return download_one(a->ctx, a->d, a->cap, i, false, out_be);
+}
+
+int vmx_requals(const vmx_rarr* a, const vmx_rarr* b, int* equal) {
+  if (!a || !b || !equal) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  VMX_TRY(same_ctx(b->ctx, c));
+  if (a->n != b->n) { *equal = 0; return VMX_OK; }
+  return arrays_equal(c, a->d, a->cap, b->d, b->cap, a->n, equal);
+}
+
+// ---------------------------------------------------------------- benchmark hook
+int vmx_bench_modmul(vmx_ctx* c, size_t n, int iters, float* ms) {
+  VMX_ENTER(c);
+  if (!n || iters <= 0 || !ms) return VMX_EARG;
+  ElemBuf a, b, o;
+  VMX_TRY(a.alloc_elems(c, n));
+  VMX_TRY(b.alloc_elems(c, n));
+  VMX_TRY(o.alloc_elems(c, n));
+  // operands: Montgomery one and R^2 pattern replicated (any residues < p do)
+  VMX_LAUNCH(c, k_gather, nblocks(n * (c->nl / 4), 256), 256, 0, reinterpret_cast<const uint4*>(c->P.consts),
+             (size_t)4, reinterpret_cast<uint4*>(a.d()), a.cap, n, c->nl / 4, (const uint32_t*)nullptr,
+             (const uint32_t*)nullptr, (long long)0, (long long)0, 1, (size_t)1);
+  VMX_LAUNCH(c, k_gather, nblocks(n * (c->nl / 4), 256), 256, 0, reinterpret_cast<const uint4*>(c->P.consts),
+             (size_t)4, reinterpret_cast<uint4*>(b.d()), b.cap, n, c->nl / 4, (const uint32_t*)nullptr,
+             (const uint32_t*)nullptr, (long long)0, (long long)0, 1, (size_t)0);
+  VMX_CHECK_LAUNCH();
+#ifndef VMX_HOST_EMUL
+  cudaEvent_t e0, e1;
+  VMX_CU(cudaEventCreate(&e0));
+  VMX_CU(cudaEventCreate(&e1));
+  VMX_CU(cudaEventRecord(e0, c->stream));
+#endif
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_mul_iter<N>, nblocks(n), kThreads, 0, a.d(), b.d(), o.d(), a.cap, n, iters,
+                                 c->P.params<N>()));
+  VMX_CHECK_LAUNCH();
+  c->modmuls += (uint64_t)n * iters;
+#ifndef VMX_HOST_EMUL
+  VMX_CU(cudaEventRecord(e1, c->stream));
+  VMX_CU(cudaEventSynchronize(e1));
+  VMX_CU(cudaEventElapsedTime(ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+#else
+  *ms = 0.f;
+#endif
+  return VMX_OK;
+}
+
+}  // extern "C"

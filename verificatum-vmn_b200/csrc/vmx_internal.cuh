@@ -1,7 +1,5 @@
 // vmx_internal.cuh -- host-side structures behind the opaque handles of include/vmx.h.
 #pragma once
-#include <cuda_runtime.h>
-
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
@@ -12,6 +10,7 @@
 #include <vector>
 
 #include "../../include/vmx.h"
+#include "cuda_compat.cuh"
 #include "kernels_elem.cuh"
 #include "kernels_mexp.cuh"
 #include "kernels_prg.cuh"
@@ -24,13 +23,13 @@ constexpr int kMaxLimbs = 96;
 
 void set_error(const char* fmt, ...);
 
-#define VMX_CU(expr)                                                                       \
-  do {                                                                                     \
-    cudaError_t _e = (expr);                                                               \
-    if (_e != cudaSuccess) {                                                               \
-      ::vmx::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-      return VMX_ECUDA;                                                                    \
-    }                                                                                      \
+#define VMX_CU(expr)                                                                                 \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      ::vmx::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);  \
+      return VMX_ECUDA;                                                                              \
+    }                                                                                                \
   } while (0)
 
 #define VMX_TRY(expr)            \
@@ -39,17 +38,20 @@ void set_error(const char* fmt, ...);
     if (_s != VMX_OK) return _s; \
   } while (0)
 
+// Fixed-base window table: entry (k, d) = base^(d * 2^(w*k)), Montgomery form, limb-major,
+// element index (k << w) + d.
 struct FixedTable {
-  uint32_t* d = nullptr;  // nwin * 2^w entries, limb-major, Montgomery form
+  uint32_t* d = nullptr;
   size_t cap = 0;
   int w = 0, nwin = 0;
 };
 
 struct Modulus {
   uint32_t n[kMaxLimbs];
-  uint32_t n0inv;
-  int bits;
-  uint32_t* consts = nullptr;  // device, cap = 4: [0] = R^2 mod n, [1] = R mod n (Montgomery one), [2] = 1
+  uint32_t n0inv = 0;
+  int bits = 0;
+  // device, limb-major with cap = 4: [0] = R^2 mod n, [1] = R mod n (Montgomery one), [2] = 1
+  uint32_t* consts = nullptr;
   template <int N> MontParams<N> params() const {
     MontParams<N> M;
     for (int i = 0; i < N; i++) M.n[i] = n[i];
@@ -62,17 +64,17 @@ struct Modulus {
 
 struct vmx_ctx {
   int device = 0;
-  int nl = 0;  // limbs per residue: 64 or 96
-  size_t eb = 0, rb = 0;
+  int nl = 0;              // limbs per residue: 16, 32, 64 or 96
+  size_t eb = 0, rb = 0;   // bytes of a serialised group / ring element
   cudaStream_t stream = nullptr;
   vmx::Modulus P, Q;
-  std::vector<uint8_t> g_be;
+  std::vector<uint32_t> pm2;  // p - 2 (inversion exponent)
   std::mutex mu;
-  std::map<std::string, vmx::FixedTable> tables;  // key = base bytes
+  std::recursive_mutex api;  // serialises API calls of host threads on this context
+  std::map<std::string, vmx::FixedTable> tables;  // key = canonical base bytes
   int fixed_window = 0;                           // 0 = choose from n
-  int* d_flag = nullptr;                          // device int flag
-  unsigned* d_bits = nullptr;
-  int* h_flag = nullptr;                          // pinned
+  int* d_flag = nullptr;                          // device scratch: 4 ints
+  int* h_flag = nullptr;                          // pinned scratch: 4 ints
   std::atomic<uint64_t> launches{0}, modmuls{0};
   int sm_count = 148;
 };
