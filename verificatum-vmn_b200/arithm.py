@@ -46,6 +46,21 @@ def _be(x: int, width: int) -> bytes:
     return x.to_bytes(width, "big")
 
 
+def _jacobi(a: int, n: int) -> int:
+    """Jacobi symbol (a|n), n odd positive (LargeInteger.legendre for prime n)."""
+    a %= n
+    t = 1
+    while a:
+        tz = (a & -a).bit_length() - 1
+        a >>= tz
+        if tz & 1 and n & 7 in (3, 5):
+            t = -t
+        if a & 3 == 3 and n & 3 == 3:
+            t = -t
+        a, n = n % a, a
+    return t if n == 1 else 0
+
+
 # ====================================================================== permutations
 class Permutation:
     """com.verificatum.arithm.Permutation (table form)."""
@@ -448,11 +463,17 @@ class ModPGroup(PGroup):
             v = int(x)
         if not 0 < v < self.p:
             raise ArithmFormatException(nat.VMX_EFORMAT, "group element out of range")
-        # membership through the engine (one-element array, Euler criterion on the device)
-        m = np.frombuffer(_be(v, self.elem_bytes), dtype=np.uint8)
-        h = C.c_void_p()
-        nat.check(self._lib.vmx_garr_from_bytes(self.ctx, 1, _ptr(m), 1, C.byref(h)))
-        self._lib.vmx_garr_free(h)
+        if self.p == 2 * self.q + 1:
+            # safe prime: the order-q subgroup is the set of quadratic residues; a single
+            # element is validated by its Legendre symbol, as VCR does for one LargeInteger
+            if _jacobi(v, self.p) != 1:
+                raise ArithmFormatException(nat.VMX_EFORMAT, "element not in the order-q subgroup")
+        else:
+            # general subgroup: Euler criterion on the device (one-element array)
+            m = np.frombuffer(_be(v, self.elem_bytes), dtype=np.uint8)
+            h = C.c_void_p()
+            nat.check(self._lib.vmx_garr_from_bytes(self.ctx, 1, _ptr(m), 1, C.byref(h)))
+            self._lib.vmx_garr_free(h)
         return PGroupElement(self, v)
 
     # -- arrays
@@ -718,32 +739,38 @@ def expProdMany(arrays: Sequence[PGroupElementArray], e: PRingElementArray) -> L
 
 # ====================================================================== product groups / rings
 class PPRing(PRing):
-    """Product ring (exponents of wide ciphertexts): `width` copies of Z_q."""
+    """Product ring: the exponent ring of a product group (one factor ring per group factor)."""
 
-    def __init__(self, ring: PField, width: int):
-        self.ring = ring
-        self.width = width
+    def __init__(self, factors, width: Optional[int] = None):
+        if width is not None:
+            factors = [factors] * width
+        self.factors = list(factors)
+
+    def project(self, i: int):
+        return self.factors[i]
 
     def getPField(self):
-        return self.ring
+        return self.factors[0].getPField()
+
+    def getZERO(self):
+        return PPRingElement(self, [f.getZERO() for f in self.factors])
 
     def randomElement(self, randomSource, statDist):
-        return PPRingElement(self, [self.ring.randomElement(randomSource, statDist) for _ in range(self.width)])
+        return PPRingElement(self, [f.randomElement(randomSource, statDist) for f in self.factors])
 
     def randomElementArray(self, size, randomSource, statDist):
-        return PPRingElementArray(self, [self.ring.randomElementArray(size, randomSource, statDist)
-                                         for _ in range(self.width)])
+        return PPRingElementArray(self, [f.randomElementArray(size, randomSource, statDist) for f in self.factors])
 
     def toElement(self, btr: ByteTreeReader):
-        if btr.isLeaf() or btr.getRemaining() != self.width:
+        if btr.isLeaf() or btr.getRemaining() != len(self.factors):
             raise ArithmFormatException(nat.VMX_EFORMAT, "product ring element of wrong arity")
-        return PPRingElement(self, [self.ring.toElement(btr.getNextChild()) for _ in range(self.width)])
+        return PPRingElement(self, [f.toElement(btr.getNextChild()) for f in self.factors])
 
     def __eq__(self, o):
-        return isinstance(o, PPRing) and o.ring == self.ring and o.width == self.width
+        return isinstance(o, PPRing) and o.factors == self.factors
 
     def __hash__(self):
-        return hash((self.ring, self.width))
+        return hash(tuple(self.factors))
 
 
 class PPRingElement:
@@ -810,10 +837,7 @@ class PPGroup(PGroup):
         return len(self.factors)
 
     def getPRing(self):
-        f = self.factors[0]
-        r = f.getPRing()
-        # exponents act per factor when the factors are themselves products of the same shape
-        return r if all(x == f for x in self.factors) and not isinstance(f, PPGroup) else PPRingOf(self)
+        return PPRing([f.getPRing() for f in self.factors])
 
     def product(self, *els):
         if len(els) == 1 and not isinstance(els[0], (PGroupElementArray, PPGroupElementArray)):
@@ -863,17 +887,6 @@ class PPGroup(PGroup):
         return hash(tuple(self.factors))
 
 
-def PPRingOf(group: PPGroup) -> PRing:
-    f = group.factors[0]
-    if isinstance(f, PPGroup):
-        return PPRing(f.factors[0].getPRing(), len(f.factors))
-    return f.getPRing()
-
-
-def _exp_dispatch(comp, e):
-    return comp.exp(e)
-
-
 class PPGroupElement:
     def __init__(self, group: PPGroup, comps):
         self.group = group
@@ -886,14 +899,10 @@ class PPGroupElement:
         return self.comps[i]
 
     def _split(self, e):
-        """Exponent per component: a product-ring exponent of matching arity acts component-wise,
-        anything else is applied to every component."""
-        if isinstance(e, (PPRingElement, PPRingElementArray)) and len(e.comps) == len(self.comps) \
-                and not isinstance(self.comps[0], PPGroupElement):
+        """An exponent from this group's own (product) ring acts component-wise; an exponent from
+        any other ring is applied to every component (PPGroupElement.exp in VCR)."""
+        if isinstance(e, (PPRingElement, PPRingElementArray)) and e.getPRing() == self.group.getPRing():
             return e.comps
-        if isinstance(e, (PPRingElement, PPRingElementArray)) and isinstance(self.comps[0], PPGroupElement) \
-                and len(e.comps) != len(self.comps):
-            return [e] * len(self.comps)
         return [e] * len(self.comps)
 
     def exp(self, e):
@@ -965,8 +974,7 @@ class PPGroupElementArray:
         return self._map(lambda a: a.inv())
 
     def exp(self, e):
-        if isinstance(e, (PPRingElement, PPRingElementArray)) and len(e.comps) == len(self.comps) \
-                and not isinstance(self.comps[0], PPGroupElementArray):
+        if isinstance(e, (PPRingElement, PPRingElementArray)) and e.getPRing() == self.group.getPRing():
             return PPGroupElementArray(self.group, [c.exp(x) for c, x in zip(self.comps, e.comps)])
         return self._map(lambda a: a.exp(e))
 

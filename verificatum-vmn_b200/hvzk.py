@@ -1,0 +1,567 @@
+"""Proofs of shuffle on the engine: mirror of `com.verificatum.protocol.hvzk`.
+
+    PoSBasicTW   -- hvzk/PoSBasicTW.java   (Terelius-Wikstrom proof of a shuffle)
+    PoSCBasicTW  -- hvzk/PoSCBasicTW.java  (proof of a shuffle of commitments)
+    CCPoSBasicW  -- hvzk/CCPoSBasicW.java  (commitment-consistent proof of a shuffle)
+    ChallengerRO -- hvzk/ChallengerRO.java (Fiat-Shamir challenges from a random oracle)
+    PoSTW / PoSCTW / CCPoSW -- the non-interactive wrappers (hvzk/PoSTW.java:73-260 etc.) with the
+                    bulletin board replaced by in-memory byte trees.
+
+Method names, the order of operations, the order in which the prover consumes its random
+source and the explicit free() discipline follow the Java line by line (cited per method), so
+that the same seeds give the same transcript.  Every array operation is one call into the C
+ABI (include/vmx.h); nothing here computes on group elements on the CPU.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+from .arithm import (ArithmFormatException, LargeIntegerArray, Permutation, PGroupElementArray, PPGroupElement,
+                     PRingElementArray)
+from .crypto import HashfunctionHeuristic, PRGHeuristic, RandomOracle
+from .eio import ByteTreeBasic, ByteTreeContainer, ByteTreeLeaf, ByteTreeReader, EIOException
+
+
+class ProtocolError(RuntimeError):
+    pass
+
+
+class ChallengerRO:
+    """hvzk/ChallengerRO.java:96-116."""
+
+    def __init__(self, roHashfunction: HashfunctionHeuristic, globalPrefix: bytes):
+        self.roHashfunction = roHashfunction
+        self.globalPrefix = bytes(globalPrefix)
+        self.hashed_bytes = 0
+
+    def challenge(self, data: ByteTreeBasic, vbitlen: int, rbitlen: int = 0) -> bytes:
+        ro = RandomOracle(self.roHashfunction, vbitlen)
+        d = ro.getDigest()
+        d.update(self.globalPrefix)
+        data.update(d)
+        self.hashed_bytes += d.nbytes
+        return d.digest()
+
+
+def _to_positive(b: bytes) -> int:
+    """LargeInteger.toPositive(byte[])."""
+    return int.from_bytes(b, "big")
+
+
+def _free(*arrays) -> None:
+    for a in arrays:
+        if a is not None:
+            a.free()
+
+
+# ====================================================================== PoSBasicTW
+class PoSBasicTW:
+    """hvzk/PoSBasicTW.java:66."""
+
+    def __init__(self, vbitlen: int, ebitlen: int, rbitlen: int, prg: PRGHeuristic, randomSource):
+        self.vbitlen, self.ebitlen, self.rbitlen = vbitlen, ebitlen, rbitlen
+        self.prg = prg
+        self.randomSource = randomSource
+        self.u = self.e = self.b = self.B = self.Bp = self.ipe = self.beta = self.epsilon = None
+        self.k_B = self.k_E = self.r = self.s = None
+
+    # -- hvzk/PoSBasicTW.java:379-396
+    def _precompute_common(self, g, h) -> None:
+        self.size = h.size()
+        self.pGroup = g.getPGroup()
+        self.pRing = self.pGroup.getPRing()
+        self.pField = self.pRing.getPField()
+        self.g = g
+        self.h = h
+
+    # -- :407-410
+    def computeAF(self) -> None:
+        self.A = self.u.expProd(self.e)
+        self.F = self.w.expProd(self.e)
+
+    # -- :421-429 / :495-501
+    def setInstance(self, pkey: PPGroupElement, w, wp, s=None) -> None:
+        self.pkey = pkey
+        self.w = w
+        self.wp = wp
+        self.s = s
+
+    # -- :436-482 (prover) and :379 (verifier: pi is None)
+    def precompute(self, g, h, pi: Optional[Permutation] = None) -> None:
+        self._precompute_common(g, h)
+        if pi is None:
+            return
+        self.pi = pi
+        # u = (h * g^r) permuted                                       :446-452
+        self.r = self.pRing.randomElementArray(self.size, self.randomSource, self.rbitlen)
+        tmp1 = g.exp(self.r)
+        tmp2 = h.mul(tmp1)
+        tmp1.free()
+        self.u = tmp2.permute(pi)
+        tmp2.free()
+        # randomizers and blinder A' = g^alpha * prod h_i^epsilon_i    :465-481
+        self.alpha = self.pRing.randomElement(self.randomSource, self.rbitlen)
+        epsilonBitLength = self.ebitlen + self.vbitlen + self.rbitlen
+        epsilonIntegers = LargeIntegerArray.random(self.size, epsilonBitLength, self.randomSource, self.pField)
+        self.epsilon = self.pField.toElementArray(epsilonIntegers)
+        epsilonIntegers.free()
+        self.Ap = g.exp(self.alpha).mul(h.expProd(self.epsilon))
+
+    # -- :505-514
+    def setPermutationCommitment(self, btr: ByteTreeReader) -> None:
+        try:
+            self.u = self.pGroup.toElementArray(self.h.size(), btr)
+        except ArithmFormatException:
+            self.u = self.h.copyOfRange(0, self.h.size())
+
+    def getPermutationCommitment(self):
+        return self.u
+
+    # -- :533-538
+    def setBatchVector(self, prgSeed: bytes) -> None:
+        self.prg.setSeed(prgSeed)
+        lia = LargeIntegerArray.random(self.size, self.ebitlen, self.prg, self.pField)
+        self.e = self.pField.unsafeToElementArray(lia)
+
+    # -- :546-700
+    def commit(self, prgSeed: bytes) -> ByteTreeBasic:
+        self.setBatchVector(prgSeed)
+        g, h = self.g, self.h
+        piinv = self.pi.inv()
+        self.ipe = self.e.permute(piinv)                               # :552-554
+        piinv.free()
+        h0 = h.get(0)                                                  # :562
+        self.b = self.pRing.randomElementArray(self.size, self.randomSource, self.rbitlen)  # :571
+        x, self.d = self.b.recLin(self.ipe)                            # :596-598
+        y = self.ipe.prods()                                           # :604
+        g_exp_x = g.exp(x)                                             # :606
+        h0_exp_y = h0.exp(y)                                           # :608
+        self.B = g_exp_x.mul(h0_exp_y)                                 # :610
+        _free(g_exp_x, h0_exp_y)
+        self.beta = self.pRing.randomElementArray(self.size, self.randomSource, self.rbitlen)  # :621
+        xp = x.shiftPush(x.getPRing().getZERO())                       # :637
+        yp = y.shiftPush(y.getPRing().getONE())                        # :638
+        _free(y, x)
+        xp_mul_epsilon = xp.mul(self.epsilon)                          # :642
+        beta_add_prod = self.beta.add(xp_mul_epsilon)                  # :643
+        g_exp_beta_add_prod = g.exp(beta_add_prod)                     # :644
+        yp_mul_epsilon = yp.mul(self.epsilon)                          # :645
+        h0_exp_yp_mul_epsilon = h0.exp(yp_mul_epsilon)                 # :646
+        self.Bp = g_exp_beta_add_prod.mul(h0_exp_yp_mul_epsilon)       # :648
+        _free(h0_exp_yp_mul_epsilon, yp_mul_epsilon, g_exp_beta_add_prod, beta_add_prod, xp_mul_epsilon, yp, xp)
+        self.gamma = self.pRing.randomElement(self.randomSource, self.rbitlen)   # :667
+        self.Cp = g.exp(self.gamma)
+        self.delta = self.pRing.randomElement(self.randomSource, self.rbitlen)   # :678
+        self.Dp = g.exp(self.delta)
+        ciphPRing = self.pkey.project(0).getPGroup().getPRing()        # :687
+        self.phi = ciphPRing.randomElement(self.randomSource, self.rbitlen)
+        self.Fp = self.pkey.exp(self.phi.neg()).mul(self.wp.expProd(self.epsilon))  # :690
+        return ByteTreeContainer(self.B.toByteTree(), self.Ap.toByteTree(), self.Bp.toByteTree(),
+                                 self.Cp.toByteTree(), self.Dp.toByteTree(), self.Fp.toByteTree())
+
+    # -- :780-823
+    def setCommitment(self, btr: ByteTreeReader) -> ByteTreeBasic:
+        ciphPGroup = self.pkey.getPGroup()
+        malformed = False
+        self.B = self.Bp = None
+        try:
+            self.B = self.pGroup.toElementArray(self.size, btr.getNextChild())
+            self.Ap = self.pGroup.toElement(btr.getNextChild())
+            self.Bp = self.pGroup.toElementArray(self.size, btr.getNextChild())
+            self.Cp = self.pGroup.toElement(btr.getNextChild())
+            self.Dp = self.pGroup.toElement(btr.getNextChild())
+            self.Fp = ciphPGroup.toElement(btr.getNextChild())
+        except (EIOException, ArithmFormatException):
+            malformed = True
+        if malformed:
+            _free(self.B, self.Bp)
+            one = self.pGroup.getONE()
+            self.B = self.pGroup.toElementArray(self.size, one)
+            self.Ap = one
+            self.Bp = self.pGroup.toElementArray(self.size, one)
+            self.Cp = one
+            self.Dp = one
+            self.Fp = ciphPGroup.getONE()
+        return ByteTreeContainer(self.B.toByteTree(), self.Ap.toByteTree(), self.Bp.toByteTree(),
+                                 self.Cp.toByteTree(), self.Dp.toByteTree(), self.Fp.toByteTree())
+
+    # -- :838-848
+    def setChallenge(self, integerChallenge: int) -> None:
+        if not (0 <= integerChallenge and integerChallenge.bit_length() <= self.vbitlen):
+            raise ProtocolError("Malformed challenge!")
+        self.v = self.pField.toElement(integerChallenge)
+
+    # -- :856-888
+    def reply(self, integerChallenge: int) -> ByteTreeBasic:
+        self.setChallenge(integerChallenge)
+        v = self.v
+        a = self.r.innerProduct(self.ipe)
+        c = self.r.sum()
+        f = self.s.innerProduct(self.e)
+        self.k_A = a.mulAdd(v, self.alpha)
+        self.k_B = self.b.mulAdd(v, self.beta)
+        self.k_C = c.mulAdd(v, self.gamma)
+        self.k_D = self.d.mulAdd(v, self.delta)
+        self.k_E = self.ipe.mulAdd(v, self.epsilon)
+        self.k_F = f.mulAdd(v, self.phi)
+        return self.getReply()
+
+    # -- :970-990
+    def _parseReplies(self, ciphPRing, btr: ByteTreeReader) -> bool:
+        try:
+            self.k_A = self.pRing.toElement(btr.getNextChild())
+            self.k_B = self.pRing.toElementArray(self.size, btr.getNextChild())
+            self.k_C = self.pRing.toElement(btr.getNextChild())
+            self.k_D = self.pRing.toElement(btr.getNextChild())
+            self.k_E = self.pField.toElementArray(self.size, btr.getNextChild())
+            self.k_F = ciphPRing.toElement(btr.getNextChild())
+            return True
+        except (EIOException, ArithmFormatException):
+            return False
+
+    # -- :1000-1066
+    def verify(self, btr: ByteTreeReader) -> bool:
+        ciphPRing = self.pkey.project(0).getPGroup().getPRing()
+        if not self._parseReplies(ciphPRing, btr):
+            return False
+        g, h, u, v = self.g, self.h, self.u, self.v
+        h0 = h.get(0)
+        self.C = u.prod().div(h.prod())                                          # :1013
+        self.D = self.B.get(self.size - 1).div(h0.exp(self.e.prod()))            # :1014
+        verdictA = self.A.expMul(v, self.Ap).equals(g.exp(self.k_A).mul(h.expProd(self.k_E)))  # :1020-1021
+        B_exp_v = self.B.exp(v)                                                  # :1028
+        leftSide = B_exp_v.mul(self.Bp)
+        g_exp_k_B = g.exp(self.k_B)                                              # :1030
+        B_shift = self.B.shiftPush(h0)                                           # :1031
+        B_shift_exp_k_E = B_shift.exp(self.k_E)                                  # :1032
+        rightSide = g_exp_k_B.mul(B_shift_exp_k_E)
+        verdictB = leftSide.equals(rightSide)                                    # :1035
+        _free(B_exp_v, leftSide, g_exp_k_B, B_shift, B_shift_exp_k_E, rightSide)
+        verdictC = self.C.expMul(v, self.Cp).equals(g.exp(self.k_C))             # :1048
+        verdictD = self.D.expMul(v, self.Dp).equals(g.exp(self.k_D))             # :1055
+        verdictF = self.F.expMul(v, self.Fp).equals(
+            self.pkey.exp(self.k_F.neg()).mul(self.wp.expProd(self.k_E)))        # :1062-1063
+        self.verdicts = (verdictA, verdictB, verdictC, verdictD, verdictF)
+        return verdictA and verdictB and verdictC and verdictD and verdictF
+
+    # -- :1073-1080
+    def getReply(self) -> ByteTreeBasic:
+        return ByteTreeContainer(self.k_A.toByteTree(), self.k_B.toByteTree(), self.k_C.toByteTree(),
+                                 self.k_D.toByteTree(), self.k_E.toByteTree(), self.k_F.toByteTree())
+
+    # -- :1088-1101
+    def free(self) -> None:
+        _free(self.r, self.u, self.e, self.b, self.B, self.Bp, self.ipe, self.beta, self.epsilon, self.k_B, self.k_E)
+        self.r = self.u = self.e = self.b = self.B = self.Bp = self.ipe = self.beta = self.epsilon = None
+        self.k_B = self.k_E = None
+
+
+# ====================================================================== PoSCBasicTW
+class PoSCBasicTW:
+    """hvzk/PoSCBasicTW.java:65 -- PoSBasicTW without the ciphertext (F) part."""
+
+    def __init__(self, vbitlen, ebitlen, rbitlen, prg, randomSource):
+        self.vbitlen, self.ebitlen, self.rbitlen = vbitlen, ebitlen, rbitlen
+        self.prg = prg
+        self.randomSource = randomSource
+        self.e = self.b = self.B = self.Bp = self.ipe = self.beta = self.epsilon = self.k_B = self.k_E = None
+
+    # -- :306-339
+    def setInstance(self, g, h, u, r=None, pi=None) -> None:
+        self.g, self.h, self.u, self.r, self.pi = g, h, u, r, pi
+        self.size = h.size()
+        self.pGroup = g.getPGroup()
+        self.pRing = self.pGroup.getPRing()
+        self.pField = self.pRing.getPField()
+
+    # -- :350-355
+    def setBatchVector(self, prgSeed: bytes) -> None:
+        self.prg.setSeed(prgSeed)
+        lia = LargeIntegerArray.random(self.size, self.ebitlen, self.prg, self.pField)
+        self.e = self.pField.unsafeToElementArray(lia)
+
+    # -- :363-529
+    def commit(self, prgSeed: bytes) -> ByteTreeBasic:
+        self.setBatchVector(prgSeed)
+        g, h = self.g, self.h
+        piinv = self.pi.inv()
+        self.ipe = self.e.permute(piinv)
+        h0 = h.get(0)
+        self.b = self.pRing.randomElementArray(self.size, self.randomSource, self.rbitlen)
+        x, self.d = self.b.recLin(self.ipe)
+        y = self.ipe.prods()
+        g_exp_x = g.exp(x)
+        h0_exp_y = h0.exp(y)
+        self.B = g_exp_x.mul(h0_exp_y)
+        _free(g_exp_x, h0_exp_y)
+        self.alpha = self.pRing.randomElement(self.randomSource, self.rbitlen)
+        epsilonBitLength = self.ebitlen + self.vbitlen + self.rbitlen
+        epsilonIntegers = LargeIntegerArray.random(self.size, epsilonBitLength, self.randomSource, self.pField)
+        self.epsilon = self.pField.toElementArray(epsilonIntegers)
+        epsilonIntegers.free()
+        self.Ap = g.exp(self.alpha).mul(h.expProd(self.epsilon))
+        self.beta = self.pRing.randomElementArray(self.size, self.randomSource, self.rbitlen)
+        xp = x.shiftPush(x.getPRing().getZERO())
+        yp = y.shiftPush(y.getPRing().getONE())
+        _free(y, x)
+        xp_mul_epsilon = xp.mul(self.epsilon)
+        beta_add_prod = self.beta.add(xp_mul_epsilon)
+        g_exp_beta_add_prod = g.exp(beta_add_prod)
+        yp_mul_epsilon = yp.mul(self.epsilon)
+        h0_exp_yp_mul_epsilon = h0.exp(yp_mul_epsilon)
+        self.Bp = g_exp_beta_add_prod.mul(h0_exp_yp_mul_epsilon)
+        _free(h0_exp_yp_mul_epsilon, yp_mul_epsilon, g_exp_beta_add_prod, beta_add_prod, xp_mul_epsilon, yp, xp)
+        self.gamma = self.pRing.randomElement(self.randomSource, self.rbitlen)
+        self.Cp = g.exp(self.gamma)
+        self.delta = self.pRing.randomElement(self.randomSource, self.rbitlen)
+        self.Dp = g.exp(self.delta)
+        return ByteTreeContainer(self.B.toByteTree(), self.Ap.toByteTree(), self.Bp.toByteTree(),
+                                 self.Cp.toByteTree(), self.Dp.toByteTree())
+
+    # -- :540-575
+    def setCommitment(self, btr: ByteTreeReader) -> ByteTreeBasic:
+        malformed = False
+        self.B = self.Bp = None
+        try:
+            self.B = self.pGroup.toElementArray(self.size, btr.getNextChild())
+            self.Ap = self.pGroup.toElement(btr.getNextChild())
+            self.Bp = self.pGroup.toElementArray(self.size, btr.getNextChild())
+            self.Cp = self.pGroup.toElement(btr.getNextChild())
+            self.Dp = self.pGroup.toElement(btr.getNextChild())
+        except (EIOException, ArithmFormatException):
+            malformed = True
+        if malformed:
+            _free(self.B, self.Bp)
+            one = self.pGroup.getONE()
+            self.B = self.pGroup.toElementArray(self.size, one)
+            self.Ap = one
+            self.Bp = self.pGroup.toElementArray(self.size, one)
+            self.Cp = one
+            self.Dp = one
+        return ByteTreeContainer(self.B.toByteTree(), self.Ap.toByteTree(), self.Bp.toByteTree(),
+                                 self.Cp.toByteTree(), self.Dp.toByteTree())
+
+    # -- :590-600
+    def setChallenge(self, integerChallenge: int) -> None:
+        if not (0 <= integerChallenge and integerChallenge.bit_length() <= self.vbitlen):
+            raise ProtocolError("Malformed challenge!")
+        self.v = self.pField.toElement(integerChallenge)
+
+    # -- :607-636
+    def reply(self, integerChallenge: int) -> ByteTreeBasic:
+        self.setChallenge(integerChallenge)
+        v = self.v
+        a = self.r.innerProduct(self.ipe)
+        c = self.r.sum()
+        self.k_A = a.mulAdd(v, self.alpha)
+        self.k_B = self.b.mulAdd(v, self.beta)
+        self.k_C = c.mulAdd(v, self.gamma)
+        self.k_D = self.d.mulAdd(v, self.delta)
+        self.k_E = self.ipe.mulAdd(v, self.epsilon)
+        return ByteTreeContainer(self.k_A.toByteTree(), self.k_B.toByteTree(), self.k_C.toByteTree(),
+                                 self.k_D.toByteTree(), self.k_E.toByteTree())
+
+    # -- :646-727
+    def verify(self, btr: ByteTreeReader) -> bool:
+        try:
+            self.k_A = self.pRing.toElement(btr.getNextChild())
+            self.k_B = self.pRing.toElementArray(self.size, btr.getNextChild())
+            self.k_C = self.pRing.toElement(btr.getNextChild())
+            self.k_D = self.pRing.toElement(btr.getNextChild())
+            self.k_E = self.pField.toElementArray(self.size, btr.getNextChild())
+        except (EIOException, ArithmFormatException):
+            return False
+        g, h, u, v = self.g, self.h, self.u, self.v
+        h0 = h.get(0)
+        A = u.expProd(self.e)
+        C = u.prod().div(h.prod())
+        D = self.B.get(self.size - 1).div(h0.exp(self.e.prod()))
+        verdict = True
+        if not A.expMul(v, self.Ap).equals(g.exp(self.k_A).mul(h.expProd(self.k_E))):
+            verdict = False
+        if verdict:
+            B_exp_v = self.B.exp(v)
+            leftSide = B_exp_v.mul(self.Bp)
+            g_exp_k_B = g.exp(self.k_B)
+            B_shift = self.B.shiftPush(h0)
+            B_shift_exp_k_E = B_shift.exp(self.k_E)
+            rightSide = g_exp_k_B.mul(B_shift_exp_k_E)
+            B_res = leftSide.equals(rightSide)
+            _free(B_exp_v, leftSide, g_exp_k_B, B_shift, B_shift_exp_k_E, rightSide)
+            if not B_res:
+                verdict = False
+        if verdict and not C.expMul(v, self.Cp).equals(g.exp(self.k_C)):
+            verdict = False
+        if verdict and not D.expMul(v, self.Dp).equals(g.exp(self.k_D)):
+            verdict = False
+        return verdict
+
+    def free(self) -> None:
+        _free(self.e, self.b, self.B, self.Bp, self.ipe, self.beta, self.epsilon, self.k_B, self.k_E)
+        self.e = self.b = self.B = self.Bp = self.ipe = self.beta = self.epsilon = self.k_B = self.k_E = None
+
+
+# ====================================================================== CCPoSBasicW
+class CCPoSBasicW:
+    """hvzk/CCPoSBasicW.java:65 (the raisedu/raisedh variant of computeAB/verify, :502-504 and
+    :571-579, mixes a basic array into a product-group array inside VCR and is not mirrored)."""
+
+    def __init__(self, vbitlen, ebitlen, rbitlen, prg):
+        self.vbitlen, self.ebitlen, self.rbitlen = vbitlen, ebitlen, rbitlen
+        self.prg = prg
+        self.e = self.ipe = self.epsilon = self.k_E = None
+
+    # -- :268-313
+    def setInstance(self, g, h, u, pkey, w, wp, r=None, pi=None, s=None) -> None:
+        self.g, self.h, self.u, self.pkey, self.w, self.wp = g, h, u, pkey, w, wp
+        self.r, self.pi, self.s = r, pi, s
+        self.size = h.size()
+        self.pGroup = g.getPGroup()
+        self.pRing = self.pGroup.getPRing()
+        self.pField = self.pRing.getPField()
+
+    # -- :330-335
+    def setBatchVector(self, prgSeed: bytes) -> None:
+        self.prg.setSeed(prgSeed)
+        lia = LargeIntegerArray.random(self.size, self.ebitlen, self.prg, self.pField)
+        self.e = self.pField.unsafeToElementArray(lia)
+
+    # -- :344-396
+    def commit(self, prgSeed: bytes, randomSource) -> ByteTreeBasic:
+        self.setBatchVector(prgSeed)
+        piinv = self.pi.inv()
+        self.ipe = self.e.permute(piinv)
+        self.alpha = self.pRing.randomElement(randomSource, self.rbitlen)
+        epsilonBitLength = self.ebitlen + self.vbitlen + self.rbitlen
+        epsilonIntegers = LargeIntegerArray.random(self.size, epsilonBitLength, randomSource, self.pField)
+        self.epsilon = self.pField.toElementArray(epsilonIntegers)
+        epsilonIntegers.free()
+        self.Ap = self.g.exp(self.alpha).mul(self.h.expProd(self.epsilon))
+        ciphPRing = self.pkey.project(0).getPGroup().getPRing()
+        self.beta = ciphPRing.randomElement(randomSource, self.rbitlen)
+        self.Bp = self.pkey.exp(self.beta.neg()).mul(self.wp.expProd(self.epsilon))
+        return ByteTreeContainer(self.Ap.toByteTree(), self.Bp.toByteTree())
+
+    # -- :406-428
+    def setCommitment(self, btr: ByteTreeReader) -> ByteTreeBasic:
+        ciphPGroup = self.pkey.getPGroup()
+        try:
+            self.Ap = self.pGroup.toElement(btr.getNextChild())
+            self.Bp = ciphPGroup.toElement(btr.getNextChild())
+        except (EIOException, ArithmFormatException):
+            self.Ap = self.pGroup.getONE()
+            self.Bp = ciphPGroup.getONE()
+        return ByteTreeContainer(self.Ap.toByteTree(), self.Bp.toByteTree())
+
+    def setChallenge(self, integerChallenge: int) -> None:
+        if not (0 <= integerChallenge and integerChallenge.bit_length() <= self.vbitlen):
+            raise ProtocolError("Malformed challenge!")
+        self.v = self.pField.toElement(integerChallenge)
+
+    # -- :462-485
+    def reply(self, integerChallenge: int) -> ByteTreeBasic:
+        self.setChallenge(integerChallenge)
+        a = self.r.innerProduct(self.ipe)
+        b = self.s.innerProduct(self.e)
+        self.k_A = a.mulAdd(self.v, self.alpha)
+        self.k_B = b.mulAdd(self.v, self.beta)
+        self.k_E = self.ipe.mulAdd(self.v, self.epsilon)
+        return ByteTreeContainer(self.k_A.toByteTree(), self.k_B.toByteTree(), self.k_E.toByteTree())
+
+    # -- :493-506
+    def computeAB(self) -> None:
+        self.A = self.u.expProd(self.e)
+        self.B = self.w.expProd(self.e)
+
+    # -- :519-584
+    def verify(self, btr: ByteTreeReader) -> bool:
+        ciphPRing = self.pkey.project(0).getPGroup().getPRing()
+        try:
+            self.k_A = self.pRing.toElement(btr.getNextChild())
+            self.k_B = ciphPRing.toElement(btr.getNextChild())
+            self.k_E = self.pField.toElementArray(self.size, btr.getNextChild())
+        except (EIOException, ArithmFormatException):
+            self.k_A = self.pRing.getZERO()
+            self.k_B = None
+            self.k_E = self.pField.toElementArray(self.size, self.pField.getZERO())
+            return False
+        verdict = True
+        if not self.A.expMul(self.v, self.Ap).equals(self.g.exp(self.k_A).mul(self.h.expProd(self.k_E))):
+            verdict = False
+        if verdict and not self.B.expMul(self.v, self.Bp).equals(
+                self.pkey.exp(self.k_B.neg()).mul(self.wp.expProd(self.k_E))):
+            verdict = False
+        return verdict
+
+    def free(self) -> None:
+        _free(self.e, self.ipe, self.epsilon, self.k_E)
+        self.e = self.ipe = self.epsilon = self.k_E = None
+
+
+# ====================================================================== Fiat-Shamir wrappers
+class PoSTW:
+    """hvzk/PoSTW.java:52 with the bulletin board replaced by byte strings: `prove` returns the
+    three published messages, `verify` consumes them (what vmnv reads from the proof directory:
+    PermutationCommitment, PoSCommitment, PoSReply; hvzk/PoSTW.java:281-307)."""
+
+    def __init__(self, vbitlen, ebitlen, rbitlen, prg: PRGHeuristic, randomSource, challenger: ChallengerRO):
+        self.vbitlen, self.ebitlen, self.rbitlen = vbitlen, ebitlen, rbitlen
+        self.prg, self.randomSource, self.challenger = prg, randomSource, challenger
+        self.P = self.V = None
+
+    # -- :80-88 / :167-173
+    def precompute(self, g, h, pi: Optional[Permutation] = None) -> None:
+        basic = PoSBasicTW(self.vbitlen, self.ebitlen, self.rbitlen, self.prg, self.randomSource)
+        basic.precompute(g, h, pi)
+        if pi is None:
+            self.V = basic
+        else:
+            self.P = basic
+
+    def _seed(self, B: PoSBasicTW, pkey, w, wp) -> bytes:
+        challengeData = ByteTreeContainer(B.g.toByteTree(), B.h.toByteTree(), B.u.toByteTree(), pkey.toByteTree(),
+                                          w.toByteTree(), wp.toByteTree())                      # :118-124
+        return self.challenger.challenge(challengeData, 8 * self.prg.minNoSeedBytes(), self.rbitlen)
+
+    # -- :95-165
+    def prove(self, pkey, w, wp, s):
+        P = self.P
+        P.setInstance(pkey, w, wp, s)
+        permutationCommitment = P.u.toByteTree().to_bytes()
+        prgSeed = self._seed(P, pkey, w, wp)
+        commitment = P.commit(prgSeed)
+        challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitment)                    # :146-147
+        challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
+        reply = P.reply(_to_positive(challengeBytes))
+        out = (permutationCommitment, commitment.to_bytes(), reply.to_bytes())
+        P.free()
+        return out
+
+    # -- :177-260
+    def verify(self, pkey, w, wp, permutationCommitment: bytes, commitment: bytes, reply: bytes) -> bool:
+        V = self.V
+        V.setInstance(pkey, w, wp)
+        try:
+            V.setPermutationCommitment(ByteTreeReader(permutationCommitment))
+        except EIOException:
+            V.u = V.h.copyOfRange(0, V.h.size())
+        prgSeed = self._seed(V, pkey, w, wp)
+        V.setBatchVector(prgSeed)
+        V.computeAF()
+        try:
+            commitmentTree = V.setCommitment(ByteTreeReader(commitment))
+        except EIOException:
+            commitmentTree = V.setCommitment(ByteTreeReader(ByteTreeContainer().to_bytes()))
+        challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitmentTree)
+        challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
+        V.setChallenge(_to_positive(challengeBytes))
+        try:
+            verdict = V.verify(ByteTreeReader(reply))
+        except EIOException:
+            verdict = False
+        return verdict
+
+    def free(self) -> None:
+        for b in (self.P, self.V):
+            if b is not None:
+                b.free()
