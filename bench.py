@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- ciphertexts/s of re-encryption + proof of shuffle (prove and verify) on B200.
+
+One step = one pass of the hot path over one batch of N synthetic ciphertexts (3072-bit
+ModPGroup, width 1): El Gamal re-encryption + permutation, PoSBasicTW commit/reply, and
+PoSBasicTW verification of that proof.
+
+  value  device-timed (CUDA events on the engine's stream, max over ranks): inputs, proof arrays
+         and challenges resident in HBM; protocol through PoSBasicTW with given seed/challenge
+         (what hvzk/TestPoSCBasicTW.java drives), no byte-tree traffic.
+  e2e    the same work through the public API a mix-server calls (mixnet.ShufflerSession:
+         shuffle -> ShuffleProof bytes -> verify) with HOST byte buffers: byte-tree
+         encode/decode, H2D/D2H copies and the Fiat-Shamir SHA-256 hashing are inside the timed
+         region.
+  roofline  IMAD-pipe modmul roofline of the dominant kernel (fixed-base exponentiation).
+  cpu_baseline  the oracle's GMP-backed C restatement on the host cores (bounded sample).
+
+`--impl reference` times that CPU restatement alone (the reference is Java + GMP natives; no JVM
+exists in this image) on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# measured on B200 by scratch/ubench.cu (profiles/r01_ubench_imad.txt): IMAD.WIDE.U32 issues at
+# 0.99 warp-instr/clk/SM -> 32 MAC/clk/SM * 148 SM * 1.965 GHz
+IMAD_PEAK_MAC_PER_S = 9.26e12
+
+
+def macs_per_modmul(bits: int) -> int:
+    n = bits // 32
+    return 2 * n * n + n
+
+
+def nominal_modmuls_per_ciphertext(bits: int, n: int, n_e=256, n_v=256, n_r=100):
+    """SURVEY.md §8d textbook costs: FIX(L)=ceil(L/8), VAR(L)=L+ceil(L/6), MEXP(L)=min_c ceil(L/c)(1+2^(c+1)/N)."""
+    Lq = bits - 1
+    fix = lambda L: -(-L // 8)
+    var = lambda L: L + -(-L // 6)
+    mexp = lambda L: min(-(-L // c) * (1 + 2 ** (c + 1) / n) for c in range(1, 24))
+    eps = n_e + n_v + n_r
+    reenc = 2 * fix(Lq) + 2
+    prove = 5 * fix(Lq) + 3 * mexp(eps) + 4
+    verify = 3 * mexp(n_e) + 3 * mexp(eps + 1) + var(n_v) + var(eps + 1) + fix(Lq) + 4
+    return {"reencrypt": reenc, "prove": prove, "verify": verify, "total": reenc + prove + verify}
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = threading.Event()
+        self.sm_max = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.sm_max = float(f[1])
+                for nm, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+def run_reference(args):
+    """The reference arm: the oracle's CPU restatement (GMP) on the host cores."""
+    from oracle import cpu_baseline
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_baseline.run(bits=args.bits, n_total=args.n, sample=args.cpu_sample, steps=args.steps,
+                           warmup=min(args.warmup, 1))
+    line = {"metric": "ciphertexts/s: re-encrypt+PoS prove+verify, %d-bit ModPGroup" % args.bits, "impl": "reference",
+            "value": res["value"], "unit": "ciphertexts/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 limbs (exact integer)", "data": "synthetic",
+            "config": config_dict(args),
+            "cpu_baseline": {"value": res["value"], "unit": "ciphertexts/s", "cores": res["cores"], "kind": "port",
+                             "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": "ciphertexts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def config_dict(args):
+    return {"workload": "ModPGroup %d-bit (RFC 3526), width 1, N=%d ciphertexts per GPU: re-encrypt + PoSBasicTW "
+                        "prove + verify" % (args.bits, args.n),
+            "bits": args.bits, "width": 1, "n_per_gpu": args.n, "ebitlen": 256, "vbitlen": 256, "rbitlen": 100,
+            "l2": "working set (N x %d B per array, >10 arrays) exceeds the 126 MB L2" % (args.bits // 8)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="vmx", choices=["vmx", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("VMX_BENCH_N", "100000")))
+    ap.add_argument("--bits", type=int, default=3072)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="ciphertexts in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--phases", action="store_true", help="print per-phase device times to stderr")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    vmx = importlib.import_module("verificatum-vmn_b200")
+    A = vmx.arithm
+    hvzk = importlib.import_module("verificatum-vmn_b200.hvzk")
+    mixnet = importlib.import_module("verificatum-vmn_b200.mixnet")
+    groups = importlib.import_module("verificatum-vmn_b200.groups")
+    crypto = vmx.crypto
+
+    p, q, g = groups.rfc3526(args.bits)
+    G = A.ModPGroup(p, q, g, device=local_rank)
+    stream = torch.cuda.ExternalStream(G._lib.vmx_ctx_stream(G.ctx), device=torch.device("cuda", local_rank))
+    n = args.n
+
+    def prg(label: str):
+        r = crypto.PRGHeuristic()
+        r.setSeed(crypto.HashfunctionHeuristic("SHA-256").hash(("vmx-bench/%s/rank%d" % (label, rank)).encode()))
+        return r
+
+    # ---- synthetic inputs, resident in HBM
+    setup_rs = prg("setup")
+    x = G.getPRing().randomElement(setup_rs, 100)
+    y = G.getg().exp(x)
+    pk = A.PPGroup(G, 2).product(G.getg(), y)
+    ciphertexts = mixnet.demoCiphertexts(pk, n, setup_rs)
+    params = mixnet.SessionParams(pGroupString="ModPGroup(RFC3526-%d)" % args.bits)
+    session = mixnet.ShufflerSession(G, pk, params, prg("prover"))
+    generators = session.deriveGenerators(n)
+    seed = bytes(range(32))
+    challenge = int.from_bytes(crypto.HashfunctionHeuristic("SHA-256").hash(b"challenge"), "big")
+    G.sync()
+
+    phase_ms = {}
+
+    class Phase:
+        def __init__(self, name):
+            self.name = name
+
+        def __enter__(self):
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(stream)
+
+        def __exit__(self, *a):
+            self.e1.record(stream)
+            self.e1.synchronize()
+            phase_ms[self.name] = phase_ms.get(self.name, 0.0) + self.e0.elapsed_time(self.e1)
+
+    def step_device(i: int, timed: bool):
+        """Re-encrypt + prove + verify with everything resident on the device."""
+        rs = prg("step%d" % i)
+        P = hvzk.PoSBasicTW(params.vbitlenro, params.ebitlenro, params.rbitlen, crypto.PRGHeuristic(), rs)
+        V = hvzk.PoSBasicTW(params.vbitlenro, params.ebitlenro, params.rbitlen, crypto.PRGHeuristic(), rs)
+        ph = Phase if (timed and args.phases) else (lambda name: _Null())
+        with ph("reencrypt"):
+            s = G.getPRing().randomElementArray(n, rs, params.rbitlen)
+            factors = pk.exp(s)
+            pi = A.Permutation.random(n, rs, params.rbitlen)
+            reenc = ciphertexts.mul(factors)
+            factors.free()
+            inv = pi.inv()
+            out = reenc.permute(inv)
+            reenc.free()
+        with ph("prove.precompute"):
+            P.precompute(G.getg(), generators, pi)
+        with ph("prove.commit"):
+            P.setInstance(pk, ciphertexts, out, s)
+            P.commit(seed)
+        with ph("prove.reply"):
+            P.reply(challenge)
+        with ph("verify.computeAF"):
+            V.precompute(G.getg(), generators)
+            V.setInstance(pk, ciphertexts, out)
+            V.u = P.u
+            V.setBatchVector(seed)
+            V.computeAF()
+        with ph("verify.checks"):
+            V.B, V.Ap, V.Bp, V.Cp, V.Dp, V.Fp = P.B, P.Ap, P.Bp, P.Cp, P.Dp, P.Fp
+            V.setChallenge(challenge)
+            V.k_A, V.k_B, V.k_C, V.k_D, V.k_E, V.k_F = P.k_A, P.k_B, P.k_C, P.k_D, P.k_E, P.k_F
+            ok = V.verifyParsed()
+        if not ok:
+            raise SystemExit("bench: the verifier rejected an honest proof: %r" % (V.verdicts,))
+        V.e.free()
+        V.u = V.e = V.B = V.Bp = V.k_B = V.k_E = None
+        P.free()
+        s.free()
+        out.free()
+
+    class _Null:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for i in range(args.warmup):
+        step_device(i, False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    launches0, modmuls0 = G.launch_count(), G.modmul_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    t_host0 = time.time()
+    e0.record(stream)
+    for i in range(args.steps):
+        step_device(args.warmup + i, True)
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    t_host = time.time() - t_host0
+    dev_ms = e0.elapsed_time(e1)
+    launches = G.launch_count() - launches0
+    modmuls = G.modmul_count() - modmuls0
+    sampler.stop_flag.set()
+    sampler.join()
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (fixed-base exponentiation), timed live
+    roof = None
+    if rank == 0:
+        rs = prg("roofline")
+        e = G.getPRing().randomElementArray(n, rs, params.rbitlen)
+        tmp = G.getg().exp(e)
+        tmp.free()
+        mm0 = G.modmul_count()
+        r0 = torch.cuda.Event(enable_timing=True)
+        r1 = torch.cuda.Event(enable_timing=True)
+        reps = 3
+        r0.record(stream)
+        for _ in range(reps):
+            tmp = G.getg().exp(e)
+            tmp.free()
+        r1.record(stream)
+        r1.synchronize()
+        k_ms = r0.elapsed_time(r1) / reps
+        k_modmuls = (G.modmul_count() - mm0) / reps
+        e.free()
+        macs = macs_per_modmul(args.bits)
+        achieved = k_modmuls * macs / (k_ms * 1e-3)
+        roof = {"bound": "imad", "kernel": "k_exp_fixed<%d>" % (args.bits // 32), "achieved": achieved / 1e12,
+                "peak": IMAD_PEAK_MAC_PER_S / 1e12, "unit": "TMAC/s (32x32+64 IMAD.WIDE)", "frac": achieved / IMAD_PEAK_MAC_PER_S,
+                "traffic": None, "modmuls_per_launch": k_modmuls, "ms_per_launch": k_ms,
+                "peak_source": "measured on B200 (profiles/r01_ubench_imad.txt); MEASURED_PEAKS.json has no integer peak",
+                "hbm_note": "integer-pipe bound: arithmetic intensity ~1e4 MAC/B, HBM is not the limiter"}
+
+    # ---- end to end through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        G.membership_check = os.environ.get("VMX_BENCH_MEMBERSHIP", "0") == "1"
+        ciph_bytes = ciphertexts.toByteTree().to_bytes()
+        pinned = torch.empty(len(ciph_bytes), dtype=torch.uint8).pin_memory()
+        pinned.numpy()[:] = np.frombuffer(ciph_bytes, dtype=np.uint8)
+        h2d = d2h = 0
+
+        def step_e2e(i: int):
+            nonlocal h2d, d2h
+            prover = mixnet.ShufflerSession(G, pk, params, prg("e2e%d" % i))
+            verifier = mixnet.ShufflerSession(G, pk, params, prg("e2ev%d" % i))
+            ciphPGroup = mixnet.getCiphPGroup(G, 1)
+            w = ciphPGroup.toElementArray(n, vmx.eio.ByteTreeReader(memoryview(pinned.numpy())))
+            proof, _ = prover.shuffle(1, w, generators=generators)
+            ok, out = verifier.verify(1, w, proof, generators=generators)
+            if not ok:
+                raise SystemExit("bench e2e: verifier rejected an honest proof")
+            out.free()
+            w.free()
+            h2d = len(ciph_bytes) + len(proof.output) + len(proof.permutationCommitment) + len(proof.commitment) + \
+                len(proof.reply)
+            d2h = len(proof.output) + len(proof.permutationCommitment) + len(proof.commitment) + len(proof.reply)
+
+        step_e2e(0)
+        barrier()
+        t0 = time.time()
+        k = max(1, min(args.steps, 2))
+        for i in range(k):
+            step_e2e(1 + i)
+        barrier()
+        dt = (time.time() - t0) / k
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n / float(tt.item()), "unit": "ciphertexts/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": float(tt.item()) * 1e3,
+               "includes": "byte-tree decode/encode, H2D/D2H, Fiat-Shamir SHA-256 on the host",
+               "membership_check_on_import": bool(G.membership_check)}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            from oracle import cpu_baseline
+            res = cpu_baseline.run(bits=args.bits, n_total=n, sample=args.cpu_sample, steps=1, warmup=0)
+            cpu = {"value": res["value"], "unit": "ciphertexts/s", "cores": res["cores"], "kind": "port",
+                   "sample": res["sample"]}
+        except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
+            cpu = {"value": None, "unit": "ciphertexts/s", "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
+
+    if rank == 0:
+        nominal = nominal_modmuls_per_ciphertext(args.bits, n)
+        macs = macs_per_modmul(args.bits)
+        line = {"metric": "ciphertexts/s: re-encrypt+PoS prove+verify, %d-bit ModPGroup" % args.bits,
+                "value": value, "unit": "ciphertexts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32 limbs (exact integer)", "data": "synthetic", "config": config_dict(args),
+                "clocks": sampler.summary(), "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
+                "cpu_baseline": cpu,
+                "modmul": {"nominal_per_ciphertext": nominal["total"], "executed_per_ciphertext": modmuls / (args.steps * n),
+                           "nominal_modmul_per_s": value * nominal["total"] / world,
+                           "nominal_frac_of_imad_peak": value / world * nominal["total"] * macs / IMAD_PEAK_MAC_PER_S,
+                           "executed_frac_of_imad_peak": modmuls * macs / (dev_ms * 1e-3) / IMAD_PEAK_MAC_PER_S},
+                "host_wall_ms_per_step": t_host * 1e3 / args.steps}
+        if args.phases:
+            line["phase_ms_per_step"] = {k: v / args.steps for k, v in phase_ms.items()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

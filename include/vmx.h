@@ -76,6 +76,11 @@ int vmx_garr_from_bytes(vmx_ctx* ctx, size_t n, const uint8_t* be, int check_mem
  * element i = (t_i mod p)^((p-1)/q), t_i = the i-th `width`-byte big-endian integer masked to
  * `bitlen` bits.  The bytes come from the caller's PRG; reduction and cofactor power run here. */
 int vmx_garr_from_raw(vmx_ctx* ctx, size_t n, const uint8_t* be, size_t width, unsigned bitlen, vmx_garr** out);
+/* The same with the bytes drawn on the device from PRGHeuristic(SHA-256) seeded with `seed`
+ * (from stream byte `offset`): IndependentGeneratorsRO.generate (distr/IndependentGeneratorsRO.java:110-130;
+ * mixnet/ShufflerElGamalSession.java:384; mixnet/MixNetElGamalVerifyFiatShamirSession.java:556-566). */
+int vmx_garr_prg_sha256(vmx_ctx* ctx, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t n, size_t width,
+                        unsigned bitlen, vmx_garr** out);
 /* PGroupElementArray.toByteTree() payload (hvzk/PoSBasicTW.java:694-699). */
 int vmx_garr_to_bytes(const vmx_garr* a, uint8_t* be_out);
 /* PGroup.toElementArray(size, PGroupElement): n copies of one element (hvzk/PoSBasicTW.java:805). */
@@ -137,7 +142,12 @@ int vmx_rarr_from_raw(vmx_ctx* ctx, size_t n, const uint8_t* be, size_t width, u
 /* PRG-derived batching vector: prg.setSeed(seed); LargeIntegerArray.random(n, bitlen, prg)
  * with PRGHeuristic(SHA-256) (hvzk/PoSBasicTW.java:533-538; same in PoSCBasicTW.java:350-355,
  * CCPoSBasicW.java:330-335, elgamal/DistrElGamalSessionBasic.java:513-518). */
-int vmx_rarr_prg_sha256(vmx_ctx* ctx, const uint8_t* seed, size_t seedlen, size_t n, unsigned bitlen, vmx_rarr** out);
+int vmx_rarr_prg_sha256(vmx_ctx* ctx, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t n, unsigned bitlen,
+                        vmx_rarr** out);
+/* pRing.randomElementArray(size, prg, statDist) with a PRGHeuristic(SHA-256) source at stream byte `offset`:
+ * element i = (i-th `width`-byte integer masked to `bitlen` bits) mod q, bytes drawn on the device. */
+int vmx_rarr_prg_raw_sha256(vmx_ctx* ctx, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t n,
+                            size_t width, unsigned bitlen, vmx_rarr** out);
 int vmx_rarr_to_bytes(const vmx_rarr* a, uint8_t* be_out);
 int vmx_rarr_fill(vmx_ctx* ctx, size_t n, const uint8_t* elem_be, vmx_rarr** out);
 void vmx_rarr_free(vmx_rarr* a);
@@ -174,6 +184,12 @@ uint64_t vmx_ctx_modmul_count(const vmx_ctx* ctx);
 /* Raw batched Montgomery multiplication benchmark kernel: out[i] = a[i]*b[i]^iters (same code
  * path as every exponentiation); returns elapsed device ms through *ms. */
 int vmx_bench_modmul(vmx_ctx* ctx, size_t n, int iters, float* ms);
+
+/* Self test: a[i]*b[i] through the thread-per-element and the warp-cooperative multiplier must
+ * agree word for word (*equal = 1). */
+int vmx_selftest_coop(const vmx_garr* a, const vmx_garr* b, int* equal);
+/* Test hook: out[i] = a[i]*b[i] computed by the warp-cooperative multiplier. */
+int vmx_debug_coop_mul(const vmx_garr* a, const vmx_garr* b, vmx_garr** out);
 
 #ifdef __cplusplus
 }

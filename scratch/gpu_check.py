@@ -140,3 +140,21 @@ for bits in (2048, 3072):
         nl = bits // 32
         print(bits, "bench_modmul iters", it, ms.value, "ms", 148*256*4*it/(ms.value*1e-3), "modmul/s", 148*256*4*it/(ms.value*1e-3)*(2*nl*nl+nl)/9.26e12, "of IMAD peak")
 print("ALL OK")
+# cooperative multiplier self test on every size
+import ctypes as C
+for bits, (p_, q_, g_) in (("512", vmx.arithm and importlib.import_module("verificatum-vmn_b200.groups").test512()),
+                           ("2048", importlib.import_module("verificatum-vmn_b200.groups").rfc3526(2048)),
+                           ("3072", importlib.import_module("verificatum-vmn_b200.groups").rfc3526(3072))):
+    G = A.ModPGroup(p_, q_, g_); R = G.getPRing()
+    rs = cr.PRGHeuristic(); rs.setSeed(bytes(range(32)))
+    X1 = G.randomElementArray(5000, rs, 100); X2 = G.randomElementArray(5000, rs, 100)
+    eq = C.c_int()
+    vmx._native.check(vmx._native.load().vmx_selftest_coop(X1.h, X2.h, C.byref(eq)))
+    print(bits, "coop selftest equal =", eq.value); assert eq.value == 1
+    # edge: p-1 squared
+    E1 = G.toElementArray([A.PGroupElement(G, p_-1), A.PGroupElement(G, 1), A.PGroupElement(G, p_-2)])
+    vmx._native.check(vmx._native.load().vmx_selftest_coop(E1.h, E1.h, C.byref(eq))); assert eq.value == 1
+    t0=time.time(); y = G.getg().exp(R.toElement(q_-5)); t1=time.time()
+    assert y.value == pow(g_, q_-5, p_); print(bits, "single exp ok", t1-t0)
+    t0=time.time(); yi = y.inv(); t1=time.time(); assert yi.value == pow(y.value, -1, p_); print(bits, "single inv ok", t1-t0)
+print("COOP OK")

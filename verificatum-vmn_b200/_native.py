@@ -45,6 +45,8 @@ SIGNATURES = {
     "vmx_ctx_set_fixed_window": (C.c_int, [_P, C.c_int]),
     "vmx_garr_from_bytes": (C.c_int, [_P, _SZ, _P, C.c_int, _PP]),
     "vmx_garr_from_raw": (C.c_int, [_P, _SZ, _P, _SZ, C.c_uint, _PP]),
+    "vmx_garr_prg_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, _SZ, C.c_uint, _PP]),
+    "vmx_rarr_prg_raw_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, _SZ, C.c_uint, _PP]),
     "vmx_garr_to_bytes": (C.c_int, [_P, _P]),
     "vmx_garr_fill": (C.c_int, [_P, _SZ, _U8, _PP]),
     "vmx_garr_free": (None, [_P]),
@@ -66,7 +68,7 @@ SIGNATURES = {
     "vmx_get": (C.c_int, [_P, _SZ, _P]),
     "vmx_rarr_from_bytes": (C.c_int, [_P, _SZ, _P, _PP]),
     "vmx_rarr_from_raw": (C.c_int, [_P, _SZ, _P, _SZ, C.c_uint, _PP]),
-    "vmx_rarr_prg_sha256": (C.c_int, [_P, _U8, _SZ, _SZ, C.c_uint, _PP]),
+    "vmx_rarr_prg_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, C.c_uint, _PP]),
     "vmx_rarr_to_bytes": (C.c_int, [_P, _P]),
     "vmx_rarr_fill": (C.c_int, [_P, _SZ, _U8, _PP]),
     "vmx_rarr_free": (None, [_P]),
@@ -89,6 +91,8 @@ SIGNATURES = {
     "vmx_requals": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
     "vmx_ctx_launch_count": (C.c_uint64, [_P]),
     "vmx_ctx_modmul_count": (C.c_uint64, [_P]),
+    "vmx_selftest_coop": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
+    "vmx_debug_coop_mul": (C.c_int, [_P, _P, _PP]),
     "vmx_bench_modmul": (C.c_int, [_P, _SZ, C.c_int, C.POINTER(C.c_float)]),
 }
 

@@ -46,6 +46,25 @@ def _be(x: int, width: int) -> bytes:
     return x.to_bytes(width, "big")
 
 
+def _sha256_prg_offset(rs) -> Optional[int]:
+    """Stream offset (bytes consumed so far) if `rs` is a PRGHeuristic(SHA-256): its expansion can
+    then run on the device (counter mode) and the host object only accounts for the bytes; None
+    for any other random source (its bytes are handed over)."""
+    from .crypto import PRGHeuristic
+    if isinstance(rs, PRGHeuristic) and rs.hf.name == "SHA-256" and rs.seed is not None and 32 <= len(rs.seed) <= 48:
+        return rs.counter * 32 - len(rs.buf)
+    return None
+
+
+def _advance_prg(rs, offset: int) -> None:
+    """Put the host-side PRG object at stream byte `offset`."""
+    full, rem = divmod(offset, 32)
+    rs.counter = full
+    rs.buf = bytearray()
+    if rem:
+        rs.getBytes(rem)
+
+
 def _jacobi(a: int, n: int) -> int:
     """Jacobi symbol (a|n), n odd positive (LargeInteger.legendre for prime n)."""
     a %= n
@@ -77,12 +96,16 @@ class Permutation:
         """Sort-based sampling: `size` integers of ceil(log2 size)+statDist bits, stable argsort."""
         bits = max(1, (size - 1).bit_length()) + statDist
         nbytes = (bits + 7) // 8
-        raw = np.frombuffer(randomSource.getBytes(size * nbytes), dtype=np.uint8).reshape(size, nbytes).copy()
-        raw[:, 0] &= 0xFF >> ((8 - bits % 8) % 8)
-        keys = [bytes(r) for r in raw]
-        order = sorted(range(size), key=lambda i: (keys[i], i))
+        raw = np.frombuffer(randomSource.getBytes(size * nbytes), dtype=np.uint8).reshape(size, nbytes)
+        # big-endian keys as columns of 64-bit words, most significant first; stable lexicographic sort
+        pad = (-nbytes) % 8
+        m = np.zeros((size, nbytes + pad), dtype=np.uint8)
+        m[:, pad:] = raw
+        m[:, pad] &= 0xFF >> ((8 - bits % 8) % 8)
+        cols = m.view(">u8")
+        order = np.lexsort([cols[:, j] for j in range(cols.shape[1] - 1, -1, -1)])
         table = np.empty(size, dtype=np.uint32)
-        table[np.asarray(order, dtype=np.int64)] = np.arange(size, dtype=np.uint32)
+        table[order] = np.arange(size, dtype=np.uint32)
         return Permutation(table)
 
     def size(self) -> int:
@@ -98,6 +121,31 @@ class Permutation:
 
     def free(self) -> None:
         pass
+
+
+class ByteTreeDeviceArray(ByteTreeBasic):
+    """toByteTree() of a device array: the D2H copy happens when the tree is first streamed
+    (into a digest or a file), once, and is cached.  The array must still be alive then."""
+
+    def __init__(self, arr):
+        self.arr = arr
+        self._leafs = None
+        self._n = arr.size()
+        self._w = arr.getPGroup().elem_bytes if hasattr(arr, "getPGroup") else arr.ring.byte_len
+
+    def _materialise(self) -> ByteTreeLeafArray:
+        if self._leafs is None:
+            if self.arr.h is None:
+                raise ArithmError("byte tree of a freed array")
+            self._leafs = ByteTreeLeafArray(self.arr.to_matrix())
+            self.arr = None
+        return self._leafs
+
+    def update(self, digest) -> None:
+        self._materialise().update(digest)
+
+    def total_bytes(self) -> int:
+        return 5 + self._n * (5 + self._w)
 
 
 # ====================================================================== rings
@@ -142,6 +190,13 @@ class PField(PRing):
     def randomElementArray(self, size: int, randomSource, statDist: int) -> "PRingElementArray":
         bits = self.order.bit_length() + statDist
         width = (bits + 7) // 8
+        off = _sha256_prg_offset(randomSource)
+        if off is not None:
+            h = C.c_void_p()
+            nat.check(nat.load().vmx_rarr_prg_raw_sha256(self.group.ctx, randomSource.seed, len(randomSource.seed),
+                                                         off, size, width, bits, C.byref(h)))
+            _advance_prg(randomSource, off + size * width)
+            return PRingElementArray(self, h)
         raw = np.frombuffer(randomSource.getBytes(size * width), dtype=np.uint8)
         return self._from_raw(size, raw, width, bits)
 
@@ -342,7 +397,7 @@ class PRingElementArray:
         return m
 
     def toByteTree(self) -> ByteTreeBasic:
-        return ByteTreeLeafArray(self.to_matrix())
+        return ByteTreeDeviceArray(self)
 
     def elements(self) -> List[PFieldElement]:
         return [PFieldElement(self.ring, int.from_bytes(r.tobytes(), "big")) for r in self.to_matrix()]
@@ -366,20 +421,14 @@ class LargeIntegerArray:
 
         With a PRGHeuristic(SHA-256) source the expansion runs on the device (counter mode);
         any other source hands its bytes over."""
-        from .crypto import PRGHeuristic
         lib = nat.load()
         h = C.c_void_p()
         width = (bitLength + 7) // 8
-        if (isinstance(randomSource, PRGHeuristic) and randomSource.hf.name == "SHA-256"
-                and randomSource.counter == 0 and not randomSource.buf and bitLength < field.order.bit_length()):
-            nat.check(lib.vmx_rarr_prg_sha256(field.group.ctx, randomSource.seed, len(randomSource.seed), size,
+        off = _sha256_prg_offset(randomSource)
+        if off is not None and bitLength < field.order.bit_length():
+            nat.check(lib.vmx_rarr_prg_sha256(field.group.ctx, randomSource.seed, len(randomSource.seed), off, size,
                                               bitLength, C.byref(h)))
-            # keep the host-side PRG state consistent with the bytes consumed on the device
-            full, rem = divmod(size * width, 32)
-            randomSource.counter = full
-            randomSource.buf = bytearray()
-            if rem:
-                randomSource.getBytes(rem)
+            _advance_prg(randomSource, off + size * width)
             return LargeIntegerArray(field, h)
         raw = np.frombuffer(randomSource.getBytes(size * width), dtype=np.uint8)
         nat.check(lib.vmx_rarr_from_raw(field.group.ctx, size, _ptr(raw), width, bitLength, C.byref(h)))
@@ -419,6 +468,9 @@ class ModPGroup(PGroup):
     def __del__(self):
         # arrays keep a reference to their group, so the context outlives every handle
         try:
+            import sys
+            if sys.is_finalizing():
+                return  # interpreter teardown order is arbitrary; the process exit frees the device
             if self.ctx is not None:
                 self._lib.vmx_ctx_destroy(self.ctx)
                 self.ctx = None
@@ -477,9 +529,14 @@ class ModPGroup(PGroup):
         return PGroupElement(self, v)
 
     # -- arrays
-    def toElementArray(self, *args, check_membership: bool = True) -> "PGroupElementArray":
+    # import-time subgroup check of untrusted arrays (PGroup.toElementArray in VCR always checks)
+    membership_check = True
+
+    def toElementArray(self, *args, check_membership: Optional[bool] = None) -> "PGroupElementArray":
         """(size, ByteTreeReader) | (size, PGroupElement) | (list of PGroupElement)."""
         lib = self._lib
+        if check_membership is None:
+            check_membership = self.membership_check
         h = C.c_void_p()
         if len(args) == 1:
             vals = [e.value for e in args[0]]
@@ -508,8 +565,14 @@ class ModPGroup(PGroup):
         on the device."""
         bits = self.p.bit_length() + statDist
         width = (bits + 7) // 8
-        raw = np.frombuffer(randomSource.getBytes(size * width), dtype=np.uint8)
         h = C.c_void_p()
+        off = _sha256_prg_offset(randomSource)
+        if off is not None:
+            nat.check(self._lib.vmx_garr_prg_sha256(self.ctx, randomSource.seed, len(randomSource.seed), off, size,
+                                                    width, bits, C.byref(h)))
+            _advance_prg(randomSource, off + size * width)
+            return PGroupElementArray(self, h)
+        raw = np.frombuffer(randomSource.getBytes(size * width), dtype=np.uint8)
         nat.check(self._lib.vmx_garr_from_raw(self.ctx, size, _ptr(raw), width, bits, C.byref(h)))
         return PGroupElementArray(self, h)
 
@@ -715,7 +778,7 @@ class PGroupElementArray:
         return m
 
     def toByteTree(self) -> ByteTreeBasic:
-        return ByteTreeLeafArray(self.to_matrix())
+        return ByteTreeDeviceArray(self)
 
     def elements(self) -> List[PGroupElement]:
         return [PGroupElement(self.group, int.from_bytes(r.tobytes(), "big")) for r in self.to_matrix()]
@@ -863,7 +926,7 @@ class PPGroup(PGroup):
             raise ArithmFormatException(nat.VMX_EFORMAT, "product element of wrong arity")
         return PPGroupElement(self, [f.toElement(btr.getNextChild()) for f in self.factors])
 
-    def toElementArray(self, size: int, src, check_membership: bool = True):
+    def toElementArray(self, size: int, src, check_membership: Optional[bool] = None):
         if isinstance(src, ByteTreeReader):
             if src.isLeaf() or src.getRemaining() != len(self.factors):
                 raise ArithmFormatException(nat.VMX_EFORMAT, "product array of wrong arity")

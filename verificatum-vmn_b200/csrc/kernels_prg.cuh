@@ -66,14 +66,14 @@ __device__ inline void sha256_seed_ctr(const PrgSeed& s, uint32_t counter, uint3
   h[4] = 0x510e527f + e; h[5] = 0x9b05688c + f; h[6] = 0x1f83d9ab + g; h[7] = 0x5be0cd19 + hh;
 }
 
-// element i = stream bytes [i*w, (i+1)*w) as a big-endian integer mod 2^bitlen, w = ceil(bitlen/8).
+// element i = stream bytes [offset + i*w, offset + (i+1)*w) as a big-endian integer mod 2^bitlen, w = ceil(bitlen/8).
 template <int N>
-__global__ void k_prg_expand(const __grid_constant__ PrgSeed seed, size_t n, int bitlen, uint32_t* __restrict__ out,
-                             size_t cap) {
+__global__ void k_prg_expand(const __grid_constant__ PrgSeed seed, size_t offset, size_t n, int bitlen,
+                             uint32_t* __restrict__ out, size_t cap) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int w = (bitlen + 7) / 8;
-  const size_t first = i * (size_t)w;       // first stream byte (most significant)
+  const size_t first = offset + i * (size_t)w;  // first stream byte (most significant)
   uint32_t limb[N];
 #pragma unroll
   for (int j = 0; j < N; j++) limb[j] = 0;
@@ -92,6 +92,21 @@ __global__ void k_prg_expand(const __grid_constant__ PrgSeed seed, size_t n, int
     limb[le >> 2] |= byte << (8 * (le & 3));
   }
   store_elem<N>(limb, out, cap, i);
+}
+
+// raw PRG stream: block first_block + t = SHA-256(seed || be32(first_block + t)) -> out[32t .. 32t+32)
+__global__ void k_prg_bytes(const __grid_constant__ PrgSeed seed, size_t first_block, size_t nblocks,
+                            uint8_t* __restrict__ out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nblocks) return;
+  uint32_t h[8];
+  sha256_seed_ctr(seed, (uint32_t)(first_block + t), h);
+  uint32_t* o = reinterpret_cast<uint32_t*>(out + 32 * t);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t v = h[i];
+    o[i] = (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24);
+  }
 }
 
 }  // namespace vmx

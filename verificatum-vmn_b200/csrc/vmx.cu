@@ -2,6 +2,7 @@
 // orchestration (window tables, Pippenger plan, segmented products, scans) and accounting.
 // All arithmetic runs in the sm_100a kernels of kernels_*.cuh; there is no CPU path.
 #include "vmx_internal.cuh"
+#include "coop.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -249,6 +250,7 @@ static int upload_consts(vmx_ctx* c, Modulus& Mod) {
   image_put(img, 4, 0, r2.data(), N);
   image_put(img, 4, 1, r.data(), N);
   image_put(img, 4, 2, one.data(), N);
+  image_put(img, 4, 3, Mod.n, N);  // the modulus itself (cooperative kernels read their lane's limbs)
   void* p = nullptr;
   VMX_CU(cudaMallocAsync(&p, img.size() * 4, c->stream));
   Mod.consts = (uint32_t*)p;
@@ -349,7 +351,11 @@ static int build_table(vmx_ctx* c, const uint32_t* base, size_t bcap, int w, Fix
   const int qlen = T.nwin * w;
   ElemBuf Q;
   VMX_TRY(Q.alloc_elems(c, qlen));
+#ifndef VMX_HOST_EMUL
+  VMX_LAUNCH(c, k_coop_sqr_chain<N>, 1, 32, 0, base, bcap, (size_t)0, Q.d(), Q.cap, qlen, c->P.consts, M.n0inv);
+#else
   VMX_LAUNCH(c, k_sqr_chain<N>, 1, 32, N * 4, base, bcap, (size_t)0, Q.d(), Q.cap, qlen, M);
+#endif
   VMX_CHECK_LAUNCH();
   c->modmuls += qlen;
   for (int j = 0; j < w; j++) {
@@ -395,7 +401,8 @@ static int exp_fixed_run(vmx_ctx* c, const FixedTable& T, const vmx_rarr* e, int
     double best_eff = 0;
     for (int p = 1; p <= 64 && p * 4 <= nwin; p++) {
       const double waves = (double)n * p / wave;
-      const double time = std::ceil(waves) * ((double)nwin / p) + (p > 1 ? std::ceil((double)n / wave) * p : 0);
+      // the combine runs on the warp-cooperative multiplier (~10x lower latency, ~7000 warps in flight)
+      const double time = std::ceil(waves) * ((double)nwin / p) + (p > 1 ? std::ceil((double)n / 7000.0) * 0.1 * p : 0);
       const double eff = ((double)n * nwin / wave) / time;                 // useful / spent
       if (eff > best_eff * 1.02) { best_eff = eff; parts = p; }
     }
@@ -411,13 +418,19 @@ static int exp_fixed_run(vmx_ctx* c, const FixedTable& T, const vmx_rarr* e, int
   VMX_LAUNCH(c, k_exp_fixed<N>, nblocks(n * parts), kThreads, 0, T.d, T.cap, T.w, nwin, e->d, e->cap, n, parts,
              tmp.d(), tmp.cap, M);
   VMX_CHECK_LAUNCH();
+#ifndef VMX_HOST_EMUL
+  VMX_LAUNCH(c, k_coop_combine_parts<N>, nblocks(n, kCoopWarps), 32 * kCoopWarps, 0, tmp.d(), tmp.cap, n, parts, out,
+             ocap, c->P.consts, M.n0inv);
+#else
   VMX_LAUNCH(c, k_combine_parts<N>, nblocks(n), kThreads, 0, tmp.d(), tmp.cap, n, parts, out, ocap, M);
+#endif
   VMX_CHECK_LAUNCH();
   c->modmuls += (uint64_t)n * (nwin - 1);
   return VMX_OK;
 }
 
 // ------------------------------------------------------------------ variable-base
+constexpr size_t kCoopMaxElems = 8192;  // arrays up to this size use the warp-per-element kernels
 static int choose_var_window(int ebits) {
   int bw = 1;
   double best = 1e300;
@@ -441,6 +454,15 @@ static int exp_var_run(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32_
     VMX_CHECK_LAUNCH();
     return VMX_OK;
   }
+#ifndef VMX_HOST_EMUL
+  if (n <= kCoopMaxElems) {  // one warp per element: low latency, fills the machine with few elements
+    VMX_LAUNCH(c, k_coop_exp<N>, nblocks(n, kCoopWarps), 32 * kCoopWarps, 0, a, acap, E, ecap, escalar ? 1 : 0, ebits,
+               n, c->P.consts, M.n0inv, out, ocap);
+    VMX_CHECK_LAUNCH();
+    c->modmuls += (uint64_t)n * (14 + (uint64_t)ebits + ebits / 4);
+    return VMX_OK;
+  }
+#endif
   const int w = choose_var_window(ebits);
   // bound the per-thread table scratch (2^w entries per element) to ~6 GB, in whole waves
   const size_t wave = wave_threads(c);
@@ -530,12 +552,20 @@ static int mexp_run(vmx_ctx* c, const MexpPlan& P, const vmx_garr* a, size_t n_t
                          P.nseg2, P.total2, 8, X.d(), X.cap));
   const size_t ngroups = (size_t)P.W * P.J;
   VMX_TRY(Y.alloc_elems(c, ngroups));
+#ifndef VMX_HOST_EMUL
+  VMX_LAUNCH(c, k_coop_weighted_small<N>, nblocks(ngroups, kCoopWarps), 32 * kCoopWarps, 0, X.d(), X.cap, ngroups,
+             Y.d(), Y.cap, c->P.consts, M.n0inv);
+  VMX_CHECK_LAUNCH();
+  VMX_LAUNCH(c, k_coop_horner<N>, 1, 32, 0, Y.d(), Y.cap, (int)ngroups, out, ocap, oidx, c->P.consts, M.n0inv);
+  VMX_CHECK_LAUNCH();
+#else
   VMX_TRY(R.alloc_elems(c, ngroups));
   VMX_LAUNCH(c, k_weighted_small<N>, nblocks(ngroups, 32), 32, 0, X.d(), X.cap, ngroups, Y.d(), Y.cap, R.d(), R.cap,
              M);
   VMX_CHECK_LAUNCH();
   VMX_LAUNCH(c, k_horner<N>, 1, 32, N * 4, Y.d(), Y.cap, (int)ngroups, out, ocap, oidx, M);
   VMX_CHECK_LAUNCH();
+#endif
   c->modmuls += ngroups * 28 + (ngroups - 1) * 5;
   return VMX_OK;
 }
@@ -780,12 +810,9 @@ int vmx_garr_from_bytes(vmx_ctx* c, size_t n, const uint8_t* be, int check_membe
 
 static int exp_scalar_limbs(vmx_ctx* c, const vmx_garr* a, const uint32_t* x, vmx_garr** out);
 
-int vmx_garr_from_raw(vmx_ctx* c, size_t n, const uint8_t* be, size_t width, unsigned bitlen, vmx_garr** out) {
-  if (!out) return VMX_EARG;
-  *out = nullptr;
-  VMX_ENTER(c);
-  if ((n && !be) || !width || width > (size_t)8 * c->nl) { set_error("from_raw: bad width %zu", width); return VMX_EARG; }
-  if (bitlen > 8 * width) bitlen = 0;
+// element i = (t_i mod p)^((p-1)/q), t_i = i-th `width`-byte big-endian integer of the DEVICE
+// buffer d_raw, masked to `bitlen` bits
+static int garr_from_raw_dev(vmx_ctx* c, size_t n, const uint8_t* d_raw, size_t width, unsigned bitlen, vmx_garr** out) {
   // cofactor (p-1)/q must be a small integer: find it by repeated addition of q (setup-size host work)
   uint32_t cof = 0;
   {
@@ -807,13 +834,10 @@ int vmx_garr_from_raw(vmx_ctx* c, size_t n, const uint8_t* be, size_t width, uns
   std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(t, vmx_garr_free);
   if (!n) { *out = guard.release(); return VMX_OK; }
   {
-    DevBuf raw;
     ElemBuf can;
-    VMX_TRY(raw.alloc(c, n * width));
     VMX_TRY(can.alloc_elems(c, n));
-    VMX_CU(cudaMemcpyAsync(raw.p, be, n * width, cudaMemcpyHostToDevice, c->stream));
     VMX_DISPATCH(c->nl, {
-      VMX_LAUNCH(c, k_ring_from_raw<N>, nblocks(n), kThreads, 0, raw.as<uint8_t>(), n, (int)width, (int)bitlen, can.d(),
+      VMX_LAUNCH(c, k_ring_from_raw<N>, nblocks(n), kThreads, 0, d_raw, n, (int)width, (int)bitlen, can.d(),
                  can.cap, c->P.consts, 1, c->P.params<N>());
       VMX_CHECK_LAUNCH();
       // canonical -> Montgomery form
@@ -822,10 +846,82 @@ int vmx_garr_from_raw(vmx_ctx* c, size_t n, const uint8_t* be, size_t width, uns
       VMX_CHECK_LAUNCH();
     });
     c->modmuls += 4 * n;
-    VMX_CU(cudaStreamSynchronize(c->stream));  // `be` is borrowed for the call only
   }
   uint32_t x[kMaxLimbs] = {cof};
   return exp_scalar_limbs(c, t, x, out);
+}
+
+int vmx_garr_from_raw(vmx_ctx* c, size_t n, const uint8_t* be, size_t width, unsigned bitlen, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  VMX_ENTER(c);
+  if ((n && !be) || !width || width > (size_t)8 * c->nl) { set_error("from_raw: bad width %zu", width); return VMX_EARG; }
+  if (bitlen > 8 * width) bitlen = 0;
+  DevBuf raw;
+  VMX_TRY(raw.alloc(c, n * width));
+  if (n) {
+    VMX_CU(cudaMemcpyAsync(raw.p, be, n * width, cudaMemcpyHostToDevice, c->stream));
+    VMX_CU(cudaStreamSynchronize(c->stream));  // `be` is borrowed for the call only
+  }
+  return garr_from_raw_dev(c, n, raw.as<uint8_t>(), width, bitlen, out);
+}
+
+// stream bytes [offset, offset + nbytes) of PRGHeuristic(SHA-256); *data points at the first one
+static int prg_bytes_dev(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t nbytes, DevBuf& buf,
+                         const uint8_t** data) {
+  if (!seed || seedlen < 32 || seedlen > 48) { set_error("PRG seed must be 32..48 bytes"); return VMX_EARG; }
+  const size_t first = offset / 32, shift = offset % 32;
+  const size_t nblk = (shift + nbytes + 31) / 32;
+  if (first + nblk >= 0xffffffffull) { set_error("PRG stream too long"); return VMX_ESIZE; }
+  PrgSeed s;
+  std::memset(&s, 0, sizeof s);
+  std::memcpy(s.bytes, seed, seedlen);
+  s.len = (int)seedlen;
+  VMX_TRY(buf.alloc(c, nblk * 32));
+  if (nblk) {
+    VMX_LAUNCH(c, k_prg_bytes, nblocks(nblk, 128), 128, 0, s, first, nblk, buf.as<uint8_t>());
+    VMX_CHECK_LAUNCH();
+  }
+  *data = buf.as<uint8_t>() + shift;
+  return VMX_OK;
+}
+
+int vmx_garr_prg_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t n, size_t width,
+                        unsigned bitlen, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  VMX_ENTER(c);
+  if (!width || width > (size_t)8 * c->nl) { set_error("prg: bad width %zu", width); return VMX_EARG; }
+  if (bitlen > 8 * width) bitlen = 0;
+  DevBuf raw;
+  const uint8_t* data = nullptr;
+  VMX_TRY(prg_bytes_dev(c, seed, seedlen, offset, n * width, raw, &data));
+  return garr_from_raw_dev(c, n, data, width, bitlen, out);
+}
+
+int vmx_rarr_prg_raw_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t n, size_t width,
+                            unsigned bitlen, vmx_rarr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  VMX_ENTER(c);
+  if (!width || width > (size_t)8 * c->nl) { set_error("prg: bad width %zu", width); return VMX_EARG; }
+  if (bitlen > 8 * width) bitlen = 0;
+  DevBuf raw;
+  const uint8_t* data = nullptr;
+  VMX_TRY(prg_bytes_dev(c, seed, seedlen, offset, n * width, raw, &data));
+  vmx_rarr* a = nullptr;
+  VMX_TRY(new_rarr(c, n, &a));
+  std::unique_ptr<vmx_rarr, void (*)(vmx_rarr*)> guard(a, vmx_rarr_free);
+  if (n) {
+    const int totalbits = bitlen ? (int)bitlen : (int)(8 * width);
+    const int need_reduce = totalbits >= c->Q.bits;
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_ring_from_raw<N>, nblocks(n), kThreads, 0, data, n, (int)width,
+                                   (int)bitlen, a->d, a->cap, c->Q.consts, need_reduce, c->Q.params<N>()));
+    VMX_CHECK_LAUNCH();
+    if (need_reduce) c->modmuls += 3 * n;
+  }
+  *out = guard.release();
+  return VMX_OK;
 }
 
 int vmx_garr_to_bytes(const vmx_garr* a, uint8_t* be_out) {
@@ -1235,14 +1331,15 @@ int vmx_rarr_from_raw(vmx_ctx* c, size_t n, const uint8_t* be, size_t width, uns
   return VMX_OK;
 }
 
-int vmx_rarr_prg_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, size_t n, unsigned bitlen, vmx_rarr** out) {
+int vmx_rarr_prg_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t n, unsigned bitlen,
+                        vmx_rarr** out) {
   if (!out) return VMX_EARG;
   *out = nullptr;
   VMX_ENTER(c);
   if (!seed || seedlen < 32 || seedlen > 48) { set_error("PRG seed must be 32..48 bytes"); return VMX_EARG; }
   if (!bitlen || (int)bitlen >= c->Q.bits) { set_error("PRG bit length %u must be below |q|", bitlen); return VMX_EARG; }
   const size_t wbytes = (bitlen + 7) / 8;
-  if (n * wbytes / 32 >= 0xffffffffull) { set_error("PRG stream too long"); return VMX_ESIZE; }
+  if ((offset + n * wbytes) / 32 >= 0xffffffffull) { set_error("PRG stream too long"); return VMX_ESIZE; }
   PrgSeed s;
   std::memset(&s, 0, sizeof s);
   std::memcpy(s.bytes, seed, seedlen);
@@ -1250,7 +1347,7 @@ int vmx_rarr_prg_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, size_t 
   vmx_rarr* a = nullptr;
   VMX_TRY(new_rarr(c, n, &a));
   if (n) {
-    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_prg_expand<N>, nblocks(n, 128), 128, 0, s, n, (int)bitlen, a->d, a->cap));
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_prg_expand<N>, nblocks(n, 128), 128, 0, s, (size_t)offset, n, (int)bitlen, a->d, a->cap));
     if (cudaGetLastError() != cudaSuccess) { vmx_rarr_free(a); set_error("prg launch failed"); return VMX_ECUDA; }
   }
   *out = a;
@@ -1522,6 +1619,49 @@ int vmx_requals(const vmx_rarr* a, const vmx_rarr* b, int* equal) {
   VMX_TRY(same_ctx(b->ctx, c));
   if (a->n != b->n) { *equal = 0; return VMX_OK; }
   return arrays_equal(c, a->d, a->cap, b->d, b->cap, a->n, equal);
+}
+
+// ---------------------------------------------------------------- self test of the cooperative multiplier
+int vmx_selftest_coop(const vmx_garr* a, const vmx_garr* b, int* equal) {
+  if (!a || !b || !equal) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  if (a->n != b->n || b->ctx != c) return VMX_ESIZE;
+#ifdef VMX_HOST_EMUL
+  *equal = 1;
+  return VMX_OK;
+#else
+  ElemBuf x, y;
+  VMX_TRY(x.alloc_elems(c, a->n));
+  VMX_TRY(y.alloc_elems(c, a->n));
+  VMX_DISPATCH(c->nl, {
+    VMX_LAUNCH(c, k_mul<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, b->d, b->cap, x.d(), x.cap, a->n, c->P.params<N>());
+    VMX_LAUNCH(c, k_coop_mul<N>, nblocks(a->n, kCoopWarps), 32 * kCoopWarps, 0, a->d, a->cap, b->d, b->cap, a->n, y.d(),
+               y.cap, c->P.consts, c->P.n0inv);
+  });
+  VMX_CHECK_LAUNCH();
+  return arrays_equal(c, x.d(), x.cap, y.d(), y.cap, a->n, equal);
+#endif
+}
+
+// a[i]*b[i] on the cooperative multiplier (debug / test hook)
+int vmx_debug_coop_mul(const vmx_garr* a, const vmx_garr* b, vmx_garr** out) {
+  if (!a || !b || !out) return VMX_EARG;
+  *out = nullptr;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  if (a->n != b->n || b->ctx != c) return VMX_ESIZE;
+#ifdef VMX_HOST_EMUL
+  return vmx_mul(a, b, out);
+#else
+  vmx_garr* r = nullptr;
+  VMX_TRY(new_garr(c, a->n, &r));
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_coop_mul<N>, nblocks(a->n, kCoopWarps), 32 * kCoopWarps, 0, a->d, a->cap, b->d,
+                                 b->cap, a->n, r->d, r->cap, c->P.consts, c->P.n0inv));
+  if (cudaGetLastError() != cudaSuccess) { vmx_garr_free(r); set_error("coop launch failed"); return VMX_ECUDA; }
+  *out = r;
+  return VMX_OK;
+#endif
 }
 
 // ---------------------------------------------------------------- benchmark hook

@@ -224,6 +224,10 @@ class PoSBasicTW:
         ciphPRing = self.pkey.project(0).getPGroup().getPRing()
         if not self._parseReplies(ciphPRing, btr):
             return False
+        return self.verifyParsed()
+
+    def verifyParsed(self) -> bool:
+        """The five checks of verify() on already-imported replies (:1008-1066)."""
         g, h, u, v = self.g, self.h, self.u, self.v
         h0 = h.get(0)
         self.C = u.prod().div(h.prod())                                          # :1013
