@@ -1,0 +1,309 @@
+"""ORACLE (test infrastructure only -- never imported by the product path).
+
+CPU restatement on Python integers of the protocol algebra of the hot path, following the
+reference line by line:
+
+  PoSBasicTW               hvzk/PoSBasicTW.java:407-482 (computeAF, precompute), :533-700 (commit),
+                           :780-823 (setCommitment), :856-888 (reply), :1000-1066 (verify)
+  PoSCBasicTW              hvzk/PoSCBasicTW.java:363-529, :607-636, :646-727
+  CCPoSBasicW              hvzk/CCPoSBasicW.java:344-396, :462-485, :493-506, :519-584
+  fiat_shamir_pos_*        hvzk/PoSTW.java:95-165 (prove), :177-260 (verify); hvzk/ChallengerRO.java:96-116
+  shuffle                  mixnet/ShufflerElGamalSession.java:362-433, :250-300
+  global_prefix            elgamal/ProtocolElGamal.java:659-683
+  independent_generators   distr/IndependentGeneratorsRO.java:110-130
+  demo_ciphertexts         elgamal/ProtocolElGamalInterfaceRaw.java:99-130
+  decryption-factor proof  elgamal/DistrElGamalSessionBasic.java:513-540, :595-727
+
+PARITY UNPINNED against a Java run (no JVM, no golden vectors in the reference).
+Pinned by: tests/golden (PRG / RO / byte-tree KATs and the in-tree ModPGroup fixture), exact
+integer arithmetic, and accept / reject behaviour (the only thing the reference's own
+hvzk/TestPoSCBasicTW.java:147-163 asserts).
+"""
+from __future__ import annotations
+
+from . import arithm as ar
+from . import bytetree as bt
+from .crypto import PRGHeuristic, RandomOracle
+
+import hashlib
+
+
+# ---------------------------------------------------------------- hashing glue
+def challenge(hashname: str, global_prefix: bytes, data: bt.ByteTree, out_bits: int) -> bytes:
+    """hvzk/ChallengerRO.java:96-116."""
+    d = RandomOracle(hashname, out_bits).get_digest()
+    d.update(global_prefix)
+    data.update(d)
+    return d.digest()
+
+
+def global_prefix(hashname, version, rosid, rbitlen, vbitlenro, ebitlenro, prg_string, pgroup_string, rohash_string):
+    """elgamal/ProtocolElGamal.java:659-683."""
+    t = bt.node(bt.string_leaf(version), bt.string_leaf(rosid), bt.int32_leaf(rbitlen), bt.int32_leaf(vbitlenro),
+                bt.int32_leaf(ebitlenro), bt.string_leaf(prg_string), bt.string_leaf(pgroup_string),
+                bt.string_leaf(rohash_string))
+    return hashlib.new(hashname, t.to_bytes()).digest()
+
+
+def independent_generators(G, hashname, prefix: bytes, sid: str, n: int, rbitlen: int):
+    """distr/IndependentGeneratorsRO.java:110-130."""
+    prg = PRGHeuristic(hashname)
+    d = RandomOracle(hashname, 8 * prg.min_no_seed_bytes()).get_digest()
+    d.update(prefix)
+    d.update(bt.string_leaf(sid).to_bytes())
+    prg.set_seed(d.digest())
+    return ar.group_random_array(G, n, prg, rbitlen)
+
+
+def demo_ciphertexts(G, pk, n: int, rs):
+    """elgamal/ProtocolElGamalInterfaceRaw.java:99-130 (width 1)."""
+    g, y = pk
+    m = ar.group_random_array(G, n, rs, 10)
+    r = ar.ring_random_array(G, n, rs, 20)
+    u = ar.g_exp(G, g, r)
+    t = ar.g_exp(G, y, r)
+    return (u, ar.g_mul(G, t, m))
+
+
+def batch_vector(hashname: str, seed: bytes, n: int, ebitlen: int):
+    """setBatchVector (hvzk/PoSBasicTW.java:533-538)."""
+    prg = PRGHeuristic(hashname)
+    prg.set_seed(seed)
+    return ar.lia_random(n, ebitlen, prg)
+
+
+def _ring_shape(pk):
+    """Shape of ciphPRing = pkey.project(0).getPGroup().getPRing() (None for Z_q)."""
+    return tuple(None for _ in pk[0]) if isinstance(pk[0], tuple) else None
+
+
+def _ring_random(G, shape, rs, rbitlen):
+    if isinstance(shape, tuple):
+        return tuple(_ring_random(G, s, rs, rbitlen) for s in shape)
+    return ar.ring_random_element(G, rs, rbitlen)
+
+
+def _rneg(G, x):
+    return ar.gmap(lambda v: (-v) % G.q, x)
+
+
+def _rmuladd(G, a, v, b):
+    """a*v + b on ring elements or arrays."""
+    def one(x, y):
+        if isinstance(x, list):
+            return [(s * v + t) % G.q for s, t in zip(x, y)]
+        return (x * v + y) % G.q
+    return ar.gmap(one, a, b)
+
+
+# ---------------------------------------------------------------- PoSBasicTW
+class PoSBasicTW:
+    def __init__(self, G, vbitlen, ebitlen, rbitlen, prg_hash, rs):
+        self.G, self.vbitlen, self.ebitlen, self.rbitlen, self.prg_hash, self.rs = G, vbitlen, ebitlen, rbitlen, prg_hash, rs
+
+    # :436-482
+    def precompute(self, g, h, pi=None):
+        G = self.G
+        self.g, self.h, self.size = g, h, len(h)
+        if pi is None:
+            return
+        self.pi = pi
+        self.r = ar.ring_random_array(G, self.size, self.rs, self.rbitlen)
+        self.u = ar.permute(ar.g_mul(G, h, ar.g_exp(G, g, self.r)), pi)
+        self.alpha = ar.ring_random_element(G, self.rs, self.rbitlen)
+        # pField.toElementArray(epsilonIntegers) (:473): field elements, i.e. reduced mod q
+        self.epsilon = [v % G.q for v in ar.lia_random(self.size, self.ebitlen + self.vbitlen + self.rbitlen, self.rs)]
+        self.Ap = pow(g, self.alpha, G.p) * ar.g_exp_prod(G, h, self.epsilon) % G.p
+
+    def set_instance(self, pkey, w, wp, s=None):
+        self.pkey, self.w, self.wp, self.s = pkey, w, wp, s
+
+    def set_batch_vector(self, seed: bytes):
+        self.e = batch_vector(self.prg_hash, seed, self.size, self.ebitlen)
+
+    # :407-410
+    def compute_AF(self):
+        self.A = ar.g_exp_prod(self.G, self.u, self.e)
+        self.F = ar.g_exp_prod(self.G, self.w, self.e)
+
+    # :546-700
+    def commit(self, seed: bytes) -> bt.ByteTree:
+        G, g, h = self.G, self.g, self.h
+        self.set_batch_vector(seed)
+        self.ipe = ar.permute(self.e, ar.perm_inv(self.pi))
+        h0 = h[0]
+        self.b = ar.ring_random_array(G, self.size, self.rs, self.rbitlen)
+        x, self.d = ar.r_rec_lin(G, self.b, self.ipe)
+        y = ar.r_prods(G, self.ipe)
+        self.B = ar.g_mul(G, ar.g_exp(G, g, x), ar.g_exp(G, h0, y))
+        self.beta = ar.ring_random_array(G, self.size, self.rs, self.rbitlen)
+        xp = [0] + x[:-1]
+        yp = [1] + y[:-1]
+        e1 = [(bb + a * c) % G.q for bb, a, c in zip(self.beta, xp, self.epsilon)]
+        e2 = [a * c % G.q for a, c in zip(yp, self.epsilon)]
+        self.Bp = ar.g_mul(G, ar.g_exp(G, g, e1), ar.g_exp(G, h0, e2))
+        self.gamma = ar.ring_random_element(G, self.rs, self.rbitlen)
+        self.Cp = pow(g, self.gamma, G.p)
+        self.delta = ar.ring_random_element(G, self.rs, self.rbitlen)
+        self.Dp = pow(g, self.delta, G.p)
+        self.phi = _ring_random(G, _ring_shape(self.pkey), self.rs, self.rbitlen)
+        self.Fp = ar.g_mul(G, ar.g_exp(G, self.pkey, _rneg(G, self.phi)), ar.g_exp_prod(G, self.wp, self.epsilon))
+        return self.commitment_tree()
+
+    def commitment_tree(self) -> bt.ByteTree:
+        G = self.G
+        return bt.node(ar.array_tree(G, self.B), ar.elem_tree(G, self.Ap), ar.array_tree(G, self.Bp),
+                       ar.elem_tree(G, self.Cp), ar.elem_tree(G, self.Dp), ar.elem_tree(G, self.Fp))
+
+    # :780-823
+    def set_commitment(self, t: bt.ByteTree) -> bt.ByteTree:
+        G = self.G
+        try:
+            if t.is_leaf() or len(t.children) != 6:
+                raise ar.FormatError("commitment arity")
+            c = t.children
+            self.B = ar.parse_array(G, c[0], self.size)
+            self.Ap = ar.parse_elem(G, c[1])
+            self.Bp = ar.parse_array(G, c[2], self.size)
+            self.Cp = ar.parse_elem(G, c[3])
+            self.Dp = ar.parse_elem(G, c[4])
+            self.Fp = ar.parse_elem(G, c[5], self.pkey)
+        except ar.FormatError:
+            self.B = [1] * self.size
+            self.Bp = [1] * self.size
+            self.Ap = self.Cp = self.Dp = 1
+            self.Fp = ar.gmap(lambda _: 1, self.pkey)
+        return self.commitment_tree()
+
+    def set_challenge(self, v: int):
+        assert 0 <= v and v.bit_length() <= self.vbitlen, "Malformed challenge!"
+        self.v = v % self.G.q
+
+    # :856-888
+    def reply(self, v: int) -> bt.ByteTree:
+        G = self.G
+        self.set_challenge(v)
+        v = self.v
+        a = ar.r_inner(G, self.r, self.ipe)
+        c = sum(self.r) % G.q
+        f = ar.r_inner(G, self.s, self.e)
+        self.k_A = (a * v + self.alpha) % G.q
+        self.k_B = [(x * v + y) % G.q for x, y in zip(self.b, self.beta)]
+        self.k_C = (c * v + self.gamma) % G.q
+        self.k_D = (self.d * v + self.delta) % G.q
+        self.k_E = [(x * v + y) % G.q for x, y in zip(self.ipe, self.epsilon)]
+        self.k_F = _rmuladd(G, f, v, self.phi)
+        return self.reply_tree()
+
+    def reply_tree(self) -> bt.ByteTree:
+        G = self.G
+        return bt.node(ar.ring_tree(G, self.k_A), ar.ring_array_tree(G, self.k_B), ar.ring_tree(G, self.k_C),
+                       ar.ring_tree(G, self.k_D), ar.ring_array_tree(G, self.k_E), ar.ring_tree(G, self.k_F))
+
+    # :970-990, :1000-1066
+    def verify(self, t: bt.ByteTree) -> bool:
+        G, g, h, u, p = self.G, self.g, self.h, self.u, self.G.p
+        try:
+            if t.is_leaf() or len(t.children) != 6:
+                raise ar.FormatError("reply arity")
+            c = t.children
+            self.k_A = ar.parse_ring(G, c[0])
+            self.k_B = ar.parse_ring_array(G, c[1], self.size)
+            self.k_C = ar.parse_ring(G, c[2])
+            self.k_D = ar.parse_ring(G, c[3])
+            self.k_E = ar.parse_ring_array(G, c[4], self.size)
+            self.k_F = ar.parse_ring(G, c[5], _ring_shape(self.pkey))
+        except ar.FormatError:
+            return False
+        v = self.v
+        h0 = h[0]
+        C = ar.g_prod(G, u) * pow(ar.g_prod(G, h), -1, p) % p
+        eprod = 1
+        for x in self.e:
+            eprod = eprod * x % G.q
+        D = self.B[-1] * pow(pow(h0, eprod, p), -1, p) % p
+        vA = pow(self.A, v, p) * self.Ap % p == pow(g, self.k_A, p) * ar.g_exp_prod(G, h, self.k_E) % p
+        left = ar.g_mul(G, ar.g_exp(G, self.B, v), self.Bp)
+        right = ar.g_mul(G, ar.g_exp(G, g, self.k_B), ar.g_exp(G, [h0] + self.B[:-1], self.k_E))
+        vB = left == right
+        vC = pow(C, v, p) * self.Cp % p == pow(g, self.k_C, p)
+        vD = pow(D, v, p) * self.Dp % p == pow(g, self.k_D, p)
+        lhsF = ar.g_mul(G, ar.g_exp(G, self.F, v), self.Fp)
+        rhsF = ar.g_mul(G, ar.g_exp(G, self.pkey, _rneg(G, self.k_F)), ar.g_exp_prod(G, self.wp, self.k_E))
+        vF = lhsF == rhsF
+        self.verdicts = (vA, vB, vC, vD, vF)
+        return all(self.verdicts)
+
+
+# ---------------------------------------------------------------- Fiat-Shamir wrapper (hvzk/PoSTW.java)
+class Params:
+    def __init__(self, vbitlenro=256, ebitlenro=256, rbitlen=100, rohash="sha256", prghash="sha256",
+                 version="3.1.0", rosid="vmx.session", pgroup_string=""):
+        self.vbitlenro, self.ebitlenro, self.rbitlen = vbitlenro, ebitlenro, rbitlen
+        self.rohash, self.prghash, self.version, self.rosid, self.pgroup_string = rohash, prghash, version, rosid, pgroup_string
+
+    def prefix(self) -> bytes:
+        names = {"sha256": "SHA-256", "sha384": "SHA-384", "sha512": "SHA-512"}
+        return global_prefix(self.rohash, self.version, self.rosid, self.rbitlen, self.vbitlenro, self.ebitlenro,
+                             "PRGHeuristic(%s)" % names[self.prghash], self.pgroup_string,
+                             "HashfunctionHeuristic(%s)" % names[self.rohash])
+
+
+def _seed_data(G, P, pkey, w, wp) -> bt.ByteTree:
+    """hvzk/PoSTW.java:118-124."""
+    return bt.node(ar.elem_tree(G, P.g), ar.array_tree(G, P.h), ar.array_tree(G, P.u), ar.elem_tree(G, pkey),
+                   ar.array_tree(G, w), ar.array_tree(G, wp))
+
+
+def shuffle_and_prove(G, params: Params, pkey, w, h, rs):
+    """mixnet/ShufflerElGamalSession.java:400-414 + :273-289 + hvzk/PoSTW.java:95-165.
+    Returns (output array, dict of the four published byte strings)."""
+    n = ar.size_of(w)
+    prefix = params.prefix()
+    shape = _ring_shape(pkey)
+    if isinstance(shape, tuple):
+        s = tuple(ar.ring_random_array(G, n, rs, params.rbitlen) for _ in shape)
+    else:
+        s = ar.ring_random_array(G, n, rs, params.rbitlen)
+    factors = ar.g_exp(G, pkey, s)
+    pi = ar.permutation_random(n, rs, params.rbitlen)
+    P = PoSBasicTW(G, params.vbitlenro, params.ebitlenro, params.rbitlen, params.prghash, rs)
+    P.precompute(G.g, h, pi)
+    wp = ar.permute(ar.g_mul(G, w, factors), ar.perm_inv(pi))
+    P.set_instance(pkey, w, wp, s)
+    seed = challenge(params.rohash, prefix, _seed_data(G, P, pkey, w, wp), 8 * PRGHeuristic(params.prghash).min_no_seed_bytes())
+    commitment = P.commit(seed)
+    cb = challenge(params.rohash, prefix, bt.node(bt.leaf(seed), commitment), params.vbitlenro)
+    reply = P.reply(int.from_bytes(cb, "big"))
+    return wp, {"output": ar.array_tree(G, wp).to_bytes(), "permutationCommitment": ar.array_tree(G, P.u).to_bytes(),
+                "commitment": commitment.to_bytes(), "reply": reply.to_bytes()}
+
+
+def verify_shuffle(G, params: Params, pkey, w, h, proof: dict) -> bool:
+    """mixnet/ShufflerElGamalSession.java:195-210,301-330 + hvzk/PoSTW.java:177-260."""
+    n = ar.size_of(w)
+    prefix = params.prefix()
+    try:
+        wp = ar.parse_array(G, bt.from_bytes(proof["output"]), n, pkey)
+    except (ar.FormatError, bt.EIOError):
+        return False
+    V = PoSBasicTW(G, params.vbitlenro, params.ebitlenro, params.rbitlen, params.prghash, None)
+    V.precompute(G.g, h)
+    V.set_instance(pkey, w, wp)
+    try:
+        V.u = ar.parse_array(G, bt.from_bytes(proof["permutationCommitment"]), n)
+    except (ar.FormatError, bt.EIOError):
+        V.u = list(h)
+    seed = challenge(params.rohash, prefix, _seed_data(G, V, pkey, w, wp), 8 * PRGHeuristic(params.prghash).min_no_seed_bytes())
+    V.set_batch_vector(seed)
+    V.compute_AF()
+    try:
+        ctree = V.set_commitment(bt.from_bytes(proof["commitment"]))
+    except bt.EIOError:
+        ctree = V.set_commitment(bt.leaf(b""))
+    cb = challenge(params.rohash, prefix, bt.node(bt.leaf(seed), ctree), params.vbitlenro)
+    V.set_challenge(int.from_bytes(cb, "big"))
+    try:
+        return V.verify(bt.from_bytes(proof["reply"]))
+    except bt.EIOError:
+        return False

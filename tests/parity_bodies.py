@@ -1,0 +1,216 @@
+"""Parity test bodies shared by the CPU (host-emulation) and GPU (CUDA) test modules: the engine
+behind the C ABI against the oracle on the same seeded inputs, bit for bit."""
+import dataclasses
+import importlib
+import random
+
+import numpy as np
+
+from oracle import arithm as oar
+from oracle import protocols as opr
+from oracle.crypto import SeededRandomSource, PRGHeuristic as OPRG
+from tests.cases import EngineCase, OracleCase, col_values, group_params, seed
+
+
+def _arrays(vmx, bits, n, rnd):
+    A = vmx.arithm
+    p, q, g = group_params(bits)
+    G = A.ModPGroup(p, q, g)
+    R = G.getPRing()
+    xs = [pow(g, rnd.randrange(q), p) for _ in range(n)]
+    es = [rnd.randrange(q) for _ in range(n)]
+    X = G.toElementArray([A.PGroupElement(G, x) for x in xs])
+    E = R.toElementArray([A.PFieldElement(R, e) for e in es])
+    return A, G, R, p, q, g, xs, es, X, E
+
+
+def group_ops(vmx, bits, n):
+    rnd = random.Random(bits * 1000 + n)
+    A, G, R, p, q, g, xs, es, X, E = _arrays(vmx, bits, n, rnd)
+    OG = oar.ModPGroup(p, q, g)
+    vals = lambda arr: [e.value for e in arr.elements()]
+    assert vals(X) == xs and vals(E) == es                                     # codec round trip
+    assert vals(X.mul(X)) == oar.g_mul(OG, xs, xs)
+    assert vals(G.getg().exp(E)) == oar.g_exp(OG, g, es)                       # fixed base
+    assert vals(X.exp(E)) == oar.g_exp(OG, xs, es)                             # variable base, per element
+    s = A.PFieldElement(R, rnd.randrange(1 << 256))
+    assert vals(X.exp(s)) == oar.g_exp(OG, xs, s.value)                        # variable base, one exponent
+    assert X.expProd(E).value == oar.g_exp_prod(OG, xs, es)                    # multi-exponentiation
+    short = [rnd.randrange(1 << 256) for _ in range(n)]
+    S = R.toElementArray([A.PFieldElement(R, e) for e in short])
+    assert X.expProd(S).value == oar.g_exp_prod(OG, xs, short)
+    assert X.prod().value == oar.g_prod(OG, xs)
+    perm = list(range(n))
+    rnd.shuffle(perm)
+    assert vals(X.permute(A.Permutation(perm))) == oar.permute(xs, perm)
+    assert vals(X.shiftPush(G.getg())) == oar.shift_push(xs, g)
+    keep = [i % 3 != 1 for i in range(n)]
+    assert vals(X.extract(keep)) == [x for x, k in zip(xs, keep) if k]
+    assert vals(X.copyOfRange(1, n - 1)) == xs[1:n - 1]
+    assert X.get(n - 1).value == xs[-1]
+    assert X.equals(X.copyOfRange(0, n)) and not X.equals(X.shiftPush(G.getg()))
+    assert vals(X.inv()) == oar.g_inv(OG, xs)
+    Y = X.mul(X)
+    cols = G.expProd([X, Y], [5, -3], 3)
+    assert vals(cols) == [pow(x, 5, p) * pow(pow(x * x % p, 3, p), -1, p) % p for x in xs]
+    # single elements go through the engine as well
+    a = A.PGroupElement(G, xs[0])
+    assert a.exp(s).value == pow(xs[0], s.value, p)
+    assert a.mul(A.PGroupElement(G, xs[1])).value == xs[0] * xs[1] % p
+    assert a.inv().value == pow(xs[0], -1, p)
+    assert a.expMul(s, A.PGroupElement(G, xs[1])).value == pow(xs[0], s.value, p) * xs[1] % p
+
+
+def edge_cases(vmx, bits):
+    A = vmx.arithm
+    p, q, g = group_params(bits)
+    G = A.ModPGroup(p, q, g)
+    R = G.getPRing()
+    one = [A.PGroupElement(G, 1)] * 3
+    X = G.toElementArray(one + [A.PGroupElement(G, p - 1 if pow(p - 1, q, p) == 1 else g)])
+    zeros = R.toElementArray([A.PFieldElement(R, 0)] * 4)
+    top = R.toElementArray([A.PFieldElement(R, q - 1)] * 4)
+    assert [e.value for e in X.exp(zeros).elements()] == [1, 1, 1, 1]          # x^0
+    assert X.expProd(zeros).value == 1
+    assert [e.value for e in G.getg().exp(zeros).elements()] == [1] * 4
+    assert [e.value for e in G.getg().exp(top).elements()] == [pow(g, q - 1, p)] * 4
+    empty = G.toElementArray([])
+    assert empty.size() == 0 and empty.to_matrix().shape == (0, G.elem_bytes)
+    single = G.toElementArray([A.PGroupElement(G, g)])
+    e1 = R.toElementArray([A.PFieldElement(R, 5)])
+    assert single.expProd(e1).value == pow(g, 5, p) and single.prod().value == g
+    # range and membership violations are ArithmFormatException, not crashes
+    for bad in (0, p, p + 1):
+        try:
+            m = np.frombuffer(bad.to_bytes(G.elem_bytes, "big"), dtype=np.uint8)
+            G.toElementArray(1, m)
+            assert False, bad
+        except A.ArithmFormatException:
+            pass
+    nonmember = next(v for v in range(2, 50) if pow(v, q, p) != 1)
+    try:
+        G.toElementArray(1, np.frombuffer(nonmember.to_bytes(G.elem_bytes, "big"), dtype=np.uint8))
+        assert False
+    except A.ArithmFormatException:
+        pass
+    try:
+        R.toElementArray(1, vmx.eio.ByteTreeReader(vmx.eio.ByteTreeContainer(
+            vmx.eio.ByteTreeLeaf(q.to_bytes(G.ring_bytes, "big"))).to_bytes()))
+        assert False
+    except A.ArithmFormatException:
+        pass
+    # size mismatch is an error status, not a crash
+    try:
+        X.mul(single)
+        assert False
+    except vmx._native.VmxError as e:
+        assert e.status == vmx._native.VMX_ESIZE
+
+
+def ring_ops(vmx, bits, n):
+    rnd = random.Random(bits * 7 + n)
+    A = vmx.arithm
+    p, q, g = group_params(bits)
+    G = A.ModPGroup(p, q, g)
+    R = G.getPRing()
+    OG = oar.ModPGroup(p, q, g)
+    a = [rnd.randrange(q) for _ in range(n)]
+    b = [rnd.randrange(q) for _ in range(n)]
+    Ar = R.toElementArray([A.PFieldElement(R, v) for v in a])
+    Br = R.toElementArray([A.PFieldElement(R, v) for v in b])
+    vals = lambda arr: [e.value for e in arr.elements()]
+    assert vals(Ar.add(Br)) == [(x + y) % q for x, y in zip(a, b)]
+    assert vals(Ar.neg()) == [(-x) % q for x in a]
+    assert vals(Ar.mul(Br)) == [x * y % q for x, y in zip(a, b)]
+    sc = A.PFieldElement(R, rnd.randrange(q))
+    assert vals(Ar.mulAdd(sc, Br)) == [(x * sc.value + y) % q for x, y in zip(a, b)]
+    assert Ar.innerProduct(Br).value == oar.r_inner(OG, a, b)
+    assert Ar.sum().value == sum(a) % q
+    pr = 1
+    for v in a:
+        pr = pr * v % q
+    assert Ar.prod().value == pr
+    assert vals(Ar.prods()) == oar.r_prods(OG, a)
+    x, d = Br.recLin(Ar)
+    ox, od = oar.r_rec_lin(OG, b, a)
+    assert vals(x) == ox and d.value == od
+    perm = list(range(n))
+    rnd.shuffle(perm)
+    assert vals(Ar.permute(A.Permutation(perm))) == oar.permute(a, perm)
+    assert vals(Ar.shiftPush(sc)) == [sc.value] + a[:-1]
+    assert Ar.bitLength() == max(v.bit_length() for v in a)
+
+
+def random_sources(vmx, bits, n):
+    """Same seed => same arrays as the oracle's reading of the VCR sampling rules, at any stream offset."""
+    A, cr = vmx.arithm, vmx.crypto
+    p, q, g = group_params(bits)
+    G = A.ModPGroup(p, q, g)
+    R = G.getPRing()
+    OG = oar.ModPGroup(p, q, g)
+    rs = cr.PRGHeuristic()
+    rs.setSeed(seed("rs"))
+    ors = SeededRandomSource(seed("rs"))
+    vals = lambda arr: [e.value for e in arr.elements()]
+    assert vals(R.randomElementArray(n, rs, 100)) == oar.ring_random_array(OG, n, ors, 100)
+    assert R.randomElement(rs, 100).value == oar.ring_random_element(OG, ors, 100)        # odd offset from here on
+    assert vals(R.toElementArray(A.LargeIntegerArray.random(n, 612, rs, R))) == [v % q for v in oar.lia_random(n, 612, ors)]
+    assert vals(G.randomElementArray(n, rs, 100)) == oar.group_random_array(OG, n, ors, 100)
+    assert vals(R.randomElementArray(n, rs, 100)) == oar.ring_random_array(OG, n, ors, 100)
+    assert list(A.Permutation.random(n, rs, 100).table) == oar.permutation_random(n, ors, 100)
+    assert rs.getBytes(50) == ors.get_bytes(50)
+    prg = cr.PRGHeuristic()
+    prg.setSeed(seed("batch"))
+    assert vals(R.toElementArray(A.LargeIntegerArray.random(n, 256, prg, R))) == opr.batch_vector("sha256", seed("batch"), n, 256)
+
+
+def transcript_parity(vmx, bits, n):
+    """The engine's mix-server and the oracle's, fed the same seeds, publish identical bytes; each
+    verifier accepts the other's proof; a corrupted proof is rejected by both."""
+    oc = OracleCase(bits, n)
+    ec = EngineCase(vmx, bits, n)
+    assert col_values(ec.w) == oc.w and ec.x.value == oc.x
+    prover = ec.session("prover")
+    h = prover.deriveGenerators(n)
+    assert col_values(h) == oc.h
+    proof, out = prover.shuffle(1, ec.w, generators=h, keep_output=True)
+    owp, oproof = opr.shuffle_and_prove(oc.G, oc.params, oc.pk, oc.w, oc.h, SeededRandomSource(seed("prover")))
+    assert col_values(out) == owp
+    assert proof.output == oproof["output"]
+    assert proof.permutationCommitment == oproof["permutationCommitment"]
+    assert proof.commitment == oproof["commitment"]
+    assert proof.reply == oproof["reply"]
+    # cross verification
+    verifier = ec.session(None)
+    ok, out2 = verifier.verify(1, ec.w, proof, generators=h)
+    assert ok and col_values(out2) == owp
+    assert opr.verify_shuffle(oc.G, oc.params, oc.pk, oc.w, oc.h, dataclasses.asdict(proof))
+    # corrupted proofs: same verdict from both
+    for field in ("reply", "commitment", "permutationCommitment", "output"):
+        raw = bytearray(getattr(proof, field))
+        raw[len(raw) // 2] ^= 0x04
+        bad = dataclasses.replace(proof, **{field: bytes(raw)})
+        okb, outb = verifier.verify(1, ec.w, bad, generators=h)
+        assert okb is False and col_values(outb) == oc.w          # "Replacing output with input"
+        assert opr.verify_shuffle(oc.G, oc.params, oc.pk, oc.w, oc.h, dataclasses.asdict(bad)) is False
+    for field in ("reply", "commitment", "permutationCommitment", "output"):
+        bad = dataclasses.replace(proof, **{field: getattr(proof, field)[:-2]})
+        assert verifier.verify(1, ec.w, bad, generators=h)[0] is False
+
+
+def accept_reject_properties(vmx, bits, n):
+    """Size-independent properties at sizes the oracle cannot follow: an honest proof verifies,
+    decrypting the output gives a permutation of the decrypted input (checked through products:
+    prod(dec(w')) == prod(dec(w))), a single flipped limb is rejected."""
+    ec = EngineCase(vmx, bits, n, label="big")
+    prover = ec.session("prover-big")
+    h = prover.deriveGenerators(n)
+    proof, out = prover.shuffle(1, ec.w, generators=h, keep_output=True)
+    verifier = ec.session(None)
+    ok, out2 = verifier.verify(1, ec.w, proof, generators=h)
+    assert ok and out2.equals(out)
+    dec = lambda w: w.project(1).prod().mul(w.project(0).prod().exp(ec.x).inv())
+    assert dec(out).equals(dec(ec.w))
+    raw = bytearray(proof.reply)
+    raw[-7] ^= 0x10
+    assert verifier.verify(1, ec.w, dataclasses.replace(proof, reply=bytes(raw)), generators=h)[0] is False

@@ -1,0 +1,38 @@
+"""CPU tests of the HOST side of the engine (handle management, table construction, Pippenger
+plan, segmented products, scans, codecs, PRG streams, protocol mirror) through the C ABI of the
+host-emulation build, against the oracle.  The same bodies run on the CUDA build in
+tests/test_gpu_parity.py."""
+import pytest
+
+from tests import parity_bodies as pb
+
+
+@pytest.mark.parametrize("n", [3, 37, 300])
+def test_group_ops(engine_emul, n):
+    pb.group_ops(engine_emul, 512, n)
+
+
+def test_edge_cases(engine_emul):
+    pb.edge_cases(engine_emul, 512)
+
+
+@pytest.mark.parametrize("n", [1, 33, 1100])
+def test_ring_ops(engine_emul, n):
+    pb.ring_ops(engine_emul, 512, n)
+
+
+def test_random_sources(engine_emul):
+    pb.random_sources(engine_emul, 512, 41)
+
+
+@pytest.mark.parametrize("n", [1, 2, 25])
+def test_transcript_parity(engine_emul, n):
+    pb.transcript_parity(engine_emul, 512, n)
+
+
+def test_accept_reject_larger(engine_emul):
+    pb.accept_reject_properties(engine_emul, 512, 700)
+
+
+def test_group_ops_2048_small(engine_emul):
+    pb.group_ops(engine_emul, 2048, 5)

@@ -1,0 +1,78 @@
+"""GPU parity tests: the CUDA engine behind the C ABI against the oracle, bit for bit, on the
+groups of BASELINE.json (2048- and 3072-bit safe primes) and on the reference unit test's own
+scale (ModPGroup(512)); plus size-independent properties at sizes the oracle cannot follow."""
+import ctypes as C
+
+import pytest
+
+from tests import parity_bodies as pb
+from tests.cases import group_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("bits,n", [(512, 300), (512, 9000), (2048, 40), (3072, 40)])
+def test_group_ops(engine_cuda, bits, n):
+    pb.group_ops(engine_cuda, bits, n)
+
+
+@pytest.mark.parametrize("bits", [512, 2048, 3072])
+def test_edge_cases(engine_cuda, bits):
+    pb.edge_cases(engine_cuda, bits)
+
+
+@pytest.mark.parametrize("bits,n", [(512, 1100), (3072, 70)])
+def test_ring_ops(engine_cuda, bits, n):
+    pb.ring_ops(engine_cuda, bits, n)
+
+
+@pytest.mark.parametrize("bits", [512, 3072])
+def test_random_sources(engine_cuda, bits):
+    pb.random_sources(engine_cuda, bits, 41)
+
+
+@pytest.mark.parametrize("bits,n", [(512, 1), (512, 100), (2048, 12), (3072, 12)])
+def test_transcript_parity(engine_cuda, bits, n):
+    """512/100 is the reference's hvzk/TestPoSCBasicTW.java scale; 2048 and 3072 are BASELINE.json's groups."""
+    pb.transcript_parity(engine_cuda, bits, n)
+
+
+@pytest.mark.parametrize("bits", [512, 2048, 3072])
+def test_cooperative_multiplier_matches_thread_per_element(engine_cuda, bits):
+    vmx = engine_cuda
+    A = vmx.arithm
+    p, q, g = group_params(bits)
+    G = A.ModPGroup(p, q, g)
+    rs = vmx.crypto.PRGHeuristic()
+    rs.setSeed(bytes(range(32)))
+    X1 = G.randomElementArray(6000, rs, 100)
+    X2 = G.randomElementArray(6000, rs, 100)
+    eq = C.c_int()
+    lib = vmx._native.load()
+    vmx._native.check(lib.vmx_selftest_coop(X1.h, X2.h, C.byref(eq)))
+    assert eq.value == 1
+    edge = G.toElementArray([A.PGroupElement(G, v) for v in (1, p - 1, p - 2, g)])
+    vmx._native.check(lib.vmx_selftest_coop(edge.h, edge.h, C.byref(eq)))
+    assert eq.value == 1
+
+
+def test_accept_reject_at_scale_3072(engine_cuda):
+    """N = 50,000 at 3072 bits (thread-per-element kernels, several waves, Pippenger c = 12)."""
+    pb.accept_reject_properties(engine_cuda, 3072, 50000)
+
+
+def test_accept_reject_at_scale_2048(engine_cuda):
+    pb.accept_reject_properties(engine_cuda, 2048, 60000)
+
+
+def test_launches_are_counted(engine_cuda):
+    vmx = engine_cuda
+    A = vmx.arithm
+    p, q, g = group_params(512)
+    G = A.ModPGroup(p, q, g)
+    before = G.launch_count()
+    rs = vmx.crypto.PRGHeuristic()
+    rs.setSeed(bytes(range(32)))
+    e = G.getPRing().randomElementArray(100, rs, 100)
+    G.getg().exp(e).free()
+    assert G.launch_count() > before and G.modmul_count() > 0
