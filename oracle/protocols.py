@@ -113,7 +113,7 @@ class PoSBasicTW:
         self.alpha = ar.ring_random_element(G, self.rs, self.rbitlen)
         # pField.toElementArray(epsilonIntegers) (:473): field elements, i.e. reduced mod q
         self.epsilon = [v % G.q for v in ar.lia_random(self.size, self.ebitlen + self.vbitlen + self.rbitlen, self.rs)]
-        self.Ap = pow(g, self.alpha, G.p) * ar.g_exp_prod(G, h, self.epsilon) % G.p
+        self.Ap = ar.g_exp(G, g, self.alpha) * ar.g_exp_prod(G, h, self.epsilon) % G.p
 
     def set_instance(self, pkey, w, wp, s=None):
         self.pkey, self.w, self.wp, self.s = pkey, w, wp, s
@@ -143,9 +143,9 @@ class PoSBasicTW:
         e2 = [a * c % G.q for a, c in zip(yp, self.epsilon)]
         self.Bp = ar.g_mul(G, ar.g_exp(G, g, e1), ar.g_exp(G, h0, e2))
         self.gamma = ar.ring_random_element(G, self.rs, self.rbitlen)
-        self.Cp = pow(g, self.gamma, G.p)
+        self.Cp = ar.g_exp(G, g, self.gamma)
         self.delta = ar.ring_random_element(G, self.rs, self.rbitlen)
-        self.Dp = pow(g, self.delta, G.p)
+        self.Dp = ar.g_exp(G, g, self.delta)
         self.phi = _ring_random(G, _ring_shape(self.pkey), self.rs, self.rbitlen)
         self.Fp = ar.g_mul(G, ar.g_exp(G, self.pkey, _rneg(G, self.phi)), ar.g_exp_prod(G, self.wp, self.epsilon))
         return self.commitment_tree()
@@ -221,13 +221,13 @@ class PoSBasicTW:
         eprod = 1
         for x in self.e:
             eprod = eprod * x % G.q
-        D = self.B[-1] * pow(pow(h0, eprod, p), -1, p) % p
-        vA = pow(self.A, v, p) * self.Ap % p == pow(g, self.k_A, p) * ar.g_exp_prod(G, h, self.k_E) % p
+        D = self.B[-1] * pow(ar.g_exp(G, h0, eprod), -1, p) % p
+        vA = ar.g_exp(G, self.A, v) * self.Ap % p == ar.g_exp(G, g, self.k_A) * ar.g_exp_prod(G, h, self.k_E) % p
         left = ar.g_mul(G, ar.g_exp(G, self.B, v), self.Bp)
         right = ar.g_mul(G, ar.g_exp(G, g, self.k_B), ar.g_exp(G, [h0] + self.B[:-1], self.k_E))
         vB = left == right
-        vC = pow(C, v, p) * self.Cp % p == pow(g, self.k_C, p)
-        vD = pow(D, v, p) * self.Dp % p == pow(g, self.k_D, p)
+        vC = ar.g_exp(G, C, v) * self.Cp % p == ar.g_exp(G, g, self.k_C)
+        vD = ar.g_exp(G, D, v) * self.Dp % p == ar.g_exp(G, g, self.k_D)
         lhsF = ar.g_mul(G, ar.g_exp(G, self.F, v), self.Fp)
         rhsF = ar.g_mul(G, ar.g_exp(G, self.pkey, _rneg(G, self.k_F)), ar.g_exp_prod(G, self.wp, self.k_E))
         vF = lhsF == rhsF
