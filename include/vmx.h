@@ -93,6 +93,9 @@ size_t vmx_garr_size(const vmx_garr* a);
  * (mixnet/ShufflerElGamalSession.java:407; hvzk/PoSBasicTW.java:447,606,608,644,646,1030).
  * The window table for `base` is built on first use and cached in the ctx. */
 int vmx_exp_fixed(vmx_ctx* ctx, const uint8_t* base_be, const vmx_rarr* e, vmx_garr** out);
+/* PGroupElement.exp(PRingElement) on a single element (hvzk/PoSBasicTW.java:481,668,679,690,1014,1021,
+ * 1048,1055,1063): uses the cached table of `base` if one exists, else a windowed ladder. */
+int vmx_elem_exp(vmx_ctx* ctx, const uint8_t* base_be, const uint8_t* e_be, uint8_t* out_be);
 /* Build (or resize) the table of `base` ahead of time for arrays of about n_hint exponents:
  * the analogue of VMG.fpowm_precomp in the reference's native seam. */
 int vmx_fixed_precompute(vmx_ctx* ctx, const uint8_t* base_be, size_t n_hint);

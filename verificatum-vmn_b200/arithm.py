@@ -629,13 +629,9 @@ class PGroupElement:
             return PGroupElementArray(self.group, h)
         if isinstance(e, int):
             e = self.group.pRing.toElement(e)
-        a = self._as_array()
-        try:
-            h = C.c_void_p()
-            nat.check(lib.vmx_exp_scalar(a, _be(e.value, self.group.ring_bytes), C.byref(h)))
-        finally:
-            lib.vmx_garr_free(a)
-        return self._single(h)
+        buf = np.empty(self.group.elem_bytes, dtype=np.uint8)
+        nat.check(lib.vmx_elem_exp(self.group.ctx, self._be(), _be(e.value, self.group.ring_bytes), _ptr(buf)))
+        return PGroupElement(self.group, int.from_bytes(buf.tobytes(), "big"))
 
     def mul(self, o: "PGroupElement") -> "PGroupElement":
         lib = self.group._lib

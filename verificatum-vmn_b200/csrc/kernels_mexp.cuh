@@ -65,18 +65,24 @@ __global__ void k_chunk_count(const uint32_t* __restrict__ seg_off, size_t nseg,
   if (len > (uint32_t)K) atomicMax(&stats[0], len);
 }
 
-// 4b. balanced chunk descriptors.  chunk_off = exclusive scan of nchunks.
+// 4b. balanced chunk descriptors, one thread per CHUNK (a single huge segment -- prod() -- must
+// not serialise on one thread): the owning segment is found by binary search in chunk_off
+// (exclusive scan of nchunks, nseg + 1 entries).
 struct Chunk { uint32_t start, len; };
 __global__ void k_chunk_fill(const uint32_t* __restrict__ seg_off, const uint32_t* __restrict__ chunk_off, size_t nseg,
                              Chunk* __restrict__ chunks) {
-  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nseg) return;
-  const uint32_t b = seg_off[s], len = seg_off[s + 1] - b;
-  const uint32_t c0 = chunk_off[s], m = chunk_off[s + 1] - c0;
-  for (uint32_t j = 0; j < m; j++) {
-    const uint32_t lo = (uint32_t)((uint64_t)len * j / m), hi = (uint32_t)((uint64_t)len * (j + 1) / m);
-    chunks[c0 + j] = Chunk{b + lo, hi - lo};
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= chunk_off[nseg]) return;
+  size_t lo = 0, hi = nseg;  // largest s with chunk_off[s] <= c
+  while (hi - lo > 1) {
+    const size_t mid = (lo + hi) >> 1;
+    if (chunk_off[mid] <= c) lo = mid; else hi = mid;
   }
+  const size_t s = lo;
+  const uint32_t b = seg_off[s], len = seg_off[s + 1] - b;
+  const uint32_t c0 = chunk_off[s], m = chunk_off[s + 1] - c0, j = (uint32_t)c - c0;
+  const uint32_t l0 = (uint32_t)((uint64_t)len * j / m), l1 = (uint32_t)((uint64_t)len * (j + 1) / m);
+  chunks[c] = Chunk{b + l0, l1 - l0};
 }
 
 // 4c. one thread per chunk: out[c] = prod_{k < len} V[idx[start + k]]   (len = 0 -> one).

@@ -208,7 +208,7 @@ static int seg_product(vmx_ctx* c, const Modulus& Mod, const uint32_t* V, size_t
                reinterpret_cast<uint32_t*>(c->d_flag));
     VMX_CHECK_LAUNCH();
     VMX_TRY(exclusive_scan(c, chunk_off.as<uint32_t>(), nseg + 1));
-    VMX_LAUNCH(c, k_chunk_fill, nblocks(nseg, 256), 256, 0, cur_off, chunk_off.as<uint32_t>(), nseg,
+    VMX_LAUNCH(c, k_chunk_fill, nblocks(nch_bound, 256), 256, 0, cur_off, chunk_off.as<uint32_t>(), nseg,
                chunks.as<Chunk>());
     VMX_CHECK_LAUNCH();
     VMX_TRY(read_flags(c, 1));
@@ -984,6 +984,35 @@ int vmx_exp_fixed(vmx_ctx* c, const uint8_t* base_be, const vmx_rarr* e, vmx_gar
   if (e->n) VMX_DISPATCH(c->nl, VMX_TRY(exp_fixed_run<N>(c, T, e, ebits, r->d, r->cap)));
   *out = guard.release();
   return VMX_OK;
+}
+
+// PGroupElement.exp(PRingElement) for ONE element: through the cached window table of the base
+// when there is one (g, h0, the public key), else on the warp-cooperative multiplier.
+int vmx_elem_exp(vmx_ctx* c, const uint8_t* base_be, const uint8_t* e_be, uint8_t* out_be) {
+  VMX_ENTER(c);
+  if (!base_be || !e_be || !out_be) return VMX_EARG;
+  bool have = false;
+  FixedTable T;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->tables.find(std::string(reinterpret_cast<const char*>(base_be), c->eb));
+    if (it != c->tables.end()) { T = it->second; have = true; }
+  }
+  vmx_rarr* e = nullptr;
+  VMX_TRY(vmx_rarr_from_bytes(c, 1, e_be, &e));
+  std::unique_ptr<vmx_rarr, void (*)(vmx_rarr*)> ge(e, vmx_rarr_free);
+  ElemBuf res;
+  VMX_TRY(res.alloc_elems(c, 1));
+  int ebits = 0;
+  VMX_TRY(rarr_bitlen(e, &ebits));
+  if (have) {
+    VMX_DISPATCH(c->nl, VMX_TRY(exp_fixed_run<N>(c, T, e, ebits, res.d(), res.cap)));
+  } else {
+    ElemBuf base;
+    VMX_TRY(upload_one(c, base_be, true, base));
+    VMX_DISPATCH(c->nl, VMX_TRY(exp_var_run<N>(c, base.d(), base.cap, e->d, e->cap, true, ebits, 1, res.d(), res.cap)));
+  }
+  return download_one(c, res.d(), res.cap, 0, true, out_be);
 }
 
 int vmx_fixed_precompute(vmx_ctx* c, const uint8_t* base_be, size_t n_hint) {
