@@ -96,6 +96,10 @@ int vmx_exp_fixed(vmx_ctx* ctx, const uint8_t* base_be, const vmx_rarr* e, vmx_g
 /* PGroupElement.exp(PRingElement) on a single element (hvzk/PoSBasicTW.java:481,668,679,690,1014,1021,
  * 1048,1055,1063): uses the cached table of `base` if one exists, else a windowed ladder. */
 int vmx_elem_exp(vmx_ctx* ctx, const uint8_t* base_be, const uint8_t* e_be, uint8_t* out_be);
+/* PGroupElement.inv() on a single element (hvzk/PoSBasicTW.java:1013-1014, PoSCBasicTW.java:668-669,
+ * elgamal/DistrElGamalSessionBasic.java:697,724): O(1) per proof, binary extended Euclid on the host
+ * (the reference inverts a host BigInteger here too).  Arrays are inverted by vmx_inv on the device. */
+int vmx_elem_inv(vmx_ctx* ctx, const uint8_t* in_be, uint8_t* out_be);
 /* Build (or resize) the table of `base` ahead of time for arrays of about n_hint exponents:
  * the analogue of VMG.fpowm_precomp in the reference's native seam. */
 int vmx_fixed_precompute(vmx_ctx* ctx, const uint8_t* base_be, size_t n_hint);

@@ -307,3 +307,356 @@ def verify_shuffle(G, params: Params, pkey, w, h, proof: dict) -> bool:
         return V.verify(bt.from_bytes(proof["reply"]))
     except bt.EIOError:
         return False
+
+
+# ---------------------------------------------------------------- PoSCBasicTW
+class PoSCBasicTW:
+    """hvzk/PoSCBasicTW.java:306-727: proof of a shuffle of commitments u = (h * g^r) permuted.
+    Order in which the prover draws from its random source (:363-446): b, alpha, epsilon, beta,
+    gamma, delta."""
+
+    def __init__(self, G, vbitlen, ebitlen, rbitlen, prg_hash, rs):
+        self.G, self.vbitlen, self.ebitlen, self.rbitlen, self.prg_hash, self.rs = G, vbitlen, ebitlen, rbitlen, prg_hash, rs
+
+    def set_instance(self, g, h, u, r=None, pi=None):
+        self.g, self.h, self.u, self.r, self.pi, self.size = g, h, u, r, pi, len(h)
+
+    def set_batch_vector(self, seed: bytes):
+        self.e = batch_vector(self.prg_hash, seed, self.size, self.ebitlen)
+
+    # :363-446
+    def commit(self, seed: bytes) -> bt.ByteTree:
+        G, g, h = self.G, self.g, self.h
+        self.set_batch_vector(seed)
+        self.ipe = ar.permute(self.e, ar.perm_inv(self.pi))
+        h0 = h[0]
+        self.b = ar.ring_random_array(G, self.size, self.rs, self.rbitlen)
+        x, self.d = ar.r_rec_lin(G, self.b, self.ipe)
+        y = ar.r_prods(G, self.ipe)
+        self.B = ar.g_mul(G, ar.g_exp(G, g, x), ar.g_exp(G, h0, y))
+        self.alpha = ar.ring_random_element(G, self.rs, self.rbitlen)
+        self.epsilon = [v % G.q for v in ar.lia_random(self.size, self.ebitlen + self.vbitlen + self.rbitlen, self.rs)]
+        self.Ap = ar.g_exp(G, g, self.alpha) * ar.g_exp_prod(G, h, self.epsilon) % G.p
+        self.beta = ar.ring_random_array(G, self.size, self.rs, self.rbitlen)
+        xp = [0] + x[:-1]
+        yp = [1] + y[:-1]
+        e1 = [(bb + a * c) % G.q for bb, a, c in zip(self.beta, xp, self.epsilon)]
+        e2 = [a * c % G.q for a, c in zip(yp, self.epsilon)]
+        self.Bp = ar.g_mul(G, ar.g_exp(G, g, e1), ar.g_exp(G, h0, e2))
+        self.gamma = ar.ring_random_element(G, self.rs, self.rbitlen)
+        self.Cp = ar.g_exp(G, g, self.gamma)
+        self.delta = ar.ring_random_element(G, self.rs, self.rbitlen)
+        self.Dp = ar.g_exp(G, g, self.delta)
+        return self.commitment_tree()
+
+    def commitment_tree(self) -> bt.ByteTree:
+        G = self.G
+        return bt.node(ar.array_tree(G, self.B), ar.elem_tree(G, self.Ap), ar.array_tree(G, self.Bp),
+                       ar.elem_tree(G, self.Cp), ar.elem_tree(G, self.Dp))
+
+    # :464-500
+    def set_commitment(self, t: bt.ByteTree) -> bt.ByteTree:
+        G = self.G
+        try:
+            if t.is_leaf() or len(t.children) < 5:
+                raise ar.FormatError("commitment arity")
+            c = t.children
+            self.B = ar.parse_array(G, c[0], self.size)
+            self.Ap = ar.parse_elem(G, c[1])
+            self.Bp = ar.parse_array(G, c[2], self.size)
+            self.Cp = ar.parse_elem(G, c[3])
+            self.Dp = ar.parse_elem(G, c[4])
+        except ar.FormatError:
+            self.B = [1] * self.size
+            self.Bp = [1] * self.size
+            self.Ap = self.Cp = self.Dp = 1
+        return self.commitment_tree()
+
+    def set_challenge(self, v: int):
+        assert 0 <= v and v.bit_length() <= self.vbitlen, "Malformed challenge!"
+        self.v = v % self.G.q
+
+    # :607-636
+    def reply(self, v: int) -> bt.ByteTree:
+        G = self.G
+        self.set_challenge(v)
+        v = self.v
+        a = ar.r_inner(G, self.r, self.ipe)
+        c = sum(self.r) % G.q
+        self.k_A = (a * v + self.alpha) % G.q
+        self.k_B = [(x * v + y) % G.q for x, y in zip(self.b, self.beta)]
+        self.k_C = (c * v + self.gamma) % G.q
+        self.k_D = (self.d * v + self.delta) % G.q
+        self.k_E = [(x * v + y) % G.q for x, y in zip(self.ipe, self.epsilon)]
+        return bt.node(ar.ring_tree(G, self.k_A), ar.ring_array_tree(G, self.k_B), ar.ring_tree(G, self.k_C),
+                       ar.ring_tree(G, self.k_D), ar.ring_array_tree(G, self.k_E))
+
+    # :646-727  (checks are short-circuited in the reference; the verdict is their conjunction)
+    def verify(self, t: bt.ByteTree) -> bool:
+        G, g, h, u, p = self.G, self.g, self.h, self.u, self.G.p
+        try:
+            if t.is_leaf() or len(t.children) < 5:
+                raise ar.FormatError("reply arity")
+            c = t.children
+            self.k_A = ar.parse_ring(G, c[0])
+            self.k_B = ar.parse_ring_array(G, c[1], self.size)
+            self.k_C = ar.parse_ring(G, c[2])
+            self.k_D = ar.parse_ring(G, c[3])
+            self.k_E = ar.parse_ring_array(G, c[4], self.size)
+        except ar.FormatError:
+            return False
+        v, h0 = self.v, h[0]
+        A = ar.g_exp_prod(G, u, self.e)
+        C = ar.g_prod(G, u) * pow(ar.g_prod(G, h), -1, p) % p
+        eprod = 1
+        for x in self.e:
+            eprod = eprod * x % G.q
+        D = self.B[-1] * pow(pow(h0, eprod, p), -1, p) % p
+        vA = pow(A, v, p) * self.Ap % p == pow(g, self.k_A, p) * ar.g_exp_prod(G, h, self.k_E) % p
+        left = ar.g_mul(G, ar.g_exp(G, self.B, v), self.Bp)
+        right = ar.g_mul(G, ar.g_exp(G, g, self.k_B), ar.g_exp(G, [h0] + self.B[:-1], self.k_E))
+        vB = left == right
+        vC = pow(C, v, p) * self.Cp % p == pow(g, self.k_C, p)
+        vD = pow(D, v, p) * self.Dp % p == pow(g, self.k_D, p)
+        self.verdicts = (vA, vB, vC, vD)
+        return all(self.verdicts)
+
+
+# ---------------------------------------------------------------- CCPoSBasicW
+class CCPoSBasicW:
+    """hvzk/CCPoSBasicW.java:268-584: commitment-consistent proof of a shuffle (the permutation is
+    fixed by the commitment u; only multi-exponentiations)."""
+
+    def __init__(self, G, vbitlen, ebitlen, rbitlen, prg_hash):
+        self.G, self.vbitlen, self.ebitlen, self.rbitlen, self.prg_hash = G, vbitlen, ebitlen, rbitlen, prg_hash
+
+    def set_instance(self, g, h, u, pkey, w, wp, r=None, pi=None, s=None):
+        self.g, self.h, self.u, self.pkey, self.w, self.wp = g, h, u, pkey, w, wp
+        self.r, self.pi, self.s, self.size = r, pi, s, len(h)
+
+    def set_batch_vector(self, seed: bytes):
+        self.e = batch_vector(self.prg_hash, seed, self.size, self.ebitlen)
+
+    # :344-396
+    def commit(self, seed: bytes, rs) -> bt.ByteTree:
+        G = self.G
+        self.set_batch_vector(seed)
+        self.ipe = ar.permute(self.e, ar.perm_inv(self.pi))
+        self.alpha = ar.ring_random_element(G, rs, self.rbitlen)
+        self.epsilon = [v % G.q for v in ar.lia_random(self.size, self.ebitlen + self.vbitlen + self.rbitlen, rs)]
+        self.Ap = pow(self.g, self.alpha, G.p) * ar.g_exp_prod(G, self.h, self.epsilon) % G.p
+        self.beta = _ring_random(G, _ring_shape(self.pkey), rs, self.rbitlen)
+        self.Bp = ar.g_mul(G, ar.g_exp(G, self.pkey, _rneg(G, self.beta)), ar.g_exp_prod(G, self.wp, self.epsilon))
+        return self.commitment_tree()
+
+    def commitment_tree(self) -> bt.ByteTree:
+        return bt.node(ar.elem_tree(self.G, self.Ap), ar.elem_tree(self.G, self.Bp))
+
+    # :407-430
+    def set_commitment(self, t: bt.ByteTree) -> bt.ByteTree:
+        G = self.G
+        try:
+            if t.is_leaf() or len(t.children) < 2:
+                raise ar.FormatError("commitment arity")
+            self.Ap = ar.parse_elem(G, t.children[0])
+            self.Bp = ar.parse_elem(G, t.children[1], self.pkey)
+        except ar.FormatError:
+            self.Ap = 1
+            self.Bp = ar.gmap(lambda _: 1, self.pkey)
+        return self.commitment_tree()
+
+    def set_challenge(self, v: int):
+        assert 0 <= v and v.bit_length() <= self.vbitlen, "Malformed challenge!"
+        self.v = v % self.G.q
+
+    # :462-485
+    def reply(self, v: int) -> bt.ByteTree:
+        G = self.G
+        self.set_challenge(v)
+        v = self.v
+        a = ar.r_inner(G, self.r, self.ipe)
+        b = ar.r_inner(G, self.s, self.e)
+        self.k_A = (a * v + self.alpha) % G.q
+        self.k_B = _rmuladd(G, b, v, self.beta)
+        self.k_E = [(x * v + y) % G.q for x, y in zip(self.ipe, self.epsilon)]
+        return bt.node(ar.ring_tree(G, self.k_A), ar.ring_tree(G, self.k_B), ar.ring_array_tree(G, self.k_E))
+
+    # :493-506 (raisedu == null)
+    def compute_AB(self):
+        self.A = ar.g_exp_prod(self.G, self.u, self.e)
+        self.B = ar.g_exp_prod(self.G, self.w, self.e)
+
+    # :519-584 (raisedExponent == null)
+    def verify(self, t: bt.ByteTree) -> bool:
+        G, p = self.G, self.G.p
+        try:
+            if t.is_leaf() or len(t.children) < 3:
+                raise ar.FormatError("reply arity")
+            self.k_A = ar.parse_ring(G, t.children[0])
+            self.k_B = ar.parse_ring(G, t.children[1], _ring_shape(self.pkey))
+            self.k_E = ar.parse_ring_array(G, t.children[2], self.size)
+        except ar.FormatError:
+            return False
+        v = self.v
+        vA = pow(self.A, v, p) * self.Ap % p == pow(self.g, self.k_A, p) * ar.g_exp_prod(G, self.h, self.k_E) % p
+        lhs = ar.g_mul(G, ar.g_exp(G, self.B, v), self.Bp)
+        rhs = ar.g_mul(G, ar.g_exp(G, self.pkey, _rneg(G, self.k_B)), ar.g_exp_prod(G, self.wp, self.k_E))
+        vB = lhs == rhs
+        self.verdicts = (vA, vB)
+        return vA and vB
+
+
+# ---------------------------------------------------------------- decryption factors and their proof
+# ODD_PRIME_TABLE (:199-215): the odd primes up to 1009
+_ODD_PRIMES = [n for n in range(3, 1010, 2) if all(n % d for d in range(3, int(n ** 0.5) + 1, 2))]
+
+
+def prime_log(number: int, prime: int) -> int:
+    """elgamal/DistrElGamalSessionBasic.java:290-302: largest power of `prime` that is <= number."""
+    a = b = 1
+    while b <= number:
+        a = b
+        b *= prime
+    return a
+
+
+def prod_factor(q: int, k: int) -> int:
+    """:304-325."""
+    res, prime, i = 1, 2, 0
+    while prime <= k:
+        res *= prime_log(k, prime)
+        prime = _ODD_PRIMES[i]
+        i += 1
+    return res * res % q
+
+
+def modified_lagrange_coefficients(q: int, correct, k: int, threshold: int):
+    """:327-452: small signed integers; correct[1..k]."""
+    pf = prod_factor(q, k)
+    out = []
+    i = 1
+    while len(out) < threshold and i <= k:
+        if correct[i]:
+            res, t, l = pf, 0, 1
+            while t < threshold and l <= k:
+                if correct[l]:
+                    if l != i:
+                        res = res * l % q
+                        res = res * pow((l - i) % q, -1, q) % q
+                    t += 1
+                l += 1
+            alt = res - q
+            out.append(alt if abs(alt) < res else res)
+        i += 1
+    if len(out) < threshold:
+        raise ValueError("Attempting to combine too few decryption factors!")
+    return out
+
+
+def decryption_factors(G, u, x: int, inverse_factor_scalar: int):
+    """elgamal/DistrElGamalSession.java:377-385: f_i = u_i^{-x * c} for all first components."""
+    ex = (-x * inverse_factor_scalar) % G.q
+    return ar.g_exp(G, u, ex)
+
+
+def combine_decryption_factors(G, factors: dict, correct, k: int, threshold: int):
+    """:454-503: element-wise prod_j f_j^{lambda_j} with small signed integers."""
+    ints = modified_lagrange_coefficients(G.q, correct, k, threshold)
+    bases = [factors[i] for i in range(1, k + 1) if correct[i]][:threshold]
+    out = None
+    for b, lam in zip(bases, ints):
+        t = ar.g_exp(G, b, lam % G.q)
+        out = t if out is None else ar.g_mul(G, out, t)
+    return out
+
+
+class DistrElGamalSessionBasic:
+    """elgamal/DistrElGamalSessionBasic.java:59: batched sigma proof that party l's decryption
+    factors f_l = u^{-x_l c} are consistent with y_l = g^{x_l} (c = inverseFactor)."""
+
+    def __init__(self, G, j, k, threshold, ebitlen, rbitlen, prg_hash, g, y: dict, u, x=None):
+        self.G, self.j, self.k, self.threshold, self.ebitlen, self.rbitlen, self.prg_hash = G, j, k, threshold, ebitlen, rbitlen, prg_hash
+        self.g, self.y, self.u, self.x = g, y, u, x
+        self.inverse_factor = pow(prod_factor(G.q, k), -1, G.q)      # :243-249
+        self.f, self.B, self.yp, self.Bp, self.k_x = {}, {}, {}, {}, {}
+        self.verdicts = {l: True for l in range(1, k + 1)}
+
+    def set_batch_vector(self, seed: bytes):                         # :513-518
+        self.e = batch_vector(self.prg_hash, seed, ar.size_of(self.u), self.ebitlen)
+
+    def batch_input(self):                                           # :524-526
+        self.A = ar.g_exp_prod(self.G, self.u, self.e)
+
+    def commit(self, rs) -> bt.ByteTree:                             # :534-540
+        G = self.G
+        self.r = ar.ring_random_element(G, rs, self.rbitlen)
+        self.yp[self.j] = pow(self.g, self.r, G.p)
+        self.Bp[self.j] = ar.g_exp(G, self.A, self.r)
+        return self.commitment_tree(self.j)
+
+    def commitment_tree(self, l) -> bt.ByteTree:
+        return bt.node(ar.elem_tree(self.G, self.yp[l]), ar.elem_tree(self.G, self.Bp[l]))
+
+    def set_commitment(self, l, t: bt.ByteTree):                     # :549-565
+        G = self.G
+        try:
+            if t.is_leaf() or len(t.children) < 2:
+                raise ar.FormatError("commitment arity")
+            self.yp[l] = ar.parse_elem(G, t.children[0])
+            self.Bp[l] = ar.parse_elem(G, t.children[1], self.A)
+        except ar.FormatError:
+            self.verdicts[l] = False
+            self.yp[l] = 1
+            self.Bp[l] = ar.gmap(lambda _: 1, self.A)
+
+    def reply(self, v: int) -> bt.ByteTree:                          # :595-598
+        G = self.G
+        self.k_x[self.j] = ((-self.x) * self.inverse_factor % G.q * (v % G.q) + self.r) % G.q
+        return ar.ring_tree(G, self.k_x[self.j])
+
+    def set_reply(self, l, t: bt.ByteTree):                          # :606-614
+        try:
+            self.k_x[l] = ar.parse_ring(self.G, t)
+        except ar.FormatError:
+            self.k_x[l] = 0
+            self.verdicts[l] = False
+
+    def batch(self, l):                                              # :707-709
+        self.B[l] = ar.g_exp_prod(self.G, self.f[l], self.e)
+
+    def verify(self, l, v: int) -> bool:                             # :718-727
+        G, p = self.G, self.G.p
+        if not self.verdicts[l]:
+            return False
+        pfev = v % G.q
+        lhs1 = pow(pow(self.y[l], -1, p), self.inverse_factor * pfev % G.q, p) * self.yp[l] % p
+        ok1 = lhs1 == pow(self.g, self.k_x[l], p)
+        lhs2 = ar.g_mul(G, ar.g_exp(G, self.B[l], pfev), self.Bp[l])
+        ok2 = lhs2 == ar.g_exp(G, self.A, self.k_x[l])
+        return ok1 and ok2
+
+    def combine(self, correct):                                      # :642-678
+        G, p = self.G, self.G.p
+        ints = modified_lagrange_coefficients(G.q, correct, self.k, self.threshold)
+        exps = [i % G.q for i in ints]
+        self.combinedyp = 1
+        self.combinedBp = ar.gmap(lambda _: 1, self.A)
+        self.combinedk_x = 0
+        t, l = 0, 1
+        while t < self.threshold and l <= self.k:
+            if correct[l]:
+                self.combinedyp = self.combinedyp * pow(self.yp[l], exps[t], p) % p
+                self.combinedBp = ar.g_mul(G, self.combinedBp, ar.g_exp(G, self.Bp[l], exps[t]))
+                self.combinedk_x = (self.combinedk_x + self.k_x[l] * exps[t]) % G.q
+                t += 1
+            l += 1
+
+    def batch_combined(self, combinedf):                             # :683-685
+        self.combinedB = ar.g_exp_prod(self.G, combinedf, self.e)
+
+    def verify_combined(self, combinedy, v: int) -> bool:            # :693-700
+        G, p = self.G, self.G.p
+        pfev = v % G.q
+        ok1 = pow(pow(combinedy, -1, p), pfev, p) * self.combinedyp % p == pow(self.g, self.combinedk_x, p)
+        ok2 = ar.g_mul(G, ar.g_exp(G, self.combinedB, pfev), self.combinedBp) == ar.g_exp(G, self.A, self.combinedk_x)
+        return ok1 and ok2

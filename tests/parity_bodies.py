@@ -7,6 +7,7 @@ import random
 import numpy as np
 
 from oracle import arithm as oar
+from oracle import bytetree as obt
 from oracle import protocols as opr
 from oracle.crypto import SeededRandomSource, PRGHeuristic as OPRG
 from tests.cases import EngineCase, OracleCase, col_values, group_params, seed
@@ -99,6 +100,12 @@ def edge_cases(vmx, bits):
         assert False
     except A.ArithmFormatException:
         pass
+    # single-element inversion (host binary Euclid in the engine) against Python, incl. 1 and p-1
+    import random
+    rnd = random.Random(bits)
+    for v in [1, p - 1, 2, g, p - 2] + [rnd.randrange(1, p) for _ in range(12)]:
+        assert A.PGroupElement(G, v).inv().value == pow(v, -1, p)
+    assert [e.value for e in X.inv().elements()] == [pow(e.value, -1, p) for e in X.elements()]
     # size mismatch is an error status, not a crash
     try:
         X.mul(single)
@@ -214,3 +221,197 @@ def accept_reject_properties(vmx, bits, n):
     raw = bytearray(proof.reply)
     raw[-7] ^= 0x10
     assert verifier.verify(1, ec.w, dataclasses.replace(proof, reply=bytes(raw)), generators=h)[0] is False
+
+
+def _bt_bytes(t) -> bytes:
+    return t.to_bytes()
+
+
+def _commitment_instance(vmx, bits, n, label):
+    """u = (h * g^r) permuted, built on both sides from the same seeds (mixnet/PermutationCommitment.java:191-215)."""
+    A = vmx.arithm
+    cr = vmx.crypto
+    oc = OracleCase(bits, n, label)
+    ec = EngineCase(vmx, bits, n, label)
+    OG = oc.G
+    h = ec.session(None).deriveGenerators(n)
+    rs = cr.PRGHeuristic()
+    rs.setSeed(seed(label + "/commit"))
+    ors = SeededRandomSource(seed(label + "/commit"))
+    r = ec.G.getPRing().randomElementArray(n, rs, 100)
+    pi = A.Permutation.random(n, rs, 100)
+    o_r = oar.ring_random_array(OG, n, ors, 100)
+    o_pi = oar.permutation_random(n, ors, 100)
+    tmp = ec.G.getg().exp(r)
+    tmp2 = h.mul(tmp)
+    u = tmp2.permute(pi)
+    o_u = oar.permute(oar.g_mul(OG, oc.h, oar.g_exp(OG, OG.g, o_r)), o_pi)
+    assert col_values(u) == o_u
+    return oc, ec, h, (r, pi, u), (o_r, o_pi, o_u), rs, ors
+
+
+def posc_parity(vmx, bits, n):
+    """PoSCBasicTW (hvzk/PoSCBasicTW.java): identical commitment and reply bytes, cross verification,
+    rejection of a corrupted reply (what hvzk/TestPoSCBasicTW.java:147-163 asserts) on both sides."""
+    hv = importlib.import_module("verificatum-vmn_b200.hvzk")
+    cr = vmx.crypto
+    oc, ec, h, (r, pi, u), (o_r, o_pi, o_u), rs, ors = _commitment_instance(vmx, bits, n, "posc")
+    OG = oc.G
+    P = hv.PoSCBasicTW(256, 256, 100, cr.PRGHeuristic(), rs)
+    P.setInstance(ec.G.getg(), h, u, r, pi)
+    OP = opr.PoSCBasicTW(OG, 256, 256, 100, "sha256", ors)
+    OP.set_instance(OG.g, oc.h, o_u, o_r, o_pi)
+    c = _bt_bytes(P.commit(seed("posc/batch")))
+    oc_ = OP.commit(seed("posc/batch")).to_bytes()
+    assert c == oc_
+    v = int.from_bytes(seed("posc/challenge"), "big")
+    rep = _bt_bytes(P.reply(v))
+    assert rep == OP.reply(v).to_bytes()
+    # engine verifier on the oracle's bytes and vice versa
+    V = hv.PoSCBasicTW(256, 256, 100, cr.PRGHeuristic(), None)
+    V.setInstance(ec.G.getg(), h, u)
+    V.setBatchVector(seed("posc/batch"))
+    assert _bt_bytes(V.setCommitment(vmx.eio.ByteTreeReader(oc_))) == oc_
+    V.setChallenge(v)
+    assert V.verify(vmx.eio.ByteTreeReader(rep)) is True
+    OV = opr.PoSCBasicTW(OG, 256, 256, 100, "sha256", None)
+    OV.set_instance(OG.g, oc.h, o_u)
+    OV.set_batch_vector(seed("posc/batch"))
+    OV.set_commitment(obt.from_bytes(c))
+    OV.set_challenge(v)
+    assert OV.verify(obt.from_bytes(rep)) is True
+    bad = bytearray(rep)
+    bad[len(bad) // 3] ^= 1
+    V.setBatchVector(seed("posc/batch"))
+    assert V.verify(vmx.eio.ByteTreeReader(bytes(bad))) is False
+    assert OV.verify(obt.from_bytes(bytes(bad))) is False
+
+
+def ccpos_parity(vmx, bits, n):
+    """CCPoSBasicW (hvzk/CCPoSBasicW.java): commitment-consistent proof of a shuffle."""
+    A = vmx.arithm
+    hv = importlib.import_module("verificatum-vmn_b200.hvzk")
+    cr = vmx.crypto
+    oc, ec, h, (r, pi, u), (o_r, o_pi, o_u), rs, ors = _commitment_instance(vmx, bits, n, "ccpos")
+    OG = oc.G
+    # re-encrypt and permute with the committed permutation (mixnet/ShufflerElGamalSession.java:771-795)
+    s = ec.G.getPRing().randomElementArray(n, rs, 100)
+    o_s = oar.ring_random_array(OG, n, ors, 100)
+    factors = ec.pk.exp(s)
+    reenc = ec.w.mul(factors)
+    piinv = pi.inv()
+    wp = reenc.permute(piinv)
+    o_wp = oar.permute(oar.g_mul(OG, oc.w, oar.g_exp(OG, oc.pk, o_s)), oar.perm_inv(o_pi))
+    assert col_values(wp) == o_wp
+    P = hv.CCPoSBasicW(256, 256, 100, cr.PRGHeuristic())
+    P.setInstance(ec.G.getg(), h, u, ec.pk, ec.w, wp, r, pi, s)
+    OP = opr.CCPoSBasicW(OG, 256, 256, 100, "sha256")
+    OP.set_instance(OG.g, oc.h, o_u, oc.pk, oc.w, o_wp, o_r, o_pi, o_s)
+    c = _bt_bytes(P.commit(seed("ccpos/batch"), rs))
+    oc_ = OP.commit(seed("ccpos/batch"), ors).to_bytes()
+    assert c == oc_
+    v = int.from_bytes(seed("ccpos/challenge"), "big")
+    rep = _bt_bytes(P.reply(v))
+    assert rep == OP.reply(v).to_bytes()
+    V = hv.CCPoSBasicW(256, 256, 100, cr.PRGHeuristic())
+    V.setInstance(ec.G.getg(), h, u, ec.pk, ec.w, wp)
+    V.setBatchVector(seed("ccpos/batch"))
+    V.computeAB()
+    V.setCommitment(vmx.eio.ByteTreeReader(oc_))
+    V.setChallenge(v)
+    assert V.verify(vmx.eio.ByteTreeReader(rep)) is True
+    OV = opr.CCPoSBasicW(OG, 256, 256, 100, "sha256")
+    OV.set_instance(OG.g, oc.h, o_u, oc.pk, oc.w, o_wp)
+    OV.set_batch_vector(seed("ccpos/batch"))
+    OV.compute_AB()
+    OV.set_commitment(obt.from_bytes(c))
+    OV.set_challenge(v)
+    assert OV.verify(obt.from_bytes(rep)) is True
+    bad = bytearray(rep)
+    bad[-3] ^= 0x20
+    assert V.verify(vmx.eio.ByteTreeReader(bytes(bad))) is False
+    assert OV.verify(obt.from_bytes(bytes(bad))) is False
+
+
+def decryption_parity(vmx, bits, n, k=3, threshold=2):
+    """Decryption factors, their combination with modified Lagrange coefficients and the batched proof
+    (elgamal/DistrElGamalSession.java:377-406, elgamal/DistrElGamalSessionBasic.java:465-727), k parties,
+    threshold of them combined; the plaintexts g^{m} come back."""
+    A = vmx.arithm
+    eg = importlib.import_module("verificatum-vmn_b200.elgamal")
+    cr = vmx.crypto
+    oc = OracleCase(bits, n, "dec")
+    ec = EngineCase(vmx, bits, n, "dec")
+    OG, G = oc.G, ec.G
+    p, q = OG.p, OG.q
+    R = G.getPRing()
+    # Shamir shares of the secret key oc.x: polynomial of degree threshold-1, x_l = f(l)
+    ors = SeededRandomSource(seed("dec/poly"))
+    coeffs = [oc.x] + [oar.ring_random_element(OG, ors, 100) for _ in range(threshold - 1)]
+    xs = {l: sum(c * pow(l, i, q) for i, c in enumerate(coeffs)) % q for l in range(1, k + 1)}
+    ys = {l: pow(OG.g, xs[l], p) for l in range(1, k + 1)}
+    correct = [False] + [True] * k
+    ints = opr.modified_lagrange_coefficients(q, correct, k, threshold)
+    assert ints == eg.modifiedLagrangeCoefficients(R, correct, k, threshold)
+    u, o_u = ec.w.project(0), oc.w[0]
+    # decryption factors of every party
+    f, o_f = {}, {}
+    inv_factor = pow(opr.prod_factor(q, k), -1, q)
+    for l in range(1, k + 1):
+        f[l] = eg.decryptionFactors(u, A.PFieldElement(R, xs[l]), k)
+        o_f[l] = opr.decryption_factors(OG, o_u, xs[l], inv_factor)
+        assert col_values(f[l]) == o_f[l]
+    combined = eg.combineDecryptionFactors(f, correct, k, threshold)
+    o_combined = opr.combine_decryption_factors(OG, o_f, correct, k, threshold)
+    assert col_values(combined) == o_combined
+    # plaintexts = v * combined  (mixnet/MixNetElGamalVerifyFiatShamirSession.java:1267-1275); the
+    # modified coefficients carry the factor prodFactor, cancelled by inverseFactor in the exponent
+    plain = ec.w.project(1).mul(combined)
+    o_plain = [b * pow(a, -oc.x, p) % p for a, b in zip(oc.w[0], oc.w[1])]
+    assert col_values(plain) == o_plain
+    # the proof of party j, verified by everybody (identical bytes on both sides)
+    v = int.from_bytes(seed("dec/challenge"), "big")
+    engines, oracles = {}, {}
+    g_el = G.getg()
+    y_el = {l: A.PGroupElement(G, ys[l]) for l in ys}
+    for j in range(1, k + 1):
+        E = eg.DistrElGamalSessionBasic(j, k, threshold, 256, 100, cr.PRGHeuristic())
+        E.setInstance(g_el, u, y_el, f, A.PFieldElement(R, xs[j]))
+        E.setBatchVector(seed("dec/batch"))
+        E.batchInput()
+        O = opr.DistrElGamalSessionBasic(OG, j, k, threshold, 256, 100, "sha256", OG.g, ys, o_u, xs[j])
+        O.f = o_f
+        O.set_batch_vector(seed("dec/batch"))
+        O.batch_input()
+        assert E.A.value == O.A
+        rs = cr.PRGHeuristic()
+        rs.setSeed(seed("dec/commit%d" % j))
+        c = E.commit(rs).to_bytes()
+        assert c == O.commit(SeededRandomSource(seed("dec/commit%d" % j))).to_bytes()
+        rep = E.reply(v).to_bytes()
+        assert rep == O.reply(v).to_bytes()
+        engines[j], oracles[j] = (E, c, rep), (O, c, rep)
+    # party 1 verifies everybody individually and combined
+    E1, O1 = engines[1][0], oracles[1][0]
+    for l in range(2, k + 1):
+        E1.setCommitment(l, vmx.eio.ByteTreeReader(engines[l][1]))
+        E1.setReply(l, vmx.eio.ByteTreeReader(engines[l][2]))
+        O1.set_commitment(l, obt.from_bytes(engines[l][1]))
+        O1.set_reply(l, obt.from_bytes(engines[l][2]))
+    for l in range(1, k + 1):
+        E1.batch(l)
+        O1.batch(l)
+        assert E1.B[l].value == O1.B[l]
+        assert E1.verify(l, v) is True and O1.verify(l, v) is True
+    E1.combine(correct)
+    O1.combine(correct)
+    # combinedy = the joint public key y = g^x (elgamal/DistrElGamalSession.java:422-428)
+    E1.combinedy, E1.combinedf = A.PGroupElement(G, oc.pk[1]), combined
+    E1.batchCombined()
+    O1.batch_combined(o_combined)
+    assert E1.combinedB.value == O1.combinedB
+    assert E1.verifyCombined(v) is True and O1.verify_combined(oc.pk[1], v) is True
+    # a wrong reply is rejected by both
+    E1.k_x[k] = E1.k_x[k].add(R.getONE())
+    O1.k_x[k] = (O1.k_x[k] + 1) % q
+    assert E1.verify(k, v) is False and O1.verify(k, v) is False

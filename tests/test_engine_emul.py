@@ -36,3 +36,18 @@ def test_accept_reject_larger(engine_emul):
 
 def test_group_ops_2048_small(engine_emul):
     pb.group_ops(engine_emul, 2048, 5)
+
+
+@pytest.mark.parametrize("n", [1, 19])
+def test_posc_parity(engine_emul, n):
+    pb.posc_parity(engine_emul, 512, n)
+
+
+@pytest.mark.parametrize("n", [1, 19])
+def test_ccpos_parity(engine_emul, n):
+    pb.ccpos_parity(engine_emul, 512, n)
+
+
+@pytest.mark.parametrize("n,k,t", [(1, 1, 1), (17, 3, 2), (9, 5, 3)])
+def test_decryption_parity(engine_emul, n, k, t):
+    pb.decryption_parity(engine_emul, 512, n, k, t)

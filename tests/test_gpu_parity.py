@@ -37,6 +37,22 @@ def test_transcript_parity(engine_cuda, bits, n):
     pb.transcript_parity(engine_cuda, bits, n)
 
 
+@pytest.mark.parametrize("bits,n", [(512, 100), (3072, 10)])
+def test_posc_parity(engine_cuda, bits, n):
+    """512/100 is exactly hvzk/TestPoSCBasicTW.java's instance size."""
+    pb.posc_parity(engine_cuda, bits, n)
+
+
+@pytest.mark.parametrize("bits,n", [(512, 100), (2048, 10)])
+def test_ccpos_parity(engine_cuda, bits, n):
+    pb.ccpos_parity(engine_cuda, bits, n)
+
+
+@pytest.mark.parametrize("bits,n,k,t", [(512, 60, 3, 2), (3072, 9, 3, 2), (2048, 8, 5, 3)])
+def test_decryption_parity(engine_cuda, bits, n, k, t):
+    pb.decryption_parity(engine_cuda, bits, n, k, t)
+
+
 @pytest.mark.parametrize("bits", [512, 2048, 3072])
 def test_cooperative_multiplier_matches_thread_per_element(engine_cuda, bits):
     vmx = engine_cuda

@@ -53,6 +53,7 @@ SIGNATURES = {
     "vmx_garr_size": (_SZ, [_P]),
     "vmx_exp_fixed": (C.c_int, [_P, _U8, _P, _PP]),
     "vmx_elem_exp": (C.c_int, [_P, _U8, _U8, _P]),
+    "vmx_elem_inv": (C.c_int, [_P, _U8, _P]),
     "vmx_fixed_precompute": (C.c_int, [_P, _U8, _SZ]),
     "vmx_exp_var": (C.c_int, [_P, _P, _PP]),
     "vmx_exp_scalar": (C.c_int, [_P, _U8, _PP]),

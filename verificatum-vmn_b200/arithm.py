@@ -645,14 +645,9 @@ class PGroupElement:
         return self._single(h)
 
     def inv(self) -> "PGroupElement":
-        lib = self.group._lib
-        a = self._as_array()
-        try:
-            h = C.c_void_p()
-            nat.check(lib.vmx_inv(a, C.byref(h)))
-        finally:
-            lib.vmx_garr_free(a)
-        return self._single(h)
+        buf = np.empty(self.group.elem_bytes, dtype=np.uint8)
+        nat.check(self.group._lib.vmx_elem_inv(self.group.ctx, self._be(), _ptr(buf)))
+        return PGroupElement(self.group, int.from_bytes(buf.tobytes(), "big"))
 
     def div(self, o: "PGroupElement") -> "PGroupElement":
         return self.mul(o.inv())

@@ -44,7 +44,8 @@ static inline size_t cap_for(size_t n) { return std::max<size_t>(8, (n + 7) & ~(
 
 // ------------------------------------------------------------------ tiny host bignum (setup only)
 // little-endian 32-bit limbs; used for R mod n, R^2 mod n, n0inv, p-2: O(bits) shifts at
-// context creation.  No group arithmetic is ever done on the host.
+// context creation.  No group arithmetic is done on the host, with one O(1) exception per
+// proof: the inversion of a single element (limbs_inv_mod, vmx_elem_inv).
 static bool be_to_limbs(const uint8_t* be, size_t nbytes, uint32_t* out, int N) {
   for (int j = 0; j < N; j++) out[j] = 0;
   for (size_t b = 0; b < nbytes; b++) {
@@ -80,6 +81,47 @@ static uint32_t neg_inv32(uint32_t n0) {
   uint32_t x = n0;  // n0 * x = 1 mod 2^3
   for (int i = 0; i < 5; i++) x *= 2u - n0 * x;
   return 0u - x;
+}
+static void limbs_add(uint32_t* a, const uint32_t* b, int N, uint32_t* carry_out) {
+  uint64_t c = 0;
+  for (int j = 0; j < N; j++) { const uint64_t t = (uint64_t)a[j] + b[j] + c; a[j] = (uint32_t)t; c = t >> 32; }
+  *carry_out = (uint32_t)c;
+}
+// x <- x / 2 mod n (n odd), x < n
+static void limbs_half_mod(uint32_t* x, const uint32_t* n, int N) {
+  uint32_t top = 0;
+  if (x[0] & 1) limbs_add(x, n, N, &top);
+  for (int j = 0; j < N; j++) x[j] = (x[j] >> 1) | ((j + 1 < N ? x[j + 1] : top) << 31);
+}
+// r = a^{-1} mod n for odd n and gcd(a, n) = 1 (binary extended Euclid).  The ONE piece of
+// residue arithmetic that runs on the host: PGroupElement.inv()/div() of a SINGLE element
+// (hvzk/PoSBasicTW.java:1013-1014 computes two of them per proof; the reference does the same on
+// a host BigInteger).  Array inversion is vmx_inv and runs on the device.
+static bool limbs_inv_mod(uint32_t* r, const uint32_t* a, const uint32_t* n, int N) {
+  std::vector<uint32_t> u(a, a + N), v(n, n + N), x1(N, 0), x2(N, 0);
+  x1[0] = 1;
+  auto is_one = [&](const std::vector<uint32_t>& t) { if (t[0] != 1) return false; for (int j = 1; j < N; j++) if (t[j]) return false; return true; };
+  auto is_zero = [&](const std::vector<uint32_t>& t) { for (int j = 0; j < N; j++) if (t[j]) return false; return true; };
+  if (is_zero(u)) return false;
+  auto sub_mod = [&](std::vector<uint32_t>& x, const std::vector<uint32_t>& y) {  // x = x - y mod n
+    if (limbs_cmp(x.data(), y.data(), N) < 0) { uint32_t c; limbs_add(x.data(), n, N, &c); }
+    limbs_sub(x.data(), y.data(), N);
+  };
+  for (int guard = 0; guard < 4 * 32 * N + 8; guard++) {
+    if (is_one(u)) { std::memcpy(r, x1.data(), 4 * (size_t)N); return true; }
+    if (is_one(v)) { std::memcpy(r, x2.data(), 4 * (size_t)N); return true; }
+    while (!(u[0] & 1)) {
+      for (int j = 0; j < N; j++) u[j] = (u[j] >> 1) | ((j + 1 < N ? u[j + 1] : 0u) << 31);
+      limbs_half_mod(x1.data(), n, N);
+    }
+    while (!(v[0] & 1)) {
+      for (int j = 0; j < N; j++) v[j] = (v[j] >> 1) | ((j + 1 < N ? v[j + 1] : 0u) << 31);
+      limbs_half_mod(x2.data(), n, N);
+    }
+    if (limbs_cmp(u.data(), v.data(), N) >= 0) { limbs_sub(u.data(), v.data(), N); sub_mod(x1, x2); if (is_zero(u)) return false; }
+    else { limbs_sub(v.data(), u.data(), N); sub_mod(x2, x1); }
+  }
+  return false;
 }
 // element `idx` of a limb-major host image with capacity `cap`
 static void image_put(std::vector<uint32_t>& img, size_t cap, size_t idx, const uint32_t* limbs, int N) {
@@ -1013,6 +1055,24 @@ int vmx_elem_exp(vmx_ctx* c, const uint8_t* base_be, const uint8_t* e_be, uint8_
     VMX_DISPATCH(c->nl, VMX_TRY(exp_var_run<N>(c, base.d(), base.cap, e->d, e->cap, true, ebits, 1, res.d(), res.cap)));
   }
   return download_one(c, res.d(), res.cap, 0, true, out_be);
+}
+
+// PGroupElement.inv() of ONE element (the divisions C = prod u / prod h and D = B_{N-1} / h0^{prod e},
+// hvzk/PoSBasicTW.java:1013-1014): binary extended Euclid on the host, ~1 ms, instead of a
+// 3072-step Fermat ladder on one warp (~20 ms).
+int vmx_elem_inv(vmx_ctx* c, const uint8_t* in_be, uint8_t* out_be) {
+  VMX_ENTER(c);
+  if (!in_be || !out_be) return VMX_EARG;
+  const int N = c->nl;
+  std::vector<uint32_t> a(N), r(N);
+  if (!be_to_limbs(in_be, c->eb, a.data(), N) || limbs_cmp(a.data(), c->P.n, N) >= 0) {
+    set_error("element out of range");
+    return VMX_EFORMAT;
+  }
+  if (!limbs_inv_mod(r.data(), a.data(), c->P.n, N)) { set_error("element not invertible"); return VMX_EFORMAT; }
+  std::memset(out_be, 0, c->eb);
+  for (size_t b = 0; b < (size_t)4 * N && b < c->eb; b++) out_be[c->eb - 1 - b] = (uint8_t)(r[b / 4] >> (8 * (b % 4)));
+  return VMX_OK;
 }
 
 int vmx_fixed_precompute(vmx_ctx* c, const uint8_t* base_be, size_t n_hint) {
