@@ -137,6 +137,20 @@ int vmx_equals(const vmx_garr* a, const vmx_garr* b, int* equal);
 /* PGroupElementArray.get(i) (hvzk/PoSBasicTW.java:562,1014). */
 int vmx_get(const vmx_garr* a, size_t i, uint8_t* out_be);
 
+/* ---------------------------------------------------------------- exchange between GPUs
+ * The N ciphertexts are sharded over the GPUs of one box in contiguous index ranges; a
+ * permutation (mixnet/ShufflerElGamalSession.java:278, hvzk/PoSBasicTW.java:451,553) moves elements
+ * between shards.  pack_rows writes the selected elements element-major (count rows of
+ * vmx_ctx_row_bytes bytes, internal representation: Montgomery form for group arrays) into a
+ * caller-provided DEVICE buffer that NCCL all-to-all moves over NVLink; unpack_rows builds a fresh
+ * array of n elements from such rows (dst_idx must be a permutation of 0..n-1; NULL = identity).
+ * idx / dst_idx are HOST lists.  Work is queued on the ctx stream (vmx_ctx_stream). */
+size_t vmx_ctx_row_bytes(const vmx_ctx* ctx);
+int vmx_garr_pack_rows(const vmx_garr* a, const uint32_t* idx, size_t count, void* rows_dev);
+int vmx_garr_unpack_rows(vmx_ctx* ctx, size_t n, const void* rows_dev, const uint32_t* dst_idx, size_t count, vmx_garr** out);
+int vmx_rarr_pack_rows(const vmx_rarr* a, const uint32_t* idx, size_t count, void* rows_dev);
+int vmx_rarr_unpack_rows(vmx_ctx* ctx, size_t n, const void* rows_dev, const uint32_t* dst_idx, size_t count, vmx_rarr** out);
+
 /* ---------------------------------------------------------------- ring arrays (Z_q) */
 /* PRing/PField.toElementArray(size, ByteTreeReader) (hvzk/PoSBasicTW.java:977,980): each
  * element must satisfy 0 <= x < q, else VMX_EFORMAT. */

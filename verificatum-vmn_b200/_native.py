@@ -55,6 +55,11 @@ SIGNATURES = {
     "vmx_elem_exp": (C.c_int, [_P, _U8, _U8, _P]),
     "vmx_elem_inv": (C.c_int, [_P, _U8, _P]),
     "vmx_fixed_precompute": (C.c_int, [_P, _U8, _SZ]),
+    "vmx_ctx_row_bytes": (_SZ, [_P]),
+    "vmx_garr_pack_rows": (C.c_int, [_P, _P, _SZ, _P]),
+    "vmx_garr_unpack_rows": (C.c_int, [_P, _SZ, _P, _P, _SZ, _PP]),
+    "vmx_rarr_pack_rows": (C.c_int, [_P, _P, _SZ, _P]),
+    "vmx_rarr_unpack_rows": (C.c_int, [_P, _SZ, _P, _P, _SZ, _PP]),
     "vmx_exp_var": (C.c_int, [_P, _P, _PP]),
     "vmx_exp_scalar": (C.c_int, [_P, _U8, _PP]),
     "vmx_expprod": (C.c_int, [_PP, _SZ, _P, _P]),

@@ -161,6 +161,10 @@ class PField(PRing):
         self.order = group.q
         self.byte_len = group.ring_bytes
 
+    def _rarr(self, h, size: Optional[int] = None) -> "PRingElementArray":
+        """Wrap a fresh engine handle (overridden by the sharded field of parallel.py)."""
+        return PRingElementArray(self, h)
+
     # -- elements
     def getZERO(self) -> "PFieldElement":
         return PFieldElement(self, 0)
@@ -196,7 +200,7 @@ class PField(PRing):
             nat.check(nat.load().vmx_rarr_prg_raw_sha256(self.group.ctx, randomSource.seed, len(randomSource.seed),
                                                          off, size, width, bits, C.byref(h)))
             _advance_prg(randomSource, off + size * width)
-            return PRingElementArray(self, h)
+            return self._rarr(h, size)
         raw = np.frombuffer(randomSource.getBytes(size * width), dtype=np.uint8)
         return self._from_raw(size, raw, width, bits)
 
@@ -204,7 +208,7 @@ class PField(PRing):
         lib = nat.load()
         h = C.c_void_p()
         nat.check(lib.vmx_rarr_from_raw(self.group.ctx, size, _ptr(raw), width, bits, C.byref(h)))
-        return PRingElementArray(self, h)
+        return self._rarr(h, size)
 
     def toElementArray(self, *args) -> "PRingElementArray":
         """(size, ByteTreeReader) | (LargeIntegerArray) | (size, element) | (list of elements)."""
@@ -216,7 +220,7 @@ class PField(PRing):
             m = np.frombuffer(b"".join(_be(v, self.byte_len) for v in vals), dtype=np.uint8)
             h = C.c_void_p()
             nat.check(lib.vmx_rarr_from_bytes(self.group.ctx, len(vals), _ptr(m), C.byref(h)))
-            return PRingElementArray(self, h)
+            return self._rarr(h, len(vals))
         size, src = args
         h = C.c_void_p()
         if isinstance(src, ByteTreeReader):
@@ -227,7 +231,7 @@ class PField(PRing):
             nat.check(lib.vmx_rarr_from_bytes(self.group.ctx, size, _ptr(m), C.byref(h)))
         else:
             nat.check(lib.vmx_rarr_fill(self.group.ctx, size, _be(src.value, self.byte_len), C.byref(h)))
-        return PRingElementArray(self, h)
+        return self._rarr(h, size)
 
     unsafeToElementArray = toElementArray
 
@@ -411,9 +415,10 @@ class PRingElementArray:
 class LargeIntegerArray:
     """Non-negative integers of bounded bit length, device-resident (already < q here)."""
 
-    def __init__(self, field: PField, handle):
+    def __init__(self, field: PField, handle, size: Optional[int] = None):
         self.field = field
         self.h = handle
+        self.gsize = size
 
     @staticmethod
     def random(size: int, bitLength: int, randomSource, field: PField) -> "LargeIntegerArray":
@@ -421,6 +426,8 @@ class LargeIntegerArray:
 
         With a PRGHeuristic(SHA-256) source the expansion runs on the device (counter mode);
         any other source hands its bytes over."""
+        if hasattr(field, "_lia_random"):  # sharded field (parallel.py): every rank draws its own slice
+            return field._lia_random(size, bitLength, randomSource)
         lib = nat.load()
         h = C.c_void_p()
         width = (bitLength + 7) // 8
@@ -436,7 +443,7 @@ class LargeIntegerArray:
 
     def _to_ring(self, field: PField) -> PRingElementArray:
         h, self.h = self.h, None
-        return PRingElementArray(field, h)
+        return field._rarr(h, self.gsize)
 
     def free(self) -> None:
         if self.h is not None and self.h.value:
@@ -476,6 +483,15 @@ class ModPGroup(PGroup):
                 self.ctx = None
         except Exception:
             pass
+
+    def _garr(self, h, size: Optional[int] = None) -> "PGroupElementArray":
+        """Wrap a fresh engine handle (overridden by the sharded group of parallel.py)."""
+        return PGroupElementArray(self, h)
+
+    def _combine_partials(self, parts: List["PGroupElement"]) -> List["PGroupElement"]:
+        """expProd / prod results of this process; the sharded group multiplies the ranks' partial
+        products here (parallel.py)."""
+        return parts
 
     # -- structure
     def getPRing(self) -> PField:
@@ -542,7 +558,7 @@ class ModPGroup(PGroup):
             vals = [e.value for e in args[0]]
             m = np.frombuffer(b"".join(_be(v, self.elem_bytes) for v in vals), dtype=np.uint8)
             nat.check(lib.vmx_garr_from_bytes(self.ctx, len(vals), _ptr(m), 0, C.byref(h)))
-            return PGroupElementArray(self, h)
+            return self._garr(h, len(vals))
         size, src = args
         if isinstance(src, ByteTreeReader):
             try:
@@ -554,7 +570,7 @@ class ModPGroup(PGroup):
             nat.check(lib.vmx_garr_from_bytes(self.ctx, size, _ptr(src), 1 if check_membership else 0, C.byref(h)))
         else:
             nat.check(lib.vmx_garr_fill(self.ctx, size, _be(src.value, self.elem_bytes), C.byref(h)))
-        return PGroupElementArray(self, h)
+        return self._garr(h, size)
 
     def unsafeToElementArray(self, *args) -> "PGroupElementArray":
         return self.toElementArray(*args, check_membership=False)
@@ -571,10 +587,10 @@ class ModPGroup(PGroup):
             nat.check(self._lib.vmx_garr_prg_sha256(self.ctx, randomSource.seed, len(randomSource.seed), off, size,
                                                     width, bits, C.byref(h)))
             _advance_prg(randomSource, off + size * width)
-            return PGroupElementArray(self, h)
+            return self._garr(h, size)
         raw = np.frombuffer(randomSource.getBytes(size * width), dtype=np.uint8)
         nat.check(self._lib.vmx_garr_from_raw(self.ctx, size, _ptr(raw), width, bits, C.byref(h)))
-        return PGroupElementArray(self, h)
+        return self._garr(h, size)
 
     def expProd(self, bases: Sequence["PGroupElementArray"], integers: Sequence[int], bitLength: int):
         """Element-wise prod_j bases[j][i]^integers[j] (elgamal/DistrElGamalSessionBasic.java:502)."""
@@ -583,7 +599,7 @@ class ModPGroup(PGroup):
         ints = (C.c_int64 * t)(*[int(x) for x in integers])
         h = C.c_void_p()
         nat.check(self._lib.vmx_expprod_cols(arr, t, ints, C.byref(h)))
-        return PGroupElementArray(self, h)
+        return self._garr(h, bases[0].size())
 
     def __eq__(self, o):
         return isinstance(o, ModPGroup) and (o.p, o.q, o.g) == (self.p, self.q, self.g)
@@ -626,7 +642,7 @@ class PGroupElement:
         if isinstance(e, PRingElementArray):
             h = C.c_void_p()
             nat.check(lib.vmx_exp_fixed(self.group.ctx, self._be(), e.h, C.byref(h)))
-            return PGroupElementArray(self.group, h)
+            return self.group._garr(h, e.size())
         if isinstance(e, int):
             e = self.group.pRing.toElement(e)
         buf = np.empty(self.group.elem_bytes, dtype=np.uint8)
@@ -727,7 +743,7 @@ class PGroupElementArray:
     def prod(self) -> PGroupElement:
         buf = np.empty(self.group.elem_bytes, dtype=np.uint8)
         nat.check(self._lib.vmx_prod(self.h, _ptr(buf)))
-        return PGroupElement(self.group, int.from_bytes(buf.tobytes(), "big"))
+        return self.group._combine_partials([PGroupElement(self.group, int.from_bytes(buf.tobytes(), "big"))])[0]
 
     # -- data movement
     def permute(self, pi: Permutation):
@@ -788,7 +804,7 @@ def expProdMany(arrays: Sequence[PGroupElementArray], e: PRingElementArray) -> L
     arr = (C.c_void_p * k)(*[a.h for a in arrays])
     buf = np.empty((k, group.elem_bytes), dtype=np.uint8)
     nat.check(group._lib.vmx_expprod(arr, k, e.h, _ptr(buf)))
-    return [PGroupElement(group, int.from_bytes(buf[i].tobytes(), "big")) for i in range(k)]
+    return group._combine_partials([PGroupElement(group, int.from_bytes(buf[i].tobytes(), "big")) for i in range(k)])
 
 
 # ====================================================================== product groups / rings

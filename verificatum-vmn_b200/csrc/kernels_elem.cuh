@@ -302,6 +302,25 @@ __global__ void k_gather(const uint4* __restrict__ in, size_t icap, uint4* __res
   out[g * ocap + d] = in[g * icap + s];
 }
 
+// Element-major packing for the exchange between GPUs (permute across shards): row r of `rows` holds the
+// `planes` uint4 groups of element idx[r] (idx == null: element r) back to back.  Writes are
+// coalesced (consecutive threads -> consecutive 16-byte groups of one row); reads are 16-byte
+// gathers.  k_unpack_rows is the inverse scatter into a limb-major array.
+__global__ void k_pack_rows(const uint4* __restrict__ in, size_t icap, const uint32_t* __restrict__ idx, size_t count,
+                            int planes, uint4* __restrict__ rows) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * (size_t)planes) return;
+  const size_t r = t / planes, g = t % planes;
+  rows[t] = in[g * icap + (idx ? idx[r] : r)];
+}
+__global__ void k_unpack_rows(const uint4* __restrict__ rows, const uint32_t* __restrict__ idx, size_t count, int planes,
+                              uint4* __restrict__ out, size_t ocap) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * (size_t)planes) return;
+  const size_t r = t / planes, g = t % planes;
+  out[g * ocap + (idx ? idx[r] : r)] = rows[t];
+}
+
 // *diff |= any word differs
 __global__ void k_equal(const uint4* __restrict__ a, size_t acap, const uint4* __restrict__ b, size_t bcap, size_t n,
                         int planes, int* __restrict__ diff) {

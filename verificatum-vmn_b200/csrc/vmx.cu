@@ -1238,6 +1238,45 @@ static int upload_u32(vmx_ctx* c, const uint32_t* h, size_t n, DevBuf& buf) {
   return VMX_OK;
 }
 
+// rows_dev[r] = element idx[r] (count rows of nl words, element-major); idx is a HOST list or null
+static int pack_rows(vmx_ctx* c, const uint32_t* d, size_t cap, size_t n, const uint32_t* idx, size_t count,
+                     void* rows_dev) {
+  if (!count) return VMX_OK;
+  if (!rows_dev) return VMX_EARG;
+  DevBuf di;
+  if (idx) {
+    for (size_t r = 0; r < count; r++) if (idx[r] >= n) { set_error("row index out of range"); return VMX_EARG; }
+    VMX_TRY(upload_u32(c, idx, count, di));
+  } else if (count > n) { set_error("more rows than elements"); return VMX_ESIZE; }
+  const int planes = c->nl / 4;
+  VMX_LAUNCH(c, k_pack_rows, nblocks(count * planes, 256), 256, 0, reinterpret_cast<const uint4*>(d), cap,
+             idx ? di.as<uint32_t>() : (const uint32_t*)nullptr, count, planes, reinterpret_cast<uint4*>(rows_dev));
+  VMX_CHECK_LAUNCH();
+  return VMX_OK;
+}
+// element dst_idx[r] of a fresh array of n elements = row r; the rows must cover every element once
+static int unpack_rows(vmx_ctx* c, uint32_t* d, size_t cap, size_t n, const void* rows_dev, const uint32_t* dst_idx,
+                       size_t count) {
+  if (count != n) { set_error("unpack_rows: %zu rows for %zu elements", count, n); return VMX_ESIZE; }
+  if (!count) return VMX_OK;
+  if (!rows_dev) return VMX_EARG;
+  DevBuf di;
+  if (dst_idx) {
+    std::vector<uint8_t> seen(n, 0);
+    for (size_t r = 0; r < count; r++) {
+      if (dst_idx[r] >= n || seen[dst_idx[r]]) { set_error("unpack_rows: destination list is not a permutation"); return VMX_EARG; }
+      seen[dst_idx[r]] = 1;
+    }
+    VMX_TRY(upload_u32(c, dst_idx, count, di));
+  }
+  const int planes = c->nl / 4;
+  VMX_LAUNCH(c, k_unpack_rows, nblocks(count * planes, 256), 256, 0, reinterpret_cast<const uint4*>(rows_dev),
+             dst_idx ? di.as<uint32_t>() : (const uint32_t*)nullptr, count, planes, reinterpret_cast<uint4*>(d), cap);
+  VMX_CHECK_LAUNCH();
+  return VMX_OK;
+}
+
+
 int vmx_permute(const vmx_garr* a, const uint32_t* perm, vmx_garr** out) {
   if (!out) return VMX_EARG;
   *out = nullptr;
@@ -1251,6 +1290,41 @@ int vmx_permute(const vmx_garr* a, const uint32_t* perm, vmx_garr** out) {
   VMX_TRY(new_garr(c, a->n, &r));
   const int s = gather(c, a->d, a->cap, r->d, r->cap, a->n, nullptr, p.as<uint32_t>(), 0, 0);
   if (s != VMX_OK) { vmx_garr_free(r); return s; }
+  *out = r;
+  return VMX_OK;
+}
+
+// ---- exchange between the GPUs of one box
+size_t vmx_ctx_row_bytes(const vmx_ctx* c) { return c ? (size_t)c->nl * 4 : 0; }
+int vmx_garr_pack_rows(const vmx_garr* a, const uint32_t* idx, size_t count, void* rows_dev) {
+  if (!a) return VMX_EARG;
+  VMX_ENTER(a->ctx);
+  return pack_rows(a->ctx, a->d, a->cap, a->n, idx, count, rows_dev);
+}
+int vmx_rarr_pack_rows(const vmx_rarr* a, const uint32_t* idx, size_t count, void* rows_dev) {
+  if (!a) return VMX_EARG;
+  VMX_ENTER(a->ctx);
+  return pack_rows(a->ctx, a->d, a->cap, a->n, idx, count, rows_dev);
+}
+int vmx_garr_unpack_rows(vmx_ctx* c, size_t n, const void* rows_dev, const uint32_t* dst_idx, size_t count, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  VMX_ENTER(c);
+  vmx_garr* r = nullptr;
+  VMX_TRY(new_garr(c, n, &r));
+  const int s = unpack_rows(c, r->d, r->cap, n, rows_dev, dst_idx, count);
+  if (s != VMX_OK) { vmx_garr_free(r); return s; }
+  *out = r;
+  return VMX_OK;
+}
+int vmx_rarr_unpack_rows(vmx_ctx* c, size_t n, const void* rows_dev, const uint32_t* dst_idx, size_t count, vmx_rarr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  VMX_ENTER(c);
+  vmx_rarr* r = nullptr;
+  VMX_TRY(new_rarr(c, n, &r));
+  const int s = unpack_rows(c, r->d, r->cap, n, rows_dev, dst_idx, count);
+  if (s != VMX_OK) { vmx_rarr_free(r); return s; }
   *out = r;
   return VMX_OK;
 }
