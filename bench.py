@@ -333,6 +333,17 @@ def main():
             d2h = len(proof.output) + len(proof.permutationCommitment) + len(proof.commitment) + len(proof.reply)
 
         step_e2e(0)
+        if args.phases and rank == 0 and world == 1:  # where does the host time go?  (untimed extra step)
+            import cProfile
+            import pstats
+            import io
+            pr = cProfile.Profile()
+            pr.enable()
+            step_e2e(99)
+            pr.disable()
+            buf = io.StringIO()
+            pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(18)
+            sys.stderr.write(buf.getvalue())
         barrier()
         t0 = time.time()
         k = max(1, min(args.steps, 2))

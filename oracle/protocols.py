@@ -660,3 +660,120 @@ class DistrElGamalSessionBasic:
         ok1 = pow(pow(combinedy, -1, p), pfev, p) * self.combinedyp % p == pow(self.g, self.combinedk_x, p)
         ok2 = ar.g_mul(G, ar.g_exp(G, self.combinedB, pfev), self.combinedBp) == ar.g_exp(G, self.A, self.combinedk_x)
         return ok1 and ok2
+
+
+# ---------------------------------------------------------------- pre-computation and committed shuffle
+def perm_shrink(table, size: int):
+    """Permutation.shrink ([VCR-mem]; used at mixnet/PermutationCommitment.java:426): restriction to the
+    first `size` inputs with images renumbered in increasing order."""
+    img = list(table[:size])
+    rank = {v: i for i, v in enumerate(sorted(img))}
+    return [rank[v] for v in img]
+
+
+def posc_prove(G, params: Params, g, h, u, r, pi, rs):
+    """hvzk/PoSCTW.java:73-128."""
+    prefix = params.prefix()
+    P = PoSCBasicTW(G, params.vbitlenro, params.ebitlenro, params.rbitlen, params.prghash, rs)
+    P.set_instance(g, h, u, r, pi)
+    seed = challenge(params.rohash, prefix, bt.node(ar.elem_tree(G, g), ar.array_tree(G, h), ar.array_tree(G, u)),
+                     8 * PRGHeuristic(params.prghash).min_no_seed_bytes())
+    commitment = P.commit(seed)
+    cb = challenge(params.rohash, prefix, bt.node(bt.leaf(seed), commitment), params.vbitlenro)
+    reply = P.reply(int.from_bytes(cb, "big"))
+    return commitment.to_bytes(), reply.to_bytes()
+
+
+def posc_verify(G, params: Params, g, h, u, commitment: bytes, reply: bytes) -> bool:
+    """hvzk/PoSCTW.java:137-210; mixnet/MixNetElGamalVerifyFiatShamirSession.java:652-705."""
+    prefix = params.prefix()
+    V = PoSCBasicTW(G, params.vbitlenro, params.ebitlenro, params.rbitlen, params.prghash, None)
+    V.set_instance(g, h, u)
+    seed = challenge(params.rohash, prefix, bt.node(ar.elem_tree(G, g), ar.array_tree(G, h), ar.array_tree(G, u)),
+                     8 * PRGHeuristic(params.prghash).min_no_seed_bytes())
+    V.set_batch_vector(seed)
+    try:
+        ctree = V.set_commitment(bt.from_bytes(commitment))
+    except bt.EIOError:
+        ctree = V.set_commitment(bt.leaf(b""))
+    cb = challenge(params.rohash, prefix, bt.node(bt.leaf(seed), ctree), params.vbitlenro)
+    V.set_challenge(int.from_bytes(cb, "big"))
+    try:
+        return V.verify(bt.from_bytes(reply))
+    except bt.EIOError:
+        return False
+
+
+def _ccpos_seed(G, params, g, h, u, pkey, w, wp):
+    return challenge(params.rohash, params.prefix(),
+                     bt.node(ar.elem_tree(G, g), ar.array_tree(G, h), ar.array_tree(G, u), ar.elem_tree(G, pkey),
+                             ar.array_tree(G, w), ar.array_tree(G, wp)),
+                     8 * PRGHeuristic(params.prghash).min_no_seed_bytes())
+
+
+def ccpos_prove(G, params: Params, g, h, u, pkey, w, wp, r, pi, s, rs):
+    """hvzk/CCPoSW.java:75-150."""
+    P = CCPoSBasicW(G, params.vbitlenro, params.ebitlenro, params.rbitlen, params.prghash)
+    P.set_instance(g, h, u, pkey, w, wp, r, pi, s)
+    seed = _ccpos_seed(G, params, g, h, u, pkey, w, wp)
+    commitment = P.commit(seed, rs)
+    cb = challenge(params.rohash, params.prefix(), bt.node(bt.leaf(seed), commitment), params.vbitlenro)
+    reply = P.reply(int.from_bytes(cb, "big"))
+    return commitment.to_bytes(), reply.to_bytes()
+
+
+def ccpos_verify(G, params: Params, g, h, u, pkey, w, wp, commitment: bytes, reply: bytes) -> bool:
+    """hvzk/CCPoSW.java:160-260 with raisedu == null; mixnet/MixNetElGamalVerifyFiatShamirSession.java:757-841."""
+    V = CCPoSBasicW(G, params.vbitlenro, params.ebitlenro, params.rbitlen, params.prghash)
+    V.set_instance(g, h, u, pkey, w, wp)
+    seed = _ccpos_seed(G, params, g, h, u, pkey, w, wp)
+    V.set_batch_vector(seed)
+    V.compute_AB()
+    try:
+        ctree = V.set_commitment(bt.from_bytes(commitment))
+    except bt.EIOError:
+        ctree = V.set_commitment(bt.leaf(b""))
+    cb = challenge(params.rohash, params.prefix(), bt.node(bt.leaf(seed), ctree), params.vbitlenro)
+    V.set_challenge(int.from_bytes(cb, "big"))
+    try:
+        return V.verify(bt.from_bytes(reply))
+    except bt.EIOError:
+        return False
+
+
+def precomp(G, params: Params, pkey, h, rs):
+    """mixnet/PermutationCommitment.java:148-219 + :251-292 and mixnet/ShufflerElGamalSession.java:647-658:
+    commit to a permutation of maxciph = len(h) generators, prove it, pre-compute re-encryption factors."""
+    n = len(h)
+    exponents = ar.ring_random_array(G, n, rs, params.rbitlen)
+    idc = ar.g_mul(G, h, ar.g_exp(G, G.g, exponents))
+    pi = ar.permutation_random(n, rs, params.rbitlen)
+    u = ar.permute(idc, pi)
+    posc_c, posc_r = posc_prove(G, params, G.g, h, u, exponents, pi, rs)
+    s = ar.ring_random_array(G, n, rs, params.rbitlen)
+    factors = ar.g_exp(G, pkey, s)
+    state = {"exponents": exponents, "pi": pi, "u": u, "s": s, "factors": factors, "h": list(h)}
+    return state, (ar.array_tree(G, u).to_bytes(), posc_c, posc_r)
+
+
+def shrink(G, state: dict, n: int) -> bytes:
+    """mixnet/PermutationCommitment.java:390-471 (l == j) + mixnet/ShufflerElGamalSession.java:673-760."""
+    size = len(state["u"])
+    keep = [False] * size
+    for i in range(n):
+        keep[state["pi"][i]] = True
+    state["exponents"] = state["exponents"][:n]
+    state["pi"] = perm_shrink(state["pi"], n)
+    state["u"] = [x for x, k in zip(state["u"], keep) if k]
+    state["h"] = state["h"][:n]
+    state["s"] = state["s"][:n]
+    state["factors"] = ar.gmap(lambda col: col[:n], state["factors"])
+    return bt.bool_array_leaf(keep).to_bytes()
+
+
+def committed_shuffle(G, params: Params, pkey, state: dict, w, rs):
+    """mixnet/ShufflerElGamalSession.java:771-822."""
+    wp = ar.permute(ar.g_mul(G, w, state["factors"]), ar.perm_inv(state["pi"]))
+    c, r = ccpos_prove(G, params, G.g, state["h"], state["u"], pkey, w, wp, state["exponents"], state["pi"],
+                       state["s"], rs)
+    return wp, {"output": ar.array_tree(G, wp).to_bytes(), "commitment": c, "reply": r}

@@ -100,6 +100,24 @@ def edge_cases(vmx, bits):
         assert False
     except A.ArithmFormatException:
         pass
+    # membership on import = Legendre symbol (binary Jacobi kernel) for safe primes: arrays of residues
+    # pass, one non-residue anywhere rejects, element by element against Euler's criterion
+    import random as _r
+    rq = _r.Random(1000 + bits)
+    cand = [rq.randrange(1, p) for _ in range(40)] + [1, p - 1, 2, 3, 4, p - 2, (p - 1) // 2, (p + 1) // 2]
+    qr = [v for v in cand if pow(v, q, p) == 1]
+    nqr = [v for v in cand if pow(v, q, p) != 1]
+    assert qr and nqr
+    as_m = lambda vs: np.frombuffer(b"".join(v.to_bytes(G.elem_bytes, "big") for v in vs), dtype=np.uint8)
+    ok_arr = G.toElementArray(len(qr), as_m(qr), check_membership=True)
+    assert [e.value for e in ok_arr.elements()] == qr
+    for v in nqr:
+        for pos in (0, len(qr) // 2, len(qr)):
+            try:
+                G.toElementArray(len(qr) + 1, as_m(qr[:pos] + [v] + qr[pos:]), check_membership=True)
+                assert False, "non-residue accepted"
+            except A.ArithmFormatException:
+                pass
     # single-element inversion (host binary Euclid in the engine) against Python, incl. 1 and p-1
     import random
     rnd = random.Random(bits)
@@ -415,3 +433,63 @@ def decryption_parity(vmx, bits, n, k=3, threshold=2):
     E1.k_x[k] = E1.k_x[k].add(R.getONE())
     O1.k_x[k] = (O1.k_x[k] + 1) % q
     assert E1.verify(k, v) is False and O1.verify(k, v) is False
+
+
+def committed_shuffle_parity(vmx, bits, maxciph, n):
+    """Pre-computation with maxciph generators (permutation commitment + PoSC), shrink to n actual
+    ciphertexts (keep list, Permutation.shrink, extract), commitment-consistent shuffle (CCPoS):
+    the engine's and the oracle's published bytes are identical and each verifies the other's."""
+    mix = importlib.import_module("verificatum-vmn_b200.mixnet")
+    oc = OracleCase(bits, n, "committed")
+    ec = EngineCase(vmx, bits, n, "committed")
+    OG = oc.G
+    oh = opr.independent_generators(OG, "sha256", oc.params.prefix(), "generators", maxciph, oc.params.rbitlen)
+    ostate, opub = opr.precomp(OG, oc.params, oc.pk, oh, SeededRandomSource(seed("committed/prover")))
+    okeep = opr.shrink(OG, ostate, n)
+    owp, oproof = opr.committed_shuffle(OG, oc.params, oc.pk, ostate, oc.w, SeededRandomSource(seed("committed/prove2")))
+    # engine prover
+    prover = ec.session("committed/prover")
+    cs = mix.CommittedShuffler(prover, 1, maxciph)
+    assert col_values(cs.generators) == oh
+    pub = cs.precomp()
+    assert pub == opub
+    keep = cs.shrink(n)
+    assert keep == okeep
+    assert list(cs.permutationCommitment.permutation.table) == ostate["pi"]
+    assert col_values(cs.permutationCommitment.commitment) == ostate["u"]
+    prover.randomSource.setSeed(seed("committed/prove2"))
+    proof, out = cs.shuffle(ec.w, keep_output=True)
+    assert col_values(out) == owp
+    assert dataclasses.asdict(proof) == oproof
+    # engine verifier: PoSC on the full commitment, shrink with the published keep list, CCPoS
+    verifier = ec.session(None)
+    gens = verifier.deriveGenerators(maxciph)
+    pcv = mix.PermutationCommitment(verifier, gens)
+    assert pcv.verify(*opub) is True
+    assert pcv.shrink(n, okeep) == okeep
+    sgens = gens.copyOfRange(0, n)
+    ok, out2 = mix.verifyCommittedShuffle(verifier, 1, sgens, pcv.commitment, ec.w, proof)
+    assert ok is True and col_values(out2) == owp
+    # oracle verifier on the engine's bytes
+    ou = oar.parse_array(OG, obt.from_bytes(pub[0]), maxciph)
+    assert opr.posc_verify(OG, oc.params, OG.g, oh, ou, pub[1], pub[2]) is True
+    assert opr.ccpos_verify(OG, oc.params, OG.g, oh[:n], ostate["u"], oc.pk, oc.w, owp, proof.commitment, proof.reply)
+    # corruption: a flipped bit in the CCPoS reply is rejected by both and the output replaced by the input
+    raw = bytearray(proof.reply)
+    raw[-2] ^= 8
+    okb, outb = mix.verifyCommittedShuffle(verifier, 1, sgens, pcv.commitment, ec.w,
+                                           dataclasses.replace(proof, reply=bytes(raw)))
+    assert okb is False and col_values(outb) == oc.w
+    assert opr.ccpos_verify(OG, oc.params, OG.g, oh[:n], ostate["u"], oc.pk, oc.w, owp, proof.commitment, bytes(raw)) is False
+    # a corrupted PoSC reply makes the commitment trivial (the generators)
+    rawp = bytearray(pub[2])
+    rawp[7] ^= 1
+    pcb = mix.PermutationCommitment(verifier, gens)
+    assert pcb.verify(pub[0], pub[1], bytes(rawp)) is False and col_values(pcb.commitment) == oh
+    assert opr.posc_verify(OG, oc.params, OG.g, oh, ou, pub[1], bytes(rawp)) is False
+    # a keep list with the wrong number of entries is replaced by the trivial one
+    bad_keep = bytearray(okeep)
+    bad_keep[-1] ^= 1
+    pcc = mix.PermutationCommitment(verifier, gens)
+    pcc.verify(*opub)
+    assert pcc.shrink(n, bytes(bad_keep)) == vmx.eio.booleanArrayToByteTree([i < n for i in range(maxciph)]).to_bytes()

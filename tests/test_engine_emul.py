@@ -51,3 +51,8 @@ def test_ccpos_parity(engine_emul, n):
 @pytest.mark.parametrize("n,k,t", [(1, 1, 1), (17, 3, 2), (9, 5, 3)])
 def test_decryption_parity(engine_emul, n, k, t):
     pb.decryption_parity(engine_emul, 512, n, k, t)
+
+
+@pytest.mark.parametrize("maxciph,n", [(12, 12), (15, 7), (9, 1)])
+def test_committed_shuffle_parity(engine_emul, maxciph, n):
+    pb.committed_shuffle_parity(engine_emul, 512, maxciph, n)

@@ -53,6 +53,12 @@ def test_decryption_parity(engine_cuda, bits, n, k, t):
     pb.decryption_parity(engine_cuda, bits, n, k, t)
 
 
+@pytest.mark.parametrize("bits,maxciph,n", [(512, 150, 100), (3072, 15, 10)])
+def test_committed_shuffle_parity(engine_cuda, bits, maxciph, n):
+    """precomp(15) + committedShuffle of 10 is the reference's mixnet/DemoShufflerElGamal.java:163-265 scale."""
+    pb.committed_shuffle_parity(engine_cuda, bits, maxciph, n)
+
+
 @pytest.mark.parametrize("bits", [512, 2048, 3072])
 def test_cooperative_multiplier_matches_thread_per_element(engine_cuda, bits):
     vmx = engine_cuda

@@ -119,6 +119,20 @@ class Permutation:
         inv[self.table] = np.arange(self.table.shape[0], dtype=np.uint32)
         return Permutation(inv)
 
+    def shrink(self, size: int) -> "Permutation":
+        """Permutation.shrink (mixnet/PermutationCommitment.java:426): the restriction to the first
+        `size` inputs, images renumbered 0..size-1 in increasing order ([VCR-mem]; it is the
+        permutation under which commitment.extract(keepList) commits, keepList[map(i)] = true)."""
+        img = self.table[:size].astype(np.int64)
+        order = np.argsort(img, kind="stable")
+        t = np.empty(size, dtype=np.uint32)
+        t[order] = np.arange(size, dtype=np.uint32)
+        return Permutation(t)
+
+    def toByteTree(self) -> ByteTreeBasic:
+        """One 4-byte leaf per entry ([VCR-mem]; only written to the prover's private state files)."""
+        return ByteTreeContainer(*[ByteTreeLeaf(int(v).to_bytes(4, "big")) for v in self.table])
+
     def free(self) -> None:
         pass
 

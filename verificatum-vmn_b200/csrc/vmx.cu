@@ -758,6 +758,13 @@ int vmx_ctx_create_modp(const uint8_t* p_be, const uint8_t* q_be, const uint8_t*
   c->Q.n0inv = neg_inv32(c->Q.n[0]);
   c->eb = (size_t)pbits / 8 + 1;
   c->rb = (size_t)c->Q.bits / 8 + 1;
+  {  // safe prime?  p == 2q + 1
+    uint32_t t2[kMaxLimbs];
+    uint32_t carry = 0;
+    for (int j = 0; j < kMaxLimbs; j++) { const uint32_t v = c->Q.n[j]; t2[j] = (v << 1) | carry; carry = v >> 31; }
+    t2[0] |= 1u;
+    c->safe_prime = !carry && limbs_cmp(t2, c->P.n, kMaxLimbs) == 0;
+  }
   c->pm2.assign(c->P.n, c->P.n + c->nl);
   { uint32_t two[kMaxLimbs] = {2}; limbs_sub(c->pm2.data(), two, c->nl); }
   VMX_CU(cudaSetDevice(device));
@@ -1138,6 +1145,17 @@ static int exp_scalar_limbs(vmx_ctx* c, const vmx_garr* a, const uint32_t* x, vm
 // Euler criterion x^q == 1 for every element (exact; a Jacobi-symbol kernel is the planned
 // replacement).
 static int garr_check_members(vmx_ctx* c, const vmx_garr* a, int* ok) {
+  if (c->safe_prime) {  // quadratic residues: Legendre symbol by the binary Jacobi algorithm
+    *ok = 1;
+    if (!a->n) return VMX_OK;
+    VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_jacobi<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, a->n, c->d_flag,
+                                   c->P.params<N>()));
+    VMX_CHECK_LAUNCH();
+    VMX_TRY(read_flags(c, 1));
+    *ok = c->h_flag[0] == 0;
+    return VMX_OK;
+  }
   vmx_garr* t = nullptr;
   VMX_TRY(exp_scalar_limbs(c, a, c->Q.n, &t));
   std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(t, vmx_garr_free);

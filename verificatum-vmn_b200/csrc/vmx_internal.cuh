@@ -12,6 +12,7 @@
 #include "../../include/vmx.h"
 #include "cuda_compat.cuh"
 #include "kernels_elem.cuh"
+#include "kernels_member.cuh"
 #include "kernels_mexp.cuh"
 #include "kernels_prg.cuh"
 #include "kernels_ring.cuh"
@@ -77,6 +78,7 @@ struct vmx_ctx {
   int* h_flag = nullptr;                          // pinned scratch: 4 ints
   std::atomic<uint64_t> launches{0}, modmuls{0};
   int sm_count = 148;
+  bool safe_prime = false;  // p = 2q + 1: membership = Legendre symbol (k_jacobi)
 };
 
 struct vmx_garr {

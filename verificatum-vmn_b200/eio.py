@@ -114,6 +114,11 @@ def int_to_bytes(x: int, length: Optional[int] = None) -> bytes:
     return x.to_bytes(length, "big", signed=True)
 
 
+def booleanArrayToByteTree(flags) -> ByteTreeLeaf:
+    """ByteTree.booleanArrayToByteTree: one byte per flag (KeepList%02d.bt, CorrectIndices.bt)."""
+    return ByteTreeLeaf(bytes(1 if f else 0 for f in flags))
+
+
 def int32_leaf(x: int) -> ByteTreeLeaf:
     return ByteTreeLeaf(struct.pack(">i", x))
 
@@ -175,6 +180,16 @@ class ByteTreeReader:
                     if (m[:, :5] == hdr).all():
                         return end
         return self.end()
+
+    def readBooleans(self, size: int) -> np.ndarray:
+        """ByteTreeReader.readBooleans (mixnet/PermutationCommitment.java:437,
+        mixnet/MixNetElGamalVerifyFiatShamirSession.java:721): a leaf of `size` bytes, one per flag."""
+        if not self.isLeaf() or self.getRemaining() != size:
+            raise EIOException("expected a leaf of %d flags" % size)
+        raw = np.frombuffer(self.read(), dtype=np.uint8)
+        if raw.size and raw.max() > 1:
+            raise EIOException("malformed boolean")
+        return raw.astype(bool)
 
     def leaf_matrix(self, size: int, width: int) -> np.ndarray:
         """This node as `size` leaves of exactly `width` bytes -> (size, width) uint8 matrix."""

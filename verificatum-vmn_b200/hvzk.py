@@ -569,3 +569,98 @@ class PoSTW:
         for b in (self.P, self.V):
             if b is not None:
                 b.free()
+
+
+class PoSCTW:
+    """hvzk/PoSCTW.java:51 (Fiat-Shamir wrapper of PoSCBasicTW) with the bulletin board replaced by
+    byte strings: the files PoSCCommitment%02d.bt / PoSCReply%02d.bt of the proof directory (:221-235)."""
+
+    def __init__(self, vbitlen, ebitlen, rbitlen, prg: PRGHeuristic, randomSource, challenger: ChallengerRO):
+        self.vbitlen, self.ebitlen, self.rbitlen = vbitlen, ebitlen, rbitlen
+        self.prg, self.randomSource, self.challenger = prg, randomSource, challenger
+
+    def _seed(self, g, h, u) -> bytes:
+        challengeData = ByteTreeContainer(g.toByteTree(), h.toByteTree(), u.toByteTree())          # :90-92
+        return self.challenger.challenge(challengeData, 8 * self.prg.minNoSeedBytes(), self.rbitlen)
+
+    # -- :73-128
+    def prove(self, g, h, u, r, pi):
+        P = PoSCBasicTW(self.vbitlen, self.ebitlen, self.rbitlen, self.prg, self.randomSource)
+        P.setInstance(g, h, u, r, pi)
+        prgSeed = self._seed(g, h, u)
+        commitment = P.commit(prgSeed)
+        challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitment)
+        challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
+        reply = P.reply(_to_positive(challengeBytes))
+        out = (commitment.to_bytes(), reply.to_bytes())
+        P.free()
+        return out
+
+    # -- :137-210
+    def verify(self, g, h, u, commitment: bytes, reply: bytes) -> bool:
+        V = PoSCBasicTW(self.vbitlen, self.ebitlen, self.rbitlen, self.prg, self.randomSource)
+        V.setInstance(g, h, u)
+        prgSeed = self._seed(g, h, u)
+        V.setBatchVector(prgSeed)
+        try:
+            commitmentTree = V.setCommitment(ByteTreeReader(commitment))
+        except EIOException:
+            commitmentTree = V.setCommitment(ByteTreeReader(ByteTreeContainer().to_bytes()))
+        challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitmentTree)
+        challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
+        V.setChallenge(_to_positive(challengeBytes))
+        try:
+            verdict = V.verify(ByteTreeReader(reply))
+        except EIOException:
+            verdict = False
+        V.free()
+        return verdict
+
+
+class CCPoSW:
+    """hvzk/CCPoSW.java:53 (Fiat-Shamir wrapper of CCPoSBasicW): CCPoSCommitment%02d.bt /
+    CCPoSReply%02d.bt (:274-288).  The verifier side is the plain variant (raisedu == null), which is
+    what the stand-alone verifier runs (mixnet/MixNetElGamalVerifyFiatShamirSession.java:757-841)."""
+
+    def __init__(self, vbitlen, ebitlen, rbitlen, prg: PRGHeuristic, randomSource, challenger: ChallengerRO):
+        self.vbitlen, self.ebitlen, self.rbitlen = vbitlen, ebitlen, rbitlen
+        self.prg, self.randomSource, self.challenger = prg, randomSource, challenger
+
+    def _seed(self, g, h, u, pkey, w, wp) -> bytes:
+        challengeData = ByteTreeContainer(g.toByteTree(), h.toByteTree(), u.toByteTree(), pkey.toByteTree(),
+                                          w.toByteTree(), wp.toByteTree())                          # :92-98
+        return self.challenger.challenge(challengeData, 8 * self.prg.minNoSeedBytes(), self.rbitlen)
+
+    # -- :75-150
+    def prove(self, g, h, u, pkey, w, wp, r, pi, s):
+        P = CCPoSBasicW(self.vbitlen, self.ebitlen, self.rbitlen, self.prg)
+        P.setInstance(g, h, u, pkey, w, wp, r, pi, s)
+        prgSeed = self._seed(g, h, u, pkey, w, wp)
+        commitment = P.commit(prgSeed, self.randomSource)
+        challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitment)
+        challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
+        reply = P.reply(_to_positive(challengeBytes))
+        out = (commitment.to_bytes(), reply.to_bytes())
+        P.free()
+        return out
+
+    # -- :160-260
+    def verify(self, g, h, u, pkey, w, wp, commitment: bytes, reply: bytes) -> bool:
+        V = CCPoSBasicW(self.vbitlen, self.ebitlen, self.rbitlen, self.prg)
+        V.setInstance(g, h, u, pkey, w, wp)
+        prgSeed = self._seed(g, h, u, pkey, w, wp)
+        V.setBatchVector(prgSeed)
+        V.computeAB()
+        try:
+            commitmentTree = V.setCommitment(ByteTreeReader(commitment))
+        except EIOException:
+            commitmentTree = V.setCommitment(ByteTreeReader(ByteTreeContainer().to_bytes()))
+        challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitmentTree)
+        challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
+        V.setChallenge(_to_positive(challengeBytes))
+        try:
+            verdict = V.verify(ByteTreeReader(reply))
+        except EIOException:
+            verdict = False
+        V.free()
+        return verdict

@@ -16,8 +16,9 @@ from typing import Optional
 
 from .arithm import ModPGroup, Permutation, PPGroup, PPGroupElement
 from .crypto import HashfunctionHeuristic, PRGHeuristic, RandomOracle
-from .eio import ByteTreeContainer, ByteTreeLeaf, ByteTreeReader, int32_leaf
-from .hvzk import ChallengerRO, PoSTW
+from .arithm import ArithmFormatException
+from .eio import ByteTreeContainer, ByteTreeLeaf, ByteTreeReader, EIOException, booleanArrayToByteTree, int32_leaf
+from .hvzk import CCPoSW, ChallengerRO, PoSCTW, PoSTW
 
 
 # ---------------------------------------------------------------- elgamal/ProtocolElGamal.java:753-800
@@ -193,3 +194,201 @@ class ShufflerSession:
             output.free()
             output = ciphertexts.copyOfRange(0, size)
         return verdict, output
+
+
+# ---------------------------------------------------------------- mixnet/PermutationCommitment.java
+class PermutationCommitment:
+    """Pre-computed commitment u = (h * g^t) permuted of one party (mixnet/PermutationCommitment.java:56).
+
+    Array work: g.exp(exponents) fixed-base (:200), mul (:201), permute (:215), the PoSC proof
+    (:286-291 / :309-313), extract(keepList) when the commitment is shrunk to the actual number of
+    ciphertexts (:462-468).  State files and the bulletin board are replaced by attributes / bytes."""
+
+    def __init__(self, session: "ShufflerSession", generators):
+        self.session = session
+        self.generators = generators
+        self.pGroup = generators.getPGroup()
+        self.exponents = self.identityCommitment = self.permutation = self.commitment = None
+        self.raisedCommitment = None
+
+    def _posc(self) -> PoSCTW:
+        p, s = self.session.params, self.session
+        return PoSCTW(p.vbitlenro, p.ebitlenro, p.rbitlen, s.prg, s.randomSource, s.challenger)
+
+    # -- :148-219 (the branch that generates fresh values)
+    def precompute(self) -> None:
+        s = self.session
+        size = self.generators.size()
+        self.exponents = self.pGroup.getPRing().randomElementArray(size, s.randomSource, s.params.rbitlen)
+        tmp = self.pGroup.getg().exp(self.exponents)
+        self.identityCommitment = self.generators.mul(tmp)
+        tmp.free()
+        self.permutation = Permutation.random(size, s.randomSource, s.params.rbitlen)
+        self.commitment = self.identityCommitment.permute(self.permutation)
+
+    # -- :251-292 for l == j: publish the commitment and prove knowledge of (exponents, permutation)
+    def prove(self):
+        """Returns (PermutationCommitment%02d.bt, PoSCCommitment%02d.bt, PoSCReply%02d.bt)."""
+        c, r = self._posc().prove(self.pGroup.getg(), self.generators, self.commitment, self.exponents,
+                                  self.permutation)
+        return self.commitment.toByteTree().to_bytes(), c, r
+
+    # -- :293-346 for l != j
+    def verify(self, commitment: bytes, poscCommitment: bytes, poscReply: bytes, raisedExponent=None) -> bool:
+        """Reads another party's commitment and verifies its PoSC; a malformed commitment or a
+        rejected proof replaces it with the generators ("trivial commitment of identity permutation")."""
+        size = self.generators.size()
+        trivial = False
+        try:
+            self.commitment = self.pGroup.toElementArray(size, ByteTreeReader(commitment))
+        except (ArithmFormatException, EIOException):
+            trivial = True
+        if not trivial:
+            trivial = not self._posc().verify(self.pGroup.getg(), self.generators, self.commitment, poscCommitment,
+                                              poscReply)
+            if trivial:
+                self.commitment.free()
+        if trivial:
+            self.commitment = self.generators.copyOfRange(0, size)
+        if raisedExponent is not None:
+            self.raisedCommitment = self.commitment.exp(raisedExponent)                             # :357
+        return not trivial
+
+    # -- :390-471
+    def shrink(self, noCiphertexts: int, keepList: Optional[bytes] = None) -> bytes:
+        """l == j (keepList is None): derive and publish the keep list, shrink exponents and permutation.
+        l != j: read the published keep list (trivial list on any defect).  Returns KeepList%02d.bt."""
+        import numpy as np
+        size = self.commitment.size()
+        if keepList is None:
+            keep = np.zeros(size, dtype=bool)
+            keep[self.permutation.table[:noCiphertexts]] = True
+            old = self.exponents
+            self.exponents = old.copyOfRange(0, noCiphertexts)
+            old.free()
+            self.permutation = self.permutation.shrink(noCiphertexts)
+        else:
+            trivial = False
+            try:
+                keep = ByteTreeReader(keepList).readBooleans(size)
+            except EIOException:
+                trivial = True
+            if not trivial and int(keep.sum()) != noCiphertexts:
+                trivial = True
+            if trivial:
+                keep = np.zeros(size, dtype=bool)
+                keep[:noCiphertexts] = True
+        old = self.commitment
+        self.commitment = old.extract(keep)
+        old.free()
+        if self.raisedCommitment is not None:
+            old = self.raisedCommitment
+            self.raisedCommitment = old.extract(keep)
+            old.free()
+        return booleanArrayToByteTree(keep).to_bytes()
+
+    def free(self) -> None:
+        for a in (self.exponents, self.identityCommitment, self.commitment, self.raisedCommitment):
+            if a is not None:
+                a.free()
+        self.exponents = self.identityCommitment = self.commitment = self.raisedCommitment = None
+
+
+@dataclass
+class CommittedShuffleProof:
+    """What a mix-server publishes for one commitment-consistent shuffle: Ciphertexts%02d.bt,
+    CCPoSCommitment%02d.bt, CCPoSReply%02d.bt (hvzk/CCPoSW.java:274-288)."""
+    output: bytes
+    commitment: bytes
+    reply: bytes
+
+
+class CommittedShuffler:
+    """Pre-computation and commitment-consistent shuffling of one party: the arithmetic of
+    ShufflerElGamalSession.precomp (:534-672), shrink (:673-760) and committedShuffle (:771-960)."""
+
+    def __init__(self, session: "ShufflerSession", width: int, maxciph: int):
+        self.session = session
+        self.width = width
+        self.maxciph = maxciph
+        self.generators = session.deriveGenerators(maxciph)                                          # :568
+        self.widePublicKey = getWidePublicKey(session.publicKey, width)
+        self.permutationCommitment = PermutationCommitment(session, self.generators)
+        self.reencExponents = self.reencFactors = None
+
+    def _ccpos(self) -> CCPoSW:
+        p, s = self.session.params, self.session
+        return CCPoSW(p.vbitlenro, p.ebitlenro, p.rbitlen, s.prg, s.randomSource, s.challenger)
+
+    # -- :598-658 for an active party
+    def precomp(self):
+        """Commit to a permutation and pre-compute the re-encryption factors for maxciph ciphertexts.
+        Returns the three published byte strings of PermutationCommitment.prove()."""
+        s = self.session
+        self.permutationCommitment.precompute()
+        published = self.permutationCommitment.prove()
+        exponentsPRing = getCiphPGroup(s.pGroup, self.width).project(0).getPRing()
+        self.reencExponents = exponentsPRing.randomElementArray(self.maxciph, s.randomSource, s.params.rbitlen)  # :647-651
+        self.reencFactors = self.widePublicKey.exp(self.reencExponents)                                          # :658
+        return published
+
+    # -- :673-760
+    def shrink(self, noCiphertexts: int) -> bytes:
+        old = self.generators
+        self.generators = old.copyOfRange(0, noCiphertexts)
+        self.permutationCommitment.generators = self.generators
+        old.free()
+        if self.reencExponents is not None:
+            old = self.reencExponents
+            self.reencExponents = _copy_of_range(old, 0, noCiphertexts)
+            old.free()
+            old = self.reencFactors
+            self.reencFactors = old.copyOfRange(0, noCiphertexts)
+            old.free()
+        return self.permutationCommitment.shrink(noCiphertexts)
+
+    # -- :771-822
+    def shuffle(self, ciphertexts, keep_output: bool = False):
+        pc = self.permutationCommitment
+        reenc = ciphertexts.mul(self.reencFactors)                                                   # :789
+        inverse = pc.permutation.inv()
+        output = reenc.permute(inverse)                                                              # :792
+        reenc.free()
+        output_bytes = output.toByteTree().to_bytes()
+        c, r = self._ccpos().prove(self.generators.getPGroup().getg(), self.generators, pc.commitment,
+                                   self.widePublicKey, ciphertexts, output, pc.exponents, pc.permutation,
+                                   self.reencExponents)                                              # :808-819
+        proof = CommittedShuffleProof(output_bytes, c, r)
+        if keep_output:
+            return proof, output
+        output.free()
+        return proof, None
+
+
+def _copy_of_range(arr, a: int, b: int):
+    if hasattr(arr, "comps"):
+        from .arithm import PPRingElementArray
+        return PPRingElementArray(arr.ring, [c.copyOfRange(a, b) for c in arr.comps])
+    return arr.copyOfRange(a, b)
+
+
+def verifyCommittedShuffle(session: "ShufflerSession", width: int, generators, commitment, ciphertexts,
+                           proof: CommittedShuffleProof):
+    """ShufflerElGamalSession.committedShuffleVerify (:875-960) without the raised-commitment
+    optimisation: read the output, verify the CCPoS against the (shrunk) permutation commitment; on
+    failure the output is replaced by the input.  Returns (verdict, output)."""
+    ciphPPGroup = ciphertexts.getPGroup()
+    size = ciphertexts.size()
+    widePublicKey = getWidePublicKey(session.publicKey, width)
+    try:
+        output = ciphPPGroup.toElementArray(size, ByteTreeReader(proof.output))
+    except Exception:
+        return False, ciphertexts.copyOfRange(0, size)
+    p = session.params
+    V = CCPoSW(p.vbitlenro, p.ebitlenro, p.rbitlen, session.prg, session.randomSource, session.challenger)
+    verdict = V.verify(generators.getPGroup().getg(), generators, commitment, widePublicKey, ciphertexts, output,
+                       proof.commitment, proof.reply)
+    if not verdict:
+        output.free()
+        output = ciphertexts.copyOfRange(0, size)
+    return verdict, output
