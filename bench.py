@@ -206,7 +206,7 @@ def main():
         with ph("reencrypt"):
             s = G.getPRing().randomElementArray(n, rs, params.rbitlen)
             factors = pk.exp(s)
-            pi = A.Permutation.random(n, rs, params.rbitlen)
+            pi = A.Permutation.random(n, rs, params.rbitlen, G)
             reenc = ciphertexts.mul(factors)
             factors.free()
             inv = pi.inv()

@@ -83,6 +83,12 @@ int vmx_garr_prg_sha256(vmx_ctx* ctx, const uint8_t* seed, size_t seedlen, uint6
                         unsigned bitlen, vmx_garr** out);
 /* PGroupElementArray.toByteTree() payload (hvzk/PoSBasicTW.java:694-699). */
 int vmx_garr_to_bytes(const vmx_garr* a, uint8_t* be_out);
+/* The same two conversions on the byte-tree form itself: `leaves` are the n children of the node
+ * an array serialises to, 0x01 || be32(elem_bytes) || payload each (n * (5 + elem_bytes) bytes), so
+ * that the host neither strips nor inserts leaf headers (the arrays of a proof are hashed and
+ * written in exactly this form, hvzk/PoSTW.java:118-130).  Headers are validated on the device. */
+int vmx_garr_from_leaves(vmx_ctx* ctx, size_t n, const uint8_t* leaves, int check_membership, vmx_garr** out);
+int vmx_garr_to_leaves(const vmx_garr* a, uint8_t* leaves_out);
 /* PGroup.toElementArray(size, PGroupElement): n copies of one element (hvzk/PoSBasicTW.java:805). */
 int vmx_garr_fill(vmx_ctx* ctx, size_t n, const uint8_t* elem_be, vmx_garr** out);
 void vmx_garr_free(vmx_garr* a);
@@ -169,7 +175,12 @@ int vmx_rarr_prg_sha256(vmx_ctx* ctx, const uint8_t* seed, size_t seedlen, uint6
  * element i = (i-th `width`-byte integer masked to `bitlen` bits) mod q, bytes drawn on the device. */
 int vmx_rarr_prg_raw_sha256(vmx_ctx* ctx, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t n,
                             size_t width, unsigned bitlen, vmx_rarr** out);
+/* Bytes [offset, offset + nbytes) of the PRGHeuristic(SHA-256) stream of `seed`, expanded on the device and
+ * copied to the host (Permutation.random, mixnet/ShufflerElGamalSession.java:408-409, PermutationCommitment.java:211). */
+int vmx_prg_bytes_sha256(vmx_ctx* ctx, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t nbytes, uint8_t* out);
 int vmx_rarr_to_bytes(const vmx_rarr* a, uint8_t* be_out);
+int vmx_rarr_from_leaves(vmx_ctx* ctx, size_t n, const uint8_t* leaves, vmx_rarr** out); /* as vmx_garr_from_leaves */
+int vmx_rarr_to_leaves(const vmx_rarr* a, uint8_t* leaves_out);
 int vmx_rarr_fill(vmx_ctx* ctx, size_t n, const uint8_t* elem_be, vmx_rarr** out);
 void vmx_rarr_free(vmx_rarr* a);
 size_t vmx_rarr_size(const vmx_rarr* a);

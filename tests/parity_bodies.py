@@ -183,6 +183,9 @@ def random_sources(vmx, bits, n):
     assert vals(G.randomElementArray(n, rs, 100)) == oar.group_random_array(OG, n, ors, 100)
     assert vals(R.randomElementArray(n, rs, 100)) == oar.ring_random_array(OG, n, ors, 100)
     assert list(A.Permutation.random(n, rs, 100).table) == oar.permutation_random(n, ors, 100)
+    # long requests are expanded on the device (vmx_prg_bytes_sha256): same permutation, same stream position
+    big = 700
+    assert list(A.Permutation.random(big, rs, 100, G).table) == oar.permutation_random(big, ors, 100)
     assert rs.getBytes(50) == ors.get_bytes(50)
     prg = cr.PRGHeuristic()
     prg.setSeed(seed("batch"))

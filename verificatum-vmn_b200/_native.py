@@ -47,7 +47,12 @@ SIGNATURES = {
     "vmx_garr_from_raw": (C.c_int, [_P, _SZ, _P, _SZ, C.c_uint, _PP]),
     "vmx_garr_prg_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, _SZ, C.c_uint, _PP]),
     "vmx_rarr_prg_raw_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, _SZ, C.c_uint, _PP]),
+    "vmx_prg_bytes_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, _P]),
     "vmx_garr_to_bytes": (C.c_int, [_P, _P]),
+    "vmx_garr_from_leaves": (C.c_int, [_P, _SZ, _P, C.c_int, _PP]),
+    "vmx_garr_to_leaves": (C.c_int, [_P, _P]),
+    "vmx_rarr_from_leaves": (C.c_int, [_P, _SZ, _P, _PP]),
+    "vmx_rarr_to_leaves": (C.c_int, [_P, _P]),
     "vmx_garr_fill": (C.c_int, [_P, _SZ, _U8, _PP]),
     "vmx_garr_free": (None, [_P]),
     "vmx_garr_size": (_SZ, [_P]),

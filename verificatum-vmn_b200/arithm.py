@@ -23,6 +23,7 @@ Semantics that live in the un-vendored VCR jar ([VCR-mem] in SURVEY.md §8c) and
 from __future__ import annotations
 
 import ctypes as C
+import struct
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -92,11 +93,21 @@ class Permutation:
         return Permutation(np.arange(size, dtype=np.uint32))
 
     @staticmethod
-    def random(size: int, randomSource, statDist: int) -> "Permutation":
-        """Sort-based sampling: `size` integers of ceil(log2 size)+statDist bits, stable argsort."""
+    def random(size: int, randomSource, statDist: int, group: Optional["ModPGroup"] = None) -> "Permutation":
+        """Sort-based sampling: `size` integers of ceil(log2 size)+statDist bits, stable argsort.
+        With `group` given and a PRGHeuristic(SHA-256) source, the random bytes are expanded on that
+        group's device (vmx_prg_bytes_sha256) instead of one host hash per 32 bytes."""
         bits = max(1, (size - 1).bit_length()) + statDist
         nbytes = (bits + 7) // 8
-        raw = np.frombuffer(randomSource.getBytes(size * nbytes), dtype=np.uint8).reshape(size, nbytes)
+        off = _sha256_prg_offset(randomSource) if group is not None else None
+        if off is not None and size * nbytes >= 4096:
+            raw = np.empty(size * nbytes, dtype=np.uint8)
+            nat.check(group._lib.vmx_prg_bytes_sha256(group.ctx, randomSource.seed, len(randomSource.seed), off,
+                                                      size * nbytes, _ptr(raw)))
+            _advance_prg(randomSource, off + size * nbytes)
+            raw = raw.reshape(size, nbytes)
+        else:
+            raw = np.frombuffer(randomSource.getBytes(size * nbytes), dtype=np.uint8).reshape(size, nbytes)
         # big-endian keys as columns of 64-bit words, most significant first; stable lexicographic sort
         pad = (-nbytes) % 8
         m = np.zeros((size, nbytes + pad), dtype=np.uint8)
@@ -138,25 +149,32 @@ class Permutation:
 
 
 class ByteTreeDeviceArray(ByteTreeBasic):
-    """toByteTree() of a device array: the D2H copy happens when the tree is first streamed
-    (into a digest or a file), once, and is cached.  The array must still be alive then."""
+    """toByteTree() of a device array.  The serialisation -- the leaves of the node, headers included,
+    written by the engine in exactly that form (vmx_*_to_leaves) -- is produced when the tree is first
+    streamed (into a digest or a file) and cached ON THE ARRAY (arrays are immutable), so hashing an
+    array that was just published, or that was imported from bytes, costs no second D2H copy."""
 
     def __init__(self, arr):
         self.arr = arr
-        self._leafs = None
         self._n = arr.size()
         self._w = arr.getPGroup().elem_bytes if hasattr(arr, "getPGroup") else arr.ring.byte_len
 
-    def _materialise(self) -> ByteTreeLeafArray:
-        if self._leafs is None:
-            if self.arr.h is None:
-                raise ArithmError("byte tree of a freed array")
-            self._leafs = ByteTreeLeafArray(self.arr.to_matrix())
-            self.arr = None
-        return self._leafs
+    def _stream(self) -> np.ndarray:
+        if hasattr(self.arr, "leaves"):
+            return self.arr.leaves()
+        m = self.arr.to_matrix()  # sharded arrays: gathered matrix
+        buf = np.empty((m.shape[0], 5 + self._w), dtype=np.uint8)
+        buf[:, :5] = np.frombuffer(struct.pack(">BI", 1, self._w), dtype=np.uint8)
+        buf[:, 5:] = m
+        return buf.reshape(-1)
 
     def update(self, digest) -> None:
-        self._materialise().update(digest)
+        digest.update(struct.pack(">BI", 0, self._n))
+        if self._n:
+            digest.update(self._stream().data)
+
+    def to_bytes(self) -> bytes:
+        return struct.pack(">BI", 0, self._n) + (self._stream().tobytes() if self._n else b"")
 
     def total_bytes(self) -> int:
         return 5 + self._n * (5 + self._w)
@@ -239,10 +257,13 @@ class PField(PRing):
         h = C.c_void_p()
         if isinstance(src, ByteTreeReader):
             try:
-                m = src.leaf_matrix(size, self.byte_len)
+                stream = src.leaf_stream(size, self.byte_len)
             except EIOException as e:
                 raise ArithmFormatException(nat.VMX_EFORMAT, str(e))
-            nat.check(lib.vmx_rarr_from_bytes(self.group.ctx, size, _ptr(m), C.byref(h)))
+            nat.check(lib.vmx_rarr_from_leaves(self.group.ctx, size, _ptr(stream), C.byref(h)))
+            arr = self._rarr(h, size)
+            arr._leaves = stream
+            return arr
         else:
             nat.check(lib.vmx_rarr_fill(self.group.ctx, size, _be(src.value, self.byte_len), C.byref(h)))
         return self._rarr(h, size)
@@ -302,6 +323,7 @@ class PRingElementArray:
         self.ring = ring
         self.h = handle
         self._lib = nat.load()
+        self._leaves = None  # cached serialisation (leaves of the byte tree)
 
     # -- bookkeeping
     def getPRing(self):
@@ -408,10 +430,22 @@ class PRingElementArray:
         return int(b.value)
 
     # -- I/O
+    def leaves(self) -> np.ndarray:
+        """The n * (5 + width) bytes this array serialises to (leaf headers included), cached."""
+        if self._leaves is None:
+            if self.h is None:
+                raise ArithmError("byte tree of a freed array")
+            buf = np.empty(self.size() * (5 + self.ring.byte_len), dtype=np.uint8)
+            nat.check(self._lib.vmx_rarr_to_leaves(self.h, _ptr(buf)))
+            self._leaves = buf
+        return self._leaves
+
     def to_matrix(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         n, w = self.size(), self.ring.byte_len
-        m = out if out is not None else np.empty((n, w), dtype=np.uint8)
-        nat.check(self._lib.vmx_rarr_to_bytes(self.h, _ptr(m)))
+        m = self.leaves().reshape(n, 5 + w)[:, 5:]
+        if out is not None:
+            out[:] = m
+            return out
         return m
 
     def toByteTree(self) -> ByteTreeBasic:
@@ -576,10 +610,13 @@ class ModPGroup(PGroup):
         size, src = args
         if isinstance(src, ByteTreeReader):
             try:
-                m = src.leaf_matrix(size, self.elem_bytes)
+                stream = src.leaf_stream(size, self.elem_bytes)
             except EIOException as e:
                 raise ArithmFormatException(nat.VMX_EFORMAT, str(e))
-            nat.check(lib.vmx_garr_from_bytes(self.ctx, size, _ptr(m), 1 if check_membership else 0, C.byref(h)))
+            nat.check(lib.vmx_garr_from_leaves(self.ctx, size, _ptr(stream), 1 if check_membership else 0, C.byref(h)))
+            arr = self._garr(h, size)
+            arr._leaves = stream
+            return arr
         elif isinstance(src, np.ndarray):
             nat.check(lib.vmx_garr_from_bytes(self.ctx, size, _ptr(src), 1 if check_membership else 0, C.byref(h)))
         else:
@@ -705,6 +742,7 @@ class PGroupElementArray:
         self.group = group
         self.h = handle
         self._lib = group._lib
+        self._leaves = None  # cached serialisation (leaves of the byte tree)
 
     def getPGroup(self):
         return self.group
@@ -792,10 +830,22 @@ class PGroupElementArray:
         return bool(eq.value)
 
     # -- I/O
+    def leaves(self) -> np.ndarray:
+        """The n * (5 + width) bytes this array serialises to (leaf headers included), cached."""
+        if self._leaves is None:
+            if self.h is None:
+                raise ArithmError("byte tree of a freed array")
+            buf = np.empty(self.size() * (5 + self.group.elem_bytes), dtype=np.uint8)
+            nat.check(self._lib.vmx_garr_to_leaves(self.h, _ptr(buf)))
+            self._leaves = buf
+        return self._leaves
+
     def to_matrix(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         n, w = self.size(), self.group.elem_bytes
-        m = out if out is not None else np.empty((n, w), dtype=np.uint8)
-        nat.check(self._lib.vmx_garr_to_bytes(self.h, _ptr(m)))
+        m = self.leaves().reshape(n, 5 + w)[:, 5:]
+        if out is not None:
+            out[:] = m
+            return out
         return m
 
     def toByteTree(self) -> ByteTreeBasic:

@@ -32,14 +32,20 @@ VMX_DEV uint32_t be_word(const uint8_t* src, int eb, int j) {  // little-endian 
 }
 
 template <int N>
-VMX_KERNEL(N) k_from_bytes(const uint8_t* __restrict__ raw, size_t n, int eb, int mode, uint32_t* __restrict__ out,
-                           size_t cap, const uint32_t* __restrict__ r2, int* __restrict__ err,
-                           const __grid_constant__ MontParams<N> M) {
+VMX_KERNEL(N) k_from_bytes(const uint8_t* __restrict__ raw, size_t n, int eb, int hdr, int mode,
+                           uint32_t* __restrict__ out, size_t cap, const uint32_t* __restrict__ r2,
+                           int* __restrict__ err, const __grid_constant__ MontParams<N> M) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint8_t* src = raw + i * (size_t)eb;
+  // hdr = 5: the elements are the leaves of a byte tree, 0x01 || be32(eb) || payload each
+  const uint8_t* src = raw + i * (size_t)(eb + hdr) + hdr;
   uint32_t a[N];
   int bad = 0;
+  if (hdr) {
+    const uint8_t* h = src - 5;
+    if (h[0] != 1 || h[1] != (uint8_t)(eb >> 24) || h[2] != (uint8_t)(eb >> 16) || h[3] != (uint8_t)(eb >> 8) ||
+        h[4] != (uint8_t)eb) bad |= kErrPad;
+  }
   for (int k = 0; k < eb - 4 * N; k++) if (src[k] != 0) bad |= kErrPad;
 #pragma unroll
   for (int j = 0; j < N; j++) a[j] = be_word<N>(src, eb, j);
@@ -63,14 +69,17 @@ VMX_KERNEL(N) k_from_bytes(const uint8_t* __restrict__ raw, size_t n, int eb, in
 
 // mode 0: group element (Montgomery -> canonical first); mode 1: ring element.
 template <int N>
-VMX_KERNEL(N) k_to_bytes(const uint32_t* __restrict__ in, size_t cap, size_t n, int eb, int mode,
+VMX_KERNEL(N) k_to_bytes(const uint32_t* __restrict__ in, size_t cap, size_t n, int eb, int hdr, int mode,
                          uint8_t* __restrict__ raw, const __grid_constant__ MontParams<N> M) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t a[N];
   load_elem<N>(a, in, cap, i);
   if (mode == 0) mont_mul<N>(a, OneLoader{}, M);
-  uint8_t* dst = raw + i * (size_t)eb;
+  uint8_t* dst = raw + i * (size_t)(eb + hdr) + hdr;
+  if (hdr) {  // byte-tree leaf header
+    dst[-5] = 1; dst[-4] = (uint8_t)(eb >> 24); dst[-3] = (uint8_t)(eb >> 16); dst[-2] = (uint8_t)(eb >> 8); dst[-1] = (uint8_t)eb;
+  }
   for (int k = 0; k < eb - 4 * N; k++) dst[k] = 0;
 #pragma unroll
   for (int j = 0; j < N; j++) {

@@ -311,7 +311,7 @@ static int upload_one(vmx_ctx* c, const uint8_t* be, bool group, ElemBuf& buf) {
   VMX_TRY(buf.alloc_elems(c, 1));
   VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
   const Modulus& Mod = group ? c->P : c->Q;
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, 1, kThreads, 0, raw.as<uint8_t>(), (size_t)1, (int)eb,
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, 1, kThreads, 0, raw.as<uint8_t>(), (size_t)1, (int)eb, 0,
                                  group ? 0 : 1, buf.d(), buf.cap, Mod.consts, c->d_flag, Mod.params<N>()));
   VMX_CHECK_LAUNCH();
   VMX_TRY(read_flags(c, 1));
@@ -326,7 +326,7 @@ static int download_one(vmx_ctx* c, const uint32_t* d, size_t cap, size_t idx, b
   VMX_TRY(raw.alloc(c, eb));
   const Modulus& Mod = group ? c->P : c->Q;
   // k_to_bytes addresses element i = thread index: shift the base so that thread 0 -> idx
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, 1, kThreads, 0, d + 4 * idx, cap, (size_t)1, (int)eb,
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, 1, kThreads, 0, d + 4 * idx, cap, (size_t)1, (int)eb, 0,
                                  group ? 0 : 1, raw.as<uint8_t>(), Mod.params<N>()));
   VMX_CHECK_LAUNCH();
   c->modmuls += group ? 1 : 0;
@@ -828,7 +828,7 @@ uint64_t vmx_ctx_modmul_count(const vmx_ctx* c) { return c ? c->modmuls.load() :
 // ---------------------------------------------------------------- group arrays: I/O
 static int garr_check_members(vmx_ctx* c, const vmx_garr* a, int* ok);
 
-int vmx_garr_from_bytes(vmx_ctx* c, size_t n, const uint8_t* be, int check_membership, vmx_garr** out) {
+static int garr_import(vmx_ctx* c, size_t n, const uint8_t* be, int hdr, int check_membership, vmx_garr** out) {
   if (!out) return VMX_EARG;
   *out = nullptr;
   VMX_ENTER(c);
@@ -838,15 +838,16 @@ int vmx_garr_from_bytes(vmx_ctx* c, size_t n, const uint8_t* be, int check_membe
   std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(a, vmx_garr_free);
   if (n) {
     DevBuf raw;
-    VMX_TRY(raw.alloc(c, n * c->eb));
-    VMX_CU(cudaMemcpyAsync(raw.p, be, n * c->eb, cudaMemcpyHostToDevice, c->stream));
+    const size_t bytes = n * (c->eb + hdr);
+    VMX_TRY(raw.alloc(c, bytes));
+    VMX_CU(cudaMemcpyAsync(raw.p, be, bytes, cudaMemcpyHostToDevice, c->stream));
     VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
-    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n), kThreads, 0, raw.as<uint8_t>(), n, (int)c->eb, 0,
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n), kThreads, 0, raw.as<uint8_t>(), n, (int)c->eb, hdr, 0,
                                    a->d, a->cap, c->P.consts, c->d_flag, c->P.params<N>()));
     VMX_CHECK_LAUNCH();
     c->modmuls += n;
     VMX_TRY(read_flags(c, 1));
-    if (c->h_flag[0]) { set_error("group element out of range (flags %d)", c->h_flag[0]); return VMX_EFORMAT; }
+    if (c->h_flag[0]) { set_error("group element out of range or malformed leaf (flags %d)", c->h_flag[0]); return VMX_EFORMAT; }
     if (check_membership) {
       int ok = 0;
       VMX_TRY(garr_check_members(c, a, &ok));
@@ -855,6 +856,12 @@ int vmx_garr_from_bytes(vmx_ctx* c, size_t n, const uint8_t* be, int check_membe
   }
   *out = guard.release();
   return VMX_OK;
+}
+int vmx_garr_from_bytes(vmx_ctx* c, size_t n, const uint8_t* be, int check_membership, vmx_garr** out) {
+  return garr_import(c, n, be, 0, check_membership, out);
+}
+int vmx_garr_from_leaves(vmx_ctx* c, size_t n, const uint8_t* leaves, int check_membership, vmx_garr** out) {
+  return garr_import(c, n, leaves, 5, check_membership, out);
 }
 
 static int exp_scalar_limbs(vmx_ctx* c, const vmx_garr* a, const uint32_t* x, vmx_garr** out);
@@ -935,6 +942,21 @@ static int prg_bytes_dev(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64
   return VMX_OK;
 }
 
+// PRGHeuristic(SHA-256) output bytes [offset, offset + nbytes) to the host: the expansion of a long
+// request (Permutation.random draws size * ~15 bytes, mixnet/ShufflerElGamalSession.java:408-409) runs
+// in counter mode on the device instead of one hash call per 32 bytes on the host.
+int vmx_prg_bytes_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t nbytes, uint8_t* out) {
+  VMX_ENTER(c);
+  if (nbytes && !out) return VMX_EARG;
+  if (!nbytes) return VMX_OK;
+  DevBuf buf;
+  const uint8_t* data = nullptr;
+  VMX_TRY(prg_bytes_dev(c, seed, seedlen, offset, nbytes, buf, &data));
+  VMX_CU(cudaMemcpyAsync(out, data, nbytes, cudaMemcpyDeviceToHost, c->stream));
+  VMX_CU(cudaStreamSynchronize(c->stream));
+  return VMX_OK;
+}
+
 int vmx_garr_prg_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t n, size_t width,
                         unsigned bitlen, vmx_garr** out) {
   if (!out) return VMX_EARG;
@@ -973,21 +995,25 @@ int vmx_rarr_prg_raw_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uin
   return VMX_OK;
 }
 
-int vmx_garr_to_bytes(const vmx_garr* a, uint8_t* be_out) {
+static int garr_export(const vmx_garr* a, int hdr, uint8_t* be_out) {
   if (!a) return VMX_EARG;
   vmx_ctx* c = a->ctx;
   VMX_ENTER(c);
   if (!a->n) return VMX_OK;
+  if (!be_out) return VMX_EARG;
   DevBuf raw;
-  VMX_TRY(raw.alloc(c, a->n * c->eb));
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, a->n, (int)c->eb, 0,
+  const size_t bytes = a->n * (c->eb + hdr);
+  VMX_TRY(raw.alloc(c, bytes));
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, a->n, (int)c->eb, hdr, 0,
                                  raw.as<uint8_t>(), c->P.params<N>()));
   VMX_CHECK_LAUNCH();
   c->modmuls += a->n;
-  VMX_CU(cudaMemcpyAsync(be_out, raw.p, a->n * c->eb, cudaMemcpyDeviceToHost, c->stream));
+  VMX_CU(cudaMemcpyAsync(be_out, raw.p, bytes, cudaMemcpyDeviceToHost, c->stream));
   VMX_CU(cudaStreamSynchronize(c->stream));
   return VMX_OK;
 }
+int vmx_garr_to_bytes(const vmx_garr* a, uint8_t* be_out) { return garr_export(a, 0, be_out); }
+int vmx_garr_to_leaves(const vmx_garr* a, uint8_t* leaves_out) { return garr_export(a, 5, leaves_out); }
 
 int vmx_garr_fill(vmx_ctx* c, size_t n, const uint8_t* elem_be, vmx_garr** out) {
   if (!out) return VMX_EARG;
@@ -1192,7 +1218,7 @@ int vmx_expprod(const vmx_garr* const* a, size_t k, const vmx_rarr* e, uint8_t* 
   }
   DevBuf raw;
   VMX_TRY(raw.alloc(c, k * c->eb));
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, 1, kThreads, 0, res.d(), res.cap, k, (int)c->eb, 0,
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, 1, kThreads, 0, res.d(), res.cap, k, (int)c->eb, 0, 0,
                                  raw.as<uint8_t>(), c->P.params<N>()));
   VMX_CHECK_LAUNCH();
   VMX_CU(cudaMemcpyAsync(out_be, raw.p, k * c->eb, cudaMemcpyDeviceToHost, c->stream));
@@ -1464,7 +1490,7 @@ int vmx_expprod_cols(const vmx_garr* const* bases, size_t t, const int64_t* ints
 }
 
 // ---------------------------------------------------------------- ring arrays
-int vmx_rarr_from_bytes(vmx_ctx* c, size_t n, const uint8_t* be, vmx_rarr** out) {
+static int rarr_import(vmx_ctx* c, size_t n, const uint8_t* be, int hdr, vmx_rarr** out) {
   if (!out) return VMX_EARG;
   *out = nullptr;
   VMX_ENTER(c);
@@ -1474,18 +1500,21 @@ int vmx_rarr_from_bytes(vmx_ctx* c, size_t n, const uint8_t* be, vmx_rarr** out)
   std::unique_ptr<vmx_rarr, void (*)(vmx_rarr*)> guard(a, vmx_rarr_free);
   if (n) {
     DevBuf raw;
-    VMX_TRY(raw.alloc(c, n * c->rb));
-    VMX_CU(cudaMemcpyAsync(raw.p, be, n * c->rb, cudaMemcpyHostToDevice, c->stream));
+    const size_t bytes = n * (c->rb + hdr);
+    VMX_TRY(raw.alloc(c, bytes));
+    VMX_CU(cudaMemcpyAsync(raw.p, be, bytes, cudaMemcpyHostToDevice, c->stream));
     VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
-    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n), kThreads, 0, raw.as<uint8_t>(), n, (int)c->rb, 1,
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n), kThreads, 0, raw.as<uint8_t>(), n, (int)c->rb, hdr, 1,
                                    a->d, a->cap, c->Q.consts, c->d_flag, c->Q.params<N>()));
     VMX_CHECK_LAUNCH();
     VMX_TRY(read_flags(c, 1));
-    if (c->h_flag[0]) { set_error("ring element out of range (flags %d)", c->h_flag[0]); return VMX_EFORMAT; }
+    if (c->h_flag[0]) { set_error("ring element out of range or malformed leaf (flags %d)", c->h_flag[0]); return VMX_EFORMAT; }
   }
   *out = guard.release();
   return VMX_OK;
 }
+int vmx_rarr_from_bytes(vmx_ctx* c, size_t n, const uint8_t* be, vmx_rarr** out) { return rarr_import(c, n, be, 0, out); }
+int vmx_rarr_from_leaves(vmx_ctx* c, size_t n, const uint8_t* leaves, vmx_rarr** out) { return rarr_import(c, n, leaves, 5, out); }
 
 int vmx_rarr_from_raw(vmx_ctx* c, size_t n, const uint8_t* be, size_t width, unsigned bitlen, vmx_rarr** out) {
   if (!out) return VMX_EARG;
@@ -1535,20 +1564,24 @@ int vmx_rarr_prg_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64_
   return VMX_OK;
 }
 
-int vmx_rarr_to_bytes(const vmx_rarr* a, uint8_t* be_out) {
+static int rarr_export(const vmx_rarr* a, int hdr, uint8_t* be_out) {
   if (!a) return VMX_EARG;
   vmx_ctx* c = a->ctx;
   VMX_ENTER(c);
   if (!a->n) return VMX_OK;
+  if (!be_out) return VMX_EARG;
   DevBuf raw;
-  VMX_TRY(raw.alloc(c, a->n * c->rb));
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, a->n, (int)c->rb, 1,
+  const size_t bytes = a->n * (c->rb + hdr);
+  VMX_TRY(raw.alloc(c, bytes));
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, a->n, (int)c->rb, hdr, 1,
                                  raw.as<uint8_t>(), c->Q.params<N>()));
   VMX_CHECK_LAUNCH();
-  VMX_CU(cudaMemcpyAsync(be_out, raw.p, a->n * c->rb, cudaMemcpyDeviceToHost, c->stream));
+  VMX_CU(cudaMemcpyAsync(be_out, raw.p, bytes, cudaMemcpyDeviceToHost, c->stream));
   VMX_CU(cudaStreamSynchronize(c->stream));
   return VMX_OK;
 }
+int vmx_rarr_to_bytes(const vmx_rarr* a, uint8_t* be_out) { return rarr_export(a, 0, be_out); }
+int vmx_rarr_to_leaves(const vmx_rarr* a, uint8_t* leaves_out) { return rarr_export(a, 5, leaves_out); }
 
 int vmx_rarr_fill(vmx_ctx* c, size_t n, const uint8_t* elem_be, vmx_rarr** out) {
   if (!out) return VMX_EARG;

@@ -191,6 +191,18 @@ class ByteTreeReader:
             raise EIOException("malformed boolean")
         return raw.astype(bool)
 
+    def leaf_stream(self, size: int, width: int) -> np.ndarray:
+        """This node as `size` leaves of exactly `width` bytes -> the size * (5 + width) bytes of the
+        leaves (headers included), as a view of the underlying buffer when that is immutable, else a
+        copy.  The engine validates the headers on the device (vmx_garr_from_leaves)."""
+        if self.kind != NODE or self.count != size:
+            raise EIOException("expected a node of %d children" % size)
+        end = self.pos + size * (5 + width)
+        if end > len(self.buf):
+            raise EIOException("truncated array")
+        v = np.frombuffer(self.buf[self.pos:end], dtype=np.uint8)
+        return v if self.buf.readonly else v.copy()
+
     def leaf_matrix(self, size: int, width: int) -> np.ndarray:
         """This node as `size` leaves of exactly `width` bytes -> (size, width) uint8 matrix."""
         if self.kind != NODE or self.count != size:

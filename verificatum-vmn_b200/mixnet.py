@@ -146,7 +146,7 @@ class ShufflerSession:
         rbitlen = self.params.rbitlen
         reencExponents = exponentsPRing.randomElementArray(size, self.randomSource, rbitlen)       # :400-403
         reencFactors = widePublicKey.exp(reencExponents)                                           # :407
-        permutation = Permutation.random(size, self.randomSource, rbitlen)                         # :408-409
+        permutation = Permutation.random(size, self.randomSource, rbitlen, self.pGroup.basic()[0])                       # :408-409
         P = self._pos()
         P.precompute(generators.getPGroup().getg(), generators, permutation)                       # :414
         reenc = ciphertexts.mul(reencFactors)                                                      # :273
@@ -223,7 +223,7 @@ class PermutationCommitment:
         tmp = self.pGroup.getg().exp(self.exponents)
         self.identityCommitment = self.generators.mul(tmp)
         tmp.free()
-        self.permutation = Permutation.random(size, s.randomSource, s.params.rbitlen)
+        self.permutation = Permutation.random(size, s.randomSource, s.params.rbitlen, self.pGroup.basic()[0])
         self.commitment = self.identityCommitment.permute(self.permutation)
 
     # -- :251-292 for l == j: publish the commitment and prove knowledge of (exponents, permutation)

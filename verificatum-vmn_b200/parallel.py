@@ -201,18 +201,22 @@ class ShardedField(PField):
         lo, hi = self._range(size)
         if isinstance(src, ByteTreeReader):
             try:
-                m = np.ascontiguousarray(src.leaf_matrix(size, self.byte_len)[lo:hi])
+                stream = src.leaf_stream(size, self.byte_len)
             except EIOException as e:
                 raise ArithmFormatException(nat.VMX_EFORMAT, str(e))
+            w = 5 + self.byte_len
             ok = True
             try:
-                nat.check(lib.vmx_rarr_from_bytes(self.group.ctx, hi - lo, _ptr(m), C.byref(h)))
+                nat.check(lib.vmx_rarr_from_leaves(self.group.ctx, hi - lo, _ptr(stream[lo * w:hi * w]), C.byref(h)))
             except ArithmFormatException:
                 ok = False
             if not self.comm.all_and(ok):  # a malformed element in ANY shard rejects the array on every rank
                 if ok:
                     lib.vmx_rarr_free(h)
                 raise ArithmFormatException(nat.VMX_EFORMAT, "ring element out of range")
+            arr = self._rarr(h, size)
+            arr._leaves = stream  # every rank parsed the same bytes: no gather needed to hash them
+            return arr
         else:
             nat.check(lib.vmx_rarr_fill(self.group.ctx, hi - lo, _be(src.value, self.byte_len), C.byref(h)))
         return self._rarr(h, size)
@@ -344,14 +348,14 @@ class ShardedRingArray(PRingElementArray):
         return self.comm.all_max(PRingElementArray.bitLength(self) if self.local_size() else 0)
 
     # -- I/O
-    def to_matrix(self, out: Optional[np.ndarray] = None) -> np.ndarray:
-        m = np.empty((self.local_size(), self.ring.byte_len), dtype=np.uint8)
-        nat.check(self._lib.vmx_rarr_to_bytes(self.h, _ptr(m)))
-        full = self.comm.allgather_matrix(m, self.bounds)
-        if out is not None:
-            out[:] = full
-            return out
-        return full
+    def leaves(self) -> np.ndarray:
+        """Serialisation of the WHOLE array (all shards, gathered to every rank), cached."""
+        if self._leaves is None:
+            w = 5 + self.ring.byte_len
+            m = np.empty((self.local_size(), w), dtype=np.uint8)
+            nat.check(self._lib.vmx_rarr_to_leaves(self.h, _ptr(m)))
+            self._leaves = np.ascontiguousarray(self.comm.allgather_matrix(m, self.bounds)).reshape(-1)
+        return self._leaves
 
 
 # ====================================================================== sharded group arrays
@@ -404,9 +408,11 @@ class ShardedModPGroup(ModPGroup):
         size, src = args
         lo, hi = self._range(size)
         if isinstance(src, (ByteTreeReader, np.ndarray)):
+            stream = None
             if isinstance(src, ByteTreeReader):
                 try:
                     m = src.leaf_matrix(size, self.elem_bytes)
+                    stream = src.leaf_stream(size, self.elem_bytes)
                 except EIOException as e:
                     raise ArithmFormatException(nat.VMX_EFORMAT, str(e))
             else:
@@ -421,6 +427,10 @@ class ShardedModPGroup(ModPGroup):
                 if ok:
                     lib.vmx_garr_free(h)
                 raise ArithmFormatException(nat.VMX_EFORMAT, "group element out of range or not in the subgroup")
+            arr = self._garr(h, size)
+            if stream is not None:
+                arr._leaves = stream  # every rank parsed the same bytes: no gather needed to hash them
+            return arr
         else:
             nat.check(lib.vmx_garr_fill(self.ctx, hi - lo, _be(src.value, self.elem_bytes), C.byref(h)))
         return self._garr(h, size)
@@ -498,14 +508,14 @@ class ShardedGroupArray(PGroupElementArray):
     def equals(self, o) -> bool:
         return self.comm.all_and(PGroupElementArray.equals(self, o) if self.local_size() else True)
 
-    def to_matrix(self, out: Optional[np.ndarray] = None) -> np.ndarray:
-        m = np.empty((self.local_size(), self.group.elem_bytes), dtype=np.uint8)
-        nat.check(self._lib.vmx_garr_to_bytes(self.h, _ptr(m)))
-        full = self.comm.allgather_matrix(m, self.bounds)
-        if out is not None:
-            out[:] = full
-            return out
-        return full
+    def leaves(self) -> np.ndarray:
+        """Serialisation of the WHOLE array (all shards, gathered to every rank), cached."""
+        if self._leaves is None:
+            w = 5 + self.group.elem_bytes
+            m = np.empty((self.local_size(), w), dtype=np.uint8)
+            nat.check(self._lib.vmx_garr_to_leaves(self.h, _ptr(m)))
+            self._leaves = np.ascontiguousarray(self.comm.allgather_matrix(m, self.bounds)).reshape(-1)
+        return self._leaves
 
 
 def _sharded_permute(arr, pi: Permutation, ring: bool):
