@@ -301,9 +301,18 @@ def main():
         e.free()
         macs = macs_per_modmul(args.bits)
         achieved = k_modmuls * macs / (k_ms * 1e-3)
+        traffic = pipe_busy = None
+        try:  # one `ncu --set full` capture of this kernel at the same shape (profiles/, per launch)
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_exp_fixed.json")))
+            if cap["n"] == n_local and args.bits == 3072:
+                traffic, pipe_busy = cap["traffic_bytes"], cap["fmaheavy_pipe_busy_pct"]
+        except Exception:
+            pass
         roof = {"bound": "imad", "kernel": "k_exp_fixed<%d>" % (args.bits // 32), "achieved": achieved / 1e12,
                 "peak": IMAD_PEAK_MAC_PER_S / 1e12, "unit": "TMAC/s (32x32+64 IMAD.WIDE)", "frac": achieved / IMAD_PEAK_MAC_PER_S,
-                "traffic": None, "modmuls_per_launch": k_modmuls, "ms_per_launch": k_ms,
+                "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu, profiles/r01_ncu_exp_fixed.json)",
+                "algorithmic_bytes": k_modmuls * (args.bits // 8) + 2 * n_local * (args.bits // 8),
+                "imad_pipe_busy_pct_ncu": pipe_busy, "modmuls_per_launch": k_modmuls, "ms_per_launch": k_ms,
                 "peak_source": "measured on B200 (profiles/r01_ubench_imad.txt); MEASURED_PEAKS.json has no integer peak",
                 "hbm_note": "integer-pipe bound: arithmetic intensity ~1e4 MAC/B, HBM is not the limiter"}
 

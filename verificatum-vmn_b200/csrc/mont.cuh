@@ -124,22 +124,45 @@ VMX_DEV void mont_final_sub(uint32_t (&r)[N], const uint32_t (&t)[N + 2], const 
 
 struct Word2 { uint32_t x, y; };
 
+// The accumulator crosses the loop back edge as 64-bit values: ptxas then keeps every (lo, hi) word
+// pair in an aligned register pair for the whole loop.  With 32-bit loop-carried words it picked
+// an unaligned assignment and re-paired them with ~150 IMAD.MOV/MOV per trip (against 384
+// IMAD.WIDE), which cost ~12 % of the integer pipe (profiles/r01_ncu_full_exp_fixed_exp_var.txt).
+#ifndef VMX_HOST_EMUL
+VMX_DEV uint64_t pack_pair(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+VMX_DEV void unpack_pair(uint32_t& lo, uint32_t& hi, uint64_t v) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+#else
+VMX_DEV uint64_t pack_pair(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+VMX_DEV void unpack_pair(uint32_t& lo, uint32_t& hi, uint64_t v) { lo = (uint32_t)v; hi = (uint32_t)(v >> 32); }
+#endif
+
 // a <- a * b * R^{-1} mod n, with b streamed through `ld2(i)` (any callable returning the
 // word pair (b[i], b[i+1]) for even i).  Result fully reduced to [0, n).
 template <int N, typename Loader>
 VMX_DEV void mont_mul(uint32_t (&a)[N], Loader ld2, const MontParams<N>& M) {
-  uint32_t t[N + 2];
+  uint64_t T[N / 2 + 1];
 #pragma unroll
-  for (int i = 0; i < N + 2; i++) t[i] = 0;
+  for (int k = 0; k < N / 2 + 1; k++) T[k] = 0;
+  uint32_t t[N + 2];
   // the operand words of trip i+1 are requested before trip i is computed (the loads are
   // gathers from L2/HBM tables in the exponentiation kernels; one trip hides their latency)
   Word2 b = ld2(0);
 #pragma unroll 1
   for (int i = 0; i < N; i += 2) {
     const Word2 nb = ld2(i + 2 < N ? i + 2 : i);
+#pragma unroll
+    for (int k = 0; k < N / 2 + 1; k++) unpack_pair(t[2 * k], t[2 * k + 1], T[k]);
     mont_rowpair<N>(t, a, b.x, b.y, M);
+#pragma unroll
+    for (int k = 0; k < N / 2 + 1; k++) T[k] = pack_pair(t[2 * k], t[2 * k + 1]);
     b = nb;
   }
+#pragma unroll
+  for (int k = 0; k < N / 2 + 1; k++) unpack_pair(t[2 * k], t[2 * k + 1], T[k]);
   mont_final_sub<N>(a, t, M);
 }
 
