@@ -29,15 +29,56 @@ from . import bytetree as bt
 
 
 class ModPGroup:
+    """Subgroup of order q of Z_p^*.  A group exposes one, op_mul / op_inv / op_exp on single elements
+    (ints here, ECPoint for oracle.ec.ECqPGroup) and its own element / array encodings, so that the
+    array functions and the protocol restatements below are written once for both."""
+
     def __init__(self, p: int, q: int, g: int):
         assert pow(g, q, p) == 1 and g != 1
         self.p, self.q, self.g = p, q, g
         self.elem_bytes = p.bit_length() // 8 + 1   # BigInteger.toByteArray() length of p
         self.ring_bytes = q.bit_length() // 8 + 1
         self.cofactor = (p - 1) // q
+        self.one = 1
 
     def contains(self, x: int) -> bool:
         return 0 < x < self.p and pow(x, self.q, self.p) == 1
+
+    def op_mul(self, a: int, b: int) -> int:
+        return a * b % self.p
+
+    def op_inv(self, a: int) -> int:
+        return pow(a, -1, self.p)
+
+    def op_exp(self, a: int, e: int) -> int:
+        return pow(a, e, self.p)
+
+    # encodings: a leaf of elem_bytes bytes per element, an array is a node of such leaves
+    def leaf_tree(self, x: int) -> bt.ByteTree:
+        return bt.int_leaf(x, self.elem_bytes)
+
+    def leaf_array_tree(self, arr) -> bt.ByteTree:
+        return bt.node([bt.int_leaf(x, self.elem_bytes) for x in arr])
+
+    def parse_leaf(self, t: bt.ByteTree) -> int:
+        if not t.is_leaf() or len(t.value) != self.elem_bytes:
+            raise FormatError("element length")
+        x = bt.bytes_to_int(t.value)
+        if not self.contains(x):
+            raise FormatError("not a group element")
+        return x
+
+    def parse_leaf_array(self, t: bt.ByteTree, size: int):
+        if t.is_leaf() or len(t.children) != size:
+            raise FormatError("array size")
+        return [self.parse_leaf(c) for c in t.children]
+
+    def random_array(self, n: int, rs, stat_dist: int):
+        """pGroup.randomElementArray(n, prg, statDist) (distr/IndependentGeneratorsRO.java:129):
+        t^((p-1)/q) for wide random t."""
+        bits = self.p.bit_length() + stat_dist
+        w = (bits + 7) // 8
+        return [pow(_masked_int(rs.get_bytes(w), bits) % self.p, self.cofactor, self.p) for _ in range(n)]
 
 
 # ---------------------------------------------------------------- structure helpers
@@ -69,13 +110,13 @@ def size_of(arr) -> int:
 def elem_tree(G: ModPGroup, x) -> bt.ByteTree:
     if isinstance(x, tuple):
         return bt.node([elem_tree(G, c) for c in x])
-    return bt.int_leaf(x, G.elem_bytes)
+    return G.leaf_tree(x)
 
 
 def array_tree(G: ModPGroup, arr) -> bt.ByteTree:
     if isinstance(arr, tuple):
         return bt.node([array_tree(G, c) for c in arr])
-    return bt.node([bt.int_leaf(x, G.elem_bytes) for x in arr])
+    return G.leaf_array_tree(arr)
 
 
 def ring_tree(G: ModPGroup, x) -> bt.ByteTree:
@@ -99,12 +140,7 @@ def parse_elem(G: ModPGroup, t: bt.ByteTree, shape=None) -> int:
         if t.is_leaf() or len(t.children) != len(shape):
             raise FormatError("arity")
         return tuple(parse_elem(G, c, s) for c, s in zip(t.children, shape))
-    if not t.is_leaf() or len(t.value) != G.elem_bytes:
-        raise FormatError("element length")
-    x = bt.bytes_to_int(t.value)
-    if not G.contains(x):
-        raise FormatError("not a group element")
-    return x
+    return G.parse_leaf(t)
 
 
 def parse_array(G: ModPGroup, t: bt.ByteTree, size: int, shape=None):
@@ -112,9 +148,7 @@ def parse_array(G: ModPGroup, t: bt.ByteTree, size: int, shape=None):
         if t.is_leaf() or len(t.children) != len(shape):
             raise FormatError("arity")
         return tuple(parse_array(G, c, size, s) for c, s in zip(t.children, shape))
-    if t.is_leaf() or len(t.children) != size:
-        raise FormatError("array size")
-    return [parse_elem(G, c) for c in t.children]
+    return G.parse_leaf_array(t, size)
 
 
 def parse_ring(G: ModPGroup, t: bt.ByteTree, shape=None):
@@ -158,12 +192,8 @@ def lia_random(n: int, bits: int, rs) -> List[int]:
     return [_masked_int(rs.get_bytes(w), bits) for _ in range(n)]
 
 
-def group_random_array(G: ModPGroup, n: int, rs, stat_dist: int) -> List[int]:
-    """pGroup.randomElementArray(n, prg, statDist) for ModPGroup
-    (distr/IndependentGeneratorsRO.java:129): t^((p-1)/q) for wide random t."""
-    bits = G.p.bit_length() + stat_dist
-    w = (bits + 7) // 8
-    return [pow(_masked_int(rs.get_bytes(w), bits) % G.p, G.cofactor, G.p) for _ in range(n)]
+def group_random_array(G: ModPGroup, n: int, rs, stat_dist: int):
+    return G.random_array(n, rs, stat_dist)
 
 
 def permutation_random(n: int, rs, stat_dist: int) -> List[int]:
@@ -198,11 +228,11 @@ def permute(arr, table):
 
 # ---------------------------------------------------------------- group array operations
 def g_mul(G, a, b):
-    return gmap(lambda x, y: [u * v % G.p for u, v in zip(x, y)] if isinstance(x, list) else x * y % G.p, a, b)
+    return gmap(lambda x, y: [G.op_mul(u, v) for u, v in zip(x, y)] if isinstance(x, list) else G.op_mul(x, y), a, b)
 
 
 def g_inv(G, a):
-    return gmap(lambda x: [pow(u, -1, G.p) for u in x] if isinstance(x, list) else pow(x, -1, G.p), a)
+    return gmap(lambda x: [G.op_inv(u) for u in x] if isinstance(x, list) else G.op_inv(x), a)
 
 
 def g_exp(G, base, e):
@@ -214,11 +244,11 @@ def g_exp(G, base, e):
         return tuple(g_exp(G, b, e) for b in base)
     if isinstance(base, list):
         if isinstance(e, list):
-            return [pow(b, x, G.p) for b, x in zip(base, e)]
-        return [pow(b, e, G.p) for b in base]
+            return [G.op_exp(b, x) for b, x in zip(base, e)]
+        return [G.op_exp(b, e) for b in base]
     if isinstance(e, list):
-        return [pow(base, x, G.p) for x in e]
-    return pow(base, e, G.p)
+        return [G.op_exp(base, x) for x in e]
+    return G.op_exp(base, e)
 
 
 def _same_shape(a, b) -> bool:
@@ -232,18 +262,18 @@ def _same_shape(a, b) -> bool:
 def g_exp_prod(G, arr, e: List[int]):
     """array.expProd(e) = prod_i arr[i]^e[i] (component-wise for product arrays)."""
     def one(col):
-        acc = 1
+        acc = G.one
         for x, k in zip(col, e):
-            acc = acc * pow(x, k, G.p) % G.p
+            acc = G.op_mul(acc, G.op_exp(x, k))
         return acc
     return gmap(one, arr)
 
 
 def g_prod(G, arr):
     def one(col):
-        acc = 1
+        acc = G.one
         for x in col:
-            acc = acc * x % G.p
+            acc = G.op_mul(acc, x)
         return acc
     return gmap(one, arr)
 

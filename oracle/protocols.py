@@ -113,7 +113,7 @@ class PoSBasicTW:
         self.alpha = ar.ring_random_element(G, self.rs, self.rbitlen)
         # pField.toElementArray(epsilonIntegers) (:473): field elements, i.e. reduced mod q
         self.epsilon = [v % G.q for v in ar.lia_random(self.size, self.ebitlen + self.vbitlen + self.rbitlen, self.rs)]
-        self.Ap = ar.g_exp(G, g, self.alpha) * ar.g_exp_prod(G, h, self.epsilon) % G.p
+        self.Ap = ar.g_mul(G, ar.g_exp(G, g, self.alpha), ar.g_exp_prod(G, h, self.epsilon))
 
     def set_instance(self, pkey, w, wp, s=None):
         self.pkey, self.w, self.wp, self.s = pkey, w, wp, s
@@ -169,10 +169,10 @@ class PoSBasicTW:
             self.Dp = ar.parse_elem(G, c[4])
             self.Fp = ar.parse_elem(G, c[5], self.pkey)
         except ar.FormatError:
-            self.B = [1] * self.size
-            self.Bp = [1] * self.size
-            self.Ap = self.Cp = self.Dp = 1
-            self.Fp = ar.gmap(lambda _: 1, self.pkey)
+            self.B = [G.one] * self.size
+            self.Bp = [G.one] * self.size
+            self.Ap = self.Cp = self.Dp = G.one
+            self.Fp = ar.gmap(lambda _: G.one, self.pkey)
         return self.commitment_tree()
 
     def set_challenge(self, v: int):
@@ -202,7 +202,7 @@ class PoSBasicTW:
 
     # :970-990, :1000-1066
     def verify(self, t: bt.ByteTree) -> bool:
-        G, g, h, u, p = self.G, self.g, self.h, self.u, self.G.p
+        G, g, h, u = self.G, self.g, self.h, self.u
         try:
             if t.is_leaf() or len(t.children) != 6:
                 raise ar.FormatError("reply arity")
@@ -217,17 +217,17 @@ class PoSBasicTW:
             return False
         v = self.v
         h0 = h[0]
-        C = ar.g_prod(G, u) * pow(ar.g_prod(G, h), -1, p) % p
+        C = ar.g_mul(G, ar.g_prod(G, u), ar.g_inv(G, ar.g_prod(G, h)))
         eprod = 1
         for x in self.e:
             eprod = eprod * x % G.q
-        D = self.B[-1] * pow(ar.g_exp(G, h0, eprod), -1, p) % p
-        vA = ar.g_exp(G, self.A, v) * self.Ap % p == ar.g_exp(G, g, self.k_A) * ar.g_exp_prod(G, h, self.k_E) % p
+        D = ar.g_mul(G, self.B[-1], ar.g_inv(G, ar.g_exp(G, h0, eprod)))
+        vA = ar.g_mul(G, ar.g_exp(G, self.A, v), self.Ap) == ar.g_mul(G, ar.g_exp(G, g, self.k_A), ar.g_exp_prod(G, h, self.k_E))
         left = ar.g_mul(G, ar.g_exp(G, self.B, v), self.Bp)
         right = ar.g_mul(G, ar.g_exp(G, g, self.k_B), ar.g_exp(G, [h0] + self.B[:-1], self.k_E))
         vB = left == right
-        vC = ar.g_exp(G, C, v) * self.Cp % p == ar.g_exp(G, g, self.k_C)
-        vD = ar.g_exp(G, D, v) * self.Dp % p == ar.g_exp(G, g, self.k_D)
+        vC = ar.g_mul(G, ar.g_exp(G, C, v), self.Cp) == ar.g_exp(G, g, self.k_C)
+        vD = ar.g_mul(G, ar.g_exp(G, D, v), self.Dp) == ar.g_exp(G, g, self.k_D)
         lhsF = ar.g_mul(G, ar.g_exp(G, self.F, v), self.Fp)
         rhsF = ar.g_mul(G, ar.g_exp(G, self.pkey, _rneg(G, self.k_F)), ar.g_exp_prod(G, self.wp, self.k_E))
         vF = lhsF == rhsF
@@ -336,7 +336,7 @@ class PoSCBasicTW:
         self.B = ar.g_mul(G, ar.g_exp(G, g, x), ar.g_exp(G, h0, y))
         self.alpha = ar.ring_random_element(G, self.rs, self.rbitlen)
         self.epsilon = [v % G.q for v in ar.lia_random(self.size, self.ebitlen + self.vbitlen + self.rbitlen, self.rs)]
-        self.Ap = ar.g_exp(G, g, self.alpha) * ar.g_exp_prod(G, h, self.epsilon) % G.p
+        self.Ap = ar.g_mul(G, ar.g_exp(G, g, self.alpha), ar.g_exp_prod(G, h, self.epsilon))
         self.beta = ar.ring_random_array(G, self.size, self.rs, self.rbitlen)
         xp = [0] + x[:-1]
         yp = [1] + y[:-1]
@@ -367,9 +367,9 @@ class PoSCBasicTW:
             self.Cp = ar.parse_elem(G, c[3])
             self.Dp = ar.parse_elem(G, c[4])
         except ar.FormatError:
-            self.B = [1] * self.size
-            self.Bp = [1] * self.size
-            self.Ap = self.Cp = self.Dp = 1
+            self.B = [G.one] * self.size
+            self.Bp = [G.one] * self.size
+            self.Ap = self.Cp = self.Dp = G.one
         return self.commitment_tree()
 
     def set_challenge(self, v: int):
@@ -393,7 +393,7 @@ class PoSCBasicTW:
 
     # :646-727  (checks are short-circuited in the reference; the verdict is their conjunction)
     def verify(self, t: bt.ByteTree) -> bool:
-        G, g, h, u, p = self.G, self.g, self.h, self.u, self.G.p
+        G, g, h, u = self.G, self.g, self.h, self.u
         try:
             if t.is_leaf() or len(t.children) < 5:
                 raise ar.FormatError("reply arity")
@@ -407,17 +407,17 @@ class PoSCBasicTW:
             return False
         v, h0 = self.v, h[0]
         A = ar.g_exp_prod(G, u, self.e)
-        C = ar.g_prod(G, u) * pow(ar.g_prod(G, h), -1, p) % p
+        C = ar.g_mul(G, ar.g_prod(G, u), ar.g_inv(G, ar.g_prod(G, h)))
         eprod = 1
         for x in self.e:
             eprod = eprod * x % G.q
-        D = self.B[-1] * pow(pow(h0, eprod, p), -1, p) % p
-        vA = pow(A, v, p) * self.Ap % p == pow(g, self.k_A, p) * ar.g_exp_prod(G, h, self.k_E) % p
+        D = ar.g_mul(G, self.B[-1], ar.g_inv(G, ar.g_exp(G, h0, eprod)))
+        vA = ar.g_mul(G, ar.g_exp(G, A, v), self.Ap) == ar.g_mul(G, ar.g_exp(G, g, self.k_A), ar.g_exp_prod(G, h, self.k_E))
         left = ar.g_mul(G, ar.g_exp(G, self.B, v), self.Bp)
         right = ar.g_mul(G, ar.g_exp(G, g, self.k_B), ar.g_exp(G, [h0] + self.B[:-1], self.k_E))
         vB = left == right
-        vC = pow(C, v, p) * self.Cp % p == pow(g, self.k_C, p)
-        vD = pow(D, v, p) * self.Dp % p == pow(g, self.k_D, p)
+        vC = ar.g_mul(G, ar.g_exp(G, C, v), self.Cp) == ar.g_exp(G, g, self.k_C)
+        vD = ar.g_mul(G, ar.g_exp(G, D, v), self.Dp) == ar.g_exp(G, g, self.k_D)
         self.verdicts = (vA, vB, vC, vD)
         return all(self.verdicts)
 
@@ -444,7 +444,7 @@ class CCPoSBasicW:
         self.ipe = ar.permute(self.e, ar.perm_inv(self.pi))
         self.alpha = ar.ring_random_element(G, rs, self.rbitlen)
         self.epsilon = [v % G.q for v in ar.lia_random(self.size, self.ebitlen + self.vbitlen + self.rbitlen, rs)]
-        self.Ap = pow(self.g, self.alpha, G.p) * ar.g_exp_prod(G, self.h, self.epsilon) % G.p
+        self.Ap = ar.g_mul(G, ar.g_exp(G, self.g, self.alpha), ar.g_exp_prod(G, self.h, self.epsilon))
         self.beta = _ring_random(G, _ring_shape(self.pkey), rs, self.rbitlen)
         self.Bp = ar.g_mul(G, ar.g_exp(G, self.pkey, _rneg(G, self.beta)), ar.g_exp_prod(G, self.wp, self.epsilon))
         return self.commitment_tree()
@@ -461,8 +461,8 @@ class CCPoSBasicW:
             self.Ap = ar.parse_elem(G, t.children[0])
             self.Bp = ar.parse_elem(G, t.children[1], self.pkey)
         except ar.FormatError:
-            self.Ap = 1
-            self.Bp = ar.gmap(lambda _: 1, self.pkey)
+            self.Ap = G.one
+            self.Bp = ar.gmap(lambda _: G.one, self.pkey)
         return self.commitment_tree()
 
     def set_challenge(self, v: int):
@@ -488,7 +488,7 @@ class CCPoSBasicW:
 
     # :519-584 (raisedExponent == null)
     def verify(self, t: bt.ByteTree) -> bool:
-        G, p = self.G, self.G.p
+        G = self.G
         try:
             if t.is_leaf() or len(t.children) < 3:
                 raise ar.FormatError("reply arity")
@@ -498,7 +498,7 @@ class CCPoSBasicW:
         except ar.FormatError:
             return False
         v = self.v
-        vA = pow(self.A, v, p) * self.Ap % p == pow(self.g, self.k_A, p) * ar.g_exp_prod(G, self.h, self.k_E) % p
+        vA = ar.g_mul(G, ar.g_exp(G, self.A, v), self.Ap) == ar.g_mul(G, ar.g_exp(G, self.g, self.k_A), ar.g_exp_prod(G, self.h, self.k_E))
         lhs = ar.g_mul(G, ar.g_exp(G, self.B, v), self.Bp)
         rhs = ar.g_mul(G, ar.g_exp(G, self.pkey, _rneg(G, self.k_B)), ar.g_exp_prod(G, self.wp, self.k_E))
         vB = lhs == rhs
@@ -590,7 +590,7 @@ class DistrElGamalSessionBasic:
     def commit(self, rs) -> bt.ByteTree:                             # :534-540
         G = self.G
         self.r = ar.ring_random_element(G, rs, self.rbitlen)
-        self.yp[self.j] = pow(self.g, self.r, G.p)
+        self.yp[self.j] = ar.g_exp(G, self.g, self.r)
         self.Bp[self.j] = ar.g_exp(G, self.A, self.r)
         return self.commitment_tree(self.j)
 
@@ -606,8 +606,8 @@ class DistrElGamalSessionBasic:
             self.Bp[l] = ar.parse_elem(G, t.children[1], self.A)
         except ar.FormatError:
             self.verdicts[l] = False
-            self.yp[l] = 1
-            self.Bp[l] = ar.gmap(lambda _: 1, self.A)
+            self.yp[l] = self.G.one
+            self.Bp[l] = ar.gmap(lambda _: self.G.one, self.A)
 
     def reply(self, v: int) -> bt.ByteTree:                          # :595-598
         G = self.G
@@ -625,27 +625,27 @@ class DistrElGamalSessionBasic:
         self.B[l] = ar.g_exp_prod(self.G, self.f[l], self.e)
 
     def verify(self, l, v: int) -> bool:                             # :718-727
-        G, p = self.G, self.G.p
+        G = self.G
         if not self.verdicts[l]:
             return False
         pfev = v % G.q
-        lhs1 = pow(pow(self.y[l], -1, p), self.inverse_factor * pfev % G.q, p) * self.yp[l] % p
-        ok1 = lhs1 == pow(self.g, self.k_x[l], p)
+        lhs1 = ar.g_mul(G, ar.g_exp(G, ar.g_inv(G, self.y[l]), self.inverse_factor * pfev % G.q), self.yp[l])
+        ok1 = lhs1 == ar.g_exp(G, self.g, self.k_x[l])
         lhs2 = ar.g_mul(G, ar.g_exp(G, self.B[l], pfev), self.Bp[l])
         ok2 = lhs2 == ar.g_exp(G, self.A, self.k_x[l])
         return ok1 and ok2
 
     def combine(self, correct):                                      # :642-678
-        G, p = self.G, self.G.p
+        G = self.G
         ints = modified_lagrange_coefficients(G.q, correct, self.k, self.threshold)
         exps = [i % G.q for i in ints]
-        self.combinedyp = 1
-        self.combinedBp = ar.gmap(lambda _: 1, self.A)
+        self.combinedyp = G.one
+        self.combinedBp = ar.gmap(lambda _: G.one, self.A)
         self.combinedk_x = 0
         t, l = 0, 1
         while t < self.threshold and l <= self.k:
             if correct[l]:
-                self.combinedyp = self.combinedyp * pow(self.yp[l], exps[t], p) % p
+                self.combinedyp = ar.g_mul(G, self.combinedyp, ar.g_exp(G, self.yp[l], exps[t]))
                 self.combinedBp = ar.g_mul(G, self.combinedBp, ar.g_exp(G, self.Bp[l], exps[t]))
                 self.combinedk_x = (self.combinedk_x + self.k_x[l] * exps[t]) % G.q
                 t += 1
@@ -655,9 +655,9 @@ class DistrElGamalSessionBasic:
         self.combinedB = ar.g_exp_prod(self.G, combinedf, self.e)
 
     def verify_combined(self, combinedy, v: int) -> bool:            # :693-700
-        G, p = self.G, self.G.p
+        G = self.G
         pfev = v % G.q
-        ok1 = pow(pow(combinedy, -1, p), pfev, p) * self.combinedyp % p == pow(self.g, self.combinedk_x, p)
+        ok1 = ar.g_mul(G, ar.g_exp(G, ar.g_inv(G, combinedy), pfev), self.combinedyp) == ar.g_exp(G, self.g, self.combinedk_x)
         ok2 = ar.g_mul(G, ar.g_exp(G, self.combinedB, pfev), self.combinedBp) == ar.g_exp(G, self.A, self.combinedk_x)
         return ok1 and ok2
 

@@ -618,6 +618,7 @@ class ModPGroup(PGroup):
             arr._leaves = stream
             return arr
         elif isinstance(src, np.ndarray):
+            src = np.ascontiguousarray(src)
             nat.check(lib.vmx_garr_from_bytes(self.ctx, size, _ptr(src), 1 if check_membership else 0, C.byref(h)))
         else:
             nat.check(lib.vmx_garr_fill(self.ctx, size, _be(src.value, self.elem_bytes), C.byref(h)))
