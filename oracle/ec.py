@@ -47,14 +47,23 @@ P256 = dict(
     n=0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551,
 )
 
+# SEC 2, section 2.4.1 (a = 0: exercises the general doubling formula and a modulus without the NIST shape)
+SECP256K1 = dict(
+    name="secp256k1",
+    p=2 ** 256 - 2 ** 32 - 977, a=0, b=7,
+    gx=0x79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798,
+    gy=0x483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8,
+    n=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141,
+)
+CURVES = {"P-256": P256, "secp256k1": SECP256K1}
+
 
 class ECqPGroup:
     """Same surface as oracle.arithm.ModPGroup (one, op_mul/op_inv/op_exp, encodings)."""
 
     def __init__(self, name="P-256", p=None, a=None, b=None, gx=None, gy=None, n=None):
         if p is None:
-            assert name == "P-256"
-            c = P256
+            c = CURVES[name]
             p, a, b, gx, gy, n = c["p"], c["a"], c["b"], c["gx"], c["gy"], c["n"]
         self.name, self.p, self.a, self.b, self.q = name, p, a % p, b % p, n
         self.g = ECPoint(gx, gy)

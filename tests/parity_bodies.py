@@ -10,7 +10,8 @@ from oracle import arithm as oar
 from oracle import bytetree as obt
 from oracle import protocols as opr
 from oracle.crypto import SeededRandomSource, PRGHeuristic as OPRG
-from tests.cases import EngineCase, OracleCase, col_values, group_params, seed
+from tests.cases import (EngineCase, OracleCase, col_values, elem_value, engine_elem, engine_group, group_params,
+                         oracle_group, seed)
 
 
 def _arrays(vmx, bits, n, rnd):
@@ -133,12 +134,11 @@ def edge_cases(vmx, bits):
 
 
 def ring_ops(vmx, bits, n):
-    rnd = random.Random(bits * 7 + n)
+    rnd = random.Random((bits if isinstance(bits, int) else 256) * 7 + n)
     A = vmx.arithm
-    p, q, g = group_params(bits)
-    G = A.ModPGroup(p, q, g)
+    G, OG = engine_group(vmx, bits), oracle_group(bits)
+    q = OG.q
     R = G.getPRing()
-    OG = oar.ModPGroup(p, q, g)
     a = [rnd.randrange(q) for _ in range(n)]
     b = [rnd.randrange(q) for _ in range(n)]
     Ar = R.toElementArray([A.PFieldElement(R, v) for v in a])
@@ -364,13 +364,13 @@ def decryption_parity(vmx, bits, n, k=3, threshold=2):
     oc = OracleCase(bits, n, "dec")
     ec = EngineCase(vmx, bits, n, "dec")
     OG, G = oc.G, ec.G
-    p, q = OG.p, OG.q
+    q = OG.q
     R = G.getPRing()
     # Shamir shares of the secret key oc.x: polynomial of degree threshold-1, x_l = f(l)
     ors = SeededRandomSource(seed("dec/poly"))
     coeffs = [oc.x] + [oar.ring_random_element(OG, ors, 100) for _ in range(threshold - 1)]
     xs = {l: sum(c * pow(l, i, q) for i, c in enumerate(coeffs)) % q for l in range(1, k + 1)}
-    ys = {l: pow(OG.g, xs[l], p) for l in range(1, k + 1)}
+    ys = {l: OG.op_exp(OG.g, xs[l]) for l in range(1, k + 1)}
     correct = [False] + [True] * k
     ints = opr.modified_lagrange_coefficients(q, correct, k, threshold)
     assert ints == eg.modifiedLagrangeCoefficients(R, correct, k, threshold)
@@ -388,13 +388,13 @@ def decryption_parity(vmx, bits, n, k=3, threshold=2):
     # plaintexts = v * combined  (mixnet/MixNetElGamalVerifyFiatShamirSession.java:1267-1275); the
     # modified coefficients carry the factor prodFactor, cancelled by inverseFactor in the exponent
     plain = ec.w.project(1).mul(combined)
-    o_plain = [b * pow(a, -oc.x, p) % p for a, b in zip(oc.w[0], oc.w[1])]
+    o_plain = [OG.op_mul(b, OG.op_inv(OG.op_exp(a, oc.x))) for a, b in zip(oc.w[0], oc.w[1])]
     assert col_values(plain) == o_plain
     # the proof of party j, verified by everybody (identical bytes on both sides)
     v = int.from_bytes(seed("dec/challenge"), "big")
     engines, oracles = {}, {}
     g_el = G.getg()
-    y_el = {l: A.PGroupElement(G, ys[l]) for l in ys}
+    y_el = {l: engine_elem(vmx, G, ys[l]) for l in ys}
     for j in range(1, k + 1):
         E = eg.DistrElGamalSessionBasic(j, k, threshold, 256, 100, cr.PRGHeuristic())
         E.setInstance(g_el, u, y_el, f, A.PFieldElement(R, xs[j]))
@@ -404,7 +404,7 @@ def decryption_parity(vmx, bits, n, k=3, threshold=2):
         O.f = o_f
         O.set_batch_vector(seed("dec/batch"))
         O.batch_input()
-        assert E.A.value == O.A
+        assert elem_value(E.A) == O.A
         rs = cr.PRGHeuristic()
         rs.setSeed(seed("dec/commit%d" % j))
         c = E.commit(rs).to_bytes()
@@ -422,15 +422,15 @@ def decryption_parity(vmx, bits, n, k=3, threshold=2):
     for l in range(1, k + 1):
         E1.batch(l)
         O1.batch(l)
-        assert E1.B[l].value == O1.B[l]
+        assert elem_value(E1.B[l]) == O1.B[l]
         assert E1.verify(l, v) is True and O1.verify(l, v) is True
     E1.combine(correct)
     O1.combine(correct)
     # combinedy = the joint public key y = g^x (elgamal/DistrElGamalSession.java:422-428)
-    E1.combinedy, E1.combinedf = A.PGroupElement(G, oc.pk[1]), combined
+    E1.combinedy, E1.combinedf = engine_elem(vmx, G, oc.pk[1]), combined
     E1.batchCombined()
     O1.batch_combined(o_combined)
-    assert E1.combinedB.value == O1.combinedB
+    assert elem_value(E1.combinedB) == O1.combinedB
     assert E1.verifyCombined(v) is True and O1.verify_combined(oc.pk[1], v) is True
     # a wrong reply is rejected by both
     E1.k_x[k] = E1.k_x[k].add(R.getONE())
@@ -496,3 +496,82 @@ def committed_shuffle_parity(vmx, bits, maxciph, n):
     pcc = mix.PermutationCommitment(verifier, gens)
     pcc.verify(*opub)
     assert pcc.shrink(n, bytes(bad_keep)) == vmx.eio.booleanArrayToByteTree([i < n for i in range(maxciph)]).to_bytes()
+
+
+def ec_group_ops(vmx, curve, n):
+    """ECqPGroup arrays behind the C ABI against oracle/ec.py: every array method, the unit element and
+    coincident / opposite operands (the branches of the addition law), byte trees, random points."""
+    from oracle import ec as oec
+    A = vmx.arithm
+    rnd = random.Random(n * 31 + len(curve))
+    G, OG = engine_group(vmx, curve), oracle_group(curve)
+    R = G.getPRing()
+    vals = lambda arr: [elem_value(e) for e in arr.elements()]
+    ring = lambda xs: R.toElementArray([R.toElement(x) for x in xs])
+    exps = [rnd.randrange(OG.q) for _ in range(n)]
+    for i, v in enumerate((0, 1, OG.q - 1, 2)):
+        if i < n:
+            exps[i] = v
+    E = ring(exps)
+    X = G.getg().exp(E)                                                        # fixed base
+    xs = [OG.op_exp(OG.g, e) for e in exps]
+    assert vals(X) == xs
+    ys_e = [rnd.randrange(OG.q) for _ in range(n)]
+    Y = G.getg().exp(ring(ys_e))
+    ys = vals(Y)
+    assert vals(X.mul(Y)) == [OG.op_mul(a, b) for a, b in zip(xs, ys)]
+    assert vals(X.mul(X)) == [OG.op_mul(a, a) for a in xs]                     # doubling branch
+    assert all(v.is_unit() for v in vals(X.mul(X.inv())))                      # opposite points
+    assert vals(X.inv()) == [OG.op_inv(a) for a in xs]
+    f = [rnd.randrange(OG.q) for _ in range(n)]
+    f[0] = 0
+    F = ring(f)
+    assert vals(X.exp(F)) == [OG.op_exp(a, k) for a, k in zip(xs, f)]          # variable base, per element
+    sc = R.toElement(rnd.randrange(1 << 200))
+    assert vals(X.exp(sc)) == [OG.op_exp(a, sc.value) for a in xs]             # variable base, one exponent
+    assert elem_value(X.expProd(F)) == oar.g_exp_prod(OG, xs, f)               # multi-exponentiation
+    short = [rnd.randrange(1 << 100) for _ in range(n)]
+    assert elem_value(X.expProd(ring(short))) == oar.g_exp_prod(OG, xs, short)
+    assert elem_value(X.prod()) == oar.g_prod(OG, xs)
+    pk = A.PPGroup(G, 2).product(X, Y)
+    both = pk.expProd(F)
+    assert [elem_value(c) for c in both.comps] == [oar.g_exp_prod(OG, xs, f), oar.g_exp_prod(OG, ys, f)]
+    perm = list(range(n))
+    rnd.shuffle(perm)
+    assert vals(X.permute(A.Permutation(perm))) == oar.permute(xs, perm)
+    assert vals(X.shiftPush(G.getg())) == [OG.g] + xs[:-1]
+    keep = [i % 3 != 1 for i in range(n)]
+    assert vals(X.extract(keep)) == [x for x, k in zip(xs, keep) if k]
+    assert vals(X.copyOfRange(1, n)) == xs[1:] and elem_value(X.get(n - 1)) == xs[-1]
+    assert X.equals(X.copyOfRange(0, n)) and (n < 2 or not X.equals(X.shiftPush(G.getg())))
+    cols = G.expProd([X, Y], [5, -3], 3)
+    assert vals(cols) == [OG.op_mul(OG.op_exp(a, 5), OG.op_inv(OG.op_exp(b, 3))) for a, b in zip(xs, ys)]
+    # byte trees: identical bytes, round trip, rejection of off-curve points and malformed trees
+    tb = X.toByteTree().to_bytes()
+    assert tb == OG.leaf_array_tree(xs).to_bytes()
+    assert G.toElementArray(n, vmx.eio.ByteTreeReader(tb)).equals(X)
+    assert G.getg().toByteTree().to_bytes() == OG.leaf_tree(OG.g).to_bytes()
+    assert G.getONE().toByteTree().to_bytes() == OG.leaf_tree(oec.UNIT).to_bytes()
+    good = next((v for v in xs if not v.is_unit()), OG.g)
+    bad_pt = oec.ECPoint(good.x, (good.y + 1) % OG.p)
+    for bad in (OG.leaf_array_tree([bad_pt] + xs[1:]).to_bytes(), tb[:-1] + bytes([tb[-1] ^ 1]), tb[:9] + b"\x07" + tb[10:]):
+        try:
+            G.toElementArray(n, vmx.eio.ByteTreeReader(bad))
+            assert False
+        except A.ArithmFormatException:
+            pass
+    # single elements
+    a = engine_elem(vmx, G, good)
+    assert elem_value(a.exp(sc)) == OG.op_exp(good, sc.value)
+    assert elem_value(a.mul(G.getg())) == OG.op_mul(good, OG.g)
+    assert elem_value(a.inv()) == OG.op_inv(good) and elem_value(a.mul(a.inv())).is_unit()
+    assert elem_value(G.getONE().mul(a)) == good and elem_value(G.getONE().exp(sc)).is_unit()
+    assert elem_value(G.toElement(vmx.eio.ByteTreeReader(OG.leaf_tree(good).to_bytes()))) == good
+    # random points (generators): same stream, same points, same stream position afterwards
+    prg = vmx.crypto.PRGHeuristic()
+    prg.setSeed(seed("ec/rs"))
+    ors = SeededRandomSource(seed("ec/rs"))
+    assert vals(G.randomElementArray(n, prg, 100)) == OG.random_array(n, ors, 100)
+    assert prg.getBytes(9) == ors.get_bytes(9)
+    assert vals(G.randomElementArray(n, prg, 100)) == OG.random_array(n, ors, 100)      # odd stream offset
+    assert vals(R.randomElementArray(n, prg, 100)) == oar.ring_random_array(OG, n, ors, 100)

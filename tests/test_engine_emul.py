@@ -56,3 +56,36 @@ def test_decryption_parity(engine_emul, n, k, t):
 @pytest.mark.parametrize("maxciph,n", [(12, 12), (15, 7), (9, 1)])
 def test_committed_shuffle_parity(engine_emul, maxciph, n):
     pb.committed_shuffle_parity(engine_emul, 512, maxciph, n)
+
+
+# ---- ECqPGroup (P-256): the same host logic and protocol mirror over the curve engine
+@pytest.mark.parametrize("n", [1, 2, 40])
+def test_ec_group_ops(engine_emul, n):
+    pb.ec_group_ops(engine_emul, "P-256", n)
+
+
+def test_ec_ring_ops(engine_emul):
+    pb.ring_ops(engine_emul, "P-256", 33)
+
+
+@pytest.mark.parametrize("n", [1, 9])
+def test_ec_transcript_parity(engine_emul, n):
+    pb.transcript_parity(engine_emul, "P-256", n)
+
+
+def test_ec_posc_ccpos_parity(engine_emul):
+    pb.posc_parity(engine_emul, "P-256", 7)
+    pb.ccpos_parity(engine_emul, "P-256", 7)
+
+
+def test_ec_decryption_parity(engine_emul):
+    pb.decryption_parity(engine_emul, "P-256", 6, 3, 2)
+
+
+def test_ec_committed_shuffle_parity(engine_emul):
+    pb.committed_shuffle_parity(engine_emul, "P-256", 9, 5)
+
+
+def test_ec_other_curve(engine_emul):
+    """secp256k1: a = 0 (general doubling formula) and the generic Montgomery reduction."""
+    pb.ec_group_ops(engine_emul, "secp256k1", 5)

@@ -98,3 +98,37 @@ def test_launches_are_counted(engine_cuda):
     e = G.getPRing().randomElementArray(100, rs, 100)
     G.getg().exp(e).free()
     assert G.launch_count() > before and G.modmul_count() > 0
+
+
+# ---- ECqPGroup (P-256, BASELINE.json config 5)
+@pytest.mark.parametrize("curve,n", [("P-256", 1), ("P-256", 40), ("P-256", 3000), ("secp256k1", 33)])
+def test_ec_group_ops(engine_cuda, curve, n):
+    """n = 3000 crosses the block size of the batched inversion (512 points) and its recursion."""
+    pb.ec_group_ops(engine_cuda, curve, n)
+
+
+def test_ec_ring_ops(engine_cuda):
+    pb.ring_ops(engine_cuda, "P-256", 1100)
+
+
+@pytest.mark.parametrize("n", [1, 100])
+def test_ec_transcript_parity(engine_cuda, n):
+    pb.transcript_parity(engine_cuda, "P-256", n)
+
+
+def test_ec_posc_ccpos_parity(engine_cuda):
+    pb.posc_parity(engine_cuda, "P-256", 60)
+    pb.ccpos_parity(engine_cuda, "P-256", 60)
+
+
+def test_ec_decryption_parity(engine_cuda):
+    pb.decryption_parity(engine_cuda, "P-256", 40, 3, 2)
+
+
+def test_ec_committed_shuffle_parity(engine_cuda):
+    pb.committed_shuffle_parity(engine_cuda, "P-256", 60, 40)
+
+
+def test_ec_accept_reject_at_scale(engine_cuda):
+    """N = 300,000 points: tables of 16-bit windows, Pippenger c = 16, several levels of the batched inversion."""
+    pb.accept_reject_properties(engine_cuda, "P-256", 300000)

@@ -37,6 +37,7 @@ SIGNATURES = {
     "vmx_last_error": (C.c_char_p, []),
     "vmx_version": (C.c_int, []),
     "vmx_ctx_create_modp": (C.c_int, [_U8, _U8, _U8, _SZ, C.c_int, _PP]),
+    "vmx_ctx_create_ecq": (C.c_int, [_U8, _U8, _U8, _U8, _U8, _U8, _SZ, C.c_int, _PP]),
     "vmx_ctx_destroy": (None, [_P]),
     "vmx_ctx_elem_bytes": (_SZ, [_P]),
     "vmx_ctx_ring_bytes": (_SZ, [_P]),
@@ -46,6 +47,8 @@ SIGNATURES = {
     "vmx_garr_from_bytes": (C.c_int, [_P, _SZ, _P, C.c_int, _PP]),
     "vmx_garr_from_raw": (C.c_int, [_P, _SZ, _P, _SZ, C.c_uint, _PP]),
     "vmx_garr_prg_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, _SZ, C.c_uint, _PP]),
+    "vmx_ctx_prg_consumed": (C.c_uint64, [_P]),
+    "vmx_garr_from_candidates": (C.c_int, [_P, _SZ, _P, _SZ, C.c_uint, _SZ, _PP, C.POINTER(C.c_size_t)]),
     "vmx_rarr_prg_raw_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, _SZ, C.c_uint, _PP]),
     "vmx_prg_bytes_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, _P]),
     "vmx_garr_to_bytes": (C.c_int, [_P, _P]),
@@ -61,6 +64,7 @@ SIGNATURES = {
     "vmx_elem_inv": (C.c_int, [_P, _U8, _P]),
     "vmx_fixed_precompute": (C.c_int, [_P, _U8, _SZ]),
     "vmx_ctx_row_bytes": (_SZ, [_P]),
+    "vmx_ctx_ring_row_bytes": (_SZ, [_P]),
     "vmx_garr_pack_rows": (C.c_int, [_P, _P, _SZ, _P]),
     "vmx_garr_unpack_rows": (C.c_int, [_P, _SZ, _P, _P, _SZ, _PP]),
     "vmx_rarr_pack_rows": (C.c_int, [_P, _P, _SZ, _P]),

@@ -158,6 +158,8 @@ class ByteTreeDeviceArray(ByteTreeBasic):
         self.arr = arr
         self._n = arr.size()
         self._w = arr.getPGroup().elem_bytes if hasattr(arr, "getPGroup") else arr.ring.byte_len
+        # curve groups: node(node(x leaves), node(y leaves)); the engine writes the two inner nodes
+        self._curve = hasattr(arr, "getPGroup") and getattr(arr.getPGroup(), "is_curve", False)
 
     def _stream(self) -> np.ndarray:
         if hasattr(self.arr, "leaves"):
@@ -169,14 +171,22 @@ class ByteTreeDeviceArray(ByteTreeBasic):
         return buf.reshape(-1)
 
     def update(self, digest) -> None:
+        if self._curve:
+            digest.update(struct.pack(">BI", 0, 2))
+            digest.update(self.arr.leaves().data)
+            return
         digest.update(struct.pack(">BI", 0, self._n))
         if self._n:
             digest.update(self._stream().data)
 
     def to_bytes(self) -> bytes:
+        if self._curve:
+            return struct.pack(">BI", 0, 2) + self.arr.leaves().tobytes()
         return struct.pack(">BI", 0, self._n) + (self._stream().tobytes() if self._n else b"")
 
     def total_bytes(self) -> int:
+        if self._curve:
+            return 5 + self.arr.getPGroup()._leaves_bytes(self._n)
         return 5 + self._n * (5 + self._w)
 
 
@@ -536,6 +546,15 @@ class ModPGroup(PGroup):
         """Wrap a fresh engine handle (overridden by the sharded group of parallel.py)."""
         return PGroupElementArray(self, h)
 
+    is_curve = False
+
+    def _leaves_bytes(self, n: int) -> int:
+        """Size of the buffer vmx_garr_to_leaves / vmx_garr_from_leaves move for n elements."""
+        return n * (5 + self.elem_bytes)
+
+    def _elem_tree(self, value: int) -> ByteTreeBasic:
+        return ByteTreeLeaf(int_to_bytes(value, self.elem_bytes))
+
     def _combine_partials(self, parts: List["PGroupElement"]) -> List["PGroupElement"]:
         """expProd / prod results of this process; the sharded group multiplies the ranks' partial
         products here (parallel.py)."""
@@ -660,6 +679,147 @@ class ModPGroup(PGroup):
         return hash((self.p, self.g))
 
 
+
+class ECqPGroup(ModPGroup):
+    """Prime-order elliptic-curve group y^2 = x^3 + ax + b over F_p (com.verificatum.arithm.ECqPGroup;
+    the reference's default groups are NIST curves: demo/mixnet/benchmarks/bench_config:33-50, P-256).
+
+    A single element is held as the integer of its wire form x || y (two fixed-width two's-complement
+    coordinates, the unit element (-1, -1)), so that PGroupElement and the array classes above serve both
+    kinds of group; only the byte-tree framing differs ([VCR-mem]):
+    element = node(leaf(x), leaf(y)), array = node(node(x_0..), node(y_0..))."""
+
+    is_curve = True
+    CURVES = {
+        "P-256": dict(
+            p=0xFFFFFFFF00000001000000000000000000000000FFFFFFFFFFFFFFFFFFFFFFFF,
+            a=0xFFFFFFFF00000001000000000000000000000000FFFFFFFFFFFFFFFFFFFFFFFC,
+            b=0x5AC635D8AA3A93E7B3EBBD55769886BC651D06B0CC53B0F63BCE3C3E27D2604B,
+            gx=0x6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296,
+            gy=0x4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5,
+            n=0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551),
+        "secp256k1": dict(
+            p=2 ** 256 - 2 ** 32 - 977, a=0, b=7,
+            gx=0x79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798,
+            gy=0x483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8,
+            n=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141),
+    }
+
+    def __init__(self, name: str = "P-256", device: int = 0, **params):
+        lib = nat.load()
+        c = dict(self.CURVES[name]) if name in self.CURVES else {}
+        c.update(params)
+        self.name = name
+        self.p, self.a, self.b, self.q = c["p"], c["a"] % c["p"], c["b"] % c["p"], c["n"]
+        self.gx, self.gy = c["gx"], c["gy"]
+        ctx = C.c_void_p()
+        nat.check(lib.vmx_ctx_create_ecq(_be(self.p, 32), _be(self.a, 32), _be(self.b, 32), _be(self.gx, 32),
+                                         _be(self.gy, 32), _be(self.q, 32), 32, device, C.byref(ctx)))
+        self.ctx = ctx
+        self._lib = lib
+        self.elem_bytes = int(lib.vmx_ctx_elem_bytes(ctx))
+        self.coord_bytes = self.elem_bytes // 2
+        self.ring_bytes = int(lib.vmx_ctx_ring_bytes(ctx))
+        self.pRing = PField(self)
+        self.g = self._pack(self.gx, self.gy)
+        self.one = (1 << (8 * self.elem_bytes)) - 1  # (-1, -1)
+
+    # -- wire form of one point
+    def _pack(self, x: int, y: int) -> int:
+        return int.from_bytes(int_to_bytes(x, self.coord_bytes) + int_to_bytes(y, self.coord_bytes), "big")
+
+    def _unpack(self, value: int):
+        raw = _be(value, self.elem_bytes)
+        cb = self.coord_bytes
+        return int.from_bytes(raw[:cb], "big", signed=True), int.from_bytes(raw[cb:], "big", signed=True)
+
+    def _leaves_bytes(self, n: int) -> int:
+        return 2 * (5 + n * (5 + self.coord_bytes))
+
+    def _elem_tree(self, value: int) -> ByteTreeBasic:
+        raw = _be(value, self.elem_bytes)
+        cb = self.coord_bytes
+        return ByteTreeContainer(ByteTreeLeaf(raw[:cb]), ByteTreeLeaf(raw[cb:]))
+
+    def getONE(self) -> "PGroupElement":
+        return PGroupElement(self, self.one)
+
+    def _on_curve(self, x: int, y: int) -> bool:
+        return 0 <= x < self.p and 0 <= y < self.p and (y * y - (x * x * x + self.a * x + self.b)) % self.p == 0
+
+    def toElement(self, x) -> "PGroupElement":
+        cb = self.coord_bytes
+        if isinstance(x, ByteTreeReader):
+            if x.isLeaf() or x.getRemaining() != 2:
+                raise ArithmFormatException(nat.VMX_EFORMAT, "curve point of wrong arity")
+            cx, cy = x.getNextChild(), x.getNextChild()
+            if not cx.isLeaf() or not cy.isLeaf() or cx.getRemaining() != cb or cy.getRemaining() != cb:
+                raise ArithmFormatException(nat.VMX_EFORMAT, "coordinate of wrong length")
+            px, py = int.from_bytes(cx.read(), "big", signed=True), int.from_bytes(cy.read(), "big", signed=True)
+        else:
+            px, py = x
+        if (px, py) == (-1, -1):
+            return self.getONE()
+        # a single point is validated on the host, as VCR does for one ECqPGroupElement (a handful of
+        # field operations on host integers; arrays are checked on the device)
+        if not self._on_curve(px, py):
+            raise ArithmFormatException(nat.VMX_EFORMAT, "not a point of the curve")
+        return PGroupElement(self, self._pack(px, py))
+
+    def toElementArray(self, *args, check_membership: Optional[bool] = None) -> "PGroupElementArray":
+        lib = self._lib
+        h = C.c_void_p()
+        if len(args) == 2 and isinstance(args[1], ByteTreeReader):
+            size, src = args
+            try:
+                stream = src.point_array_stream(size, self.coord_bytes)
+            except EIOException as e:
+                raise ArithmFormatException(nat.VMX_EFORMAT, str(e))
+            nat.check(lib.vmx_garr_from_leaves(self.ctx, size, _ptr(stream), 1, C.byref(h)))
+            arr = self._garr(h, size)
+            arr._leaves = stream
+            return arr
+        return super().toElementArray(*args, check_membership=check_membership)
+
+    def randomElementArray(self, size: int, randomSource, statDist: int) -> "PGroupElementArray":
+        """Per point: draw ceil((|p|+statDist)/8) bytes, reduce mod p to x, accept if x^3+ax+b is a square and
+        take the smaller root, else draw again ([VCR-mem]; distr/IndependentGeneratorsRO.java:129).  The
+        candidates are tested in parallel on the device and compacted in stream order."""
+        bits = self.p.bit_length() + statDist
+        width = (bits + 7) // 8
+        h = C.c_void_p()
+        off = _sha256_prg_offset(randomSource)
+        if off is not None:
+            nat.check(self._lib.vmx_garr_prg_sha256(self.ctx, randomSource.seed, len(randomSource.seed), off, size,
+                                                    width, bits, C.byref(h)))
+            _advance_prg(randomSource, off + int(self._lib.vmx_ctx_prg_consumed(self.ctx)))
+            return self._garr(h, size)
+        # any other source: its bytes are consumed candidate by candidate, so ask for exactly one candidate
+        # per missing point and round (expected two rounds per point on average ... log n rounds in total)
+        parts, have = [], 0
+        while have < size:
+            m = size - have
+            raw = np.frombuffer(randomSource.getBytes(m * width), dtype=np.uint8)
+            used = C.c_size_t()
+            hh = C.c_void_p()
+            nat.check(self._lib.vmx_garr_from_candidates(self.ctx, m, _ptr(raw), width, bits, m, C.byref(hh),
+                                                         C.byref(used)))
+            part = PGroupElementArray(self, hh)
+            have += part.size()
+            parts.append(part)
+        pts = []
+        for part in parts:
+            pts += part.elements()
+            part.free()
+        return self.toElementArray(pts)
+
+    def __eq__(self, o):
+        return isinstance(o, ECqPGroup) and (o.p, o.a, o.b, o.g, o.q) == (self.p, self.a, self.b, self.g, self.q)
+
+    def __hash__(self):
+        return hash((self.p, self.b, self.g))
+
+
 class PGroupElement:
     """A single group element: host value; exponentiations go through the engine."""
 
@@ -733,7 +893,7 @@ class PGroupElement:
         return hash(self.value)
 
     def toByteTree(self) -> ByteTreeBasic:
-        return ByteTreeLeaf(int_to_bytes(self.value, self.group.elem_bytes))
+        return self.group._elem_tree(self.value)
 
 
 class PGroupElementArray:
@@ -836,13 +996,21 @@ class PGroupElementArray:
         if self._leaves is None:
             if self.h is None:
                 raise ArithmError("byte tree of a freed array")
-            buf = np.empty(self.size() * (5 + self.group.elem_bytes), dtype=np.uint8)
+            buf = np.empty(self.group._leaves_bytes(self.size()), dtype=np.uint8)
             nat.check(self._lib.vmx_garr_to_leaves(self.h, _ptr(buf)))
             self._leaves = buf
         return self._leaves
 
     def to_matrix(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         n, w = self.size(), self.group.elem_bytes
+        if self.group.is_curve:  # x || y per point
+            m = np.empty((n, w), dtype=np.uint8)
+            if n:
+                nat.check(self._lib.vmx_garr_to_bytes(self.h, _ptr(m)))
+            if out is not None:
+                out[:] = m
+                return out
+            return m
         m = self.leaves().reshape(n, 5 + w)[:, 5:]
         if out is not None:
             out[:] = m

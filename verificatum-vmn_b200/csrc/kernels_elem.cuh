@@ -92,7 +92,9 @@ VMX_KERNEL(N) k_to_bytes(const uint32_t* __restrict__ in, size_t cap, size_t n, 
 }
 
 // raw unsigned integers of `width` bytes (big-endian), masked to `bitlen` bits (0 = all),
-// reduced mod q.  Handles width*8 up to 2*32N bits.
+// reduced mod q.  The integer is read as chunks of 32N bits, x = sum_k c_k 2^(32N k), and folded
+// from the top: acc <- acc * 2^(32N) + c_k (mod q).  Up to 4 chunks (an n_e + n_v + n_r = 612-bit
+// integer is 3 chunks over the 256-bit order of a curve group, hvzk/PoSBasicTW.java:470-474).
 template <int N>
 VMX_KERNEL(N) k_ring_from_raw(const uint8_t* __restrict__ raw, size_t n, int width, int bitlen,
                               uint32_t* __restrict__ out, size_t cap, const uint32_t* __restrict__ r2,
@@ -115,36 +117,42 @@ VMX_KERNEL(N) k_ring_from_raw(const uint8_t* __restrict__ raw, size_t n, int wid
     }
     return v;
   };
-  uint32_t lo[N];
+  uint32_t acc[N];
+  if (!need_reduce) {
 #pragma unroll
-  for (int j = 0; j < N; j++) lo[j] = word(j);
-  if (need_reduce) {
-    // x = hi * 2^(32N) + lo ;  x mod q = hi*R mod q + lo mod q
-    const GlobalLoader R2(r2, 4, 0);
-    mont_mul<N>(lo, R2, M);          // lo * R
-    mont_mul<N>(lo, OneLoader{}, M); // lo mod q
-    if (8 * width > 32 * N) {
-      uint32_t hi[N];
-#pragma unroll
-      for (int j = 0; j < N; j++) hi[j] = word(N + j);
-      mont_mul<N>(hi, R2, M);        // hi * R mod q
-      // lo = lo + hi mod q
-      uint32_t c;
-      add_cc(lo[0], lo[0], hi[0]);
-#pragma unroll
-      for (int j = 1; j < N; j++) addc_cc(lo[j], lo[j], hi[j]);
-      addc(c, 0, 0);
-      uint32_t d[N], brw;
-      sub_cc(d[0], lo[0], M.n[0]);
-#pragma unroll
-      for (int j = 1; j < N; j++) subc_cc(d[j], lo[j], M.n[j]);
-      subc(brw, c, 0);
-      const bool keep = (brw != 0);
-#pragma unroll
-      for (int j = 0; j < N; j++) lo[j] = keep ? lo[j] : d[j];
-    }
+    for (int j = 0; j < N; j++) acc[j] = word(j);
+    store_elem<N>(acc, out, cap, i);
+    return;
   }
-  store_elem<N>(lo, out, cap, i);
+  const GlobalLoader R2(r2, 4, 0);
+  const int nchunks = (8 * width + 32 * N - 1) / (32 * N);
+  for (int c = nchunks - 1; c >= 0; c--) {
+    uint32_t ch[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) ch[j] = word(c * N + j);
+    mont_mul<N>(ch, R2, M);          // c_k * R
+    mont_mul<N>(ch, OneLoader{}, M); // c_k mod q
+    if (c == nchunks - 1) {
+#pragma unroll
+      for (int j = 0; j < N; j++) acc[j] = ch[j];
+      continue;
+    }
+    mont_mul<N>(acc, R2, M);         // acc * 2^(32N) mod q
+    uint32_t cy;
+    add_cc(acc[0], acc[0], ch[0]);
+#pragma unroll
+    for (int j = 1; j < N; j++) addc_cc(acc[j], acc[j], ch[j]);
+    addc(cy, 0, 0);
+    uint32_t d[N], brw;
+    sub_cc(d[0], acc[0], M.n[0]);
+#pragma unroll
+    for (int j = 1; j < N; j++) subc_cc(d[j], acc[j], M.n[j]);
+    subc(brw, cy, 0);
+    const bool keep = (brw != 0);
+#pragma unroll
+    for (int j = 0; j < N; j++) acc[j] = keep ? acc[j] : d[j];
+  }
+  store_elem<N>(acc, out, cap, i);
 }
 
 // ------------------------------------------------------------------ out[i] = a[i] * b[i]

@@ -19,6 +19,7 @@
 #pragma once
 #include "cuda_compat.cuh"
 #include "ptx_arith.cuh"
+#include "fp256.cuh"
 
 namespace vmx {
 
@@ -144,6 +145,18 @@ VMX_DEV void unpack_pair(uint32_t& lo, uint32_t& hi, uint64_t v) { lo = (uint32_
 // word pair (b[i], b[i+1]) for even i).  Result fully reduced to [0, n).
 template <int N, typename Loader>
 VMX_DEV void mont_mul(uint32_t (&a)[N], Loader ld2, const MontParams<N>& M) {
+  if constexpr (N == 8) {  // 256-bit residues (curve groups): separated product + reduction, fp256.cuh
+    Fp256 F;
+    uint32_t b[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) { const Word2 w = ld2(i); b[i] = w.x; b[i + 1] = w.y; }
+#pragma unroll
+    for (int i = 0; i < 8; i++) F.n[i] = M.n[i];
+    F.n0inv = M.n0inv;
+    F.solinas = 0;
+    fp_mul(a, a, b, F);
+    return;
+  } else {
   uint64_t T[N / 2 + 1];
 #pragma unroll
   for (int k = 0; k < N / 2 + 1; k++) T[k] = 0;
@@ -164,6 +177,7 @@ VMX_DEV void mont_mul(uint32_t (&a)[N], Loader ld2, const MontParams<N>& M) {
 #pragma unroll
   for (int k = 0; k < N / 2 + 1; k++) unpack_pair(t[2 * k], t[2 * k + 1], T[k]);
   mont_final_sub<N>(a, t, M);
+  }
 }
 
 }  // namespace vmx

@@ -30,6 +30,7 @@ void set_error(const char* fmt, ...) {
 
 #define VMX_DISPATCH(nl, ...)                                                  \
   switch (nl) {                                                                \
+    case 8: { constexpr int N = 8; __VA_ARGS__; } break;                       \
     case 16: { constexpr int N = 16; __VA_ARGS__; } break;                     \
     case 32: { constexpr int N = 32; __VA_ARGS__; } break;                     \
     case 64: { constexpr int N = 64; __VA_ARGS__; } break;                     \
@@ -155,6 +156,8 @@ struct DevBuf {  // stream-ordered temporary
 struct ElemBuf : DevBuf {
   size_t cap = 0;
   int alloc_elems(vmx_ctx* ctx, size_t n) { cap = cap_for(n); return alloc(ctx, cap * ctx->nl * 4); }
+  int alloc_limbs(vmx_ctx* ctx, size_t n, int limbs) { cap = cap_for(n); return alloc(ctx, cap * (size_t)limbs * 4); }
+  int alloc_gelems(vmx_ctx* ctx, size_t n) { return alloc_limbs(ctx, n, ctx->gl); }  // group elements
   uint32_t* d() const { return as<uint32_t>(); }
 };
 
@@ -163,10 +166,10 @@ static int new_garr(vmx_ctx* c, size_t n, vmx_garr** out) {
   auto* a = new (std::nothrow) vmx_garr{c, n, cap_for(n), nullptr};
   if (!a) return VMX_ENOMEM;
   void* p = nullptr;
-  if (cudaMallocAsync(&p, a->cap * c->nl * 4, c->stream) != cudaSuccess) {
+  if (cudaMallocAsync(&p, a->cap * c->gl * 4, c->stream) != cudaSuccess) {
     (void)cudaGetLastError();
     delete a;
-    set_error("device allocation of %zu bytes failed", a->cap * c->nl * 4);
+    set_error("device allocation of %zu bytes failed", a->cap * c->gl * 4);
     return VMX_ENOMEM;
   }
   a->d = (uint32_t*)p;
@@ -303,7 +306,10 @@ static int upload_consts(vmx_ctx* c, Modulus& Mod) {
 
 // upload one element given as big-endian bytes into a fresh 1-element (cap 8) temporary,
 // group: to Montgomery form with range check; ring: canonical with range check.
+static int ec_upload_one(vmx_ctx* c, const uint8_t* be, ElemBuf& buf);
+static int ec_download_one(vmx_ctx* c, const uint32_t* d, size_t cap, size_t idx, uint8_t* out_be);
 static int upload_one(vmx_ctx* c, const uint8_t* be, bool group, ElemBuf& buf) {
+  if (group && c->kind == 1) return ec_upload_one(c, be, buf);
   const size_t eb = group ? c->eb : c->rb;
   DevBuf raw;
   VMX_TRY(raw.alloc(c, eb));
@@ -321,6 +327,7 @@ static int upload_one(vmx_ctx* c, const uint8_t* be, bool group, ElemBuf& buf) {
 
 // download element `idx` of a limb-major array as big-endian bytes (synchronises)
 static int download_one(vmx_ctx* c, const uint32_t* d, size_t cap, size_t idx, bool group, uint8_t* out_be) {
+  if (group && c->kind == 1) return ec_download_one(c, d, cap, idx, out_be);
   const size_t eb = group ? c->eb : c->rb;
   DevBuf raw;
   VMX_TRY(raw.alloc(c, eb));
@@ -411,21 +418,28 @@ static int build_table(vmx_ctx* c, const uint32_t* base, size_t bcap, int w, Fix
 }
 
 // find or build the table for `base_be`, sized for n exponents
+static int ec_choose_fixed_window(const vmx_ctx* c, size_t n);
+static double ec_fixed_cost(int w, size_t n, int ebits);
+static int ec_build_table(vmx_ctx* c, const uint32_t* base, size_t bcap, int w, FixedTable& T);
 static int get_table(vmx_ctx* c, const uint8_t* base_be, size_t n, FixedTable* out) {
   const std::string key(reinterpret_cast<const char*>(base_be), c->eb);
   const int ebits = c->Q.bits;
-  const int wbest = choose_fixed_window(c, n, ebits);
+  const bool ec = c->kind == 1;
+  const int wbest = ec ? ec_choose_fixed_window(c, n) : choose_fixed_window(c, n, ebits);
   std::lock_guard<std::mutex> lk(c->mu);
   auto it = c->tables.find(key);
   if (it != c->tables.end()) {
-    if (fixed_cost(it->second.w, n, ebits) <= 1.3 * fixed_cost(wbest, n, ebits)) { *out = it->second; return VMX_OK; }
+    const double have = ec ? ec_fixed_cost(it->second.w, n, ebits) : fixed_cost(it->second.w, n, ebits);
+    const double want = ec ? ec_fixed_cost(wbest, n, ebits) : fixed_cost(wbest, n, ebits);
+    if (have <= 1.3 * want) { *out = it->second; return VMX_OK; }
     cudaFreeAsync(it->second.d, c->stream);
     c->tables.erase(it);
   }
   ElemBuf base;
   VMX_TRY(upload_one(c, base_be, true, base));
   FixedTable T;
-  VMX_DISPATCH(c->nl, VMX_TRY(build_table<N>(c, base.d(), base.cap, wbest, T)));
+  if (ec) VMX_TRY(ec_build_table(c, base.d(), base.cap, wbest, T));
+  else VMX_DISPATCH(c->nl, VMX_TRY(build_table<N>(c, base.d(), base.cap, wbest, T)));
   c->tables[key] = T;
   *out = T;
   return VMX_OK;
@@ -701,9 +715,9 @@ static int ring_scan(vmx_ctx* c, const uint32_t* eM, size_t ecap, const uint32_t
 
 // generic plane-wise copy out[dst(i)] = in[src(i)]
 static int gather(vmx_ctx* c, const uint32_t* in, size_t icap, uint32_t* out, size_t ocap, size_t n,
-                  const uint32_t* src_idx, const uint32_t* dst_idx, long long src_off, long long dst_off) {
+                  const uint32_t* src_idx, const uint32_t* dst_idx, long long src_off, long long dst_off, int limbs = 0) {
   if (!n) return VMX_OK;
-  const int planes = c->nl / 4;
+  const int planes = (limbs ? limbs : c->nl) / 4;
   VMX_LAUNCH(c, k_gather, nblocks(n * planes, 256), 256, 0, reinterpret_cast<const uint4*>(in), icap,
              reinterpret_cast<uint4*>(out), ocap, n, planes, src_idx, dst_idx, src_off, dst_off, 0, (size_t)0);
   VMX_CHECK_LAUNCH();
@@ -714,6 +728,28 @@ static int same_ctx(const void* a, const void* b) {
   if (a != b) { set_error("operands belong to different contexts"); return VMX_EARG; }
   return VMX_OK;
 }
+
+// stream bytes [offset, offset + nbytes) of PRGHeuristic(SHA-256); *data points at the first one
+static int prg_bytes_dev(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t nbytes, DevBuf& buf,
+                         const uint8_t** data) {
+  if (!seed || seedlen < 32 || seedlen > 48) { set_error("PRG seed must be 32..48 bytes"); return VMX_EARG; }
+  const size_t first = offset / 32, shift = offset % 32;
+  const size_t nblk = (shift + nbytes + 31) / 32;
+  if (first + nblk >= 0xffffffffull) { set_error("PRG stream too long"); return VMX_ESIZE; }
+  PrgSeed s;
+  std::memset(&s, 0, sizeof s);
+  std::memcpy(s.bytes, seed, seedlen);
+  s.len = (int)seedlen;
+  VMX_TRY(buf.alloc(c, nblk * 32));
+  if (nblk) {
+    VMX_LAUNCH(c, k_prg_bytes, nblocks(nblk, 128), 128, 0, s, first, nblk, buf.as<uint8_t>());
+    VMX_CHECK_LAUNCH();
+  }
+  *data = buf.as<uint8_t>() + shift;
+  return VMX_OK;
+}
+
+#include "vmx_ec.inl"
 
 }  // namespace vmx
 
@@ -744,6 +780,7 @@ int vmx_ctx_create_modp(const uint8_t* p_be, const uint8_t* q_be, const uint8_t*
   if (!be_to_limbs(p_be, nbytes, tmp, kMaxLimbs)) { set_error("modulus larger than 3072 bits"); return VMX_EARG; }
   const int pbits = limbs_bits(tmp, kMaxLimbs);
   c->nl = pbits <= 512 ? 16 : pbits <= 1024 ? 32 : pbits <= 2048 ? 64 : 96;
+  c->gl = c->nl;
   if (pbits < 64 || !(tmp[0] & 1)) { set_error("modulus must be odd and >= 64 bits"); return VMX_EARG; }
   std::memcpy(c->P.n, tmp, sizeof tmp);
   c->P.bits = pbits;
@@ -795,6 +832,120 @@ int vmx_ctx_create_modp(const uint8_t* p_be, const uint8_t* q_be, const uint8_t*
   return VMX_OK;
 }
 
+// ECqPGroup over y^2 = x^3 + a x + b mod p with a base point of prime order n (256-bit p and n):
+// replaces arithm.ECqPGroup construction (the reference's default groups are NIST curves,
+// demo/mixnet/benchmarks/bench_config:33-50).  All values big-endian unsigned, `nbytes` each.
+int vmx_ctx_create_ecq(const uint8_t* p_be, const uint8_t* a_be, const uint8_t* b_be, const uint8_t* gx_be,
+                       const uint8_t* gy_be, const uint8_t* n_be, size_t nbytes, int device, vmx_ctx** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!p_be || !a_be || !b_be || !gx_be || !gy_be || !n_be || !nbytes) { set_error("null curve parameter"); return VMX_EARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    (void)cudaGetLastError();
+    set_error("no CUDA device: this engine has no CPU path");
+    return VMX_ECUDA;
+  }
+  if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return VMX_EARG; }
+  std::unique_ptr<vmx_ctx> c(new vmx_ctx);
+  c->device = device;
+  c->kind = 1;
+  c->nl = 8;
+  c->gl = 16;
+  uint32_t p[8], a[8], b[8], q[8];
+  if (!be_to_limbs(p_be, nbytes, p, 8) || !be_to_limbs(a_be, nbytes, a, 8) || !be_to_limbs(b_be, nbytes, b, 8) ||
+      !be_to_limbs(n_be, nbytes, q, 8)) {
+    set_error("curve parameters must fit 256 bits");
+    return VMX_EARG;
+  }
+  const int pbits = limbs_bits(p, 8), qbits = limbs_bits(q, 8);
+  if (pbits <= 224 || !(p[0] & 1) || qbits <= 192 || !(q[0] & 1) || limbs_cmp(a, p, 8) >= 0 || limbs_cmp(b, p, 8) >= 0) {
+    set_error("unsupported curve: p and n must be odd, p of 225..256 bits, a, b < p");
+    return VMX_EARG;
+  }
+  std::memset(c->P.n, 0, sizeof c->P.n);
+  std::memset(c->Q.n, 0, sizeof c->Q.n);
+  std::memcpy(c->P.n, p, sizeof p);
+  std::memcpy(c->Q.n, q, sizeof q);
+  c->P.bits = pbits;
+  c->Q.bits = qbits;
+  c->P.n0inv = neg_inv32(p[0]);
+  c->Q.n0inv = neg_inv32(q[0]);
+  c->cb = (size_t)pbits / 8 + 1;
+  c->eb = 2 * c->cb;
+  c->rb = (size_t)qbits / 8 + 1;
+  // constants of the coordinate field
+  vmx::EcCurve& E = c->ecc;
+  std::memset(&E, 0, sizeof E);
+  std::memcpy(E.F.n, p, sizeof p);
+  E.F.n0inv = c->P.n0inv;
+  static const uint32_t p256[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0, 1, 0xffffffffu};
+  E.F.solinas = limbs_cmp(p, p256, 8) == 0 ? 1u : 0u;
+  auto to_mont = [&](uint32_t* r, const uint32_t* x) {  // r = x * 2^256 mod p
+    std::memcpy(r, x, 32);
+    for (int s = 0; s < 256; s++) {
+      uint32_t cy = 0;
+      for (int j = 0; j < 8; j++) { const uint32_t nc = r[j] >> 31; r[j] = (r[j] << 1) | cy; cy = nc; }
+      if (cy || limbs_cmp(r, p, 8) >= 0) limbs_sub(r, p, 8);
+    }
+  };
+  uint32_t one[8] = {1};
+  to_mont(E.a, a);
+  to_mont(E.b, b);
+  to_mont(E.one, one);
+  to_mont(E.r2, E.one);
+  std::memcpy(E.pm2, p, sizeof p);
+  { uint32_t two[8] = {2}; limbs_sub(E.pm2, two, 8); }
+  c->ec_sqrt_ok = (p[0] & 3) == 3;
+  if (c->ec_sqrt_ok) {  // (p + 1) / 4
+    uint32_t t[9];
+    std::memcpy(t, p, sizeof p);
+    t[8] = 0;
+    for (int j = 0; j < 9; j++) { if (++t[j] != 0) break; }
+    for (int j = 0; j < 8; j++) E.sqe[j] = (t[j] >> 2) | (t[j + 1] << 30);
+  }
+  { uint32_t t[8], three[8] = {3}; std::memcpy(t, p, sizeof p); limbs_sub(t, three, 8); E.a_minus3 = limbs_cmp(a, t, 8) == 0 ? 1u : 0u; }
+  VMX_CU(cudaSetDevice(device));
+#ifndef VMX_HOST_EMUL
+  {
+    cudaDeviceProp prop;
+    VMX_CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+      set_error("device %d is sm_%d%d; this engine is built for sm_100a only", device, prop.major, prop.minor);
+      return VMX_ECUDA;
+    }
+    cudaMemPool_t pool;
+    VMX_CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = ~0ull;
+    VMX_CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  }
+#endif
+  VMX_CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  void* ptr = nullptr;
+  VMX_CU(cudaMallocAsync(&ptr, sizeof(int) * 4, c->stream));
+  c->d_flag = (int*)ptr;
+  VMX_CU(cudaMallocHost(&ptr, sizeof(int) * 4));
+  c->h_flag = (int*)ptr;
+  VMX_TRY(upload_consts(c.get(), c->P));
+  VMX_TRY(upload_consts(c.get(), c->Q));
+  {  // the base point must be on the curve
+    std::vector<uint8_t> g(2 * c->cb, 0);
+    if (nbytes > c->cb) { set_error("coordinate width"); return VMX_EARG; }
+    std::memcpy(g.data() + (c->cb - nbytes), gx_be, nbytes);
+    std::memcpy(g.data() + c->cb + (c->cb - nbytes), gy_be, nbytes);
+    ElemBuf gb;
+    const int st = ec_upload_one(c.get(), g.data(), gb);
+    if (st != VMX_OK) {
+      vmx_ctx_destroy(c.release());
+      set_error("the base point is not on the curve");
+      return st == VMX_EFORMAT ? VMX_EARG : st;
+    }
+  }
+  *out = c.release();
+  return VMX_OK;
+}
+
 void vmx_ctx_destroy(vmx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -833,6 +984,7 @@ static int garr_import(vmx_ctx* c, size_t n, const uint8_t* be, int hdr, int che
   *out = nullptr;
   VMX_ENTER(c);
   if (n && !be) return VMX_EARG;
+  if (c->kind == 1) return ec_import(c, n, be, hdr, out);
   vmx_garr* a = nullptr;
   VMX_TRY(new_garr(c, n, &a));
   std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(a, vmx_garr_free);
@@ -911,7 +1063,8 @@ int vmx_garr_from_raw(vmx_ctx* c, size_t n, const uint8_t* be, size_t width, uns
   if (!out) return VMX_EARG;
   *out = nullptr;
   VMX_ENTER(c);
-  if ((n && !be) || !width || width > (size_t)8 * c->nl) { set_error("from_raw: bad width %zu", width); return VMX_EARG; }
+  if (c->kind == 1) { set_error("curve groups draw random points with vmx_garr_from_candidates"); return VMX_EARG; }
+  if ((n && !be) || !width || width > (size_t)16 * c->nl) { set_error("from_raw: bad width %zu", width); return VMX_EARG; }
   if (bitlen > 8 * width) bitlen = 0;
   DevBuf raw;
   VMX_TRY(raw.alloc(c, n * width));
@@ -920,26 +1073,6 @@ int vmx_garr_from_raw(vmx_ctx* c, size_t n, const uint8_t* be, size_t width, uns
     VMX_CU(cudaStreamSynchronize(c->stream));  // `be` is borrowed for the call only
   }
   return garr_from_raw_dev(c, n, raw.as<uint8_t>(), width, bitlen, out);
-}
-
-// stream bytes [offset, offset + nbytes) of PRGHeuristic(SHA-256); *data points at the first one
-static int prg_bytes_dev(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t nbytes, DevBuf& buf,
-                         const uint8_t** data) {
-  if (!seed || seedlen < 32 || seedlen > 48) { set_error("PRG seed must be 32..48 bytes"); return VMX_EARG; }
-  const size_t first = offset / 32, shift = offset % 32;
-  const size_t nblk = (shift + nbytes + 31) / 32;
-  if (first + nblk >= 0xffffffffull) { set_error("PRG stream too long"); return VMX_ESIZE; }
-  PrgSeed s;
-  std::memset(&s, 0, sizeof s);
-  std::memcpy(s.bytes, seed, seedlen);
-  s.len = (int)seedlen;
-  VMX_TRY(buf.alloc(c, nblk * 32));
-  if (nblk) {
-    VMX_LAUNCH(c, k_prg_bytes, nblocks(nblk, 128), 128, 0, s, first, nblk, buf.as<uint8_t>());
-    VMX_CHECK_LAUNCH();
-  }
-  *data = buf.as<uint8_t>() + shift;
-  return VMX_OK;
 }
 
 // PRGHeuristic(SHA-256) output bytes [offset, offset + nbytes) to the host: the expansion of a long
@@ -962,12 +1095,45 @@ int vmx_garr_prg_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64_
   if (!out) return VMX_EARG;
   *out = nullptr;
   VMX_ENTER(c);
-  if (!width || width > (size_t)8 * c->nl) { set_error("prg: bad width %zu", width); return VMX_EARG; }
+  if (!width || width > (size_t)16 * c->nl) { set_error("prg: bad width %zu", width); return VMX_EARG; }
   if (bitlen > 8 * width) bitlen = 0;
+  if (c->kind == 1) return ec_random_prg(c, seed, seedlen, offset, n, width, bitlen, out);
   DevBuf raw;
   const uint8_t* data = nullptr;
   VMX_TRY(prg_bytes_dev(c, seed, seedlen, offset, n * width, raw, &data));
+  c->prg_consumed = (uint64_t)n * width;
   return garr_from_raw_dev(c, n, data, width, bitlen, out);
+}
+
+uint64_t vmx_ctx_prg_consumed(const vmx_ctx* c) { return c ? c->prg_consumed : 0; }
+
+int vmx_garr_from_candidates(vmx_ctx* c, size_t m, const uint8_t* be, size_t width, unsigned bitlen, size_t n_want,
+                             vmx_garr** out, size_t* used) {
+  if (!out || !used) return VMX_EARG;
+  *out = nullptr;
+  *used = 0;
+  VMX_ENTER(c);
+  if (c->kind != 1) { set_error("from_candidates: not a curve group"); return VMX_EARG; }
+  if ((m && !be) || !width || width > 64) { set_error("from_candidates: bad width %zu", width); return VMX_EARG; }
+  if (bitlen > 8 * width) bitlen = 0;
+  vmx_garr* full = nullptr;
+  VMX_TRY(new_garr(c, n_want, &full));
+  std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(full, vmx_garr_free);
+  size_t acc = 0, u = 0;
+  if (m && n_want) {
+    DevBuf raw;
+    VMX_TRY(raw.alloc(c, m * width));
+    VMX_CU(cudaMemcpyAsync(raw.p, be, m * width, cudaMemcpyHostToDevice, c->stream));
+    VMX_TRY(ec_candidates(c, raw.as<uint8_t>(), m, width, bitlen, full, 0, &acc, &u));
+  }
+  *used = n_want ? u : 0;
+  if (acc == n_want) { *out = guard.release(); return VMX_OK; }
+  vmx_garr* part = nullptr;  // fewer accepted than wanted: hand back the accepted prefix
+  VMX_TRY(new_garr(c, acc, &part));
+  const int st = gather(c, full->d, full->cap, part->d, part->cap, acc, nullptr, nullptr, 0, 0, c->gl);
+  if (st != VMX_OK) { vmx_garr_free(part); return st; }
+  *out = part;
+  return VMX_OK;
 }
 
 int vmx_rarr_prg_raw_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t n, size_t width,
@@ -975,7 +1141,7 @@ int vmx_rarr_prg_raw_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uin
   if (!out) return VMX_EARG;
   *out = nullptr;
   VMX_ENTER(c);
-  if (!width || width > (size_t)8 * c->nl) { set_error("prg: bad width %zu", width); return VMX_EARG; }
+  if (!width || width > (size_t)16 * c->nl) { set_error("prg: bad width %zu", width); return VMX_EARG; }
   if (bitlen > 8 * width) bitlen = 0;
   DevBuf raw;
   const uint8_t* data = nullptr;
@@ -999,6 +1165,7 @@ static int garr_export(const vmx_garr* a, int hdr, uint8_t* be_out) {
   if (!a) return VMX_EARG;
   vmx_ctx* c = a->ctx;
   VMX_ENTER(c);
+  if (c->kind == 1) return be_out ? ec_export(a, hdr, be_out) : VMX_EARG;
   if (!a->n) return VMX_OK;
   if (!be_out) return VMX_EARG;
   DevBuf raw;
@@ -1024,7 +1191,7 @@ int vmx_garr_fill(vmx_ctx* c, size_t n, const uint8_t* elem_be, vmx_garr** out) 
   vmx_garr* a = nullptr;
   VMX_TRY(new_garr(c, n, &a));
   if (n) {
-    const int planes = c->nl / 4;
+    const int planes = c->gl / 4;
     VMX_LAUNCH(c, k_gather, nblocks(n * planes, 256), 256, 0, reinterpret_cast<const uint4*>(one.d()), one.cap,
                reinterpret_cast<uint4*>(a->d), a->cap, n, planes, (const uint32_t*)nullptr, (const uint32_t*)nullptr,
                (long long)0, (long long)0, 1, (size_t)0);
@@ -1056,7 +1223,8 @@ int vmx_exp_fixed(vmx_ctx* c, const uint8_t* base_be, const vmx_rarr* e, vmx_gar
   vmx_garr* r = nullptr;
   VMX_TRY(new_garr(c, e->n, &r));
   std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(r, vmx_garr_free);
-  if (e->n) VMX_DISPATCH(c->nl, VMX_TRY(exp_fixed_run<N>(c, T, e, ebits, r->d, r->cap)));
+  if (c->kind == 1) VMX_TRY(ec_exp_fixed_run(c, T, e, ebits, r->d, r->cap));
+  else if (e->n) VMX_DISPATCH(c->nl, VMX_TRY(exp_fixed_run<N>(c, T, e, ebits, r->d, r->cap)));
   *out = guard.release();
   return VMX_OK;
 }
@@ -1077,10 +1245,18 @@ int vmx_elem_exp(vmx_ctx* c, const uint8_t* base_be, const uint8_t* e_be, uint8_
   VMX_TRY(vmx_rarr_from_bytes(c, 1, e_be, &e));
   std::unique_ptr<vmx_rarr, void (*)(vmx_rarr*)> ge(e, vmx_rarr_free);
   ElemBuf res;
-  VMX_TRY(res.alloc_elems(c, 1));
+  VMX_TRY(res.alloc_gelems(c, 1));
   int ebits = 0;
   VMX_TRY(rarr_bitlen(e, &ebits));
-  if (have) {
+  if (c->kind == 1) {
+    if (have) {
+      VMX_TRY(ec_exp_fixed_run(c, T, e, ebits, res.d(), res.cap));
+    } else {
+      ElemBuf base;
+      VMX_TRY(upload_one(c, base_be, true, base));
+      VMX_TRY(ec_exp_var_run(c, base.d(), base.cap, e->d, e->cap, true, ebits, 1, res.d(), res.cap));
+    }
+  } else if (have) {
     VMX_DISPATCH(c->nl, VMX_TRY(exp_fixed_run<N>(c, T, e, ebits, res.d(), res.cap)));
   } else {
     ElemBuf base;
@@ -1096,6 +1272,7 @@ int vmx_elem_exp(vmx_ctx* c, const uint8_t* base_be, const uint8_t* e_be, uint8_
 int vmx_elem_inv(vmx_ctx* c, const uint8_t* in_be, uint8_t* out_be) {
   VMX_ENTER(c);
   if (!in_be || !out_be) return VMX_EARG;
+  if (c->kind == 1) return ec_elem_inv(c, in_be, out_be);
   const int N = c->nl;
   std::vector<uint32_t> a(N), r(N);
   if (!be_to_limbs(in_be, c->eb, a.data(), N) || limbs_cmp(a.data(), c->P.n, N) >= 0) {
@@ -1127,7 +1304,8 @@ int vmx_exp_var(const vmx_garr* a, const vmx_rarr* e, vmx_garr** out) {
   vmx_garr* r = nullptr;
   VMX_TRY(new_garr(c, a->n, &r));
   std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(r, vmx_garr_free);
-  VMX_DISPATCH(c->nl, VMX_TRY(exp_var_run<N>(c, a->d, a->cap, e->d, e->cap, false, ebits, a->n, r->d, r->cap)));
+  if (c->kind == 1) VMX_TRY(ec_exp_var_run(c, a->d, a->cap, e->d, e->cap, false, ebits, a->n, r->d, r->cap));
+  else VMX_DISPATCH(c->nl, VMX_TRY(exp_var_run<N>(c, a->d, a->cap, e->d, e->cap, false, ebits, a->n, r->d, r->cap)));
   *out = guard.release();
   return VMX_OK;
 }
@@ -1146,7 +1324,8 @@ int vmx_exp_scalar(const vmx_garr* a, const uint8_t* e_be, vmx_garr** out) {
   vmx_garr* r = nullptr;
   VMX_TRY(new_garr(c, a->n, &r));
   std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(r, vmx_garr_free);
-  VMX_DISPATCH(c->nl, VMX_TRY(exp_var_run<N>(c, a->d, a->cap, e.d(), e.cap, true, ebits, a->n, r->d, r->cap)));
+  if (c->kind == 1) VMX_TRY(ec_exp_var_run(c, a->d, a->cap, e.d(), e.cap, true, ebits, a->n, r->d, r->cap));
+  else VMX_DISPATCH(c->nl, VMX_TRY(exp_var_run<N>(c, a->d, a->cap, e.d(), e.cap, true, ebits, a->n, r->d, r->cap)));
   *out = guard.release();
   return VMX_OK;
 }
@@ -1203,6 +1382,7 @@ int vmx_expprod(const vmx_garr* const* a, size_t k, const vmx_rarr* e, uint8_t* 
     VMX_TRY(same_ctx(a[l]->ctx, c));
     if (a[l]->n != e->n) { set_error("expProd: size mismatch %zu vs %zu", a[l]->n, e->n); return VMX_ESIZE; }
   }
+  if (c->kind == 1) return ec_expprod(c, a, k, e, out_be);
   int L = 0;
   VMX_TRY(rarr_bitlen(e, &L));
   ElemBuf res;
@@ -1236,6 +1416,12 @@ int vmx_mul(const vmx_garr* a, const vmx_garr* b, vmx_garr** out) {
   if (a->n != b->n) { set_error("mul: size mismatch %zu vs %zu", a->n, b->n); return VMX_ESIZE; }
   vmx_garr* r = nullptr;
   VMX_TRY(new_garr(c, a->n, &r));
+  if (c->kind == 1) {
+    const int st = ec_mul(c, a, b, r);
+    if (st != VMX_OK) { vmx_garr_free(r); return st; }
+    *out = r;
+    return VMX_OK;
+  }
   if (a->n) {
     VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_mul<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, b->d, b->cap, r->d, r->cap,
                                    a->n, c->P.params<N>()));
@@ -1252,6 +1438,14 @@ int vmx_inv(const vmx_garr* a, vmx_garr** out) {
   if (!a) return VMX_EARG;
   vmx_ctx* c = a->ctx;
   VMX_ENTER(c);
+  if (c->kind == 1) {
+    vmx_garr* r = nullptr;
+    VMX_TRY(new_garr(c, a->n, &r));
+    const int st = ec_neg(c, a, r);
+    if (st != VMX_OK) { vmx_garr_free(r); return st; }
+    *out = r;
+    return VMX_OK;
+  }
   return exp_scalar_limbs(c, a, c->pm2.data(), out);
 }
 
@@ -1259,6 +1453,7 @@ int vmx_prod(const vmx_garr* a, uint8_t* out_be) {
   if (!a || !out_be) return VMX_EARG;
   vmx_ctx* c = a->ctx;
   VMX_ENTER(c);
+  if (c->kind == 1) return ec_prod(c, a, out_be);
   ElemBuf res;
   VMX_TRY(res.alloc_elems(c, 1));
   DevBuf off;
@@ -1284,7 +1479,7 @@ static int upload_u32(vmx_ctx* c, const uint32_t* h, size_t n, DevBuf& buf) {
 
 // rows_dev[r] = element idx[r] (count rows of nl words, element-major); idx is a HOST list or null
 static int pack_rows(vmx_ctx* c, const uint32_t* d, size_t cap, size_t n, const uint32_t* idx, size_t count,
-                     void* rows_dev) {
+                     void* rows_dev, int limbs) {
   if (!count) return VMX_OK;
   if (!rows_dev) return VMX_EARG;
   DevBuf di;
@@ -1292,7 +1487,7 @@ static int pack_rows(vmx_ctx* c, const uint32_t* d, size_t cap, size_t n, const 
     for (size_t r = 0; r < count; r++) if (idx[r] >= n) { set_error("row index out of range"); return VMX_EARG; }
     VMX_TRY(upload_u32(c, idx, count, di));
   } else if (count > n) { set_error("more rows than elements"); return VMX_ESIZE; }
-  const int planes = c->nl / 4;
+  const int planes = limbs / 4;
   VMX_LAUNCH(c, k_pack_rows, nblocks(count * planes, 256), 256, 0, reinterpret_cast<const uint4*>(d), cap,
              idx ? di.as<uint32_t>() : (const uint32_t*)nullptr, count, planes, reinterpret_cast<uint4*>(rows_dev));
   VMX_CHECK_LAUNCH();
@@ -1300,7 +1495,7 @@ static int pack_rows(vmx_ctx* c, const uint32_t* d, size_t cap, size_t n, const 
 }
 // element dst_idx[r] of a fresh array of n elements = row r; the rows must cover every element once
 static int unpack_rows(vmx_ctx* c, uint32_t* d, size_t cap, size_t n, const void* rows_dev, const uint32_t* dst_idx,
-                       size_t count) {
+                       size_t count, int limbs) {
   if (count != n) { set_error("unpack_rows: %zu rows for %zu elements", count, n); return VMX_ESIZE; }
   if (!count) return VMX_OK;
   if (!rows_dev) return VMX_EARG;
@@ -1313,7 +1508,7 @@ static int unpack_rows(vmx_ctx* c, uint32_t* d, size_t cap, size_t n, const void
     }
     VMX_TRY(upload_u32(c, dst_idx, count, di));
   }
-  const int planes = c->nl / 4;
+  const int planes = limbs / 4;
   VMX_LAUNCH(c, k_unpack_rows, nblocks(count * planes, 256), 256, 0, reinterpret_cast<const uint4*>(rows_dev),
              dst_idx ? di.as<uint32_t>() : (const uint32_t*)nullptr, count, planes, reinterpret_cast<uint4*>(d), cap);
   VMX_CHECK_LAUNCH();
@@ -1332,23 +1527,24 @@ int vmx_permute(const vmx_garr* a, const uint32_t* perm, vmx_garr** out) {
   VMX_TRY(upload_u32(c, perm, a->n, p));
   vmx_garr* r = nullptr;
   VMX_TRY(new_garr(c, a->n, &r));
-  const int s = gather(c, a->d, a->cap, r->d, r->cap, a->n, nullptr, p.as<uint32_t>(), 0, 0);
+  const int s = gather(c, a->d, a->cap, r->d, r->cap, a->n, nullptr, p.as<uint32_t>(), 0, 0, c->gl);
   if (s != VMX_OK) { vmx_garr_free(r); return s; }
   *out = r;
   return VMX_OK;
 }
 
 // ---- exchange between the GPUs of one box
-size_t vmx_ctx_row_bytes(const vmx_ctx* c) { return c ? (size_t)c->nl * 4 : 0; }
+size_t vmx_ctx_row_bytes(const vmx_ctx* c) { return c ? (size_t)c->gl * 4 : 0; }
+size_t vmx_ctx_ring_row_bytes(const vmx_ctx* c) { return c ? (size_t)c->nl * 4 : 0; }
 int vmx_garr_pack_rows(const vmx_garr* a, const uint32_t* idx, size_t count, void* rows_dev) {
   if (!a) return VMX_EARG;
   VMX_ENTER(a->ctx);
-  return pack_rows(a->ctx, a->d, a->cap, a->n, idx, count, rows_dev);
+  return pack_rows(a->ctx, a->d, a->cap, a->n, idx, count, rows_dev, a->ctx->gl);
 }
 int vmx_rarr_pack_rows(const vmx_rarr* a, const uint32_t* idx, size_t count, void* rows_dev) {
   if (!a) return VMX_EARG;
   VMX_ENTER(a->ctx);
-  return pack_rows(a->ctx, a->d, a->cap, a->n, idx, count, rows_dev);
+  return pack_rows(a->ctx, a->d, a->cap, a->n, idx, count, rows_dev, a->ctx->nl);
 }
 int vmx_garr_unpack_rows(vmx_ctx* c, size_t n, const void* rows_dev, const uint32_t* dst_idx, size_t count, vmx_garr** out) {
   if (!out) return VMX_EARG;
@@ -1356,7 +1552,7 @@ int vmx_garr_unpack_rows(vmx_ctx* c, size_t n, const void* rows_dev, const uint3
   VMX_ENTER(c);
   vmx_garr* r = nullptr;
   VMX_TRY(new_garr(c, n, &r));
-  const int s = unpack_rows(c, r->d, r->cap, n, rows_dev, dst_idx, count);
+  const int s = unpack_rows(c, r->d, r->cap, n, rows_dev, dst_idx, count, c->gl);
   if (s != VMX_OK) { vmx_garr_free(r); return s; }
   *out = r;
   return VMX_OK;
@@ -1367,7 +1563,7 @@ int vmx_rarr_unpack_rows(vmx_ctx* c, size_t n, const void* rows_dev, const uint3
   VMX_ENTER(c);
   vmx_rarr* r = nullptr;
   VMX_TRY(new_rarr(c, n, &r));
-  const int s = unpack_rows(c, r->d, r->cap, n, rows_dev, dst_idx, count);
+  const int s = unpack_rows(c, r->d, r->cap, n, rows_dev, dst_idx, count, c->nl);
   if (s != VMX_OK) { vmx_rarr_free(r); return s; }
   *out = r;
   return VMX_OK;
@@ -1385,8 +1581,8 @@ int vmx_shift_push(const vmx_garr* a, const uint8_t* elem_be, vmx_garr** out) {
   VMX_TRY(new_garr(c, a->n, &r));
   std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(r, vmx_garr_free);
   if (a->n) {
-    VMX_TRY(gather(c, a->d, a->cap, r->d, r->cap, a->n - 1, nullptr, nullptr, 0, 1));
-    VMX_TRY(gather(c, el.d(), el.cap, r->d, r->cap, 1, nullptr, nullptr, 0, 0));
+    VMX_TRY(gather(c, a->d, a->cap, r->d, r->cap, a->n - 1, nullptr, nullptr, 0, 1, c->gl));
+    VMX_TRY(gather(c, el.d(), el.cap, r->d, r->cap, 1, nullptr, nullptr, 0, 0, c->gl));
   }
   *out = guard.release();
   return VMX_OK;
@@ -1404,7 +1600,7 @@ int vmx_extract(const vmx_garr* a, const uint8_t* keep, vmx_garr** out) {
   VMX_TRY(upload_u32(c, src.data(), src.size(), p));
   vmx_garr* r = nullptr;
   VMX_TRY(new_garr(c, src.size(), &r));
-  const int s = gather(c, a->d, a->cap, r->d, r->cap, src.size(), p.as<uint32_t>(), nullptr, 0, 0);
+  const int s = gather(c, a->d, a->cap, r->d, r->cap, src.size(), p.as<uint32_t>(), nullptr, 0, 0, c->gl);
   if (s != VMX_OK) { vmx_garr_free(r); return s; }
   *out = r;
   return VMX_OK;
@@ -1419,16 +1615,17 @@ int vmx_slice(const vmx_garr* a, size_t begin, size_t end, vmx_garr** out) {
   VMX_ENTER(c);
   vmx_garr* r = nullptr;
   VMX_TRY(new_garr(c, end - begin, &r));
-  const int s = gather(c, a->d, a->cap, r->d, r->cap, end - begin, nullptr, nullptr, (long long)begin, 0);
+  const int s = gather(c, a->d, a->cap, r->d, r->cap, end - begin, nullptr, nullptr, (long long)begin, 0, c->gl);
   if (s != VMX_OK) { vmx_garr_free(r); return s; }
   *out = r;
   return VMX_OK;
 }
 
-static int arrays_equal(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32_t* b, size_t bcap, size_t n, int* eq) {
+static int arrays_equal(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32_t* b, size_t bcap, size_t n, int* eq,
+                        int limbs) {
   VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
   if (n) {
-    const int planes = c->nl / 4;
+    const int planes = limbs / 4;
     VMX_LAUNCH(c, k_equal, nblocks(n * planes, 256), 256, 0, reinterpret_cast<const uint4*>(a), acap,
                reinterpret_cast<const uint4*>(b), bcap, n, planes, c->d_flag);
     VMX_CHECK_LAUNCH();
@@ -1444,7 +1641,7 @@ int vmx_equals(const vmx_garr* a, const vmx_garr* b, int* equal) {
   VMX_ENTER(c);
   VMX_TRY(same_ctx(b->ctx, c));
   if (a->n != b->n) { *equal = 0; return VMX_OK; }
-  return arrays_equal(c, a->d, a->cap, b->d, b->cap, a->n, equal);
+  return arrays_equal(c, a->d, a->cap, b->d, b->cap, a->n, equal, c->gl);
 }
 
 int vmx_get(const vmx_garr* a, size_t i, uint8_t* out_be) {
@@ -1461,6 +1658,16 @@ int vmx_expprod_cols(const vmx_garr* const* bases, size_t t, const int64_t* ints
   vmx_ctx* c = bases[0]->ctx;
   VMX_ENTER(c);
   const size_t n = bases[0]->n;
+  if (c->kind == 1) {
+    for (size_t j = 0; j < t; j++)
+      if (bases[j]->ctx != c || bases[j]->n != n) { set_error("expProd: size mismatch"); return VMX_ESIZE; }
+    vmx_garr* r = nullptr;
+    VMX_TRY(new_garr(c, n, &r));
+    const int st = ec_cols(c, bases, t, ints, r);
+    if (st != VMX_OK) { vmx_garr_free(r); return st; }
+    *out = r;
+    return VMX_OK;
+  }
   vmx_garr* acc = nullptr;
   for (size_t j = 0; j < t; j++) {
     if (bases[j]->ctx != c || bases[j]->n != n) { if (acc) vmx_garr_free(acc); set_error("expProd: size mismatch"); return VMX_ESIZE; }
@@ -1520,7 +1727,7 @@ int vmx_rarr_from_raw(vmx_ctx* c, size_t n, const uint8_t* be, size_t width, uns
   if (!out) return VMX_EARG;
   *out = nullptr;
   VMX_ENTER(c);
-  if ((n && !be) || !width || width > (size_t)8 * c->nl) { set_error("from_raw: bad width %zu", width); return VMX_EARG; }
+  if ((n && !be) || !width || width > (size_t)16 * c->nl) { set_error("from_raw: bad width %zu", width); return VMX_EARG; }
   if (bitlen > 8 * width) bitlen = 0;
   vmx_rarr* a = nullptr;
   VMX_TRY(new_rarr(c, n, &a));
@@ -1832,7 +2039,7 @@ int vmx_requals(const vmx_rarr* a, const vmx_rarr* b, int* equal) {
   VMX_ENTER(c);
   VMX_TRY(same_ctx(b->ctx, c));
   if (a->n != b->n) { *equal = 0; return VMX_OK; }
-  return arrays_equal(c, a->d, a->cap, b->d, b->cap, a->n, equal);
+  return arrays_equal(c, a->d, a->cap, b->d, b->cap, a->n, equal, c->nl);
 }
 
 // ---------------------------------------------------------------- self test of the cooperative multiplier
@@ -1840,6 +2047,7 @@ int vmx_selftest_coop(const vmx_garr* a, const vmx_garr* b, int* equal) {
   if (!a || !b || !equal) return VMX_EARG;
   vmx_ctx* c = a->ctx;
   VMX_ENTER(c);
+  if (c->kind == 1) { set_error("cooperative multiplier: ModPGroup contexts only"); return VMX_EARG; }
   if (a->n != b->n || b->ctx != c) return VMX_ESIZE;
 #ifdef VMX_HOST_EMUL
   *equal = 1;
@@ -1854,7 +2062,7 @@ int vmx_selftest_coop(const vmx_garr* a, const vmx_garr* b, int* equal) {
                y.cap, c->P.consts, c->P.n0inv);
   });
   VMX_CHECK_LAUNCH();
-  return arrays_equal(c, x.d(), x.cap, y.d(), y.cap, a->n, equal);
+  return arrays_equal(c, x.d(), x.cap, y.d(), y.cap, a->n, equal, c->nl);
 #endif
 }
 
@@ -1864,6 +2072,7 @@ int vmx_debug_coop_mul(const vmx_garr* a, const vmx_garr* b, vmx_garr** out) {
   *out = nullptr;
   vmx_ctx* c = a->ctx;
   VMX_ENTER(c);
+  if (c->kind == 1) { set_error("cooperative multiplier: ModPGroup contexts only"); return VMX_EARG; }
   if (a->n != b->n || b->ctx != c) return VMX_ESIZE;
 #ifdef VMX_HOST_EMUL
   return vmx_mul(a, b, out);

@@ -12,6 +12,7 @@
 #include "../../include/vmx.h"
 #include "cuda_compat.cuh"
 #include "kernels_elem.cuh"
+#include "kernels_ec.cuh"
 #include "kernels_member.cuh"
 #include "kernels_mexp.cuh"
 #include "kernels_prg.cuh"
@@ -65,7 +66,13 @@ struct Modulus {
 
 struct vmx_ctx {
   int device = 0;
-  int nl = 0;              // limbs per residue: 16, 32, 64 or 96
+  int kind = 0;            // 0: ModPGroup, 1: ECqPGroup (256-bit prime curve)
+  int nl = 0;              // limbs per residue: 16, 32, 64 or 96 (ModP); 8 (curve: coordinate field and Z_q)
+  int gl = 0;              // limbs per stored group element: nl (ModP), 16 (affine curve point)
+  size_t cb = 0;           // curve: bytes of one serialised coordinate
+  vmx::EcCurve ecc;        // curve: field, coefficients and constants handed to the kernels
+  bool ec_sqrt_ok = false; // curve: p = 3 mod 4 (square roots by one exponentiation)
+  uint64_t prg_consumed = 0;  // stream bytes the last *_prg_sha256 call consumed
   size_t eb = 0, rb = 0;   // bytes of a serialised group / ring element
   cudaStream_t stream = nullptr;
   vmx::Modulus P, Q;

@@ -203,6 +203,18 @@ class ByteTreeReader:
         v = np.frombuffer(self.buf[self.pos:end], dtype=np.uint8)
         return v if self.buf.readonly else v.copy()
 
+    def point_array_stream(self, size: int, width: int) -> np.ndarray:
+        """An array over a curve group: this node has two children, node(size)[x leaves] and
+        node(size)[y leaves], every leaf `width` bytes -> the 2 * (5 + size * (5 + width)) bytes of the two
+        children (the engine validates every header, vmx_garr_from_leaves)."""
+        if self.kind != NODE or self.count != 2 or self.read_children:
+            raise EIOException("expected a node of 2 coordinate arrays")
+        end = self.pos + 2 * (5 + size * (5 + width))
+        if end > len(self.buf):
+            raise EIOException("truncated point array")
+        v = np.frombuffer(self.buf[self.pos:end], dtype=np.uint8)
+        return v if self.buf.readonly else v.copy()
+
     def leaf_matrix(self, size: int, width: int) -> np.ndarray:
         """This node as `size` leaves of exactly `width` bytes -> (size, width) uint8 matrix."""
         if self.kind != NODE or self.count != size:
