@@ -55,6 +55,18 @@ def nominal_modmuls_per_ciphertext(bits: int, n: int, n_e=256, n_v=256, n_r=100)
     return {"reencrypt": reenc, "prove": prove, "verify": verify, "total": reenc + prove + verify}
 
 
+def nominal_fieldmuls_per_ciphertext_ec(n: int, L=256):
+    """The same textbook operation counts on a 256-bit curve, in field multiplications (136 word MACs each,
+    SURVEY.md §8d): mixed addition 11, doubling 8, full addition 16; every exponent is < q (256 bits)."""
+    fix = lambda: -(-L // 8) * 11
+    var = lambda: L * 8 + -(-L // 6) * 16
+    mexp = lambda: min(-(-L // c) * (11 + 16 * 2 ** (c + 1) / n) for c in range(1, 24))
+    reenc = 2 * fix() + 2 * 11
+    prove = 5 * fix() + 3 * mexp() + 4 * 11
+    verify = 6 * mexp() + 2 * var() + fix() + 4 * 11
+    return {"reencrypt": reenc, "prove": prove, "verify": verify, "total": reenc + prove + verify}
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -93,9 +105,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if is_curve(args):
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU restatement in C (oracle/cpu_ref.c) covers "
+                          "ModPGroup only; curve groups are checked against oracle/ec.py (Python)"}))
+        return
     res = cpu_baseline.run(bits=args.bits, n_total=args.n, sample=args.cpu_sample, steps=args.steps,
                            warmup=min(args.warmup, 1))
-    line = {"metric": "ciphertexts/s: re-encrypt+PoS prove+verify, %d-bit ModPGroup" % args.bits, "impl": "reference",
+    line = {"metric": metric_name(args), "impl": "reference",
             "value": res["value"], "unit": "ciphertexts/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 limbs (exact integer)", "data": "synthetic",
@@ -106,11 +122,26 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def is_curve(args) -> bool:
+    return args.group != "modp"
+
+
+def group_label(args) -> str:
+    return "ECqPGroup %s" % args.group if is_curve(args) else "ModPGroup %d-bit (RFC 3526)" % args.bits
+
+
+def metric_name(args) -> str:
+    return "ciphertexts/s: re-encrypt+PoS prove+verify, " + \
+        ("%s ECqPGroup" % args.group if is_curve(args) else "%d-bit ModPGroup" % args.bits)
+
+
 def config_dict(args):
-    return {"workload": "ModPGroup %d-bit (RFC 3526), width 1, N=%d ciphertexts per GPU: re-encrypt + PoSBasicTW "
-                        "prove + verify" % (args.bits, args.n),
-            "bits": args.bits, "width": 1, "n_per_gpu": args.n, "ebitlen": 256, "vbitlen": 256, "rbitlen": 100,
-            "l2": "working set (N x %d B per array, >10 arrays) exceeds the 126 MB L2" % (args.bits // 8)}
+    elem = 64 if is_curve(args) else args.bits // 8
+    return {"workload": "%s, width 1, N=%d ciphertexts per GPU: re-encrypt + PoSBasicTW prove + verify"
+                        % (group_label(args), args.n),
+            "group": args.group, "bits": 256 if is_curve(args) else args.bits, "width": 1, "n_per_gpu": args.n,
+            "ebitlen": 256, "vbitlen": 256, "rbitlen": 100,
+            "l2": "working set (N x %d B per array, >10 arrays) exceeds the 126 MB L2" % elem}
 
 
 def main():
@@ -121,6 +152,7 @@ def main():
     ap.add_argument("--impl", default="vmx", choices=["vmx", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("VMX_BENCH_N", "100000")))
     ap.add_argument("--bits", type=int, default=3072)
+    ap.add_argument("--group", default="modp", help="modp (RFC 3526 safe prime of --bits) or a curve name (P-256)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="ciphertexts in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -151,7 +183,13 @@ def main():
     crypto = vmx.crypto
 
     p, q, g = groups.rfc3526(args.bits)
-    if world > 1:
+    if is_curve(args):
+        if world > 1:
+            par = importlib.import_module("verificatum-vmn_b200.parallel")
+            G = par.make_curve_group(args.group, local_rank)
+        else:
+            G = A.ECqPGroup(args.group, device=local_rank)
+    elif world > 1:
         # ONE list of world * n ciphertexts, sharded in contiguous index ranges over the GPUs: one
         # shuffle, one proof; expProd partial products and permuted rows travel over NCCL
         par = importlib.import_module("verificatum-vmn_b200.parallel")
@@ -174,7 +212,8 @@ def main():
     y = G.getg().exp(x)
     pk = A.PPGroup(G, 2).product(G.getg(), y)
     ciphertexts = mixnet.demoCiphertexts(pk, n, setup_rs)
-    params = mixnet.SessionParams(pGroupString="ModPGroup(RFC3526-%d)" % args.bits)
+    params = mixnet.SessionParams(pGroupString="ECqPGroup(%s)" % args.group if is_curve(args)
+                                  else "ModPGroup(RFC3526-%d)" % args.bits)
     session = mixnet.ShufflerSession(G, pk, params, prg("prover"))
     generators = session.deriveGenerators(n)
     seed = bytes(range(32))
@@ -299,19 +338,24 @@ def main():
         k_ms = r0.elapsed_time(r1) / reps
         k_modmuls = (G.modmul_count() - mm0) / reps
         e.free()
-        macs = macs_per_modmul(args.bits)
+        macs = 136 if is_curve(args) else macs_per_modmul(args.bits)
+        elem_bytes = 64 if is_curve(args) else args.bits // 8
         achieved = k_modmuls * macs / (k_ms * 1e-3)
         traffic = pipe_busy = None
         try:  # one `ncu --set full` capture of this kernel at the same shape (profiles/, per launch)
             cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_exp_fixed.json")))
-            if cap["n"] == n_local and args.bits == 3072:
+            if cap["n"] == n_local and args.bits == 3072 and not is_curve(args):
                 traffic, pipe_busy = cap["traffic_bytes"], cap["fmaheavy_pipe_busy_pct"]
         except Exception:
             pass
-        roof = {"bound": "imad", "kernel": "k_exp_fixed<%d>" % (args.bits // 32), "achieved": achieved / 1e12,
+        roof = {"bound": "imad", "kernel": "k_ec_exp_fixed" if is_curve(args) else "k_exp_fixed<%d>" % (args.bits // 32),
+                "achieved": achieved / 1e12,
                 "peak": IMAD_PEAK_MAC_PER_S / 1e12, "unit": "TMAC/s (32x32+64 IMAD.WIDE)", "frac": achieved / IMAD_PEAK_MAC_PER_S,
                 "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu, profiles/r01_ncu_exp_fixed.json)",
-                "algorithmic_bytes": k_modmuls * (args.bits // 8) + 2 * n_local * (args.bits // 8),
+                "algorithmic_bytes": (k_modmuls / 11 * elem_bytes + 32 * n_local + 96 * n_local) if is_curve(args)
+                else k_modmuls * elem_bytes + 2 * n_local * elem_bytes,
+                "unit_of_work": "field multiplication = 136 word MACs nominal (the P-256 reduction executes 64 + adds)"
+                if is_curve(args) else "modmul = 2N^2+N word MACs",
                 "imad_pipe_busy_pct_ncu": pipe_busy, "modmuls_per_launch": k_modmuls, "ms_per_launch": k_ms,
                 "peak_source": "measured on B200 (profiles/r01_ubench_imad.txt); MEASURED_PEAKS.json has no integer peak",
                 "hbm_note": "integer-pipe bound: arithmetic intensity ~1e4 MAC/B, HBM is not the limiter"}
@@ -319,7 +363,7 @@ def main():
     # ---- end to end through the public API with host buffers
     e2e = None
     if not args.no_e2e:
-        G.membership_check = os.environ.get("VMX_BENCH_MEMBERSHIP", "0") == "1"
+        G.membership_check = os.environ.get("VMX_BENCH_MEMBERSHIP", "1") == "1"
         ciph_bytes = ciphertexts.toByteTree().to_bytes()
         pinned = torch.empty(len(ciph_bytes), dtype=torch.uint8).pin_memory()
         pinned.numpy()[:] = np.frombuffer(ciph_bytes, dtype=np.uint8)
@@ -370,7 +414,7 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not is_curve(args):
         try:
             from oracle import cpu_baseline
             res = cpu_baseline.run(bits=args.bits, n_total=n, sample=args.cpu_sample, steps=1, warmup=0)
@@ -380,9 +424,9 @@ def main():
             cpu = {"value": None, "unit": "ciphertexts/s", "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
 
     if rank == 0:
-        nominal = nominal_modmuls_per_ciphertext(args.bits, n)
-        macs = macs_per_modmul(args.bits)
-        line = {"metric": "ciphertexts/s: re-encrypt+PoS prove+verify, %d-bit ModPGroup" % args.bits,
+        nominal = nominal_fieldmuls_per_ciphertext_ec(n) if is_curve(args) else nominal_modmuls_per_ciphertext(args.bits, n)
+        macs = 136 if is_curve(args) else macs_per_modmul(args.bits)
+        line = {"metric": metric_name(args),
                 "value": value, "unit": "ciphertexts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32 limbs (exact integer)", "data": "synthetic", "config": config_dict(args),

@@ -26,7 +26,7 @@ def main():
     import torch
     import torch.distributed as dist
     mode = sys.argv[1]
-    bits = int(sys.argv[2])
+    bits = sys.argv[2] if not sys.argv[2].isdigit() else int(sys.argv[2])   # group: bit size or curve name
     n = int(sys.argv[3])
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
@@ -45,9 +45,13 @@ def main():
     eg = importlib.import_module("verificatum-vmn_b200.elgamal")
     groups = importlib.import_module("verificatum-vmn_b200.groups")
     cr = vmx.crypto
-    p, q, g = groups.test512() if bits == 512 else groups.rfc3526(bits)
-    G1 = A.ModPGroup(p, q, g, device=device or 0)          # plain: the whole array on this rank
-    GS = par.make_group(p, q, g, device)                   # sharded over the ranks
+    if isinstance(bits, str):
+        G1 = A.ECqPGroup(bits, device=device or 0)
+        GS = par.make_curve_group(bits, device)
+    else:
+        p, q, g = groups.test512() if bits == 512 else groups.rfc3526(bits)
+        G1 = A.ModPGroup(p, q, g, device=device or 0)          # plain: the whole array on this rank
+        GS = par.make_group(p, q, g, device)                   # sharded over the ranks
 
     def rs(label):
         r = cr.PRGHeuristic()
@@ -177,7 +181,7 @@ def main():
     stats = (GS.comm.collectives, GS.comm.bytes_exchanged)
     dist.barrier()
     if rank == 0:
-        print("PARALLEL OK world=%d bits=%d n=%d collectives=%d bytes=%d" % (world, bits, n, stats[0], stats[1]))
+        print("PARALLEL OK world=%d group=%s n=%d collectives=%d bytes=%d" % (world, bits, n, stats[0], stats[1]))
     dist.destroy_process_group()
 
 

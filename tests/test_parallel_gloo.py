@@ -19,7 +19,7 @@ def _free_port() -> int:
     return port
 
 
-def _run(world: int, bits: int, n: int, emul_lib: str):
+def _run(world: int, bits, n: int, emul_lib: str):
     port = _free_port()
     procs = []
     for rank in range(world):
@@ -45,3 +45,8 @@ def _run(world: int, bits: int, n: int, emul_lib: str):
 @pytest.mark.parametrize("world,n", [(2, 37), (3, 20), (2, 1)])
 def test_sharded_equals_single(emul_lib, world, n):
     _run(world, 512, n, emul_lib)
+
+
+@pytest.mark.parametrize("world,n", [(2, 21), (3, 8)])
+def test_sharded_curve_equals_single(emul_lib, world, n):
+    _run(world, "P-256", n, emul_lib)

@@ -781,10 +781,8 @@ class ECqPGroup(ModPGroup):
             return arr
         return super().toElementArray(*args, check_membership=check_membership)
 
-    def randomElementArray(self, size: int, randomSource, statDist: int) -> "PGroupElementArray":
-        """Per point: draw ceil((|p|+statDist)/8) bytes, reduce mod p to x, accept if x^3+ax+b is a square and
-        take the smaller root, else draw again ([VCR-mem]; distr/IndependentGeneratorsRO.java:129).  The
-        candidates are tested in parallel on the device and compacted in stream order."""
+    def _random_full_handle(self, size: int, randomSource, statDist: int):
+        """Engine handle of `size` random points drawn from `randomSource` (the whole array on this device)."""
         bits = self.p.bit_length() + statDist
         width = (bits + 7) // 8
         h = C.c_void_p()
@@ -793,10 +791,10 @@ class ECqPGroup(ModPGroup):
             nat.check(self._lib.vmx_garr_prg_sha256(self.ctx, randomSource.seed, len(randomSource.seed), off, size,
                                                     width, bits, C.byref(h)))
             _advance_prg(randomSource, off + int(self._lib.vmx_ctx_prg_consumed(self.ctx)))
-            return self._garr(h, size)
+            return h
         # any other source: its bytes are consumed candidate by candidate, so ask for exactly one candidate
-        # per missing point and round (expected two rounds per point on average ... log n rounds in total)
-        parts, have = [], 0
+        # per missing point and round (about log2(size) rounds)
+        rows, have = [], 0
         while have < size:
             m = size - have
             raw = np.frombuffer(randomSource.getBytes(m * width), dtype=np.uint8)
@@ -806,12 +804,17 @@ class ECqPGroup(ModPGroup):
                                                          C.byref(used)))
             part = PGroupElementArray(self, hh)
             have += part.size()
-            parts.append(part)
-        pts = []
-        for part in parts:
-            pts += part.elements()
+            rows.append(part.to_matrix())
             part.free()
-        return self.toElementArray(pts)
+        m = np.ascontiguousarray(np.concatenate(rows)) if rows else np.empty((0, self.elem_bytes), dtype=np.uint8)
+        nat.check(self._lib.vmx_garr_from_bytes(self.ctx, size, _ptr(m), 0, C.byref(h)))
+        return h
+
+    def randomElementArray(self, size: int, randomSource, statDist: int) -> "PGroupElementArray":
+        """Per point: draw ceil((|p|+statDist)/8) bytes, reduce mod p to x, accept if x^3+ax+b is a square and
+        take the smaller root, else draw again ([VCR-mem]; distr/IndependentGeneratorsRO.java:129).  The
+        candidates are tested in parallel on the device and compacted in stream order."""
+        return self._garr(self._random_full_handle(size, randomSource, statDist), size)
 
     def __eq__(self, o):
         return isinstance(o, ECqPGroup) and (o.p, o.a, o.b, o.g, o.q) == (self.p, self.a, self.b, self.g, self.q)

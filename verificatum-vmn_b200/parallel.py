@@ -26,12 +26,13 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import struct
 from typing import List, Optional, Sequence
 
 import numpy as np
 
 from . import _native as nat
-from .arithm import (ArithmFormatException, ByteTreeDeviceArray, LargeIntegerArray, ModPGroup, Permutation, PField,
+from .arithm import (ArithmFormatException, ByteTreeDeviceArray, ECqPGroup, LargeIntegerArray, ModPGroup, Permutation, PField,
                      PFieldElement, PGroupElement, PGroupElementArray, PRingElementArray, _advance_prg, _be, _ptr,
                      _sha256_prg_offset)
 from .eio import ByteTreeReader, EIOException
@@ -359,11 +360,9 @@ class ShardedRingArray(PRingElementArray):
 
 
 # ====================================================================== sharded group arrays
-class ShardedModPGroup(ModPGroup):
-    def __init__(self, p: int, q: int, g: int, comm_factory, device: int = 0):
-        super().__init__(p, q, g, device=device)
-        self.comm = comm_factory(self)
-        self.pRing = ShardedField(self)
+class _ShardedGroupMixin:
+    """What a sharded group adds to ModPGroup / ECqPGroup: array wrappers, index ranges, combination of the
+    ranks' partial products."""
 
     def _garr(self, h, size: Optional[int] = None):
         return ShardedGroupArray(self, h, size)
@@ -393,6 +392,13 @@ class ShardedModPGroup(ModPGroup):
                 self._lib.vmx_garr_free(h)
             out.append(PGroupElement(self, int.from_bytes(buf.tobytes(), "big")))
         return out
+
+
+class ShardedModPGroup(_ShardedGroupMixin, ModPGroup):
+    def __init__(self, p: int, q: int, g: int, comm_factory, device: int = 0):
+        ModPGroup.__init__(self, p, q, g, device=device)
+        self.comm = comm_factory(self)
+        self.pRing = ShardedField(self)
 
     def toElementArray(self, *args, check_membership: Optional[bool] = None):
         lib = self._lib
@@ -449,6 +455,74 @@ class ShardedModPGroup(ModPGroup):
         raw = np.frombuffer(randomSource.getBytes(size * width), dtype=np.uint8)[lo * width:hi * width]
         nat.check(self._lib.vmx_garr_from_raw(self.ctx, hi - lo, _ptr(np.ascontiguousarray(raw)), width, bits,
                                               C.byref(h)))
+        return self._garr(h, size)
+
+
+class ShardedECqPGroup(_ShardedGroupMixin, ECqPGroup):
+    """ECqPGroup with arrays sharded over the ranks (BASELINE.json config 5: P-256 at 1/2/4/8 GPUs)."""
+
+    def __init__(self, name: str, comm_factory, device: int = 0):
+        ECqPGroup.__init__(self, name, device=device)
+        self.comm = comm_factory(self)
+        self.pRing = ShardedField(self)
+
+    def toElementArray(self, *args, check_membership: Optional[bool] = None):
+        lib = self._lib
+        h = C.c_void_p()
+        cb = self.coord_bytes
+        if len(args) == 1:
+            vals = [e.value for e in args[0]]
+            lo, hi = self._range(len(vals))
+            m = np.frombuffer(b"".join(_be(v, self.elem_bytes) for v in vals[lo:hi]), dtype=np.uint8)
+            nat.check(lib.vmx_garr_from_bytes(self.ctx, hi - lo, _ptr(m), 0, C.byref(h)))
+            return self._garr(h, len(vals))
+        size, src = args
+        lo, hi = self._range(size)
+        if isinstance(src, (ByteTreeReader, np.ndarray)):
+            stream = None
+            if isinstance(src, ByteTreeReader):
+                try:
+                    stream = src.point_array_stream(size, cb)
+                except EIOException as e:
+                    raise ArithmFormatException(nat.VMX_EFORMAT, str(e))
+                run = size * (5 + cb)
+                hdr = np.frombuffer(struct.pack(">BI", 0, size), dtype=np.uint8)
+                leaf = np.frombuffer(struct.pack(">BI", 1, cb), dtype=np.uint8)
+                xs = stream[5:5 + run].reshape(size, 5 + cb)
+                ys = stream[10 + run:].reshape(size, 5 + cb)
+                if not (np.array_equal(stream[:5], hdr) and np.array_equal(stream[5 + run:10 + run], hdr) and
+                        (xs[:, :5] == leaf).all() and (ys[:, :5] == leaf).all()):
+                    raise ArithmFormatException(nat.VMX_EFORMAT, "point array: malformed coordinate nodes")
+                m = np.concatenate([xs[lo:hi, 5:], ys[lo:hi, 5:]], axis=1)
+            else:
+                m = src.reshape(size, self.elem_bytes)[lo:hi]
+            m = np.ascontiguousarray(m)
+            ok = True
+            try:
+                nat.check(lib.vmx_garr_from_bytes(self.ctx, hi - lo, _ptr(m), 1, C.byref(h)))
+            except ArithmFormatException:
+                ok = False
+            if not self.comm.all_and(ok):
+                if ok:
+                    lib.vmx_garr_free(h)
+                raise ArithmFormatException(nat.VMX_EFORMAT, "not a point of the curve")
+            arr = self._garr(h, size)
+            if stream is not None:
+                arr._leaves = stream
+            return arr
+        nat.check(lib.vmx_garr_fill(self.ctx, hi - lo, _be(src.value, self.elem_bytes), C.byref(h)))
+        return self._garr(h, size)
+
+    def randomElementArray(self, size: int, randomSource, statDist: int):
+        """Rejection sampling makes the position of point i in the stream depend on all earlier candidates:
+        every rank derives the whole array (one square-root test per candidate) and keeps its range."""
+        full = self._random_full_handle(size, randomSource, statDist)
+        lo, hi = self._range(size)
+        h = C.c_void_p()
+        try:
+            nat.check(self._lib.vmx_slice(full, lo, hi, C.byref(h)))
+        finally:
+            self._lib.vmx_garr_free(full)
         return self._garr(h, size)
 
 
@@ -510,12 +584,33 @@ class ShardedGroupArray(PGroupElementArray):
 
     def leaves(self) -> np.ndarray:
         """Serialisation of the WHOLE array (all shards, gathered to every rank), cached."""
+        if self._leaves is None and self.group.is_curve:
+            cb, nloc = self.group.coord_bytes, self.local_size()
+            buf = np.empty(self.group._leaves_bytes(nloc), dtype=np.uint8)
+            nat.check(self._lib.vmx_garr_to_leaves(self.h, _ptr(buf)))
+            run = nloc * (5 + cb)
+            gx = self.comm.allgather_matrix(buf[5:5 + run].reshape(nloc, 5 + cb), self.bounds)
+            gy = self.comm.allgather_matrix(buf[10 + run:].reshape(nloc, 5 + cb), self.bounds)
+            hdr = np.frombuffer(struct.pack(">BI", 0, self.gsize), dtype=np.uint8)
+            self._leaves = np.concatenate([hdr, gx.reshape(-1), hdr, gy.reshape(-1)])
         if self._leaves is None:
             w = 5 + self.group.elem_bytes
             m = np.empty((self.local_size(), w), dtype=np.uint8)
             nat.check(self._lib.vmx_garr_to_leaves(self.h, _ptr(m)))
             self._leaves = np.ascontiguousarray(self.comm.allgather_matrix(m, self.bounds)).reshape(-1)
         return self._leaves
+
+    def to_matrix(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if not self.group.is_curve:
+            return PGroupElementArray.to_matrix(self, out)
+        cb, n = self.group.coord_bytes, self.gsize
+        lv = self.leaves()
+        run = n * (5 + cb)
+        m = np.concatenate([lv[5:5 + run].reshape(n, 5 + cb)[:, 5:], lv[10 + run:].reshape(n, 5 + cb)[:, 5:]], axis=1)
+        if out is not None:
+            out[:] = m
+            return out
+        return m
 
 
 def _sharded_permute(arr, pi: Permutation, ring: bool):
@@ -526,7 +621,7 @@ def _sharded_permute(arr, pi: Permutation, ring: bool):
     lib = arr._lib
     torch = comm.torch
     ctx = arr.ring.group.ctx if ring else arr.group.ctx
-    nl = int(lib.vmx_ctx_row_bytes(ctx)) // 4
+    nl = int(lib.vmx_ctx_ring_row_bytes(ctx) if ring else lib.vmx_ctx_row_bytes(ctx)) // 4
     tbl = pi.table
     if tbl.shape[0] != arr.gsize:
         raise nat.VmxError(nat.VMX_ESIZE, "permutation of the wrong size")
@@ -557,6 +652,13 @@ def _sharded_permute(arr, pi: Permutation, ring: bool):
             recv.record_stream(torch.cuda.current_stream())
             send.record_stream(torch.cuda.current_stream())
     return arr._new(h)
+
+
+def make_curve_group(name: str, device: Optional[int], group=None) -> ShardedECqPGroup:
+    """An ECqPGroup whose arrays are sharded over the ranks of `group` (default: the world)."""
+    def factory(G):
+        return Comm(group, device, int(G._lib.vmx_ctx_stream(G.ctx) or 0) if device is not None else None)
+    return ShardedECqPGroup(name, factory, device=0 if device is None else device)
 
 
 def make_group(p: int, q: int, g: int, device: Optional[int], group=None) -> ShardedModPGroup:
