@@ -114,7 +114,14 @@ class Permutation:
         m[:, pad:] = raw
         m[:, pad] &= 0xFF >> ((8 - bits % 8) % 8)
         cols = m.view(">u8")
-        order = np.lexsort([cols[:, j] for j in range(cols.shape[1] - 1, -1, -1)])
+        # the keys are ~(log2 size + statDist)-bit random integers: sort by the leading 64-bit word and fall
+        # back to the full lexicographic sort only if two leading words collide (same result either way)
+        lead = cols[:, 0].astype(np.uint64)
+        order = np.argsort(lead)  # distinct leading words: every sort gives the same order
+        if size > 1:
+            s_lead = lead[order]
+            if (s_lead[1:] == s_lead[:-1]).any():
+                order = np.lexsort([cols[:, j] for j in range(cols.shape[1] - 1, -1, -1)])
         table = np.empty(size, dtype=np.uint32)
         table[order] = np.arange(size, dtype=np.uint32)
         return Permutation(table)
@@ -493,6 +500,14 @@ class LargeIntegerArray:
         if off is not None and bitLength < field.order.bit_length():
             nat.check(lib.vmx_rarr_prg_sha256(field.group.ctx, randomSource.seed, len(randomSource.seed), off, size,
                                               bitLength, C.byref(h)))
+            _advance_prg(randomSource, off + size * width)
+            return LargeIntegerArray(field, h)
+        if off is not None:
+            # integers as wide as or wider than q (n_e + n_v + n_r = 612 bits over the 256-bit order of a curve
+            # group): every use converts them to field elements (pField.toElementArray, hvzk/PoSBasicTW.java:473),
+            # so they are reduced mod q as they are drawn
+            nat.check(lib.vmx_rarr_prg_raw_sha256(field.group.ctx, randomSource.seed, len(randomSource.seed), off, size,
+                                                  width, bitLength, C.byref(h)))
             _advance_prg(randomSource, off + size * width)
             return LargeIntegerArray(field, h)
         raw = np.frombuffer(randomSource.getBytes(size * width), dtype=np.uint8)

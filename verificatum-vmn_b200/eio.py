@@ -156,7 +156,7 @@ class ByteTreeReader:
             return self.start + 5 + self.count
         pos = self.pos
         for _ in range(self.count - self.read_children):
-            pos = ByteTreeReader(self.buf, pos).end()
+            pos = ByteTreeReader(self.buf, pos).end_fast()
         return pos
 
     def getNextChild(self) -> "ByteTreeReader":

@@ -177,7 +177,7 @@ class ShardedField(PField):
         lo, hi = self._range(size)
         h = C.c_void_p()
         off = _sha256_prg_offset(randomSource)
-        if off is not None and bitLength < self.order.bit_length():
+        if off is not None:  # integers of any width up to 4 residues: reduced mod q on the device
             nat.check(lib.vmx_rarr_prg_raw_sha256(self.group.ctx, randomSource.seed, len(randomSource.seed),
                                                   off + lo * width, hi - lo, width, bitLength, C.byref(h)))
             _advance_prg(randomSource, off + size * width)
