@@ -187,6 +187,11 @@ def random_sources(vmx, bits, n):
     big = 700
     assert list(A.Permutation.random(big, rs, 100, G).table) == oar.permutation_random(big, ors, 100)
     assert rs.getBytes(50) == ors.get_bytes(50)
+    # n >= 4096: the keys are also RANKED on the device (vmx_permutation_prg_sha256); short keys (statDist 0)
+    # tie and are ordered by index, as a stable sort does
+    for big, sd in ((5000, 100), (4100, 0)):
+        assert list(A.Permutation.random(big, rs, sd, G).table) == oar.permutation_random(big, ors, sd)
+    assert rs.getBytes(3) == ors.get_bytes(3)
     prg = cr.PRGHeuristic()
     prg.setSeed(seed("batch"))
     assert vals(R.toElementArray(A.LargeIntegerArray.random(n, 256, prg, R))) == opr.batch_vector("sha256", seed("batch"), n, 256)

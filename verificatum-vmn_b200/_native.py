@@ -51,6 +51,8 @@ SIGNATURES = {
     "vmx_garr_from_candidates": (C.c_int, [_P, _SZ, _P, _SZ, C.c_uint, _SZ, _PP, C.POINTER(C.c_size_t)]),
     "vmx_rarr_prg_raw_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, _SZ, C.c_uint, _PP]),
     "vmx_prg_bytes_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, _P]),
+    "vmx_permutation_prg_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, _SZ, C.c_uint, _P, C.POINTER(C.c_int)]),
+    "vmx_permutation_from_raw": (C.c_int, [_P, _SZ, _P, _SZ, C.c_uint, _P, C.POINTER(C.c_int)]),
     "vmx_garr_to_bytes": (C.c_int, [_P, _P]),
     "vmx_garr_from_leaves": (C.c_int, [_P, _SZ, _P, C.c_int, _PP]),
     "vmx_garr_to_leaves": (C.c_int, [_P, _P]),

@@ -100,6 +100,15 @@ class Permutation:
         bits = max(1, (size - 1).bit_length()) + statDist
         nbytes = (bits + 7) // 8
         off = _sha256_prg_offset(randomSource) if group is not None else None
+        if off is not None and size >= 4096:
+            # keys drawn AND ranked on the device; only the table comes back
+            table = np.empty(size, dtype=np.uint32)
+            fb = C.c_int()
+            nat.check(group._lib.vmx_permutation_prg_sha256(group.ctx, randomSource.seed, len(randomSource.seed), off,
+                                                            size, nbytes, bits, _ptr(table), C.byref(fb)))
+            if not fb.value:
+                _advance_prg(randomSource, off + size * nbytes)
+                return Permutation(table)
         if off is not None and size * nbytes >= 4096:
             raw = np.empty(size * nbytes, dtype=np.uint8)
             nat.check(group._lib.vmx_prg_bytes_sha256(group.ctx, randomSource.seed, len(randomSource.seed), off,

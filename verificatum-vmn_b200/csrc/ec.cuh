@@ -50,130 +50,149 @@ VMX_DEV bool aff_is_inf(const uint32_t (&x)[8]) {
 }
 
 // P <- 2P
+template <bool SOL>
 VMX_DEV void jac_dbl(Jac& P, const EcCurve& C) {
   const Fp256& F = C.F;
   uint32_t t0[8], t1[8], t2[8], t3[8];
-  if (C.a_minus3) {
+  if (SOL || C.a_minus3) {  // the P-256 instantiation carries the a = -3 formula only
     // dbl-2001-b: 3M + 5S
-    fp_sqr(t0, P.Z, F);            // delta
-    fp_sqr(t1, P.Y, F);            // gamma
-    fp_mul(t2, P.X, t1, F);        // beta
+    fp_sqr<SOL>(t0, P.Z, F);            // delta
+    fp_sqr<SOL>(t1, P.Y, F);            // gamma
+    fp_mul<SOL>(t2, P.X, t1, F);        // beta
     fp_sub(t3, P.X, t0, F);
     fp_add(t0, P.X, t0, F);        // (t0 keeps delta no longer; Z3 needs it -> recompute below)
-    fp_mul(t3, t3, t0, F);
+    fp_mul<SOL>(t3, t3, t0, F);
     fp_dbl(t0, t3, F);
     fp_add(t3, t0, t3, F);         // alpha = 3 (X - delta)(X + delta)
     // Z3 = (Y + Z)^2 - gamma - delta = 2 Y Z
-    fp_mul(t0, P.Y, P.Z, F);
+    fp_mul<SOL>(t0, P.Y, P.Z, F);
     fp_dbl(P.Z, t0, F);
     // X3 = alpha^2 - 8 beta
     fp_dbl(t2, t2, F); fp_dbl(t2, t2, F);  // 4 beta
-    fp_sqr(t0, t3, F);
+    fp_sqr<SOL>(t0, t3, F);
     fp_sub(t0, t0, t2, F);
     fp_sub(P.X, t0, t2, F);
     // Y3 = alpha (4 beta - X3) - 8 gamma^2
     fp_sub(t2, t2, P.X, F);
-    fp_mul(t2, t3, t2, F);
-    fp_sqr(t1, t1, F);
+    fp_mul<SOL>(t2, t3, t2, F);
+    fp_sqr<SOL>(t1, t1, F);
     fp_dbl(t1, t1, F); fp_dbl(t1, t1, F); fp_dbl(t1, t1, F);
     fp_sub(P.Y, t2, t1, F);
   } else {
     // general a: M = 3 X^2 + a Z^4, S = 4 X Y^2
-    fp_sqr(t0, P.Z, F);
-    fp_sqr(t0, t0, F);
-    fp_mul(t0, t0, C.a, F);        // a Z^4
-    fp_sqr(t1, P.X, F);
+    fp_sqr<SOL>(t0, P.Z, F);
+    fp_sqr<SOL>(t0, t0, F);
+    fp_mul<SOL>(t0, t0, C.a, F);        // a Z^4
+    fp_sqr<SOL>(t1, P.X, F);
     fp_dbl(t2, t1, F);
     fp_add(t1, t2, t1, F);
     fp_add(t3, t1, t0, F);         // M
-    fp_sqr(t1, P.Y, F);            // Y^2
-    fp_mul(t2, P.X, t1, F);
+    fp_sqr<SOL>(t1, P.Y, F);            // Y^2
+    fp_mul<SOL>(t2, P.X, t1, F);
     fp_dbl(t2, t2, F); fp_dbl(t2, t2, F);  // S
-    fp_mul(t0, P.Y, P.Z, F);
+    fp_mul<SOL>(t0, P.Y, P.Z, F);
     fp_dbl(P.Z, t0, F);            // Z3 = 2 Y Z
-    fp_sqr(t0, t3, F);
+    fp_sqr<SOL>(t0, t3, F);
     fp_sub(t0, t0, t2, F);
     fp_sub(P.X, t0, t2, F);        // X3 = M^2 - 2 S
     fp_sub(t2, t2, P.X, F);
-    fp_mul(t2, t3, t2, F);
-    fp_sqr(t1, t1, F);
+    fp_mul<SOL>(t2, t3, t2, F);
+    fp_sqr<SOL>(t1, t1, F);
     fp_dbl(t1, t1, F); fp_dbl(t1, t1, F); fp_dbl(t1, t1, F);
     fp_sub(P.Y, t2, t1, F);        // Y3 = M (S - X3) - 8 Y^4
   }
 }
 
+// The doubling branch of an addition (both operands equal) is never taken on honest inputs: it lives in
+// ONE out-of-line copy per instantiation so that the hot loops stay small enough for the instruction cache
+// (an inlined point operation is 30-50 KB of straight-line SASS).
+#ifndef VMX_HOST_EMUL
+#define VMX_NOINLINE __device__ __noinline__
+#else
+#define VMX_NOINLINE inline
+#endif
+template <bool SOL>
+VMX_NOINLINE void jac_dbl_rare(Jac* P, const EcCurve* C) {
+  Jac T = *P;
+  jac_dbl<SOL>(T, *C);
+  *P = T;
+}
+
 // P <- P + (x2, y2), (x2, y2) an affine point that is not the unit.  8M + 3S.
+template <bool SOL>
 VMX_DEV void jac_madd(Jac& P, const uint32_t (&x2)[8], const uint32_t (&y2)[8], const EcCurve& C) {
   const Fp256& F = C.F;
   if (jac_is_inf(P)) { jac_from_affine(P, x2, y2, C); return; }
   uint32_t zz[8], u2[8], s2[8], h[8], r[8];
-  fp_sqr(zz, P.Z, F);
-  fp_mul(u2, x2, zz, F);
-  fp_mul(s2, P.Z, zz, F);
-  fp_mul(s2, y2, s2, F);
+  fp_sqr<SOL>(zz, P.Z, F);
+  fp_mul<SOL>(u2, x2, zz, F);
+  fp_mul<SOL>(s2, P.Z, zz, F);
+  fp_mul<SOL>(s2, y2, s2, F);
   fp_sub(h, u2, P.X, F);
   fp_sub(r, s2, P.Y, F);
   if (fp_is_zero(h)) {
-    if (fp_is_zero(r)) jac_dbl(P, C); else jac_set_inf(P, C);
+    if (fp_is_zero(r)) { Jac T = P; jac_dbl_rare<SOL>(&T, &C); P = T; } else jac_set_inf(P, C);
     return;
   }
-  fp_mul(P.Z, P.Z, h, F);          // Z3 = Z1 H
-  fp_sqr(zz, h, F);                // HH
-  fp_mul(h, h, zz, F);             // HHH
-  fp_mul(u2, P.X, zz, F);          // V = X1 HH
-  fp_sqr(s2, r, F);
+  fp_mul<SOL>(P.Z, P.Z, h, F);          // Z3 = Z1 H
+  fp_sqr<SOL>(zz, h, F);                // HH
+  fp_mul<SOL>(h, h, zz, F);             // HHH
+  fp_mul<SOL>(u2, P.X, zz, F);          // V = X1 HH
+  fp_sqr<SOL>(s2, r, F);
   fp_sub(s2, s2, h, F);
   fp_sub(s2, s2, u2, F);
   fp_sub(P.X, s2, u2, F);          // X3 = r^2 - HHH - 2V
   fp_sub(u2, u2, P.X, F);
-  fp_mul(u2, r, u2, F);
-  fp_mul(h, P.Y, h, F);
+  fp_mul<SOL>(u2, r, u2, F);
+  fp_mul<SOL>(h, P.Y, h, F);
   fp_sub(P.Y, u2, h, F);           // Y3 = r (V - X3) - Y1 HHH
 }
 
 // P <- P + Q (both Jacobian).  12M + 4S.
+template <bool SOL>
 VMX_DEV void jac_add(Jac& P, const Jac& Q, const EcCurve& C) {
   const Fp256& F = C.F;
   if (jac_is_inf(Q)) return;
   if (jac_is_inf(P)) { P = Q; return; }
   uint32_t z1z1[8], z2z2[8], u1[8], u2[8], s1[8], s2[8];
-  fp_sqr(z1z1, P.Z, F);
-  fp_sqr(z2z2, Q.Z, F);
-  fp_mul(u1, P.X, z2z2, F);
-  fp_mul(u2, Q.X, z1z1, F);
-  fp_mul(s1, Q.Z, z2z2, F);
-  fp_mul(s1, P.Y, s1, F);
-  fp_mul(s2, P.Z, z1z1, F);
-  fp_mul(s2, Q.Y, s2, F);
+  fp_sqr<SOL>(z1z1, P.Z, F);
+  fp_sqr<SOL>(z2z2, Q.Z, F);
+  fp_mul<SOL>(u1, P.X, z2z2, F);
+  fp_mul<SOL>(u2, Q.X, z1z1, F);
+  fp_mul<SOL>(s1, Q.Z, z2z2, F);
+  fp_mul<SOL>(s1, P.Y, s1, F);
+  fp_mul<SOL>(s2, P.Z, z1z1, F);
+  fp_mul<SOL>(s2, Q.Y, s2, F);
   fp_sub(u2, u2, u1, F);           // H
   fp_sub(s2, s2, s1, F);           // r
   if (fp_is_zero(u2)) {
-    if (fp_is_zero(s2)) jac_dbl(P, C); else jac_set_inf(P, C);
+    if (fp_is_zero(s2)) { Jac T = P; jac_dbl_rare<SOL>(&T, &C); P = T; } else jac_set_inf(P, C);
     return;
   }
-  fp_mul(P.Z, P.Z, Q.Z, F);
-  fp_mul(P.Z, P.Z, u2, F);         // Z3 = Z1 Z2 H
-  fp_sqr(z1z1, u2, F);             // HH
-  fp_mul(u2, u2, z1z1, F);         // HHH
-  fp_mul(u1, u1, z1z1, F);         // V = U1 HH
-  fp_sqr(z2z2, s2, F);
+  fp_mul<SOL>(P.Z, P.Z, Q.Z, F);
+  fp_mul<SOL>(P.Z, P.Z, u2, F);         // Z3 = Z1 Z2 H
+  fp_sqr<SOL>(z1z1, u2, F);             // HH
+  fp_mul<SOL>(u2, u2, z1z1, F);         // HHH
+  fp_mul<SOL>(u1, u1, z1z1, F);         // V = U1 HH
+  fp_sqr<SOL>(z2z2, s2, F);
   fp_sub(z2z2, z2z2, u2, F);
   fp_sub(z2z2, z2z2, u1, F);
   fp_sub(P.X, z2z2, u1, F);        // X3
   fp_sub(u1, u1, P.X, F);
-  fp_mul(u1, s2, u1, F);
-  fp_mul(s1, s1, u2, F);
+  fp_mul<SOL>(u1, s2, u1, F);
+  fp_mul<SOL>(s1, s1, u2, F);
   fp_sub(P.Y, u1, s1, F);          // Y3
 }
 
 // y^2 == x^3 + a x + b ?   (x, y in Montgomery form)
+template <bool SOL>
 VMX_DEV bool ec_on_curve(const uint32_t (&x)[8], const uint32_t (&y)[8], const EcCurve& C) {
   const Fp256& F = C.F;
   uint32_t l[8], r[8];
-  fp_sqr(l, y, F);
-  fp_sqr(r, x, F);
+  fp_sqr<SOL>(l, y, F);
+  fp_sqr<SOL>(r, x, F);
   fp_add(r, r, C.a, F);
-  fp_mul(r, r, x, F);
+  fp_mul<SOL>(r, r, x, F);
   fp_add(r, r, C.b, F);
   return fp_eq(l, r);
 }

@@ -66,10 +66,57 @@ VMX_DEV void fp_mul_wide(uint32_t (&t)[16], const uint32_t (&a)[8], const uint32
   addc(t[15], e[15], o[14]);
 }
 
+// a^2 as 16 words: the 28 products a_i a_j (i < j) once, doubled, plus the 8 squares on the (aligned) even
+// pairs: 36 IMAD.WIDE instead of 64.
+VMX_DEV void fp_sqr_wide(uint32_t (&t)[16], const uint32_t (&a)[8]) {
+  uint32_t e[16], o[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) { e[k] = 0; o[k] = 0; }
+  // row i holds a_j * a_i for j > i; column i+j even -> e pair (i+j, i+j+1), odd -> o[i+j-1], o[i+j]
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    // same-parity partners j = i+2, i+4, ... -> even columns
+    if (i + 2 < 8) {
+      mad_wide_cc(e[2 * i + 2], e[2 * i + 3], a[i + 2], a[i]);
+#pragma unroll
+      for (int j = i + 4; j < 8; j += 2) madc_wide_cc(e[i + j], e[i + j + 1], a[j], a[i]);
+      // last pair written: j = i + 2 * ((7 - i) / 2); carry word lands two columns above it
+      const int jl = i + 2 * ((7 - i) / 2);
+      if (i + jl + 2 < 16) addc(e[i + jl + 2], e[i + jl + 2], 0);
+    }
+    // opposite-parity partners j = i+1, i+3, ... -> odd columns
+    mad_wide_cc(o[2 * i], o[2 * i + 1], a[i + 1], a[i]);
+#pragma unroll
+    for (int j = i + 3; j < 8; j += 2) madc_wide_cc(o[i + j - 1], o[i + j], a[j], a[i]);
+    const int jo = i + 1 + 2 * ((7 - i - 1) / 2);
+    if (i + jo + 1 < 15) addc(o[i + jo + 1], o[i + jo + 1], 0);
+  }
+  // s = e + (o << 32)
+  uint32_t s[16];
+  s[0] = e[0];
+  add_cc(s[1], e[1], o[0]);
+#pragma unroll
+  for (int k = 2; k < 15; k++) addc_cc(s[k], e[k], o[k - 1]);
+  addc(s[15], e[15], o[14]);
+  // t = 2 s + sum_i a_i^2 2^(64 i)
+  add_cc(s[0], s[0], s[0]);
+#pragma unroll
+  for (int k = 1; k < 15; k++) addc_cc(s[k], s[k], s[k]);
+  addc(s[15], s[15], s[15]);
+  mad_wide_cc(s[0], s[1], a[0], a[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) madc_wide_cc(s[2 * i], s[2 * i + 1], a[i], a[i]);
+#pragma unroll
+  for (int k = 0; k < 16; k++) t[k] = s[k];
+}
+
 // r = t / 2^256 mod n (Montgomery reduction of a 16-word value < n * 2^256), fully reduced.
+// SOL (compile time): n is the P-256 prime.  Kernels are instantiated for both so that a curve context
+// carries only the reduction it uses (the straight-line code of one point addition is ~50 KB of SASS).
+template <bool SOL>
 VMX_DEV void fp_redc(uint32_t (&r)[8], uint32_t (&t)[16], const Fp256& F) {
   uint32_t extra = 0;  // pending carry into column i+9
-  if (F.solinas) {
+  if (SOL) {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const uint32_t m = t[i];
@@ -111,12 +158,18 @@ VMX_DEV void fp_redc(uint32_t (&r)[8], uint32_t (&t)[16], const Fp256& F) {
 }
 
 // r = a * b * 2^-256 mod n.  r may alias a or b.
+template <bool SOL>
 VMX_DEV void fp_mul(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8], const Fp256& F) {
   uint32_t t[16];
   fp_mul_wide(t, a, b);
-  fp_redc(r, t, F);
+  fp_redc<SOL>(r, t, F);
 }
-VMX_DEV void fp_sqr(uint32_t (&r)[8], const uint32_t (&a)[8], const Fp256& F) { fp_mul(r, a, a, F); }
+template <bool SOL>
+VMX_DEV void fp_sqr(uint32_t (&r)[8], const uint32_t (&a)[8], const Fp256& F) {
+  uint32_t t[16];
+  fp_sqr_wide(t, a);
+  fp_redc<SOL>(r, t, F);
+}
 
 // r = a + b mod n (a, b < n)
 VMX_DEV void fp_add(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8], const Fp256& F) {
@@ -194,15 +247,17 @@ VMX_DEV void fp_copy(uint32_t (&r)[8], const uint32_t (&a)[8]) {
 // r = a^e mod n for a 256-bit exponent given as plain limbs (uniform across threads: the bits
 // come from the parameter bank).  `one` = R mod n.  Used for inversion (e = n - 2) and square
 // roots (e = (n + 1) / 4).
+template <bool SOL>
 VMX_DEV void fp_pow(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&e)[8], const uint32_t (&one)[8],
                     const Fp256& F) {
   uint32_t acc[8];
   fp_copy(acc, one);
   bool started = false;
+#pragma unroll 1
   for (int bit = 255; bit >= 0; bit--) {
-    if (started) fp_sqr(acc, acc, F);
+    if (started) fp_sqr<SOL>(acc, acc, F);
     if ((e[bit >> 5] >> (bit & 31)) & 1u) {
-      if (started) fp_mul(acc, acc, a, F); else { fp_copy(acc, a); started = true; }
+      if (started) fp_mul<SOL>(acc, acc, a, F); else { fp_copy(acc, a); started = true; }
     }
   }
   fp_copy(r, acc);

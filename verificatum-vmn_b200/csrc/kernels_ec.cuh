@@ -19,7 +19,7 @@ namespace vmx {
 
 constexpr int kEcThreads = 128;
 constexpr int kInvK = 4;  // residues per thread in the batched inversion
-#define VMX_EC_KERNEL __global__ void __launch_bounds__(kEcThreads)
+#define VMX_EC_KERNEL template <bool SOL> __global__ void __launch_bounds__(kEcThreads)
 
 // ------------------------------------------------------------------ byte codec
 // Element i: x at rawx + i*stride, y at rawy + i*stride, `cb` big-endian bytes each (two's complement:
@@ -61,9 +61,9 @@ VMX_EC_KERNEL k_ec_from_bytes(const uint8_t* __restrict__ rawx, const uint8_t* _
   for (int j = 0; j < 8; j++) { x[j] = ec_be_word(sx, cb, j); y[j] = ec_be_word(sy, cb, j); }
   if (!fp_lt(x, C.F.n) || !fp_lt(y, C.F.n)) bad |= kErrRange;
   if (!bad) {
-    fp_mul(x, x, C.r2, C.F);
-    fp_mul(y, y, C.r2, C.F);
-    if (!ec_on_curve(x, y, C)) bad |= kErrMember;
+    fp_mul<SOL>(x, x, C.r2, C.F);
+    fp_mul<SOL>(y, y, C.r2, C.F);
+    if (!ec_on_curve<SOL>(x, y, C)) bad |= kErrMember;
   }
   if (bad) atomicOr(err, bad);
   ec_store_affine(x, y, out, cap, i);
@@ -89,8 +89,8 @@ VMX_EC_KERNEL k_ec_to_bytes(const uint32_t* __restrict__ in, size_t cap, size_t 
   uint32_t one[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) one[j] = j == 0 ? 1u : 0u;
-  fp_mul(x, x, one, C.F);
-  fp_mul(y, y, one, C.F);
+  fp_mul<SOL>(x, x, one, C.F);
+  fp_mul<SOL>(y, y, one, C.F);
   for (int k = 0; k < cb - 32; k++) { dx[k] = 0; dy[k] = 0; }
 #pragma unroll
   for (int j = 0; j < 8; j++) {
@@ -116,6 +116,7 @@ struct InvLoad {
   uint32_t z[kInvK][8];
   uint32_t pre[kInvK][8];  // pre[k] = z[0] * ... * z[k]
 };
+template <bool SOL>
 VMX_DEV void inv_load(InvLoad& L, const uint32_t* __restrict__ in, size_t icap, size_t n, size_t base, int tid,
                       int bsize, const EcCurve& C) {
 #pragma unroll
@@ -123,17 +124,18 @@ VMX_DEV void inv_load(InvLoad& L, const uint32_t* __restrict__ in, size_t icap, 
     const size_t i = base + (size_t)k * bsize + tid;
     if (i < n) fp_load(L.z[k], in, icap, i); else fp_copy(L.z[k], C.one);
     if (fp_is_zero(L.z[k])) fp_copy(L.z[k], C.one);
-    if (k == 0) fp_copy(L.pre[0], L.z[0]); else fp_mul(L.pre[k], L.pre[k - 1], L.z[k], C.F);
+    if (k == 0) fp_copy(L.pre[0], L.z[0]); else fp_mul<SOL>(L.pre[k], L.pre[k - 1], L.z[k], C.F);
   }
 }
 // given inv = 1 / pre[K-1], write the inverses of the thread's residues
+template <bool SOL>
 VMX_DEV void inv_finish(const InvLoad& L, uint32_t (&inv)[8], uint32_t* __restrict__ out, size_t ocap, size_t n,
                         size_t base, int tid, int bsize, const EcCurve& C) {
 #pragma unroll
   for (int k = kInvK - 1; k >= 0; k--) {
     const size_t i = base + (size_t)k * bsize + tid;
     uint32_t zi[8];
-    if (k > 0) { fp_mul(zi, inv, L.pre[k - 1], C.F); fp_mul(inv, inv, L.z[k], C.F); } else fp_copy(zi, inv);
+    if (k > 0) { fp_mul<SOL>(zi, inv, L.pre[k - 1], C.F); fp_mul<SOL>(inv, inv, L.z[k], C.F); } else fp_copy(zi, inv);
     if (i < n) fp_store(zi, out, ocap, i);
   }
 }
@@ -141,6 +143,7 @@ VMX_DEV void inv_finish(const InvLoad& L, uint32_t (&inv)[8], uint32_t* __restri
 #ifndef VMX_HOST_EMUL
 // block-wide products: on return `excl` = product of the T of all OTHER threads, `total` = product of all.
 // sh: 2 * 8 * blockDim words.
+template <bool SOL>
 __device__ __forceinline__ void block_products(const uint32_t (&T)[8], uint32_t (&excl)[8], uint32_t (&total)[8],
                                                uint32_t* sh, const EcCurve& C) {
   const int tid = threadIdx.x, bs = blockDim.x;
@@ -155,12 +158,12 @@ __device__ __forceinline__ void block_products(const uint32_t (&T)[8], uint32_t 
     if (tid >= d) {
 #pragma unroll
       for (int j = 0; j < 8; j++) o[j] = shp[j * bs + tid - d];
-      fp_mul(p, p, o, C.F);
+      fp_mul<SOL>(p, p, o, C.F);
     }
     if (tid + d < bs) {
 #pragma unroll
       for (int j = 0; j < 8; j++) o[j] = shs[j * bs + tid + d];
-      fp_mul(s, s, o, C.F);
+      fp_mul<SOL>(s, s, o, C.F);
     }
     __syncthreads();
   }
@@ -179,7 +182,7 @@ __device__ __forceinline__ void block_products(const uint32_t (&T)[8], uint32_t 
   if (tid + 1 < bs) {
 #pragma unroll
     for (int j = 0; j < 8; j++) o[j] = shs[j * bs + tid + 1];
-    fp_mul(excl, excl, o, C.F);
+    fp_mul<SOL>(excl, excl, o, C.F);
   }
   __syncthreads();
 }
@@ -189,9 +192,9 @@ VMX_EC_KERNEL k_fp_inv_up(const uint32_t* __restrict__ in, size_t icap, size_t n
   __shared__ uint32_t sh[2 * 8 * kEcThreads];
   const size_t base = (size_t)blockIdx.x * (kEcThreads * kInvK);
   InvLoad L;
-  inv_load(L, in, icap, n, base, threadIdx.x, kEcThreads, C);
+  inv_load<SOL>(L, in, icap, n, base, threadIdx.x, kEcThreads, C);
   uint32_t excl[8], total[8];
-  block_products(L.pre[kInvK - 1], excl, total, sh, C);
+  block_products<SOL>(L.pre[kInvK - 1], excl, total, sh, C);
   fp_store(excl, excl_out, ecap, (size_t)blockIdx.x * kEcThreads + threadIdx.x);
   if (threadIdx.x == 0) fp_store(total, totals, tcap, blockIdx.x);
 }
@@ -201,12 +204,12 @@ VMX_EC_KERNEL k_fp_inv_down(const uint32_t* __restrict__ in, size_t icap, size_t
                             uint32_t* __restrict__ out, size_t ocap, const __grid_constant__ EcCurve C) {
   const size_t base = (size_t)blockIdx.x * (kEcThreads * kInvK);
   InvLoad L;
-  inv_load(L, in, icap, n, base, threadIdx.x, kEcThreads, C);
+  inv_load<SOL>(L, in, icap, n, base, threadIdx.x, kEcThreads, C);
   uint32_t inv[8], ti[8];
   fp_load(inv, excl_in, ecap, (size_t)blockIdx.x * kEcThreads + threadIdx.x);
   fp_load(ti, totals_inv, tcap, blockIdx.x);
-  fp_mul(inv, inv, ti, C.F);
-  inv_finish(L, inv, out, ocap, n, base, threadIdx.x, kEcThreads, C);
+  fp_mul<SOL>(inv, inv, ti, C.F);
+  inv_finish<SOL>(L, inv, out, ocap, n, base, threadIdx.x, kEcThreads, C);
 }
 
 // n <= kEcThreads * kInvK: one block, one Fermat inversion (thread 0).
@@ -215,12 +218,12 @@ VMX_EC_KERNEL k_fp_inv_block(const uint32_t* __restrict__ in, size_t icap, size_
   __shared__ uint32_t sh[2 * 8 * kEcThreads];
   __shared__ uint32_t sh_inv[8];
   InvLoad L;
-  inv_load(L, in, icap, n, 0, threadIdx.x, kEcThreads, C);
+  inv_load<SOL>(L, in, icap, n, 0, threadIdx.x, kEcThreads, C);
   uint32_t excl[8], total[8];
-  block_products(L.pre[kInvK - 1], excl, total, sh, C);
+  block_products<SOL>(L.pre[kInvK - 1], excl, total, sh, C);
   if (threadIdx.x == 0) {
     uint32_t ti[8];
-    fp_pow(ti, total, C.pm2, C.one, C.F);
+    fp_pow<SOL>(ti, total, C.pm2, C.one, C.F);
 #pragma unroll
     for (int j = 0; j < 8; j++) sh_inv[j] = ti[j];
   }
@@ -228,8 +231,8 @@ VMX_EC_KERNEL k_fp_inv_block(const uint32_t* __restrict__ in, size_t icap, size_
   uint32_t ti[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) ti[j] = sh_inv[j];
-  fp_mul(excl, excl, ti, C.F);
-  inv_finish(L, excl, out, ocap, n, 0, threadIdx.x, kEcThreads, C);
+  fp_mul<SOL>(excl, excl, ti, C.F);
+  inv_finish<SOL>(L, excl, out, ocap, n, 0, threadIdx.x, kEcThreads, C);
 }
 #endif
 
@@ -242,7 +245,7 @@ VMX_EC_KERNEL k_fp_inv_each(const uint32_t* __restrict__ in, size_t icap, size_t
   uint32_t z[8];
   fp_load(z, in, icap, i);
   if (fp_is_zero(z)) fp_copy(z, C.one);
-  fp_pow(z, z, C.pm2, C.one, C.F);
+  fp_pow<SOL>(z, z, C.pm2, C.one, C.F);
   fp_store(z, out, ocap, i);
 }
 
@@ -260,10 +263,10 @@ VMX_EC_KERNEL k_ec_finish(const uint32_t* __restrict__ jac, size_t jcap, const u
   if (jac_is_inf(P)) { ec_store_affine_inf(out, ocap, dst); return; }
   uint32_t zi[8], zi2[8];
   fp_load(zi, zinv, zcap, i);
-  fp_sqr(zi2, zi, C.F);
-  fp_mul(P.X, P.X, zi2, C.F);
-  fp_mul(zi2, zi2, zi, C.F);
-  fp_mul(P.Y, P.Y, zi2, C.F);
+  fp_sqr<SOL>(zi2, zi, C.F);
+  fp_mul<SOL>(P.X, P.X, zi2, C.F);
+  fp_mul<SOL>(zi2, zi2, zi, C.F);
+  fp_mul<SOL>(P.Y, P.Y, zi2, C.F);
   ec_store_affine(P.X, P.Y, out, ocap, dst);
 }
 
@@ -278,7 +281,7 @@ VMX_EC_KERNEL k_ec_add(const uint32_t* __restrict__ a_, size_t acap, const uint3
   ec_load_affine(x, y, a_, acap, i);
   if (aff_is_inf(x)) jac_set_inf(P, C); else jac_from_affine(P, x, y, C);
   ec_load_affine(x, y, b_, bcap, i);
-  if (!aff_is_inf(x)) jac_madd(P, x, y, C);
+  if (!aff_is_inf(x)) jac_madd<SOL>(P, x, y, C);
   ec_store_jac(P, jac, jcap, i);
 }
 
@@ -319,11 +322,12 @@ VMX_EC_KERNEL k_ec_cols(const __grid_constant__ EcCols A, size_t n, uint32_t* __
     jac_set_inf(T, C);
     int top = 63;
     while (!((m >> top) & 1ull)) top--;
+#pragma unroll 1
     for (int b = top; b >= 0; b--) {
-      jac_dbl(T, C);
-      if ((m >> b) & 1ull) jac_madd(T, x, y, C);
+      jac_dbl<SOL>(T, C);
+      if ((m >> b) & 1ull) jac_madd<SOL>(T, x, y, C);
     }
-    jac_add(R, T, C);
+    jac_add<SOL>(R, T, C);
   }
   ec_store_jac(R, jac, jcap, i);
 }
@@ -347,7 +351,7 @@ VMX_EC_KERNEL k_ec_exp_fixed(const uint32_t* __restrict__ table, size_t tcap, in
       d = window_bits<8>(e_, ecap, i, (k + 1) * w, w);
       if (d) ec_load_affine(nx, ny, table, tcap, ((size_t)(k + 1) << w) + d);
     }
-    if (dc && !aff_is_inf(x)) jac_madd(P, x, y, C);
+    if (dc && !aff_is_inf(x)) jac_madd<SOL>(P, x, y, C);
   }
   ec_store_jac(P, jac, jcap, i);
 }
@@ -362,7 +366,7 @@ VMX_EC_KERNEL k_ec_dbl_chain(const uint32_t* __restrict__ base, size_t bcap, uin
   if (aff_is_inf(x)) jac_set_inf(P, C); else jac_from_affine(P, x, y, C);
   for (int m = 0; m < len; m++) {
     ec_store_jac(P, jac, jcap, m);
-    jac_dbl(P, C);
+    jac_dbl<SOL>(P, C);
   }
 }
 
@@ -385,7 +389,7 @@ VMX_EC_KERNEL k_ec_table_level(const uint32_t* __restrict__ table, size_t tcap, 
     if (!aff_is_inf(x)) jac_from_affine(P, x, y, C);
     if (r) {
       ec_load_affine(x, y, table, tcap, ((size_t)k << w) + r);
-      if (!aff_is_inf(x)) jac_madd(P, x, y, C);
+      if (!aff_is_inf(x)) jac_madd<SOL>(P, x, y, C);
     }
   }
   ec_store_jac(P, jac, jcap, t);
@@ -410,19 +414,24 @@ VMX_EC_KERNEL k_ec_exp_var(const uint32_t* __restrict__ a_, size_t acap, const u
   }
   jac_from_affine(P, x, y, C);
   ec_store_jac(P, tab, tabcap, i);
+#pragma unroll 1
   for (int d = 2; d < 16; d++) {
-    jac_madd(P, x, y, C);
+    jac_madd<SOL>(P, x, y, C);
     ec_store_jac(P, tab, tabcap, (size_t)(d - 1) * n + i);
   }
   const int nwin = (ebits + 3) / 4;
   jac_set_inf(P, C);
+#pragma unroll 1
   for (int k = nwin - 1; k >= 0; k--) {
-    if (k != nwin - 1) { jac_dbl(P, C); jac_dbl(P, C); jac_dbl(P, C); jac_dbl(P, C); }
+    if (k != nwin - 1) {
+#pragma unroll 1
+      for (int s = 0; s < 4; s++) jac_dbl<SOL>(P, C);
+    }
     const uint32_t d = window_bits<8>(e_, ecap, ei, 4 * k, 4);
     if (d) {
       Jac T;
       ec_load_jac(T, tab, tabcap, (size_t)(d - 1) * n + i);
-      jac_add(P, T, C);
+      jac_add<SOL>(P, T, C);
     }
   }
   ec_store_jac(P, jac, jcap, i);
@@ -443,7 +452,7 @@ VMX_EC_KERNEL k_ec_seg_sum(const uint32_t* __restrict__ V, size_t vcap, int vjac
       const size_t ik = idx ? idx[ch.start + k] : ch.start + k;
       Jac T;
       ec_load_jac(T, V, vcap, ik);
-      jac_add(P, T, C);
+      jac_add<SOL>(P, T, C);
     }
   } else {
     uint32_t x[8], y[8], nx[8], ny[8];
@@ -451,7 +460,7 @@ VMX_EC_KERNEL k_ec_seg_sum(const uint32_t* __restrict__ V, size_t vcap, int vjac
     for (uint32_t k = 0; k < ch.len; k++) {
       fp_copy(x, nx); fp_copy(y, ny);
       if (k + 1 < ch.len) ec_load_affine(nx, ny, V, vcap, idx ? idx[ch.start + k + 1] : ch.start + k + 1);
-      if (!aff_is_inf(x)) jac_madd(P, x, y, C);
+      if (!aff_is_inf(x)) jac_madd<SOL>(P, x, y, C);
     }
   }
   ec_store_jac(P, out, ocap, c);
@@ -463,15 +472,17 @@ VMX_EC_KERNEL k_ec_weighted_small(const uint32_t* __restrict__ X, size_t xcap, s
   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ngroups) return;
   const size_t x0 = g * kSubVals;
-  Jac run, tot, T;
-  jac_set_inf(run, C);
-  jac_set_inf(tot, C);
-  for (int v = kSubVals; v >= 1; v--) {
-    ec_load_jac(T, X, xcap, x0 + v - 1);
-    jac_add(run, T, C);
-    jac_add(tot, run, C);
+  // run += X_v; tot += run, written as ONE addition site "A += Q" with the roles swapped after every step
+  Jac A, B, Q;  // (A, B) = (run, tot) before even steps, (tot, run) before odd steps
+  jac_set_inf(A, C);
+  jac_set_inf(B, C);
+#pragma unroll 1
+  for (int it = 0; it < 2 * kSubVals; it++) {
+    if ((it & 1) == 0) ec_load_jac(Q, X, xcap, x0 + (kSubVals - it / 2) - 1); else Q = B;
+    jac_add<SOL>(A, Q, C);
+    Q = A; A = B; B = Q;
   }
-  ec_store_jac(tot, Y, ycap, g);
+  ec_store_jac(B, Y, ycap, g);
 }
 
 // One thread per column col < ncols: out[col] = sum_m 16^m * Y[col * Mcount + m] by Horner from the top.
@@ -481,10 +492,14 @@ VMX_EC_KERNEL k_ec_horner(const uint32_t* __restrict__ Y, size_t ycap, int Mcoun
   if (col >= ncols) return;
   Jac P, T;
   jac_set_inf(P, C);
+#pragma unroll 1
   for (int m = Mcount - 1; m >= 0; m--) {
-    if (m != Mcount - 1) { jac_dbl(P, C); jac_dbl(P, C); jac_dbl(P, C); jac_dbl(P, C); }
+    if (m != Mcount - 1) {
+#pragma unroll 1
+      for (int s = 0; s < 4; s++) jac_dbl<SOL>(P, C);
+    }
     ec_load_jac(T, Y, ycap, (size_t)col * Mcount + m);
-    jac_add(P, T, C);
+    jac_add<SOL>(P, T, C);
   }
   ec_store_jac(P, out, ocap, col);
 }
@@ -500,21 +515,21 @@ VMX_EC_KERNEL k_ec_candidates(const uint32_t* __restrict__ xs, size_t xcap, size
   const Fp256& F = C.F;
   uint32_t x[8], rhs[8], y[8], t[8];
   fp_load(x, xs, xcap, j);
-  fp_mul(x, x, C.r2, F);
-  fp_sqr(rhs, x, F);
+  fp_mul<SOL>(x, x, C.r2, F);
+  fp_sqr<SOL>(rhs, x, F);
   fp_add(rhs, rhs, C.a, F);
-  fp_mul(rhs, rhs, x, F);
+  fp_mul<SOL>(rhs, rhs, x, F);
   fp_add(rhs, rhs, C.b, F);
-  fp_pow(y, rhs, C.sqe, C.one, F);
-  fp_sqr(t, y, F);
+  fp_pow<SOL>(y, rhs, C.sqe, C.one, F);
+  fp_sqr<SOL>(t, y, F);
   if (!fp_eq(t, rhs)) { ok[j] = 0; ec_store_affine_inf(cand, ccap, j); return; }
   // the smaller root as an integer: compare canonical forms
   uint32_t one[8], yc[8], ync[8], yn[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) one[k] = k == 0 ? 1u : 0u;
   fp_neg(yn, y, F);
-  fp_mul(yc, y, one, F);
-  fp_mul(ync, yn, one, F);
+  fp_mul<SOL>(yc, y, one, F);
+  fp_mul<SOL>(ync, yn, one, F);
   if (fp_lt(ync, yc)) fp_copy(y, yn);
   ok[j] = 1;
   ec_store_affine(x, y, cand, ccap, j);

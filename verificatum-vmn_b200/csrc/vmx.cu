@@ -1107,6 +1107,68 @@ int vmx_garr_prg_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64_
 
 uint64_t vmx_ctx_prg_consumed(const vmx_ctx* c) { return c ? c->prg_consumed : 0; }
 
+// Ranks of n random keys held in DEVICE memory (see kernels_perm.cuh).  *fallback = 1: not ranked (degenerate
+// key distribution or colliding leading words); the caller ranks on the host.
+static int permutation_dev(vmx_ctx* c, const uint8_t* d_raw, size_t n, size_t nbytes, unsigned bits, uint32_t* table_out,
+                           int* fallback) {
+  *fallback = 0;
+  if (!n) return VMX_OK;
+  if (n >= 0xffffffffull) { set_error("permutation too large"); return VMX_ESIZE; }
+  const int lbits = nbytes >= 8 ? (int)(bits - 8 * (nbytes - 8)) : (int)bits;  // significant bits of the lead word
+  int B = 1;
+  while (((size_t)1 << (B + 1)) * 4 <= n && B + 1 < 28) B++;
+  if (B > lbits) B = lbits;
+  const size_t nbuckets = (size_t)1 << B;
+  DevBuf off, cursor, keys, table;
+  VMX_TRY(off.alloc(c, (nbuckets + 1) * 4));
+  VMX_TRY(cursor.alloc(c, (nbuckets + 1) * 4));
+  VMX_TRY(keys.alloc(c, n * sizeof(PermKey)));
+  VMX_TRY(table.alloc(c, n * 4));
+  VMX_CU(cudaMemsetAsync(off.p, 0, (nbuckets + 1) * 4, c->stream));
+  VMX_LAUNCH(c, k_perm_hist, nblocks(n, 256), 256, 0, d_raw, n, (int)nbytes, (int)bits, lbits, B, off.as<uint32_t>());
+  VMX_CHECK_LAUNCH();
+  VMX_TRY(exclusive_scan(c, off.as<uint32_t>(), nbuckets + 1));
+  VMX_CU(cudaMemcpyAsync(cursor.p, off.p, (nbuckets + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
+  VMX_LAUNCH(c, k_perm_scatter, nblocks(n, 256), 256, 0, d_raw, n, (int)nbytes, (int)bits, lbits, B,
+             cursor.as<uint32_t>(), keys.as<PermKey>());
+  VMX_CHECK_LAUNCH();
+  VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
+  VMX_LAUNCH(c, k_perm_rank, nblocks(nbuckets, 128), 128, 0, off.as<uint32_t>(), nbuckets, keys.as<PermKey>(),
+             nbytes > 8 ? 1 : 0, table.as<uint32_t>(), c->d_flag);
+  VMX_CHECK_LAUNCH();
+  VMX_TRY(read_flags(c, 1));
+  if (c->h_flag[0]) { *fallback = 1; return VMX_OK; }
+  VMX_CU(cudaMemcpyAsync(table_out, table.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  VMX_CU(cudaStreamSynchronize(c->stream));
+  return VMX_OK;
+}
+
+int vmx_permutation_prg_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64_t offset, size_t n, size_t nbytes,
+                               unsigned bits, uint32_t* table_out, int* fallback) {
+  VMX_ENTER(c);
+  if (!fallback || (n && !table_out) || !nbytes || bits > 8 * nbytes || bits + 7 < 8 * nbytes || !bits) {
+    set_error("permutation: bad key width");
+    return VMX_EARG;
+  }
+  DevBuf raw;
+  const uint8_t* data = nullptr;
+  VMX_TRY(prg_bytes_dev(c, seed, seedlen, offset, n * nbytes, raw, &data));
+  return permutation_dev(c, data, n, nbytes, bits, table_out, fallback);
+}
+
+int vmx_permutation_from_raw(vmx_ctx* c, size_t n, const uint8_t* be, size_t nbytes, unsigned bits, uint32_t* table_out,
+                             int* fallback) {
+  VMX_ENTER(c);
+  if (!fallback || (n && (!table_out || !be)) || !nbytes || bits > 8 * nbytes || bits + 7 < 8 * nbytes || !bits) {
+    set_error("permutation: bad key width");
+    return VMX_EARG;
+  }
+  DevBuf raw;
+  VMX_TRY(raw.alloc(c, n * nbytes));
+  if (n) VMX_CU(cudaMemcpyAsync(raw.p, be, n * nbytes, cudaMemcpyHostToDevice, c->stream));
+  return permutation_dev(c, raw.as<uint8_t>(), n, nbytes, bits, table_out, fallback);
+}
+
 int vmx_garr_from_candidates(vmx_ctx* c, size_t m, const uint8_t* be, size_t width, unsigned bitlen, size_t n_want,
                              vmx_garr** out, size_t* used) {
   if (!out || !used) return VMX_EARG;

@@ -10,6 +10,12 @@ struct LimbBuf : DevBuf {  // limb-major temporary with an explicit limb count
 };
 constexpr int kAffLimbs = 16, kJacLimbs = 24;
 static inline unsigned ec_blocks(size_t n) { return nblocks(n, kEcThreads); }
+// kernels are instantiated per reduction (P-256 shift-add / generic Montgomery): pick the context's
+#define VMX_EC_LAUNCH(c, kernel, grid, block, smem, ...)                                   \
+  do {                                                                                     \
+    if ((c)->ecc.F.solinas) VMX_LAUNCH(c, kernel<true>, grid, block, smem, __VA_ARGS__);   \
+    else VMX_LAUNCH(c, kernel<false>, grid, block, smem, __VA_ARGS__);                     \
+  } while (0)
 
 // field multiplications per point operation (accounting only)
 constexpr uint64_t kMulMadd = 11, kMulAdd = 16, kMulDbl = 8, kMulNorm = 11;
@@ -21,7 +27,7 @@ static int ec_batch_inv(vmx_ctx* c, const uint32_t* in, size_t icap, size_t n, u
   const size_t per = (size_t)kEcThreads * kInvK;
   if (n > 32) {
     if (n <= per) {
-      VMX_LAUNCH(c, k_fp_inv_block, 1, kEcThreads, 0, in, icap, n, out, ocap, c->ecc);
+      VMX_EC_LAUNCH(c, k_fp_inv_block, 1, kEcThreads, 0, in, icap, n, out, ocap, c->ecc);
       VMX_CHECK_LAUNCH();
       c->modmuls += 7 * n + 400;
       return VMX_OK;
@@ -31,17 +37,17 @@ static int ec_batch_inv(vmx_ctx* c, const uint32_t* in, size_t icap, size_t n, u
     VMX_TRY(excl.alloc_limbs(c, nb * kEcThreads, 8));
     VMX_TRY(totals.alloc_limbs(c, nb, 8));
     VMX_TRY(totals_inv.alloc_limbs(c, nb, 8));
-    VMX_LAUNCH(c, k_fp_inv_up, nb, kEcThreads, 0, in, icap, n, excl.d(), excl.cap, totals.d(), totals.cap, c->ecc);
+    VMX_EC_LAUNCH(c, k_fp_inv_up, nb, kEcThreads, 0, in, icap, n, excl.d(), excl.cap, totals.d(), totals.cap, c->ecc);
     VMX_CHECK_LAUNCH();
     VMX_TRY(ec_batch_inv(c, totals.d(), totals.cap, nb, totals_inv.d(), totals_inv.cap));
-    VMX_LAUNCH(c, k_fp_inv_down, nb, kEcThreads, 0, in, icap, n, excl.d(), excl.cap, totals_inv.d(), totals_inv.cap, out,
+    VMX_EC_LAUNCH(c, k_fp_inv_down, nb, kEcThreads, 0, in, icap, n, excl.d(), excl.cap, totals_inv.d(), totals_inv.cap, out,
                ocap, c->ecc);
     VMX_CHECK_LAUNCH();
     c->modmuls += 7 * n;
     return VMX_OK;
   }
 #endif
-  VMX_LAUNCH(c, k_fp_inv_each, ec_blocks(n), kEcThreads, 0, in, icap, n, out, ocap, c->ecc);
+  VMX_EC_LAUNCH(c, k_fp_inv_each, ec_blocks(n), kEcThreads, 0, in, icap, n, out, ocap, c->ecc);
   VMX_CHECK_LAUNCH();
   c->modmuls += 384 * n;
   return VMX_OK;
@@ -54,7 +60,7 @@ static int ec_normalize(vmx_ctx* c, const uint32_t* jac, size_t jcap, size_t n, 
   LimbBuf zinv;
   VMX_TRY(zinv.alloc_limbs(c, n, 8));
   VMX_TRY(ec_batch_inv(c, jac + 16 * jcap, jcap, n, zinv.d(), zinv.cap));
-  VMX_LAUNCH(c, k_ec_finish, ec_blocks(n), kEcThreads, 0, jac, jcap, zinv.d(), zinv.cap, n, out, ocap, dst_off, tw, tj,
+  VMX_EC_LAUNCH(c, k_ec_finish, ec_blocks(n), kEcThreads, 0, jac, jcap, zinv.d(), zinv.cap, n, out, ocap, dst_off, tw, tj,
              c->ecc);
   VMX_CHECK_LAUNCH();
   c->modmuls += 4 * n;
@@ -81,7 +87,7 @@ static int ec_import_dev(vmx_ctx* c, size_t n, const uint8_t* d_raw, int hdr, ui
   const uint8_t* ry = hdr ? d_raw + 5 + n * (5 + cb) + 10 : d_raw + cb;
   const size_t stride = hdr ? 5 + cb : 2 * cb;
   VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
-  VMX_LAUNCH(c, k_ec_from_bytes, ec_blocks(n), kEcThreads, 0, rx, ry, stride, n, (int)cb, hdr, out, ocap, c->d_flag, c->ecc);
+  VMX_EC_LAUNCH(c, k_ec_from_bytes, ec_blocks(n), kEcThreads, 0, rx, ry, stride, n, (int)cb, hdr, out, ocap, c->d_flag, c->ecc);
   VMX_CHECK_LAUNCH();
   c->modmuls += 6 * n;
   VMX_TRY(read_flags(c, 1));
@@ -124,7 +130,7 @@ static int ec_export(const vmx_garr* a, int hdr, uint8_t* be_out) {
   uint8_t* rx = hdr ? raw.as<uint8_t>() + 10 : raw.as<uint8_t>();
   uint8_t* ry = hdr ? raw.as<uint8_t>() + 5 + n * (5 + cb) + 10 : raw.as<uint8_t>() + cb;
   const size_t stride = hdr ? 5 + cb : 2 * cb;
-  VMX_LAUNCH(c, k_ec_to_bytes, ec_blocks(n), kEcThreads, 0, a->d, a->cap, n, (int)cb, hdr, rx, ry, stride, c->ecc);
+  VMX_EC_LAUNCH(c, k_ec_to_bytes, ec_blocks(n), kEcThreads, 0, a->d, a->cap, n, (int)cb, hdr, rx, ry, stride, c->ecc);
   VMX_CHECK_LAUNCH();
   c->modmuls += 2 * n;
   if (hdr) {  // the two node headers are host-written: copy the leaf runs only
@@ -150,7 +156,7 @@ static int ec_upload_one(vmx_ctx* c, const uint8_t* be, ElemBuf& buf) {
 static int ec_download_one(vmx_ctx* c, const uint32_t* d, size_t cap, size_t idx, uint8_t* out_be) {
   DevBuf raw;
   VMX_TRY(raw.alloc(c, 2 * c->cb));
-  VMX_LAUNCH(c, k_ec_to_bytes, 1, kEcThreads, 0, d + 4 * idx, cap, (size_t)1, (int)c->cb, 0, raw.as<uint8_t>(),
+  VMX_EC_LAUNCH(c, k_ec_to_bytes, 1, kEcThreads, 0, d + 4 * idx, cap, (size_t)1, (int)c->cb, 0, raw.as<uint8_t>(),
              raw.as<uint8_t>() + c->cb, 2 * c->cb, c->ecc);
   VMX_CHECK_LAUNCH();
   VMX_CU(cudaMemcpyAsync(out_be, raw.p, 2 * c->cb, cudaMemcpyDeviceToHost, c->stream));
@@ -194,7 +200,7 @@ static int ec_build_table(vmx_ctx* c, const uint32_t* base, size_t bcap, int w, 
   LimbBuf Qj, Q;
   VMX_TRY(Qj.alloc_limbs(c, qlen, kJacLimbs));
   VMX_TRY(Q.alloc_limbs(c, qlen, kAffLimbs));
-  VMX_LAUNCH(c, k_ec_dbl_chain, 1, 32, 0, base, bcap, Qj.d(), Qj.cap, qlen, c->ecc);
+  VMX_EC_LAUNCH(c, k_ec_dbl_chain, 1, 32, 0, base, bcap, Qj.d(), Qj.cap, qlen, c->ecc);
   VMX_CHECK_LAUNCH();
   c->modmuls += kMulDbl * qlen;
   VMX_TRY(ec_normalize(c, Qj.d(), Qj.cap, qlen, Q.d(), Q.cap));
@@ -202,7 +208,7 @@ static int ec_build_table(vmx_ctx* c, const uint32_t* base, size_t bcap, int w, 
   VMX_TRY(lvl.alloc_limbs(c, (size_t)T.nwin << (w - 1), kJacLimbs));
   for (int j = 0; j < w; j++) {
     const size_t items = (size_t)T.nwin << j;
-    VMX_LAUNCH(c, k_ec_table_level, ec_blocks(items), kEcThreads, 0, T.d, T.cap, w, T.nwin, j, qlen, Q.d(), Q.cap,
+    VMX_EC_LAUNCH(c, k_ec_table_level, ec_blocks(items), kEcThreads, 0, T.d, T.cap, w, T.nwin, j, qlen, Q.d(), Q.cap,
                lvl.d(), lvl.cap, c->ecc);
     VMX_CHECK_LAUNCH();
     c->modmuls += kMulMadd * items;
@@ -217,7 +223,7 @@ static int ec_exp_fixed_run(vmx_ctx* c, const FixedTable& T, const vmx_rarr* e, 
   const int nwin = std::min(T.nwin, std::max(1, (ebits + T.w - 1) / T.w));
   LimbBuf jac;
   VMX_TRY(jac.alloc_limbs(c, n, kJacLimbs));
-  VMX_LAUNCH(c, k_ec_exp_fixed, ec_blocks(n), kEcThreads, 0, T.d, T.cap, T.w, nwin, e->d, e->cap, n, jac.d(), jac.cap,
+  VMX_EC_LAUNCH(c, k_ec_exp_fixed, ec_blocks(n), kEcThreads, 0, T.d, T.cap, T.w, nwin, e->d, e->cap, n, jac.d(), jac.cap,
              c->ecc);
   VMX_CHECK_LAUNCH();
   c->modmuls += kMulMadd * n * nwin;
@@ -236,7 +242,7 @@ static int ec_exp_var_run(vmx_ctx* c, const uint32_t* a, size_t acap, const uint
   const int nwin = (ebits + 3) / 4;
   for (size_t i0 = 0; i0 < n; i0 += chunk) {
     const size_t m = std::min(chunk, n - i0);
-    VMX_LAUNCH(c, k_ec_exp_var, ec_blocks(m), kEcThreads, 0, a + 4 * i0, acap, escalar ? E : E + 4 * i0, ecap,
+    VMX_EC_LAUNCH(c, k_ec_exp_var, ec_blocks(m), kEcThreads, 0, a + 4 * i0, acap, escalar ? E : E + 4 * i0, ecap,
                escalar ? 1 : 0, ebits, m, tab.d(), tab.cap, jac.d() + 4 * i0, jac.cap, c->ecc);
     VMX_CHECK_LAUNCH();
     c->modmuls += (uint64_t)m * (14 * kMulMadd + (uint64_t)nwin * (4 * kMulDbl + kMulAdd));
@@ -275,14 +281,14 @@ static int ec_seg_sum(vmx_ctx* c, const uint32_t* V, size_t vcap, int vjac, cons
     const uint32_t* nch_dev = chunk_off.as<uint32_t>() + nseg;
     c->modmuls += (cur_jac ? kMulAdd : kMulMadd) * cur_total;
     if (last) {
-      VMX_LAUNCH(c, k_ec_seg_sum, ec_blocks(nseg), kEcThreads, 0, cur_V, cur_vcap, cur_jac, cur_idx, chunks.as<Chunk>(),
+      VMX_EC_LAUNCH(c, k_ec_seg_sum, ec_blocks(nseg), kEcThreads, 0, cur_V, cur_vcap, cur_jac, cur_idx, chunks.as<Chunk>(),
                  nch_dev, out, ocap, c->ecc);
       VMX_CHECK_LAUNCH();
       return VMX_OK;
     }
     LimbBuf part;
     VMX_TRY(part.alloc_limbs(c, nch_bound, kJacLimbs));
-    VMX_LAUNCH(c, k_ec_seg_sum, ec_blocks(nch_bound), kEcThreads, 0, cur_V, cur_vcap, cur_jac, cur_idx,
+    VMX_EC_LAUNCH(c, k_ec_seg_sum, ec_blocks(nch_bound), kEcThreads, 0, cur_V, cur_vcap, cur_jac, cur_idx,
                chunks.as<Chunk>(), nch_dev, part.d(), part.cap, c->ecc);
     VMX_CHECK_LAUNCH();
     std::swap(val_keep.p, part.p); std::swap(val_keep.c, part.c); std::swap(val_keep.cap, part.cap);
@@ -310,7 +316,7 @@ static int ec_mexp_run(vmx_ctx* c, const MexpPlan& P, const vmx_garr* a, size_t 
   VMX_TRY(ec_seg_sum(c, buckets.d(), buckets.cap, 1, P.idx2.as<uint32_t>(), P.seg2_off.as<uint32_t>(), P.nseg2, P.total2,
                      8, X.d(), X.cap));
   const size_t ngroups = (size_t)P.W * P.J;
-  VMX_LAUNCH(c, k_ec_weighted_small, ec_blocks(ngroups), kEcThreads, 0, X.d(), X.cap, ngroups, Y + 4 * col * ngroups,
+  VMX_EC_LAUNCH(c, k_ec_weighted_small, ec_blocks(ngroups), kEcThreads, 0, X.d(), X.cap, ngroups, Y + 4 * col * ngroups,
              ycap, c->ecc);
   VMX_CHECK_LAUNCH();
   c->modmuls += ngroups * 30 * kMulAdd;
@@ -332,7 +338,7 @@ static int ec_expprod(vmx_ctx* c, const vmx_garr* const* a, size_t k, const vmx_
     VMX_TRY(Y.alloc_limbs(c, k * ngroups, kJacLimbs));
     for (size_t l = 0; l < k; l++) VMX_TRY(ec_mexp_run(c, P, a[l], e->n, Y.d(), Y.cap, l));
     VMX_TRY(R.alloc_limbs(c, k, kJacLimbs));
-    VMX_LAUNCH(c, k_ec_horner, nblocks(k, 32), 32, 0, Y.d(), Y.cap, (int)ngroups, (int)k, R.d(), R.cap, c->ecc);
+    VMX_EC_LAUNCH(c, k_ec_horner, nblocks(k, 32), 32, 0, Y.d(), Y.cap, (int)ngroups, (int)k, R.d(), R.cap, c->ecc);
     VMX_CHECK_LAUNCH();
     c->modmuls += k * ngroups * (4 * kMulDbl + kMulAdd);
     VMX_TRY(ec_normalize(c, R.d(), R.cap, k, res.d(), res.cap));
@@ -361,7 +367,7 @@ static int ec_mul(vmx_ctx* c, const vmx_garr* a, const vmx_garr* b, vmx_garr* r)
   if (!a->n) return VMX_OK;
   LimbBuf jac;
   VMX_TRY(jac.alloc_limbs(c, a->n, kJacLimbs));
-  VMX_LAUNCH(c, k_ec_add, ec_blocks(a->n), kEcThreads, 0, a->d, a->cap, b->d, b->cap, a->n, jac.d(), jac.cap, c->ecc);
+  VMX_EC_LAUNCH(c, k_ec_add, ec_blocks(a->n), kEcThreads, 0, a->d, a->cap, b->d, b->cap, a->n, jac.d(), jac.cap, c->ecc);
   VMX_CHECK_LAUNCH();
   c->modmuls += kMulMadd * a->n;
   return ec_normalize(c, jac.d(), jac.cap, a->n, r->d, r->cap);
@@ -369,7 +375,7 @@ static int ec_mul(vmx_ctx* c, const vmx_garr* a, const vmx_garr* b, vmx_garr* r)
 
 static int ec_neg(vmx_ctx* c, const vmx_garr* a, vmx_garr* r) {
   if (!a->n) return VMX_OK;
-  VMX_LAUNCH(c, k_ec_neg, ec_blocks(a->n), kEcThreads, 0, a->d, a->cap, a->n, r->d, r->cap, c->ecc);
+  VMX_EC_LAUNCH(c, k_ec_neg, ec_blocks(a->n), kEcThreads, 0, a->d, a->cap, a->n, r->d, r->cap, c->ecc);
   VMX_CHECK_LAUNCH();
   return VMX_OK;
 }
@@ -393,7 +399,7 @@ static int ec_cols(vmx_ctx* c, const vmx_garr* const* bases, size_t t, const int
   }
   LimbBuf jac;
   VMX_TRY(jac.alloc_limbs(c, n, kJacLimbs));
-  VMX_LAUNCH(c, k_ec_cols, ec_blocks(n), kEcThreads, 0, A, n, jac.d(), jac.cap, c->ecc);
+  VMX_EC_LAUNCH(c, k_ec_cols, ec_blocks(n), kEcThreads, 0, A, n, jac.d(), jac.cap, c->ecc);
   VMX_CHECK_LAUNCH();
   c->modmuls += work * n;
   return ec_normalize(c, jac.d(), jac.cap, n, r->d, r->cap);
@@ -438,7 +444,7 @@ static int ec_candidates(vmx_ctx* c, const uint8_t* d_raw, size_t m, size_t widt
              c->P.consts, 1, c->P.params<8>());
   VMX_CHECK_LAUNCH();
   VMX_CU(cudaMemsetAsync(ok.p, 0, (m + 1) * 4, c->stream));
-  VMX_LAUNCH(c, k_ec_candidates, ec_blocks(m), kEcThreads, 0, xs.d(), xs.cap, m, cand.d(), cand.cap, ok.as<uint32_t>(),
+  VMX_EC_LAUNCH(c, k_ec_candidates, ec_blocks(m), kEcThreads, 0, xs.d(), xs.cap, m, cand.d(), cand.cap, ok.as<uint32_t>(),
              c->ecc);
   VMX_CHECK_LAUNCH();
   c->modmuls += 400 * m;

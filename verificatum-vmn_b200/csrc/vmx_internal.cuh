@@ -16,6 +16,7 @@
 #include "kernels_member.cuh"
 #include "kernels_mexp.cuh"
 #include "kernels_prg.cuh"
+#include "kernels_perm.cuh"
 #include "kernels_ring.cuh"
 #include "scan.cuh"
 
