@@ -113,6 +113,9 @@ VMX_DEV void fp_sqr_wide(uint32_t (&t)[16], const uint32_t (&a)[8]) {
 // r = t / 2^256 mod n (Montgomery reduction of a 16-word value < n * 2^256), fully reduced.
 // SOL (compile time): n is the P-256 prime.  Kernels are instantiated for both so that a curve context
 // carries only the reduction it uses (the straight-line code of one point addition is ~50 KB of SASS).
+// The P-256 prime, for the instantiations that know it at compile time (immediates instead of loads).
+VMX_DEV uint32_t p256_word(int j) { return j < 3 ? 0xffffffffu : j < 6 ? 0u : j == 6 ? 1u : 0xffffffffu; }
+
 template <bool SOL>
 VMX_DEV void fp_redc(uint32_t (&r)[8], uint32_t (&t)[16], const Fp256& F) {
   uint32_t extra = 0;  // pending carry into column i+9
@@ -148,27 +151,68 @@ VMX_DEV void fp_redc(uint32_t (&r)[8], uint32_t (&t)[16], const Fp256& F) {
   }
   // value = t[8..15] + extra * 2^256 < 2n
   uint32_t d[8], brw;
-  sub_cc(d[0], t[8], F.n[0]);
+  sub_cc(d[0], t[8], SOL ? p256_word(0) : F.n[0]);
 #pragma unroll
-  for (int j = 1; j < 8; j++) subc_cc(d[j], t[8 + j], F.n[j]);
+  for (int j = 1; j < 8; j++) subc_cc(d[j], t[8 + j], SOL ? p256_word(j) : F.n[j]);
   subc(brw, extra, 0);
   const bool keep = (brw != 0);  // borrow out of the 9-word subtraction: value < n
 #pragma unroll
   for (int j = 0; j < 8; j++) r[j] = keep ? t[8 + j] : d[j];
 }
 
-// r = a * b * 2^-256 mod n.  r may alias a or b.
+// r = a * b * 2^-256 mod n, expanded in place (the exponent-ring kernels, a few multiplications per thread).
 template <bool SOL>
-VMX_DEV void fp_mul(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8], const Fp256& F) {
+VMX_DEV void fp_mul_inline(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8], const Fp256& F) {
   uint32_t t[16];
   fp_mul_wide(t, a, b);
   fp_redc<SOL>(r, t, F);
 }
+
+// The curve kernels CALL their field multiplication: one point addition is 16 multiplications, i.e. ~55 KB
+// of SASS when expanded in place, and the loop of a scalar multiplication then runs out of the 32 KB
+// instruction cache (measured: 2.9 "no instruction" stall cycles per issued instruction, profiles/).  Operands
+// and result travel in registers (a 32-byte struct by value: R4.. in the device ABI; no local memory); the
+// 3.5 KB body stays resident in the instruction caches.
+struct F8 { uint32_t v[8]; };
+#ifndef VMX_HOST_EMUL
+#define VMX_FN __device__ __noinline__
+#else
+#define VMX_FN inline
+#endif
+template <bool SOL>
+VMX_FN F8 fp_mul_fn(F8 a, F8 b, const Fp256* F) {
+  uint32_t t[16];
+  fp_mul_wide(t, a.v, b.v);
+  F8 r;
+  fp_redc<SOL>(r.v, t, *F);
+  return r;
+}
+template <bool SOL>
+VMX_FN F8 fp_sqr_fn(F8 a, const Fp256* F) {
+  uint32_t t[16];
+  fp_sqr_wide(t, a.v);
+  F8 r;
+  fp_redc<SOL>(r.v, t, *F);
+  return r;
+}
+// r = a * b * 2^-256 mod n.  r may alias a or b.
+template <bool SOL>
+VMX_DEV void fp_mul(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8], const Fp256& F) {
+  F8 A, B;
+#pragma unroll
+  for (int j = 0; j < 8; j++) { A.v[j] = a[j]; B.v[j] = b[j]; }
+  const F8 R = fp_mul_fn<SOL>(A, B, &F);
+#pragma unroll
+  for (int j = 0; j < 8; j++) r[j] = R.v[j];
+}
 template <bool SOL>
 VMX_DEV void fp_sqr(uint32_t (&r)[8], const uint32_t (&a)[8], const Fp256& F) {
-  uint32_t t[16];
-  fp_sqr_wide(t, a);
-  fp_redc<SOL>(r, t, F);
+  F8 A;
+#pragma unroll
+  for (int j = 0; j < 8; j++) A.v[j] = a[j];
+  const F8 R = fp_sqr_fn<SOL>(A, &F);
+#pragma unroll
+  for (int j = 0; j < 8; j++) r[j] = R.v[j];
 }
 
 // r = a + b mod n (a, b < n)

@@ -154,7 +154,7 @@ VMX_DEV void mont_mul(uint32_t (&a)[N], Loader ld2, const MontParams<N>& M) {
     for (int i = 0; i < 8; i++) F.n[i] = M.n[i];
     F.n0inv = M.n0inv;
     F.solinas = 0;
-    fp_mul<false>(a, a, b, F);
+    fp_mul_inline<false>(a, a, b, F);
     return;
   } else {
   uint64_t T[N / 2 + 1];
