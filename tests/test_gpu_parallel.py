@@ -20,7 +20,7 @@ def _free_port() -> int:
     return port
 
 
-@pytest.mark.parametrize("bits,n", [(512, 3000), (3072, 20000)])
+@pytest.mark.parametrize("bits,n", [(512, 3000), (3072, 20000), ("P-256", 50000)])
 def test_nccl_sharded_equals_single(bits, n):
     import torch
     ngpu = torch.cuda.device_count()
