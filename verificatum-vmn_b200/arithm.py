@@ -142,9 +142,13 @@ class Permutation:
         return int(self.table[i])
 
     def inv(self) -> "Permutation":
-        inv = np.empty_like(self.table)
-        inv[self.table] = np.arange(self.table.shape[0], dtype=np.uint32)
-        return Permutation(inv)
+        """The inverse table (kept: the protocols ask for it several times per proof, hvzk/PoSBasicTW.java:552)."""
+        if getattr(self, "_inv", None) is None:
+            inv = np.empty_like(self.table)
+            inv[self.table] = np.arange(self.table.shape[0], dtype=np.uint32)
+            self._inv = Permutation(inv)
+            self._inv._inv = self
+        return self._inv
 
     def shrink(self, size: int) -> "Permutation":
         """Permutation.shrink (mixnet/PermutationCommitment.java:426): the restriction to the first

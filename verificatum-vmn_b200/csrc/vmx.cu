@@ -364,22 +364,28 @@ static size_t wave_threads(const vmx_ctx* c) {
 }
 
 // ------------------------------------------------------------------ fixed-base tables
+// Window width of a fixed-base table for arrays of n exponents.  A table is built once per base and serves
+// every later array (the bases of a mix-net session are g, h0 and the public key components: 8 fixed-base
+// arrays per shuffle, mixnet/ShufflerElGamalSession.java:407, hvzk/PoSBasicTW.java:447,606-646,1030), so
+// the 2^w entries per window are weighed against kReuse arrays of n products.  Memory bound: 10 GB per
+// table (w = 17 at 3072 bits: 181 windows x 131,072 x 384 B = 9.1 GB of the 180 GB).
+constexpr double kFixedReuse = 8.0;
+static double fixed_cost(int w, size_t n, int ebits) {
+  const double nwin = (ebits + w - 1) / w;
+  return nwin * (kFixedReuse * (double)n + (double)(1u << w));
+}
 static int choose_fixed_window(const vmx_ctx* c, size_t n, int ebits) {
   if (c->fixed_window) return c->fixed_window;
   double best = 1e300;
   int bw = 4;
-  for (int w = 4; w <= 16; w++) {
+  for (int w = 4; w <= 18; w++) {
     const double nwin = (ebits + w - 1) / w;
     const double entries = nwin * (double)(1u << w);
-    if (entries * c->nl * 4 > 8e9) break;
-    const double cost = nwin * (3.0 * (double)n + (double)(1u << w));
+    if (entries * c->nl * 4 > 10e9) break;
+    const double cost = fixed_cost(w, n, ebits);
     if (cost < best) { best = cost; bw = w; }
   }
   return bw;
-}
-static double fixed_cost(int w, size_t n, int ebits) {
-  const double nwin = (ebits + w - 1) / w;
-  return nwin * (3.0 * (double)n + (double)(1u << w));
 }
 
 template <int N>
@@ -431,7 +437,8 @@ static int get_table(vmx_ctx* c, const uint8_t* base_be, size_t n, FixedTable* o
   if (it != c->tables.end()) {
     const double have = ec ? ec_fixed_cost(it->second.w, n, ebits) : fixed_cost(it->second.w, n, ebits);
     const double want = ec ? ec_fixed_cost(wbest, n, ebits) : fixed_cost(wbest, n, ebits);
-    if (have <= 1.3 * want) { *out = it->second; return VMX_OK; }
+    // a wider table than this array size asks for is never slower to USE: keep it; rebuild only to widen
+    if (it->second.w >= wbest || have <= 1.3 * want) { *out = it->second; return VMX_OK; }
     cudaFreeAsync(it->second.d, c->stream);
     c->tables.erase(it);
   }
@@ -594,6 +601,14 @@ static int mexp_plan(vmx_ctx* c, const vmx_rarr* e, int L, MexpPlan& P) {
   return VMX_OK;
 }
 
+// Terms per thread in the bucket accumulation.  The threads of a warp finish together with the longest chunk
+// among them, so short chunks (a bucket of ~24 terms cut in 3 x 8) keep the lanes balanced at the price of a
+// second, much smaller round over the partial products.
+static int mexp_chunk() {
+  static const int k = [] { const char* e = std::getenv("VMX_MEXP_K"); const int v = e ? std::atoi(e) : 0; return v >= 2 ? v : 8; }();
+  return k;
+}
+
 // result element written to out[oidx] (Montgomery form)
 template <int N>
 static int mexp_run(vmx_ctx* c, const MexpPlan& P, const vmx_garr* a, size_t n_terms, uint32_t* out, size_t ocap,
@@ -602,7 +617,7 @@ static int mexp_run(vmx_ctx* c, const MexpPlan& P, const vmx_garr* a, size_t n_t
   ElemBuf buckets, X, Y, R;
   VMX_TRY(buckets.alloc_elems(c, P.nb));
   VMX_TRY(seg_product<N>(c, c->P, a->d, a->cap, P.idx.as<uint32_t>(), P.seg_off.as<uint32_t>(), P.nb,
-                         n_terms * (size_t)P.W, 32, buckets.d(), buckets.cap));
+                         n_terms * (size_t)P.W, mexp_chunk(), buckets.d(), buckets.cap));
   VMX_TRY(X.alloc_elems(c, P.nseg2));
   VMX_TRY(seg_product<N>(c, c->P, buckets.d(), buckets.cap, P.idx2.as<uint32_t>(), P.seg2_off.as<uint32_t>(),
                          P.nseg2, P.total2, 8, X.d(), X.cap));
@@ -969,7 +984,7 @@ int vmx_ctx_sync(vmx_ctx* c) {
 }
 void* vmx_ctx_stream(vmx_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int vmx_ctx_set_fixed_window(vmx_ctx* c, int w) {
-  if (!c || w < 0 || w > 16) return VMX_EARG;
+  if (!c || w < 0 || w > 22) return VMX_EARG;
   c->fixed_window = w;
   return VMX_OK;
 }

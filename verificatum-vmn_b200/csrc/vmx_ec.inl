@@ -165,21 +165,24 @@ static int ec_download_one(vmx_ctx* c, const uint32_t* d, size_t cap, size_t idx
 }
 
 // ------------------------------------------------------------------ fixed base
+// an entry is 64 B and costs one mixed addition + its share of the batched inversion to build: wide windows
+// are cheap (w = 20 at n = 10^6: 13 windows x 2^20 x 64 B = 872 MB, built in a few ms, 13 additions per point)
+static double ec_fixed_cost(int w, size_t n, int ebits) {
+  const double nwin = (ebits + w - 1) / w;
+  return nwin * (kFixedReuse * (double)kMulMadd * (double)n + 2.0 * kMulMadd * (double)(1u << w));
+}
 static int ec_choose_fixed_window(const vmx_ctx* c, size_t n) {
   if (c->fixed_window) return c->fixed_window;
   const int ebits = c->Q.bits;
   double best = 1e300;
   int bw = 4;
-  for (int w = 4; w <= 16; w++) {
+  for (int w = 4; w <= 22; w++) {
     const double nwin = (ebits + w - 1) / w;
-    const double cost = nwin * ((double)kMulMadd * (double)n + 2.0 * kMulMadd * (double)(1u << w));
+    if (nwin * (double)(1u << w) * kAffLimbs * 4 > 4e9) break;
+    const double cost = ec_fixed_cost(w, n, ebits);
     if (cost < best) { best = cost; bw = w; }
   }
   return bw;
-}
-static double ec_fixed_cost(int w, size_t n, int ebits) {
-  const double nwin = (ebits + w - 1) / w;
-  return nwin * ((double)kMulMadd * (double)n + 2.0 * kMulMadd * (double)(1u << w));
 }
 
 static int ec_build_table(vmx_ctx* c, const uint32_t* base, size_t bcap, int w, FixedTable& T) {
@@ -310,8 +313,8 @@ static int ec_mexp_run(vmx_ctx* c, const MexpPlan& P, const vmx_garr* a, size_t 
                        size_t col) {
   LimbBuf buckets, X;
   VMX_TRY(buckets.alloc_limbs(c, P.nb, kJacLimbs));
-  VMX_TRY(ec_seg_sum(c, a->d, a->cap, 0, P.idx.as<uint32_t>(), P.seg_off.as<uint32_t>(), P.nb, n_terms * (size_t)P.W, 32,
-                     buckets.d(), buckets.cap));
+  VMX_TRY(ec_seg_sum(c, a->d, a->cap, 0, P.idx.as<uint32_t>(), P.seg_off.as<uint32_t>(), P.nb, n_terms * (size_t)P.W,
+                     mexp_chunk(), buckets.d(), buckets.cap));
   VMX_TRY(X.alloc_limbs(c, P.nseg2, kJacLimbs));
   VMX_TRY(ec_seg_sum(c, buckets.d(), buckets.cap, 1, P.idx2.as<uint32_t>(), P.seg2_off.as<uint32_t>(), P.nseg2, P.total2,
                      8, X.d(), X.cap));

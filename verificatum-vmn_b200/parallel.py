@@ -627,16 +627,21 @@ def _sharded_permute(arr, pi: Permutation, ring: bool):
         raise nat.VmxError(nat.VMX_ESIZE, "permutation of the wrong size")
     b = np.asarray(arr.bounds, dtype=np.int64)
     lo, hi = arr.lo, arr.hi
-    dest = tbl[lo:hi].astype(np.int64)
-    dest_rank = np.searchsorted(b[1:], dest, side="right")
-    order = np.argsort(dest_rank, kind="stable").astype(np.uint32)
-    send_counts = np.bincount(dest_rank, minlength=comm.world).astype(np.int64)
-    dst_lists = []
-    for s in range(comm.world):
-        seg = tbl[b[s]:b[s + 1]].astype(np.int64)
-        dst_lists.append(seg[(seg >= lo) & (seg < hi)] - lo)
-    recv_counts = np.array([len(x) for x in dst_lists], dtype=np.int64)
-    dst_idx = np.ascontiguousarray(np.concatenate(dst_lists).astype(np.uint32)) if dst_lists else np.zeros(0, np.uint32)
+    # the routing plan depends on the table and the shard bounds only: one permutation moves several arrays
+    # (both ciphertext components, the commitment, the batching vector), so it is kept on the Permutation
+    plans = pi.__dict__.setdefault("_shard_plans", {})
+    key = (arr.gsize, comm.rank, comm.world)
+    if key not in plans:
+        dest = tbl[lo:hi]
+        dest_rank = (np.searchsorted(b[1:], dest, side="right")).astype(np.int32)
+        order = np.argsort(dest_rank, kind="stable").astype(np.uint32)
+        send_counts = np.bincount(dest_rank, minlength=comm.world).astype(np.int64)
+        mine = np.flatnonzero((tbl >= lo) & (tbl < hi))          # global sources landing here, in source order
+        src_rank = np.searchsorted(b[1:], mine, side="right")
+        recv_counts = np.bincount(src_rank, minlength=comm.world).astype(np.int64)
+        dst_idx = np.ascontiguousarray((tbl[mine].astype(np.int64) - lo).astype(np.uint32))
+        plans[key] = (order, send_counts, recv_counts, dst_idx)
+    order, send_counts, recv_counts, dst_idx = plans[key]
     pack = lib.vmx_rarr_pack_rows if ring else lib.vmx_garr_pack_rows
     unpack = lib.vmx_rarr_unpack_rows if ring else lib.vmx_garr_unpack_rows
     with comm.on_stream():
