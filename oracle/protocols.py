@@ -23,7 +23,7 @@ from __future__ import annotations
 
 from . import arithm as ar
 from . import bytetree as bt
-from .crypto import PRGHeuristic, RandomOracle
+from .crypto import PRGHeuristic, RandomOracle, SeededRandomSource
 
 import hashlib
 
@@ -777,3 +777,185 @@ def committed_shuffle(G, params: Params, pkey, state: dict, w, rs):
     c, r = ccpos_prove(G, params, G.g, state["h"], state["u"], pkey, w, wp, state["exponents"], state["pi"],
                        state["s"], rs)
     return wp, {"output": ar.array_tree(G, wp).to_bytes(), "commitment": c, "reply": r}
+
+
+# ---------------------------------------------------------------- a whole mix and its verification (vmnv)
+# mixnet/MixNetElGamalSession (shuffling by the first `threshold` parties), elgamal/DistrElGamalSession.java:361-545
+# (decryption), mixnet/MixNetElGamalVerifyFiatShamirSession.java:1318-1668 (verification); file names of the proof
+# directory: mixnet/MixNetElGamalSession.java:381-446, mixnet/ShufflerElGamalSession.java:1077-1101,
+# hvzk/PoSTW.java:281-307, elgamal/DistrElGamalSession.java:553-601, elgamal/DistrElGamal.java:245-255.
+# Key generation is a Shamir sharing in the exponent dealt from `rs` (the DKG is control plane, out of scope);
+# [VCR-mem] PolynomialInExponent.toByteTree() = node of its coefficient elements.
+def _party_source(rs):
+    prg = PRGHeuristic("sha256")
+    seed = rs.get_bytes(prg.min_no_seed_bytes())
+    return SeededRandomSource(seed)
+
+
+def _dec_seed_data(G, g, w, coeffs, f, k):
+    bt_in = bt.node(ar.elem_tree(G, g), ar.array_tree(G, w))
+    pk_bt = bt.node([ar.elem_tree(G, c) for c in coeffs])
+    df_bt = bt.node([ar.array_tree(G, f[l]) for l in range(1, k + 1)])
+    return bt.node(bt_in, bt.node(pk_bt, df_bt))
+
+
+def _eval_in_exponent(G, coeffs, l):
+    acc, power = coeffs[0], 1
+    for c in coeffs[1:]:
+        power *= l
+        acc = G.op_mul(acc, G.op_exp(c, power % G.q))
+    return acc
+
+
+def run_mix(G, params: Params, k: int, threshold: int, w, rs, auxsid="default"):
+    """Returns (proof directory as dict name -> bytes, plaintext elements)."""
+    q = G.q
+    poly = [ar.ring_random_element(G, rs, params.rbitlen) for _ in range(threshold)]
+    xs = {l: sum(a * pow(l, i, q) for i, a in enumerate(poly)) % q for l in range(1, k + 1)}
+    coeffs = [G.op_exp(G.g, a) for a in poly]
+    pk = (G.g, coeffs[0])
+    d = {"version": params.version.encode(), "type": b"mixing", "auxsid": auxsid.encode(), "width": b"1",
+         "FullPublicKey.bt": ar.elem_tree(G, pk).to_bytes(),
+         "proofs/PolynomialInExponent.bt": bt.node([ar.elem_tree(G, c) for c in coeffs]).to_bytes(),
+         "Ciphertexts.bt": ar.array_tree(G, w).to_bytes(), "proofs/activethreshold": str(threshold).encode()}
+    n = ar.size_of(w)
+    h = independent_generators(G, params.rohash, params.prefix(), "generators", n, params.rbitlen)
+    inp = w
+    for l in range(1, threshold + 1):
+        out, proof = shuffle_and_prove(G, params, pk, inp, h, _party_source(rs))
+        d["ShuffledCiphertexts.bt" if l == threshold else "proofs/Ciphertexts%02d.bt" % l] = proof["output"]
+        d["proofs/PermutationCommitment%02d.bt" % l] = proof["permutationCommitment"]
+        d["proofs/PoSCommitment%02d.bt" % l] = proof["commitment"]
+        d["proofs/PoSReply%02d.bt" % l] = proof["reply"]
+        inp = out
+    # decryption
+    u = inp[0]
+    inv_factor = pow(prod_factor(q, k), -1, q)
+    f = {l: decryption_factors(G, u, xs[l], inv_factor) for l in range(1, k + 1)}
+    for l in f:
+        d["proofs/DecryptionFactors%02d.bt" % l] = ar.array_tree(G, f[l]).to_bytes()
+    correct = [False] + [True] * k
+    combined = combine_decryption_factors(G, f, correct, k, threshold)
+    prefix = params.prefix()
+    seed = challenge(params.rohash, prefix, _dec_seed_data(G, G.g, inp, coeffs, f, k),
+                     8 * PRGHeuristic(params.prghash).min_no_seed_bytes())
+    ys = {l: G.op_exp(G.g, xs[l]) for l in xs}
+    parties = {}
+    for l in range(1, k + 1):
+        E = DistrElGamalSessionBasic(G, l, k, threshold, params.ebitlenro, params.rbitlen, params.prghash, G.g, ys, u, xs[l])
+        E.f = f
+        E.set_batch_vector(seed)
+        E.batch_input()
+        d["proofs/DecrFactCommitment%02d.bt" % l] = E.commit(_party_source(rs)).to_bytes()
+        parties[l] = E
+    E1 = parties[1]
+    for l in range(2, k + 1):
+        E1.set_commitment(l, bt.from_bytes(d["proofs/DecrFactCommitment%02d.bt" % l]))
+    cdata = bt.node(bt.leaf(seed), bt.node([E1.commitment_tree(l) for l in range(1, k + 1)]))
+    v = int.from_bytes(challenge(params.rohash, prefix, cdata, params.vbitlenro), "big")
+    for l in range(1, k + 1):
+        d["proofs/DecrFactReply%02d.bt" % l] = parties[l].reply(v).to_bytes()
+    d["proofs/CorrectIndices.bt"] = bt.leaf(bytes(1 if c else 0 for c in correct)).to_bytes()
+    plain = ar.g_mul(G, inp[1], combined)
+    d["Plaintexts.bt"] = ar.array_tree(G, plain).to_bytes()
+    return d, plain
+
+
+class MixVerificationError(Exception):
+    pass
+
+
+def verify_mix(G, params: Params, k: int, threshold: int, d: dict) -> dict:
+    """The verdicts of mixnet/MixNetElGamalVerifyFiatShamirSession.verify for a proof of type "mixing"."""
+    def need(name):
+        if name not in d:
+            raise MixVerificationError("missing " + name)
+        return d[name]
+    if need("version").decode() != params.version or need("type") != b"mixing" or need("width") != b"1":
+        raise MixVerificationError("header")
+    try:
+        pk = ar.parse_elem(G, bt.from_bytes(need("FullPublicKey.bt")), (None, None))
+        t = bt.from_bytes(need("proofs/PolynomialInExponent.bt"))
+        if t.is_leaf() or len(t.children) != threshold:
+            raise ar.FormatError("degree")
+        coeffs = [ar.parse_elem(G, c) for c in t.children]
+    except (ar.FormatError, bt.EIOError):
+        raise MixVerificationError("keys")
+    if pk[0] != G.g or pk[1] != coeffs[0]:
+        raise MixVerificationError("mismatching keys")
+    ys = {l: _eval_in_exponent(G, coeffs, l) for l in range(1, k + 1)}
+    active = int(need("proofs/activethreshold"))
+    if active > k or active < threshold:
+        raise MixVerificationError("active threshold")
+    ct = bt.from_bytes(need("Ciphertexts.bt"))
+    first = ct.children[0]
+    n = len(first.children[0].children) if hasattr(G, "coord_bytes") else len(first.children)
+    try:
+        w = ar.parse_array(G, ct, n, pk)
+    except (ar.FormatError, bt.EIOError):
+        raise MixVerificationError("ciphertexts")
+    h = independent_generators(G, params.rohash, params.prefix(), "generators", n, params.rbitlen)
+    rep = {"shuffles": {}}
+    inp, valid = w, 0
+    for l in range(1, active + 1):
+        name = "proofs/Ciphertexts%02d.bt" % l
+        if l == active and name not in d:
+            name = "ShuffledCiphertexts.bt"
+        proof = {"output": need(name), "permutationCommitment": need("proofs/PermutationCommitment%02d.bt" % l),
+                 "commitment": need("proofs/PoSCommitment%02d.bt" % l), "reply": need("proofs/PoSReply%02d.bt" % l)}
+        try:
+            out = ar.parse_array(G, bt.from_bytes(proof["output"]), n, pk)
+        except (ar.FormatError, bt.EIOError):
+            raise MixVerificationError("output of party %d" % l)
+        ok = verify_shuffle(G, params, pk, inp, h, proof)
+        rep["shuffles"][l] = ok
+        valid += 1 if ok else 0
+        inp = out if ok else inp
+    rep["validProofs"] = valid
+    rep["enoughValidProofs"] = valid >= threshold
+    flags = bt.from_bytes(need("proofs/CorrectIndices.bt"))
+    if not flags.is_leaf() or len(flags.value) != k + 1 or max(flags.value) > 1:
+        raise MixVerificationError("correct indices")
+    correct = [bool(x) for x in flags.value]
+    if sum(correct[1:]) < threshold:
+        raise MixVerificationError("too few correct decryption factors")
+    u = inp[0]
+    try:
+        f = {l: ar.parse_array(G, bt.from_bytes(need("proofs/DecryptionFactors%02d.bt" % l)), n) for l in range(1, k + 1)}
+    except (ar.FormatError, bt.EIOError):
+        raise MixVerificationError("decryption factors")
+    combined = combine_decryption_factors(G, f, correct, k, threshold)
+    prefix = params.prefix()
+    seed = challenge(params.rohash, prefix, _dec_seed_data(G, G.g, inp, coeffs, f, k),
+                     8 * PRGHeuristic(params.prghash).min_no_seed_bytes())
+    V = DistrElGamalSessionBasic(G, 0, k, threshold, params.ebitlenro, params.rbitlen, params.prghash, G.g, ys, u)
+    V.f = f
+    V.set_batch_vector(seed)
+    V.batch_input()
+    V.batch_combined(combined)
+    for l in range(1, k + 1):
+        try:
+            V.set_commitment(l, bt.from_bytes(need("proofs/DecrFactCommitment%02d.bt" % l)))
+        except bt.EIOError:
+            V.set_commitment(l, bt.leaf(b""))
+    cdata = bt.node(bt.leaf(seed), bt.node([V.commitment_tree(l) for l in range(1, k + 1)]))
+    v = int.from_bytes(challenge(params.rohash, prefix, cdata, params.vbitlenro), "big")
+    for l in range(1, k + 1):
+        try:
+            V.set_reply(l, bt.from_bytes(need("proofs/DecrFactReply%02d.bt" % l)))
+        except bt.EIOError:
+            V.set_reply(l, bt.node([]))
+    V.combine(correct)
+    rep["decryption"] = V.verify_combined(pk[1], v)
+    if not rep["decryption"]:
+        raise MixVerificationError("combined proof of decryption")
+    computed = ar.g_mul(G, inp[1], combined)
+    try:
+        plain = ar.parse_array(G, bt.from_bytes(need("Plaintexts.bt")), n)
+    except (ar.FormatError, bt.EIOError):
+        raise MixVerificationError("plaintexts")
+    rep["plaintexts"] = plain == computed
+    if not rep["plaintexts"]:
+        raise MixVerificationError("plaintexts are incorrect")
+    rep["accepted"] = rep["enoughValidProofs"]
+    return rep

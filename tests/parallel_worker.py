@@ -178,6 +178,20 @@ def main():
     f1, f2 = fs(G1), fs(GS)
     assert f1[1:] == (True, True, False, True) and f1 == f2, "sharded shuffle session differs on rank %d" % rank
 
+    # ---- a whole 3-party mix and its vmnv-style verification on shards
+    def whole_mix(Gx):
+        vm = importlib.import_module("verificatum-vmn_b200.vmnv")
+        mix = importlib.import_module("verificatum-vmn_b200.mixnet")
+        params = mix.SessionParams(pGroupString="par-mix")
+        M = vm.MixNetElGamal(Gx, params, 3, 2, rs("mix/dealer"))
+        w = mix.demoCiphertexts(M.fullPublicKey, n, rs("mix/input"))
+        M.run(w)
+        rep = vm.MixNetElGamalVerifyFiatShamirSession(Gx, params, 3, 2).verify(M.nizkp)
+        return dict(M.nizkp), rep
+
+    m1, m2 = whole_mix(G1), whole_mix(GS)
+    assert m1[1]["accepted"] and m1 == m2, "sharded mix differs from the single-process one on rank %d" % rank
+
     stats = (GS.comm.collectives, GS.comm.bytes_exchanged)
     dist.barrier()
     if rank == 0:

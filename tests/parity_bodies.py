@@ -580,3 +580,67 @@ def ec_group_ops(vmx, curve, n):
     assert prg.getBytes(9) == ors.get_bytes(9)
     assert vals(G.randomElementArray(n, prg, 100)) == OG.random_array(n, ors, 100)      # odd stream offset
     assert vals(R.randomElementArray(n, prg, 100)) == oar.ring_random_array(OG, n, ors, 100)
+
+
+def mix_parity(vmx, spec, n, k=3, threshold=2, tmpdir=None):
+    """A whole mix (keys, `threshold` shuffles, threshold decryption with proofs) on the engine and on the
+    oracle from the same seeds: every file of the proof directory is byte-identical; the engine's vmnv
+    (vmnv.MixNetElGamalVerifyFiatShamirSession) and the oracle's accept it, also after a round trip through a
+    directory on disk; corrupted files are rejected by both (BASELINE.json config 3 at test size)."""
+    vm = importlib.import_module("verificatum-vmn_b200.vmnv")
+    mix = importlib.import_module("verificatum-vmn_b200.mixnet")
+    G, OG = engine_group(vmx, spec), oracle_group(spec)
+    params = mix.SessionParams(pGroupString="mix-%s" % spec)
+    oparams = opr.Params(pgroup_string="mix-%s" % spec)
+    rs = vmx.crypto.PRGHeuristic()
+    rs.setSeed(seed("mix/dealer"))
+    M = vm.MixNetElGamal(G, params, k, threshold, rs)
+    irs = vmx.crypto.PRGHeuristic()
+    irs.setSeed(seed("mix/input"))
+    w = mix.demoCiphertexts(M.fullPublicKey, n, irs)
+    plain = M.run(w)
+    # the oracle deals the same keys from the same stream, so the demo ciphertexts coincide
+    probe = SeededRandomSource(seed("mix/dealer"))
+    poly0 = oar.ring_random_element(OG, probe, 100)
+    opk = (OG.g, OG.op_exp(OG.g, poly0))
+    ow = opr.demo_ciphertexts(OG, opk, n, SeededRandomSource(seed("mix/input")))
+    assert col_values(w) == ow
+    od, oplain = opr.run_mix(OG, oparams, k, threshold, ow, SeededRandomSource(seed("mix/dealer")))
+    assert set(od) == set(M.nizkp)
+    for name in sorted(od):
+        assert od[name] == M.nizkp[name], name
+    assert col_values(plain) == oplain
+    # decrypting mixes the plaintexts: same multiset as the inputs' plaintexts m_i (product as a cheap witness)
+    V = vm.MixNetElGamalVerifyFiatShamirSession(G, params, k, threshold)
+    nizkp = M.nizkp
+    if tmpdir is not None:
+        nizkp.write(str(tmpdir))
+        nizkp = vm.ProofDirectory.read(str(tmpdir))
+        assert dict(nizkp) == dict(M.nizkp)
+    rep = V.verify(nizkp)
+    orep = opr.verify_mix(OG, oparams, k, threshold, dict(nizkp))
+    assert rep["accepted"] and orep["accepted"]
+    assert rep["shuffles"] == orep["shuffles"] == {l: True for l in range(1, threshold + 1)}
+
+    def both_reject(bad):
+        for fn, exc in ((lambda: V.verify(bad), vm.VerificationError),
+                        (lambda: opr.verify_mix(OG, oparams, k, threshold, dict(bad)), opr.MixVerificationError)):
+            try:
+                r = fn()
+                assert not r["accepted"], "corrupted proof accepted"
+            except exc:
+                pass
+
+    def flipped(name, pos, bit=1):
+        bad = vm.ProofDirectory(M.nizkp)
+        raw = bytearray(bad[name])
+        raw[pos] ^= bit
+        bad[name] = bytes(raw)
+        return bad
+    both_reject(flipped("proofs/PoSReply01.bt", -3))
+    both_reject(flipped("proofs/DecrFactReply02.bt", -1))
+    both_reject(flipped("proofs/DecryptionFactors03.bt", -2))
+    both_reject(flipped("Plaintexts.bt", -3))
+    missing = vm.ProofDirectory(M.nizkp)
+    del missing["proofs/PoSCommitment02.bt"]
+    both_reject(missing)

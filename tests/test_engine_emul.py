@@ -89,3 +89,8 @@ def test_ec_committed_shuffle_parity(engine_emul):
 def test_ec_other_curve(engine_emul):
     """secp256k1: a = 0 (general doubling formula) and the generic Montgomery reduction."""
     pb.ec_group_ops(engine_emul, "secp256k1", 5)
+
+
+@pytest.mark.parametrize("spec,n", [(512, 9), ("P-256", 6)])
+def test_mix_and_vmnv_parity(engine_emul, spec, n, tmp_path):
+    pb.mix_parity(engine_emul, spec, n, tmpdir=tmp_path)

@@ -132,3 +132,9 @@ def test_ec_committed_shuffle_parity(engine_cuda):
 def test_ec_accept_reject_at_scale(engine_cuda):
     """N = 300,000 points: tables of 16-bit windows, Pippenger c = 16, several levels of the batched inversion."""
     pb.accept_reject_properties(engine_cuda, "P-256", 300000)
+
+
+@pytest.mark.parametrize("spec,n", [(3072, 12), (512, 300), ("P-256", 200)])
+def test_mix_and_vmnv_parity(engine_cuda, spec, n, tmp_path):
+    """A 3-party mix with threshold 2 and its vmnv-style verification (BASELINE.json config 3 at oracle size)."""
+    pb.mix_parity(engine_cuda, spec, n, tmpdir=tmp_path)

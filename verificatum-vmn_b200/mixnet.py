@@ -168,9 +168,9 @@ class ShufflerSession:
         return proof, None
 
     # ShufflerElGamalSession.java:195-210 (readOutput) + :301-330 (verify branch)
-    def verify(self, width: int, ciphertexts, proof: ShuffleProof, generators=None):
+    def verify(self, width: int, ciphertexts, proof: ShuffleProof, generators=None, output=None):
         """Returns (verdict, output array) -- on failure the output is a copy of the input
-        ("Replacing output with input", :321-327)."""
+        ("Replacing output with input", :321-327).  `output`: proof.output already parsed (vmnv reads it itself)."""
         ciphPPGroup = ciphertexts.getPGroup()
         widePublicKey = getWidePublicKey(self.publicKey, width)
         size = ciphertexts.size()
@@ -178,7 +178,8 @@ class ShufflerSession:
         if own_generators:
             generators = self.deriveGenerators(size)
         try:
-            output = ciphPPGroup.toElementArray(size, ByteTreeReader(proof.output))
+            if output is None:
+                output = ciphPPGroup.toElementArray(size, ByteTreeReader(proof.output))
         except Exception:
             if own_generators:
                 generators.free()
