@@ -10,7 +10,9 @@ from __future__ import annotations
 
 import hashlib
 import os
+import queue
 import struct
+import threading
 
 
 class HashfunctionHeuristic:
@@ -110,3 +112,44 @@ class RandomOracle:
         d = self.getDigest()
         d.update(data)
         return d.digest()
+
+
+class AsyncDigest:
+    """A RandomOracleDigest fed by one worker thread.
+
+    Fiat-Shamir hashing is one SHA-256 stream per challenge (hvzk/ChallengerRO.java:96-116) and cannot be spread
+    over cores, but it can run BESIDE the GPU: `update` only queues the buffer (hashlib releases the GIL while it
+    hashes), so the caller goes on queueing kernels for everything that does not depend on the challenge.  The
+    buffers must not change until `digest()` has returned (array serialisations are immutable)."""
+
+    def __init__(self, inner: RandomOracleDigest):
+        self.inner = inner
+        self._q: "queue.SimpleQueue" = queue.SimpleQueue()
+        self._err = None
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def _run(self) -> None:
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            if self._err is None:
+                try:
+                    self.inner.update(item)
+                except BaseException as e:  # surfaced by digest()
+                    self._err = e
+
+    def update(self, data) -> None:
+        self._q.put(data)
+
+    def digest(self) -> bytes:
+        self._q.put(None)
+        self._t.join()
+        if self._err is not None:
+            raise self._err
+        return self.inner.digest()
+
+    @property
+    def nbytes(self) -> int:
+        return self.inner.nbytes

@@ -43,7 +43,8 @@ class _Collector:
         self.parts: List[bytes] = []
 
     def update(self, data) -> None:
-        self.parts.append(bytes(data))
+        # bytes-like pieces are kept by reference (arrays' serialisations are immutable): one copy, in join
+        self.parts.append(data if isinstance(data, (bytes, memoryview)) else bytes(data))
 
     def value(self) -> bytes:
         return b"".join(self.parts)

@@ -18,7 +18,9 @@ from typing import Optional
 
 from .arithm import (ArithmFormatException, LargeIntegerArray, Permutation, PGroupElementArray, PPGroupElement,
                      PRingElementArray)
-from .crypto import HashfunctionHeuristic, PRGHeuristic, RandomOracle
+import struct
+
+from .crypto import AsyncDigest, HashfunctionHeuristic, PRGHeuristic, RandomOracle
 from .eio import ByteTreeBasic, ByteTreeContainer, ByteTreeLeaf, ByteTreeReader, EIOException
 
 
@@ -41,6 +43,23 @@ class ChallengerRO:
         data.update(d)
         self.hashed_bytes += d.nbytes
         return d.digest()
+
+    # The same challenge, streamed: `begin` returns a digest that hashes on a worker thread while the caller
+    # keeps the GPU busy with work that does not depend on the challenge; the caller writes the byte tree into
+    # it piece by piece (node headers included: `node_header(n)`) and calls `finish`.
+    def begin(self, vbitlen: int) -> AsyncDigest:
+        d = AsyncDigest(RandomOracle(self.roHashfunction, vbitlen).getDigest())
+        d.update(self.globalPrefix)
+        return d
+
+    def finish(self, d: AsyncDigest) -> bytes:
+        out = d.digest()
+        self.hashed_bytes += d.nbytes
+        return out
+
+
+def node_header(n: int) -> bytes:
+    return struct.pack(">BI", 0, n)
 
 
 def _to_positive(b: bytes) -> int:
@@ -124,21 +143,40 @@ class PoSBasicTW:
         self.e = self.pField.unsafeToElementArray(lia)
 
     # -- :546-700
-    def commit(self, prgSeed: bytes) -> ByteTreeBasic:
+    def commitIndependent(self) -> None:
+        """The part of commit() that does not depend on the batching vector: every value drawn from the random
+        source (in the reference's order b, beta, gamma, delta, phi: :571,621,667,678,688) and C', D', F'.  A
+        caller that derives the seed by hashing (PoSTW.prove) runs this while the hash is being computed."""
+        if self.b is not None:
+            return
+        g = self.g
+        self.b = self.pRing.randomElementArray(self.size, self.randomSource, self.rbitlen)  # :571
+        self.beta = self.pRing.randomElementArray(self.size, self.randomSource, self.rbitlen)  # :621
+        self.gamma = self.pRing.randomElement(self.randomSource, self.rbitlen)   # :667
+        self.delta = self.pRing.randomElement(self.randomSource, self.rbitlen)   # :678
+        ciphPRing = self.pkey.project(0).getPGroup().getPRing()        # :687
+        self.phi = ciphPRing.randomElement(self.randomSource, self.rbitlen)
+        self.Cp = g.exp(self.gamma)
+        self.Dp = g.exp(self.delta)
+        self.Fp = self.pkey.exp(self.phi.neg()).mul(self.wp.expProd(self.epsilon))  # :690
+
+    def commit(self, prgSeed: bytes, on_B=None) -> ByteTreeBasic:
+        """`on_B(B)` is called as soon as the first array of the commitment exists (its hashing can start)."""
         self.setBatchVector(prgSeed)
+        self.commitIndependent()
         g, h = self.g, self.h
         piinv = self.pi.inv()
         self.ipe = self.e.permute(piinv)                               # :552-554
         piinv.free()
         h0 = h.get(0)                                                  # :562
-        self.b = self.pRing.randomElementArray(self.size, self.randomSource, self.rbitlen)  # :571
         x, self.d = self.b.recLin(self.ipe)                            # :596-598
         y = self.ipe.prods()                                           # :604
         g_exp_x = g.exp(x)                                             # :606
         h0_exp_y = h0.exp(y)                                           # :608
         self.B = g_exp_x.mul(h0_exp_y)                                 # :610
         _free(g_exp_x, h0_exp_y)
-        self.beta = self.pRing.randomElementArray(self.size, self.randomSource, self.rbitlen)  # :621
+        if on_B is not None:
+            on_B(self.B)
         xp = x.shiftPush(x.getPRing().getZERO())                       # :637
         yp = y.shiftPush(y.getPRing().getONE())                        # :638
         _free(y, x)
@@ -149,13 +187,6 @@ class PoSBasicTW:
         h0_exp_yp_mul_epsilon = h0.exp(yp_mul_epsilon)                 # :646
         self.Bp = g_exp_beta_add_prod.mul(h0_exp_yp_mul_epsilon)       # :648
         _free(h0_exp_yp_mul_epsilon, yp_mul_epsilon, g_exp_beta_add_prod, beta_add_prod, xp_mul_epsilon, yp, xp)
-        self.gamma = self.pRing.randomElement(self.randomSource, self.rbitlen)   # :667
-        self.Cp = g.exp(self.gamma)
-        self.delta = self.pRing.randomElement(self.randomSource, self.rbitlen)   # :678
-        self.Dp = g.exp(self.delta)
-        ciphPRing = self.pkey.project(0).getPGroup().getPRing()        # :687
-        self.phi = ciphPRing.randomElement(self.randomSource, self.rbitlen)
-        self.Fp = self.pkey.exp(self.phi.neg()).mul(self.wp.expProd(self.epsilon))  # :690
         return ByteTreeContainer(self.B.toByteTree(), self.Ap.toByteTree(), self.Bp.toByteTree(),
                                  self.Cp.toByteTree(), self.Dp.toByteTree(), self.Fp.toByteTree())
 
@@ -512,15 +543,39 @@ class PoSTW:
         self.vbitlen, self.ebitlen, self.rbitlen = vbitlen, ebitlen, rbitlen
         self.prg, self.randomSource, self.challenger = prg, randomSource, challenger
         self.P = self.V = None
+        self._seedDigest = None
 
     # -- :80-88 / :167-173
     def precompute(self, g, h, pi: Optional[Permutation] = None) -> None:
         basic = PoSBasicTW(self.vbitlen, self.ebitlen, self.rbitlen, self.prg, self.randomSource)
+        # The seed of the batching vector is RO(g, h, u, pk, w, w') (:118-124): g and h are known now, so a
+        # prover starts hashing them BEFORE queueing its exponentiations and the worker thread hashes beside them.
+        if pi is not None and getattr(self, "_seedDigest", None) is None:
+            self._seedDigest = self._seed_begin(g, h)
         basic.precompute(g, h, pi)
         if pi is None:
             self.V = basic
         else:
             self.P = basic
+
+    def beginSeed(self, g, h) -> None:
+        """Prover: start hashing (g, h) now -- call it before any device work is queued (the serialisation of
+        h is a device-to-host copy that would otherwise wait behind that work)."""
+        self._seedDigest = self._seed_begin(g, h)
+
+    def _seed_begin(self, g, h) -> AsyncDigest:
+        d = self.challenger.begin(8 * self.prg.minNoSeedBytes())
+        d.update(node_header(6))
+        g.toByteTree().update(d)
+        h.toByteTree().update(d)
+        return d
+
+    def _seed_finish(self, d: AsyncDigest, u, pkey, w, wp) -> AsyncDigest:
+        u.toByteTree().update(d)
+        pkey.toByteTree().update(d)
+        w.toByteTree().update(d)
+        wp.toByteTree().update(d)
+        return d
 
     def _seed(self, B: PoSBasicTW, pkey, w, wp) -> bytes:
         challengeData = ByteTreeContainer(B.g.toByteTree(), B.h.toByteTree(), B.u.toByteTree(), pkey.toByteTree(),
@@ -532,10 +587,20 @@ class PoSTW:
         P = self.P
         P.setInstance(pkey, w, wp, s)
         permutationCommitment = P.u.toByteTree().to_bytes()
-        prgSeed = self._seed(P, pkey, w, wp)
-        commitment = P.commit(prgSeed)
-        challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitment)                    # :146-147
-        challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
+        d = self._seedDigest if self._seedDigest is not None else self._seed_begin(P.g, P.h)
+        self._seedDigest = None
+        self._seed_finish(d, P.u, pkey, w, wp)
+        P.commitIndependent()            # the GPU works on C', D', F' while the worker thread hashes
+        prgSeed = self.challenger.finish(d)
+        # challenge = RO(node(leaf(seed), commitment)) (:146-147): B is hashed while B' is being computed
+        cd = self.challenger.begin(self.vbitlen)
+        cd.update(node_header(2))
+        ByteTreeLeaf(prgSeed).update(cd)
+        cd.update(node_header(6))
+        commitment = P.commit(prgSeed, on_B=lambda B: B.toByteTree().update(cd))
+        for child in commitment.children[1:]:
+            child.update(cd)
+        challengeBytes = self.challenger.finish(cd)
         reply = P.reply(_to_positive(challengeBytes))
         out = (permutationCommitment, commitment.to_bytes(), reply.to_bytes())
         P.free()
@@ -549,15 +614,20 @@ class PoSTW:
             V.setPermutationCommitment(ByteTreeReader(permutationCommitment))
         except EIOException:
             V.u = V.h.copyOfRange(0, V.h.size())
-        prgSeed = self._seed(V, pkey, w, wp)
-        V.setBatchVector(prgSeed)
-        V.computeAF()
+        # every input of the seed is on the host already: hash it on the worker thread while the device imports
+        # (and membership-checks) the commitment, which does not depend on the seed
+        d = self._seed_finish(self._seed_begin(V.g, V.h), V.u, pkey, w, wp)
         try:
             commitmentTree = V.setCommitment(ByteTreeReader(commitment))
         except EIOException:
             commitmentTree = V.setCommitment(ByteTreeReader(ByteTreeContainer().to_bytes()))
-        challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitmentTree)
-        challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
+        prgSeed = self.challenger.finish(d)
+        V.setBatchVector(prgSeed)
+        # the challenge is hashed while the device computes A and F
+        cd = self.challenger.begin(self.vbitlen)
+        ByteTreeContainer(ByteTreeLeaf(prgSeed), commitmentTree).update(cd)
+        V.computeAF()
+        challengeBytes = self.challenger.finish(cd)
         V.setChallenge(_to_positive(challengeBytes))
         try:
             verdict = V.verify(ByteTreeReader(reply))

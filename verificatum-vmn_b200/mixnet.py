@@ -144,10 +144,11 @@ class ShufflerSession:
         if own_generators:
             generators = self.deriveGenerators(size)
         rbitlen = self.params.rbitlen
+        P = self._pos()
+        P.beginSeed(generators.getPGroup().getg(), generators)   # Fiat-Shamir hashing of (g, h) runs beside the GPU
         reencExponents = exponentsPRing.randomElementArray(size, self.randomSource, rbitlen)       # :400-403
         reencFactors = widePublicKey.exp(reencExponents)                                           # :407
         permutation = Permutation.random(size, self.randomSource, rbitlen, self.pGroup.basic()[0])                       # :408-409
-        P = self._pos()
         P.precompute(generators.getPGroup().getg(), generators, permutation)                       # :414
         reenc = ciphertexts.mul(reencFactors)                                                      # :273
         reencFactors.free()
