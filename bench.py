@@ -421,7 +421,7 @@ def main():
         achieved = k_modmuls * macs / (k_ms * 1e-3)
         traffic = pipe_busy = None
         try:  # one `ncu --set full` capture of this kernel at the same shape (profiles/, per launch)
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_exp_fixed.json")))
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_exp_fixed.json")))
             if cap["n"] == n_local and args.bits == 3072 and not is_curve(args):
                 traffic, pipe_busy = cap["traffic_bytes"], cap["fmaheavy_pipe_busy_pct"]
         except Exception:
@@ -429,7 +429,7 @@ def main():
         roof = {"bound": "imad", "kernel": "k_ec_exp_fixed" if is_curve(args) else "k_exp_fixed<%d>" % (args.bits // 32),
                 "achieved": achieved / 1e12,
                 "peak": IMAD_PEAK_MAC_PER_S / 1e12, "unit": "TMAC/s (32x32+64 IMAD.WIDE)", "frac": achieved / IMAD_PEAK_MAC_PER_S,
-                "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu, profiles/r01_ncu_exp_fixed.json)",
+                "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu, profiles/r02_ncu_exp_fixed.json; 16-byte gathers use half of each 32-byte sector, hence ~2x the algorithmic bytes; 0.34 TB/s, not the limiter)",
                 "algorithmic_bytes": (k_modmuls / 11 * elem_bytes + 32 * n_local + 96 * n_local) if is_curve(args)
                 else k_modmuls * elem_bytes + 2 * n_local * elem_bytes,
                 "unit_of_work": "field multiplication = 136 word MACs nominal (the P-256 reduction executes 64 + adds)"
