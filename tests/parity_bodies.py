@@ -644,3 +644,55 @@ def mix_parity(vmx, spec, n, k=3, threshold=2, tmpdir=None):
     missing = vm.ProofDirectory(M.nizkp)
     del missing["proofs/PoSCommitment02.bt"]
     both_reject(missing)
+
+
+def ec_edge_cases(vmx, curve):
+    """Unit elements inside arrays, zero exponents everywhere, empty arrays, range violations."""
+    from oracle import ec as oec
+    A = vmx.arithm
+    G, OG = engine_group(vmx, curve), oracle_group(curve)
+    R = G.getPRing()
+    vals = lambda arr: [elem_value(e) for e in arr.elements()]
+    ring = lambda xs: R.toElementArray([R.toElement(x) for x in xs])
+    pts = [oec.UNIT, OG.g, OG.op_exp(OG.g, 5), oec.UNIT, OG.op_inv(OG.g), OG.op_exp(OG.g, OG.q - 2)]
+    X = G.toElementArray([engine_elem(vmx, G, P) for P in pts])
+    n = len(pts)
+    assert vals(X) == pts
+    zeros = ring([0] * n)
+    ones = ring([1] * n)
+    mixed = [0, 7, OG.q - 1, 3, 1, 2]
+    assert vals(X.exp(zeros)) == [oec.UNIT] * n and vals(X.exp(ones)) == pts
+    assert vals(X.exp(ring(mixed))) == [OG.op_exp(P, k) for P, k in zip(pts, mixed)]
+    assert vals(X.exp(R.toElement(0))) == [oec.UNIT] * n
+    assert elem_value(X.expProd(zeros)).is_unit()
+    assert elem_value(X.expProd(ring(mixed))) == oar.g_exp_prod(OG, pts, mixed)
+    assert elem_value(X.prod()) == oar.g_prod(OG, pts)
+    assert vals(X.mul(X.inv())) == [oec.UNIT] * n
+    assert vals(X.mul(X)) == [OG.op_mul(P, P) for P in pts]
+    rev = G.toElementArray([engine_elem(vmx, G, P) for P in reversed(pts)])
+    assert vals(X.mul(rev)) == [OG.op_mul(P, Q) for P, Q in zip(pts, reversed(pts))]
+    assert vals(G.getg().exp(zeros)) == [oec.UNIT] * n
+    assert vals(G.getONE().exp(ring(mixed))) == [oec.UNIT] * n            # fixed base = unit element
+    assert vals(G.expProd([X, rev], [0, -1], 1)) == [OG.op_inv(P) for P in reversed(pts)]
+    units = G.toElementArray(4, G.getONE())
+    assert vals(units) == [oec.UNIT] * 4 and elem_value(units.prod()).is_unit()
+    assert elem_value(units.expProd(ring([5, 6, 7, 8]))).is_unit()
+    empty = G.toElementArray([])
+    assert empty.size() == 0 and empty.to_matrix().shape == (0, G.elem_bytes)
+    assert elem_value(empty.prod()).is_unit() and elem_value(empty.expProd(ring([]))).is_unit()
+    assert G.toElementArray(0, vmx.eio.ByteTreeReader(empty.toByteTree().to_bytes())).size() == 0
+    # coordinates >= p, a negative coordinate other than the unit's, points off the curve: ArithmFormatException
+    cb = G.coord_bytes
+    good = OG.g
+    for x, y in ((OG.p, good.y), (good.x, OG.p + 1), (-2, -2), (-1, good.y), (good.x, good.y ^ 1)):
+        raw = x.to_bytes(cb, "big", signed=True) + y.to_bytes(cb, "big", signed=True)
+        try:
+            G.toElementArray(1, np.frombuffer(raw, dtype=np.uint8))
+            assert False, (x, y)
+        except A.ArithmFormatException:
+            pass
+    try:
+        X.mul(units)
+        assert False
+    except vmx._native.VmxError as e:
+        assert e.status == vmx._native.VMX_ESIZE

@@ -94,3 +94,8 @@ def test_ec_other_curve(engine_emul):
 @pytest.mark.parametrize("spec,n", [(512, 9), ("P-256", 6)])
 def test_mix_and_vmnv_parity(engine_emul, spec, n, tmp_path):
     pb.mix_parity(engine_emul, spec, n, tmpdir=tmp_path)
+
+
+@pytest.mark.parametrize("curve", ["P-256", "secp256k1"])
+def test_ec_edge_cases(engine_emul, curve):
+    pb.ec_edge_cases(engine_emul, curve)

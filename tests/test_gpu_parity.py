@@ -138,3 +138,8 @@ def test_ec_accept_reject_at_scale(engine_cuda):
 def test_mix_and_vmnv_parity(engine_cuda, spec, n, tmp_path):
     """A 3-party mix with threshold 2 and its vmnv-style verification (BASELINE.json config 3 at oracle size)."""
     pb.mix_parity(engine_cuda, spec, n, tmpdir=tmp_path)
+
+
+@pytest.mark.parametrize("curve", ["P-256", "secp256k1"])
+def test_ec_edge_cases(engine_cuda, curve):
+    pb.ec_edge_cases(engine_cuda, curve)
