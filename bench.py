@@ -42,28 +42,30 @@ def macs_per_modmul(bits: int) -> int:
     return 2 * n * n + n
 
 
-def nominal_modmuls_per_ciphertext(bits: int, n: int, n_e=256, n_v=256, n_r=100):
+def nominal_modmuls_per_ciphertext(bits: int, n: int, n_e=256, n_v=256, n_r=100, width=1):
     """SURVEY.md §8d textbook costs: FIX(L)=ceil(L/8), VAR(L)=L+ceil(L/6), MEXP(L)=min_c ceil(L/c)(1+2^(c+1)/N)."""
     Lq = bits - 1
     fix = lambda L: -(-L // 8)
     var = lambda L: L + -(-L // 6)
     mexp = lambda L: min(-(-L // c) * (1 + 2 ** (c + 1) / n) for c in range(1, 24))
     eps = n_e + n_v + n_r
-    reenc = 2 * fix(Lq) + 2
-    prove = 5 * fix(Lq) + 3 * mexp(eps) + 4
-    verify = 3 * mexp(n_e) + 3 * mexp(eps + 1) + var(n_v) + var(eps + 1) + fix(Lq) + 4
+    k = 1 + 2 * width
+    reenc = 2 * width * (fix(Lq) + 1)
+    prove = 5 * fix(Lq) + k * mexp(eps) + 4
+    verify = k * mexp(n_e) + k * mexp(eps + 1) + var(n_v) + var(eps + 1) + fix(Lq) + 4
     return {"reencrypt": reenc, "prove": prove, "verify": verify, "total": reenc + prove + verify}
 
 
-def nominal_fieldmuls_per_ciphertext_ec(n: int, L=256):
+def nominal_fieldmuls_per_ciphertext_ec(n: int, L=256, width=1):
     """The same textbook operation counts on a 256-bit curve, in field multiplications (136 word MACs each,
     SURVEY.md §8d): mixed addition 11, doubling 8, full addition 16; every exponent is < q (256 bits)."""
     fix = lambda: -(-L // 8) * 11
     var = lambda: L * 8 + -(-L // 6) * 16
     mexp = lambda: min(-(-L // c) * (11 + 16 * 2 ** (c + 1) / n) for c in range(1, 24))
-    reenc = 2 * fix() + 2 * 11
-    prove = 5 * fix() + 3 * mexp() + 4 * 11
-    verify = 6 * mexp() + 2 * var() + fix() + 4 * 11
+    k = 1 + 2 * width
+    reenc = 2 * width * (fix() + 11)
+    prove = 5 * fix() + k * mexp() + 4 * 11
+    verify = 2 * k * mexp() + 2 * var() + fix() + 4 * 11
     return {"reencrypt": reenc, "prove": prove, "verify": verify, "total": reenc + prove + verify}
 
 
@@ -137,9 +139,9 @@ def metric_name(args) -> str:
 
 def config_dict(args):
     elem = 64 if is_curve(args) else args.bits // 8
-    return {"workload": "%s, width 1, N=%d ciphertexts per GPU: re-encrypt + PoSBasicTW prove + verify"
-                        % (group_label(args), args.n),
-            "group": args.group, "bits": 256 if is_curve(args) else args.bits, "width": 1, "n_per_gpu": args.n,
+    return {"workload": "%s, width %d, N=%d ciphertexts per GPU: re-encrypt + PoSBasicTW prove + verify"
+                        % (group_label(args), args.width, args.n),
+            "group": args.group, "bits": 256 if is_curve(args) else args.bits, "width": args.width, "n_per_gpu": args.n,
             "ebitlen": 256, "vbitlen": 256, "rbitlen": 100,
             "l2": "working set (N x %d B per array, >10 arrays) exceeds the 126 MB L2" % elem}
 
@@ -224,6 +226,7 @@ def main():
     ap.add_argument("--impl", default="vmx", choices=["vmx", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("VMX_BENCH_N", "100000")))
     ap.add_argument("--bits", type=int, default=3072)
+    ap.add_argument("--width", type=int, default=1, help="blocks per ciphertext (BASELINE.json config 4 uses 3)")
     ap.add_argument("--group", default="modp", help="modp (RFC 3526 safe prime of --bits) or a curve name (P-256)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="ciphertexts in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -289,10 +292,18 @@ def main():
     x = G.getPRing().randomElement(setup_rs, 100)
     y = G.getg().exp(x)
     pk = A.PPGroup(G, 2).product(G.getg(), y)
-    ciphertexts = mixnet.demoCiphertexts(pk, n, setup_rs)
+    width = args.width
+    exponentsRing = mixnet.getPlainPGroup(G, width).getPRing()
+    if width == 1:
+        ciphertexts = mixnet.demoCiphertexts(pk, n, setup_rs)
+    else:  # multi-block ciphertexts: w = widePk^r, r in the product ring (encryptions of the unit element)
+        r0 = exponentsRing.randomElementArray(n, setup_rs, 100)
+        ciphertexts = mixnet.getWidePublicKey(pk, width).exp(r0)
+        r0.free()
+    basic_pk, pk = pk, mixnet.getWidePublicKey(pk, width)
     params = mixnet.SessionParams(pGroupString="ECqPGroup(%s)" % args.group if is_curve(args)
                                   else "ModPGroup(RFC3526-%d)" % args.bits)
-    session = mixnet.ShufflerSession(G, pk, params, prg("prover"))
+    session = mixnet.ShufflerSession(G, basic_pk, params, prg("prover"))
     generators = session.deriveGenerators(n)
     seed = bytes(range(32))
     challenge = int.from_bytes(crypto.HashfunctionHeuristic("SHA-256").hash(b"challenge"), "big")
@@ -321,7 +332,7 @@ def main():
         V = hvzk.PoSBasicTW(params.vbitlenro, params.ebitlenro, params.rbitlen, crypto.PRGHeuristic(), rs)
         ph = Phase if (timed and args.phases) else (lambda name: _Null())
         with ph("reencrypt"):
-            s = G.getPRing().randomElementArray(n, rs, params.rbitlen)
+            s = exponentsRing.randomElementArray(n, rs, params.rbitlen)
             factors = pk.exp(s)
             pi = A.Permutation.random(n, rs, params.rbitlen, G)
             reenc = ciphertexts.mul(factors)
@@ -449,12 +460,12 @@ def main():
 
         def step_e2e(i: int):
             nonlocal h2d, d2h
-            prover = mixnet.ShufflerSession(G, pk, params, prg("e2e%d" % i))
-            verifier = mixnet.ShufflerSession(G, pk, params, prg("e2ev%d" % i))
-            ciphPGroup = mixnet.getCiphPGroup(G, 1)
+            prover = mixnet.ShufflerSession(G, basic_pk, params, prg("e2e%d" % i))
+            verifier = mixnet.ShufflerSession(G, basic_pk, params, prg("e2ev%d" % i))
+            ciphPGroup = mixnet.getCiphPGroup(G, width)
             w = ciphPGroup.toElementArray(n, vmx.eio.ByteTreeReader(memoryview(pinned.numpy())))
-            proof, _ = prover.shuffle(1, w, generators=generators)
-            ok, out = verifier.verify(1, w, proof, generators=generators)
+            proof, _ = prover.shuffle(width, w, generators=generators)
+            ok, out = verifier.verify(width, w, proof, generators=generators)
             if not ok:
                 raise SystemExit("bench e2e: verifier rejected an honest proof")
             out.free()
@@ -502,7 +513,8 @@ def main():
             cpu = {"value": None, "unit": "ciphertexts/s", "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
 
     if rank == 0:
-        nominal = nominal_fieldmuls_per_ciphertext_ec(n) if is_curve(args) else nominal_modmuls_per_ciphertext(args.bits, n)
+        nominal = nominal_fieldmuls_per_ciphertext_ec(n, width=args.width) if is_curve(args) else \
+            nominal_modmuls_per_ciphertext(args.bits, n, width=args.width)
         macs = 136 if is_curve(args) else macs_per_modmul(args.bits)
         line = {"metric": metric_name(args),
                 "value": value, "unit": "ciphertexts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

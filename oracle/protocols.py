@@ -750,7 +750,11 @@ def precomp(G, params: Params, pkey, h, rs):
     pi = ar.permutation_random(n, rs, params.rbitlen)
     u = ar.permute(idc, pi)
     posc_c, posc_r = posc_prove(G, params, G.g, h, u, exponents, pi, rs)
-    s = ar.ring_random_array(G, n, rs, params.rbitlen)
+    shape = _ring_shape(pkey)        # exponents of the (possibly wide) ciphertext ring, component by component
+    if isinstance(shape, tuple):
+        s = tuple(ar.ring_random_array(G, n, rs, params.rbitlen) for _ in shape)
+    else:
+        s = ar.ring_random_array(G, n, rs, params.rbitlen)
     factors = ar.g_exp(G, pkey, s)
     state = {"exponents": exponents, "pi": pi, "u": u, "s": s, "factors": factors, "h": list(h)}
     return state, (ar.array_tree(G, u).to_bytes(), posc_c, posc_r)
@@ -766,7 +770,7 @@ def shrink(G, state: dict, n: int) -> bytes:
     state["pi"] = perm_shrink(state["pi"], n)
     state["u"] = [x for x, k in zip(state["u"], keep) if k]
     state["h"] = state["h"][:n]
-    state["s"] = state["s"][:n]
+    state["s"] = ar.gmap(lambda col: col[:n], state["s"]) if isinstance(state["s"], tuple) else state["s"][:n]
     state["factors"] = ar.gmap(lambda col: col[:n], state["factors"])
     return bt.bool_array_leaf(keep).to_bytes()
 

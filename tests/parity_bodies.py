@@ -696,3 +696,81 @@ def ec_edge_cases(vmx, curve):
         assert False
     except vmx._native.VmxError as e:
         assert e.status == vmx._native.VMX_ESIZE
+
+
+def _wide_instance(vmx, spec, width, n, label):
+    """Width-omega ciphertexts (BASELINE.json config 4: multi-block ciphertexts): w = widePk^{r}, r in the product ring."""
+    A = vmx.arithm
+    mix = importlib.import_module("verificatum-vmn_b200.mixnet")
+    G, OG = engine_group(vmx, spec), oracle_group(spec)
+    rs = vmx.crypto.PRGHeuristic()
+    rs.setSeed(seed(label + "/setup"))
+    x = G.getPRing().randomElement(rs, 100)
+    pk = A.PPGroup(G, 2).product(G.getg(), G.getg().exp(x))
+    wide = mix.getWidePublicKey(pk, width)
+    r = mix.getPlainPGroup(G, width).getPRing().randomElementArray(n, rs, 100)
+    w = wide.exp(r)
+    ors = SeededRandomSource(seed(label + "/setup"))
+    ox = oar.ring_random_element(OG, ors, 100)
+    owide = ((OG.g,) * width, (OG.op_exp(OG.g, ox),) * width)
+    ow = oar.g_exp(OG, owide, tuple(oar.ring_random_array(OG, n, ors, 100) for _ in range(width)))
+    assert col_values(w) == ow
+    return G, OG, pk, w, owide, ow
+
+
+def wide_shuffle_parity(vmx, spec, width, n):
+    """Shuffle + PoS of width-omega ciphertexts: identical bytes, cross verification, rejection."""
+    mix = importlib.import_module("verificatum-vmn_b200.mixnet")
+    G, OG, pk, w, owide, ow = _wide_instance(vmx, spec, width, n, "wide")
+    params = mix.SessionParams(pGroupString="wide-%s" % spec)
+    oparams = opr.Params(pgroup_string="wide-%s" % spec)
+    prs = vmx.crypto.PRGHeuristic()
+    prs.setSeed(seed("wide/prover"))
+    proof, out = mix.ShufflerSession(G, pk, params, prs).shuffle(width, w, keep_output=True)
+    oh = opr.independent_generators(OG, "sha256", oparams.prefix(), "generators", n, 100)
+    owp, oproof = opr.shuffle_and_prove(OG, oparams, owide, ow, oh, SeededRandomSource(seed("wide/prover")))
+    assert col_values(out) == owp
+    assert dataclasses.asdict(proof) == oproof
+    verifier = mix.ShufflerSession(G, pk, params, None)
+    ok, out2 = verifier.verify(width, w, proof)
+    assert ok and col_values(out2) == owp
+    assert opr.verify_shuffle(OG, oparams, owide, ow, oh, oproof)
+    raw = bytearray(proof.reply)
+    raw[-9] ^= 2
+    bad = dataclasses.replace(proof, reply=bytes(raw))
+    assert verifier.verify(width, w, bad)[0] is False
+    assert opr.verify_shuffle(OG, oparams, owide, ow, oh, dataclasses.asdict(bad)) is False
+
+
+def wide_committed_shuffle_parity(vmx, spec, width, maxciph, n):
+    """Pre-computation + commitment-consistent shuffle (CCPoS: pure multi-exponentiation over (1 + 2 omega) N
+    elements, the verify of config 4) of width-omega ciphertexts."""
+    mix = importlib.import_module("verificatum-vmn_b200.mixnet")
+    G, OG, pk, w, owide, ow = _wide_instance(vmx, spec, width, n, "widecc")
+    params = mix.SessionParams(pGroupString="widecc-%s" % spec)
+    oparams = opr.Params(pgroup_string="widecc-%s" % spec)
+    prs = vmx.crypto.PRGHeuristic()
+    prs.setSeed(seed("widecc/prover"))
+    prover = mix.ShufflerSession(G, pk, params, prs)
+    cs = mix.CommittedShuffler(prover, width, maxciph)
+    pub = cs.precomp()
+    keep = cs.shrink(n)
+    prover.randomSource.setSeed(seed("widecc/prove2"))
+    proof, out = cs.shuffle(w, keep_output=True)
+    oh = opr.independent_generators(OG, "sha256", oparams.prefix(), "generators", maxciph, 100)
+    ostate, opub = opr.precomp(OG, oparams, owide, oh, SeededRandomSource(seed("widecc/prover")))
+    okeep = opr.shrink(OG, ostate, n)
+    owp, oproof = opr.committed_shuffle(OG, oparams, owide, ostate, ow, SeededRandomSource(seed("widecc/prove2")))
+    assert pub == opub and keep == okeep and col_values(out) == owp and dataclasses.asdict(proof) == oproof
+    verifier = mix.ShufflerSession(G, pk, params, None)
+    gens = verifier.deriveGenerators(maxciph)
+    pcv = mix.PermutationCommitment(verifier, gens)
+    assert pcv.verify(*opub) is True and pcv.shrink(n, okeep) == okeep
+    sg = gens.copyOfRange(0, n)
+    ok, out2 = mix.verifyCommittedShuffle(verifier, width, sg, pcv.commitment, w, proof)
+    assert ok and col_values(out2) == owp
+    assert opr.ccpos_verify(OG, oparams, OG.g, oh[:n], ostate["u"], owide, ow, owp, proof.commitment, proof.reply)
+    raw = bytearray(proof.reply)
+    raw[-2] ^= 8
+    okb, outb = mix.verifyCommittedShuffle(verifier, width, sg, pcv.commitment, w, dataclasses.replace(proof, reply=bytes(raw)))
+    assert okb is False and col_values(outb) == ow

@@ -99,3 +99,10 @@ def test_mix_and_vmnv_parity(engine_emul, spec, n, tmp_path):
 @pytest.mark.parametrize("curve", ["P-256", "secp256k1"])
 def test_ec_edge_cases(engine_emul, curve):
     pb.ec_edge_cases(engine_emul, curve)
+
+
+@pytest.mark.parametrize("spec,width,n", [(512, 3, 6), ('P-256', 2, 4)])
+def test_wide_ciphertexts_parity(engine_emul, spec, width, n):
+    """BASELINE.json config 4: width-3 ciphertexts, shuffle + PoS and pre-computation + CCPoS."""
+    pb.wide_shuffle_parity(engine_emul, spec, width, n)
+    pb.wide_committed_shuffle_parity(engine_emul, spec, width, n + 3, n)
