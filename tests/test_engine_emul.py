@@ -38,6 +38,11 @@ def test_group_ops_2048_small(engine_emul):
     pb.group_ops(engine_emul, 2048, 5)
 
 
+def test_ring_ops_2048(engine_emul):
+    """Long residues take the 4-per-thread scan (several levels of recursion at n = 300)."""
+    pb.ring_ops(engine_emul, 2048, 300)
+
+
 @pytest.mark.parametrize("n", [1, 19])
 def test_posc_parity(engine_emul, n):
     pb.posc_parity(engine_emul, 512, n)

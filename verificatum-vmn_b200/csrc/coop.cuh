@@ -212,22 +212,25 @@ k_coop_sqr_chain(const uint32_t* __restrict__ base, size_t bcap, size_t bidx, ui
   }
 }
 
-// out[oidx] = prod_m Y[m]^(16^m), m = 0..Mcount-1, Horner from the top (one warp)
+// out[oidx + c] = prod_m Y[c * Mcount + m]^(16^m), m = 0..Mcount-1, Horner from the top: one warp (block) per
+// column c -- the components of a product-group expProd share the exponents, so their Horner chains (L
+// sequential squarings each) run side by side instead of one after the other.
 template <int N>
 __global__ void __launch_bounds__(32)
 k_coop_horner(const uint32_t* __restrict__ Y, size_t ycap, int Mcount, uint32_t* __restrict__ out, size_t ocap,
               size_t oidx, const uint32_t* __restrict__ consts, uint32_t n0inv) {
   VMX_COOP_PROLOGUE(N);
   (void)wib;
+  const size_t base = (size_t)blockIdx.x * Mcount;
   uint32_t a[L], y[L];
-  coop_load<N>(a, Y, ycap, (size_t)Mcount - 1, lane);
+  coop_load<N>(a, Y, ycap, base + (size_t)Mcount - 1, lane);
   for (int m = Mcount - 2; m >= 0; m--) {
 #pragma unroll 1
     for (int q = 0; q < 4; q++) coop_mul<N>(a, a, a, nmod, n0inv, lane);
-    coop_load<N>(y, Y, ycap, (size_t)m, lane);
+    coop_load<N>(y, Y, ycap, base + (size_t)m, lane);
     coop_mul<N>(a, a, y, nmod, n0inv, lane);
   }
-  coop_store<N>(a, out, ocap, oidx, lane);
+  coop_store<N>(a, out, ocap, oidx + blockIdx.x, lane);
 }
 
 // Y[g] = prod_{v=1}^{15} X[15g + v-1]^v (running products), one warp per group

@@ -609,12 +609,13 @@ static int mexp_chunk() {
   return k;
 }
 
-// result element written to out[oidx] (Montgomery form)
+// Column `col` of an expProd: buckets, sub-digit products and the weighted sums Y[col * ngroups + g] (Montgomery
+// form); mexp_horner then folds the columns' Y into the results.
 template <int N>
-static int mexp_run(vmx_ctx* c, const MexpPlan& P, const vmx_garr* a, size_t n_terms, uint32_t* out, size_t ocap,
-                    size_t oidx) {
+static int mexp_run(vmx_ctx* c, const MexpPlan& P, const vmx_garr* a, size_t n_terms, uint32_t* Yall, size_t ycap,
+                    size_t col) {
   const MontParams<N> M = c->P.params<N>();
-  ElemBuf buckets, X, Y, R;
+  ElemBuf buckets, X, R;
   VMX_TRY(buckets.alloc_elems(c, P.nb));
   VMX_TRY(seg_product<N>(c, c->P, a->d, a->cap, P.idx.as<uint32_t>(), P.seg_off.as<uint32_t>(), P.nb,
                          n_terms * (size_t)P.W, mexp_chunk(), buckets.d(), buckets.cap));
@@ -622,22 +623,36 @@ static int mexp_run(vmx_ctx* c, const MexpPlan& P, const vmx_garr* a, size_t n_t
   VMX_TRY(seg_product<N>(c, c->P, buckets.d(), buckets.cap, P.idx2.as<uint32_t>(), P.seg2_off.as<uint32_t>(),
                          P.nseg2, P.total2, 8, X.d(), X.cap));
   const size_t ngroups = (size_t)P.W * P.J;
-  VMX_TRY(Y.alloc_elems(c, ngroups));
+  uint32_t* Y = Yall + 4 * col * ngroups;
 #ifndef VMX_HOST_EMUL
   VMX_LAUNCH(c, k_coop_weighted_small<N>, nblocks(ngroups, kCoopWarps), 32 * kCoopWarps, 0, X.d(), X.cap, ngroups,
-             Y.d(), Y.cap, c->P.consts, M.n0inv);
-  VMX_CHECK_LAUNCH();
-  VMX_LAUNCH(c, k_coop_horner<N>, 1, 32, 0, Y.d(), Y.cap, (int)ngroups, out, ocap, oidx, c->P.consts, M.n0inv);
+             Y, ycap, c->P.consts, M.n0inv);
   VMX_CHECK_LAUNCH();
 #else
   VMX_TRY(R.alloc_elems(c, ngroups));
-  VMX_LAUNCH(c, k_weighted_small<N>, nblocks(ngroups, 32), 32, 0, X.d(), X.cap, ngroups, Y.d(), Y.cap, R.d(), R.cap,
-             M);
-  VMX_CHECK_LAUNCH();
-  VMX_LAUNCH(c, k_horner<N>, 1, 32, N * 4, Y.d(), Y.cap, (int)ngroups, out, ocap, oidx, M);
+  VMX_LAUNCH(c, k_weighted_small<N>, nblocks(ngroups, 32), 32, 0, X.d(), X.cap, ngroups, Y, ycap, R.d(), R.cap, M);
   VMX_CHECK_LAUNCH();
 #endif
-  c->modmuls += ngroups * 28 + (ngroups - 1) * 5;
+  c->modmuls += ngroups * 28;
+  return VMX_OK;
+}
+
+// out[oidx + col] = prod_g Y[col * ngroups + g]^(16^g) for col < k: the k Horner chains run side by side
+template <int N>
+static int mexp_horner(vmx_ctx* c, const MexpPlan& P, const uint32_t* Yall, size_t ycap, size_t k, uint32_t* out,
+                       size_t ocap, size_t oidx) {
+  const MontParams<N> M = c->P.params<N>();
+  const size_t ngroups = (size_t)P.W * P.J;
+#ifndef VMX_HOST_EMUL
+  VMX_LAUNCH(c, k_coop_horner<N>, k, 32, 0, Yall, ycap, (int)ngroups, out, ocap, oidx, c->P.consts, M.n0inv);
+  VMX_CHECK_LAUNCH();
+#else
+  for (size_t col = 0; col < k; col++) {
+    VMX_LAUNCH(c, k_horner<N>, 1, 32, N * 4, Yall + 4 * col * ngroups, ycap, (int)ngroups, out, ocap, oidx + col, M);
+    VMX_CHECK_LAUNCH();
+  }
+#endif
+  c->modmuls += k * (ngroups - 1) * 5;
   return VMX_OK;
 }
 
@@ -694,7 +709,9 @@ template <int N>
 static int ring_scan(vmx_ctx* c, const uint32_t* eM, size_t ecap, const uint32_t* b, size_t bcap, size_t n,
                      int want_y, uint32_t* out, size_t ocap) {
   const MontParams<N> M = c->Q.params<N>();
-  const int K = 32;
+  // elements per thread: a level costs ~2K sequential modmuls of latency (45 us each at 3072 bits, one thread
+  // per residue) and there are log_K(n) levels: K = 4 minimises K / log K; short residues are not latency bound
+  const int K = N >= 64 ? 4 : 32;
   const size_t nch = (n + K - 1) / K;
   if (nch <= 1) {
     VMX_LAUNCH(c, k_scan_phaseB<N>, 1, kThreads, 0, eM, ecap, b, bcap, n, K, (const uint32_t*)nullptr, (size_t)0,
@@ -1470,7 +1487,10 @@ int vmx_expprod(const vmx_garr* const* a, size_t k, const vmx_rarr* e, uint8_t* 
     VMX_DISPATCH(c->nl, {
       MexpPlan P;
       VMX_TRY(mexp_plan<N>(c, e, L, P));
-      for (size_t l = 0; l < k; l++) VMX_TRY(mexp_run<N>(c, P, a[l], e->n, res.d(), res.cap, l));
+      ElemBuf Y;
+      VMX_TRY(Y.alloc_elems(c, k * (size_t)P.W * P.J));
+      for (size_t l = 0; l < k; l++) VMX_TRY(mexp_run<N>(c, P, a[l], e->n, Y.d(), Y.cap, l));
+      VMX_TRY(mexp_horner<N>(c, P, Y.d(), Y.cap, k, res.d(), res.cap, 0));
     });
   }
   DevBuf raw;
