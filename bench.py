@@ -232,6 +232,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--phases", action="store_true", help="print per-phase device times to stderr")
+    ap.add_argument("--trace", default="", help="write the host timeline (ABI calls, hashing) of one extra untimed "
+                                                "end-to-end step to this JSON file")
     ap.add_argument("--workload", default="shuffle", choices=["shuffle", "verify-mix"],
                     help="shuffle: re-encrypt + PoS prove + verify (BASELINE.json config 2, the default); "
                          "verify-mix: vmnv-style verification of a 3-party mix, threshold 2 (config 3)")
@@ -239,6 +241,8 @@ def main():
 
     if args.impl == "reference":
         return run_reference(args)
+    if args.trace:
+        os.environ["VMX_TRACE"] = "1"
 
     import numpy as np
     import torch
@@ -458,14 +462,18 @@ def main():
         pinned.numpy()[:] = np.frombuffer(ciph_bytes, dtype=np.uint8)
         h2d = d2h = 0
 
+        _span = importlib.import_module("verificatum-vmn_b200._trace").span
+
         def step_e2e(i: int):
             nonlocal h2d, d2h
             prover = mixnet.ShufflerSession(G, basic_pk, params, prg("e2e%d" % i))
             verifier = mixnet.ShufflerSession(G, basic_pk, params, prg("e2ev%d" % i))
             ciphPGroup = mixnet.getCiphPGroup(G, width)
-            w = ciphPGroup.toElementArray(n, vmx.eio.ByteTreeReader(memoryview(pinned.numpy())))
-            proof, _ = prover.shuffle(width, w, generators=generators)
-            ok, out = verifier.verify(width, w, proof, generators=generators)
+            w = ciphPGroup.toElementArray(n, vmx.eio.ByteTreeReader(memoryview(pinned.numpy()).toreadonly()))
+            with _span("e2e.shuffle"):
+                proof, _ = prover.shuffle(width, w, generators=generators)
+            with _span("e2e.verify"):
+                ok, out = verifier.verify(width, w, proof, generators=generators)
             if not ok:
                 raise SystemExit("bench e2e: verifier rejected an honest proof")
             out.free()
@@ -486,6 +494,13 @@ def main():
             buf = io.StringIO()
             pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(18)
             sys.stderr.write(buf.getvalue())
+        if args.trace and rank == 0:
+            tr = importlib.import_module("verificatum-vmn_b200._trace")
+            tr.start()
+            with tr.span("e2e.step"):
+                step_e2e(98)
+            with open(args.trace, "w") as f:
+                json.dump(tr.stop(), f)
         barrier()
         t0 = time.time()
         k = max(1, min(args.steps, 2))

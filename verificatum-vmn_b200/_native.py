@@ -39,6 +39,9 @@ SIGNATURES = {
     "vmx_ctx_create_modp": (C.c_int, [_U8, _U8, _U8, _SZ, C.c_int, _PP]),
     "vmx_ctx_create_ecq": (C.c_int, [_U8, _U8, _U8, _U8, _U8, _U8, _SZ, C.c_int, _PP]),
     "vmx_ctx_destroy": (None, [_P]),
+    "vmx_host_alloc": (C.c_int, [C.c_int, _SZ, _PP]),
+    "vmx_host_free": (None, [_P]),
+    "vmx_host_pool_bytes": (_SZ, []),
     "vmx_ctx_elem_bytes": (_SZ, [_P]),
     "vmx_ctx_ring_bytes": (_SZ, [_P]),
     "vmx_ctx_sync": (C.c_int, [_P]),
@@ -136,6 +139,9 @@ def load(path: str | None = None):
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("VMX_TRACE"):  # development aid (bench.py --trace): record every ABI call with its times
+        from ._trace import TracedLibrary
+        lib = TracedLibrary(lib)
     _lib, _lib_path = lib, path
     return lib
 
@@ -147,3 +153,17 @@ def check(status: int) -> None:
     if status == VMX_EFORMAT:
         raise ArithmFormatError(status, msg)
     raise VmxError(status, msg)
+
+
+def host_buffer(device: int, nbytes: int):
+    """A pinned, pooled host buffer of `nbytes` bytes as a numpy uint8 array (include/vmx.h, "pinned host
+    buffers"); it goes back to the pool when the last view of it is garbage-collected."""
+    import weakref
+
+    import numpy as np
+    lib = load()
+    p = C.c_void_p()
+    check(lib.vmx_host_alloc(device, max(1, nbytes), C.byref(p)))
+    raw = (C.c_uint8 * max(1, nbytes)).from_address(p.value)
+    weakref.finalize(raw, lib.vmx_host_free, p.value)
+    return np.frombuffer(raw, dtype=np.uint8, count=nbytes)

@@ -168,6 +168,24 @@ class Permutation:
         pass
 
 
+_PINNED_MIN = 1 << 16
+
+
+def _host_buffer(device: int, nbytes: int) -> np.ndarray:
+    """Destination of a device-to-host copy: page-locked and pooled (vmx_host_alloc) when it is large enough
+    to matter, so that the copy is one DMA transfer and does not hold up the stream behind it."""
+    if nbytes < _PINNED_MIN:
+        return np.empty(nbytes, dtype=np.uint8)
+    return nat.host_buffer(device, nbytes)
+
+
+def _install_host_buffers(device: int) -> None:
+    """Published messages (ByteTreeBasic.to_buffer) are assembled in page-locked memory too: whoever imports
+    them next (a verifier in the same process, a file writer) reads them by DMA."""
+    from . import eio
+    eio.set_buffer_factory(lambda nbytes: nat.host_buffer(device, nbytes))
+
+
 class ByteTreeDeviceArray(ByteTreeBasic):
     """toByteTree() of a device array.  The serialisation -- the leaves of the node, headers included,
     written by the engine in exactly that form (vmx_*_to_leaves) -- is produced when the tree is first
@@ -465,7 +483,7 @@ class PRingElementArray:
         if self._leaves is None:
             if self.h is None:
                 raise ArithmError("byte tree of a freed array")
-            buf = np.empty(self.size() * (5 + self.ring.byte_len), dtype=np.uint8)
+            buf = _host_buffer(self.ring.group.device, self.size() * (5 + self.ring.byte_len))
             nat.check(self._lib.vmx_rarr_to_leaves(self.h, _ptr(buf)))
             self._leaves = buf
         return self._leaves
@@ -554,6 +572,8 @@ class ModPGroup(PGroup):
                                           C.byref(ctx)))
         self.ctx = ctx
         self._lib = lib
+        self.device = device
+        _install_host_buffers(device)
         self.elem_bytes = int(lib.vmx_ctx_elem_bytes(ctx))
         self.ring_bytes = int(lib.vmx_ctx_ring_bytes(ctx))
         self.pRing = PField(self)
@@ -745,6 +765,8 @@ class ECqPGroup(ModPGroup):
                                          _be(self.gy, 32), _be(self.q, 32), 32, device, C.byref(ctx)))
         self.ctx = ctx
         self._lib = lib
+        self.device = device
+        _install_host_buffers(device)
         self.elem_bytes = int(lib.vmx_ctx_elem_bytes(ctx))
         self.coord_bytes = self.elem_bytes // 2
         self.ring_bytes = int(lib.vmx_ctx_ring_bytes(ctx))
@@ -1027,7 +1049,7 @@ class PGroupElementArray:
         if self._leaves is None:
             if self.h is None:
                 raise ArithmError("byte tree of a freed array")
-            buf = np.empty(self.group._leaves_bytes(self.size()), dtype=np.uint8)
+            buf = _host_buffer(self.group.device, self.group._leaves_bytes(self.size()))
             nat.check(self._lib.vmx_garr_to_leaves(self.h, _ptr(buf)))
             self._leaves = buf
         return self._leaves

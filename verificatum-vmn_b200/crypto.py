@@ -14,6 +14,8 @@ import queue
 import struct
 import threading
 
+from . import _trace
+
 
 class HashfunctionHeuristic:
     def __init__(self, name: str = "SHA-256"):
@@ -85,8 +87,13 @@ class RandomOracleDigest:
         self.nbytes = 4
 
     def update(self, data) -> None:
-        self.h.update(data)
-        self.nbytes += len(data) if not hasattr(data, "nbytes") else data.nbytes
+        n = len(data) if not hasattr(data, "nbytes") else data.nbytes
+        if _trace.enabled and n >= 1 << 16:
+            with _trace.span("sha256.update", n):
+                self.h.update(data)
+        else:
+            self.h.update(data)
+        self.nbytes += n
 
     def digest(self) -> bytes:
         prg = PRGHeuristic(self.hf)
@@ -145,7 +152,8 @@ class AsyncDigest:
 
     def digest(self) -> bytes:
         self._q.put(None)
-        self._t.join()
+        with _trace.span("digest.wait"):
+            self._t.join()
         if self._err is not None:
             raise self._err
         return self.inner.digest()

@@ -25,6 +25,17 @@ class EIOException(ValueError):
     """Malformed byte tree (com.verificatum.eio.EIOException)."""
 
 
+_buffer_factory = None
+_BUFFER_MIN = 1 << 20
+
+
+def set_buffer_factory(fn) -> None:
+    """`fn(nbytes)` -> writable uint8 numpy array for large serialisations (arithm installs the engine's pool of
+    page-locked buffers, include/vmx.h vmx_host_alloc)."""
+    global _buffer_factory
+    _buffer_factory = fn
+
+
 class ByteTreeBasic:
     def update(self, digest) -> None:
         raise NotImplementedError
@@ -36,6 +47,35 @@ class ByteTreeBasic:
         out = _Collector()
         self.update(out)
         return out.value()
+
+    def to_buffer(self):
+        """The serialisation as a read-only bytes-like object: a `bytes` when it is small, else a memoryview of
+        a pooled page-locked buffer, which the engine imports (and exports into) by DMA.  This is what a
+        message published by a mix-server is held in (mixnet.ShuffleProof)."""
+        if _buffer_factory is None:
+            return self.to_bytes()
+        n = self.total_bytes()
+        if n < _BUFFER_MIN:
+            return self.to_bytes()
+        out = _Writer(_buffer_factory(n))
+        self.update(out)
+        return out.value()
+
+
+class _Writer:
+    def __init__(self, buf: np.ndarray):
+        self.buf = buf
+        self.pos = 0
+
+    def update(self, data) -> None:
+        a = np.frombuffer(data, dtype=np.uint8)
+        self.buf[self.pos:self.pos + a.size] = a
+        self.pos += a.size
+
+    def value(self):
+        if self.pos != self.buf.size:
+            raise AssertionError("total_bytes() disagrees with update(): %d != %d" % (self.buf.size, self.pos))
+        return memoryview(self.buf).toreadonly()
 
 
 class _Collector:

@@ -106,7 +106,8 @@ class PoSBasicTW:
         self.s = s
 
     # -- :436-482 (prover) and :379 (verifier: pi is None)
-    def precompute(self, g, h, pi: Optional[Permutation] = None) -> None:
+    def precompute(self, g, h, pi: Optional[Permutation] = None, on_u=None) -> None:
+        """`on_u(u)` is called as soon as the permutation commitment exists (its hashing can start)."""
         self._precompute_common(g, h)
         if pi is None:
             return
@@ -118,6 +119,8 @@ class PoSBasicTW:
         tmp1.free()
         self.u = tmp2.permute(pi)
         tmp2.free()
+        if on_u is not None:
+            on_u(self.u)
         # randomizers and blinder A' = g^alpha * prod h_i^epsilon_i    :465-481
         self.alpha = self.pRing.randomElement(self.randomSource, self.rbitlen)
         epsilonBitLength = self.ebitlen + self.vbitlen + self.rbitlen
@@ -257,25 +260,45 @@ class PoSBasicTW:
             return False
         return self.verifyParsed()
 
-    def verifyParsed(self) -> bool:
-        """The five checks of verify() on already-imported replies (:1008-1066)."""
-        g, h, u, v = self.g, self.h, self.u, self.v
+    def verifyIndependent(self) -> None:
+        """The operands of the five checks that depend on the proof alone, not on the batching vector or the
+        challenge: g^k_A * prod h^k_E, g^k_B * B_shift^k_E (the largest item of a verification), g^k_C, g^k_D,
+        pk^-k_F * prod w'^k_E and C (:1013,1021,1030-1033,1048,1055,1063).  A verifier that derives its challenges
+        by hashing (PoSTW.verify) queues these while the hash is being computed; the verdict is the same
+        conjunction of the same five equalities."""
+        g, h, u = self.g, self.h, self.u
         h0 = h.get(0)
-        self.C = u.prod().div(h.prod())                                          # :1013
-        self.D = self.B.get(self.size - 1).div(h0.exp(self.e.prod()))            # :1014
-        verdictA = self.A.expMul(v, self.Ap).equals(g.exp(self.k_A).mul(h.expProd(self.k_E)))  # :1020-1021
-        B_exp_v = self.B.exp(v)                                                  # :1028
-        leftSide = B_exp_v.mul(self.Bp)
+        ind = {}
+        ind["C"] = u.prod().div(h.prod())                                        # :1013
+        ind["rightA"] = g.exp(self.k_A).mul(h.expProd(self.k_E))                 # :1021
         g_exp_k_B = g.exp(self.k_B)                                              # :1030
         B_shift = self.B.shiftPush(h0)                                           # :1031
         B_shift_exp_k_E = B_shift.exp(self.k_E)                                  # :1032
-        rightSide = g_exp_k_B.mul(B_shift_exp_k_E)
+        ind["rightB"] = g_exp_k_B.mul(B_shift_exp_k_E)
+        _free(g_exp_k_B, B_shift, B_shift_exp_k_E)
+        ind["rightC"] = g.exp(self.k_C)                                          # :1048
+        ind["rightD"] = g.exp(self.k_D)                                          # :1055
+        ind["rightF"] = self.pkey.exp(self.k_F.neg()).mul(self.wp.expProd(self.k_E))  # :1063
+        self._ind = ind
+
+    def verifyParsed(self) -> bool:
+        """The five checks of verify() on already-imported replies (:1008-1066)."""
+        if getattr(self, "_ind", None) is None:
+            self.verifyIndependent()
+        ind, self._ind = self._ind, None
+        h, v = self.h, self.v
+        h0 = h.get(0)
+        self.C = ind["C"]
+        self.D = self.B.get(self.size - 1).div(h0.exp(self.e.prod()))            # :1014
+        verdictA = self.A.expMul(v, self.Ap).equals(ind["rightA"])               # :1020-1021
+        B_exp_v = self.B.exp(v)                                                  # :1028
+        leftSide = B_exp_v.mul(self.Bp)
+        rightSide = ind["rightB"]
         verdictB = leftSide.equals(rightSide)                                    # :1035
-        _free(B_exp_v, leftSide, g_exp_k_B, B_shift, B_shift_exp_k_E, rightSide)
-        verdictC = self.C.expMul(v, self.Cp).equals(g.exp(self.k_C))             # :1048
-        verdictD = self.D.expMul(v, self.Dp).equals(g.exp(self.k_D))             # :1055
-        verdictF = self.F.expMul(v, self.Fp).equals(
-            self.pkey.exp(self.k_F.neg()).mul(self.wp.expProd(self.k_E)))        # :1062-1063
+        _free(B_exp_v, leftSide, rightSide)
+        verdictC = self.C.expMul(v, self.Cp).equals(ind["rightC"])               # :1048
+        verdictD = self.D.expMul(v, self.Dp).equals(ind["rightD"])               # :1055
+        verdictF = self.F.expMul(v, self.Fp).equals(ind["rightF"])               # :1062-1063
         self.verdicts = (verdictA, verdictB, verdictC, verdictD, verdictF)
         return verdictA and verdictB and verdictC and verdictD and verdictF
 
@@ -286,6 +309,10 @@ class PoSBasicTW:
 
     # -- :1088-1101
     def free(self) -> None:
+        ind = getattr(self, "_ind", None)
+        if ind is not None:
+            _free(ind["rightB"])
+            self._ind = None
         _free(self.r, self.u, self.e, self.b, self.B, self.Bp, self.ipe, self.beta, self.epsilon, self.k_B, self.k_E)
         self.r = self.u = self.e = self.b = self.B = self.Bp = self.ipe = self.beta = self.epsilon = None
         self.k_B = self.k_E = None
@@ -544,6 +571,7 @@ class PoSTW:
         self.prg, self.randomSource, self.challenger = prg, randomSource, challenger
         self.P = self.V = None
         self._seedDigest = None
+        self._seedFed = 0       # how far the streamed seed hash has got: 0 (g, h), 1 (.. u), 2 (.. pk, w)
 
     # -- :80-88 / :167-173
     def precompute(self, g, h, pi: Optional[Permutation] = None) -> None:
@@ -552,11 +580,24 @@ class PoSTW:
         # prover starts hashing them BEFORE queueing its exponentiations and the worker thread hashes beside them.
         if pi is not None and getattr(self, "_seedDigest", None) is None:
             self._seedDigest = self._seed_begin(g, h)
-        basic.precompute(g, h, pi)
         if pi is None:
+            basic.precompute(g, h)
             self.V = basic
         else:
+            basic.precompute(g, h, pi, on_u=self._seed_u)   # u is hashed while A' is being computed
             self.P = basic
+
+    def _seed_u(self, u) -> None:
+        u.toByteTree().update(self._seedDigest)
+        self._seedFed = 1
+
+    def continueSeed(self, pkey, w) -> None:
+        """Prover: the public key and the input ciphertexts are known before the output exists -- hash them
+        (after g, h, u) while the device re-encrypts."""
+        if self._seedDigest is not None and self._seedFed == 1:
+            pkey.toByteTree().update(self._seedDigest)
+            w.toByteTree().update(self._seedDigest)
+            self._seedFed = 2
 
     def beginSeed(self, g, h) -> None:
         """Prover: start hashing (g, h) now -- call it before any device work is queued (the serialisation of
@@ -570,10 +611,12 @@ class PoSTW:
         h.toByteTree().update(d)
         return d
 
-    def _seed_finish(self, d: AsyncDigest, u, pkey, w, wp) -> AsyncDigest:
-        u.toByteTree().update(d)
-        pkey.toByteTree().update(d)
-        w.toByteTree().update(d)
+    def _seed_finish(self, d: AsyncDigest, u, pkey, w, wp, fed: int = 0) -> AsyncDigest:
+        if fed < 1:
+            u.toByteTree().update(d)
+        if fed < 2:
+            pkey.toByteTree().update(d)
+            w.toByteTree().update(d)
         wp.toByteTree().update(d)
         return d
 
@@ -586,10 +629,10 @@ class PoSTW:
     def prove(self, pkey, w, wp, s):
         P = self.P
         P.setInstance(pkey, w, wp, s)
-        permutationCommitment = P.u.toByteTree().to_bytes()
+        permutationCommitment = P.u.toByteTree().to_buffer()
         d = self._seedDigest if self._seedDigest is not None else self._seed_begin(P.g, P.h)
-        self._seedDigest = None
-        self._seed_finish(d, P.u, pkey, w, wp)
+        fed, self._seedDigest, self._seedFed = self._seedFed, None, 0
+        self._seed_finish(d, P.u, pkey, w, wp, fed)
         P.commitIndependent()            # the GPU works on C', D', F' while the worker thread hashes
         prgSeed = self.challenger.finish(d)
         # challenge = RO(node(leaf(seed), commitment)) (:146-147): B is hashed while B' is being computed
@@ -602,7 +645,7 @@ class PoSTW:
             child.update(cd)
         challengeBytes = self.challenger.finish(cd)
         reply = P.reply(_to_positive(challengeBytes))
-        out = (permutationCommitment, commitment.to_bytes(), reply.to_bytes())
+        out = (permutationCommitment, commitment.to_buffer(), reply.to_buffer())
         P.free()
         return out
 
@@ -621,6 +664,16 @@ class PoSTW:
             commitmentTree = V.setCommitment(ByteTreeReader(commitment))
         except EIOException:
             commitmentTree = V.setCommitment(ByteTreeReader(ByteTreeContainer().to_bytes()))
+        # ... and so do the replies: everything in the five checks that is a function of the proof alone (two of
+        # the three array exponentiations among it) is queued before the seed is known.  A reply that does not
+        # parse rejects, as in PoSBasicTW.verify (:1000-1006), once the challenge has been derived.
+        ciphPRing = pkey.project(0).getPGroup().getPRing()
+        try:
+            parsed = V._parseReplies(ciphPRing, ByteTreeReader(reply))
+        except EIOException:
+            parsed = False
+        if parsed:
+            V.verifyIndependent()
         prgSeed = self.challenger.finish(d)
         V.setBatchVector(prgSeed)
         # the challenge is hashed while the device computes A and F
@@ -629,11 +682,7 @@ class PoSTW:
         V.computeAF()
         challengeBytes = self.challenger.finish(cd)
         V.setChallenge(_to_positive(challengeBytes))
-        try:
-            verdict = V.verify(ByteTreeReader(reply))
-        except EIOException:
-            verdict = False
-        return verdict
+        return V.verifyParsed() if parsed else False
 
     def free(self) -> None:
         for b in (self.P, self.V):
@@ -662,7 +711,7 @@ class PoSCTW:
         challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitment)
         challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
         reply = P.reply(_to_positive(challengeBytes))
-        out = (commitment.to_bytes(), reply.to_bytes())
+        out = (commitment.to_buffer(), reply.to_buffer())
         P.free()
         return out
 
@@ -710,7 +759,7 @@ class CCPoSW:
         challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitment)
         challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
         reply = P.reply(_to_positive(challengeBytes))
-        out = (commitment.to_bytes(), reply.to_bytes())
+        out = (commitment.to_buffer(), reply.to_buffer())
         P.free()
         return out
 

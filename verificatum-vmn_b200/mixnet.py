@@ -146,17 +146,21 @@ class ShufflerSession:
         rbitlen = self.params.rbitlen
         P = self._pos()
         P.beginSeed(generators.getPGroup().getg(), generators)   # Fiat-Shamir hashing of (g, h) runs beside the GPU
+        # The random source is consumed in the reference's order (exponents, permutation, then the proof's r,
+        # alpha, epsilon), but the device computes u BEFORE the re-encryption factors: u is the third input of
+        # the Fiat-Shamir seed, and its hashing -- then that of pk and w -- runs beside the re-encryption.
         reencExponents = exponentsPRing.randomElementArray(size, self.randomSource, rbitlen)       # :400-403
-        reencFactors = widePublicKey.exp(reencExponents)                                           # :407
         permutation = Permutation.random(size, self.randomSource, rbitlen, self.pGroup.basic()[0])                       # :408-409
         P.precompute(generators.getPGroup().getg(), generators, permutation)                       # :414
+        reencFactors = widePublicKey.exp(reencExponents)                                           # :407
+        P.continueSeed(widePublicKey, ciphertexts)
         reenc = ciphertexts.mul(reencFactors)                                                      # :273
         reencFactors.free()
         inverse = permutation.inv()
         output = reenc.permute(inverse)                                                            # :278
         reenc.free()
         inverse.free()
-        output_bytes = output.toByteTree().to_bytes()                                              # :284
+        output_bytes = output.toByteTree().to_buffer()                                              # :284
         pc, commitment, reply = P.prove(widePublicKey, ciphertexts, output, reencExponents)        # :289
         reencExponents.free()
         if own_generators:
@@ -233,7 +237,7 @@ class PermutationCommitment:
         """Returns (PermutationCommitment%02d.bt, PoSCCommitment%02d.bt, PoSCReply%02d.bt)."""
         c, r = self._posc().prove(self.pGroup.getg(), self.generators, self.commitment, self.exponents,
                                   self.permutation)
-        return self.commitment.toByteTree().to_bytes(), c, r
+        return self.commitment.toByteTree().to_buffer(), c, r
 
     # -- :293-346 for l != j
     def verify(self, commitment: bytes, poscCommitment: bytes, poscReply: bytes, raisedExponent=None) -> bool:
@@ -356,7 +360,7 @@ class CommittedShuffler:
         inverse = pc.permutation.inv()
         output = reenc.permute(inverse)                                                              # :792
         reenc.free()
-        output_bytes = output.toByteTree().to_bytes()
+        output_bytes = output.toByteTree().to_buffer()
         c, r = self._ccpos().prove(self.generators.getPGroup().getg(), self.generators, pc.commitment,
                                    self.widePublicKey, ciphertexts, output, pc.exponents, pc.permutation,
                                    self.reencExponents)                                              # :808-819

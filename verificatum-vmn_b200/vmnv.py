@@ -135,7 +135,7 @@ class MixNetElGamal:
 
     # -- mixnet/MixNetElGamalSession: the first `threshold` parties shuffle in turn
     def shuffle(self, ciphertexts):
-        self.nizkp["Ciphertexts.bt"] = ciphertexts.toByteTree().to_bytes()
+        self.nizkp["Ciphertexts.bt"] = ciphertexts.toByteTree().to_buffer()
         active = self.threshold
         self.nizkp["proofs/activethreshold"] = str(active).encode()
         inp, owned = ciphertexts, False
@@ -159,7 +159,7 @@ class MixNetElGamal:
         u = ciphertexts.project(0)
         f = {l: eg.decryptionFactors(u, self.secretKeys[l], k) for l in range(1, k + 1)}
         for l in range(1, k + 1):
-            self.nizkp[ProofDirectory.DFfile(l)] = f[l].toByteTree().to_bytes()
+            self.nizkp[ProofDirectory.DFfile(l)] = f[l].toByteTree().to_buffer()
         correct = [False] + [True] * k
         combined = eg.combineDecryptionFactors(f, correct, k, t)
         challenger = ShufflerSession(self.pGroup, self.fullPublicKey, p, None).challenger
@@ -187,7 +187,7 @@ class MixNetElGamal:
         combined.free()
         for l in f:
             f[l].free()
-        self.nizkp["Plaintexts.bt"] = plaintexts.toByteTree().to_bytes()
+        self.nizkp["Plaintexts.bt"] = plaintexts.toByteTree().to_buffer()
         return plaintexts
 
     def run(self, ciphertexts):
