@@ -174,6 +174,13 @@ def run_verify_mix(args, G, prg, stream, world, rank, local_rank, torch, dist):
     for _ in range(max(1, min(args.warmup, 2))):
         if not V.verify(nizkp)["accepted"]:
             raise SystemExit("bench: the verifier rejected an honest mix")
+    if args.trace and rank == 0:
+        tr = importlib.import_module("verificatum-vmn_b200._trace")
+        tr.start()
+        with tr.span("e2e.step"):
+            V.verify(nizkp)
+        with open(args.trace, "w") as f:
+            json.dump(tr.stop(), f)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()

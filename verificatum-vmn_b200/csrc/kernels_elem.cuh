@@ -167,6 +167,49 @@ VMX_KERNEL(N) k_mul(const uint32_t* __restrict__ a_, size_t acap, const uint32_t
   store_elem<N>(a, out, ocap, i);
 }
 
+// ------------------------------------------------------------------ batched inversion (Montgomery's trick)
+// One level of a product tree with interleaved chunks: thread t of T owns the elements t, t + T, t + 2T, ...
+// (consecutive threads touch consecutive elements: every access is a coalesced 16-byte vector per lane).
+//   up:   pre[i] = a[t] * a[t + T] * ... * a[i] for the elements after the first, part[t] = the whole product;
+//   down: given inv[t] = part[t]^-1 (consumed as scratch), out[i] = a[i]^-1 -- `out` is the `pre` of the up pass.
+// 3 multiplications per element and one inversion at the root, against ~1.2 * |p| for a Fermat inversion of
+// every element.  Only one residue lives in registers at a time (two would not fit at 96 limbs): the running
+// inverse stays in its slot of `inv` and is streamed as the second operand.
+template <int N>
+VMX_KERNEL(N) k_inv_up(const uint32_t* __restrict__ a_, size_t acap, size_t n, size_t T, uint32_t* __restrict__ pre,
+                       size_t pcap, uint32_t* __restrict__ part, size_t partcap, const __grid_constant__ MontParams<N> M) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  uint32_t x[N];
+  load_elem<N>(x, a_, acap, t);
+  for (size_t i = t + T; i < n; i += T) {
+    mont_mul<N>(x, GlobalLoader(a_, acap, i), M);
+    store_elem<N>(x, pre, pcap, i);
+  }
+  store_elem<N>(x, part, partcap, t);
+}
+
+template <int N>
+VMX_KERNEL(N) k_inv_down(const uint32_t* __restrict__ a_, size_t acap, size_t n, size_t T, uint32_t* inv, size_t icap,
+                         uint32_t* out, size_t ocap, const __grid_constant__ MontParams<N> M) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  uint32_t x[N];
+  size_t i = t + ((n - 1 - t) / T) * T;  // last element of this thread
+  for (; i > t; i -= T) {
+    // a[i]^-1 = (running inverse of the prefix up to i) * (prefix up to i - T)
+    if (i - T == t) load_elem<N>(x, a_, acap, t); else load_elem<N>(x, out, ocap, i - T);
+    mont_mul<N>(x, GlobalLoader(inv, icap, t), M);
+    store_elem<N>(x, out, ocap, i);
+    // running inverse <- running inverse * a[i]
+    load_elem<N>(x, a_, acap, i);
+    mont_mul<N>(x, GlobalLoader(inv, icap, t), M);
+    store_elem<N>(x, inv, icap, t);
+  }
+  load_elem<N>(x, inv, icap, t);
+  store_elem<N>(x, out, ocap, t);
+}
+
 // out[i] = a[i] * b[i]^iters  (benchmark of the raw modmul path)
 template <int N>
 VMX_KERNEL(N) k_mul_iter(const uint32_t* __restrict__ a_, const uint32_t* __restrict__ b_, uint32_t* __restrict__ out,

@@ -788,6 +788,62 @@ static int prg_bytes_dev(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uint64
 using namespace vmx;
 
 // ====================================================================== C ABI
+// out[i] = a[i]^-1 for n residues in Montgomery form (kernels_elem.cuh, "batched inversion"): a product tree of
+// arity kInvArity down to ONE residue, which the host inverts by the binary extended Euclid (limbs_inv_mod).
+constexpr size_t kInvArity = 4;
+template <int N>
+static int inv_batch(vmx_ctx* c, const uint32_t* a, size_t acap, size_t n, uint32_t* out, size_t ocap) {
+  struct Level { const uint32_t* a; size_t acap, n, T; uint32_t* out; size_t ocap; };
+  std::vector<Level> lv;
+  std::vector<std::unique_ptr<ElemBuf>> bufs;
+  const auto P = c->P.params<N>();
+  Level cur{a, acap, n, 0, out, ocap};
+  ElemBuf* root = nullptr;
+  for (;;) {
+    cur.T = (cur.n + kInvArity - 1) / kInvArity;
+    bufs.emplace_back(new ElemBuf);  // the partial products = the array of the next level
+    ElemBuf* part = bufs.back().get();
+    VMX_TRY(part->alloc_elems(c, cur.T));
+    VMX_LAUNCH(c, k_inv_up<N>, nblocks(cur.T), kThreads, 0, cur.a, cur.acap, cur.n, cur.T, cur.out, cur.ocap, part->d(),
+               part->cap, P);
+    VMX_CHECK_LAUNCH();
+    c->modmuls += cur.n - cur.T;
+    lv.push_back(cur);
+    if (cur.T == 1) { root = part; break; }
+    bufs.emplace_back(new ElemBuf);  // prefixes, then inverses, of the next level
+    ElemBuf* o = bufs.back().get();
+    VMX_TRY(o->alloc_elems(c, cur.T));
+    cur = Level{part->d(), part->cap, cur.T, 0, o->d(), o->cap};
+  }
+  // root: (x R)^-1 on the host, back to Montgomery form with two multiplications by R^2
+  std::vector<uint32_t> img(root->cap * N), x(N), r(N);
+  VMX_CU(cudaMemcpyAsync(img.data(), root->p, img.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+  VMX_CU(cudaStreamSynchronize(c->stream));
+  for (int j = 0; j < N; j++) x[j] = img[((size_t)(j >> 2) * root->cap) * 4 + (j & 3)];
+  if (!limbs_inv_mod(r.data(), x.data(), c->P.n, N)) { set_error("inv: an element of the array is not invertible"); return VMX_EFORMAT; }
+  image_put(img, root->cap, 0, r.data(), N);
+  VMX_CU(cudaMemcpyAsync(root->p, img.data(), img.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  VMX_CU(cudaStreamSynchronize(c->stream));  // img is a stack-lifetime buffer
+  for (int k = 0; k < 2; k++) {
+    VMX_LAUNCH(c, k_mul_const<N>, 1, kThreads, 0, root->d(), root->cap, c->P.consts, (size_t)4, (size_t)0,
+               (const uint32_t*)nullptr, (size_t)0, root->d(), root->cap, (size_t)1, P);
+    VMX_CHECK_LAUNCH();
+  }
+  c->modmuls += 2;
+  // down: the inverses of level l + 1 are the chunk inverses of level l
+  uint32_t* inv = root->d();
+  size_t icap = root->cap;
+  for (size_t l = lv.size(); l-- > 0;) {
+    const Level& L = lv[l];
+    VMX_LAUNCH(c, k_inv_down<N>, nblocks(L.T), kThreads, 0, L.a, L.acap, L.n, L.T, inv, icap, L.out, L.ocap, P);
+    VMX_CHECK_LAUNCH();
+    c->modmuls += 2 * (L.n - L.T);
+    inv = L.out;
+    icap = L.ocap;
+  }
+  return VMX_OK;
+}
+
 extern "C" {
 
 const char* vmx_last_error(void) { return g_err; }
@@ -1624,7 +1680,12 @@ int vmx_inv(const vmx_garr* a, vmx_garr** out) {
     *out = r;
     return VMX_OK;
   }
-  return exp_scalar_limbs(c, a, c->pm2.data(), out);
+  vmx_garr* r = nullptr;
+  VMX_TRY(new_garr(c, a->n, &r));
+  std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(r, vmx_garr_free);
+  if (a->n) VMX_DISPATCH(c->nl, VMX_TRY(inv_batch<N>(c, a->d, a->cap, a->n, r->d, r->cap)));
+  *out = guard.release();
+  return VMX_OK;
 }
 
 int vmx_prod(const vmx_garr* a, uint8_t* out_be) {
