@@ -52,6 +52,15 @@ def group_ops(vmx, bits, n):
     assert X.get(n - 1).value == xs[-1]
     assert X.equals(X.copyOfRange(0, n)) and not X.equals(X.shiftPush(G.getg()))
     assert vals(X.inv()) == oar.g_inv(OG, xs)
+    # simultaneous exponentiation x_i^s * y_i^{e_i} (the verifier's B-chain check): long and short exponents
+    Yr = X.permute(A.Permutation(perm))
+    ys = oar.permute(xs, perm)
+    assert vals(X.expMulExp(s, Yr, E)) == [a * b % p for a, b in zip(oar.g_exp(OG, xs, s.value), oar.g_exp(OG, ys, es))]
+    k613 = [rnd.randrange(1 << 613) % q for _ in range(n)]
+    K = R.toElementArray([A.PFieldElement(R, e) for e in k613])
+    assert vals(X.expMulExp(s, Yr, K)) == [a * b % p for a, b in zip(oar.g_exp(OG, xs, s.value), oar.g_exp(OG, ys, k613))]
+    zero = A.PFieldElement(R, 0)
+    assert vals(X.expMulExp(zero, Yr, K)) == oar.g_exp(OG, ys, k613)
     Y = X.mul(X)
     cols = G.expProd([X, Y], [5, -3], 3)
     assert vals(cols) == [pow(x, 5, p) * pow(pow(x * x % p, 3, p), -1, p) % p for x in xs]

@@ -76,6 +76,7 @@ SIGNATURES = {
     "vmx_rarr_unpack_rows": (C.c_int, [_P, _SZ, _P, _P, _SZ, _PP]),
     "vmx_exp_var": (C.c_int, [_P, _P, _PP]),
     "vmx_exp_scalar": (C.c_int, [_P, _U8, _PP]),
+    "vmx_exp_scalar_var": (C.c_int, [_P, _U8, _P, _P, _PP]),
     "vmx_expprod": (C.c_int, [_PP, _SZ, _P, _P]),
     "vmx_expprod_cols": (C.c_int, [_PP, _SZ, C.POINTER(C.c_int64), _PP]),
     "vmx_mul": (C.c_int, [_P, _P, _PP]),

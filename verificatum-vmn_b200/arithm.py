@@ -1002,6 +1002,13 @@ class PGroupElementArray:
             nat.check(self._lib.vmx_exp_scalar(self.h, _be(e.value, self.group.ring_bytes), C.byref(h)))
         return self._new(h)
 
+    def expMulExp(self, x: PFieldElement, other: "PGroupElementArray", y: PRingElementArray):
+        """this[i]^x * other[i]^y[i] by simultaneous exponentiation (vmx_exp_scalar_var): what the verifier's
+        B.exp(v) and B_shift.exp(k_E) (PoSBasicTW.java:1028-1032) become once both are on one side."""
+        h = C.c_void_p()
+        nat.check(self._lib.vmx_exp_scalar_var(self.h, _be(x.value, self.group.ring_bytes), other.h, y.h, C.byref(h)))
+        return self._new(h)
+
     def expProd(self, e: PRingElementArray) -> PGroupElement:
         """prod_i this[i]^e[i] (PoSBasicTW.java:408-409,481,690,1021,1063)."""
         return expProdMany([self], e)[0]

@@ -348,6 +348,54 @@ VMX_KERNEL(N) k_exp_var(const uint32_t* __restrict__ a_, size_t acap, const uint
   store_elem<N>(a, out, ocap, i);
 }
 
+// out[i] = a[i]^{x} * b[i]^{y[i]}: simultaneous exponentiation, one chain of squarings for both bases (the
+// verifier's B_i^v * B_{i-1}^{-k_E,i}, hvzk/PoSBasicTW.java:1028-1035, costs max(|v|, |k_E|) squarings instead of
+// |v| + |k_E|).  x is element 0 of x_ (one exponent for all), y per element; both use w-bit windows at the same
+// positions.  tabA / tabB: 2^w entries per element each, entry d of element i at d*n + i.
+template <int N>
+VMX_KERNEL(N) k_exp_var2(const uint32_t* __restrict__ a_, size_t acap, const uint32_t* __restrict__ x_, size_t xcap,
+                         int xbits, const uint32_t* __restrict__ b_, size_t bcap, const uint32_t* __restrict__ y_,
+                         size_t ycap, int ybits, int w, size_t n, uint32_t* __restrict__ tabA,
+                         uint32_t* __restrict__ tabB, size_t tabcap, const uint32_t* __restrict__ one,
+                         uint32_t* __restrict__ out, size_t ocap, const __grid_constant__ MontParams<N> M) {
+  VMX_DYN_SMEM(uint2, smem);
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint2* sc = smem + threadIdx.x;
+  const unsigned ss = blockDim.x;
+  uint32_t a[N];
+  for (int side = 0; side < 2; side++) {
+    const uint32_t* src = side ? b_ : a_;
+    const size_t scap = side ? bcap : acap;
+    uint32_t* tab = side ? tabB : tabA;
+    load_elem<N>(a, one, 4, 1);
+    store_elem<N>(a, tab, tabcap, i);
+    load_elem<N>(a, src, scap, i);
+    store_elem<N>(a, tab, tabcap, n + i);
+    const GlobalLoader Bse(src, scap, i);
+    for (int d = 2; d < (1 << w); d++) {
+      mont_mul<N>(a, Bse, M);
+      store_elem<N>(a, tab, tabcap, (size_t)d * n + i);
+    }
+  }
+  const int nwy = (ybits + w - 1) / w, nwx = (xbits + w - 1) / w;
+  const int nwin = nwy > nwx ? nwy : nwx;
+  for (int k = nwin - 1; k >= 0; k--) {
+    const uint32_t dy = window_bits<N>(y_, ycap, i, k * w, w);
+    if (k == nwin - 1) {
+      load_elem<N>(a, tabB, tabcap, (size_t)dy * n + i);
+    } else {
+      for (int s = 0; s < w; s++) mont_sqr<N>(a, sc, ss, M);
+      mont_mul<N>(a, GlobalLoader(tabB, tabcap, (size_t)dy * n + i), M);
+    }
+    if (k < nwx) {  // uniform over the grid: x is one exponent
+      const uint32_t dx = window_bits<N>(x_, xcap, 0, k * w, w);
+      if (dx) mont_mul<N>(a, GlobalLoader(tabA, tabcap, (size_t)dx * n + i), M);
+    }
+  }
+  store_elem<N>(a, out, ocap, i);
+}
+
 // ------------------------------------------------------------------ data movement (uint4 granularity)
 // out[dst(i)] = in[src(i)] for plane-wise copies; one thread per (plane, element).
 // bcast != 0: every destination receives source element `bidx` (fill).

@@ -546,6 +546,54 @@ static int exp_var_run(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32_
   return VMX_OK;
 }
 
+// out[i] = a[i]^{X[0]} * b[i]^{Y[i]} (k_exp_var2); arrays too small to fill the machine with one thread per element
+// take the warp-cooperative path of exp_var_run twice.
+template <int N>
+static int exp_var2_run(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32_t* X, size_t xcap, int xbits,
+                        const uint32_t* b, size_t bcap, const uint32_t* Y, size_t ycap, int ybits, size_t n,
+                        uint32_t* out, size_t ocap) {
+  const MontParams<N> M = c->P.params<N>();
+  if (n == 0) return VMX_OK;
+  bool split = xbits == 0 || ybits == 0;
+#ifndef VMX_HOST_EMUL
+  split = split || n <= kCoopMaxElems;
+#endif
+  if (split) {
+    ElemBuf t;
+    VMX_TRY(t.alloc_elems(c, n));
+    VMX_TRY(exp_var_run<N>(c, a, acap, X, xcap, true, xbits, n, t.d(), t.cap));
+    VMX_TRY(exp_var_run<N>(c, b, bcap, Y, ycap, false, ybits, n, out, ocap));
+    VMX_LAUNCH(c, k_mul<N>, nblocks(n), kThreads, 0, t.d(), t.cap, out, ocap, out, ocap, n, M);
+    VMX_CHECK_LAUNCH();
+    c->modmuls += n;
+    return VMX_OK;
+  }
+  int w = 1;
+  {
+    double best = 1e300;
+    for (int ww = 1; ww <= 6; ww++) {
+      const double cost = 2.0 * (1 << ww) + std::max(xbits, ybits) + (double)(xbits + ybits) / ww;
+      if (cost < best) { best = cost; w = ww; }
+    }
+  }
+  const size_t wave = wave_threads(c);
+  size_t chunk = (size_t)(6e9 / (2.0 * (double)(1u << w) * N * 4));
+  chunk = std::max(wave, chunk / wave * wave);
+  chunk = std::min(chunk, n);
+  ElemBuf tabA, tabB;
+  VMX_TRY(tabA.alloc_elems(c, chunk << w));
+  VMX_TRY(tabB.alloc_elems(c, chunk << w));
+  const int nwin = (std::max(xbits, ybits) + w - 1) / w, nwx = (xbits + w - 1) / w;
+  for (size_t i0 = 0; i0 < n; i0 += chunk) {
+    const size_t m = std::min(chunk, n - i0);
+    VMX_LAUNCH(c, k_exp_var2<N>, nblocks(m), kThreads, kThreads * N * 4, a + 4 * i0, acap, X, xcap, xbits, b + 4 * i0,
+               bcap, Y + 4 * i0, ycap, ybits, w, m, tabA.d(), tabB.d(), tabA.cap, c->P.consts, out + 4 * i0, ocap, M);
+    VMX_CHECK_LAUNCH();
+    c->modmuls += (uint64_t)m * (2 * ((1u << w) - 2) + (uint64_t)(nwin - 1) * (w + 1) + nwx);
+  }
+  return VMX_OK;
+}
+
 // ------------------------------------------------------------------ Pippenger
 struct MexpPlan {
   int c = 0, W = 0, J = 0;
@@ -1557,6 +1605,42 @@ int vmx_exp_scalar(const vmx_garr* a, const uint8_t* e_be, vmx_garr** out) {
   std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(r, vmx_garr_free);
   if (c->kind == 1) VMX_TRY(ec_exp_var_run(c, a->d, a->cap, e.d(), e.cap, true, ebits, a->n, r->d, r->cap));
   else VMX_DISPATCH(c->nl, VMX_TRY(exp_var_run<N>(c, a->d, a->cap, e.d(), e.cap, true, ebits, a->n, r->d, r->cap)));
+  *out = guard.release();
+  return VMX_OK;
+}
+
+int vmx_exp_scalar_var(const vmx_garr* a, const uint8_t* x_be, const vmx_garr* b, const vmx_rarr* y, vmx_garr** out) {
+  if (!out) return VMX_EARG;
+  *out = nullptr;
+  if (!a || !x_be || !b || !y) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  VMX_TRY(same_ctx(b->ctx, c));
+  VMX_TRY(same_ctx(y->ctx, c));
+  if (a->n != b->n || a->n != y->n) { set_error("exp: size mismatch %zu, %zu, %zu", a->n, b->n, y->n); return VMX_ESIZE; }
+  ElemBuf x;
+  VMX_TRY(upload_one(c, x_be, false, x));
+  uint32_t limbs[kMaxLimbs];
+  if (!be_to_limbs(x_be, c->rb, limbs, kMaxLimbs)) return VMX_EFORMAT;
+  const int xbits = limbs_bits(limbs, kMaxLimbs);
+  int ybits = 0;
+  VMX_TRY(rarr_bitlen(y, &ybits));
+  vmx_garr* r = nullptr;
+  VMX_TRY(new_garr(c, a->n, &r));
+  std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(r, vmx_garr_free);
+  if (c->kind == 1) {  // curve groups: the two scalar multiplications, then one addition per point
+    vmx_garr* t = nullptr;
+    VMX_TRY(new_garr(c, a->n, &t));
+    std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> tguard(t, vmx_garr_free);
+    VMX_TRY(ec_exp_var_run(c, a->d, a->cap, x.d(), x.cap, true, xbits, a->n, t->d, t->cap));
+    VMX_TRY(ec_exp_var_run(c, b->d, b->cap, y->d, y->cap, false, ybits, a->n, r->d, r->cap));
+    vmx_garr* prod = nullptr;
+    VMX_TRY(vmx_mul(t, r, &prod));
+    *out = prod;
+    return VMX_OK;
+  }
+  VMX_DISPATCH(c->nl, VMX_TRY(exp_var2_run<N>(c, a->d, a->cap, x.d(), x.cap, xbits, b->d, b->cap, y->d, y->cap, ybits,
+                                              a->n, r->d, r->cap)));
   *out = guard.release();
   return VMX_OK;
 }

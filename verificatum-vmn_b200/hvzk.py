@@ -271,11 +271,13 @@ class PoSBasicTW:
         ind = {}
         ind["C"] = u.prod().div(h.prod())                                        # :1013
         ind["rightA"] = g.exp(self.k_A).mul(h.expProd(self.k_E))                 # :1021
-        g_exp_k_B = g.exp(self.k_B)                                              # :1030
+        # B^v * B' == g^k_B * B_shift^k_E (:1028-1035) is checked as B^v * (B_shift^-1)^k_E * B' == g^k_B: the two
+        # variable-base exponentiations then share one chain of squarings (expMulExp); the inverses cost three
+        # multiplications per element and do not depend on the challenge.
+        ind["rightB"] = g.exp(self.k_B)                                          # :1030
         B_shift = self.B.shiftPush(h0)                                           # :1031
-        B_shift_exp_k_E = B_shift.exp(self.k_E)                                  # :1032
-        ind["rightB"] = g_exp_k_B.mul(B_shift_exp_k_E)
-        _free(g_exp_k_B, B_shift, B_shift_exp_k_E)
+        ind["B_shift_inv"] = B_shift.inv()
+        _free(B_shift)
         ind["rightC"] = g.exp(self.k_C)                                          # :1048
         ind["rightD"] = g.exp(self.k_D)                                          # :1055
         ind["rightF"] = self.pkey.exp(self.k_F.neg()).mul(self.wp.expProd(self.k_E))  # :1063
@@ -291,11 +293,11 @@ class PoSBasicTW:
         self.C = ind["C"]
         self.D = self.B.get(self.size - 1).div(h0.exp(self.e.prod()))            # :1014
         verdictA = self.A.expMul(v, self.Ap).equals(ind["rightA"])               # :1020-1021
-        B_exp_v = self.B.exp(v)                                                  # :1028
-        leftSide = B_exp_v.mul(self.Bp)
+        both = self.B.expMulExp(v, ind["B_shift_inv"], self.k_E)                 # :1028,1032
+        leftSide = both.mul(self.Bp)
         rightSide = ind["rightB"]
         verdictB = leftSide.equals(rightSide)                                    # :1035
-        _free(B_exp_v, leftSide, rightSide)
+        _free(both, leftSide, rightSide, ind["B_shift_inv"])
         verdictC = self.C.expMul(v, self.Cp).equals(ind["rightC"])               # :1048
         verdictD = self.D.expMul(v, self.Dp).equals(ind["rightD"])               # :1055
         verdictF = self.F.expMul(v, self.Fp).equals(ind["rightF"])               # :1062-1063
@@ -311,7 +313,7 @@ class PoSBasicTW:
     def free(self) -> None:
         ind = getattr(self, "_ind", None)
         if ind is not None:
-            _free(ind["rightB"])
+            _free(ind["rightB"], ind["B_shift_inv"])
             self._ind = None
         _free(self.r, self.u, self.e, self.b, self.B, self.Bp, self.ipe, self.beta, self.epsilon, self.k_B, self.k_E)
         self.r = self.u = self.e = self.b = self.B = self.Bp = self.ipe = self.beta = self.epsilon = None
@@ -442,14 +444,14 @@ class PoSCBasicTW:
         if not A.expMul(v, self.Ap).equals(g.exp(self.k_A).mul(h.expProd(self.k_E))):
             verdict = False
         if verdict:
-            B_exp_v = self.B.exp(v)
-            leftSide = B_exp_v.mul(self.Bp)
-            g_exp_k_B = g.exp(self.k_B)
+            # as in PoSBasicTW.verifyParsed: B^v * (B_shift^-1)^k_E * B' == g^k_B, one chain of squarings
             B_shift = self.B.shiftPush(h0)
-            B_shift_exp_k_E = B_shift.exp(self.k_E)
-            rightSide = g_exp_k_B.mul(B_shift_exp_k_E)
+            B_shift_inv = B_shift.inv()
+            both = self.B.expMulExp(v, B_shift_inv, self.k_E)
+            leftSide = both.mul(self.Bp)
+            rightSide = g.exp(self.k_B)
             B_res = leftSide.equals(rightSide)
-            _free(B_exp_v, leftSide, g_exp_k_B, B_shift, B_shift_exp_k_E, rightSide)
+            _free(B_shift, B_shift_inv, both, leftSide, rightSide)
             if not B_res:
                 verdict = False
         if verdict and not C.expMul(v, self.Cp).equals(g.exp(self.k_C)):
