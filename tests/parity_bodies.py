@@ -67,6 +67,9 @@ def group_ops(vmx, bits, n):
     # single elements go through the engine as well
     a = A.PGroupElement(G, xs[0])
     assert a.exp(s).value == pow(xs[0], s.value, p)
+    for e in (q - 5, q - 1, q - (1 << 200)):                                   # short negative exponents
+        assert a.exp(A.PFieldElement(R, e)).value == pow(xs[0], e, p)
+    assert A.PGroupElement(G, p - 1).exp(A.PFieldElement(R, q - 5)).value == pow(p - 1, q - 5, p)   # not a member
     assert a.mul(A.PGroupElement(G, xs[1])).value == xs[0] * xs[1] % p
     assert a.inv().value == pow(xs[0], -1, p)
     assert a.expMul(s, A.PGroupElement(G, xs[1])).value == pow(xs[0], s.value, p) * xs[1] % p

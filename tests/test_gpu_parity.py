@@ -134,7 +134,7 @@ def test_ec_accept_reject_at_scale(engine_cuda):
     pb.accept_reject_properties(engine_cuda, "P-256", 300000)
 
 
-@pytest.mark.parametrize("spec,n", [(3072, 12), (512, 300), ("P-256", 200)])
+@pytest.mark.parametrize("spec,n", [(3072, 5), (512, 300), ("P-256", 80)])
 def test_mix_and_vmnv_parity(engine_cuda, spec, n, tmp_path):
     """A 3-party mix with threshold 2 and its vmnv-style verification (BASELINE.json config 3 at oracle size)."""
     pb.mix_parity(engine_cuda, spec, n, tmpdir=tmp_path)
@@ -145,7 +145,7 @@ def test_ec_edge_cases(engine_cuda, curve):
     pb.ec_edge_cases(engine_cuda, curve)
 
 
-@pytest.mark.parametrize("spec,width,n", [(2048, 3, 40), ('P-256', 3, 300)])
+@pytest.mark.parametrize("spec,width,n", [(2048, 3, 16), ("P-256", 3, 120)])
 def test_wide_ciphertexts_parity(engine_cuda, spec, width, n):
     """BASELINE.json config 4: width-3 ciphertexts, shuffle + PoS and pre-computation + CCPoS."""
     pb.wide_shuffle_parity(engine_cuda, spec, width, n)

@@ -910,9 +910,23 @@ class PGroupElement:
             return self.group._garr(h, e.size())
         if isinstance(e, int):
             e = self.group.pRing.toElement(e)
+        # An exponent just below the group order is a small negative one (the modified Lagrange coefficients of
+        # DistrElGamalSessionBasic.combine, :642-678, arrive as q - |lambda|): x^(q-m) = (x^-1)^m for x of order
+        # dividing q -- an inversion and a short chain instead of |q| squarings on one warp.
+        m = self.group.q - e.value
+        if e.value and m.bit_length() + 64 < e.value.bit_length() and self._order_divides_q():
+            return self.inv().exp(self.group.pRing.toElement(m))
         buf = np.empty(self.group.elem_bytes, dtype=np.uint8)
         nat.check(lib.vmx_elem_exp(self.group.ctx, self._be(), _be(e.value, self.group.ring_bytes), _ptr(buf)))
         return PGroupElement(self.group, int.from_bytes(buf.tobytes(), "big"))
+
+    def _order_divides_q(self) -> bool:
+        G = self.group
+        if G.is_curve:
+            return True     # prime-order curve: every point of the group
+        if G.p == 2 * G.q + 1:
+            return _jacobi(self.value, G.p) == 1
+        return False
 
     def mul(self, o: "PGroupElement") -> "PGroupElement":
         lib = self.group._lib

@@ -158,6 +158,11 @@ class AsyncDigest:
             raise self._err
         return self.inner.digest()
 
+    def abandon(self) -> None:
+        """Stop the worker without waiting for it (a speculative hash whose premise failed)."""
+        self._err = self._err or RuntimeError("abandoned")
+        self._q.put(None)
+
     @property
     def nbytes(self) -> int:
         return self.inner.nbytes

@@ -25,7 +25,7 @@ from . import elgamal as eg
 from .arithm import ArithmFormatException, PFieldElement
 from .crypto import PRGHeuristic
 from .eio import ByteTreeContainer, ByteTreeLeaf, ByteTreeReader, EIOException, booleanArrayToByteTree
-from .hvzk import _to_positive
+from .hvzk import _to_positive, node_header
 from .mixnet import SessionParams, ShuffleProof, ShufflerSession, getCiphPGroup
 
 
@@ -227,6 +227,15 @@ class MixNetElGamalVerifyFiatShamirSession:
             raise VerificationError("Unable to read array %s! (%s)" % (name, e))
 
     def verify(self, nizkp: ProofDirectory) -> Dict[str, object]:
+        self._spec = None
+        try:
+            return self._verify(nizkp)
+        finally:
+            if self._spec is not None:   # a fail-stop condition was met while the speculative hash was running
+                self._spec.abandon()
+                self._spec = None
+
+    def _verify(self, nizkp: ProofDirectory) -> Dict[str, object]:
         p, k, threshold, G = self.params, self.k, self.threshold, self.pGroup
         rep = self.report = {"shuffles": {}, "decryption": None}
         if self._file(nizkp, "version").decode() != p.version:
@@ -274,6 +283,27 @@ class MixNetElGamalVerifyFiatShamirSession:
         # ---- shuffles :1403-1520
         generators = session.deriveGenerators(size)
         inp, valid = ciphertexts, 0
+        # The seed of the decryption proof is RO(node(node(g, L_active), node(node(pk), node(f_1..f_k)))) (:1586-1600):
+        # 190 MB of SHA-256 at N = 10^5 that depend on files only.  It is hashed on a worker thread WHILE the
+        # shuffles are verified, speculating that the last shuffle is valid and that the files are canonical;
+        # the speculation is checked below and the hash redone in place if it does not hold.
+        lastName = ProofDirectory.Lfile(active)
+        if lastName not in nizkp:
+            lastName = "ShuffledCiphertexts.bt"
+        dfNames = [ProofDirectory.DFfile(l) for l in range(1, k + 1)]
+        spec = None
+        if lastName in nizkp and all(nm in nizkp for nm in dfNames):
+            spec = challenger.begin(8 * PRGHeuristic().minNoSeedBytes())
+            spec.update(node_header(2))
+            spec.update(node_header(2))
+            G.getg().toByteTree().update(spec)
+            spec.update(nizkp[lastName])
+            spec.update(node_header(2))
+            ByteTreeContainer(*[c.toByteTree() for c in coeffs]).update(spec)
+            spec.update(node_header(k))
+            for nm in dfNames:
+                spec.update(nizkp[nm])
+            self._spec = spec
         for l in range(1, active + 1):
             name = ProofDirectory.Lfile(l)
             if l == active and name not in nizkp:
@@ -308,8 +338,17 @@ class MixNetElGamalVerifyFiatShamirSession:
         combined = eg.combineDecryptionFactors(f, correct, k, threshold)
         basic = eg.DistrElGamalSessionBasic(0, k, threshold, p.ebitlenro, p.rbitlen, PRGHeuristic())
         basic.setInstance(G.getg(), u, pkeys, f, None, fullPKey.project(1), combined)
-        seedData = _decryption_seed_data(G.getg(), mixed, coeffs, f, k)
-        prgSeed = challenger.challenge(seedData, 8 * PRGHeuristic().minNoSeedBytes(), p.rbitlen)
+        holds = spec is not None and rep["shuffles"].get(active) is True and \
+            len(nizkp[lastName]) == mixed.toByteTree().total_bytes() and \
+            all(len(nizkp[nm]) == f[l].toByteTree().total_bytes() for l, nm in zip(range(1, k + 1), dfNames))
+        self._spec = None
+        if holds:
+            prgSeed = challenger.finish(spec)
+        else:
+            if spec is not None:
+                spec.abandon()
+            seedData = _decryption_seed_data(G.getg(), mixed, coeffs, f, k)
+            prgSeed = challenger.challenge(seedData, 8 * PRGHeuristic().minNoSeedBytes(), p.rbitlen)
         basic.setBatchVector(prgSeed)
         basic.batchInput()
         basic.batchCombined()
