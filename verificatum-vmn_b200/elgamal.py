@@ -12,7 +12,7 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence
 
-from .arithm import ArithmFormatException, LargeIntegerArray, PFieldElement
+from .arithm import ArithmFormatException, LargeIntegerArray, PFieldElement, expMany
 from .eio import ByteTreeBasic, ByteTreeContainer, ByteTreeReader, EIOException
 from .hvzk import ProtocolError
 
@@ -185,14 +185,19 @@ class DistrElGamalSessionBasic:
         self.combinedyp = self.yp[1].getPGroup().getONE()
         self.combinedBp = self.Bp[1].getPGroup().getONE()
         self.combinedk_x = self.k_x[1].getPRing().getZERO()
-        t, l = 0, 1
+        t, l, used = 0, 1, []
         while t < self.threshold and l <= self.k:
             if correct[l]:
-                self.combinedyp = self.combinedyp.mul(self.yp[l].exp(exponents[t]))
-                self.combinedBp = self.combinedBp.mul(self.Bp[l].exp(exponents[t]))
-                self.combinedk_x = self.combinedk_x.add(self.k_x[l].mul(exponents[t]))
+                used.append((l, t))
                 t += 1
             l += 1
+        # the 2|S| single-element exponentiations are independent: one small array call (arithm.expMany)
+        powers = expMany([self.yp[l] for l, _ in used] + [self.Bp[l] for l, _ in used],
+                         [exponents[t] for _, t in used] * 2)
+        for j, (l, t) in enumerate(used):
+            self.combinedyp = self.combinedyp.mul(powers[j])
+            self.combinedBp = self.combinedBp.mul(powers[len(used) + j])
+            self.combinedk_x = self.combinedk_x.add(self.k_x[l].mul(exponents[t]))
 
     # :683-685
     def batchCombined(self) -> None:
@@ -201,8 +206,9 @@ class DistrElGamalSessionBasic:
     # :693-700
     def verifyCombined(self, v: int) -> bool:
         pfev = self.pField.toElement(v)
-        return (self.combinedy.inv().exp(pfev).mul(self.combinedyp).equals(self.g.exp(self.combinedk_x))
-                and self.combinedB.exp(pfev).mul(self.combinedBp).equals(self.A.exp(self.combinedk_x)))
+        yv, Bv, Ak = expMany([self.combinedy.inv(), self.combinedB, self.A], [pfev, pfev, self.combinedk_x])
+        return (yv.mul(self.combinedyp).equals(self.g.exp(self.combinedk_x))
+                and Bv.mul(self.combinedBp).equals(Ak))
 
     # :707-709
     def batch(self, l: int) -> None:
