@@ -12,6 +12,10 @@ import sys
 
 import pytest
 
+# published messages of the small test instances take the pooled page-locked buffer path (read-only
+# memoryviews) that full-size ones take (eio.ByteTreeBasic.to_buffer); read when the package is imported
+os.environ.setdefault("VMX_BUFFER_MIN", "4096")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -24,7 +24,8 @@ def _run(world: int, bits, n: int, emul_lib: str):
     procs = []
     for rank in range(world):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(port), VMX_LIBRARY_PATH=emul_lib, OMP_NUM_THREADS="1")
+                   MASTER_PORT=str(port), VMX_LIBRARY_PATH=emul_lib, OMP_NUM_THREADS="1",
+                   VMX_BUFFER_MIN="512")   # published messages take the pooled-buffer (memoryview) path as at full size
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "parallel_worker.py"), "cpu",
                                        str(bits), str(n)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                       text=True))

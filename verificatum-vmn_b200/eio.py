@@ -13,6 +13,7 @@ is streamed into a digest or a file.
 """
 from __future__ import annotations
 
+import os
 import struct
 from typing import Iterable, List, Optional, Sequence
 
@@ -26,7 +27,7 @@ class EIOException(ValueError):
 
 
 _buffer_factory = None
-_BUFFER_MIN = 1 << 20
+_BUFFER_MIN = int(os.environ.get("VMX_BUFFER_MIN", 1 << 20))   # smaller serialisations stay `bytes`
 
 
 def set_buffer_factory(fn) -> None:
