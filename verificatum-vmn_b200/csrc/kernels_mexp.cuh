@@ -85,15 +85,56 @@ __global__ void k_chunk_fill(const uint32_t* __restrict__ seg_off, const uint32_
   chunks[c] = Chunk{b + l0, l1 - l0};
 }
 
+// 4b'. chunks ordered by length, longest first (counting sort over the lengths 0..K): the lanes of a warp of
+// k_seg_prod then multiply the same number of terms and finish together -- unsorted, a warp waits for its longest
+// chunk (a bucket of 25 terms is cut in 4 x 6.25, its neighbour of 24 in 3 x 8).  bins: K + 2 counters, zeroed;
+// after k_chunk_len_hist + k_chunk_len_offsets, bins[l] = first position of the chunks of length l.
+__global__ void k_chunk_len_hist(const Chunk* __restrict__ chunks, const uint32_t* __restrict__ nchunks_dev, int K,
+                                 uint32_t* __restrict__ bins) {
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = c < *nchunks_dev;
+  const uint32_t len = live ? min(chunks[c].len, (uint32_t)K) : 0;
+#ifndef VMX_HOST_EMUL
+  // one atomic per distinct length in the warp
+  const unsigned peers = __match_any_sync(0xffffffffu, live ? len : 0xffffffffu);
+  if (live && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&bins[len], (uint32_t)__popc(peers));
+#else
+  if (live) atomicAdd(&bins[len], 1u);
+#endif
+}
+__global__ void k_chunk_len_offsets(int K, uint32_t* __restrict__ bins) {  // one thread: descending lengths
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint32_t run = 0;
+  for (int l = K; l >= 0; l--) { const uint32_t cnt = bins[l]; bins[l] = run; run += cnt; }
+}
+__global__ void k_chunk_len_scatter(const Chunk* __restrict__ chunks, const uint32_t* __restrict__ nchunks_dev, int K,
+                                    uint32_t* __restrict__ bins, uint32_t* __restrict__ order) {
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = c < *nchunks_dev;
+  const uint32_t len = live ? min(chunks[c].len, (uint32_t)K) : 0;
+#ifndef VMX_HOST_EMUL
+  const unsigned peers = __match_any_sync(0xffffffffu, live ? len : 0xffffffffu);
+  const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (live && leader == lane) base = atomicAdd(&bins[len], (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  if (live) order[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)c;
+#else
+  if (live) order[atomicAdd(&bins[len], 1u)] = (uint32_t)c;
+#endif
+}
+
 // 4c. one thread per chunk: out[c] = prod_{k < len} V[idx[start + k]]   (len = 0 -> one).
 // The number of chunks lives on the device (*nchunks_dev): the grid is sized from a host bound.
+// order != null: thread t takes chunk order[t] (chunks of equal length side by side).
 template <int N>
 VMX_KERNEL(N) k_seg_prod(const uint32_t* __restrict__ V, size_t vcap, const uint32_t* __restrict__ idx,
                          const Chunk* __restrict__ chunks, const uint32_t* __restrict__ nchunks_dev,
-                         uint32_t* __restrict__ out, size_t ocap, const uint32_t* __restrict__ one,
-                         const __grid_constant__ MontParams<N> M) {
-  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= *nchunks_dev) return;
+                         const uint32_t* __restrict__ order, uint32_t* __restrict__ out, size_t ocap,
+                         const uint32_t* __restrict__ one, const __grid_constant__ MontParams<N> M) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *nchunks_dev) return;
+  const size_t c = order ? order[t] : t;
   const Chunk ch = chunks[c];
   uint32_t a[N];
   if (ch.len == 0) {

@@ -229,6 +229,13 @@ static int exclusive_scan(vmx_ctx* c, uint32_t* d, size_t n) {
   return VMX_OK;
 }
 
+static size_t wave_threads(const vmx_ctx* c);
+// chunks per round from which k_seg_prod takes them sorted by length (env VMX_MEXP_SORT_MIN: tests force it)
+static size_t mexp_sort_min(const vmx_ctx* c) {
+  static const long v = [] { const char* e = std::getenv("VMX_MEXP_SORT_MIN"); return e ? std::atol(e) : -1L; }();
+  return v >= 0 ? (size_t)v : 4 * wave_threads(c);
+}
+
 // ------------------------------------------------------------------ segmented products
 // out[s] = prod_{k in [seg_off[s], seg_off[s+1])} V[idx ? idx[k] : k]  (empty -> one) for
 // s < nseg.  `total_bound` >= seg_off[nseg].  Runs chunked rounds (K terms per thread).
@@ -259,9 +266,25 @@ static int seg_product(vmx_ctx* c, const Modulus& Mod, const uint32_t* V, size_t
     VMX_TRY(read_flags(c, 1));
     const bool last = (c->h_flag[0] == 0);  // every segment fits one chunk: chunk id == segment id
     const uint32_t* nch_dev = chunk_off.as<uint32_t>() + nseg;
+    // chunks of equal length side by side (worth it once there are several waves of them)
+    DevBuf order_buf, bins;
+    const uint32_t* order = nullptr;
+    if (nch_bound >= mexp_sort_min(c)) {
+      VMX_TRY(order_buf.alloc(c, nch_bound * 4));
+      VMX_TRY(bins.alloc(c, (K + 2) * 4));
+      VMX_CU(cudaMemsetAsync(bins.p, 0, (K + 2) * 4, c->stream));
+      VMX_LAUNCH(c, k_chunk_len_hist, nblocks(nch_bound, 256), 256, 0, chunks.as<Chunk>(), nch_dev, K, bins.as<uint32_t>());
+      VMX_CHECK_LAUNCH();
+      VMX_LAUNCH(c, k_chunk_len_offsets, 1, 32, 0, K, bins.as<uint32_t>());
+      VMX_CHECK_LAUNCH();
+      VMX_LAUNCH(c, k_chunk_len_scatter, nblocks(nch_bound, 256), 256, 0, chunks.as<Chunk>(), nch_dev, K,
+                 bins.as<uint32_t>(), order_buf.as<uint32_t>());
+      VMX_CHECK_LAUNCH();
+      order = order_buf.as<uint32_t>();
+    }
     if (last) {
       VMX_LAUNCH(c, k_seg_prod<N>, nblocks(nseg), kThreads, 0, cur_V, cur_vcap, cur_idx, chunks.as<Chunk>(), nch_dev,
-                 out, ocap, Mod.consts, M);
+                 order, out, ocap, Mod.consts, M);
       VMX_CHECK_LAUNCH();
       c->modmuls += cur_total;
       return VMX_OK;
@@ -269,7 +292,7 @@ static int seg_product(vmx_ctx* c, const Modulus& Mod, const uint32_t* V, size_t
     ElemBuf part;
     VMX_TRY(part.alloc_elems(c, nch_bound));
     VMX_LAUNCH(c, k_seg_prod<N>, nblocks(nch_bound), kThreads, 0, cur_V, cur_vcap, cur_idx, chunks.as<Chunk>(),
-               nch_dev, part.d(), part.cap, Mod.consts, M);
+               nch_dev, order, part.d(), part.cap, Mod.consts, M);
     VMX_CHECK_LAUNCH();
     c->modmuls += cur_total;
     // next round: values = partial products, segments = chunk ranges
