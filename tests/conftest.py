@@ -14,7 +14,7 @@ import pytest
 
 # published messages of the small test instances take the pooled page-locked buffer path (read-only
 # memoryviews) that full-size ones take (eio.ByteTreeBasic.to_buffer); read when the package is imported
-os.environ.setdefault("VMX_BUFFER_MIN", "4096")
+os.environ.setdefault("VMX_BUFFER_MIN", "256")
 # ... and their multi-exponentiations the length-sorted chunk order of full-size ones (csrc/vmx.cu, seg_product)
 os.environ.setdefault("VMX_MEXP_SORT_MIN", "1")
 

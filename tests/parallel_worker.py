@@ -173,8 +173,7 @@ def main():
         raw = bytearray(proof.commitment)
         raw[len(raw) // 2] ^= 1
         rej, out3 = verifier.verify(1, w, dataclasses.replace(proof, commitment=bytes(raw)))
-        published = tuple(bytes(getattr(proof, f.name)) for f in dataclasses.fields(proof))   # bytes-like -> bytes
-        return published, ok, out2.equals(out), rej, out3.equals(w)
+        return dataclasses.astuple(proof), ok, out2.equals(out), rej, out3.equals(w)
 
     f1, f2 = fs(G1), fs(GS)
     assert f1[1:] == (True, True, False, True) and f1 == f2, "sharded shuffle session differs on rank %d" % rank
@@ -188,7 +187,7 @@ def main():
         w = mix.demoCiphertexts(M.fullPublicKey, n, rs("mix/input"))
         M.run(w)
         rep = vm.MixNetElGamalVerifyFiatShamirSession(Gx, params, 3, 2).verify(M.nizkp)
-        return {name: bytes(data) for name, data in M.nizkp.items()}, rep
+        return dict(M.nizkp), rep
 
     m1, m2 = whole_mix(G1), whole_mix(GS)
     assert m1[1]["accepted"] and m1 == m2, "sharded mix differs from the single-process one on rank %d" % rank

@@ -50,7 +50,7 @@ class ByteTreeBasic:
         return out.value()
 
     def to_buffer(self):
-        """The serialisation as a read-only bytes-like object: a `bytes` when it is small, else a memoryview of
+        """The serialisation as an immutable bytes-like value: a `bytes` when it is small, else a `HostBytes` over
         a pooled page-locked buffer, which the engine imports (and exports into) by DMA.  This is what a
         message published by a mix-server is held in (mixnet.ShuffleProof)."""
         if _buffer_factory is None:
@@ -61,6 +61,54 @@ class ByteTreeBasic:
         out = _Writer(_buffer_factory(n))
         self.update(out)
         return out.value()
+
+
+class HostBytes:
+    """An immutable bytes-like value over a pooled page-locked buffer (Python 3.12 buffer protocol, PEP 688):
+    `memoryview(x)`, `bytearray(x)`, `bytes(x)`, `len(x)`, `x == b"..."`, slicing (-> bytes), file.write(x) and
+    hashlib's update(x) work as for `bytes`; copy / deepcopy return the value itself and pickling stores `bytes`,
+    so a dataclass holding it (mixnet.ShuffleProof) can go through dataclasses.asdict / replace."""
+
+    __slots__ = ("_a",)
+
+    def __init__(self, array: np.ndarray):
+        array.flags.writeable = False
+        self._a = array
+
+    def __buffer__(self, flags):
+        return memoryview(self._a)
+
+    def __len__(self) -> int:
+        return int(self._a.size)
+
+    def __bytes__(self) -> bytes:
+        return self._a.tobytes()
+
+    def __getitem__(self, k):
+        return int(self._a[k]) if isinstance(k, int) else self._a[k].tobytes()
+
+    def __eq__(self, o):
+        if isinstance(o, HostBytes):
+            o = o._a
+        try:
+            m = memoryview(o)
+        except TypeError:
+            return NotImplemented
+        return m.nbytes == self._a.size and memoryview(self._a) == m.cast("B")
+
+    __hash__ = None
+
+    def __copy__(self):
+        return self
+
+    def __deepcopy__(self, memo):
+        return self
+
+    def __reduce__(self):
+        return (bytes, (self._a.tobytes(),))
+
+    def __repr__(self):
+        return "HostBytes(%d bytes)" % self._a.size
 
 
 class _Writer:
@@ -76,7 +124,7 @@ class _Writer:
     def value(self):
         if self.pos != self.buf.size:
             raise AssertionError("total_bytes() disagrees with update(): %d != %d" % (self.buf.size, self.pos))
-        return memoryview(self.buf).toreadonly()
+        return HostBytes(self.buf)
 
 
 class _Collector:

@@ -99,8 +99,8 @@ class SessionParams:
 class ShuffleProof:
     """What one mix-server publishes for one shuffle: the files Ciphertexts%02d.bt,
     PermutationCommitment%02d.bt, PoSCommitment%02d.bt, PoSReply%02d.bt of the proof directory
-    (mixnet/MixNetElGamalSession.java:381-446, hvzk/PoSTW.java:281-307).  The fields are bytes-like: `bytes`, or a
-    read-only memoryview of a page-locked buffer when the message is large (eio.ByteTreeBasic.to_buffer)."""
+    (mixnet/MixNetElGamalSession.java:381-446, hvzk/PoSTW.java:281-307).  The fields are immutable bytes-like
+    values: `bytes`, or `eio.HostBytes` over a page-locked buffer when the message is large (ByteTreeBasic.to_buffer)."""
     output: bytes
     permutationCommitment: bytes
     commitment: bytes
