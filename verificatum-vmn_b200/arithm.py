@@ -176,14 +176,17 @@ def _host_buffer(device: int, nbytes: int) -> np.ndarray:
     to matter, so that the copy is one DMA transfer and does not hold up the stream behind it."""
     if nbytes < _PINNED_MIN:
         return np.empty(nbytes, dtype=np.uint8)
-    return nat.host_buffer(device, nbytes)
+    try:
+        return nat.host_buffer(device, nbytes)
+    except nat.VmxError:      # the host cannot page-lock more memory: a pageable buffer is only slower
+        return np.empty(nbytes, dtype=np.uint8)
 
 
 def _install_host_buffers(device: int) -> None:
     """Published messages (ByteTreeBasic.to_buffer) are assembled in page-locked memory too: whoever imports
     them next (a verifier in the same process, a file writer) reads them by DMA."""
     from . import eio
-    eio.set_buffer_factory(lambda nbytes: nat.host_buffer(device, nbytes))
+    eio.set_buffer_factory(lambda nbytes: _host_buffer(device, nbytes))
 
 
 class ByteTreeDeviceArray(ByteTreeBasic):
@@ -1140,6 +1143,21 @@ def expProdMany(arrays: Sequence[PGroupElementArray], e: PRingElementArray) -> L
     buf = np.empty((k, group.elem_bytes), dtype=np.uint8)
     nat.check(group._lib.vmx_expprod(arr, k, e.h, _ptr(buf)))
     return group._combine_partials([PGroupElement(group, int.from_bytes(buf[i].tobytes(), "big")) for i in range(k)])
+
+
+def expProdTogether(arrays: Sequence, e: PRingElementArray) -> list:
+    """[a.expProd(e) for a in arrays] for arrays (of a basic or of a product group) that share the exponent
+    array e -- u and w in computeAF (PoSBasicTW.java:408-409), h and w' in the checks (:1021,1063): ONE call into
+    the engine, so the exponent digits are sorted once and the Horner chains of all results (|e| dependent
+    squarings each, on one warp) run side by side instead of one after the other."""
+    flats = [a.basic() for a in arrays]
+    it = iter(expProdMany([x for f in flats for x in f], e))
+
+    def rebuild(arr):
+        if isinstance(arr, PPGroupElementArray):
+            return PPGroupElement(arr.group, [rebuild(c) for c in arr.comps])
+        return next(it)
+    return [rebuild(a) for a in arrays]
 
 
 # ====================================================================== product groups / rings

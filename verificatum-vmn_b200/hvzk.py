@@ -17,7 +17,7 @@ from __future__ import annotations
 from typing import Optional
 
 from .arithm import (ArithmFormatException, LargeIntegerArray, Permutation, PGroupElementArray, PPGroupElement,
-                     PRingElementArray)
+                     PRingElementArray, expProdTogether)
 import struct
 
 from .crypto import AsyncDigest, HashfunctionHeuristic, PRGHeuristic, RandomOracle
@@ -95,8 +95,7 @@ class PoSBasicTW:
 
     # -- :407-410
     def computeAF(self) -> None:
-        self.A = self.u.expProd(self.e)
-        self.F = self.w.expProd(self.e)
+        self.A, self.F = expProdTogether([self.u, self.w], self.e)
 
     # -- :421-429 / :495-501
     def setInstance(self, pkey: PPGroupElement, w, wp, s=None) -> None:
@@ -270,7 +269,8 @@ class PoSBasicTW:
         h0 = h.get(0)
         ind = {}
         ind["C"] = u.prod().div(h.prod())                                        # :1013
-        ind["rightA"] = g.exp(self.k_A).mul(h.expProd(self.k_E))                 # :1021
+        h_k_E, wp_k_E = expProdTogether([h, self.wp], self.k_E)                  # :1021,1063
+        ind["rightA"] = g.exp(self.k_A).mul(h_k_E)                               # :1021
         # B^v * B' == g^k_B * B_shift^k_E (:1028-1035) is checked as B^v * (B_shift^-1)^k_E * B' == g^k_B: the two
         # variable-base exponentiations then share one chain of squarings (expMulExp); the inverses cost three
         # multiplications per element and do not depend on the challenge.
@@ -280,7 +280,7 @@ class PoSBasicTW:
         _free(B_shift)
         ind["rightC"] = g.exp(self.k_C)                                          # :1048
         ind["rightD"] = g.exp(self.k_D)                                          # :1055
-        ind["rightF"] = self.pkey.exp(self.k_F.neg()).mul(self.wp.expProd(self.k_E))  # :1063
+        ind["rightF"] = self.pkey.exp(self.k_F.neg()).mul(wp_k_E)                # :1063
         self._ind = ind
 
     def verifyParsed(self) -> bool:
