@@ -546,6 +546,11 @@ def ec_group_ops(vmx, curve, n):
     assert vals(X.exp(F)) == [OG.op_exp(a, k) for a, k in zip(xs, f)]          # variable base, per element
     sc = R.toElement(rnd.randrange(1 << 200))
     assert vals(X.exp(sc)) == [OG.op_exp(a, sc.value) for a in xs]             # variable base, one exponent
+    # simultaneous scalar multiples sc * X_i + f_i * Y_i (units, equal and opposite operands among them)
+    want = [OG.op_mul(OG.op_exp(a, sc.value), OG.op_exp(b, k)) for a, b, k in zip(xs, ys, f)]
+    assert vals(X.expMulExp(sc, Y, F)) == want
+    assert vals(X.expMulExp(sc, X, F)) == [OG.op_exp(a, (sc.value + k) % OG.q) for a, k in zip(xs, f)]
+    assert all(v.is_unit() for v in vals(X.expMulExp(sc, X.inv(), ring([sc.value] * n))))
     assert elem_value(X.expProd(F)) == oar.g_exp_prod(OG, xs, f)               # multi-exponentiation
     short = [rnd.randrange(1 << 100) for _ in range(n)]
     assert elem_value(X.expProd(ring(short))) == oar.g_exp_prod(OG, xs, short)

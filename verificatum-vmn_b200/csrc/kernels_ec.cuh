@@ -437,6 +437,55 @@ VMX_EC_KERNEL k_ec_exp_var(const uint32_t* __restrict__ a_, size_t acap, const u
   ec_store_jac(P, jac, jcap, i);
 }
 
+// jac[i] = x * a[i] + y[i] * b[i] (x = element 0 of x_): both scalar multiples on ONE chain of doublings, the curve
+// form of k_exp_var2 (the verifier's v * B_i - k_E,i * B_{i-1}, hvzk/PoSBasicTW.java:1028-1035).  Two tables of 15
+// Jacobian multiples per point; the two additions of a window go through one addition site (code size).
+VMX_EC_KERNEL k_ec_exp_var2(const uint32_t* __restrict__ a_, size_t acap, const uint32_t* __restrict__ x_, size_t xcap,
+                            int xbits, const uint32_t* __restrict__ b_, size_t bcap, const uint32_t* __restrict__ y_,
+                            size_t ycap, int ybits, size_t n, uint32_t* __restrict__ tabA, uint32_t* __restrict__ tabB,
+                            size_t tabcap, uint32_t* __restrict__ jac, size_t jcap, const __grid_constant__ EcCurve C) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x[8], y[8];
+  Jac P;
+  bool use[2];
+#pragma unroll 1
+  for (int side = 0; side < 2; side++) {
+    uint32_t* tab = side ? tabB : tabA;
+    ec_load_affine(x, y, side ? b_ : a_, side ? bcap : acap, i);
+    use[side] = !aff_is_inf(x) && (side ? ybits : xbits) != 0;
+    if (!use[side]) continue;
+    jac_from_affine(P, x, y, C);
+    ec_store_jac(P, tab, tabcap, i);
+#pragma unroll 1
+    for (int d = 2; d < 16; d++) {
+      jac_madd<SOL>(P, x, y, C);
+      ec_store_jac(P, tab, tabcap, (size_t)(d - 1) * n + i);
+    }
+  }
+  const int nwx = (xbits + 3) / 4, nwy = (ybits + 3) / 4;
+  const int nwin = nwx > nwy ? nwx : nwy;
+  jac_set_inf(P, C);
+#pragma unroll 1
+  for (int k = nwin - 1; k >= 0; k--) {
+    if (k != nwin - 1) {
+#pragma unroll 1
+      for (int s = 0; s < 4; s++) jac_dbl<SOL>(P, C);
+    }
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+      if (!use[side]) continue;
+      const uint32_t d = side ? window_bits<8>(y_, ycap, i, 4 * k, 4) : window_bits<8>(x_, xcap, 0, 4 * k, 4);
+      if (d) {
+        Jac T;
+        ec_load_jac(T, side ? tabB : tabA, tabcap, (size_t)(d - 1) * n + i);
+        jac_add<SOL>(P, T, C);
+      }
+    }
+  }
+  ec_store_jac(P, jac, jcap, i);
+}
+
 // ------------------------------------------------------------------ segmented sums (Pippenger buckets, prod)
 // out[c] = sum_{k < len} V[idx[start + k]]; V affine (vjac = 0) or Jacobian (vjac = 1); out Jacobian.
 VMX_EC_KERNEL k_ec_seg_sum(const uint32_t* __restrict__ V, size_t vcap, int vjac, const uint32_t* __restrict__ idx,

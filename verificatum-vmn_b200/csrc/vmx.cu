@@ -1651,15 +1651,9 @@ int vmx_exp_scalar_var(const vmx_garr* a, const uint8_t* x_be, const vmx_garr* b
   vmx_garr* r = nullptr;
   VMX_TRY(new_garr(c, a->n, &r));
   std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> guard(r, vmx_garr_free);
-  if (c->kind == 1) {  // curve groups: the two scalar multiplications, then one addition per point
-    vmx_garr* t = nullptr;
-    VMX_TRY(new_garr(c, a->n, &t));
-    std::unique_ptr<vmx_garr, void (*)(vmx_garr*)> tguard(t, vmx_garr_free);
-    VMX_TRY(ec_exp_var_run(c, a->d, a->cap, x.d(), x.cap, true, xbits, a->n, t->d, t->cap));
-    VMX_TRY(ec_exp_var_run(c, b->d, b->cap, y->d, y->cap, false, ybits, a->n, r->d, r->cap));
-    vmx_garr* prod = nullptr;
-    VMX_TRY(vmx_mul(t, r, &prod));
-    *out = prod;
+  if (c->kind == 1) {
+    VMX_TRY(ec_exp_var2_run(c, a->d, a->cap, x.d(), x.cap, xbits, b->d, b->cap, y->d, y->cap, ybits, a->n, r->d, r->cap));
+    *out = guard.release();
     return VMX_OK;
   }
   VMX_DISPATCH(c->nl, VMX_TRY(exp_var2_run<N>(c, a->d, a->cap, x.d(), x.cap, xbits, b->d, b->cap, y->d, y->cap, ybits,

@@ -253,6 +253,28 @@ static int ec_exp_var_run(vmx_ctx* c, const uint32_t* a, size_t acap, const uint
   return ec_normalize(c, jac.d(), jac.cap, n, out, ocap);
 }
 
+// out[i] = X[0] * a[i] + Y[i] * b[i] (k_ec_exp_var2), normalised to affine
+static int ec_exp_var2_run(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32_t* X, size_t xcap, int xbits,
+                           const uint32_t* b, size_t bcap, const uint32_t* Y, size_t ycap, int ybits, size_t n,
+                           uint32_t* out, size_t ocap) {
+  if (!n) return VMX_OK;
+  LimbBuf jac, tabA, tabB;
+  VMX_TRY(jac.alloc_limbs(c, n, kJacLimbs));
+  size_t chunk = (size_t)(6e9 / (30.0 * kJacLimbs * 4));
+  chunk = std::min(std::max<size_t>(chunk & ~(size_t)1023, 1024), n);
+  VMX_TRY(tabA.alloc_limbs(c, chunk * 15, kJacLimbs));
+  VMX_TRY(tabB.alloc_limbs(c, chunk * 15, kJacLimbs));
+  const int nwx = (xbits + 3) / 4, nwy = (ybits + 3) / 4, nwin = std::max(nwx, nwy);
+  for (size_t i0 = 0; i0 < n; i0 += chunk) {
+    const size_t m = std::min(chunk, n - i0);
+    VMX_EC_LAUNCH(c, k_ec_exp_var2, ec_blocks(m), kEcThreads, 0, a + 4 * i0, acap, X, xcap, xbits, b + 4 * i0, bcap,
+               Y + 4 * i0, ycap, ybits, m, tabA.d(), tabB.d(), tabA.cap, jac.d() + 4 * i0, jac.cap, c->ecc);
+    VMX_CHECK_LAUNCH();
+    c->modmuls += (uint64_t)m * (28 * kMulMadd + (uint64_t)nwin * 4 * kMulDbl + (uint64_t)(nwx + nwy) * kMulAdd);
+  }
+  return ec_normalize(c, jac.d(), jac.cap, n, out, ocap);
+}
+
 // ------------------------------------------------------------------ segmented sums
 // out[s] = sum_{k in [seg_off[s], seg_off[s+1])} V[idx ? idx[k] : k] as Jacobian points (empty -> unit);
 // V affine (vjac = 0) or Jacobian.  Same chunked rounds as seg_product.
