@@ -87,6 +87,18 @@ class Comm:
         w = m.shape[1]
         counts = [bounds[r + 1] - bounds[r] for r in range(self.world)]
         mx = max(counts)
+        if min(counts) == mx and mx:
+            # equal shards: the gathered tensor IS the concatenation.  It is read back into one page-locked
+            # buffer (DMA) and handed on without a further copy -- these are the serialisations that get hashed.
+            with self.on_stream():
+                src = torch.from_numpy(np.ascontiguousarray(m).reshape(-1)).to(self.device)
+                dst = torch.empty(self.world * mx * w, dtype=torch.uint8, device=self.device)
+                self.dist.all_gather_into_tensor(dst, src, group=self.group)
+                full = self.host_buffer(self.world * mx * w)
+                torch.from_numpy(full).copy_(dst)
+            self.collectives += 1
+            self.bytes_exchanged += full.nbytes
+            return full.reshape(self.world * mx, w)
         with self.on_stream():
             src = torch.zeros((mx, w), dtype=torch.uint8, device=self.device)   # padded to the largest shard
             src[:m.shape[0]] = torch.from_numpy(np.ascontiguousarray(m)).to(self.device)
@@ -97,6 +109,13 @@ class Comm:
         self.collectives += 1
         self.bytes_exchanged += full.nbytes
         return full
+
+    def host_buffer(self, nbytes: int) -> np.ndarray:
+        """Host destination of a gathered serialisation: pooled page-locked memory beside a GPU."""
+        if self.device.type != "cuda":
+            return np.empty(nbytes, dtype=np.uint8)
+        from .arithm import _host_buffer
+        return _host_buffer(self.device.index or 0, nbytes)
 
     def all_and(self, flag: bool) -> bool:
         if self.world == 1:
@@ -353,7 +372,7 @@ class ShardedRingArray(PRingElementArray):
         """Serialisation of the WHOLE array (all shards, gathered to every rank), cached."""
         if self._leaves is None:
             w = 5 + self.ring.byte_len
-            m = np.empty((self.local_size(), w), dtype=np.uint8)
+            m = self.comm.host_buffer(self.local_size() * w).reshape(self.local_size(), w)
             nat.check(self._lib.vmx_rarr_to_leaves(self.h, _ptr(m)))
             self._leaves = np.ascontiguousarray(self.comm.allgather_matrix(m, self.bounds)).reshape(-1)
         return self._leaves
@@ -586,7 +605,7 @@ class ShardedGroupArray(PGroupElementArray):
         """Serialisation of the WHOLE array (all shards, gathered to every rank), cached."""
         if self._leaves is None and self.group.is_curve:
             cb, nloc = self.group.coord_bytes, self.local_size()
-            buf = np.empty(self.group._leaves_bytes(nloc), dtype=np.uint8)
+            buf = self.comm.host_buffer(self.group._leaves_bytes(nloc))
             nat.check(self._lib.vmx_garr_to_leaves(self.h, _ptr(buf)))
             run = nloc * (5 + cb)
             gx = self.comm.allgather_matrix(buf[5:5 + run].reshape(nloc, 5 + cb), self.bounds)
@@ -595,7 +614,7 @@ class ShardedGroupArray(PGroupElementArray):
             self._leaves = np.concatenate([hdr, gx.reshape(-1), hdr, gy.reshape(-1)])
         if self._leaves is None:
             w = 5 + self.group.elem_bytes
-            m = np.empty((self.local_size(), w), dtype=np.uint8)
+            m = self.comm.host_buffer(self.local_size() * w).reshape(self.local_size(), w)
             nat.check(self._lib.vmx_garr_to_leaves(self.h, _ptr(m)))
             self._leaves = np.ascontiguousarray(self.comm.allgather_matrix(m, self.bounds)).reshape(-1)
         return self._leaves
