@@ -90,6 +90,19 @@ def edge_cases(vmx, bits):
     assert [e.value for e in G.getg().exp(top).elements()] == [pow(g, q - 1, p)] * 4
     empty = G.toElementArray([])
     assert empty.size() == 0 and empty.to_matrix().shape == (0, G.elem_bytes)
+    assert empty.inv().size() == 0
+    # batched inversion: every shape of the product tree (arity 4), units and p - 1 among the elements;
+    # simultaneous exponentiation with a zero scalar / zero array and on the empty array
+    rnd = random.Random(bits)
+    for m in (1, 2, 3, 4, 5, 16, 17, 21, 65):
+        vs = [pow(g, rnd.randrange(1, q), p) for _ in range(m)]
+        vs[rnd.randrange(m)] = 1
+        V = G.toElementArray([A.PGroupElement(G, v) for v in vs])
+        assert [e.value for e in V.inv().elements()] == [pow(v, -1, p) for v in vs], m
+    assert empty.expMulExp(A.PFieldElement(R, 3), empty, R.toElementArray([])).size() == 0
+    assert [e.value for e in X.expMulExp(A.PFieldElement(R, 0), X, zeros).elements()] == [1, 1, 1, 1]
+    assert [e.value for e in X.expMulExp(A.PFieldElement(R, 2), X, top).elements()] == \
+        [pow(e.value, q + 1, p) for e in X.elements()]
     single = G.toElementArray([A.PGroupElement(G, g)])
     e1 = R.toElementArray([A.PFieldElement(R, 5)])
     assert single.expProd(e1).value == pow(g, 5, p) and single.prod().value == g
@@ -132,7 +145,6 @@ def edge_cases(vmx, bits):
             except A.ArithmFormatException:
                 pass
     # single-element inversion (host binary Euclid in the engine) against Python, incl. 1 and p-1
-    import random
     rnd = random.Random(bits)
     for v in [1, p - 1, 2, g, p - 2] + [rnd.randrange(1, p) for _ in range(12)]:
         assert A.PGroupElement(G, v).inv().value == pow(v, -1, p)
