@@ -107,12 +107,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if is_curve(args):
-        print(json.dumps({"impl": "reference", "unavailable": "the CPU restatement in C (oracle/cpu_ref.c) covers "
-                          "ModPGroup only; curve groups are checked against oracle/ec.py (Python)"}))
-        return
     res = cpu_baseline.run(bits=args.bits, n_total=args.n, sample=args.cpu_sample, steps=args.steps,
-                           warmup=min(args.warmup, 1))
+                           warmup=min(args.warmup, 1), group=args.group)
     line = {"metric": metric_name(args), "impl": "reference",
             "value": res["value"], "unit": "ciphertexts/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -525,10 +521,11 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu and not is_curve(args):
+    if rank == 0 and world == 1 and not args.no_cpu and args.width == 1:
         try:
             from oracle import cpu_baseline
-            res = cpu_baseline.run(bits=args.bits, n_total=n, sample=args.cpu_sample, steps=1, warmup=0)
+            res = cpu_baseline.run(bits=args.bits, n_total=n, sample=args.cpu_sample, steps=1, warmup=0,
+                                   group=args.group)
             cpu = {"value": res["value"], "unit": "ciphertexts/s", "cores": res["cores"], "kind": "port",
                    "sample": res["sample"]}
         except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line

@@ -167,3 +167,127 @@ def install(G, threads: int | None = None):
         ar.g_exp, ar.g_exp_prod, ar.g_mul = orig
         ar.parse_array = orig_parse
     return undo
+
+
+# ---------------------------------------------------------------------------------------------- curve groups
+def _lib_ec():
+    L = lib()
+    if not getattr(L, "_ec_ready", False):
+        vp, sz, ci = C.c_char_p, C.c_size_t, C.c_int
+        L.ref_ec_exp_array.argtypes = [vp, vp, ci, vp, ci, sz, vp, sz, ci]
+        L.ref_ec_mul_array.argtypes = [vp, vp, vp, sz, vp, ci]
+        L.ref_ec_fixed_table_create.argtypes = [vp, vp, ci, ci]
+        L.ref_ec_fixed_table_create.restype = C.c_void_p
+        L.ref_ec_fixed_table_free.argtypes = [C.c_void_p]
+        L.ref_ec_fixed_table_free.restype = None
+        L.ref_ec_fixed_exp.argtypes = [vp, C.c_void_p, vp, sz, vp, sz, ci]
+        L.ref_ec_expprod.argtypes = [vp, vp, vp, sz, vp, sz, ci, ci]
+        for f in (L.ref_ec_exp_array, L.ref_ec_mul_array, L.ref_ec_fixed_exp, L.ref_ec_expprod):
+            f.restype = None
+        L._ec_ready = True
+    return L
+
+
+class AccelEC:
+    """GMP-backed versions of the oracle's array operations over an oracle.ec.ECqPGroup (cpu_ref_ec.c): the CPU
+    baseline of the curve workloads.  Points cross as x || y (32 bytes each), the unit element as 64 bytes 0xff."""
+
+    XW = 32
+
+    def __init__(self, G, threads: int | None = None, fixed_window: int = 8, smul_width: int = 5):
+        from .ec import ECPoint, UNIT
+        self.G, self.ECPoint, self.UNIT = G, ECPoint, UNIT
+        self.curve = G.p.to_bytes(32, "big") + (G.a % G.p).to_bytes(32, "big") + (G.b % G.p).to_bytes(32, "big")
+        self.threads = threads or cores()
+        self.w, self.k = fixed_window, smul_width
+        self.tables = {}
+
+    def __del__(self):
+        try:
+            for h in self.tables.values():
+                _lib_ec().ref_ec_fixed_table_free(h)
+        except Exception:
+            pass
+
+    def _pt(self, P) -> bytes:
+        return b"\xff" * 64 if P.is_unit() else P.x.to_bytes(32, "big") + P.y.to_bytes(32, "big")
+
+    def _pack(self, pts) -> bytes:
+        return b"".join(self._pt(P) for P in pts)
+
+    def _unpack(self, raw: bytes, n: int):
+        out = []
+        for i in range(n):
+            c = raw[64 * i:64 * i + 64]
+            out.append(self.UNIT if c == b"\xff" * 64 else
+                       self.ECPoint(int.from_bytes(c[:32], "big"), int.from_bytes(c[32:], "big")))
+        return out
+
+    def _scalars(self, exps) -> bytes:
+        q = self.G.q
+        return b"".join((e % q).to_bytes(self.XW, "big") for e in exps)
+
+    def exp_fixed(self, base, exps):
+        n = len(exps)
+        key = self._pt(base)
+        if key not in self.tables:
+            self.tables[key] = _lib_ec().ref_ec_fixed_table_create(key, self.curve, self.G.q.bit_length(), self.w)
+        out = C.create_string_buffer(64 * n)
+        _lib_ec().ref_ec_fixed_exp(out, self.tables[key], self._scalars(exps), n, self.curve, self.XW, self.threads)
+        return self._unpack(out.raw, n)
+
+    def exp_var(self, bases, exps):
+        n = len(bases)
+        e_scalar = not isinstance(exps, list)
+        out = C.create_string_buffer(64 * n)
+        _lib_ec().ref_ec_exp_array(out, self._pack(bases), 0, self._scalars([exps] if e_scalar else exps),
+                                   1 if e_scalar else 0, n, self.curve, self.XW, self.threads)
+        return self._unpack(out.raw, n)
+
+    def expprod(self, bases, exps):
+        out = C.create_string_buffer(64)
+        _lib_ec().ref_ec_expprod(out, self._pack(bases), self._scalars(exps), len(bases), self.curve, self.XW, self.k,
+                                 self.threads)
+        return self._unpack(out.raw, 1)[0]
+
+    def mul(self, a, b):
+        n = len(a)
+        out = C.create_string_buffer(64 * n)
+        _lib_ec().ref_ec_mul_array(out, self._pack(a), self._pack(b), n, self.curve, self.threads)
+        return self._unpack(out.raw, n)
+
+
+def install_ec(G, threads: int | None = None):
+    """Route oracle.arithm's heavy array operations for the curve group G through cpu_ref_ec.c.  Returns an undo()."""
+    from . import arithm as ar
+    acc = AccelEC(G, threads)
+    orig = (ar.g_exp, ar.g_exp_prod, ar.g_mul)
+
+    def g_exp(GG, base, e):
+        if GG is not G:
+            return orig[0](GG, base, e)
+        if isinstance(base, tuple):
+            if isinstance(e, tuple) and ar._same_shape(base, e):
+                return tuple(g_exp(GG, b, x) for b, x in zip(base, e))
+            return tuple(g_exp(GG, b, e) for b in base)
+        if isinstance(base, list):
+            return acc.exp_var(base, e) if base else []
+        if isinstance(e, list):
+            return acc.exp_fixed(base, e) if e else []
+        return acc.exp_var([base], [e])[0]
+
+    def g_exp_prod(GG, arr, e):
+        if GG is not G:
+            return orig[1](GG, arr, e)
+        return ar.gmap(lambda col: acc.expprod(col, e) if col else GG.one, arr)
+
+    def g_mul(GG, a, b):
+        if GG is not G:
+            return orig[2](GG, a, b)
+        return ar.gmap(lambda x, y: acc.mul(x, y) if isinstance(x, list) else GG.op_mul(x, y), a, b)
+
+    ar.g_exp, ar.g_exp_prod, ar.g_mul = g_exp, g_exp_prod, g_mul
+
+    def undo():
+        ar.g_exp, ar.g_exp_prod, ar.g_mul = orig
+    return undo

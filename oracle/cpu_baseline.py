@@ -1,7 +1,8 @@
 """ORACLE (test infrastructure).  The reported CPU baseline: the oracle's restatement of
 re-encryption + PoSBasicTW prove + verify (oracle/protocols.py) with its array operations on
 GMP (oracle/cpu_ref.c: fixed-base tables, mpz_powm, simultaneous exponentiation -- the
-algorithms of the reference's gmpmee/vmgj natives) over all host cores, on a bounded sample of
+algorithms of the reference's gmpmee/vmgj natives; oracle/cpu_ref_ec.c: the same over a prime
+curve, the vec/vecj natives) over all host cores, on a bounded sample of
 the bench workload.  A stand-in for the Java/GMP path (no JVM in the image); kind = "port"."""
 from __future__ import annotations
 
@@ -15,21 +16,33 @@ from . import protocols as pr
 from .crypto import SeededRandomSource
 
 
-def run(bits: int = 3072, n_total: int = 100000, sample: int = 0, steps: int = 1, warmup: int = 0):
-    groups = importlib.import_module("verificatum-vmn_b200.groups")  # constants only
-    p, q, g = groups.rfc3526(bits) if bits != 512 else groups.test512()
-    G = ar.ModPGroup(p, q, g)
+def run(bits: int = 3072, n_total: int = 100000, sample: int = 0, steps: int = 1, warmup: int = 0,
+        group: str = "modp"):
     cores = accel.cores()
-    if sample <= 0:
-        # measured here: ~46 ms per ciphertext and core at 3072 bits; aim at ~15 s per step
-        per_ct = 0.046 * (bits / 3072.0) ** 2
-        sample = max(8 * cores, min(n_total, int(15.0 * cores / per_ct)))
-    undo = accel.install(G, cores)
+    if group != "modp":   # a curve group (BASELINE.json config 5): cpu_ref_ec.c
+        from . import ec
+        G = ec.ECqPGroup(group)
+        if sample <= 0:
+            # measured here: ~13 ms per ciphertext and core on P-256 (a third of it the Python orchestration of
+            # the oracle around the GMP calls); aim at ~15 s per step
+            sample = max(8 * cores, min(n_total, int(15.0 * cores / 0.0125)))
+        undo = accel.install_ec(G, cores)
+        label, lib_note, member_note = "ECqPGroup(%s)" % group, "oracle/cpu_ref_ec.c", "on-curve"
+    else:
+        groups = importlib.import_module("verificatum-vmn_b200.groups")  # constants only
+        p, q, g = groups.rfc3526(bits) if bits != 512 else groups.test512()
+        G = ar.ModPGroup(p, q, g)
+        if sample <= 0:
+            # measured here: ~46 ms per ciphertext and core at 3072 bits; aim at ~15 s per step
+            per_ct = 0.046 * (bits / 3072.0) ** 2
+            sample = max(8 * cores, min(n_total, int(15.0 * cores / per_ct)))
+        undo = accel.install(G, cores)
+        label, lib_note, member_note = "ModPGroup(RFC3526-%d)" % bits, "oracle/cpu_ref.c", "Legendre-symbol"
     try:
-        params = pr.Params(pgroup_string="ModPGroup(RFC3526-%d)" % bits)
+        params = pr.Params(pgroup_string=label)
         rs = SeededRandomSource(hashlib.sha256(b"cpu-baseline/setup").digest())
         x = ar.ring_random_element(G, rs, 100)
-        pk = (g, pow(g, x, p))
+        pk = (G.g, ar.g_exp(G, G.g, x))
         w = pr.demo_ciphertexts(G, pk, sample, rs)
         h = pr.independent_generators(G, "sha256", params.prefix(), "generators", sample, params.rbitlen)
         times = []
@@ -47,5 +60,5 @@ def run(bits: int = 3072, n_total: int = 100000, sample: int = 0, steps: int = 1
     finally:
         undo()
     return {"value": sample / t, "ms_per_step": t * 1e3, "cores": cores,
-            "sample": "%d of %d ciphertexts (re-encrypt + prove + verify incl. Fiat-Shamir hashing and Legendre-symbol "
-                      "membership checks), GMP 6 via oracle/cpu_ref.c, %d threads" % (sample, n_total, cores)}
+            "sample": "%d of %d ciphertexts (re-encrypt + prove + verify incl. Fiat-Shamir hashing and %s "
+                      "membership checks), GMP 6 via %s, %d threads" % (sample, n_total, member_note, lib_note, cores)}

@@ -2,6 +2,8 @@
 laws, encodings round trip.  CPU only."""
 import random
 
+import pytest
+
 from oracle import bytetree as bt
 from oracle.crypto import SeededRandomSource
 from oracle.ec import ECPoint, ECqPGroup, UNIT
@@ -39,3 +41,38 @@ def test_encodings_round_trip():
         assert False
     except ValueError:
         pass
+
+
+@pytest.mark.parametrize("curve", ["P-256", "secp256k1"])
+def test_c_restatement_matches_python_oracle(curve):
+    """oracle/cpu_ref_ec.c (the GMP-backed CPU baseline of the curve workloads) against oracle/ec.py: fixed-base,
+    variable-base (per element and one exponent), simultaneous multiplication and point addition, with the
+    unit element, equal and opposite operands and the exponents 0, 1, q - 1 among the inputs."""
+    import random
+
+    from oracle import accel, arithm as ar, ec as oec
+    G = oec.ECqPGroup(curve)
+    rnd = random.Random(11)
+    n = 23
+    es = [rnd.randrange(G.q) for _ in range(n)]
+    es[0], es[1], es[2] = 0, 1, G.q - 1
+    pts = [G.op_exp(G.g, rnd.randrange(1, G.q)) for _ in range(n)]
+    pts[3] = G.one
+    pts[5] = pts[4]
+    pts[7] = G.op_inv(pts[6])
+    rot = pts[1:] + pts[:1]
+    want = (ar.g_exp(G, G.g, es), ar.g_exp(G, pts, es), ar.g_exp(G, pts, es[5]), ar.g_exp_prod(G, pts, es),
+            ar.g_mul(G, pts, rot), ar.g_mul(G, pts, pts), ar.g_exp_prod(G, (pts, rot), es))
+    undo = accel.install_ec(G, 3)
+    try:
+        got = (ar.g_exp(G, G.g, es), ar.g_exp(G, pts, es), ar.g_exp(G, pts, es[5]), ar.g_exp_prod(G, pts, es),
+               ar.g_mul(G, pts, rot), ar.g_mul(G, pts, pts), ar.g_exp_prod(G, (pts, rot), es))
+    finally:
+        undo()
+    assert got == want
+
+
+def test_cpu_baseline_runs_on_the_curve():
+    from oracle import cpu_baseline
+    r = cpu_baseline.run(n_total=1000, sample=24, group="P-256")
+    assert r["value"] > 0 and "cpu_ref_ec.c" in r["sample"]
