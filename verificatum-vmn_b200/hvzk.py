@@ -426,7 +426,8 @@ class PoSCBasicTW:
                                  self.k_D.toByteTree(), self.k_E.toByteTree())
 
     # -- :646-727
-    def verify(self, btr: ByteTreeReader) -> bool:
+    def parseReply(self, btr: ByteTreeReader) -> bool:
+        self._ind = None
         try:
             self.k_A = self.pRing.toElement(btr.getNextChild())
             self.k_B = self.pRing.toElementArray(self.size, btr.getNextChild())
@@ -435,32 +436,53 @@ class PoSCBasicTW:
             self.k_E = self.pField.toElementArray(self.size, btr.getNextChild())
         except (EIOException, ArithmFormatException):
             return False
-        g, h, u, v = self.g, self.h, self.u, self.v
+        return True
+
+    def verifyIndependent(self) -> None:
+        """What the four checks need from the proof alone (cf. PoSBasicTW.verifyIndependent): queued by
+        PoSCTW.verify while the seed of the batching vector is being hashed."""
+        g, h, u = self.g, self.h, self.u
+        h0 = h.get(0)
+        ind = {}
+        ind["C"] = u.prod().div(h.prod())
+        ind["rightA"] = g.exp(self.k_A).mul(h.expProd(self.k_E))
+        ind["rightB"] = g.exp(self.k_B)
+        B_shift = self.B.shiftPush(h0)
+        ind["B_shift_inv"] = B_shift.inv()
+        _free(B_shift)
+        ind["rightC"] = g.exp(self.k_C)
+        ind["rightD"] = g.exp(self.k_D)
+        self._ind = ind
+
+    def verifyParsed(self) -> bool:
+        if getattr(self, "_ind", None) is None:
+            self.verifyIndependent()
+        ind, self._ind = self._ind, None
+        h, u, v = self.h, self.u, self.v
         h0 = h.get(0)
         A = u.expProd(self.e)
-        C = u.prod().div(h.prod())
         D = self.B.get(self.size - 1).div(h0.exp(self.e.prod()))
-        verdict = True
-        if not A.expMul(v, self.Ap).equals(g.exp(self.k_A).mul(h.expProd(self.k_E))):
-            verdict = False
-        if verdict:
-            # as in PoSBasicTW.verifyParsed: B^v * (B_shift^-1)^k_E * B' == g^k_B, one chain of squarings
-            B_shift = self.B.shiftPush(h0)
-            B_shift_inv = B_shift.inv()
-            both = self.B.expMulExp(v, B_shift_inv, self.k_E)
-            leftSide = both.mul(self.Bp)
-            rightSide = g.exp(self.k_B)
-            B_res = leftSide.equals(rightSide)
-            _free(B_shift, B_shift_inv, both, leftSide, rightSide)
-            if not B_res:
-                verdict = False
-        if verdict and not C.expMul(v, self.Cp).equals(g.exp(self.k_C)):
-            verdict = False
-        if verdict and not D.expMul(v, self.Dp).equals(g.exp(self.k_D)):
-            verdict = False
+        verdict = A.expMul(v, self.Ap).equals(ind["rightA"])
+        # as in PoSBasicTW.verifyParsed: B^v * (B_shift^-1)^k_E * B' == g^k_B, one chain of squarings
+        both = self.B.expMulExp(v, ind["B_shift_inv"], self.k_E)
+        leftSide = both.mul(self.Bp)
+        B_res = leftSide.equals(ind["rightB"])
+        _free(both, leftSide, ind["rightB"], ind["B_shift_inv"])
+        verdict = verdict and B_res
+        verdict = verdict and ind["C"].expMul(v, self.Cp).equals(ind["rightC"])
+        verdict = verdict and D.expMul(v, self.Dp).equals(ind["rightD"])
         return verdict
 
+    def verify(self, btr: ByteTreeReader) -> bool:
+        if not self.parseReply(btr):
+            return False
+        return self.verifyParsed()
+
     def free(self) -> None:
+        ind = getattr(self, "_ind", None)
+        if ind is not None:
+            _free(ind["rightB"], ind["B_shift_inv"])
+            self._ind = None
         _free(self.e, self.b, self.B, self.Bp, self.ipe, self.beta, self.epsilon, self.k_B, self.k_E)
         self.e = self.b = self.B = self.Bp = self.ipe = self.beta = self.epsilon = self.k_B = self.k_E = None
 
@@ -534,12 +556,12 @@ class CCPoSBasicW:
 
     # -- :493-506
     def computeAB(self) -> None:
-        self.A = self.u.expProd(self.e)
-        self.B = self.w.expProd(self.e)
+        self.A, self.B = expProdTogether([self.u, self.w], self.e)
 
     # -- :519-584
-    def verify(self, btr: ByteTreeReader) -> bool:
+    def parseReply(self, btr: ByteTreeReader) -> bool:
         ciphPRing = self.pkey.project(0).getPGroup().getPRing()
+        self._ind = None
         try:
             self.k_A = self.pRing.toElement(btr.getNextChild())
             self.k_B = ciphPRing.toElement(btr.getNextChild())
@@ -549,13 +571,30 @@ class CCPoSBasicW:
             self.k_B = None
             self.k_E = self.pField.toElementArray(self.size, self.pField.getZERO())
             return False
+        return True
+
+    def verifyIndependent(self) -> None:
+        """The right-hand sides g^k_A * prod h^k_E and pk^-k_B * prod w'^k_E (:554-579): functions of the proof
+        alone (the two multi-exponentiations are nearly all of a CCPoS verification), queued by CCPoSW.verify while
+        the seed of the batching vector is being hashed."""
+        h_k_E, wp_k_E = expProdTogether([self.h, self.wp], self.k_E)
+        self._ind = (self.g.exp(self.k_A).mul(h_k_E), self.pkey.exp(self.k_B.neg()).mul(wp_k_E))
+
+    def verifyParsed(self) -> bool:
+        if getattr(self, "_ind", None) is None:
+            self.verifyIndependent()
+        (rightA, rightB), self._ind = self._ind, None
         verdict = True
-        if not self.A.expMul(self.v, self.Ap).equals(self.g.exp(self.k_A).mul(self.h.expProd(self.k_E))):
+        if not self.A.expMul(self.v, self.Ap).equals(rightA):
             verdict = False
-        if verdict and not self.B.expMul(self.v, self.Bp).equals(
-                self.pkey.exp(self.k_B.neg()).mul(self.wp.expProd(self.k_E))):
+        if verdict and not self.B.expMul(self.v, self.Bp).equals(rightB):
             verdict = False
         return verdict
+
+    def verify(self, btr: ByteTreeReader) -> bool:
+        if not self.parseReply(btr):
+            return False
+        return self.verifyParsed()
 
     def free(self) -> None:
         _free(self.e, self.ipe, self.epsilon, self.k_E)
@@ -721,19 +760,26 @@ class PoSCTW:
     def verify(self, g, h, u, commitment: bytes, reply: bytes) -> bool:
         V = PoSCBasicTW(self.vbitlen, self.ebitlen, self.rbitlen, self.prg, self.randomSource)
         V.setInstance(g, h, u)
-        prgSeed = self._seed(g, h, u)
-        V.setBatchVector(prgSeed)
+        # as in PoSTW.verify: the seed RO(g, h, u) is hashed on the worker thread while the device imports the
+        # commitment and the reply and computes what depends on the proof alone
+        d = self.challenger.begin(8 * self.prg.minNoSeedBytes())
+        ByteTreeContainer(g.toByteTree(), h.toByteTree(), u.toByteTree()).update(d)                # :90-92
         try:
             commitmentTree = V.setCommitment(ByteTreeReader(commitment))
         except EIOException:
             commitmentTree = V.setCommitment(ByteTreeReader(ByteTreeContainer().to_bytes()))
+        try:
+            parsed = V.parseReply(ByteTreeReader(reply))
+        except EIOException:
+            parsed = False
+        if parsed:
+            V.verifyIndependent()
+        prgSeed = self.challenger.finish(d)
+        V.setBatchVector(prgSeed)
         challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitmentTree)
         challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
         V.setChallenge(_to_positive(challengeBytes))
-        try:
-            verdict = V.verify(ByteTreeReader(reply))
-        except EIOException:
-            verdict = False
+        verdict = V.verifyParsed() if parsed else False
         V.free()
         return verdict
 
@@ -769,19 +815,28 @@ class CCPoSW:
     def verify(self, g, h, u, pkey, w, wp, commitment: bytes, reply: bytes) -> bool:
         V = CCPoSBasicW(self.vbitlen, self.ebitlen, self.rbitlen, self.prg)
         V.setInstance(g, h, u, pkey, w, wp)
-        prgSeed = self._seed(g, h, u, pkey, w, wp)
-        V.setBatchVector(prgSeed)
-        V.computeAB()
+        # as in PoSTW.verify: the seed RO(g, h, u, pk, w, w') is hashed on the worker thread while the device
+        # computes what depends on the proof alone (the two multi-exponentiations with k_E)
+        d = self.challenger.begin(8 * self.prg.minNoSeedBytes())
+        ByteTreeContainer(g.toByteTree(), h.toByteTree(), u.toByteTree(), pkey.toByteTree(), w.toByteTree(),
+                          wp.toByteTree()).update(d)                                                # :92-98
         try:
             commitmentTree = V.setCommitment(ByteTreeReader(commitment))
         except EIOException:
             commitmentTree = V.setCommitment(ByteTreeReader(ByteTreeContainer().to_bytes()))
-        challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitmentTree)
-        challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
-        V.setChallenge(_to_positive(challengeBytes))
         try:
-            verdict = V.verify(ByteTreeReader(reply))
+            parsed = V.parseReply(ByteTreeReader(reply))
         except EIOException:
-            verdict = False
+            parsed = False
+        if parsed:
+            V.verifyIndependent()
+        prgSeed = self.challenger.finish(d)
+        V.setBatchVector(prgSeed)
+        cd = self.challenger.begin(self.vbitlen)
+        ByteTreeContainer(ByteTreeLeaf(prgSeed), commitmentTree).update(cd)
+        V.computeAB()
+        challengeBytes = self.challenger.finish(cd)
+        V.setChallenge(_to_positive(challengeBytes))
+        verdict = V.verifyParsed() if parsed else False
         V.free()
         return verdict
