@@ -107,13 +107,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_baseline.run(bits=args.bits, n_total=args.n, sample=args.cpu_sample, steps=args.steps,
-                           warmup=min(args.warmup, 1), group=args.group)
-    line = {"metric": metric_name(args), "impl": "reference",
+    if args.workload == "verify-mix":
+        res = cpu_baseline.run_verify_mix(bits=args.bits, n_total=args.n, sample=args.cpu_sample, steps=args.steps,
+                                          warmup=min(args.warmup, 1), group=args.group)
+    else:
+        res = cpu_baseline.run(bits=args.bits, n_total=args.n, sample=args.cpu_sample, steps=args.steps,
+                               warmup=min(args.warmup, 1), group=args.group)
+    mixw = args.workload == "verify-mix"
+    line = {"metric": mix_metric_name(args) if mixw else metric_name(args), "impl": "reference",
             "value": res["value"], "unit": "ciphertexts/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 limbs (exact integer)", "data": "synthetic",
-            "config": config_dict(args),
+            "config": mix_config_dict(args) if mixw else config_dict(args),
             "cpu_baseline": {"value": res["value"], "unit": "ciphertexts/s", "cores": res["cores"], "kind": "port",
                              "sample": res["sample"]},
             "e2e": {"value": res["value"], "unit": "ciphertexts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -131,6 +136,17 @@ def group_label(args) -> str:
 def metric_name(args) -> str:
     return "ciphertexts/s: re-encrypt+PoS prove+verify, " + \
         ("%s ECqPGroup" % args.group if is_curve(args) else "%d-bit ModPGroup" % args.bits)
+
+
+def mix_metric_name(args) -> str:
+    return "ciphertexts/s: vmnv-style verification of a 3-party mix (2 x PoS + decryption proofs), " + \
+        ("%s ECqPGroup" % args.group if is_curve(args) else "%d-bit ModPGroup" % args.bits)
+
+
+def mix_config_dict(args):
+    return dict(config_dict(args), workload="%s, width 1, N=%d ciphertexts per GPU: verification of a 3-party "
+                "mix with threshold 2 from its proof directory in host memory" % (group_label(args), args.n),
+                k=3, threshold=2)
 
 
 def config_dict(args):
@@ -201,14 +217,11 @@ def run_verify_mix(args, G, prg, stream, world, rank, local_rank, torch, dist):
         macs = 136 if is_curve(args) else macs_per_modmul(args.bits)
         nbytes = sum(len(v) for v in nizkp.values())
         modmuls = G.modmul_count() - modmuls0
-        line = {"metric": "ciphertexts/s: vmnv-style verification of a 3-party mix (2 x PoS + decryption proofs), " +
-                          ("%s ECqPGroup" % args.group if is_curve(args) else "%d-bit ModPGroup" % args.bits),
+        line = {"metric": mix_metric_name(args),
                 "value": n / (ms_per_step * 1e-3), "unit": "ciphertexts/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32 limbs (exact integer)", "data": "synthetic",
-                "config": dict(config_dict(args), workload="%s, width 1, N=%d ciphertexts per GPU: verification of a 3-party "
-                               "mix with threshold 2 from its proof directory in host memory" % (group_label(args), args.n),
-                               k=3, threshold=2),
+                "config": mix_config_dict(args),
                 "clocks": sampler.summary(), "gpu_launches": int(G.launch_count() - launches0),
                 "e2e": {"value": n / (wall / args.steps), "unit": "ciphertexts/s", "h2d_bytes_per_step": nbytes,
                         "d2h_bytes_per_step": 0, "ms_per_step": wall / args.steps * 1e3,
@@ -216,6 +229,15 @@ def run_verify_mix(args, G, prg, stream, world, rank, local_rank, torch, dist):
                 "modmul": {"executed_per_ciphertext": modmuls / (args.steps * args.n),
                            "executed_frac_of_imad_peak": modmuls * macs / (ms_per_step * args.steps * 1e-3) / IMAD_PEAK_MAC_PER_S},
                 "prover_s": prove_s, "proof_directory_bytes": nbytes}
+        if world == 1 and not args.no_cpu:
+            try:
+                from oracle import cpu_baseline
+                res = cpu_baseline.run_verify_mix(bits=args.bits, n_total=n, sample=args.cpu_sample, group=args.group)
+                line["cpu_baseline"] = {"value": res["value"], "unit": "ciphertexts/s", "cores": res["cores"],
+                                        "kind": "port", "sample": res["sample"]}
+            except Exception as ex:  # a reported number, never a reason to lose the GPU line
+                line["cpu_baseline"] = {"value": None, "unit": "ciphertexts/s", "cores": 0, "kind": "port",
+                                        "sample": "failed: %s" % ex}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -21,6 +21,8 @@ def lib():
         vp, sz, ci = C.c_char_p, C.c_size_t, C.c_int
         L.ref_powm_array.argtypes = [vp, vp, ci, vp, ci, sz, vp, sz, sz, ci]
         L.ref_mul_array.argtypes = [vp, vp, vp, sz, vp, sz, ci]
+        L.ref_powm_array_neg.argtypes = [vp, vp, vp, sz, vp, sz, sz, ci]
+        L.ref_powm_array_neg.restype = None
         L.ref_fixed_table_create.argtypes = [vp, vp, sz, ci, ci]
         L.ref_fixed_table_create.restype = C.c_void_p
         L.ref_fixed_table_free.argtypes = [C.c_void_p]
@@ -53,8 +55,9 @@ def _unpack(buf, n, w):
 class Accel:
     """GMP-backed versions of oracle.arithm's g_exp / g_exp_prod / g_mul for basic (non-product) operands."""
 
-    def __init__(self, p: int, threads: int | None = None, fixed_window: int = 8, spowm_width: int = 7):
+    def __init__(self, p: int, threads: int | None = None, fixed_window: int = 8, spowm_width: int = 7, q: int = 0):
         self.p = p
+        self.q = q
         self.ew = (p.bit_length() + 7) // 8
         self.mod = p.to_bytes(self.ew, "big")
         self.threads = threads or cores()
@@ -88,6 +91,10 @@ class Accel:
         n = len(bases)
         e_scalar = not isinstance(exps, list)
         out = C.create_string_buffer(n * self.ew)
+        if e_scalar and self.q and 0 < self.q - exps < 1 << 64:   # a small negative integer mod q
+            lib().ref_powm_array_neg(out, _pack(bases, self.ew), (self.q - exps).to_bytes(self.ew, "big"), n, self.mod,
+                                     self.ew, self.ew, self.threads)
+            return _unpack(out.raw, n, self.ew)
         lib().ref_powm_array(out, _pack(bases, self.ew), 0, _pack([exps] if e_scalar else exps, self.ew),
                              1 if e_scalar else 0, n, self.mod, self.ew, self.ew, self.threads)
         return _unpack(out.raw, n, self.ew)
@@ -109,7 +116,7 @@ class Accel:
 def install(G, threads: int | None = None):
     """Route oracle.arithm's heavy array operations for group G through GMP.  Returns an undo()."""
     from . import arithm as ar
-    acc = Accel(G.p, threads)
+    acc = Accel(G.p, threads, q=G.q)
     orig = (ar.g_exp, ar.g_exp_prod, ar.g_mul)
 
     def g_exp(GG, base, e):

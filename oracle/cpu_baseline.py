@@ -62,3 +62,48 @@ def run(bits: int = 3072, n_total: int = 100000, sample: int = 0, steps: int = 1
     return {"value": sample / t, "ms_per_step": t * 1e3, "cores": cores,
             "sample": "%d of %d ciphertexts (re-encrypt + prove + verify incl. Fiat-Shamir hashing and %s "
                       "membership checks), GMP 6 via %s, %d threads" % (sample, n_total, member_note, lib_note, cores)}
+
+
+def run_verify_mix(bits: int = 3072, n_total: int = 100000, sample: int = 0, steps: int = 1, warmup: int = 0,
+                   group: str = "modp", k: int = 3, threshold: int = 2):
+    """The same baseline for `bench.py --workload verify-mix` (BASELINE.json config 3): the oracle's vmnv
+    (protocols.verify_mix: `threshold` verifyPoS + the verification of the decryption, from the bytes of a proof
+    directory) over a k-party mix produced, untimed, by protocols.run_mix."""
+    cores = accel.cores()
+    if group != "modp":
+        from . import ec
+        G = ec.ECqPGroup(group)
+        per_ct, label, lib_note = 0.016, "ECqPGroup(%s)" % group, "oracle/cpu_ref_ec.c"
+        install = accel.install_ec
+    else:
+        groups = importlib.import_module("verificatum-vmn_b200.groups")  # constants only
+        p, q, g = groups.rfc3526(bits) if bits != 512 else groups.test512()
+        G = ar.ModPGroup(p, q, g)
+        per_ct, label, lib_note = 0.055 * (bits / 3072.0) ** 2, "ModPGroup(RFC3526-%d)" % bits, "oracle/cpu_ref.c"
+        install = accel.install
+    if sample <= 0:
+        sample = max(8 * cores, min(n_total, int(15.0 * cores / per_ct)))
+    undo = install(G, cores)
+    try:
+        params = pr.Params(pgroup_string=label)
+        rs = SeededRandomSource(hashlib.sha256(b"cpu-baseline/mix").digest())
+        probe = SeededRandomSource(hashlib.sha256(b"cpu-baseline/mix").digest())
+        pk = (G.g, ar.g_exp(G, G.g, ar.ring_random_element(G, probe, params.rbitlen)))   # the key run_mix will deal
+        w = pr.demo_ciphertexts(G, pk, sample, SeededRandomSource(hashlib.sha256(b"cpu-baseline/mix-input").digest()))
+        d, _plain = pr.run_mix(G, params, k, threshold, w, rs)
+        times = []
+        for i in range(warmup + steps):
+            t0 = time.time()
+            rep = pr.verify_mix(G, params, k, threshold, d)
+            dt = time.time() - t0
+            if not rep["accepted"]:
+                raise RuntimeError("cpu baseline: the verifier rejected an honest mix")
+            if i >= warmup:
+                times.append(dt)
+        t = sum(times) / len(times)
+    finally:
+        undo()
+    return {"value": sample / t, "ms_per_step": t * 1e3, "cores": cores,
+            "sample": "%d of %d ciphertexts (verification of a %d-party mix, threshold %d, from its proof directory "
+                      "incl. Fiat-Shamir hashing and membership checks), GMP 6 via %s, %d threads"
+                      % (sample, n_total, k, threshold, lib_note, cores)}

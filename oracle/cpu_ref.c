@@ -35,6 +35,7 @@ extern void __gmpz_mod(mpz_t, const mpz_t, const mpz_t);
 extern int __gmpz_tstbit(const mpz_t, unsigned long);
 extern size_t __gmpz_sizeinbase(const mpz_t, int);
 extern int __gmpz_jacobi(const mpz_t, const mpz_t);
+extern void __gmpz_neg(mpz_t, const mpz_t);
 #define mpz_init __gmpz_init
 #define mpz_clear __gmpz_clear
 #define mpz_set __gmpz_set
@@ -65,7 +66,7 @@ typedef struct {
   size_t n, ew, xw;
   const uint8_t *a, *b, *e, *mod;
   uint8_t* out;
-  int a_scalar, e_scalar;
+  int a_scalar, e_scalar, e_neg;
   /* fixed base */
   __mpz_struct* table; int w, nwin;
   /* expprod */
@@ -88,6 +89,7 @@ static void* worker(void* arg) {
     for (size_t i = lo; i < hi; i++) {
       get(x, j->a + (j->a_scalar ? 0 : i * j->ew), j->ew);
       get(e, j->e + (j->e_scalar ? 0 : i * j->xw), j->xw);
+      if (j->e_neg) __gmpz_neg(e, e);   /* GMP inverts the base first */
       mpz_powm(y, x, e, m);
       put(j->out + i * j->ew, j->ew, y);
     }
@@ -161,6 +163,16 @@ void ref_powm_array(uint8_t* out, const uint8_t* a, int a_scalar, const uint8_t*
                     const uint8_t* mod, size_t ew, size_t xw, int threads) {
   job_t j; memset(&j, 0, sizeof j);
   j.kind = 0; j.n = n; j.ew = ew; j.xw = xw; j.a = a; j.e = e; j.mod = mod; j.out = out; j.a_scalar = a_scalar; j.e_scalar = e_scalar;
+  run(&j, threads);
+}
+
+/* out[i] = a[i]^{-e} mod m for one small magnitude e: how a negative integer exponent (the modified Lagrange
+ * coefficients of DistrElGamalSessionBasic.java:465-503) is applied -- an inversion and a short power, not a
+ * |q|-bit exponentiation by q - e */
+void ref_powm_array_neg(uint8_t* out, const uint8_t* a, const uint8_t* e_abs, size_t n, const uint8_t* mod, size_t ew,
+                        size_t xw, int threads) {
+  job_t j; memset(&j, 0, sizeof j);
+  j.kind = 0; j.n = n; j.ew = ew; j.xw = xw; j.a = a; j.e = e_abs; j.mod = mod; j.out = out; j.e_scalar = 1; j.e_neg = 1;
   run(&j, threads);
 }
 

@@ -80,3 +80,12 @@ def test_ring_scans():
     assert oar.r_prods(G, e) == [2, 8, 48 % 11, 384 % 11]
     assert oar.permute([10, 11, 12], [2, 0, 1]) == [11, 12, 10]
     assert oar.perm_inv([2, 0, 1]) == [1, 2, 0]
+
+
+def test_cpu_baseline_of_the_mix_verification_runs():
+    """oracle/cpu_baseline.run_verify_mix (the CPU arm of `bench.py --workload verify-mix`): a 3-party mix on the
+    GMP back end is produced and accepted, on the small test group and on the curve."""
+    from oracle import cpu_baseline
+    for kw in (dict(bits=512), dict(group="P-256")):
+        r = cpu_baseline.run_verify_mix(n_total=100, sample=12, **kw)
+        assert r["value"] > 0 and "3-party mix" in r["sample"]
