@@ -572,6 +572,14 @@ def main():
                 "host_wall_ms_per_step": t_host * 1e3 / args.steps}
         if args.phases:
             line["phase_ms_per_step"] = {k: v / args.steps for k, v in phase_ms.items()}
+        try:  # how this line relates to the headline metric of BASELINE.json
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "BASELINE.json")) as f:
+                line["baseline_metric"] = {"metric": json.load(f)["metric"],
+                                           "relation": "same unit and path; one step here also includes the PROVER "
+                                                       "(configs[1]: re-encryption + proof-of-shuffle prove/verify) and "
+                                                       "runs at N = %d per GPU; --n 1000000 gives the metric's N" % args.n}
+        except Exception:
+            pass
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
