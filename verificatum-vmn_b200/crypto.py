@@ -158,6 +158,13 @@ class AsyncDigest:
             raise self._err
         return self.inner.digest()
 
+    def __del__(self):
+        # a digest dropped without digest()/abandon() (an exception on the way) must not leave its worker waiting
+        try:
+            self._q.put(None)
+        except Exception:
+            pass
+
     def abandon(self) -> None:
         """Stop the worker without waiting for it (a speculative hash whose premise failed)."""
         self._err = self._err or RuntimeError("abandoned")
