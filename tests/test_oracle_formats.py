@@ -63,3 +63,28 @@ def test_rfc3526_constants(vmx):
         assert p % 8 == 7 and pow(2, (p - 1) // 2, p) == 1
     p, q, g = groups.test512()
     assert gen_groups.is_probable_prime(p) and gen_groups.is_probable_prime(q) and pow(g, q, p) == 1
+
+
+def test_async_digest_matches_and_releases_its_worker():
+    """crypto.AsyncDigest (Fiat-Shamir hashing beside the GPU): same value as the synchronous oracle, and a digest
+    that is abandoned or simply dropped (an exception on the way) does not leave a thread behind."""
+    import gc
+    import importlib
+    import threading
+    import time
+    cr = importlib.import_module("verificatum-vmn_b200.crypto")
+    ro = cr.RandomOracle(cr.HashfunctionHeuristic("SHA-256"), 256)
+    n0 = threading.active_count()
+    d = cr.AsyncDigest(ro.getDigest())
+    for piece in (b"abc", b"d" * 100000, b"ef"):
+        d.update(piece)
+    assert d.digest() == ro.hash(b"abc" + b"d" * 100000 + b"ef")
+    d = cr.AsyncDigest(ro.getDigest())
+    d.update(b"abc")
+    d.abandon()
+    d = cr.AsyncDigest(ro.getDigest())
+    d.update(b"abc")
+    del d
+    gc.collect()
+    time.sleep(0.3)
+    assert threading.active_count() == n0

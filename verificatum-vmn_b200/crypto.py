@@ -121,6 +121,20 @@ class RandomOracle:
         return d.digest()
 
 
+def _digest_worker(q, inner, state) -> None:
+    """Worker of an AsyncDigest.  It holds the queue and the inner digest, NOT the AsyncDigest itself, so that a
+    digest dropped on an exception path is collected and its __del__ releases the worker."""
+    while True:
+        item = q.get()
+        if item is None:
+            return
+        if state["err"] is None:
+            try:
+                inner.update(item)
+            except BaseException as e:  # surfaced by digest()
+                state["err"] = e
+
+
 class AsyncDigest:
     """A RandomOracleDigest fed by one worker thread.
 
@@ -132,20 +146,9 @@ class AsyncDigest:
     def __init__(self, inner: RandomOracleDigest):
         self.inner = inner
         self._q: "queue.SimpleQueue" = queue.SimpleQueue()
-        self._err = None
-        self._t = threading.Thread(target=self._run, daemon=True)
+        self._state = {"err": None}
+        self._t = threading.Thread(target=_digest_worker, args=(self._q, inner, self._state), daemon=True)
         self._t.start()
-
-    def _run(self) -> None:
-        while True:
-            item = self._q.get()
-            if item is None:
-                return
-            if self._err is None:
-                try:
-                    self.inner.update(item)
-                except BaseException as e:  # surfaced by digest()
-                    self._err = e
 
     def update(self, data) -> None:
         self._q.put(data)
@@ -154,8 +157,8 @@ class AsyncDigest:
         self._q.put(None)
         with _trace.span("digest.wait"):
             self._t.join()
-        if self._err is not None:
-            raise self._err
+        if self._state["err"] is not None:
+            raise self._state["err"]
         return self.inner.digest()
 
     def __del__(self):
@@ -167,7 +170,7 @@ class AsyncDigest:
 
     def abandon(self) -> None:
         """Stop the worker without waiting for it (a speculative hash whose premise failed)."""
-        self._err = self._err or RuntimeError("abandoned")
+        self._state["err"] = self._state["err"] or RuntimeError("abandoned")
         self._q.put(None)
 
     @property
