@@ -32,7 +32,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# measured on B200 by scratch/ubench.cu (profiles/r01_ubench_imad.txt): IMAD.WIDE.U32 issues at
+# measured on B200 by tools/ubench.cu (profiles/r01_ubench_imad.txt): IMAD.WIDE.U32 issues at
 # 0.99 warp-instr/clk/SM -> 32 MAC/clk/SM * 148 SM * 1.965 GHz
 IMAD_PEAK_MAC_PER_S = 9.26e12
 
@@ -108,21 +108,41 @@ def run_reference(args):
     if rank != 0:
         return
     if args.workload == "verify-mix":
-        res = cpu_baseline.run_verify_mix(bits=args.bits, n_total=args.n, sample=args.cpu_sample, steps=args.steps,
+        res = cpu_baseline.run_verify_mix(bits=args.bits, n_total=args.n, sample=cpu_sample_size(args), steps=args.steps,
                                           warmup=min(args.warmup, 1), group=args.group)
     else:
-        res = cpu_baseline.run(bits=args.bits, n_total=args.n, sample=args.cpu_sample, steps=args.steps,
+        res = cpu_baseline.run(bits=args.bits, n_total=args.n, sample=cpu_sample_size(args), steps=args.steps,
                                warmup=min(args.warmup, 1), group=args.group)
     mixw = args.workload == "verify-mix"
+    cfg = mix_config_dict(args, args.gpus) if mixw else config_dict(args, args.gpus)
+    assert cfg["cpu_sample"] == res["sample_n"]
     line = {"metric": mix_metric_name(args) if mixw else metric_name(args), "impl": "reference",
             "value": res["value"], "unit": "ciphertexts/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32 limbs (exact integer)", "data": "synthetic",
-            "config": mix_config_dict(args) if mixw else config_dict(args),
+            "config": cfg,
             "cpu_baseline": {"value": res["value"], "unit": "ciphertexts/s", "cores": res["cores"], "kind": "port",
                              "sample": res["sample"]},
             "e2e": {"value": res["value"], "unit": "ciphertexts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def cpu_sample_size(args) -> int:
+    """Ciphertexts one step of the CPU arm runs: a bounded sample of the workload, about 15 s of work on this
+    host's cores (measured per ciphertext and core: ~46 ms at 3072 bits, 55 ms for the verification of a mix;
+    ~13 / 16 ms on P-256).  Both arms name it in `config`."""
+    if args.cpu_sample:
+        return args.cpu_sample
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    mix = args.workload == "verify-mix"
+    if is_curve(args):
+        per_ct = 0.016 if mix else 0.0125
+    else:
+        per_ct = (0.055 if mix else 0.046) * (args.bits / 3072.0) ** 2
+    return max(8 * cores, min(args.n, int(15.0 * cores / per_ct)))
 
 
 def is_curve(args) -> bool:
@@ -143,33 +163,84 @@ def mix_metric_name(args) -> str:
         ("%s ECqPGroup" % args.group if is_curve(args) else "%d-bit ModPGroup" % args.bits)
 
 
-def mix_config_dict(args):
-    return dict(config_dict(args), workload="%s, width 1, N=%d ciphertexts per GPU: verification of a 3-party "
-                "mix with threshold 2 from its proof directory in host memory" % (group_label(args), args.n),
-                k=3, threshold=2)
+def mix_config_dict(args, world=1):
+    return dict(config_dict(args, world), workload="%s, width 1, N=%d ciphertexts in total (one list, sharded over "
+                "%d GPU%s): verification of a 3-party mix with threshold 2 from its proof directory in host memory"
+                % (group_label(args), args.n, world, "" if world == 1 else "s"), k=3, threshold=2)
 
 
-def config_dict(args):
+def config_dict(args, world=1):
     elem = 64 if is_curve(args) else args.bits // 8
-    return {"workload": "%s, width %d, N=%d ciphertexts per GPU: re-encrypt + PoSBasicTW prove + verify"
-                        % (group_label(args), args.width, args.n),
-            "group": args.group, "bits": 256 if is_curve(args) else args.bits, "width": args.width, "n_per_gpu": args.n,
+    return {"workload": "%s, width %d, N=%d ciphertexts in total (one list, sharded over %d GPU%s): re-encrypt + "
+                        "PoSBasicTW prove + verify" % (group_label(args), args.width, args.n, world,
+                                                       "" if world == 1 else "s"),
+            "group": args.group, "bits": 256 if is_curve(args) else args.bits, "width": args.width,
+            "n_total": args.n, "n_per_gpu": -(-args.n // world),
             "ebitlen": 256, "vbitlen": 256, "rbitlen": 100,
+            # the CPU arm (cpu_baseline, --impl reference) runs a bounded SAMPLE of the N ciphertexts per step and
+            # reports sample / time: this many, on all host cores
+            "cpu_sample": cpu_sample_size(args),
             "l2": "working set (N x %d B per array, >10 arrays) exceeds the 126 MB L2" % elem}
 
 
-def run_verify_mix(args, G, prg, stream, world, rank, local_rank, torch, dist):
+class Env:
+    """What every measurement of this process shares: torch, the process group, this rank."""
+
+    def __init__(self, torch, dist, world, rank, local_rank):
+        self.torch, self.dist, self.world, self.rank, self.local_rank = torch, dist, world, rank, local_rank
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v: float) -> float:
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def make_group(args, env):
+    vmx = importlib.import_module("verificatum-vmn_b200")
+    groups = importlib.import_module("verificatum-vmn_b200.groups")
+    A = vmx.arithm
+    if env.world > 1:
+        # ONE list of n ciphertexts, sharded in contiguous index ranges over the GPUs: one shuffle, one proof;
+        # expProd partial products and permuted rows travel over NCCL
+        par = importlib.import_module("verificatum-vmn_b200.parallel")
+        if is_curve(args):
+            return par.make_curve_group(args.group, env.local_rank)
+        return par.make_group(*groups.rfc3526(args.bits), env.local_rank)
+    if is_curve(args):
+        return A.ECqPGroup(args.group, device=env.local_rank)
+    return A.ModPGroup(*groups.rfc3526(args.bits), device=env.local_rank)
+
+
+def make_prg(label: str):
+    # the same stream on every rank: each rank expands its own slice of it on the device
+    crypto = importlib.import_module("verificatum-vmn_b200.crypto")
+    r = crypto.PRGHeuristic()
+    r.setSeed(crypto.HashfunctionHeuristic("SHA-256").hash(("vmx-bench/%s" % label).encode()))
+    return r
+
+
+def run_verify_mix(args, env):
     """BASELINE.json config 3: what `vmnv` does with the proof directory of a 3-party mix (threshold 2): two
     verifyPoS and the verification of the decryption (3 arrays of decryption factors, batched proof, plaintexts)
     -- mixnet/MixNetElGamalVerifyFiatShamirSession.java:1318-1668.  The proof directory is produced by the engine's
     own mix (untimed) and held in HOST memory; one step = one full verification from those bytes (import with
     membership checks, Fiat-Shamir hashing, all array work), so `value` and `e2e` are the same measurement here."""
+    torch, world, rank = env.torch, env.world, env.rank
     vm = importlib.import_module("verificatum-vmn_b200.vmnv")
     mixnet = importlib.import_module("verificatum-vmn_b200.mixnet")
-    n = args.n * world
+    G = make_group(args, env)
+    stream = torch.cuda.ExternalStream(G._lib.vmx_ctx_stream(G.ctx), device=torch.device("cuda", env.local_rank))
+    n = args.n
+    n_local = n * (rank + 1) // world - n * rank // world
     params = mixnet.SessionParams(pGroupString="%s" % group_label(args))
-    M = vm.MixNetElGamal(G, params, 3, 2, prg("mix/dealer"))
-    w = mixnet.demoCiphertexts(M.fullPublicKey, n, prg("mix/input"))
+    M = vm.MixNetElGamal(G, params, 3, 2, make_prg("mix/dealer"))
+    w = mixnet.demoCiphertexts(M.fullPublicKey, n, make_prg("mix/input"))
     t0 = time.time()
     M.run(w).free()
     G.sync()
@@ -177,11 +248,6 @@ def run_verify_mix(args, G, prg, stream, world, rank, local_rank, torch, dist):
     nizkp = M.nizkp
     V = vm.MixNetElGamalVerifyFiatShamirSession(G, params, 3, 2)
     G.membership_check = True
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     for _ in range(max(1, min(args.warmup, 2))):
         if not V.verify(nizkp)["accepted"]:
@@ -193,9 +259,9 @@ def run_verify_mix(args, G, prg, stream, world, rank, local_rank, torch, dist):
             V.verify(nizkp)
         with open(args.trace, "w") as f:
             json.dump(tr.stop(), f)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(env.local_rank)
     sampler.start()
-    barrier()
+    env.barrier()
     launches0, modmuls0 = G.launch_count(), G.modmul_count()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -205,116 +271,65 @@ def run_verify_mix(args, G, prg, stream, world, rank, local_rank, torch, dist):
         V.verify(nizkp)
     e1.record(stream)
     e1.synchronize()
-    barrier()
-    wall = time.time() - t0
+    env.barrier()
+    wall = env.max_over_ranks(time.time() - t0)
     sampler.stop_flag.set()
     sampler.join()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
+    ms_per_step = env.max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    line = None
     if rank == 0:
         macs = 136 if is_curve(args) else macs_per_modmul(args.bits)
         nbytes = sum(len(v) for v in nizkp.values())
         modmuls = G.modmul_count() - modmuls0
         line = {"metric": mix_metric_name(args),
                 "value": n / (ms_per_step * 1e-3), "unit": "ciphertexts/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u32 limbs (exact integer)", "data": "synthetic",
-                "config": mix_config_dict(args),
+                "config": mix_config_dict(args, world),
                 "clocks": sampler.summary(), "gpu_launches": int(G.launch_count() - launches0),
                 "e2e": {"value": n / (wall / args.steps), "unit": "ciphertexts/s", "h2d_bytes_per_step": nbytes,
                         "d2h_bytes_per_step": 0, "ms_per_step": wall / args.steps * 1e3,
                         "includes": "byte-tree decode, H2D, membership checks, Fiat-Shamir SHA-256 on the host"},
-                "modmul": {"executed_per_ciphertext": modmuls / (args.steps * args.n),
+                "modmul": {"executed_per_ciphertext": modmuls / (args.steps * max(1, n_local)),
                            "executed_frac_of_imad_peak": modmuls * macs / (ms_per_step * args.steps * 1e-3) / IMAD_PEAK_MAC_PER_S},
                 "prover_s": prove_s, "proof_directory_bytes": nbytes}
         if world == 1 and not args.no_cpu:
             try:
                 from oracle import cpu_baseline
-                res = cpu_baseline.run_verify_mix(bits=args.bits, n_total=n, sample=args.cpu_sample, group=args.group)
+                res = cpu_baseline.run_verify_mix(bits=args.bits, n_total=n, sample=cpu_sample_size(args), group=args.group)
                 line["cpu_baseline"] = {"value": res["value"], "unit": "ciphertexts/s", "cores": res["cores"],
                                         "kind": "port", "sample": res["sample"]}
             except Exception as ex:  # a reported number, never a reason to lose the GPU line
                 line["cpu_baseline"] = {"value": None, "unit": "ciphertexts/s", "cores": 0, "kind": "port",
                                         "sample": "failed: %s" % ex}
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    del V, M, w
+    return line
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="vmx", choices=["vmx", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("VMX_BENCH_N", "100000")))
-    ap.add_argument("--bits", type=int, default=3072)
-    ap.add_argument("--width", type=int, default=1, help="blocks per ciphertext (BASELINE.json config 4 uses 3)")
-    ap.add_argument("--group", default="modp", help="modp (RFC 3526 safe prime of --bits) or a curve name (P-256)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="ciphertexts in the CPU baseline sample (0 = auto)")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--phases", action="store_true", help="print per-phase device times to stderr")
-    ap.add_argument("--trace", default="", help="write the host timeline (ABI calls, hashing) of one extra untimed "
-                                                "end-to-end step to this JSON file")
-    ap.add_argument("--workload", default="shuffle", choices=["shuffle", "verify-mix"],
-                    help="shuffle: re-encrypt + PoS prove + verify (BASELINE.json config 2, the default); "
-                         "verify-mix: vmnv-style verification of a 3-party mix, threshold 2 (config 3)")
-    args = ap.parse_args()
+class _Null:
+    def __enter__(self):
+        return self
 
-    if args.impl == "reference":
-        return run_reference(args)
-    if args.trace:
-        os.environ["VMX_TRACE"] = "1"
+    def __exit__(self, *a):
+        return False
 
+
+def run_shuffle(args, env):
+    """One list of N ciphertexts: re-encrypt + permute, PoSBasicTW prove, PoSBasicTW verify (BASELINE.json's metric;
+    `configs[1]` at --n 100000).  Returns the JSON line as a dict on rank 0, None elsewhere."""
     import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
+    torch, world, rank, local_rank = env.torch, env.world, env.rank, env.local_rank
     vmx = importlib.import_module("verificatum-vmn_b200")
     A = vmx.arithm
     hvzk = importlib.import_module("verificatum-vmn_b200.hvzk")
     mixnet = importlib.import_module("verificatum-vmn_b200.mixnet")
-    groups = importlib.import_module("verificatum-vmn_b200.groups")
     crypto = vmx.crypto
+    prg = make_prg
 
-    p, q, g = groups.rfc3526(args.bits)
-    if is_curve(args):
-        if world > 1:
-            par = importlib.import_module("verificatum-vmn_b200.parallel")
-            G = par.make_curve_group(args.group, local_rank)
-        else:
-            G = A.ECqPGroup(args.group, device=local_rank)
-    elif world > 1:
-        # ONE list of world * n ciphertexts, sharded in contiguous index ranges over the GPUs: one
-        # shuffle, one proof; expProd partial products and permuted rows travel over NCCL
-        par = importlib.import_module("verificatum-vmn_b200.parallel")
-        G = par.make_group(p, q, g, local_rank)
-    else:
-        G = A.ModPGroup(p, q, g, device=local_rank)
+    G = make_group(args, env)
     stream = torch.cuda.ExternalStream(G._lib.vmx_ctx_stream(G.ctx), device=torch.device("cuda", local_rank))
-    n_local = args.n
-    n = args.n * world          # global list size (every rank holds n_local of every array)
-
-    def prg(label: str):
-        # the same stream on every rank: each rank expands its own slice of it on the device
-        r = crypto.PRGHeuristic()
-        r.setSeed(crypto.HashfunctionHeuristic("SHA-256").hash(("vmx-bench/%s" % label).encode()))
-        return r
-
-    if args.workload == "verify-mix":
-        return run_verify_mix(args, G, prg, stream, world, rank, local_rank, torch, dist)
+    n = args.n                                              # global list size
+    n_local = n * (rank + 1) // world - n * rank // world   # this rank's contiguous index range
 
     # ---- synthetic inputs, resident in HBM
     setup_rs = prg("setup")
@@ -395,24 +410,24 @@ def main():
         s.free()
         out.free()
 
-    class _Null:
-        def __enter__(self):
-            return self
-
-        def __exit__(self, *a):
-            return False
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # ---- the first step of a session builds the fixed-base tables of g, the public key and h0: timed on its own
+    env.barrier()
+    c0 = torch.cuda.Event(enable_timing=True)
+    c1 = torch.cuda.Event(enable_timing=True)
+    mm_cold0 = G.modmul_count()
+    c0.record(stream)
+    step_device(0, False)
+    c1.record(stream)
+    c1.synchronize()
+    cold_ms = env.max_over_ranks(c0.elapsed_time(c1))
+    cold_modmuls = G.modmul_count() - mm_cold0
 
     # ---- device-resident timing
-    for i in range(args.warmup):
+    for i in range(1, args.warmup):
         step_device(i, False)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
+    env.barrier()
     launches0, modmuls0 = G.launch_count(), G.modmul_count()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -422,61 +437,64 @@ def main():
         step_device(args.warmup + i, True)
     e1.record(stream)
     e1.synchronize()
-    barrier()
+    env.barrier()
     t_host = time.time() - t_host0
-    dev_ms = e0.elapsed_time(e1)
     launches = G.launch_count() - launches0
     modmuls = G.modmul_count() - modmuls0
     sampler.stop_flag.set()
     sampler.join()
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
+    dev_ms = env.max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = dev_ms / args.steps
     value = n / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel (fixed-base exponentiation), timed live
-    roof = None
-    if True:  # every rank runs it on its shard (no collective inside); rank 0 reports its own
-        rs = prg("roofline")
-        e = G.getPRing().randomElementArray(n, rs, params.rbitlen)
+    # every rank runs it on its shard (no collective inside); rank 0 reports its own
+    rs = prg("roofline")
+    e = G.getPRing().randomElementArray(n, rs, params.rbitlen)
+    tmp = G.getg().exp(e)
+    tmp.free()
+    mm0 = G.modmul_count()
+    r0 = torch.cuda.Event(enable_timing=True)
+    r1 = torch.cuda.Event(enable_timing=True)
+    reps = 3
+    r0.record(stream)
+    for _ in range(reps):
         tmp = G.getg().exp(e)
         tmp.free()
-        mm0 = G.modmul_count()
-        r0 = torch.cuda.Event(enable_timing=True)
-        r1 = torch.cuda.Event(enable_timing=True)
-        reps = 3
-        r0.record(stream)
-        for _ in range(reps):
-            tmp = G.getg().exp(e)
-            tmp.free()
-        r1.record(stream)
-        r1.synchronize()
-        k_ms = r0.elapsed_time(r1) / reps
-        k_modmuls = (G.modmul_count() - mm0) / reps
-        e.free()
-        macs = 136 if is_curve(args) else macs_per_modmul(args.bits)
-        elem_bytes = 64 if is_curve(args) else args.bits // 8
-        achieved = k_modmuls * macs / (k_ms * 1e-3)
-        traffic = pipe_busy = None
-        try:  # one `ncu --set full` capture of this kernel at the same shape (profiles/, per launch)
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_exp_fixed.json")))
-            if cap["n"] == n_local and args.bits == 3072 and not is_curve(args):
-                traffic, pipe_busy = cap["traffic_bytes"], cap["fmaheavy_pipe_busy_pct"]
-        except Exception:
-            pass
-        roof = {"bound": "imad", "kernel": "k_ec_exp_fixed" if is_curve(args) else "k_exp_fixed<%d>" % (args.bits // 32),
-                "achieved": achieved / 1e12,
-                "peak": IMAD_PEAK_MAC_PER_S / 1e12, "unit": "TMAC/s (32x32+64 IMAD.WIDE)", "frac": achieved / IMAD_PEAK_MAC_PER_S,
-                "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu, profiles/r02_ncu_exp_fixed.json; 16-byte gathers use half of each 32-byte sector, hence ~2x the algorithmic bytes; 0.34 TB/s, not the limiter)",
-                "algorithmic_bytes": (k_modmuls / 11 * elem_bytes + 32 * n_local + 96 * n_local) if is_curve(args)
-                else k_modmuls * elem_bytes + 2 * n_local * elem_bytes,
-                "unit_of_work": "field multiplication = 136 word MACs nominal (the P-256 reduction executes 64 + adds)"
-                if is_curve(args) else "modmul = 2N^2+N word MACs",
-                "imad_pipe_busy_pct_ncu": pipe_busy, "modmuls_per_launch": k_modmuls, "ms_per_launch": k_ms,
-                "peak_source": "measured on B200 (profiles/r01_ubench_imad.txt); MEASURED_PEAKS.json has no integer peak",
-                "hbm_note": "integer-pipe bound: arithmetic intensity ~1e4 MAC/B, HBM is not the limiter"}
+    r1.record(stream)
+    r1.synchronize()
+    k_ms = r0.elapsed_time(r1) / reps
+    k_modmuls = (G.modmul_count() - mm0) / reps
+    e.free()
+    macs = 136 if is_curve(args) else macs_per_modmul(args.bits)
+    elem_bytes = 64 if is_curve(args) else args.bits // 8
+    achieved = k_modmuls * macs / (k_ms * 1e-3)
+    traffic = pipe_busy = traffic_src = None
+    per_exp = k_modmuls / max(1, n_local)
+    try:  # an `ncu --set full` capture of this kernel counts only if it ran the SAME launch (size and window)
+        for name in sorted(os.listdir(os.path.join(ROOT, "profiles"))):
+            if not name.endswith(".json") or "ncu_exp_fixed" not in name:
+                continue
+            cap = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if cap.get("n") == n_local and cap.get("bits", 3072) == args.bits and not is_curve(args) and \
+                    abs(cap.get("modmuls_per_exponent", -1) - per_exp) < 0.5:
+                traffic, pipe_busy, traffic_src = cap["traffic_bytes"], cap["fmaheavy_pipe_busy_pct"], "profiles/" + name
+    except Exception:
+        pass
+    roof = {"bound": "imad", "kernel": "k_ec_exp_fixed" if is_curve(args) else "k_exp_fixed<%d>" % (args.bits // 32),
+            "achieved": achieved / 1e12,
+            "peak": IMAD_PEAK_MAC_PER_S / 1e12, "unit": "TMAC/s (32x32+64 IMAD.WIDE)", "frac": achieved / IMAD_PEAK_MAC_PER_S,
+            "traffic": traffic,
+            "traffic_unit": ("bytes of DRAM read+write per launch, ncu --set full of the same launch (%s)" % traffic_src)
+            if traffic_src else "no ncu capture of this exact launch (size, window) is committed: null",
+            "algorithmic_bytes": (k_modmuls / 11 * elem_bytes + 32 * n_local + 96 * n_local) if is_curve(args)
+            else k_modmuls * elem_bytes + 2 * n_local * elem_bytes,
+            "unit_of_work": "field multiplication = 136 word MACs nominal (the P-256 reduction executes 64 + adds)"
+            if is_curve(args) else "modmul = 2N^2+N word MACs",
+            "imad_pipe_busy_pct_ncu": pipe_busy, "modmuls_per_launch": k_modmuls, "modmuls_per_exponent": per_exp,
+            "ms_per_launch": k_ms,
+            "peak_source": "measured on B200 (profiles/r01_ubench_imad.txt); MEASURED_PEAKS.json has no integer peak",
+            "hbm_note": "integer-pipe bound: arithmetic intensity ~1e4 MAC/B, HBM is not the limiter"}
 
     # ---- end to end through the public API with host buffers
     e2e = None
@@ -485,9 +503,11 @@ def main():
         ciph_bytes = ciphertexts.toByteTree().to_bytes()
         pinned = torch.empty(len(ciph_bytes), dtype=torch.uint8).pin_memory()
         pinned.numpy()[:] = np.frombuffer(ciph_bytes, dtype=np.uint8)
-        h2d = d2h = 0
+        del ciph_bytes
+        h2d = d2h = hashed = 0
 
-        _span = importlib.import_module("verificatum-vmn_b200._trace").span
+        tracemod = importlib.import_module("verificatum-vmn_b200._trace")
+        _span = tracemod.span
 
         def step_e2e(i: int):
             nonlocal h2d, d2h
@@ -503,7 +523,7 @@ def main():
                 raise SystemExit("bench e2e: verifier rejected an honest proof")
             out.free()
             w.free()
-            h2d = len(ciph_bytes) + len(proof.output) + len(proof.permutationCommitment) + len(proof.commitment) + \
+            h2d = pinned.numel() + len(proof.output) + len(proof.permutationCommitment) + len(proof.commitment) + \
                 len(proof.reply)
             d2h = len(proof.output) + len(proof.permutationCommitment) + len(proof.commitment) + len(proof.reply)
 
@@ -520,66 +540,173 @@ def main():
             pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(18)
             sys.stderr.write(buf.getvalue())
         if args.trace and rank == 0:
-            tr = importlib.import_module("verificatum-vmn_b200._trace")
-            tr.start()
-            with tr.span("e2e.step"):
+            tracemod.start()
+            with tracemod.span("e2e.step"):
                 step_e2e(98)
             with open(args.trace, "w") as f:
-                json.dump(tr.stop(), f)
-        barrier()
+                json.dump(tracemod.stop(), f)
+        hash0 = crypto.hashed_bytes() if hasattr(crypto, "hashed_bytes") else None
+        hsec0 = crypto.hashed_seconds() if hasattr(crypto, "hashed_seconds") else None
+        env.barrier()
         t0 = time.time()
-        k = max(1, min(args.steps, 2))
+        k = args.e2e_steps
         for i in range(k):
             step_e2e(1 + i)
-        barrier()
-        dt = (time.time() - t0) / k
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n / float(tt.item()), "unit": "ciphertexts/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": float(tt.item()) * 1e3,
+        env.barrier()
+        dt = env.max_over_ranks((time.time() - t0) / k)
+        e2e = {"value": n / dt, "unit": "ciphertexts/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": k,
                "includes": "byte-tree decode/encode, H2D/D2H, Fiat-Shamir SHA-256 on the host",
                "membership_check_on_import": bool(G.membership_check)}
+        if hash0 is not None:
+            hb = (crypto.hashed_bytes() - hash0) / k
+            hs = (crypto.hashed_seconds() - hsec0) / k
+            e2e["hash_bytes_per_step"] = hb
+            e2e["sha256_gbs"] = hb / hs / 1e9 if hs > 0 else None
+            e2e["sha256_bound_ciphertexts_per_s"] = n / hs if hs > 0 else None
+            e2e["hash_note"] = ("Fiat-Shamir is ONE SHA-256 stream per challenge (hvzk/ChallengerRO.java:96-116): "
+                                "hash_bytes_per_step at sha256_gbs is the Amdahl bound of the end-to-end figure at any "
+                                "number of GPUs (rank 0's hashing)")
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and args.width == 1:
         try:
             from oracle import cpu_baseline
-            res = cpu_baseline.run(bits=args.bits, n_total=n, sample=args.cpu_sample, steps=1, warmup=0,
+            res = cpu_baseline.run(bits=args.bits, n_total=n, sample=cpu_sample_size(args), steps=1, warmup=0,
                                    group=args.group)
             cpu = {"value": res["value"], "unit": "ciphertexts/s", "cores": res["cores"], "kind": "port",
                    "sample": res["sample"]}
         except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
             cpu = {"value": None, "unit": "ciphertexts/s", "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
 
+    line = None
     if rank == 0:
         nominal = nominal_fieldmuls_per_ciphertext_ec(n, width=args.width) if is_curve(args) else \
             nominal_modmuls_per_ciphertext(args.bits, n, width=args.width)
-        macs = 136 if is_curve(args) else macs_per_modmul(args.bits)
         line = {"metric": metric_name(args),
                 "value": value, "unit": "ciphertexts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u32 limbs (exact integer)", "data": "synthetic", "config": config_dict(args),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u32 limbs (exact integer)", "data": "synthetic", "config": config_dict(args, world),
                 "clocks": sampler.summary(), "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
                 "cpu_baseline": cpu,
+                "cold_first_step_ms": cold_ms,
+                "cold_first_step_note": "the first step of a session, fixed-base tables of g, pk and h0 built inside "
+                                        "(%d modmuls against %d of a warm step); a mix-server builds them once per "
+                                        "session" % (cold_modmuls, modmuls // max(1, args.steps)),
                 "modmul": {"nominal_per_ciphertext": nominal["total"],
-                           "executed_per_ciphertext": modmuls / (args.steps * n_local),
+                           "executed_per_ciphertext": modmuls / (args.steps * max(1, n_local)),
                            "nominal_modmul_per_s": value * nominal["total"],
                            "nominal_frac_of_imad_peak": value / world * nominal["total"] * macs / IMAD_PEAK_MAC_PER_S,
                            "executed_frac_of_imad_peak": modmuls * macs / (dev_ms * 1e-3) / IMAD_PEAK_MAC_PER_S,
-                           "note": "fractions are per GPU (rank 0's kernels against one GPU's peak)"},
+                           "note": "fractions are per GPU (rank 0's kernels against one GPU's peak); a squaring "
+                                   "counts as one modmul although it executes ~0.79 of a multiplication's MACs"},
                 "host_wall_ms_per_step": t_host * 1e3 / args.steps}
         if args.phases:
             line["phase_ms_per_step"] = {k: v / args.steps for k, v in phase_ms.items()}
         try:  # how this line relates to the headline metric of BASELINE.json
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "BASELINE.json")) as f:
+            with open(os.path.join(ROOT, "BASELINE.json")) as f:
                 line["baseline_metric"] = {"metric": json.load(f)["metric"],
-                                           "relation": "same unit and path; one step here also includes the PROVER "
-                                                       "(configs[1]: re-encryption + proof-of-shuffle prove/verify) and "
-                                                       "runs at N = %d per GPU; --n 1000000 gives the metric's N" % args.n}
+                                           "relation": "same unit, path and list size when --n is 1000000 (the default); "
+                                                       "one step here also includes the PROVER (re-encryption + "
+                                                       "proof-of-shuffle prove AND verify)"}
         except Exception:
             pass
+    ciphertexts.free()
+    generators.free()
+    del G
+    return line
+
+
+# BASELINE.json configs 3, 4, 5 at sizes whose set-up fits a side run (the mix of config 3 at N = 10^6 takes the
+# three decryption servers ~30 s each to produce): short runs in the same process, after the headline measurement
+OTHER_CONFIGS = [
+    ("config3_verify_mix_3072", dict(workload="verify-mix", bits=3072, group="modp", width=1, n=100000)),
+    ("config4_width3_2048", dict(workload="shuffle", bits=2048, group="modp", width=3, n=100000)),
+    ("config5_p256", dict(workload="shuffle", bits=3072, group="P-256", width=1, n=1000000)),
+]
+
+
+def run_other_configs(args, env):
+    import copy
+    import gc
+    out = {}
+    for name, over in OTHER_CONFIGS:
+        a = copy.copy(args)
+        for k, v in over.items():
+            setattr(a, k, v)
+        a.steps, a.warmup, a.e2e_steps = 2, 2, 2
+        a.no_cpu, a.phases, a.trace, a.cpu_sample = True, False, "", 0
+        gc.collect()
+        t0 = time.time()
+        try:
+            line = run_verify_mix(a, env) if a.workload == "verify-mix" else run_shuffle(a, env)
+        except SystemExit as ex:
+            line = {"error": str(ex)}
+        except Exception as ex:  # a side measurement never costs the headline line
+            line = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        if env.rank == 0 and line is not None:
+            keep = ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "n_gpus", "scaling", "gpu_launches",
+                    "e2e", "modmul", "cold_first_step_ms", "error")
+            sub = {k: line[k] for k in keep if k in line}
+            if "config" in line:
+                sub["workload"] = line["config"]["workload"]
+            if "roofline" in line and line["roofline"]:
+                sub["roofline"] = {k: line["roofline"][k] for k in ("kernel", "achieved", "peak", "unit", "frac")}
+            sub["wall_s"] = time.time() - t0
+            out[name] = sub
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="vmx", choices=["vmx", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("VMX_BENCH_N", "1000000")),
+                    help="ciphertexts in the list, in TOTAL (sharded over the GPUs): BASELINE.json's metric is N = 10^6")
+    ap.add_argument("--bits", type=int, default=3072)
+    ap.add_argument("--width", type=int, default=1, help="blocks per ciphertext (BASELINE.json config 4 uses 3)")
+    ap.add_argument("--group", default="modp", help="modp (RFC 3526 safe prime of --bits) or a curve name (P-256)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="ciphertexts in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="end-to-end steps averaged (after one untimed)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the short side runs of BASELINE.json configs 3, 4, 5")
+    ap.add_argument("--phases", action="store_true", help="print per-phase device times to stderr")
+    ap.add_argument("--trace", default="", help="write the host timeline (ABI calls, hashing) of one extra untimed "
+                                                "end-to-end step to this JSON file")
+    ap.add_argument("--workload", default="shuffle", choices=["shuffle", "verify-mix"],
+                    help="shuffle: re-encrypt + PoS prove + verify (BASELINE.json's metric, the default); "
+                         "verify-mix: vmnv-style verification of a 3-party mix, threshold 2 (config 3)")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.trace:
+        os.environ["VMX_TRACE"] = "1"
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    env = Env(torch, dist, world, rank, local_rank)
+
+    headline = (args.workload == "shuffle" and args.group == "modp" and args.bits == 3072 and args.width == 1)
+    line = run_verify_mix(args, env) if args.workload == "verify-mix" else run_shuffle(args, env)
+    if headline and not args.no_other:
+        other = run_other_configs(args, env)
+        if rank == 0:
+            line["other_configs"] = other
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -86,7 +86,12 @@ class EIOError(ValueError):
     """Malformed byte tree (EIOException in the reference)."""
 
 
-def parse(data: bytes, offset: int = 0) -> Tuple[ByteTree, int]:
+MAX_DEPTH = 64   # the trees of a proof directory are at most ~6 deep; deeper input is malformed
+
+
+def parse(data: bytes, offset: int = 0, depth: int = 0) -> Tuple[ByteTree, int]:
+    if depth > MAX_DEPTH:
+        raise EIOError("byte tree nested too deep")
     if offset + 5 > len(data):
         raise EIOError("truncated header")
     kind, n = struct.unpack_from(">BI", data, offset)
@@ -98,7 +103,7 @@ def parse(data: bytes, offset: int = 0) -> Tuple[ByteTree, int]:
     if kind == NODE:
         kids = []
         for _ in range(n):
-            c, offset = parse(data, offset)
+            c, offset = parse(data, offset, depth + 1)
             kids.append(c)
         return ByteTree(kids), offset
     raise EIOError("bad tag %d" % kind)

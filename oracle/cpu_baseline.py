@@ -16,6 +16,19 @@ from . import protocols as pr
 from .crypto import SeededRandomSource
 
 
+def default_sample(bits: int, n_total: int, group: str = "modp", mix: bool = False) -> int:
+    """Ciphertexts in the bounded sample one CPU step runs (about 15 s of work on this host's cores)."""
+    cores = accel.cores()
+    if group != "modp":
+        # measured: ~13 ms per ciphertext and core on P-256 (a third of it the Python orchestration of the oracle
+        # around the GMP calls), 16 ms for the verification of a mix
+        per_ct = 0.016 if mix else 0.0125
+    else:
+        # measured: ~46 ms per ciphertext and core at 3072 bits (55 ms for the verification of a mix)
+        per_ct = (0.055 if mix else 0.046) * (bits / 3072.0) ** 2
+    return max(8 * cores, min(n_total, int(15.0 * cores / per_ct)))
+
+
 def run(bits: int = 3072, n_total: int = 100000, sample: int = 0, steps: int = 1, warmup: int = 0,
         group: str = "modp"):
     cores = accel.cores()
@@ -23,9 +36,7 @@ def run(bits: int = 3072, n_total: int = 100000, sample: int = 0, steps: int = 1
         from . import ec
         G = ec.ECqPGroup(group)
         if sample <= 0:
-            # measured here: ~13 ms per ciphertext and core on P-256 (a third of it the Python orchestration of
-            # the oracle around the GMP calls); aim at ~15 s per step
-            sample = max(8 * cores, min(n_total, int(15.0 * cores / 0.0125)))
+            sample = default_sample(bits, n_total, group)
         undo = accel.install_ec(G, cores)
         label, lib_note, member_note = "ECqPGroup(%s)" % group, "oracle/cpu_ref_ec.c", "on-curve"
     else:
@@ -33,9 +44,7 @@ def run(bits: int = 3072, n_total: int = 100000, sample: int = 0, steps: int = 1
         p, q, g = groups.rfc3526(bits) if bits != 512 else groups.test512()
         G = ar.ModPGroup(p, q, g)
         if sample <= 0:
-            # measured here: ~46 ms per ciphertext and core at 3072 bits; aim at ~15 s per step
-            per_ct = 0.046 * (bits / 3072.0) ** 2
-            sample = max(8 * cores, min(n_total, int(15.0 * cores / per_ct)))
+            sample = default_sample(bits, n_total, group)
         undo = accel.install(G, cores)
         label, lib_note, member_note = "ModPGroup(RFC3526-%d)" % bits, "oracle/cpu_ref.c", "Legendre-symbol"
     try:
@@ -59,7 +68,7 @@ def run(bits: int = 3072, n_total: int = 100000, sample: int = 0, steps: int = 1
         t = sum(times) / len(times)
     finally:
         undo()
-    return {"value": sample / t, "ms_per_step": t * 1e3, "cores": cores,
+    return {"value": sample / t, "ms_per_step": t * 1e3, "cores": cores, "sample_n": sample,
             "sample": "%d of %d ciphertexts (re-encrypt + prove + verify incl. Fiat-Shamir hashing and %s "
                       "membership checks), GMP 6 via %s, %d threads" % (sample, n_total, member_note, lib_note, cores)}
 
@@ -82,7 +91,7 @@ def run_verify_mix(bits: int = 3072, n_total: int = 100000, sample: int = 0, ste
         per_ct, label, lib_note = 0.055 * (bits / 3072.0) ** 2, "ModPGroup(RFC3526-%d)" % bits, "oracle/cpu_ref.c"
         install = accel.install
     if sample <= 0:
-        sample = max(8 * cores, min(n_total, int(15.0 * cores / per_ct)))
+        sample = default_sample(bits, n_total, group, mix=True)
     undo = install(G, cores)
     try:
         params = pr.Params(pgroup_string=label)
@@ -103,7 +112,7 @@ def run_verify_mix(bits: int = 3072, n_total: int = 100000, sample: int = 0, ste
         t = sum(times) / len(times)
     finally:
         undo()
-    return {"value": sample / t, "ms_per_step": t * 1e3, "cores": cores,
+    return {"value": sample / t, "ms_per_step": t * 1e3, "cores": cores, "sample_n": sample,
             "sample": "%d of %d ciphertexts (verification of a %d-party mix, threshold %d, from its proof directory "
                       "incl. Fiat-Shamir hashing and membership checks), GMP 6 via %s, %d threads"
                       % (sample, n_total, k, threshold, lib_note, cores)}

@@ -238,9 +238,19 @@ class PoSBasicTW:
 # ---------------------------------------------------------------- Fiat-Shamir wrapper (hvzk/PoSTW.java)
 class Params:
     def __init__(self, vbitlenro=256, ebitlenro=256, rbitlen=100, rohash="sha256", prghash="sha256",
-                 version="3.1.0", rosid="vmx.session", pgroup_string=""):
+                 version="3.1.0", sid="vmx", auxsid="default", pgroup_string=""):
         self.vbitlenro, self.ebitlenro, self.rbitlen = vbitlenro, ebitlenro, rbitlen
-        self.rohash, self.prghash, self.version, self.rosid, self.pgroup_string = rohash, prghash, version, rosid, pgroup_string
+        self.rohash, self.prghash, self.version, self.pgroup_string = rohash, prghash, version, pgroup_string
+        self.sid, self.auxsid = sid, auxsid
+
+    @property
+    def rosid(self) -> str:
+        """mixnet/MixNetElGamalVerifyFiatShamirSession.java:160."""
+        return self.sid + "." + self.auxsid
+
+    def with_auxsid(self, auxsid: str) -> "Params":
+        return Params(self.vbitlenro, self.ebitlenro, self.rbitlen, self.rohash, self.prghash, self.version, self.sid,
+                      auxsid, self.pgroup_string)
 
     def prefix(self) -> bytes:
         names = {"sha256": "SHA-256", "sha384": "SHA-384", "sha512": "SHA-512"}
@@ -811,14 +821,16 @@ def _eval_in_exponent(G, coeffs, l):
     return acc
 
 
-def run_mix(G, params: Params, k: int, threshold: int, w, rs, auxsid="default"):
+def run_mix(G, params: Params, k: int, threshold: int, w, rs, auxsid=None):
     """Returns (proof directory as dict name -> bytes, plaintext elements)."""
+    if auxsid is not None:
+        params = params.with_auxsid(auxsid)
     q = G.q
     poly = [ar.ring_random_element(G, rs, params.rbitlen) for _ in range(threshold)]
     xs = {l: sum(a * pow(l, i, q) for i, a in enumerate(poly)) % q for l in range(1, k + 1)}
     coeffs = [G.op_exp(G.g, a) for a in poly]
     pk = (G.g, coeffs[0])
-    d = {"version": params.version.encode(), "type": b"mixing", "auxsid": auxsid.encode(), "width": b"1",
+    d = {"version": params.version.encode(), "type": b"mixing", "auxsid": params.auxsid.encode(), "width": b"1",
          "FullPublicKey.bt": ar.elem_tree(G, pk).to_bytes(),
          "proofs/PolynomialInExponent.bt": bt.node([ar.elem_tree(G, c) for c in coeffs]).to_bytes(),
          "Ciphertexts.bt": ar.array_tree(G, w).to_bytes(), "proofs/activethreshold": str(threshold).encode()}
@@ -869,14 +881,31 @@ class MixVerificationError(Exception):
     pass
 
 
-def verify_mix(G, params: Params, k: int, threshold: int, d: dict) -> dict:
-    """The verdicts of mixnet/MixNetElGamalVerifyFiatShamirSession.verify for a proof of type "mixing"."""
+def verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_auxsid=None) -> dict:
+    """The verdicts of mixnet/MixNetElGamalVerifyFiatShamirSession.verify for a proof of type "mixing".  A file
+    that is malformed where the reference does not substitute trivial values is fail-stop."""
+    try:
+        return _verify_mix(G, params, k, threshold, d, expected_auxsid)
+    except (bt.EIOError, ar.FormatError, ValueError, IndexError, AttributeError, TypeError) as e:
+        raise MixVerificationError("malformed proof directory: %s" % e)
+
+
+def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_auxsid=None) -> dict:
     def need(name):
         if name not in d:
             raise MixVerificationError("missing " + name)
         return d[name]
     if need("version").decode() != params.version or need("type") != b"mixing" or need("width") != b"1":
         raise MixVerificationError("header")
+    # determineAuxsid (MixNetElGamalVerifyFiatShamirSession.java:369-395): read from the proof, validated, and part
+    # of the global prefix (:160); [VCR-mem] Protocol.validateSid = letters, digits, underscores, spaces
+    import re
+    auxsid = need("auxsid").decode("ascii", errors="replace")
+    if re.fullmatch(r"[A-Za-z0-9_ ]{1,1024}", auxsid) is None:
+        raise MixVerificationError("auxsid")
+    if expected_auxsid is not None and auxsid != expected_auxsid:
+        raise MixVerificationError("auxsid mismatch")
+    params = params.with_auxsid(auxsid)
     try:
         pk = ar.parse_elem(G, bt.from_bytes(need("FullPublicKey.bt")), (None, None))
         t = bt.from_bytes(need("proofs/PolynomialInExponent.bt"))

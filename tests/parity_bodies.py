@@ -803,3 +803,181 @@ def wide_committed_shuffle_parity(vmx, spec, width, maxciph, n):
     raw[-2] ^= 8
     okb, outb = mix.verifyCommittedShuffle(verifier, width, sg, pcv.commitment, w, dataclasses.replace(proof, reply=bytes(raw)))
     assert okb is False and col_values(outb) == ow
+
+
+# ---------------------------------------------------------------------------------------- production-shape kernels
+def production_kernels(vmx, bits, n, fixed_windows=(16, 17), mexp_window=12, var_chunk=0):
+    """The launches a BASELINE-sized step makes -- thread-per-element k_exp_var / k_exp_var2 (n above the
+    cooperative-kernel bound), k_exp_fixed over tables of 16/17-bit windows (split over `parts`), Pippenger at
+    c = 12 with length-sorted chunks, k_inv_up/down, the Z_q scans -- bit for bit against the GMP oracle
+    (oracle/accel.py, itself pinned to Python integers in tests/test_oracle_accel.py).
+    Reference semantics: hvzk/PoSBasicTW.java:1028-1035 (B-chain), elgamal/DistrElGamalSession.java:377-385
+    (decryption factors), hvzk/PoSBasicTW.java:407-410,1020-1021 (multi-exponentiations)."""
+    from oracle import accel
+    rnd = random.Random(bits * 31 + n)
+    A = vmx.arithm
+    p, q, g = group_params(bits)
+    G = A.ModPGroup(p, q, g)
+    R = G.getPRing()
+    OG = oar.ModPGroup(p, q, g)
+    acc = accel.Accel(p, q=q)
+    lq = q.bit_length()
+    vals = lambda arr: [e.value for e in arr.elements()]
+    ring = lambda es: R.toElementArray([A.PFieldElement(R, e) for e in es])
+
+    full = [rnd.randrange(q) for _ in range(n)]
+    full[:4] = [0, 1, q - 1, 1 << (lq - 1)]
+    xs = acc.exp_fixed(g, [rnd.randrange(q) for _ in range(n)], lq)
+    xs[:3] = [1, p - 1, g]
+    ys = xs[1:] + xs[:1]
+    X = G.toElementArray([A.PGroupElement(G, x) for x in xs])
+    Y = G.toElementArray([A.PGroupElement(G, y) for y in ys])
+    assert vals(X) == xs
+    if var_chunk:
+        G.set_tuning(var_chunk=var_chunk)
+
+    # fixed base, full-length exponents, at the windows the cost model picks for N = 10^5 .. 10^6
+    E = ring(full)
+    want = acc.exp_fixed(g, full, lq)
+    for w in fixed_windows:
+        G.set_tuning(fixed_window=w)
+        assert vals(G.getg().exp(E)) == want, "k_exp_fixed w=%d" % w
+    G.set_tuning(fixed_window=0)
+
+    # variable base: per-element 613-bit exponents (B_shift.exp(k_E)), one L_q-bit exponent for all (decryption factors)
+    k613 = [rnd.randrange(1 << 613) % q for _ in range(n)]
+    k613[:3] = [0, 1, ((1 << 613) - 1) % q]
+    K = ring(k613)
+    assert vals(X.exp(K)) == acc.exp_var(xs, k613), "k_exp_var per-element"
+    s = rnd.randrange(q >> 1, q - (1 << 70))
+    assert vals(X.exp(A.PFieldElement(R, s))) == acc.exp_var(xs, s), "k_exp_var common exponent"
+    assert vals(X.exp(E)) == acc.exp_var(xs, full), "k_exp_var full-length per-element"
+
+    # simultaneous exponentiation x^v * y^k (the verifier's B-chain check)
+    v = rnd.randrange(1 << 256)
+    got = vals(X.expMulExp(A.PFieldElement(R, v), Y, K))
+    assert got == acc.mul(acc.exp_var(xs, v), acc.exp_var(ys, k613)), "k_exp_var2"
+
+    # multi-exponentiation at the production window
+    G.set_tuning(mexp_window=mexp_window)
+    e256 = [rnd.randrange(1 << 256) for _ in range(n)]
+    e256[:2] = [0, (1 << 256) - 1]
+    assert X.expProd(ring(e256)).value == acc.expprod(xs, e256), "Pippenger 256"
+    assert X.expProd(K).value == acc.expprod(xs, k613), "Pippenger 613"
+    assert X.expProd(E).value == acc.expprod(xs, full), "Pippenger L_q"
+    G.set_tuning(mexp_window=0)
+
+    # element-wise product, product of all, inversion by Montgomery's trick
+    assert vals(X.mul(Y)) == acc.mul(xs, ys)
+    pr = 1
+    for x in xs:
+        pr = pr * x % p
+    assert X.prod().value == pr
+    inv = vals(X.inv())
+    assert acc.mul(inv, xs) == [1] * n and inv[:3] == [1, p - 1, pow(g, -1, p)]
+
+    # Z_q scans at this size
+    a = [rnd.randrange(q) for _ in range(n)]
+    b = [rnd.randrange(q) for _ in range(n)]
+    Ar, Br = ring(a), ring(b)
+    assert vals(Ar.prods()) == oar.r_prods(OG, a)
+    x_, d_ = Br.recLin(Ar)
+    ox, od = oar.r_rec_lin(OG, b, a)
+    assert vals(x_) == ox and d_.value == od
+    assert Ar.innerProduct(Br).value == oar.r_inner(OG, a, b)
+
+
+def with_env(monkeypatch, **env):
+    for k, v in env.items():
+        monkeypatch.setenv(k, str(v))
+
+
+def malformed_proof_files(vmx, spec, n, k=3, threshold=2):
+    """Every file of a proof directory replaced in turn by (a) thousands of nested node headers, (b) nothing,
+    (c) two bytes: the verifier answers with a verdict or VerificationError (the reference's fail-stop), never a
+    stray parser exception (RecursionError, EIOException, ValueError), and the oracle agrees on accept/reject."""
+    vm = importlib.import_module("verificatum-vmn_b200.vmnv")
+    mix = importlib.import_module("verificatum-vmn_b200.mixnet")
+    G, OG = engine_group(vmx, spec), oracle_group(spec)
+    params = mix.SessionParams(pGroupString="mix-%s" % spec)
+    oparams = opr.Params(pgroup_string="mix-%s" % spec)
+    rs = vmx.crypto.PRGHeuristic()
+    rs.setSeed(seed("mix/dealer"))
+    M = vm.MixNetElGamal(G, params, k, threshold, rs)
+    irs = vmx.crypto.PRGHeuristic()
+    irs.setSeed(seed("mix/input"))
+    M.run(mix.demoCiphertexts(M.fullPublicKey, n, irs)).free()
+    V = vm.MixNetElGamalVerifyFiatShamirSession(G, params, k, threshold)
+    assert V.verify(M.nizkp)["accepted"]
+    nested = b"\x00\x00\x00\x00\x01" * 5000
+    for name in sorted(M.nizkp):
+        for junk in (nested, b"", b"\x00\x01"):
+            bad = vm.ProofDirectory(M.nizkp)
+            bad[name] = junk
+            try:
+                accepted = V.verify(bad)["accepted"]
+            except vm.VerificationError:
+                accepted = False
+            try:
+                oaccepted = opr.verify_mix(OG, oparams, k, threshold, dict(bad))["accepted"]
+            except opr.MixVerificationError:
+                oaccepted = False
+            assert accepted == oaccepted, (name, len(junk), accepted, oaccepted)
+            # the combined check uses the replies of the first `threshold` correct parties only
+            # (elgamal/DistrElGamalSessionBasic.java:642-678): a malformed reply of a later party is ignored
+            unused = [vm.ProofDirectory.DFRfile(l) for l in range(threshold + 1, k + 1)]
+            assert not accepted or name in unused, (name, len(junk))
+    # the auxiliary session identifier is read from the proof and enters the global prefix
+    # (mixnet/MixNetElGamalVerifyFiatShamirSession.java:160,369-395): another valid one fails every proof, a
+    # mismatch with the expected one is fail-stop
+    other = vm.ProofDirectory(M.nizkp)
+    other["auxsid"] = b"another_session"
+    rep = None
+    try:
+        rep = V.verify(other)
+    except vm.VerificationError:
+        pass
+    assert rep is None or not rep["accepted"]
+    try:
+        vm.MixNetElGamalVerifyFiatShamirSession(G, params, k, threshold, expectedAuxsid="elsewhere").verify(M.nizkp)
+        assert False
+    except vm.VerificationError:
+        pass
+    assert vm.MixNetElGamalVerifyFiatShamirSession(G, params, k, threshold,
+                                                   expectedAuxsid=params.auxsid).verify(M.nizkp)["accepted"]
+    M2 = vm.MixNetElGamal(G, params, k, threshold, rs, auxsid="second run")
+    M2.run(mix.demoCiphertexts(M2.fullPublicKey, n, irs)).free()
+    assert V.verify(M2.nizkp)["accepted"]
+    assert opr.verify_mix(OG, oparams, k, threshold, dict(M2.nizkp))["accepted"]
+
+
+def squaring_selftest(vmx, bits, n, iters=3):
+    """The dedicated (block-triangular) squaring against repeated multiplication, word for word, on random
+    residues and on the edge patterns of its doubling logic (top bits at the 16-word block boundaries, all-ones
+    words, p - 1, small values); then against Python integers."""
+    import ctypes as C
+    rnd = random.Random(bits + n)
+    A = vmx.arithm
+    p, q, g = group_params(bits)
+    G = A.ModPGroup(p, q, g)
+    nl = bits // 32
+    R = 1 << bits
+    Rinv = pow(R, -1, p)
+    vals = [rnd.randrange(1, p) for _ in range(n)]
+    # the kernels see x * R mod p: choose the Montgomery images, then map back
+    mont = [1, p - 1, p - 2, 2, (1 << (bits - 1)) - 1, (1 << (bits - 1)) % p]
+    for blk in range(nl // 16):
+        mont.append(((1 << (512 * (blk + 1))) - 1) % p)                    # all-ones up to a block boundary
+        mont.append((1 << (512 * blk + 511)) % p)                           # only the top bit of block blk
+        mont.append(sum(1 << (512 * b + 511) for b in range(blk + 1)) % p)  # top bits of blocks 0..blk
+    vals += [m * Rinv % p or 1 for m in mont if 0 < m < p]
+    X = G.toElementArray([A.PGroupElement(G, v) for v in vals])
+    eq = C.c_int()
+    lib = vmx._native.load()
+    for it in (1, iters):
+        vmx._native.check(lib.vmx_selftest_sqr(X.h, it, C.byref(eq), None))
+        assert eq.value == 1, it
+    # and the squaring chain of a variable-base exponentiation against Python
+    e = A.PFieldElement(G.getPRing(), 1 << 7)
+    G.set_tuning(coop_max=0)
+    assert [x.value for x in X.exp(e).elements()] == [pow(v, 1 << 7, p) for v in vals]

@@ -30,6 +30,20 @@ def test_transcript_parity(engine_emul, n):
     pb.transcript_parity(engine_emul, 512, n)
 
 
+def test_variable_base_kernels_in_several_launches(engine_emul, monkeypatch):
+    """VMX_VAR_CHUNK bounds the elements per launch of k_exp_var / k_exp_var2 (production: the table scratch
+    bound, reached above ~244k elements at 3072 bits): the i0 > 0 launches, and Pippenger at c = 12."""
+    pb.with_env(monkeypatch, VMX_VAR_CHUNK=3, VMX_MEXP_WINDOW=12)
+    pb.group_ops(engine_emul, 512, 37)
+    pb.decryption_parity(engine_emul, 512, 11, 3, 2)
+    pb.transcript_parity(engine_emul, 512, 10)
+
+
+def test_production_kernels_body_on_emulation(engine_emul):
+    """The body of the GPU production-shape test (GMP oracle) at a size the emulation build follows."""
+    pb.production_kernels(engine_emul, 512, 150, fixed_windows=(5, 9), mexp_window=8, var_chunk=64)
+
+
 def test_accept_reject_larger(engine_emul):
     pb.accept_reject_properties(engine_emul, 512, 700)
 
@@ -111,3 +125,13 @@ def test_wide_ciphertexts_parity(engine_emul, spec, width, n):
     """BASELINE.json config 4: width-3 ciphertexts, shuffle + PoS and pre-computation + CCPoS."""
     pb.wide_shuffle_parity(engine_emul, spec, width, n)
     pb.wide_committed_shuffle_parity(engine_emul, spec, width, n + 3, n)
+
+
+def test_malformed_proof_files_are_verdicts_not_crashes(engine_emul):
+    pb.malformed_proof_files(engine_emul, 512, 5)
+
+
+@pytest.mark.parametrize("bits,n", [(2048, 12), (3072, 8)])
+def test_dedicated_squaring(engine_emul, bits, n):
+    """mont_sqr_tri (4 and 6 blocks of 16 words) on the emulated carry chains."""
+    pb.squaring_selftest(engine_emul, bits, n, iters=2)

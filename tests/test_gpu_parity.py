@@ -78,6 +78,35 @@ def test_cooperative_multiplier_matches_thread_per_element(engine_cuda, bits):
     assert eq.value == 1
 
 
+@pytest.mark.parametrize("bits,n", [(3072, 10240), (2048, 12288)])
+def test_production_kernels_against_gmp_oracle(engine_cuda, bits, n):
+    """n above the cooperative-kernel bound (8192): k_exp_var / k_exp_var2 / k_exp_fixed at w = 16, 17 / Pippenger
+    c = 12 / k_inv_up,down at 96 and 64 limbs, bit for bit against GMP."""
+    pb.production_kernels(engine_cuda, bits, n)
+
+
+def test_production_kernels_multi_launch(engine_cuda):
+    """The variable-base kernels cut an array in several launches once their table scratch is bounded (n above
+    ~244k at 3072 bits); forced here at n = 9000 with 4096 elements per launch (i0 > 0 offsets)."""
+    pb.production_kernels(engine_cuda, 3072, 9000, fixed_windows=(16,), var_chunk=4096)
+
+
+@pytest.mark.parametrize("bits,n", [(2048, 12), (3072, 11)])
+def test_transcripts_through_thread_per_element_kernels(engine_cuda, monkeypatch, bits, n):
+    """The oracle-sized protocol transcripts with the kernel selection of a BASELINE-sized run: no
+    warp-cooperative shortcut for small arrays (VMX_COOP_MAX=0), several launches per array (VMX_VAR_CHUNK),
+    Pippenger at c = 12: PoS prove/verify, decryption factors and their proof, byte for byte."""
+    pb.with_env(monkeypatch, VMX_COOP_MAX=0, VMX_VAR_CHUNK=5, VMX_MEXP_WINDOW=12)
+    pb.transcript_parity(engine_cuda, bits, n)
+    pb.decryption_parity(engine_cuda, bits, n - 2, 3, 2)
+    pb.group_ops(engine_cuda, bits, n + 9)
+
+
+@pytest.mark.parametrize("bits,n", [(2048, 3000), (3072, 3000)])
+def test_dedicated_squaring(engine_cuda, bits, n):
+    pb.squaring_selftest(engine_cuda, bits, n, iters=5)
+
+
 def test_accept_reject_at_scale_3072(engine_cuda):
     """N = 50,000 at 3072 bits (thread-per-element kernels, several waves, Pippenger c = 12)."""
     pb.accept_reject_properties(engine_cuda, 3072, 50000)

@@ -47,6 +47,7 @@ SIGNATURES = {
     "vmx_ctx_sync": (C.c_int, [_P]),
     "vmx_ctx_stream": (_P, [_P]),
     "vmx_ctx_set_fixed_window": (C.c_int, [_P, C.c_int]),
+    "vmx_ctx_set_tuning": (C.c_int, [_P, C.c_char_p, C.c_longlong]),
     "vmx_garr_from_bytes": (C.c_int, [_P, _SZ, _P, C.c_int, _PP]),
     "vmx_garr_from_raw": (C.c_int, [_P, _SZ, _P, _SZ, C.c_uint, _PP]),
     "vmx_garr_prg_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, _SZ, C.c_uint, _PP]),
@@ -114,6 +115,7 @@ SIGNATURES = {
     "vmx_ctx_launch_count": (C.c_uint64, [_P]),
     "vmx_ctx_modmul_count": (C.c_uint64, [_P]),
     "vmx_selftest_coop": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
+    "vmx_selftest_sqr": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "vmx_debug_coop_mul": (C.c_int, [_P, _P, _PP]),
     "vmx_bench_modmul": (C.c_int, [_P, _SZ, C.c_int, C.POINTER(C.c_float)]),
 }

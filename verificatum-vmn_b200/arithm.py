@@ -636,6 +636,12 @@ class ModPGroup(PGroup):
     def sync(self) -> None:
         nat.check(self._lib.vmx_ctx_sync(self.ctx))
 
+    def set_tuning(self, **knobs: int) -> None:
+        """Kernel-selection knobs of the engine (vmx_ctx_set_tuning: coop_max, var_chunk, mexp_window,
+        fixed_window); none changes a result."""
+        for k, v in knobs.items():
+            nat.check(self._lib.vmx_ctx_set_tuning(self.ctx, k.encode(), int(v)))
+
     def precomputeFixedBase(self, el: "PGroupElement", size_hint: int) -> None:
         nat.check(self._lib.vmx_fixed_precompute(self.ctx, _be(el.value, self.elem_bytes), size_hint))
 

@@ -13,6 +13,7 @@ import os
 import queue
 import struct
 import threading
+import time
 
 from . import _trace
 
@@ -78,6 +79,21 @@ class PRGHeuristic(RandomSource):
         return out
 
 
+# process-wide accounting of the Fiat-Shamir hashing (bytes fed to random-oracle digests and the seconds spent
+# in their SHA-256 updates): bench.py reports the hashed bytes per step and the SHA-256 rate next to the
+# end-to-end figure, so that its Amdahl bound (one stream per challenge) can be audited
+_hash_account = {"bytes": 0, "seconds": 0.0}
+_hash_lock = threading.Lock()
+
+
+def hashed_bytes() -> int:
+    return _hash_account["bytes"]
+
+
+def hashed_seconds() -> float:
+    return _hash_account["seconds"]
+
+
 class RandomOracleDigest:
     def __init__(self, hf: HashfunctionHeuristic, out_bits: int):
         self.hf = hf
@@ -88,9 +104,17 @@ class RandomOracleDigest:
 
     def update(self, data) -> None:
         n = len(data) if not hasattr(data, "nbytes") else data.nbytes
-        if _trace.enabled and n >= 1 << 16:
-            with _trace.span("sha256.update", n):
+        if n >= 1 << 16:
+            t0 = time.perf_counter()
+            if _trace.enabled:
+                with _trace.span("sha256.update", n):
+                    self.h.update(data)
+            else:
                 self.h.update(data)
+            dt = time.perf_counter() - t0
+            with _hash_lock:
+                _hash_account["bytes"] += n
+                _hash_account["seconds"] += dt
         else:
             self.h.update(data)
         self.nbytes += n

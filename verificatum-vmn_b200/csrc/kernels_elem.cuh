@@ -223,6 +223,19 @@ VMX_KERNEL(N) k_mul_iter(const uint32_t* __restrict__ a_, const uint32_t* __rest
   store_elem<N>(a, out, cap, i);
 }
 
+// out[i] = a[i]^(2^iters): the dedicated squaring (mont_sqr) on its own -- self test against k_mul and benchmark
+template <int N>
+VMX_KERNEL(N) k_sqr_iter(const uint32_t* __restrict__ a_, size_t acap, uint32_t* __restrict__ out, size_t ocap, size_t n,
+                         int iters, const __grid_constant__ MontParams<N> M) {
+  VMX_DYN_SMEM(uint2, smem);
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t a[N];
+  load_elem<N>(a, a_, acap, i);
+  for (int it = 0; it < iters; it++) mont_sqr<N>(a, smem + threadIdx.x, blockDim.x, M);
+  store_elem<N>(a, out, ocap, i);
+}
+
 // ------------------------------------------------------------------ fixed-base exponentiation
 // table: nwin * 2^w entries, entry (k, d) = base^(d * 2^(w*k)) in Montgomery form (d = 0 -> one).
 // Work item = (element i, window range part): part p of `parts` multiplies windows

@@ -64,11 +64,13 @@ struct OneLoader {
   VMX_DEV Word2 operator()(int i) const { return Word2{i == 0 ? 1u : 0u, 0u}; }
 };
 
-// a <- a^2 (Montgomery), via a shared-memory copy of a.
+// a <- a^2 (Montgomery), via a shared-memory copy of a: the block-triangular squaring of mont.cuh from 32 limbs
+// on (0.79 of a multiplication's IMAD.WIDE at 96 limbs), a plain multiplication below.
 template <int N>
 VMX_DEV void mont_sqr(uint32_t (&a)[N], uint2* s, unsigned stride, const MontParams<N>& M) {
   stash_shared<N>(a, s, stride);
-  mont_mul<N>(a, SharedLoader{s, stride}, M);
+  if constexpr (N >= 32 && N % 16 == 0) mont_sqr_tri<N>(a, SharedLoader{s, stride}, M);
+  else mont_mul<N>(a, SharedLoader{s, stride}, M);
 }
 
 // bit window [pos, pos+w) of the little-endian limb string of element i in a limb-major array.

@@ -180,4 +180,153 @@ VMX_DEV void mont_mul(uint32_t (&a)[N], Loader ld2, const MontParams<N>& M) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ squaring
+// a^2 with every cross product a[i]*a[j], i != j, of DIFFERENT 16-word blocks computed once.
+//
+// Write a = sum_I A_I B^(16 I) (B = 2^32, A_I = 16 words).  Then
+//     a^2 = sum_I A_I^2 B^(32 I)  +  sum_I (2 A_I) B^(16 I) * A_{>I},      A_{>I} = sum_{j >= 16(I+1)} a[j] B^j.
+// Row i of block I (i = 16 I + r) therefore multiplies
+//     the diagonal block   a[j], 16 I <= j < 16(I+1),  by x = a[i]               (the block squared in full)
+//     the columns beyond   a[j], j >= 16(I+1),          by y = word r of 2 A_I   (each cross block once, doubled)
+// and nothing below the diagonal block.  2 A_I has 16 words d'[r] = (a[i] << 1) | (r ? a[i-1] >> 31 : 0) and one
+// bit c_I = a[16 I + 15] >> 31 on top; the top bit contributes c_I * B^(16(I+1)) * A_{>I}, which sits exactly on the
+// accumulator's own columns once the block's 16 rows are done (relative column j <-> a[j]): one masked add chain per
+// block boundary.  Column index ranges are static per block (the row-wise CIOS keeps columns in registers, so a
+// row cannot skip a dynamic number of them): one loop per block, N/16 loops.  The reduction rows are those of the
+// multiplication.  Work: N^2 (reduction) + 16 * sum_I (N - 16 I) = N^2 + 8 N (N/16 + 1) IMAD.WIDE:
+// 14,592 at N = 96 (multiplication 18,432: 0.79), 6,656 at N = 64 (8,192: 0.81).  The order of the additions differs
+// from mont_mul(a, a), the sum does not: the accumulator ends at (a^2 + m n) / R < 2n with the same m.
+//
+// Structure of a trip as in mont_rowpair (E/O column classes, O-class products in an aligned side block).
+template <int N, int D0, int J0>
+VMX_DEV void mont_sqr_rowpair(uint32_t (&t)[N + 2], const uint32_t (&a)[N], uint32_t x0, uint32_t x1, uint32_t y0,
+                              uint32_t y1, const MontParams<N>& M) {
+  static_assert(N % (2 * kPairBlock) == 0 && D0 % (2 * kPairBlock) == 0 && J0 == D0 + 2 * kPairBlock, "16-word blocks");
+  constexpr int PB = kPairBlock;
+  uint32_t top2 = 0;  // column N+2
+
+  // E-class, row 0: a[even j >= D0] * (x0 | y0) on pairs (j, j+1)
+  mad_wide_cc(t[D0], t[D0 + 1], a[D0], x0);
+#pragma unroll
+  for (int j = D0 + 2; j < N; j += 2) madc_wide_cc(t[j], t[j + 1], a[j], j < J0 ? x0 : y0);
+  addc_cc(t[N], t[N], 0);
+  addc(t[N + 1], t[N + 1], 0);
+
+  const uint32_t m0 = t[0] * M.n0inv;
+
+  // E-class, row 0 reduction: n[even j] * m0
+  mad_wide_cc(t[0], t[1], M.n[0], m0);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) madc_wide_cc(t[j], t[j + 1], M.n[j], m0);
+  addc_cc(t[N], t[N], 0);
+  addc(t[N + 1], t[N + 1], 0);
+
+  // E-class, row 1: a[odd j >= D0] * (x1 | y1) on pairs (1+j, 2+j)
+  mad_wide_cc(t[D0 + 2], t[D0 + 3], a[D0 + 1], x1);
+#pragma unroll
+  for (int j = D0 + 3; j < N; j += 2) madc_wide_cc(t[j + 1], t[j + 2], a[j], j < J0 ? x1 : y1);
+  addc(top2, top2, 0);
+
+  // O-class: pair q on columns (c, c+1), c = 2q+1, receives a[c]*s0 + n[c]*m0 + a[c-1]*s1 + n[c-1]*m1, the
+  // a-terms only for columns of the diagonal block and beyond
+  uint32_t m1 = 0;
+  uint32_t cw = 0;
+#pragma unroll
+  for (int kb = 0; kb < N / 2 / PB; kb++) {
+    uint32_t o[2 * PB];
+    uint32_t oc;
+    const int c0 = 2 * kb * PB + 1;
+    const bool has_a = (c0 - 1 >= D0);
+    const uint32_t s0 = (c0 - 1 < J0) ? x0 : y0, s1 = (c0 - 1 < J0) ? x1 : y1;
+    if (has_a) {
+      mad_wide_cc3(o[0], o[1], a[c0], s0, cw, 0);
+#pragma unroll
+      for (int r = 1; r < PB; r++) mul_wide(o[2 * r], o[2 * r + 1], a[c0 + 2 * r], s0);
+      mad_wide_cc(o[0], o[1], M.n[c0], m0);
+#pragma unroll
+      for (int r = 1; r < PB; r++) madc_wide_cc(o[2 * r], o[2 * r + 1], M.n[c0 + 2 * r], m0);
+      addc(oc, 0, 0);
+      mad_wide_cc(o[0], o[1], a[c0 - 1], s1);
+#pragma unroll
+      for (int r = 1; r < PB; r++) madc_wide_cc(o[2 * r], o[2 * r + 1], a[c0 - 1 + 2 * r], s1);
+      addc(oc, oc, 0);
+    } else {
+      mad_wide_cc3(o[0], o[1], M.n[c0], m0, cw, 0);
+#pragma unroll
+      for (int r = 1; r < PB; r++) mul_wide(o[2 * r], o[2 * r + 1], M.n[c0 + 2 * r], m0);
+      oc = 0;
+    }
+    if (kb == 0) m1 = (t[1] + o[0]) * M.n0inv;
+    mad_wide_cc(o[0], o[1], M.n[c0 - 1], m1);
+#pragma unroll
+    for (int r = 1; r < PB; r++) madc_wide_cc(o[2 * r], o[2 * r + 1], M.n[c0 - 1 + 2 * r], m1);
+    addc(oc, oc, 0);
+    add_cc(t[c0], t[c0], o[0]);
+#pragma unroll
+    for (int r = 1; r < 2 * PB; r++) addc_cc(t[c0 + r], t[c0 + r], o[r]);
+    addc(cw, oc, 0);
+  }
+  add_cc(t[N + 1], t[N + 1], cw);
+  addc(top2, top2, 0);
+
+  // E-class, row 1 reduction: n[odd j] * m1 on pairs (1+j, 2+j), written two columns lower.
+  mad_wide_cc3(t[0], t[1], M.n[1], m1, t[2], t[3]);
+#pragma unroll
+  for (int j = 3; j < N; j += 2) madc_wide_cc3(t[j - 1], t[j], M.n[j], m1, t[j + 1], t[j + 2]);
+  addc_cc(t[N], top2, 0);
+  addc(t[N + 1], 0, 0);
+}
+
+// The 16 rows of block I (8 trips), the correction row of its boundary, then block I + 1.  `x` holds the words
+// (a[16 I], a[16 I + 1]) on entry; `ld2(i)` returns (a[i], a[i+1]) from the copy of a in shared memory.
+template <int N, int I, typename Loader>
+VMX_DEV void mont_sqr_blocks(uint64_t (&T)[N / 2 + 1], const uint32_t (&a)[N], Loader ld2, Word2 x,
+                             const MontParams<N>& M) {
+  constexpr int D0 = 16 * I, J0 = 16 * (I + 1);
+  uint32_t t[N + 2];
+  uint32_t prevtop = 0;
+#pragma unroll 1
+  for (int r = 0; r < 16; r += 2) {
+    const int i = D0 + r;
+    const Word2 nx = ld2(i + 2 < N ? i + 2 : i);
+    const uint32_t y0 = (x.x << 1) | prevtop;
+    const uint32_t y1 = (x.y << 1) | (x.x >> 31);
+    prevtop = x.y >> 31;
+#pragma unroll
+    for (int k = 0; k < N / 2 + 1; k++) unpack_pair(t[2 * k], t[2 * k + 1], T[k]);
+    mont_sqr_rowpair<N, D0, J0>(t, a, x.x, x.y, y0, y1, M);
+#pragma unroll
+    for (int k = 0; k < N / 2 + 1; k++) T[k] = pack_pair(t[2 * k], t[2 * k + 1]);
+    x = nx;
+  }
+  if constexpr (J0 < N) {
+    // the top bit of 2 A_I times A_{>I}: relative column j of the accumulator is now absolute column 16(I+1) + j
+    const uint32_t mask = 0u - prevtop;
+#pragma unroll
+    for (int k = 0; k < N / 2 + 1; k++) unpack_pair(t[2 * k], t[2 * k + 1], T[k]);
+    add_cc(t[J0], t[J0], a[J0] & mask);
+#pragma unroll
+    for (int j = J0 + 1; j < N; j++) addc_cc(t[j], t[j], a[j] & mask);
+    addc_cc(t[N], t[N], 0);
+    addc(t[N + 1], t[N + 1], 0);
+#pragma unroll
+    for (int k = 0; k < N / 2 + 1; k++) T[k] = pack_pair(t[2 * k], t[2 * k + 1]);
+    mont_sqr_blocks<N, I + 1>(T, a, ld2, x, M);
+  }
+}
+
+// a <- a * a * R^{-1} mod n; `ld2` streams a copy of a (shared memory).  Result fully reduced.
+template <int N, typename Loader>
+VMX_DEV void mont_sqr_tri(uint32_t (&a)[N], Loader ld2, const MontParams<N>& M) {
+  static_assert(N % 16 == 0 && N >= 32, "block-triangular squaring needs at least two 16-word blocks");
+  uint64_t T[N / 2 + 1];
+#pragma unroll
+  for (int k = 0; k < N / 2 + 1; k++) T[k] = 0;
+  mont_sqr_blocks<N, 0>(T, a, ld2, ld2(0), M);
+  uint32_t t[N + 2];
+#pragma unroll
+  for (int k = 0; k < N / 2 + 1; k++) unpack_pair(t[2 * k], t[2 * k + 1], T[k]);
+  mont_final_sub<N>(a, t, M);
+}
+
 }  // namespace vmx

@@ -516,7 +516,6 @@ static int exp_fixed_run(vmx_ctx* c, const FixedTable& T, const vmx_rarr* e, int
 }
 
 // ------------------------------------------------------------------ variable-base
-constexpr size_t kCoopMaxElems = 8192;  // arrays up to this size use the warp-per-element kernels
 static int choose_var_window(int ebits) {
   int bw = 1;
   double best = 1e300;
@@ -541,7 +540,7 @@ static int exp_var_run(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32_
     return VMX_OK;
   }
 #ifndef VMX_HOST_EMUL
-  if (n <= kCoopMaxElems) {  // one warp per element: low latency, fills the machine with few elements
+  if (n <= c->coop_max) {  // one warp per element: low latency, fills the machine with few elements
     VMX_LAUNCH(c, k_coop_exp<N>, nblocks(n, kCoopWarps), 32 * kCoopWarps, 0, a, acap, E, ecap, escalar ? 1 : 0, ebits,
                n, c->P.consts, M.n0inv, out, ocap);
     VMX_CHECK_LAUNCH();
@@ -554,6 +553,7 @@ static int exp_var_run(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32_
   const size_t wave = wave_threads(c);
   size_t chunk = (size_t)(6e9 / ((double)(1u << w) * N * 4));
   chunk = std::max(wave, chunk / wave * wave);
+  if (c->var_chunk) chunk = c->var_chunk;
   chunk = std::min(chunk, n);
   ElemBuf tab;
   VMX_TRY(tab.alloc_elems(c, chunk << w));
@@ -579,7 +579,7 @@ static int exp_var2_run(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32
   if (n == 0) return VMX_OK;
   bool split = xbits == 0 || ybits == 0;
 #ifndef VMX_HOST_EMUL
-  split = split || n <= kCoopMaxElems;
+  split = split || n <= c->coop_max;
 #endif
   if (split) {
     ElemBuf t;
@@ -602,6 +602,7 @@ static int exp_var2_run(vmx_ctx* c, const uint32_t* a, size_t acap, const uint32
   const size_t wave = wave_threads(c);
   size_t chunk = (size_t)(6e9 / (2.0 * (double)(1u << w) * N * 4));
   chunk = std::max(wave, chunk / wave * wave);
+  if (c->var_chunk) chunk = c->var_chunk;
   chunk = std::min(chunk, n);
   ElemBuf tabA, tabB;
   VMX_TRY(tabA.alloc_elems(c, chunk << w));
@@ -640,7 +641,7 @@ static int choose_mexp_window(size_t n, int L) {
 template <int N>
 static int mexp_plan(vmx_ctx* c, const vmx_rarr* e, int L, MexpPlan& P) {
   const size_t n = e->n;
-  P.c = choose_mexp_window(n, L);
+  P.c = c->mexp_window ? c->mexp_window : choose_mexp_window(n, L);
   P.W = (L + P.c - 1) / P.c;
   P.J = P.c / kSubDigit;
   P.nb = (size_t)P.W << P.c;
@@ -915,6 +916,19 @@ static int inv_batch(vmx_ctx* c, const uint32_t* a, size_t acap, size_t n, uint3
   return VMX_OK;
 }
 
+// Initial values of the tuning knobs (vmx_ctx_set_tuning) from the environment, read when a context is created:
+// VMX_COOP_MAX, VMX_VAR_CHUNK, VMX_MEXP_WINDOW.  The parity tests use them to send the oracle-sized protocol
+// transcripts through the kernels that production-sized arrays take.
+template <typename Ctx>
+static void tuning_from_env(Ctx& c) {
+  if (const char* e = std::getenv("VMX_COOP_MAX")) c->coop_max = (size_t)std::strtoull(e, nullptr, 10);
+  if (const char* e = std::getenv("VMX_VAR_CHUNK")) c->var_chunk = (size_t)std::strtoull(e, nullptr, 10);
+  if (const char* e = std::getenv("VMX_MEXP_WINDOW")) {
+    const int v = std::atoi(e);
+    if (v == 4 || v == 8 || v == 12 || v == 16) c->mexp_window = v;
+  }
+}
+
 extern "C" {
 
 const char* vmx_last_error(void) { return g_err; }
@@ -963,6 +977,7 @@ int vmx_ctx_create_modp(const uint8_t* p_be, const uint8_t* q_be, const uint8_t*
   }
   c->pm2.assign(c->P.n, c->P.n + c->nl);
   { uint32_t two[kMaxLimbs] = {2}; limbs_sub(c->pm2.data(), two, c->nl); }
+  tuning_from_env(c);
   VMX_CU(cudaSetDevice(device));
 #ifndef VMX_HOST_EMUL
   {
@@ -1064,6 +1079,7 @@ int vmx_ctx_create_ecq(const uint8_t* p_be, const uint8_t* a_be, const uint8_t* 
     for (int j = 0; j < 8; j++) E.sqe[j] = (t[j] >> 2) | (t[j + 1] << 30);
   }
   { uint32_t t[8], three[8] = {3}; std::memcpy(t, p, sizeof p); limbs_sub(t, three, 8); E.a_minus3 = limbs_cmp(a, t, 8) == 0 ? 1u : 0u; }
+  tuning_from_env(c);
   VMX_CU(cudaSetDevice(device));
 #ifndef VMX_HOST_EMUL
   {
@@ -1211,6 +1227,18 @@ void* vmx_ctx_stream(vmx_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int vmx_ctx_set_fixed_window(vmx_ctx* c, int w) {
   if (!c || w < 0 || w > 22) return VMX_EARG;
   c->fixed_window = w;
+  return VMX_OK;
+}
+int vmx_ctx_set_tuning(vmx_ctx* c, const char* key, long long value) {
+  if (!c || !key || value < 0) return VMX_EARG;
+  const std::string k(key);
+  if (k == "coop_max") c->coop_max = (size_t)value;
+  else if (k == "var_chunk") c->var_chunk = (size_t)value;
+  else if (k == "mexp_window") {
+    if (value != 0 && (value % kSubDigit != 0 || value > 16)) { set_error("mexp_window must be 0, 4, 8, 12 or 16"); return VMX_EARG; }
+    c->mexp_window = (int)value;
+  } else if (k == "fixed_window") return vmx_ctx_set_fixed_window(c, (int)value);
+  else { set_error("unknown tuning key %s", key); return VMX_EARG; }
   return VMX_OK;
 }
 uint64_t vmx_ctx_launch_count(const vmx_ctx* c) { return c ? c->launches.load() : 0; }
@@ -2404,6 +2432,52 @@ int vmx_selftest_coop(const vmx_garr* a, const vmx_garr* b, int* equal) {
   VMX_CHECK_LAUNCH();
   return arrays_equal(c, x.d(), x.cap, y.d(), y.cap, a->n, equal, c->nl);
 #endif
+}
+
+// a[i]^2 by the dedicated squaring (mont_sqr, block-triangular from 32 limbs on) against a[i] * a[i] by the
+// multiplication; *ms (optional) = device time of `iters` chained squarings per element
+int vmx_selftest_sqr(const vmx_garr* a, int iters, int* equal, float* ms) {
+  if (!a || !equal || iters < 1) return VMX_EARG;
+  vmx_ctx* c = a->ctx;
+  VMX_ENTER(c);
+  if (c->kind == 1) { set_error("squaring self test: ModPGroup contexts only"); return VMX_EARG; }
+  if (a->n == 0) { *equal = 1; if (ms) *ms = 0.f; return VMX_OK; }
+  ElemBuf x, y;
+  VMX_TRY(x.alloc_elems(c, a->n));
+  VMX_TRY(y.alloc_elems(c, a->n));
+#ifndef VMX_HOST_EMUL
+  cudaEvent_t e0, e1;
+  VMX_CU(cudaEventCreate(&e0));
+  VMX_CU(cudaEventCreate(&e1));
+#endif
+  VMX_DISPATCH(c->nl, {
+    const MontParams<N> M = c->P.params<N>();
+    // reference: x <- a, then x <- x * x (second operand streamed from x itself before it is overwritten: k_mul
+    // reads b[i] word by word while a[i] sits in registers, and writes only at the end)
+    VMX_LAUNCH(c, k_mul<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, a->d, a->cap, x.d(), x.cap, a->n, M);
+    for (int it = 1; it < iters; it++)
+      VMX_LAUNCH(c, k_mul<N>, nblocks(a->n), kThreads, 0, x.d(), x.cap, x.d(), x.cap, x.d(), x.cap, a->n, M);
+#ifndef VMX_HOST_EMUL
+    VMX_CU(cudaEventRecord(e0, c->stream));
+#endif
+    VMX_LAUNCH(c, k_sqr_iter<N>, nblocks(a->n), kThreads, kThreads * N * 4, a->d, a->cap, y.d(), y.cap, a->n, iters, M);
+#ifndef VMX_HOST_EMUL
+    VMX_CU(cudaEventRecord(e1, c->stream));
+#endif
+  });
+  VMX_CHECK_LAUNCH();
+  c->modmuls += 2 * (uint64_t)a->n * iters;
+#ifndef VMX_HOST_EMUL
+  VMX_CU(cudaEventSynchronize(e1));
+  float t = 0.f;
+  VMX_CU(cudaEventElapsedTime(&t, e0, e1));
+  if (ms) *ms = t;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+#else
+  if (ms) *ms = 0.f;
+#endif
+  return arrays_equal(c, x.d(), x.cap, y.d(), y.cap, a->n, equal, c->nl);
 }
 
 // a[i]*b[i] on the cooperative multiplier (debug / test hook)

@@ -82,6 +82,11 @@ struct vmx_ctx {
   std::recursive_mutex api;  // serialises API calls of host threads on this context
   std::map<std::string, vmx::FixedTable> tables;  // key = canonical base bytes
   int fixed_window = 0;                           // 0 = choose from n
+  // tuning knobs (vmx_ctx_set_tuning): production defaults; the parity tests lower them so that small
+  // oracle-sized arrays run through the thread-per-element kernels and their multi-chunk loops
+  size_t coop_max = 8192;                         // arrays up to this size use the warp-per-element kernels
+  size_t var_chunk = 0;                           // elements per launch of k_exp_var / k_exp_var2 (0 = from memory)
+  int mexp_window = 0;                            // Pippenger window c (0 = choose from n and the exponent length)
   int* d_flag = nullptr;                          // device scratch: 4 ints
   int* h_flag = nullptr;                          // pinned scratch: 4 ints
   std::atomic<uint64_t> launches{0}, modmuls{0};

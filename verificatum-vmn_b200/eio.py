@@ -213,6 +213,61 @@ def int32_leaf(x: int) -> ByteTreeLeaf:
     return ByteTreeLeaf(struct.pack(">i", x))
 
 
+MAX_DEPTH = 64   # nesting the reader follows; the trees of a proof directory are at most ~6 deep
+
+
+def _skip_subtrees(buf, pos: int, count: int) -> int:
+    """Offset one past `count` consecutive subtrees starting at `pos`.  Iterative (an explicit stack of sibling
+    counters, no recursion), so a crafted file of thousands of nested node headers is an EIOException -- a
+    malformed proof the caller rejects (hvzk/PoSBasicTW.java:794-815) -- not a RecursionError; arrays of
+    equal-width leaves, the bulk of every proof file, are skipped arithmetically."""
+    n = len(buf)
+    stack = [count]
+    while stack:
+        if stack[-1] == 0:
+            stack.pop()
+            continue
+        stack[-1] -= 1
+        if pos + 5 > n:
+            raise EIOException("truncated header")
+        kind, cnt = struct.unpack_from(">BI", buf, pos)
+        pos += 5
+        if kind == LEAF:
+            if pos + cnt > n:
+                raise EIOException("truncated leaf")
+            pos += cnt
+        elif kind == NODE:
+            if cnt == 0:
+                continue
+            end = _uniform_leaves_end(buf, pos, cnt)
+            if end:
+                pos = end
+                continue
+            if len(stack) >= MAX_DEPTH:
+                raise EIOException("byte tree nested deeper than %d levels" % MAX_DEPTH)
+            stack.append(cnt)
+        else:
+            raise EIOException("bad tag %d" % kind)
+    return pos
+
+
+def _uniform_leaves_end(buf, pos: int, cnt: int) -> int:
+    """If the `cnt` children at `pos` are leaves of one width, the offset past them; else 0."""
+    n = len(buf)
+    if pos + 5 > n or buf[pos] != LEAF:
+        return 0
+    w = struct.unpack_from(">I", buf, pos + 1)[0]
+    end = pos + cnt * (5 + w)
+    if end > n:
+        return 0
+    if cnt > 1:
+        m = np.frombuffer(buf[pos:end], dtype=np.uint8).reshape(cnt, 5 + w)
+        hdr = np.frombuffer(struct.pack(">BI", LEAF, w), dtype=np.uint8)
+        if not (m[:, :5] == hdr).all():
+            return 0
+    return end
+
+
 class ByteTreeReader:
     """Sequential reader over a serialised tree (ByteTreeReader): `getNextChild`, `read`."""
 
@@ -244,10 +299,7 @@ class ByteTreeReader:
         """Offset one past this subtree."""
         if self.kind == LEAF:
             return self.start + 5 + self.count
-        pos = self.pos
-        for _ in range(self.count - self.read_children):
-            pos = ByteTreeReader(self.buf, pos).end_fast()
-        return pos
+        return _skip_subtrees(self.buf, self.pos, self.count - self.read_children)
 
     def getNextChild(self) -> "ByteTreeReader":
         if self.kind != NODE or self.read_children >= self.count:
@@ -258,17 +310,6 @@ class ByteTreeReader:
         return child
 
     def end_fast(self) -> int:
-        # arrays of equal-width leaves are the common case: skip them arithmetically
-        if self.kind == NODE and self.count and self.read_children == 0:
-            first = ByteTreeReader(self.buf, self.pos)
-            if first.kind == LEAF:
-                w = first.count
-                end = self.pos + self.count * (5 + w)
-                if end <= len(self.buf):
-                    m = np.frombuffer(self.buf[self.pos:end], dtype=np.uint8).reshape(self.count, 5 + w)
-                    hdr = np.frombuffer(struct.pack(">BI", LEAF, w), dtype=np.uint8)
-                    if (m[:, :5] == hdr).all():
-                        return end
         return self.end()
 
     def readBooleans(self, size: int) -> np.ndarray:

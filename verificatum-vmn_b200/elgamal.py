@@ -142,8 +142,13 @@ class DistrElGamalSessionBasic:
         return ByteTreeContainer(self.yp[self.j].toByteTree(), self.Bp[self.j].toByteTree())
 
     # :549-565
-    def setCommitment(self, l: int, commitmentReader: ByteTreeReader) -> None:
+    def setCommitment(self, l: int, commitmentReader) -> None:
+        """`commitmentReader`: a ByteTreeReader, or the raw bytes of the file -- the reader's constructor parses
+        the first header, so a truncated or empty file must fail INSIDE the handler below (verdicts[l] = false,
+        trivial values substituted, the combined check still runs: :553-566)."""
         try:
+            if not isinstance(commitmentReader, ByteTreeReader):
+                commitmentReader = ByteTreeReader(commitmentReader)
             self.yp[l] = self.g.getPGroup().toElement(commitmentReader.getNextChild())
             self.Bp[l] = self.A.getPGroup().toElement(commitmentReader.getNextChild())
         except (EIOException, ArithmFormatException):
@@ -164,9 +169,11 @@ class DistrElGamalSessionBasic:
         return self.k_x[self.j].toByteTree()
 
     # :606-614
-    def setReply(self, l: int, replyReader: ByteTreeReader) -> None:
+    def setReply(self, l: int, replyReader) -> None:
         pRing = self.g.getPGroup().getPRing()
         try:
+            if not isinstance(replyReader, ByteTreeReader):
+                replyReader = ByteTreeReader(replyReader)
             self.k_x[l] = pRing.toElement(replyReader)
         except (EIOException, ArithmFormatException):
             self.k_x[l] = pRing.getZERO()

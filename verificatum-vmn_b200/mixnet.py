@@ -91,8 +91,20 @@ class SessionParams:
     rohash: str = "SHA-256"
     prghash: str = "SHA-256"
     version: str = "3.1.0"
-    rosid: str = "vmx.session"
+    sid: str = "vmx"              # session identifier of the protocol info file
+    auxsid: str = "default"       # auxiliary session identifier of this execution (the `auxsid` file of a proof)
     pGroupString: str = ""
+
+    @property
+    def rosid(self) -> str:
+        """mixnet/MixNetElGamalVerifyFiatShamirSession.java:160: sid + "." + auxsid goes into the global prefix."""
+        return self.sid + "." + self.auxsid
+
+
+def validateSid(sid: str) -> bool:
+    """[VCR-mem] Protocol.validateSid: a non-empty string of letters, digits, underscores and spaces."""
+    import re
+    return re.fullmatch(r"[A-Za-z0-9_ ]{1,1024}", sid) is not None
 
 
 @dataclass

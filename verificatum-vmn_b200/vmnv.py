@@ -18,6 +18,7 @@ process, as the reference's own demo does (Demo.java:282-290).
 """
 from __future__ import annotations
 
+import dataclasses
 import os
 from typing import Dict, List, Optional, Sequence
 
@@ -26,7 +27,7 @@ from .arithm import ArithmFormatException, PFieldElement
 from .crypto import PRGHeuristic
 from .eio import ByteTreeContainer, ByteTreeLeaf, ByteTreeReader, EIOException, booleanArrayToByteTree
 from .hvzk import _to_positive, node_header
-from .mixnet import SessionParams, ShuffleProof, ShufflerSession, getCiphPGroup
+from .mixnet import SessionParams, ShuffleProof, ShufflerSession, getCiphPGroup, validateSid
 
 
 class VerificationError(RuntimeError):
@@ -99,7 +100,9 @@ class MixNetElGamal:
     """Keys + mixing + decryption of one list of ciphertexts; everything published goes to `self.nizkp`."""
 
     def __init__(self, pGroup, params: SessionParams, k: int, threshold: int, randomSource, width: int = 1,
-                 auxsid: str = "default"):
+                 auxsid: Optional[str] = None):
+        if auxsid is not None:
+            params = dataclasses.replace(params, auxsid=auxsid)
         if width != 1:
             raise NotImplementedError("the in-process mix driver handles width 1 (the array classes handle any width)")
         self.pGroup, self.params, self.k, self.threshold, self.width = pGroup, params, k, threshold, width
@@ -121,7 +124,7 @@ class MixNetElGamal:
         self.nizkp = ProofDirectory()
         self.nizkp["version"] = params.version.encode()
         self.nizkp["type"] = b"mixing"
-        self.nizkp["auxsid"] = auxsid.encode()
+        self.nizkp["auxsid"] = params.auxsid.encode()
         self.nizkp["width"] = str(width).encode()
         self.nizkp["FullPublicKey.bt"] = self.fullPublicKey.toByteTree().to_bytes()
         self.nizkp["proofs/PolynomialInExponent.bt"] = \
@@ -176,7 +179,7 @@ class MixNetElGamal:
         # every party reads the others' commitments; the challenge binds all of them
         E1 = parties[1]
         for l in range(2, k + 1):
-            E1.setCommitment(l, ByteTreeReader(self.nizkp[ProofDirectory.DFCfile(l)]))
+            E1.setCommitment(l, self.nizkp[ProofDirectory.DFCfile(l)])
         challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), E1.getCommitment())
         v = _to_positive(challenger.challenge(challengeData, p.vbitlenro, p.rbitlen))
         for l in range(1, k + 1):
@@ -211,8 +214,10 @@ class MixNetElGamalVerifyFiatShamirSession:
     pre-computation (verify:1318-1668).  `verify` returns a report; conditions under which the reference stops
     with an error raise VerificationError."""
 
-    def __init__(self, pGroup, params: SessionParams, k: int, threshold: int):
+    def __init__(self, pGroup, params: SessionParams, k: int, threshold: int, expectedAuxsid: Optional[str] = None):
+        """`expectedAuxsid`: the `-auxsid` option of vmnv; None accepts whatever the proof directory names."""
         self.pGroup, self.params, self.k, self.threshold = pGroup, params, k, threshold
+        self.expectedAuxsid = expectedAuxsid
         self.report: Dict[str, object] = {}
 
     def _file(self, nizkp: ProofDirectory, name: str) -> bytes:
@@ -230,6 +235,10 @@ class MixNetElGamalVerifyFiatShamirSession:
         self._spec = None
         try:
             return self._verify(nizkp)
+        except (EIOException, ArithmFormatException, ValueError, UnicodeDecodeError) as e:
+            # a malformed file outside the places where the reference substitutes trivial values is fail-stop
+            # (mixnet/MixNetElGamalVerifyFiatShamirSession.java: `failStop`), never a stray parser exception
+            raise VerificationError("Malformed proof directory: %s" % e)
         finally:
             if self._spec is not None:   # a fail-stop condition was met while the speculative hash was running
                 self._spec.abandon()
@@ -242,6 +251,14 @@ class MixNetElGamalVerifyFiatShamirSession:
             raise VerificationError("Mismatching versions!")
         if self._file(nizkp, "type").decode() != "mixing":
             raise VerificationError("Unsupported proof type")
+        # determineAuxsid :369-395: the identifier is read from the proof, validated, compared with the expected
+        # one if there is one, and enters the global prefix of every random-oracle call (setGlobalPrefix :158-189)
+        auxsid = self._file(nizkp, "auxsid").decode("ascii", errors="replace")
+        if not validateSid(auxsid):
+            raise VerificationError("Can not read auxsid from file!")
+        if self.expectedAuxsid is not None and auxsid != self.expectedAuxsid:
+            raise VerificationError("The given auxiliary session identifier does not match the one in the proof!")
+        p = dataclasses.replace(p, auxsid=auxsid)
         width = int(self._file(nizkp, "width").decode())
         if width != 1:
             raise VerificationError("Unsupported width")
@@ -353,11 +370,11 @@ class MixNetElGamalVerifyFiatShamirSession:
         basic.batchInput()
         basic.batchCombined()
         for l in range(1, k + 1):
-            basic.setCommitment(l, ByteTreeReader(self._file(nizkp, ProofDirectory.DFCfile(l))))
+            basic.setCommitment(l, self._file(nizkp, ProofDirectory.DFCfile(l)))
         challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), basic.getCommitment())
         v = _to_positive(challenger.challenge(challengeData, p.vbitlenro, p.rbitlen))
         for l in range(1, k + 1):
-            basic.setReply(l, ByteTreeReader(self._file(nizkp, ProofDirectory.DFRfile(l))))
+            basic.setReply(l, self._file(nizkp, ProofDirectory.DFRfile(l)))
         basic.combine(correct)
         ok = basic.verifyCombined(v)
         basic.free()
