@@ -83,6 +83,9 @@ def main():
             rperm=e.permute(pi), permi=X.permute(pi.inv()), shift=X.shiftPush(el), rshift=e.shiftPush(sc),
             prods=small.prods(), reclin=x_rl, radd=e.add(f), rmul=e.mul(f), rmuladd=e.mulAdd(sc, f),
             cols=Gx.expProd([X, Y], [3, -2], 2),
+            extract=X.extract([i % 3 != 1 for i in range(n)]), extract_none=X.extract([False] * n),
+            extract_one=X.extract([i == n - 1 for i in range(n)]),
+            rng=X.copyOfRange(n // 3, n - n // 4), rrng=e.copyOfRange(min(1, n - 1), n), full=X.copyOfRange(0, n),
             scalars=(X.expProd(small).value, X.prod().value, e.innerProduct(f).value, e.sum().value, small.prod().value,
                      d_rl.value, X.get(0).value, X.get(n - 1).value, e.get(n // 2).value, f.bitLength(),
                      X.equals(X), X.equals(Y), A.expProdMany([X, Y], f)[1].value))
@@ -177,6 +180,40 @@ def main():
 
     f1, f2 = fs(G1), fs(GS)
     assert f1[1:] == (True, True, False, True) and f1 == f2, "sharded shuffle session differs on rank %d" % rank
+
+    # ---- pre-computation, shrink and commitment-consistent shuffle on shards (BASELINE.json config 4's protocol):
+    # extract / copyOfRange move elements between shards (mixnet/PermutationCommitment.java:390-471)
+    def committed(Gx):
+        import dataclasses
+        mix = importlib.import_module("verificatum-vmn_b200.mixnet")
+        R = Gx.getPRing()
+        r0 = rs("cs/setup")
+        y = Gx.getg().exp(R.randomElement(r0, 100))
+        pk = A.PPGroup(Gx, 2).product(Gx.getg(), y)
+        maxciph = n + 5
+        w = mix.demoCiphertexts(pk, n, r0)
+        params = mix.SessionParams(pGroupString="par-committed")
+        prover = mix.ShufflerSession(Gx, pk, params, rs("cs/prover"))
+        cs = mix.CommittedShuffler(prover, 1, maxciph)
+        pub = cs.precomp()
+        keep = cs.shrink(n)
+        proof, out = cs.shuffle(w, keep_output=True)
+        verifier = mix.ShufflerSession(Gx, pk, params, None)
+        gens = verifier.deriveGenerators(maxciph)
+        pcv = mix.PermutationCommitment(verifier, gens)
+        okc = pcv.verify(*pub)
+        keep2 = pcv.shrink(n, keep)
+        ok, out2 = mix.verifyCommittedShuffle(verifier, 1, gens.copyOfRange(0, n), pcv.commitment, w, proof)
+        raw = bytearray(proof.reply)
+        raw[-2] ^= 8
+        rej, _ = mix.verifyCommittedShuffle(verifier, 1, gens.copyOfRange(0, n), pcv.commitment, w,
+                                            dataclasses.replace(proof, reply=bytes(raw)))
+        return tuple(bytes(b) for b in pub), bytes(keep), dataclasses.astuple(proof), okc, bytes(keep2), ok, \
+            out2.equals(out), rej
+
+    c1, c2 = committed(G1), committed(GS)
+    assert c1[3] is True and c1[5] is True and c1[6] is True and c1[7] is False, c1[3:]
+    assert c1 == c2, "sharded committed shuffle differs from the single-process one on rank %d" % rank
 
     # ---- a whole 3-party mix and its vmnv-style verification on shards
     def whole_mix(Gx):

@@ -41,3 +41,15 @@ G.toElementArray(n, m, check_membership=True).free(); G.sync(); t2 = time.time()
 timed("import no check", lambda: G.toElementArray(n, m, check_membership=False).free())
 timed("import + Jacobi membership", lambda: G.toElementArray(n, m, check_membership=True).free())
 print("host wall: import %.1f ms, import+membership %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))
+# dedicated squaring against the multiplication: `iters` chained operations per element
+import ctypes as C
+eq, ms, ms2 = C.c_int(), C.c_float(), C.c_float()
+iters = 64
+vmx._native.check(G._lib.vmx_selftest_sqr(X.h, iters, C.byref(eq), C.byref(ms)))
+vmx._native.check(G._lib.vmx_selftest_sqr(X.h, iters, C.byref(eq), C.byref(ms)))
+vmx._native.check(G._lib.vmx_bench_modmul(G.ctx, n, iters, C.byref(ms2)))
+vmx._native.check(G._lib.vmx_bench_modmul(G.ctx, n, iters, C.byref(ms2)))
+macs = 2 * (bits // 32) ** 2 + bits // 32
+print("mont_sqr  x%d: %8.3f ms (equal=%d)  %5.1f%% of IMAD peak counted as modmuls" % (iters, ms.value, eq.value, 100 * n * iters * macs / (ms.value * 1e-3) / 9.26e12))
+print("mont_mul  x%d: %8.3f ms             %5.1f%% of IMAD peak" % (iters, ms2.value, 100 * n * iters * macs / (ms2.value * 1e-3) / 9.26e12))
+print("sqr / mul time = %.3f" % (ms.value / ms2.value))

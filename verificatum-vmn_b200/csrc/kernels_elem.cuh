@@ -237,7 +237,12 @@ VMX_KERNEL(N) k_sqr_iter(const uint32_t* __restrict__ a_, size_t acap, uint32_t*
 }
 
 // ------------------------------------------------------------------ fixed-base exponentiation
-// table: nwin * 2^w entries, entry (k, d) = base^(d * 2^(w*k)) in Montgomery form (d = 0 -> one).
+// table: nwin * 2^w entries, entry (k, d) = base^(d * 2^(w*k)) in Montgomery form (d = 0 -> one), stored
+// ENTRY-MAJOR: the N limbs of entry e are the N consecutive words at table + e * N (a limb-major "array" of
+// capacity 1, which is how load_elem / GlobalLoader are pointed at it).  A thread walks its entry 8 bytes per CIOS
+// trip, so the 384 bytes of a 3072-bit entry are three 128-byte lines read once each (L1 keeps the line for the
+// 16 trips that use it); in the limb-major layout of the arrays the same entry is 24 half-used 32-byte sectors in
+// 24 planes (2.07x the algorithmic DRAM bytes, profiles/r02_ncu_exp_fixed.txt, and 24 pages per entry).
 // Work item = (element i, window range part): part p of `parts` multiplies windows
 // [p*nwin/parts, (p+1)*nwin/parts) and writes to out element p*n + i (parts > 1 -> combined later).
 template <int N>
@@ -252,11 +257,11 @@ VMX_KERNEL(N) k_exp_fixed(const uint32_t* __restrict__ table, size_t tcap, int w
   uint32_t a[N];
   {
     const uint32_t d = window_bits<N>(e_, ecap, i, k0 * w, w);
-    load_elem<N>(a, table, tcap, ((size_t)k0 << w) + d);
+    load_elem<N>(a, table + (((size_t)k0 << w) + d) * N, 1, 0);
   }
   uint32_t dn = (k0 + 1 < k1) ? window_bits<N>(e_, ecap, i, (k0 + 1) * w, w) : 0;
   for (int k = k0 + 1; k < k1; k++) {
-    const GlobalLoader B(table, tcap, ((size_t)k << w) + dn);
+    const GlobalLoader B(table + (((size_t)k << w) + dn) * N, 1, 0);
     if (k + 1 < k1) dn = window_bits<N>(e_, ecap, i, (k + 1) * w, w);
     mont_mul<N>(a, B, M);
   }
@@ -306,7 +311,7 @@ VMX_KERNEL(N) k_table_level(uint32_t* __restrict__ table, size_t tcap, int w, in
   const size_t dst = ((size_t)k << w) + per + r;
   if (m >= qlen) {  // beyond the exponent range: never addressed, keep defined
     load_elem<N>(a, one, 4, 1);
-    store_elem<N>(a, table, tcap, dst);
+    store_elem<N>(a, table + dst * N, 1, 0);
     return;
   }
   if (r == 0) {
@@ -314,18 +319,19 @@ VMX_KERNEL(N) k_table_level(uint32_t* __restrict__ table, size_t tcap, int w, in
     if (j == 0) {  // also write entry 0 = one
       uint32_t o[N];
       load_elem<N>(o, one, 4, 1);
-      store_elem<N>(o, table, tcap, (size_t)k << w);
+      store_elem<N>(o, table + ((size_t)k << w) * N, 1, 0);
     }
   } else {
-    load_elem<N>(a, table, tcap, ((size_t)k << w) + r);
+    load_elem<N>(a, table + (((size_t)k << w) + r) * N, 1, 0);
     mont_mul<N>(a, GlobalLoader(Q, qcap, m), M);
   }
-  store_elem<N>(a, table, tcap, dst);
+  store_elem<N>(a, table + dst * N, 1, 0);
 }
 
 // ------------------------------------------------------------------ variable-base exponentiation
 // out[i] = a[i]^{e[i]} (escalar = 0) or a[i]^{e[0]} (escalar = 1); fixed w-bit windows, top-down.
-// tab: scratch for per-thread tables, (2^w) * n elements, entry d of element i at d*n + i.
+// tab: scratch for per-thread tables, (2^w) * n entries, entry-major as the fixed-base tables: entry d of element i
+// is the N words at tab + ((i << w) + d) * N.  Written once (two 16-byte stores fill a sector), read at random d.
 template <int N>
 VMX_KERNEL(N) k_exp_var(const uint32_t* __restrict__ a_, size_t acap, const uint32_t* __restrict__ e_, size_t ecap,
                         int escalar, int ebits, int w, size_t n, uint32_t* __restrict__ tab, size_t tabcap,
@@ -340,23 +346,23 @@ VMX_KERNEL(N) k_exp_var(const uint32_t* __restrict__ a_, size_t acap, const uint
   uint32_t a[N];
   // table: tab[0] = 1, tab[1] = base, tab[d] = tab[d-1] * base
   load_elem<N>(a, one, 4, 1);
-  store_elem<N>(a, tab, tabcap, i);
+  store_elem<N>(a, tab + ((size_t)i << w) * N, 1, 0);
   load_elem<N>(a, a_, acap, i);
-  store_elem<N>(a, tab, tabcap, n + i);
+  store_elem<N>(a, tab + (((size_t)i << w) + 1) * N, 1, 0);
   const GlobalLoader Bse(a_, acap, i);
   for (int d = 2; d < (1 << w); d++) {
     mont_mul<N>(a, Bse, M);
-    store_elem<N>(a, tab, tabcap, (size_t)d * n + i);
+    store_elem<N>(a, tab + (((size_t)i << w) + d) * N, 1, 0);
   }
   const int nwin = (ebits + w - 1) / w;
   {
     const uint32_t d = window_bits<N>(e_, ecap, ei, (nwin - 1) * w, w);
-    load_elem<N>(a, tab, tabcap, (size_t)d * n + i);
+    load_elem<N>(a, tab + (((size_t)i << w) + d) * N, 1, 0);
   }
   for (int k = nwin - 2; k >= 0; k--) {
     const uint32_t d = window_bits<N>(e_, ecap, ei, k * w, w);
     for (int s = 0; s < w; s++) mont_sqr<N>(a, sc, ss, M);
-    mont_mul<N>(a, GlobalLoader(tab, tabcap, (size_t)d * n + i), M);
+    mont_mul<N>(a, GlobalLoader(tab + (((size_t)i << w) + d) * N, 1, 0), M);
   }
   store_elem<N>(a, out, ocap, i);
 }
@@ -364,7 +370,7 @@ VMX_KERNEL(N) k_exp_var(const uint32_t* __restrict__ a_, size_t acap, const uint
 // out[i] = a[i]^{x} * b[i]^{y[i]}: simultaneous exponentiation, one chain of squarings for both bases (the
 // verifier's B_i^v * B_{i-1}^{-k_E,i}, hvzk/PoSBasicTW.java:1028-1035, costs max(|v|, |k_E|) squarings instead of
 // |v| + |k_E|).  x is element 0 of x_ (one exponent for all), y per element; both use w-bit windows at the same
-// positions.  tabA / tabB: 2^w entries per element each, entry d of element i at d*n + i.
+// positions.  tabA / tabB: 2^w entries per element each, entry-major (entry d of element i at ((i << w) + d) * N).
 template <int N>
 VMX_KERNEL(N) k_exp_var2(const uint32_t* __restrict__ a_, size_t acap, const uint32_t* __restrict__ x_, size_t xcap,
                          int xbits, const uint32_t* __restrict__ b_, size_t bcap, const uint32_t* __restrict__ y_,
@@ -382,13 +388,13 @@ VMX_KERNEL(N) k_exp_var2(const uint32_t* __restrict__ a_, size_t acap, const uin
     const size_t scap = side ? bcap : acap;
     uint32_t* tab = side ? tabB : tabA;
     load_elem<N>(a, one, 4, 1);
-    store_elem<N>(a, tab, tabcap, i);
+    store_elem<N>(a, tab + ((size_t)i << w) * N, 1, 0);
     load_elem<N>(a, src, scap, i);
-    store_elem<N>(a, tab, tabcap, n + i);
+    store_elem<N>(a, tab + (((size_t)i << w) + 1) * N, 1, 0);
     const GlobalLoader Bse(src, scap, i);
     for (int d = 2; d < (1 << w); d++) {
       mont_mul<N>(a, Bse, M);
-      store_elem<N>(a, tab, tabcap, (size_t)d * n + i);
+      store_elem<N>(a, tab + (((size_t)i << w) + d) * N, 1, 0);
     }
   }
   const int nwy = (ybits + w - 1) / w, nwx = (xbits + w - 1) / w;
@@ -396,14 +402,14 @@ VMX_KERNEL(N) k_exp_var2(const uint32_t* __restrict__ a_, size_t acap, const uin
   for (int k = nwin - 1; k >= 0; k--) {
     const uint32_t dy = window_bits<N>(y_, ycap, i, k * w, w);
     if (k == nwin - 1) {
-      load_elem<N>(a, tabB, tabcap, (size_t)dy * n + i);
+      load_elem<N>(a, tabB + (((size_t)i << w) + dy) * N, 1, 0);
     } else {
       for (int s = 0; s < w; s++) mont_sqr<N>(a, sc, ss, M);
-      mont_mul<N>(a, GlobalLoader(tabB, tabcap, (size_t)dy * n + i), M);
+      mont_mul<N>(a, GlobalLoader(tabB + (((size_t)i << w) + dy) * N, 1, 0), M);
     }
     if (k < nwx) {  // uniform over the grid: x is one exponent
       const uint32_t dx = window_bits<N>(x_, xcap, 0, k * w, w);
-      if (dx) mont_mul<N>(a, GlobalLoader(tabA, tabcap, (size_t)dx * n + i), M);
+      if (dx) mont_mul<N>(a, GlobalLoader(tabA + (((size_t)i << w) + dx) * N, 1, 0), M);
     }
   }
   store_elem<N>(a, out, ocap, i);

@@ -390,8 +390,9 @@ static size_t wave_threads(const vmx_ctx* c) {
 // Window width of a fixed-base table for arrays of n exponents.  A table is built once per base and serves
 // every later array (the bases of a mix-net session are g, h0 and the public key components: 8 fixed-base
 // arrays per shuffle, mixnet/ShufflerElGamalSession.java:407, hvzk/PoSBasicTW.java:447,606-646,1030), so
-// the 2^w entries per window are weighed against kReuse arrays of n products.  Memory bound: 10 GB per
-// table (w = 17 at 3072 bits: 181 windows x 131,072 x 384 B = 9.1 GB of the 180 GB).
+// the 2^w entries per window are weighed against kReuse arrays of n products.  Memory bound per table:
+// ctx->table_max_bytes (20 GB: w = 18 at 3072 bits is 171 windows x 262,144 x 384 B = 17.2 GB of the 180 GB; four
+// long-lived bases); all cached tables together stay below ctx->table_budget (least recently used evicted).
 constexpr double kFixedReuse = 8.0;
 static double fixed_cost(int w, size_t n, int ebits) {
   const double nwin = (ebits + w - 1) / w;
@@ -404,7 +405,7 @@ static int choose_fixed_window(const vmx_ctx* c, size_t n, int ebits) {
   for (int w = 4; w <= 18; w++) {
     const double nwin = (ebits + w - 1) / w;
     const double entries = nwin * (double)(1u << w);
-    if (entries * c->nl * 4 > 10e9) break;
+    if (entries * c->nl * 4 > (double)c->table_max_bytes) break;
     const double cost = fixed_cost(w, n, ebits);
     if (cost < best) { best = cost; bw = w; }
   }
@@ -461,8 +462,13 @@ static int get_table(vmx_ctx* c, const uint8_t* base_be, size_t n, FixedTable* o
     const double have = ec ? ec_fixed_cost(it->second.w, n, ebits) : fixed_cost(it->second.w, n, ebits);
     const double want = ec ? ec_fixed_cost(wbest, n, ebits) : fixed_cost(wbest, n, ebits);
     // a wider table than this array size asks for is never slower to USE: keep it; rebuild only to widen
-    if (it->second.w >= wbest || have <= 1.3 * want) { *out = it->second; return VMX_OK; }
+    if (it->second.w >= wbest || have <= 1.3 * want) {
+      it->second.last_use = ++c->table_clock;
+      *out = it->second;
+      return VMX_OK;
+    }
     cudaFreeAsync(it->second.d, c->stream);
+    c->table_bytes -= it->second.bytes;
     c->tables.erase(it);
   }
   ElemBuf base;
@@ -470,7 +476,21 @@ static int get_table(vmx_ctx* c, const uint8_t* base_be, size_t n, FixedTable* o
   FixedTable T;
   if (ec) VMX_TRY(ec_build_table(c, base.d(), base.cap, wbest, T));
   else VMX_DISPATCH(c->nl, VMX_TRY(build_table<N>(c, base.d(), base.cap, wbest, T)));
+  T.bytes = T.cap * (size_t)c->gl * 4;
+  T.last_use = ++c->table_clock;
   c->tables[key] = T;
+  c->table_bytes += T.bytes;
+  // a long-lived context that meets many bases (a key per election, ad-hoc g.exp(array) bases) must not grow
+  // without bound: evict the least recently used tables (stream-ordered free: kernels already queued finish first)
+  while (c->table_bytes > c->table_budget && c->tables.size() > 1) {
+    auto victim = c->tables.end();
+    for (auto jt = c->tables.begin(); jt != c->tables.end(); ++jt)
+      if (jt->first != key && (victim == c->tables.end() || jt->second.last_use < victim->second.last_use)) victim = jt;
+    if (victim == c->tables.end()) break;
+    cudaFreeAsync(victim->second.d, c->stream);
+    c->table_bytes -= victim->second.bytes;
+    c->tables.erase(victim);
+  }
   *out = T;
   return VMX_OK;
 }
@@ -1237,7 +1257,9 @@ int vmx_ctx_set_tuning(vmx_ctx* c, const char* key, long long value) {
   else if (k == "mexp_window") {
     if (value != 0 && (value % kSubDigit != 0 || value > 16)) { set_error("mexp_window must be 0, 4, 8, 12 or 16"); return VMX_EARG; }
     c->mexp_window = (int)value;
-  } else if (k == "fixed_window") return vmx_ctx_set_fixed_window(c, (int)value);
+  } else if (k == "table_max_bytes") c->table_max_bytes = (size_t)value;
+  else if (k == "table_budget") c->table_budget = (size_t)value;
+  else if (k == "fixed_window") return vmx_ctx_set_fixed_window(c, (int)value);
   else { set_error("unknown tuning key %s", key); return VMX_EARG; }
   return VMX_OK;
 }

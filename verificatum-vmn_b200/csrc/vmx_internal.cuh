@@ -47,6 +47,8 @@ struct FixedTable {
   uint32_t* d = nullptr;
   size_t cap = 0;
   int w = 0, nwin = 0;
+  size_t bytes = 0;       // device memory of the table
+  uint64_t last_use = 0;  // tick of the context's table clock (least recently used tables are evicted first)
 };
 
 struct Modulus {
@@ -87,6 +89,10 @@ struct vmx_ctx {
   size_t coop_max = 8192;                         // arrays up to this size use the warp-per-element kernels
   size_t var_chunk = 0;                           // elements per launch of k_exp_var / k_exp_var2 (0 = from memory)
   int mexp_window = 0;                            // Pippenger window c (0 = choose from n and the exponent length)
+  size_t table_max_bytes = (size_t)20e9;          // largest single fixed-base table (w = 18 at 3072 bits: 17.2 GB)
+  size_t table_budget = (size_t)100e9;            // all cached tables together; beyond it the least recently used go
+  size_t table_bytes = 0;                         // currently cached
+  uint64_t table_clock = 0;
   int* d_flag = nullptr;                          // device scratch: 4 ints
   int* h_flag = nullptr;                          // pinned scratch: 4 ints
   std::atomic<uint64_t> launches{0}, modmuls{0};

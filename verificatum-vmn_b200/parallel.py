@@ -351,9 +351,12 @@ class ShardedRingArray(PRingElementArray):
         return PRingElementArray.shiftPush(self, PFieldElement(self.ring, first))
 
     def copyOfRange(self, a: int, b: int):
-        if (a, b) != (0, self.gsize):
-            raise NotImplementedError("sharded copyOfRange supports the full range only")
-        return PRingElementArray.copyOfRange(self, 0, self.local_size())
+        if (a, b) == (0, self.gsize):
+            return PRingElementArray.copyOfRange(self, 0, self.local_size())
+        return _sharded_select(self, np.arange(a, b, dtype=np.int64), ring=True)
+
+    def extract(self, keep: Sequence[bool]):
+        return _sharded_select(self, _kept_indices(keep, self.gsize), ring=True)
 
     def get(self, i: int) -> PFieldElement:
         own = self.lo <= i < self.hi
@@ -585,12 +588,14 @@ class ShardedGroupArray(PGroupElementArray):
         return PGroupElementArray.shiftPush(self, PGroupElement(self.group, first))
 
     def extract(self, keep: Sequence[bool]):
-        raise NotImplementedError("sharded extract: run PermutationCommitment.shrink on one GPU")
+        """mixnet/PermutationCommitment.java:462-468 (`commitment.extract(keepList)`): the kept elements in order;
+        the result is sharded over its own (smaller) index range, so kept elements move between ranks."""
+        return _sharded_select(self, _kept_indices(keep, self.gsize), ring=False)
 
     def copyOfRange(self, a: int, b: int):
-        if (a, b) != (0, self.gsize):
-            raise NotImplementedError("sharded copyOfRange supports the full range only")
-        return PGroupElementArray.copyOfRange(self, 0, self.local_size())
+        if (a, b) == (0, self.gsize):
+            return PGroupElementArray.copyOfRange(self, 0, self.local_size())
+        return _sharded_select(self, np.arange(a, b, dtype=np.int64), ring=False)
 
     def get(self, i: int) -> PGroupElement:
         own = self.lo <= i < self.hi
@@ -676,6 +681,57 @@ def _sharded_permute(arr, pi: Permutation, ring: bool):
             recv.record_stream(torch.cuda.current_stream())
             send.record_stream(torch.cuda.current_stream())
     return arr._new(h)
+
+
+def _kept_indices(keep, size: int) -> np.ndarray:
+    flags = np.asarray(keep, dtype=bool)
+    if flags.shape[0] != size:
+        raise nat.VmxError(nat.VMX_ESIZE, "keep list of the wrong size")
+    return np.flatnonzero(flags).astype(np.int64)
+
+
+def _sharded_select(arr, src: np.ndarray, ring: bool):
+    """out[j] = a[src[j]] for an increasing list of GLOBAL source indices (extract, copyOfRange): stream
+    compaction across shards.  `src` is replicated host data (a keep list, a range), so every rank derives the
+    whole routing from it -- the "local compaction + exclusive scan of counts" of SURVEY.md section 8e without a
+    collective for the counts: rank r packs its selected elements in output order (the destination rank is
+    monotone in j), one all-to-all of element rows moves them, and the receiver scatters them to their slots of
+    the new, smaller index range."""
+    comm = arr.comm
+    lib = arr._lib
+    torch = comm.torch
+    ctx = arr.ring.group.ctx if ring else arr.group.ctx
+    nl = int(lib.vmx_ctx_ring_row_bytes(ctx) if ring else lib.vmx_ctx_row_bytes(ctx)) // 4
+    m = int(src.shape[0])
+    if m and (src[0] < 0 or src[-1] >= arr.gsize or (m > 1 and (np.diff(src) <= 0).any())):
+        raise nat.VmxError(nat.VMX_EARG, "selection out of range or not increasing")
+    ob = np.asarray(arr.bounds, dtype=np.int64)
+    nb = np.asarray(shard_bounds(m, comm.world), dtype=np.int64)
+    lo, hi = arr.lo, arr.hi
+    nlo, nhi = int(nb[comm.rank]), int(nb[comm.rank + 1])
+    j0, j1 = np.searchsorted(src, lo, side="left"), np.searchsorted(src, hi, side="left")   # outputs sourced here
+    mine_j = np.arange(j0, j1, dtype=np.int64)
+    order = np.ascontiguousarray((src[j0:j1] - lo).astype(np.uint32))                       # local rows, output order
+    dest_rank = np.searchsorted(nb[1:], mine_j, side="right")
+    send_counts = np.bincount(dest_rank, minlength=comm.world).astype(np.int64)
+    src_rank = np.searchsorted(ob[1:], src[nlo:nhi], side="right")                          # monotone in j as well
+    recv_counts = np.bincount(src_rank, minlength=comm.world).astype(np.int64)
+    nloc = nhi - nlo
+    dst_idx = np.arange(nloc, dtype=np.uint32)    # rows arrive by source rank, i.e. already in output order
+    pack = lib.vmx_rarr_pack_rows if ring else lib.vmx_garr_pack_rows
+    unpack = lib.vmx_rarr_unpack_rows if ring else lib.vmx_garr_unpack_rows
+    with comm.on_stream():
+        send = torch.empty((int(order.shape[0]), nl), dtype=torch.int32, device=comm.device)
+        if order.shape[0]:
+            nat.check(pack(arr.h, _ptr(order), int(order.shape[0]), C.c_void_p(send.data_ptr())))
+        recv = comm.exchange_rows(send, send_counts, recv_counts)
+        h = C.c_void_p()
+        nat.check(unpack(ctx, nloc, C.c_void_p(recv.data_ptr()) if nloc else None,
+                         _ptr(dst_idx) if nloc else None, nloc, C.byref(h)))
+        if comm.device.type == "cuda":
+            recv.record_stream(torch.cuda.current_stream())
+            send.record_stream(torch.cuda.current_stream())
+    return ShardedRingArray(arr.ring, h, m) if ring else ShardedGroupArray(arr.group, h, m)
 
 
 def make_curve_group(name: str, device: Optional[int], group=None) -> ShardedECqPGroup:
