@@ -133,7 +133,7 @@ class ShufflerSession:
         self.globalPrefix = globalPrefix(self.roHashfunction, params.version, params.rosid, params.rbitlen,
                                          params.vbitlenro, params.ebitlenro, "PRGHeuristic(%s)" % params.prghash,
                                          params.pGroupString, "HashfunctionHeuristic(%s)" % params.rohash)
-        self.challenger = ChallengerRO(self.roHashfunction, self.globalPrefix)
+        self.challenger = ChallengerRO(self.roHashfunction, self.globalPrefix, comm=getattr(pGroup, "comm", None))
         self.sid = sid
         self.generators = None
 

@@ -79,6 +79,23 @@ class Comm:
         self.bytes_exchanged += len(raw)
         return [raw[i * len(b):(i + 1) * len(b)] for i in range(self.world)]
 
+    def broadcast_bytes(self, b: Optional[bytes], nbytes: int, root: int = 0) -> bytes:
+        """`nbytes` bytes of the root rank to every rank (Fiat-Shamir digests: the root alone hashes)."""
+        torch = self.torch
+        if self.world == 1:
+            return bytes(b)
+        with self.on_stream():
+            if self.rank == root:
+                assert b is not None and len(b) == nbytes
+                t = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(self.device)
+            else:
+                t = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.dist.broadcast(t, self._global(root), group=self.group)
+            out = t.cpu().numpy().tobytes()
+        self.collectives += 1
+        self.bytes_exchanged += nbytes
+        return out
+
     def allgather_matrix(self, m: np.ndarray, bounds: Sequence[int]) -> np.ndarray:
         """Rows of all ranks, concatenated in rank order (ragged: bounds gives the row ranges)."""
         torch = self.torch
