@@ -515,10 +515,19 @@ def run_shuffle(args, env):
             verifier = mixnet.ShufflerSession(G, basic_pk, params, prg("e2ev%d" % i))
             ciphPGroup = mixnet.getCiphPGroup(G, width)
             w = ciphPGroup.toElementArray(n, vmx.eio.ByteTreeReader(memoryview(pinned.numpy()).toreadonly()))
-            with _span("e2e.shuffle"):
-                proof, _ = prover.shuffle(width, w, generators=generators)
-            with _span("e2e.verify"):
-                ok, out = verifier.verify(width, w, proof, generators=generators)
+            if args.offline_verify:
+                with _span("e2e.shuffle"):
+                    proof, _ = prover.shuffle(width, w, generators=generators)
+                with _span("e2e.verify"):
+                    ok, out = verifier.verify(width, w, proof, generators=generators)
+            else:
+                # the verifier follows the bulletin board, as the reference's mix-servers do (hvzk/PoSTW.java:195-245):
+                # it hashes each message as the prover publishes it, then verifies
+                ov = verifier.beginVerify(width, w, generators=generators)
+                with _span("e2e.shuffle"):
+                    proof, _ = prover.shuffle(width, w, generators=generators, publish=ov.publish)
+                with _span("e2e.verify"):
+                    ok, out = ov.finish(proof)
             if not ok:
                 raise SystemExit("bench e2e: verifier rejected an honest proof")
             out.free()
@@ -557,7 +566,10 @@ def run_shuffle(args, env):
         e2e = {"value": n / dt, "unit": "ciphertexts/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": k,
                "includes": "byte-tree decode/encode, H2D/D2H, Fiat-Shamir SHA-256 on the host",
-               "membership_check_on_import": bool(G.membership_check)}
+               "membership_check_on_import": bool(G.membership_check),
+               "verifier": "offline: verify(proof) after shuffle() returned" if args.offline_verify else
+               "online: the verifier hashes each message as the prover publishes it (bulletin-board order), "
+               "verdict after the last message"}
         if hash0 is not None:
             hb = (crypto.hashed_bytes() - hash0) / k
             hs = (crypto.hashed_seconds() - hsec0) / k
@@ -671,6 +683,9 @@ def main():
     ap.add_argument("--group", default="modp", help="modp (RFC 3526 safe prime of --bits) or a curve name (P-256)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="ciphertexts in the CPU baseline sample (0 = auto)")
     ap.add_argument("--e2e-steps", type=int, default=5, help="end-to-end steps averaged (after one untimed)")
+    ap.add_argument("--offline-verify", action="store_true",
+                    help="end to end: verify only after the whole proof was returned (default: the verifier "
+                         "follows the messages as they are published)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the short side runs of BASELINE.json configs 3, 4, 5")

@@ -821,7 +821,12 @@ def _eval_in_exponent(G, coeffs, l):
     return acc
 
 
-def run_mix(G, params: Params, k: int, threshold: int, w, rs, auxsid=None):
+def wide_key(pk, width: int):
+    """elgamal/ProtocolElGamal.java:785-800: the basic key (g, y) as a key over width-omega ciphertexts."""
+    return pk if width == 1 else ((pk[0],) * width, (pk[1],) * width)
+
+
+def run_mix(G, params: Params, k: int, threshold: int, w, rs, auxsid=None, width: int = 1):
     """Returns (proof directory as dict name -> bytes, plaintext elements)."""
     if auxsid is not None:
         params = params.with_auxsid(auxsid)
@@ -830,7 +835,9 @@ def run_mix(G, params: Params, k: int, threshold: int, w, rs, auxsid=None):
     xs = {l: sum(a * pow(l, i, q) for i, a in enumerate(poly)) % q for l in range(1, k + 1)}
     coeffs = [G.op_exp(G.g, a) for a in poly]
     pk = (G.g, coeffs[0])
-    d = {"version": params.version.encode(), "type": b"mixing", "auxsid": params.auxsid.encode(), "width": b"1",
+    wpk = wide_key(pk, width)
+    d = {"version": params.version.encode(), "type": b"mixing", "auxsid": params.auxsid.encode(),
+         "width": str(width).encode(),
          "FullPublicKey.bt": ar.elem_tree(G, pk).to_bytes(),
          "proofs/PolynomialInExponent.bt": bt.node([ar.elem_tree(G, c) for c in coeffs]).to_bytes(),
          "Ciphertexts.bt": ar.array_tree(G, w).to_bytes(), "proofs/activethreshold": str(threshold).encode()}
@@ -838,7 +845,7 @@ def run_mix(G, params: Params, k: int, threshold: int, w, rs, auxsid=None):
     h = independent_generators(G, params.rohash, params.prefix(), "generators", n, params.rbitlen)
     inp = w
     for l in range(1, threshold + 1):
-        out, proof = shuffle_and_prove(G, params, pk, inp, h, _party_source(rs))
+        out, proof = shuffle_and_prove(G, params, wpk, inp, h, _party_source(rs))
         d["ShuffledCiphertexts.bt" if l == threshold else "proofs/Ciphertexts%02d.bt" % l] = proof["output"]
         d["proofs/PermutationCommitment%02d.bt" % l] = proof["permutationCommitment"]
         d["proofs/PoSCommitment%02d.bt" % l] = proof["commitment"]
@@ -881,22 +888,25 @@ class MixVerificationError(Exception):
     pass
 
 
-def verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_auxsid=None) -> dict:
+def verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_auxsid=None, expected_width=None) -> dict:
     """The verdicts of mixnet/MixNetElGamalVerifyFiatShamirSession.verify for a proof of type "mixing".  A file
     that is malformed where the reference does not substitute trivial values is fail-stop."""
     try:
-        return _verify_mix(G, params, k, threshold, d, expected_auxsid)
+        return _verify_mix(G, params, k, threshold, d, expected_auxsid, expected_width)
     except (bt.EIOError, ar.FormatError, ValueError, IndexError, AttributeError, TypeError) as e:
         raise MixVerificationError("malformed proof directory: %s" % e)
 
 
-def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_auxsid=None) -> dict:
+def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_auxsid=None, expected_width=None) -> dict:
     def need(name):
         if name not in d:
             raise MixVerificationError("missing " + name)
         return d[name]
-    if need("version").decode() != params.version or need("type") != b"mixing" or need("width") != b"1":
+    if need("version").decode() != params.version or need("type") != b"mixing":
         raise MixVerificationError("header")
+    width = int(need("width").decode())
+    if width < 1 or (expected_width is not None and width != expected_width):
+        raise MixVerificationError("width")
     # determineAuxsid (MixNetElGamalVerifyFiatShamirSession.java:369-395): read from the proof, validated, and part
     # of the global prefix (:160); [VCR-mem] Protocol.validateSid = letters, digits, underscores, spaces
     import re
@@ -922,7 +932,10 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
         raise MixVerificationError("active threshold")
     ct = bt.from_bytes(need("Ciphertexts.bt"))
     first = ct.children[0]
-    n = len(first.children[0].children) if hasattr(G, "coord_bytes") else len(first.children)
+    for _ in range((1 if width > 1 else 0) + (1 if hasattr(G, "coord_bytes") else 0)):
+        first = first.children[0]
+    n = len(first.children)
+    basic_pk, pk = pk, wide_key(pk, width)
     try:
         w = ar.parse_array(G, ct, n, pk)
     except (ar.FormatError, bt.EIOError):
@@ -954,7 +967,8 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
         raise MixVerificationError("too few correct decryption factors")
     u = inp[0]
     try:
-        f = {l: ar.parse_array(G, bt.from_bytes(need("proofs/DecryptionFactors%02d.bt" % l)), n) for l in range(1, k + 1)}
+        f = {l: ar.parse_array(G, bt.from_bytes(need("proofs/DecryptionFactors%02d.bt" % l)), n, pk[0] if width > 1 else None)
+             for l in range(1, k + 1)}
     except (ar.FormatError, bt.EIOError):
         raise MixVerificationError("decryption factors")
     combined = combine_decryption_factors(G, f, correct, k, threshold)
@@ -979,12 +993,12 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
         except bt.EIOError:
             V.set_reply(l, bt.node([]))
     V.combine(correct)
-    rep["decryption"] = V.verify_combined(pk[1], v)
+    rep["decryption"] = V.verify_combined(basic_pk[1], v)
     if not rep["decryption"]:
         raise MixVerificationError("combined proof of decryption")
     computed = ar.g_mul(G, inp[1], combined)
     try:
-        plain = ar.parse_array(G, bt.from_bytes(need("Plaintexts.bt")), n)
+        plain = ar.parse_array(G, bt.from_bytes(need("Plaintexts.bt")), n, pk[0] if width > 1 else None)
     except (ar.FormatError, bt.EIOError):
         raise MixVerificationError("plaintexts")
     rep["plaintexts"] = plain == computed

@@ -176,10 +176,19 @@ def main():
         raw = bytearray(proof.commitment)
         raw[len(raw) // 2] ^= 1
         rej, out3 = verifier.verify(1, w, dataclasses.replace(proof, commitment=bytes(raw)))
-        return dataclasses.astuple(proof), ok, out2.equals(out), rej, out3.equals(w)
+        # online: the verifier hashes the messages as they are published (the root rank alone hashes when sharded)
+        ov = verifier.beginVerify(1, w)
+        proof2, _ = mix.ShufflerSession(Gx, pk, params, rs("fs/prover")).shuffle(1, w, publish=ov.publish)
+        ok3, out4 = ov.finish(proof2)
+        ov = verifier.beginVerify(1, w)
+        proof3, _ = mix.ShufflerSession(Gx, pk, params, rs("fs/prover")).shuffle(1, w, publish=ov.publish)
+        rej3, _ = ov.finish(dataclasses.replace(proof3, reply=bytes(proof3.reply)[:-1] + b"\x00"))
+        same_proof = tuple(bytes(x) for x in dataclasses.astuple(proof2)) == tuple(bytes(x) for x in dataclasses.astuple(proof))
+        return dataclasses.astuple(proof), ok, out2.equals(out), rej, out3.equals(w), same_proof, ok3, out4.equals(out), rej3
 
     f1, f2 = fs(G1), fs(GS)
-    assert f1[1:] == (True, True, False, True) and f1 == f2, "sharded shuffle session differs on rank %d" % rank
+    assert f1[1:] == (True, True, False, True, True, True, True, False), f1[1:]
+    assert f1 == f2, "sharded shuffle session differs on rank %d" % rank
 
     # ---- pre-computation, shrink and commitment-consistent shuffle on shards (BASELINE.json config 4's protocol):
     # extract / copyOfRange move elements between shards (mixnet/PermutationCommitment.java:390-471)

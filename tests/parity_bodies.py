@@ -241,6 +241,34 @@ def transcript_parity(vmx, bits, n):
     verifier = ec.session(None)
     ok, out2 = verifier.verify(1, ec.w, proof, generators=h)
     assert ok and col_values(out2) == owp
+    # online verification (the verifier hashes each message as the prover publishes it): same transcript, same
+    # verdict; a message altered between the board and the final proof falls back to the offline order
+    prover2 = ec.session("prover")
+    ov = verifier.beginVerify(1, ec.w, generators=h)
+    proof2, _ = prover2.shuffle(1, ec.w, generators=h, publish=ov.publish)
+    assert dataclasses.astuple(proof2) == dataclasses.astuple(proof)
+    ok2, out3 = ov.finish(proof2)
+    assert ok2 and col_values(out3) == owp
+    ov = verifier.beginVerify(1, ec.w, generators=h)
+    seen = {}
+    prover3 = ec.session("prover")
+    proof3, _ = prover3.shuffle(1, ec.w, generators=h, publish=lambda nm, msg: (seen.__setitem__(nm, msg), ov.publish(nm, msg)))
+    assert set(seen) == {"output", "permutationCommitment", "commitment", "reply"}
+    raw = bytearray(proof3.commitment)
+    raw[len(raw) // 2] ^= 0x04
+    okb, outb = ov.finish(dataclasses.replace(proof3, commitment=bytes(raw)))
+    assert okb is False and col_values(outb) == oc.w
+    ov = verifier.beginVerify(1, ec.w, generators=h)
+    ov.publish("output", proof.output)
+    ov.publish("permutationCommitment", proof.permutationCommitment[:-2])      # a truncated message on the board
+    ov.publish("commitment", proof.commitment)
+    assert ov.finish(proof)[0] is True                                          # ... the proof itself is intact
+    ov = verifier.beginVerify(1, ec.w, generators=h)
+    ov.publish("output", proof.output)
+    ov.publish("permutationCommitment", bytes(proof.permutationCommitment) + b"\x00")   # trailing byte: not canonical
+    ov.publish("commitment", proof.commitment)
+    trailing = dataclasses.replace(proof, permutationCommitment=bytes(proof.permutationCommitment) + b"\x00")
+    assert ov.finish(trailing)[0] == verifier.verify(1, ec.w, trailing, generators=h)[0]
     assert opr.verify_shuffle(oc.G, oc.params, oc.pk, oc.w, oc.h, dataclasses.asdict(proof))
     # corrupted proofs: same verdict from both
     for field in ("reply", "commitment", "permutationCommitment", "output"):
@@ -611,7 +639,7 @@ def ec_group_ops(vmx, curve, n):
     assert vals(R.randomElementArray(n, prg, 100)) == oar.ring_random_array(OG, n, ors, 100)
 
 
-def mix_parity(vmx, spec, n, k=3, threshold=2, tmpdir=None):
+def mix_parity(vmx, spec, n, k=3, threshold=2, tmpdir=None, width=1):
     """A whole mix (keys, `threshold` shuffles, threshold decryption with proofs) on the engine and on the
     oracle from the same seeds: every file of the proof directory is byte-identical; the engine's vmnv
     (vmnv.MixNetElGamalVerifyFiatShamirSession) and the oracle's accept it, also after a round trip through a
@@ -623,18 +651,24 @@ def mix_parity(vmx, spec, n, k=3, threshold=2, tmpdir=None):
     oparams = opr.Params(pgroup_string="mix-%s" % spec)
     rs = vmx.crypto.PRGHeuristic()
     rs.setSeed(seed("mix/dealer"))
-    M = vm.MixNetElGamal(G, params, k, threshold, rs)
+    M = vm.MixNetElGamal(G, params, k, threshold, rs, width=width)
     irs = vmx.crypto.PRGHeuristic()
     irs.setSeed(seed("mix/input"))
-    w = mix.demoCiphertexts(M.fullPublicKey, n, irs)
-    plain = M.run(w)
-    # the oracle deals the same keys from the same stream, so the demo ciphertexts coincide
+    # the oracle deals the same keys from the same stream, so the input ciphertexts coincide
     probe = SeededRandomSource(seed("mix/dealer"))
     poly0 = oar.ring_random_element(OG, probe, 100)
     opk = (OG.g, OG.op_exp(OG.g, poly0))
-    ow = opr.demo_ciphertexts(OG, opk, n, SeededRandomSource(seed("mix/input")))
+    if width == 1:
+        w = mix.demoCiphertexts(M.fullPublicKey, n, irs)
+        ow = opr.demo_ciphertexts(OG, opk, n, SeededRandomSource(seed("mix/input")))
+    else:   # width-omega ciphertexts (elgamal/ProtocolElGamal.java:769-800): widePk^r, r in the product ring
+        r = mix.getPlainPGroup(G, width).getPRing().randomElementArray(n, irs, 100)
+        w = mix.getWidePublicKey(M.fullPublicKey, width).exp(r)
+        ors = SeededRandomSource(seed("mix/input"))
+        ow = oar.g_exp(OG, opr.wide_key(opk, width), tuple(oar.ring_random_array(OG, n, ors, 100) for _ in range(width)))
+    plain = M.run(w)
     assert col_values(w) == ow
-    od, oplain = opr.run_mix(OG, oparams, k, threshold, ow, SeededRandomSource(seed("mix/dealer")))
+    od, oplain = opr.run_mix(OG, oparams, k, threshold, ow, SeededRandomSource(seed("mix/dealer")), width=width)
     assert set(od) == set(M.nizkp)
     for name in sorted(od):
         assert od[name] == M.nizkp[name], name
@@ -981,3 +1015,49 @@ def squaring_selftest(vmx, bits, n, iters=3):
     e = A.PFieldElement(G.getPRing(), 1 << 7)
     G.set_tuning(coop_max=0)
     assert [x.value for x in X.exp(e).elements()] == [pow(v, 1 << 7, p) for v in vals]
+
+
+def concurrent_threads(vmx, bits, n, rounds=6):
+    """One context driven from two host threads at once, as the reference does with its export thread
+    (hvzk/CCPoSW.java:116-122: the proof is written to file while the protocol goes on) and its optimistic
+    next-output thread (mixnet/ShufflerElGamalSession.java:847-856): thread A serialises arrays (device-to-host
+    export) while thread B runs array operations and frees temporaries; every result equals the sequential one.
+    The C ABI serialises calls per context (one stream, a recursive mutex)."""
+    import threading
+    rnd = random.Random(bits * 17 + n)
+    A, G, R, p, q, g, xs, es, X, E = _arrays(vmx, bits, n, rnd)
+    want_exp = oar.g_exp(oar.ModPGroup(p, q, g), xs, es)
+    want_bytes = X.toByteTree().to_bytes()
+    errors, exported, computed = [], [], []
+
+    def exporter():
+        try:
+            for _ in range(rounds):
+                Y = X.mul(X)                      # a fresh array: its serialisation is not cached
+                Z = Y.copyOfRange(0, n)
+                exported.append((bytes(X.copyOfRange(0, n).toByteTree().to_bytes()), [e.value for e in Z.elements()][:3]))
+                Y.free()
+                Z.free()
+        except BaseException as e:   # noqa: surfaced below
+            errors.append(e)
+
+    def worker():
+        try:
+            for _ in range(rounds):
+                Y = X.exp(E)
+                computed.append([e.value for e in Y.elements()])
+                Y.free()
+                computed.append(X.expProd(E).value)
+        except BaseException as e:
+            errors.append(e)
+
+    ts = [threading.Thread(target=exporter), threading.Thread(target=worker)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    sq = [x * x % p for x in xs][:3]
+    assert all(b == want_bytes and z == sq for b, z in exported) and len(exported) == rounds
+    prod = oar.g_exp_prod(oar.ModPGroup(p, q, g), xs, es)
+    assert computed[0::2] == [want_exp] * rounds and computed[1::2] == [prod] * rounds

@@ -127,6 +127,12 @@ def test_wide_ciphertexts_parity(engine_emul, spec, width, n):
     pb.wide_committed_shuffle_parity(engine_emul, spec, width, n + 3, n)
 
 
+@pytest.mark.parametrize("spec,width,n", [(512, 3, 5), ("P-256", 2, 4)])
+def test_mix_and_vmnv_parity_wide(engine_emul, spec, width, n, tmp_path):
+    """A whole mix of width-omega ciphertexts and its verification (any width, elgamal/ProtocolElGamal.java:769-800)."""
+    pb.mix_parity(engine_emul, spec, n, tmpdir=tmp_path, width=width)
+
+
 def test_malformed_proof_files_are_verdicts_not_crashes(engine_emul):
     pb.malformed_proof_files(engine_emul, 512, 5)
 
@@ -135,3 +141,7 @@ def test_malformed_proof_files_are_verdicts_not_crashes(engine_emul):
 def test_dedicated_squaring(engine_emul, bits, n):
     """mont_sqr_tri (4 and 6 blocks of 16 words) on the emulated carry chains."""
     pb.squaring_selftest(engine_emul, bits, n, iters=2)
+
+
+def test_one_context_two_threads(engine_emul):
+    pb.concurrent_threads(engine_emul, 512, 40)

@@ -116,6 +116,12 @@ def test_accept_reject_at_scale_2048(engine_cuda):
     pb.accept_reject_properties(engine_cuda, 2048, 60000)
 
 
+@pytest.mark.parametrize("bits,n", [(512, 3000), (3072, 300)])
+def test_one_context_two_threads(engine_cuda, bits, n):
+    """Export thread + compute thread on one context (hvzk/CCPoSW.java:116-122, mixnet/ShufflerElGamalSession.java:847-856)."""
+    pb.concurrent_threads(engine_cuda, bits, n)
+
+
 def test_launches_are_counted(engine_cuda):
     vmx = engine_cuda
     A = vmx.arithm

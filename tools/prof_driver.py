@@ -28,13 +28,26 @@ X = G.randomElementArray(n, rs, 100)
 kE = R.toElementArray(A.LargeIntegerArray.random(n, 613, rs, R))
 e256 = R.toElementArray(A.LargeIntegerArray.random(n, 256, rs, R))
 v = R.toElement(int.from_bytes(bytes(range(32)), "big"))
-timed("exp_fixed (3071 bit)", lambda: G.getg().exp(e).free())
+quick = len(sys.argv) > 3 and sys.argv[3] == "quick"
+for w in ([0] if quick else [0, 16, 17, 18]):
+    if w == 18 and n < 500000:
+        continue
+    G.set_tuning(fixed_window=w)
+    timed("exp_fixed (3071 bit) w=%s" % (w or "auto"), lambda: G.getg().exp(e).free())
+G.set_tuning(fixed_window=0)
+Y = G.randomElementArray(n, rs, 100)
+timed("expMulExp (256 / 613 bit)", lambda: X.expMulExp(v, Y, kE).free())
+if n <= 200000:
+    full = R.toElement(G.q - 12345678901234567890123)
+    timed("exp_scalar (3071 bit)", lambda: X.exp(full).free(), reps=1)
 timed("exp_var (613 bit)", lambda: X.exp(kE).free())
 timed("exp_scalar (256 bit)", lambda: X.exp(v).free())
 timed("expProd (613 bit)", lambda: X.expProd(kE))
 timed("expProd (256 bit)", lambda: X.expProd(e256))
 timed("mul", lambda: X.mul(X).free())
 timed("prod", lambda: X.prod())
+if quick:
+    sys.exit(0)
 m = X.to_matrix()
 t0 = time.time(); G.toElementArray(n, m, check_membership=False).free(); G.sync(); t1 = time.time()
 G.toElementArray(n, m, check_membership=True).free(); G.sync(); t2 = time.time()

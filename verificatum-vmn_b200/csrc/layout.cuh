@@ -64,12 +64,19 @@ struct OneLoader {
   VMX_DEV Word2 operator()(int i) const { return Word2{i == 0 ? 1u : 0u, 0u}; }
 };
 
-// a <- a^2 (Montgomery), via a shared-memory copy of a: the block-triangular squaring of mont.cuh from 32 limbs
-// on (0.79 of a multiplication's IMAD.WIDE at 96 limbs), a plain multiplication below.
-template <int N>
+// a <- a^2 (Montgomery), via a shared-memory copy of a: the block-triangular squaring of mont.cuh with blocks of
+// VMX_SQR_BLOCK words where the residue has at least two of them, a plain multiplication otherwise.  32-word
+// blocks: 0.83 of a multiplication's IMAD.WIDE at 96 limbs (3 blocks), 0.875 at 64 (2 blocks).  16-word blocks
+// would be 0.79 but their six loop bodies (45 KB of SASS) push the loop of an exponentiation kernel out of the
+// instruction cache: measured on B200 at 3072 bits, n = 10^5 (profiles/r04_squaring_block_sizes.txt),
+// x^v * y^k: plain 216 ms, 48-word blocks 194, 32-word 197, 16-word 227; x^e, |e| = 3071: 922 / 824 / 820 / 850.
+#ifndef VMX_SQR_BLOCK
+#define VMX_SQR_BLOCK 32
+#endif
+template <int N, int BS = VMX_SQR_BLOCK>
 VMX_DEV void mont_sqr(uint32_t (&a)[N], uint2* s, unsigned stride, const MontParams<N>& M) {
   stash_shared<N>(a, s, stride);
-  if constexpr (N >= 32 && N % 16 == 0) mont_sqr_tri<N>(a, SharedLoader{s, stride}, M);
+  if constexpr (BS % 16 == 0 && N % BS == 0 && N >= 2 * BS) mont_sqr_tri<N, BS>(a, SharedLoader{s, stride}, M);
   else mont_mul<N>(a, SharedLoader{s, stride}, M);
 }
 

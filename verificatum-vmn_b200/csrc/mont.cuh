@@ -201,7 +201,8 @@ VMX_DEV void mont_mul(uint32_t (&a)[N], Loader ld2, const MontParams<N>& M) {
 template <int N, int D0, int J0>
 VMX_DEV void mont_sqr_rowpair(uint32_t (&t)[N + 2], const uint32_t (&a)[N], uint32_t x0, uint32_t x1, uint32_t y0,
                               uint32_t y1, const MontParams<N>& M) {
-  static_assert(N % (2 * kPairBlock) == 0 && D0 % (2 * kPairBlock) == 0 && J0 == D0 + 2 * kPairBlock, "16-word blocks");
+  static_assert(N % (2 * kPairBlock) == 0 && D0 % (2 * kPairBlock) == 0 && J0 % (2 * kPairBlock) == 0 && J0 > D0 && J0 <= N,
+                "blocks are multiples of 16 words");
   constexpr int PB = kPairBlock;
   uint32_t top2 = 0;  // column N+2
 
@@ -277,16 +278,19 @@ VMX_DEV void mont_sqr_rowpair(uint32_t (&t)[N + 2], const uint32_t (&a)[N], uint
   addc(t[N + 1], 0, 0);
 }
 
-// The 16 rows of block I (8 trips), the correction row of its boundary, then block I + 1.  `x` holds the words
-// (a[16 I], a[16 I + 1]) on entry; `ld2(i)` returns (a[i], a[i+1]) from the copy of a in shared memory.
-template <int N, int I, typename Loader>
+// The BS rows of block I (BS / 2 trips), the correction row of its boundary, then block I + 1.  `x` holds the words
+// (a[BS I], a[BS I + 1]) on entry; `ld2(i)` returns (a[i], a[i+1]) from the copy of a in shared memory.
+// BS (a multiple of 16 dividing N) trades multiplications against code: every block is its own unrolled loop body
+// (BS = 16 at N = 96: 6 bodies, 45 KB of SASS, 0.79 of a multiplication; 32: 3 bodies, 24 KB, 0.83; 48: 2 bodies, 17 KB,
+// 0.875) and the loop of an exponentiation kernel holds two or three multiplications besides.
+template <int N, int BS, int I, typename Loader>
 VMX_DEV void mont_sqr_blocks(uint64_t (&T)[N / 2 + 1], const uint32_t (&a)[N], Loader ld2, Word2 x,
                              const MontParams<N>& M) {
-  constexpr int D0 = 16 * I, J0 = 16 * (I + 1);
+  constexpr int D0 = BS * I, J0 = BS * (I + 1);
   uint32_t t[N + 2];
   uint32_t prevtop = 0;
 #pragma unroll 1
-  for (int r = 0; r < 16; r += 2) {
+  for (int r = 0; r < BS; r += 2) {
     const int i = D0 + r;
     const Word2 nx = ld2(i + 2 < N ? i + 2 : i);
     const uint32_t y0 = (x.x << 1) | prevtop;
@@ -311,18 +315,18 @@ VMX_DEV void mont_sqr_blocks(uint64_t (&T)[N / 2 + 1], const uint32_t (&a)[N], L
     addc(t[N + 1], t[N + 1], 0);
 #pragma unroll
     for (int k = 0; k < N / 2 + 1; k++) T[k] = pack_pair(t[2 * k], t[2 * k + 1]);
-    mont_sqr_blocks<N, I + 1>(T, a, ld2, x, M);
+    mont_sqr_blocks<N, BS, I + 1>(T, a, ld2, x, M);
   }
 }
 
 // a <- a * a * R^{-1} mod n; `ld2` streams a copy of a (shared memory).  Result fully reduced.
-template <int N, typename Loader>
+template <int N, int BS, typename Loader>
 VMX_DEV void mont_sqr_tri(uint32_t (&a)[N], Loader ld2, const MontParams<N>& M) {
-  static_assert(N % 16 == 0 && N >= 32, "block-triangular squaring needs at least two 16-word blocks");
+  static_assert(BS % 16 == 0 && N % BS == 0 && N >= 2 * BS, "block-triangular squaring needs at least two blocks");
   uint64_t T[N / 2 + 1];
 #pragma unroll
   for (int k = 0; k < N / 2 + 1; k++) T[k] = 0;
-  mont_sqr_blocks<N, 0>(T, a, ld2, ld2(0), M);
+  mont_sqr_blocks<N, BS, 0>(T, a, ld2, ld2(0), M);
   uint32_t t[N + 2];
 #pragma unroll
   for (int k = 0; k < N / 2 + 1; k++) unpack_pair(t[2 * k], t[2 * k + 1], T[k]);

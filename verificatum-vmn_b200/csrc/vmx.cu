@@ -41,6 +41,8 @@ void set_error(const char* fmt, ...) {
 #define VMX_CHECK_LAUNCH() VMX_CU(cudaGetLastError())
 
 static inline unsigned nblocks(size_t n, int per = kThreads) { return (unsigned)((n + per - 1) / per); }
+// dynamic shared memory of the byte codec kernels: the records of one block (kCodecThreads elements)
+static inline size_t codec_smem(size_t rec) { return ((size_t)kCodecThreads * rec + 15) & ~(size_t)15; }
 static inline size_t cap_for(size_t n) { return std::max<size_t>(8, (n + 7) & ~(size_t)7); }
 
 // ------------------------------------------------------------------ tiny host bignum (setup only)
@@ -340,7 +342,7 @@ static int upload_one(vmx_ctx* c, const uint8_t* be, bool group, ElemBuf& buf) {
   VMX_TRY(buf.alloc_elems(c, 1));
   VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
   const Modulus& Mod = group ? c->P : c->Q;
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, 1, kThreads, 0, raw.as<uint8_t>(), (size_t)1, (int)eb, 0,
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, 1, kCodecThreads, codec_smem(eb), raw.as<uint8_t>(), (size_t)1, (int)eb, 0,
                                  group ? 0 : 1, buf.d(), buf.cap, Mod.consts, c->d_flag, Mod.params<N>()));
   VMX_CHECK_LAUNCH();
   VMX_TRY(read_flags(c, 1));
@@ -356,7 +358,7 @@ static int download_one(vmx_ctx* c, const uint32_t* d, size_t cap, size_t idx, b
   VMX_TRY(raw.alloc(c, eb));
   const Modulus& Mod = group ? c->P : c->Q;
   // k_to_bytes addresses element i = thread index: shift the base so that thread 0 -> idx
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, 1, kThreads, 0, d + 4 * idx, cap, (size_t)1, (int)eb, 0,
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, 1, kCodecThreads, codec_smem(eb), d + 4 * idx, cap, (size_t)1, (int)eb, 0,
                                  group ? 0 : 1, raw.as<uint8_t>(), Mod.params<N>()));
   VMX_CHECK_LAUNCH();
   c->modmuls += group ? 1 : 0;
@@ -1284,7 +1286,7 @@ static int garr_import(vmx_ctx* c, size_t n, const uint8_t* be, int hdr, int che
     VMX_TRY(raw.alloc(c, bytes));
     VMX_CU(cudaMemcpyAsync(raw.p, be, bytes, cudaMemcpyHostToDevice, c->stream));
     VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
-    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n), kThreads, 0, raw.as<uint8_t>(), n, (int)c->eb, hdr, 0,
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n, kCodecThreads), kCodecThreads, codec_smem(c->eb + hdr), raw.as<uint8_t>(), n, (int)c->eb, hdr, 0,
                                    a->d, a->cap, c->P.consts, c->d_flag, c->P.params<N>()));
     VMX_CHECK_LAUNCH();
     c->modmuls += n;
@@ -1523,7 +1525,7 @@ static int garr_export(const vmx_garr* a, int hdr, uint8_t* be_out) {
   DevBuf raw;
   const size_t bytes = a->n * (c->eb + hdr);
   VMX_TRY(raw.alloc(c, bytes));
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, a->n, (int)c->eb, hdr, 0,
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n, kCodecThreads), kCodecThreads, codec_smem(c->eb + hdr), a->d, a->cap, a->n, (int)c->eb, hdr, 0,
                                  raw.as<uint8_t>(), c->P.params<N>()));
   VMX_CHECK_LAUNCH();
   c->modmuls += a->n;
@@ -1783,7 +1785,7 @@ int vmx_expprod(const vmx_garr* const* a, size_t k, const vmx_rarr* e, uint8_t* 
   }
   DevBuf raw;
   VMX_TRY(raw.alloc(c, k * c->eb));
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, 1, kThreads, 0, res.d(), res.cap, k, (int)c->eb, 0, 0,
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(k, kCodecThreads), kCodecThreads, codec_smem(c->eb), res.d(), res.cap, k, (int)c->eb, 0, 0,
                                  raw.as<uint8_t>(), c->P.params<N>()));
   VMX_CHECK_LAUNCH();
   VMX_CU(cudaMemcpyAsync(out_be, raw.p, k * c->eb, cudaMemcpyDeviceToHost, c->stream));
@@ -2101,7 +2103,7 @@ static int rarr_import(vmx_ctx* c, size_t n, const uint8_t* be, int hdr, vmx_rar
     VMX_TRY(raw.alloc(c, bytes));
     VMX_CU(cudaMemcpyAsync(raw.p, be, bytes, cudaMemcpyHostToDevice, c->stream));
     VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
-    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n), kThreads, 0, raw.as<uint8_t>(), n, (int)c->rb, hdr, 1,
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n, kCodecThreads), kCodecThreads, codec_smem(c->rb + hdr), raw.as<uint8_t>(), n, (int)c->rb, hdr, 1,
                                    a->d, a->cap, c->Q.consts, c->d_flag, c->Q.params<N>()));
     VMX_CHECK_LAUNCH();
     VMX_TRY(read_flags(c, 1));
@@ -2170,7 +2172,7 @@ static int rarr_export(const vmx_rarr* a, int hdr, uint8_t* be_out) {
   DevBuf raw;
   const size_t bytes = a->n * (c->rb + hdr);
   VMX_TRY(raw.alloc(c, bytes));
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n), kThreads, 0, a->d, a->cap, a->n, (int)c->rb, hdr, 1,
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n, kCodecThreads), kCodecThreads, codec_smem(c->rb + hdr), a->d, a->cap, a->n, (int)c->rb, hdr, 1,
                                  raw.as<uint8_t>(), c->Q.params<N>()));
   VMX_CHECK_LAUNCH();
   VMX_CU(cudaMemcpyAsync(be_out, raw.p, bytes, cudaMemcpyDeviceToHost, c->stream));

@@ -167,11 +167,14 @@ class PoSBasicTW:
         self.Ap = g.exp(self.alpha).mul(h.expProd(self.epsilon))
 
     # -- :505-514
-    def setPermutationCommitment(self, btr: ByteTreeReader) -> None:
+    def setPermutationCommitment(self, btr: ByteTreeReader) -> bool:
+        """Returns False if the commitment was malformed and replaced by the trivial one."""
         try:
             self.u = self.pGroup.toElementArray(self.h.size(), btr)
+            return True
         except ArithmFormatException:
             self.u = self.h.copyOfRange(0, self.h.size())
+            return False
 
     def getPermutationCommitment(self):
         return self.u
@@ -244,6 +247,7 @@ class PoSBasicTW:
             self.Fp = ciphPGroup.toElement(btr.getNextChild())
         except (EIOException, ArithmFormatException):
             malformed = True
+        self.commitmentMalformed = malformed
         if malformed:
             _free(self.B, self.Bp)
             one = self.pGroup.getONE()
@@ -705,10 +709,15 @@ class PoSTW:
         return self.challenger.challenge(challengeData, 8 * self.prg.minNoSeedBytes(), self.rbitlen)
 
     # -- :95-165
-    def prove(self, pkey, w, wp, s):
+    def prove(self, pkey, w, wp, s, publish=None):
+        """`publish(name, message)`: called as each message goes to the bulletin board (:105, :148, :160), so
+        that an online verifier (the other mix-servers of the reference wait on the board message by message,
+        :195-245) can hash and import it while this prover is still computing."""
         P = self.P
         P.setInstance(pkey, w, wp, s)
         permutationCommitment = P.u.toByteTree().to_buffer()
+        if publish is not None:
+            publish("permutationCommitment", permutationCommitment)
         d = self._seedDigest if self._seedDigest is not None else self._seed_begin(P.g, P.h)
         fed, self._seedDigest, self._seedFed = self._seedFed, None, 0
         self._seed_finish(d, P.u, pkey, w, wp, fed)
@@ -722,23 +731,75 @@ class PoSTW:
         commitment = P.commit(prgSeed, on_B=lambda B: B.toByteTree().update(cd))
         for child in commitment.children[1:]:
             child.update(cd)
+        commitmentBytes = commitment.to_buffer()
+        if publish is not None:
+            publish("commitment", commitmentBytes)
         challengeBytes = self.challenger.finish(cd)
         reply = P.reply(_to_positive(challengeBytes))
-        out = (permutationCommitment, commitment.to_buffer(), reply.to_buffer())
+        replyBytes = reply.to_buffer()
+        if publish is not None:
+            publish("reply", replyBytes)
+        out = (permutationCommitment, commitmentBytes, replyBytes)
         P.free()
         return out
+
+    # -- verifier, online: the hashing of a published message starts when it appears on the board, under the
+    # premise that it is well formed (then its bytes ARE the byte tree of the parsed value); `verify` checks the
+    # premise and hashes again if it does not hold, so verdicts are those of the offline order.
+    def prehashSeed(self, pkey, w, permutationCommitment, output) -> None:
+        V = self.V
+        d = self._seed_begin(V.g, V.h)
+        d.update(permutationCommitment)
+        pkey.toByteTree().update(d)
+        w.toByteTree().update(d)
+        d.update(output)
+        self._preSeed = (d, permutationCommitment, output)
+        self._preChallenge = None
+
+    def prehashChallenge(self, commitment) -> None:
+        """Needs the verifier's own seed: waits for the streamed seed hash, then streams the challenge hash."""
+        pre = getattr(self, "_preSeed", None)
+        if pre is None or isinstance(pre[0], bytes):
+            return
+        prgSeed = self.challenger.finish(pre[0])
+        self._preSeed = (prgSeed, pre[1], pre[2])
+        cd = self.challenger.begin(self.vbitlen)
+        cd.update(node_header(2))
+        ByteTreeLeaf(prgSeed).update(cd)
+        cd.update(commitment)
+        self._preChallenge = (cd, commitment)
+
+    def _abandon_prehash(self) -> None:
+        """Drop streamed hashes whose premise failed (every rank of a sharded run decides alike: the premise is a
+        function of the published bytes)."""
+        for st in (getattr(self, "_preSeed", None), getattr(self, "_preChallenge", None)):
+            if st is not None and not isinstance(st[0], bytes):
+                st[0].abandon()
+        self._preSeed = self._preChallenge = None
 
     # -- :177-260
     def verify(self, pkey, w, wp, permutationCommitment: bytes, commitment: bytes, reply: bytes) -> bool:
         V = self.V
         V.setInstance(pkey, w, wp)
+        u_parsed = True
         try:
-            V.setPermutationCommitment(ByteTreeReader(permutationCommitment))
+            u_parsed = V.setPermutationCommitment(ByteTreeReader(permutationCommitment)) is not False
         except EIOException:
             V.u = V.h.copyOfRange(0, V.h.size())
+            u_parsed = False
+        # online verification (prehashSeed): the seed hash was started from the published bytes; it stands if
+        # they are exactly the byte trees of the parsed arrays (well formed, no trailing bytes)
+        pre, prc = getattr(self, "_preSeed", None), getattr(self, "_preChallenge", None)
+        self._preSeed = self._preChallenge = None
+        pre_ok = pre is not None and u_parsed and pre[1] is permutationCommitment and \
+            len(permutationCommitment) == V.u.toByteTree().total_bytes() and len(pre[2]) == wp.toByteTree().total_bytes()
+        if pre is not None and not pre_ok:
+            self._preSeed, self._preChallenge = pre, prc
+            self._abandon_prehash()
+            pre = prc = None
         # every input of the seed is on the host already: hash it on the worker thread while the device imports
         # (and membership-checks) the commitment, which does not depend on the seed
-        d = self._seed_finish(self._seed_begin(V.g, V.h), V.u, pkey, w, wp)
+        d = pre[0] if pre is not None else self._seed_finish(self._seed_begin(V.g, V.h), V.u, pkey, w, wp)
         try:
             commitmentTree = V.setCommitment(ByteTreeReader(commitment))
         except EIOException:
@@ -753,17 +814,27 @@ class PoSTW:
             parsed = False
         if parsed:
             V.verifyIndependent()
-        prgSeed = self.challenger.finish(d)
+        prgSeed = d if isinstance(d, bytes) else self.challenger.finish(d)
         V.setBatchVector(prgSeed)
-        # the challenge is hashed while the device computes A and F
-        cd = self.challenger.begin(self.vbitlen)
-        ByteTreeContainer(ByteTreeLeaf(prgSeed), commitmentTree).update(cd)
+        # the challenge is hashed while the device computes A and F (online: its hash is already running, and
+        # stands if the published commitment is exactly the byte tree of what was parsed from it)
+        if prc is not None and not (prc[1] is commitment and not getattr(V, "commitmentMalformed", True) and
+                                    len(commitment) == commitmentTree.total_bytes() and
+                                    bytes(commitment[:5]) == node_header(len(commitmentTree.children))):
+            prc[0].abandon()
+            prc = None
+        if prc is not None:
+            cd = prc[0]
+        else:
+            cd = self.challenger.begin(self.vbitlen)
+            ByteTreeContainer(ByteTreeLeaf(prgSeed), commitmentTree).update(cd)
         V.computeAF()
         challengeBytes = self.challenger.finish(cd)
         V.setChallenge(_to_positive(challengeBytes))
         return V.verifyParsed() if parsed else False
 
     def free(self) -> None:
+        self._abandon_prehash()
         for b in (self.P, self.V):
             if b is not None:
                 b.free()

@@ -147,8 +147,10 @@ class ShufflerSession:
         return igs.generate(self.pGroup, size)
 
     # ShufflerElGamalSession.java:362-433 + :250-300 for l == j
-    def shuffle(self, width: int, ciphertexts, generators=None, keep_output: bool = False):
-        """Re-encrypt, permute and prove.  Returns (ShuffleProof, output array or None)."""
+    def shuffle(self, width: int, ciphertexts, generators=None, keep_output: bool = False, publish=None):
+        """Re-encrypt, permute and prove.  Returns (ShuffleProof, output array or None).  `publish(name, message)`
+        is called as each of the four messages ("output", "permutationCommitment", "commitment", "reply") goes
+        to the bulletin board (an OnlineVerification's `publish`, a file writer)."""
         ciphPPGroup = ciphertexts.getPGroup()
         exponentsPRing = ciphPPGroup.project(0).getPRing()
         widePublicKey = getWidePublicKey(self.publicKey, width)
@@ -174,7 +176,9 @@ class ShufflerSession:
         reenc.free()
         inverse.free()
         output_bytes = output.toByteTree().to_buffer()                                              # :284
-        pc, commitment, reply = P.prove(widePublicKey, ciphertexts, output, reencExponents)        # :289
+        if publish is not None:
+            publish("output", output_bytes)
+        pc, commitment, reply = P.prove(widePublicKey, ciphertexts, output, reencExponents, publish)   # :289
         reencExponents.free()
         if own_generators:
             generators.free()
@@ -186,7 +190,15 @@ class ShufflerSession:
         return proof, None
 
     # ShufflerElGamalSession.java:195-210 (readOutput) + :301-330 (verify branch)
-    def verify(self, width: int, ciphertexts, proof: ShuffleProof, generators=None, output=None):
+    def beginVerify(self, width: int, ciphertexts, generators=None) -> "OnlineVerification":
+        """Verification of a shuffle WHILE it is being proved: the returned object's `publish` is handed to the
+        prover (`shuffle(..., publish=...)`), `finish(proof)` gives the verdict.  This is how the reference's
+        mix-servers verify each other -- they wait on the bulletin board message by message (hvzk/PoSTW.java:195-245,
+        mixnet/ShufflerElGamalSession.java:301-330) -- and it takes the verifier's Fiat-Shamir hashing (3.1 KB per
+        ciphertext at 3072 bits, one SHA-256 stream) off the critical path: it runs beside the prover's."""
+        return OnlineVerification(self, width, ciphertexts, generators)
+
+    def verify(self, width: int, ciphertexts, proof: ShuffleProof, generators=None, output=None, _pos=None):
         """Returns (verdict, output array) -- on failure the output is a copy of the input
         ("Replacing output with input", :321-327).  `output`: proof.output already parsed (vmnv reads it itself)."""
         ciphPPGroup = ciphertexts.getPGroup()
@@ -201,9 +213,13 @@ class ShufflerSession:
         except Exception:
             if own_generators:
                 generators.free()
+            if _pos is not None:
+                _pos.free()
             return False, ciphertexts.copyOfRange(0, size)
-        V = self._pos()
-        V.precompute(generators.getPGroup().getg(), generators)
+        V = _pos
+        if V is None:
+            V = self._pos()
+            V.precompute(generators.getPGroup().getg(), generators)
         verdict = V.verify(widePublicKey, ciphertexts, output, proof.permutationCommitment, proof.commitment,
                            proof.reply)
         V.free()
@@ -213,6 +229,36 @@ class ShufflerSession:
             output.free()
             output = ciphertexts.copyOfRange(0, size)
         return verdict, output
+
+
+class OnlineVerification:
+    """One shuffle being verified as its messages are published (ShufflerSession.beginVerify)."""
+
+    def __init__(self, session: ShufflerSession, width: int, ciphertexts, generators=None):
+        self.session, self.width, self.ciphertexts = session, width, ciphertexts
+        self.own_generators = generators is None
+        self.generators = session.deriveGenerators(ciphertexts.size()) if generators is None else generators
+        self.widePublicKey = getWidePublicKey(session.publicKey, width)
+        self.V = session._pos()
+        self.V.precompute(self.generators.getPGroup().getg(), self.generators)
+        self.messages = {}
+
+    def publish(self, name: str, message) -> None:
+        """A message appeared on the board: start the hashing it unlocks (no verdict depends on this being
+        called -- `finish` redoes whatever was not, or not validly, anticipated)."""
+        self.messages[name] = message
+        m = self.messages
+        if name in ("output", "permutationCommitment") and "output" in m and "permutationCommitment" in m:
+            self.V.prehashSeed(self.widePublicKey, self.ciphertexts, m["permutationCommitment"], m["output"])
+        elif name == "commitment":
+            self.V.prehashChallenge(message)
+
+    def finish(self, proof: ShuffleProof):
+        """(verdict, output array), as ShufflerSession.verify."""
+        verdict, out = self.session.verify(self.width, self.ciphertexts, proof, generators=self.generators, _pos=self.V)
+        if self.own_generators:
+            self.generators.free()
+        return verdict, out
 
 
 # ---------------------------------------------------------------- mixnet/PermutationCommitment.java

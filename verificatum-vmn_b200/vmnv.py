@@ -103,8 +103,8 @@ class MixNetElGamal:
                  auxsid: Optional[str] = None):
         if auxsid is not None:
             params = dataclasses.replace(params, auxsid=auxsid)
-        if width != 1:
-            raise NotImplementedError("the in-process mix driver handles width 1 (the array classes handle any width)")
+        if width < 1:
+            raise ValueError("width must be positive")
         self.pGroup, self.params, self.k, self.threshold, self.width = pGroup, params, k, threshold, width
         self.randomSource = randomSource
         pField = pGroup.getPRing()
@@ -214,10 +214,12 @@ class MixNetElGamalVerifyFiatShamirSession:
     pre-computation (verify:1318-1668).  `verify` returns a report; conditions under which the reference stops
     with an error raise VerificationError."""
 
-    def __init__(self, pGroup, params: SessionParams, k: int, threshold: int, expectedAuxsid: Optional[str] = None):
-        """`expectedAuxsid`: the `-auxsid` option of vmnv; None accepts whatever the proof directory names."""
+    def __init__(self, pGroup, params: SessionParams, k: int, threshold: int, expectedAuxsid: Optional[str] = None,
+                 expectedWidth: Optional[int] = None):
+        """`expectedAuxsid`, `expectedWidth`: the `-auxsid` / `-width` options of vmnv; None accepts whatever the
+        proof directory names."""
         self.pGroup, self.params, self.k, self.threshold = pGroup, params, k, threshold
-        self.expectedAuxsid = expectedAuxsid
+        self.expectedAuxsid, self.expectedWidth = expectedAuxsid, expectedWidth
         self.report: Dict[str, object] = {}
 
     def _file(self, nizkp: ProofDirectory, name: str) -> bytes:
@@ -259,9 +261,14 @@ class MixNetElGamalVerifyFiatShamirSession:
         if self.expectedAuxsid is not None and auxsid != self.expectedAuxsid:
             raise VerificationError("The given auxiliary session identifier does not match the one in the proof!")
         p = dataclasses.replace(p, auxsid=auxsid)
-        width = int(self._file(nizkp, "width").decode())
-        if width != 1:
-            raise VerificationError("Unsupported width")
+        # determineWidth (:404-440): the number of ciphertexts shuffled in parallel; the keys of the directory are
+        # the basic ones and are widened where they are used (elgamal/ProtocolElGamal.java:769-800)
+        try:
+            width = int(self._file(nizkp, "width").decode())
+        except ValueError:
+            raise VerificationError("Can not parse width given in file!")
+        if width < 1 or (self.expectedWidth is not None and width != self.expectedWidth):
+            raise VerificationError("Mismatching or invalid width!")
         ciphPGroup = getCiphPGroup(G, width)
         # readFullPKey :195-226
         try:
@@ -292,8 +299,12 @@ class MixNetElGamalVerifyFiatShamirSession:
         # readCiphertexts
         raw = self._file(nizkp, "Ciphertexts.bt")
         try:
-            size = ByteTreeReader(raw).getNextChild().getRemaining() if not G.is_curve else \
-                ByteTreeReader(raw).getNextChild().getNextChild().getRemaining()
+            # Ciphertexts.bt = node(u, v); for width > 1 each of them is a node of `width` arrays; an array over a
+            # curve group is node(x leaves, y leaves): descend to the first array of leaves
+            r = ByteTreeReader(raw).getNextChild()
+            for _ in range((1 if width > 1 else 0) + (1 if G.is_curve else 0)):
+                r = r.getNextChild()
+            size = r.getRemaining()
         except EIOException:
             raise VerificationError("Unable to read ciphertexts!")
         ciphertexts = self._readArray(size, ciphPGroup, raw, "Ciphertexts.bt")
