@@ -433,12 +433,16 @@ def run_shuffle(args, env):
     e1 = torch.cuda.Event(enable_timing=True)
     t_host0 = time.time()
     e0.record(stream)
+    marks = []
     for i in range(args.steps):
         step_device(args.warmup + i, True)
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record(stream)
     e1.record(stream)
     e1.synchronize()
     env.barrier()
     t_host = time.time() - t_host0
+    step_ms = [(marks[i - 1] if i else e0).elapsed_time(marks[i]) for i in range(len(marks))]
     launches = G.launch_count() - launches0
     modmuls = G.modmul_count() - modmuls0
     sampler.stop_flag.set()
@@ -613,7 +617,8 @@ def run_shuffle(args, env):
                            "executed_frac_of_imad_peak": modmuls * macs / (dev_ms * 1e-3) / IMAD_PEAK_MAC_PER_S,
                            "note": "fractions are per GPU (rank 0's kernels against one GPU's peak); a squaring "
                                    "counts as one modmul although it executes ~0.79 of a multiplication's MACs"},
-                "host_wall_ms_per_step": t_host * 1e3 / args.steps}
+                "host_wall_ms_per_step": t_host * 1e3 / args.steps,
+                "step_ms": {"min": min(step_ms), "max": max(step_ms), "all": step_ms[:32]}}
         if args.phases:
             line["phase_ms_per_step"] = {k: v / args.steps for k, v in phase_ms.items()}
         try:  # how this line relates to the headline metric of BASELINE.json

@@ -33,10 +33,10 @@ def test_transcript_parity(engine_emul, n):
 def test_variable_base_kernels_in_several_launches(engine_emul, monkeypatch):
     """VMX_VAR_CHUNK bounds the elements per launch of k_exp_var / k_exp_var2 (production: the table scratch
     bound, reached above ~244k elements at 3072 bits): the i0 > 0 launches, and Pippenger at c = 12."""
-    pb.with_env(monkeypatch, VMX_VAR_CHUNK=3, VMX_MEXP_WINDOW=12)
-    pb.group_ops(engine_emul, 512, 37)
-    pb.decryption_parity(engine_emul, 512, 11, 3, 2)
-    pb.transcript_parity(engine_emul, 512, 10)
+    pb.with_env(monkeypatch, VMX_VAR_CHUNK=3, VMX_MEXP_WINDOW=8)
+    pb.group_ops(engine_emul, 512, 17)
+    pb.decryption_parity(engine_emul, 512, 7, 3, 2)
+    pb.transcript_parity(engine_emul, 512, 7)
 
 
 def test_production_kernels_body_on_emulation(engine_emul):
@@ -134,7 +134,7 @@ def test_mix_and_vmnv_parity_wide(engine_emul, spec, width, n, tmp_path):
 
 
 def test_malformed_proof_files_are_verdicts_not_crashes(engine_emul):
-    pb.malformed_proof_files(engine_emul, 512, 5)
+    pb.malformed_proof_files(engine_emul, 512, 3)
 
 
 @pytest.mark.parametrize("bits,n", [(2048, 12), (3072, 8)])

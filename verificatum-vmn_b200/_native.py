@@ -48,6 +48,7 @@ SIGNATURES = {
     "vmx_ctx_stream": (_P, [_P]),
     "vmx_ctx_set_fixed_window": (C.c_int, [_P, C.c_int]),
     "vmx_ctx_set_tuning": (C.c_int, [_P, C.c_char_p, C.c_longlong]),
+    "vmx_leaves_uniform": (C.c_int, [_P, _SZ, _SZ]),
     "vmx_garr_from_bytes": (C.c_int, [_P, _SZ, _P, C.c_int, _PP]),
     "vmx_garr_from_raw": (C.c_int, [_P, _SZ, _P, _SZ, C.c_uint, _PP]),
     "vmx_garr_prg_sha256": (C.c_int, [_P, _U8, _SZ, C.c_uint64, _SZ, _SZ, C.c_uint, _PP]),

@@ -38,6 +38,21 @@ VMX_DEV uint32_t be_word(const uint8_t* src, int eb, int j) {  // little-endian 
 // 100 ms per 10^6 elements on import and again on export, ~1.7 s of an end-to-end step at N = 10^6.
 constexpr int kCodecThreads = 64;
 
+#ifndef VMX_HOST_EMUL
+// The `bytes` bytes at g -> shared memory, as aligned 16-byte vectors whatever the alignment of g (PRG output
+// starts anywhere in its first 32-byte block): returns where g[0] sits in `stage`.  The vectors cover
+// [g - mis, g + bytes) rounded up to 16; the last one stays inside the 16-byte granule that holds g[bytes - 1].
+// Needs (bytes + 31) bytes of shared memory (codec_smem in vmx.cu); ends with a block barrier.
+VMX_DEV const uint8_t* stage_in(uint4* stage, const uint8_t* g, size_t bytes) {
+  const size_t mis = reinterpret_cast<uintptr_t>(g) & 15;
+  const uint4* g16 = reinterpret_cast<const uint4*>(g - mis);
+  const size_t vecs = (mis + bytes + 15) >> 4;
+  for (size_t v = threadIdx.x; v < vecs; v += blockDim.x) stage[v] = g16[v];
+  __syncthreads();
+  return reinterpret_cast<const uint8_t*>(stage) + mis;
+}
+#endif
+
 template <int N>
 VMX_KERNEL(N) k_from_bytes(const uint8_t* __restrict__ raw, size_t n, int eb, int hdr, int mode,
                            uint32_t* __restrict__ out, size_t cap, const uint32_t* __restrict__ r2,
@@ -46,18 +61,11 @@ VMX_KERNEL(N) k_from_bytes(const uint8_t* __restrict__ raw, size_t n, int eb, in
   const size_t rec = (size_t)(eb + hdr);
 #ifndef VMX_HOST_EMUL
   VMX_DYN_SMEM(uint4, stage);
-  {
-    const size_t e0 = (size_t)blockIdx.x * blockDim.x;
-    const size_t cnt = n - e0 < blockDim.x ? n - e0 : blockDim.x;
-    const uint8_t* g = raw + e0 * rec;
-    const size_t bytes = cnt * rec, vecs = bytes >> 4;
-    for (size_t v = threadIdx.x; v < vecs; v += blockDim.x) stage[v] = reinterpret_cast<const uint4*>(g)[v];
-    for (size_t b = (vecs << 4) + threadIdx.x; b < bytes; b += blockDim.x) reinterpret_cast<uint8_t*>(stage)[b] = g[b];
-    __syncthreads();
-  }
+  const size_t e0 = (size_t)blockIdx.x * blockDim.x;
+  const uint8_t* sbase = stage_in(stage, raw + e0 * rec, (n - e0 < blockDim.x ? n - e0 : blockDim.x) * rec);
   if (i >= n) return;
   // hdr = 5: the elements are the leaves of a byte tree, 0x01 || be32(eb) || payload each
-  const uint8_t* src = reinterpret_cast<const uint8_t*>(stage) + threadIdx.x * rec + hdr;
+  const uint8_t* src = sbase + threadIdx.x * rec + hdr;
 #else
   if (i >= n) return;
   const uint8_t* src = raw + i * rec + hdr;
@@ -146,8 +154,16 @@ VMX_KERNEL(N) k_ring_from_raw(const uint8_t* __restrict__ raw, size_t n, int wid
                               uint32_t* __restrict__ out, size_t cap, const uint32_t* __restrict__ r2,
                               int need_reduce, const __grid_constant__ MontParams<N> M) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#ifndef VMX_HOST_EMUL
+  VMX_DYN_SMEM(uint4, stage);
+  const size_t e0 = (size_t)blockIdx.x * blockDim.x;
+  const uint8_t* sbase = stage_in(stage, raw + e0 * (size_t)width, (n - e0 < blockDim.x ? n - e0 : blockDim.x) * (size_t)width);
+  if (i >= n) return;
+  const uint8_t* src = sbase + threadIdx.x * (size_t)width;
+#else
   if (i >= n) return;
   const uint8_t* src = raw + i * (size_t)width;
+#endif
   const int totalbits = bitlen ? bitlen : 8 * width;
   auto word = [&](int j) -> uint32_t {  // little-endian word j of the masked integer
     uint32_t v = 0;

@@ -42,7 +42,14 @@ void set_error(const char* fmt, ...) {
 
 static inline unsigned nblocks(size_t n, int per = kThreads) { return (unsigned)((n + per - 1) / per); }
 // dynamic shared memory of the byte codec kernels: the records of one block (kCodecThreads elements)
-static inline size_t codec_smem(size_t rec) { return ((size_t)kCodecThreads * rec + 15) & ~(size_t)15; }
+// threads per block and dynamic shared memory of the byte codec kernels: the records of one block plus the slack
+// of stage_in; long records (wide random integers) take smaller blocks to stay below the 48 KB default limit
+static inline int codec_threads(size_t rec) {
+  int t = kCodecThreads;
+  while (t > 8 && (size_t)t * rec + 48 > 48 * 1024) t >>= 1;
+  return t;
+}
+static inline size_t codec_smem(size_t rec) { return ((size_t)codec_threads(rec) * rec + 47) & ~(size_t)15; }
 static inline size_t cap_for(size_t n) { return std::max<size_t>(8, (n + 7) & ~(size_t)7); }
 
 // ------------------------------------------------------------------ tiny host bignum (setup only)
@@ -342,7 +349,7 @@ static int upload_one(vmx_ctx* c, const uint8_t* be, bool group, ElemBuf& buf) {
   VMX_TRY(buf.alloc_elems(c, 1));
   VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
   const Modulus& Mod = group ? c->P : c->Q;
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, 1, kCodecThreads, codec_smem(eb), raw.as<uint8_t>(), (size_t)1, (int)eb, 0,
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, 1, codec_threads(eb), codec_smem(eb), raw.as<uint8_t>(), (size_t)1, (int)eb, 0,
                                  group ? 0 : 1, buf.d(), buf.cap, Mod.consts, c->d_flag, Mod.params<N>()));
   VMX_CHECK_LAUNCH();
   VMX_TRY(read_flags(c, 1));
@@ -358,7 +365,7 @@ static int download_one(vmx_ctx* c, const uint32_t* d, size_t cap, size_t idx, b
   VMX_TRY(raw.alloc(c, eb));
   const Modulus& Mod = group ? c->P : c->Q;
   // k_to_bytes addresses element i = thread index: shift the base so that thread 0 -> idx
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, 1, kCodecThreads, codec_smem(eb), d + 4 * idx, cap, (size_t)1, (int)eb, 0,
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, 1, codec_threads(eb), codec_smem(eb), d + 4 * idx, cap, (size_t)1, (int)eb, 0,
                                  group ? 0 : 1, raw.as<uint8_t>(), Mod.params<N>()));
   VMX_CHECK_LAUNCH();
   c->modmuls += group ? 1 : 0;
@@ -1251,6 +1258,20 @@ int vmx_ctx_set_fixed_window(vmx_ctx* c, int w) {
   c->fixed_window = w;
   return VMX_OK;
 }
+// Host-side helper of the byte-tree reader: are the n records of 5 + width bytes all leaf headers 0x01 || be32(width)?
+// One pass over n cache lines (the reader needs it to skip an array arithmetically before the engine imports it).
+int vmx_leaves_uniform(const uint8_t* leaves, size_t n, size_t width) {
+  if (!leaves && n) return 0;
+  const uint8_t h1 = (uint8_t)(width >> 24), h2 = (uint8_t)(width >> 16), h3 = (uint8_t)(width >> 8), h4 = (uint8_t)width;
+  const size_t rec = 5 + width;
+  unsigned bad = 0;
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t* h = leaves + i * rec;
+    bad |= (unsigned)(h[0] ^ 1) | (unsigned)(h[1] ^ h1) | (unsigned)(h[2] ^ h2) | (unsigned)(h[3] ^ h3) | (unsigned)(h[4] ^ h4);
+  }
+  return bad == 0;
+}
+
 int vmx_ctx_set_tuning(vmx_ctx* c, const char* key, long long value) {
   if (!c || !key || value < 0) return VMX_EARG;
   const std::string k(key);
@@ -1286,7 +1307,7 @@ static int garr_import(vmx_ctx* c, size_t n, const uint8_t* be, int hdr, int che
     VMX_TRY(raw.alloc(c, bytes));
     VMX_CU(cudaMemcpyAsync(raw.p, be, bytes, cudaMemcpyHostToDevice, c->stream));
     VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
-    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n, kCodecThreads), kCodecThreads, codec_smem(c->eb + hdr), raw.as<uint8_t>(), n, (int)c->eb, hdr, 0,
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n, codec_threads(c->eb + hdr)), codec_threads(c->eb + hdr), codec_smem(c->eb + hdr), raw.as<uint8_t>(), n, (int)c->eb, hdr, 0,
                                    a->d, a->cap, c->P.consts, c->d_flag, c->P.params<N>()));
     VMX_CHECK_LAUNCH();
     c->modmuls += n;
@@ -1337,7 +1358,7 @@ static int garr_from_raw_dev(vmx_ctx* c, size_t n, const uint8_t* d_raw, size_t 
     ElemBuf can;
     VMX_TRY(can.alloc_elems(c, n));
     VMX_DISPATCH(c->nl, {
-      VMX_LAUNCH(c, k_ring_from_raw<N>, nblocks(n), kThreads, 0, d_raw, n, (int)width, (int)bitlen, can.d(),
+      VMX_LAUNCH(c, k_ring_from_raw<N>, nblocks(n, codec_threads(width)), codec_threads(width), codec_smem(width), d_raw, n, (int)width, (int)bitlen, can.d(),
                  can.cap, c->P.consts, 1, c->P.params<N>());
       VMX_CHECK_LAUNCH();
       // canonical -> Montgomery form
@@ -1506,7 +1527,7 @@ int vmx_rarr_prg_raw_sha256(vmx_ctx* c, const uint8_t* seed, size_t seedlen, uin
   if (n) {
     const int totalbits = bitlen ? (int)bitlen : (int)(8 * width);
     const int need_reduce = totalbits >= c->Q.bits;
-    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_ring_from_raw<N>, nblocks(n), kThreads, 0, data, n, (int)width,
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_ring_from_raw<N>, nblocks(n, codec_threads(width)), codec_threads(width), codec_smem(width), data, n, (int)width,
                                    (int)bitlen, a->d, a->cap, c->Q.consts, need_reduce, c->Q.params<N>()));
     VMX_CHECK_LAUNCH();
     if (need_reduce) c->modmuls += 3 * n;
@@ -1525,7 +1546,7 @@ static int garr_export(const vmx_garr* a, int hdr, uint8_t* be_out) {
   DevBuf raw;
   const size_t bytes = a->n * (c->eb + hdr);
   VMX_TRY(raw.alloc(c, bytes));
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n, kCodecThreads), kCodecThreads, codec_smem(c->eb + hdr), a->d, a->cap, a->n, (int)c->eb, hdr, 0,
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n, codec_threads(c->eb + hdr)), codec_threads(c->eb + hdr), codec_smem(c->eb + hdr), a->d, a->cap, a->n, (int)c->eb, hdr, 0,
                                  raw.as<uint8_t>(), c->P.params<N>()));
   VMX_CHECK_LAUNCH();
   c->modmuls += a->n;
@@ -1785,7 +1806,7 @@ int vmx_expprod(const vmx_garr* const* a, size_t k, const vmx_rarr* e, uint8_t* 
   }
   DevBuf raw;
   VMX_TRY(raw.alloc(c, k * c->eb));
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(k, kCodecThreads), kCodecThreads, codec_smem(c->eb), res.d(), res.cap, k, (int)c->eb, 0, 0,
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(k, codec_threads(c->eb)), codec_threads(c->eb), codec_smem(c->eb), res.d(), res.cap, k, (int)c->eb, 0, 0,
                                  raw.as<uint8_t>(), c->P.params<N>()));
   VMX_CHECK_LAUNCH();
   VMX_CU(cudaMemcpyAsync(out_be, raw.p, k * c->eb, cudaMemcpyDeviceToHost, c->stream));
@@ -2103,7 +2124,7 @@ static int rarr_import(vmx_ctx* c, size_t n, const uint8_t* be, int hdr, vmx_rar
     VMX_TRY(raw.alloc(c, bytes));
     VMX_CU(cudaMemcpyAsync(raw.p, be, bytes, cudaMemcpyHostToDevice, c->stream));
     VMX_CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int) * 4, c->stream));
-    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n, kCodecThreads), kCodecThreads, codec_smem(c->rb + hdr), raw.as<uint8_t>(), n, (int)c->rb, hdr, 1,
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_from_bytes<N>, nblocks(n, codec_threads(c->rb + hdr)), codec_threads(c->rb + hdr), codec_smem(c->rb + hdr), raw.as<uint8_t>(), n, (int)c->rb, hdr, 1,
                                    a->d, a->cap, c->Q.consts, c->d_flag, c->Q.params<N>()));
     VMX_CHECK_LAUNCH();
     VMX_TRY(read_flags(c, 1));
@@ -2130,7 +2151,7 @@ int vmx_rarr_from_raw(vmx_ctx* c, size_t n, const uint8_t* be, size_t width, uns
     VMX_CU(cudaMemcpyAsync(raw.p, be, n * width, cudaMemcpyHostToDevice, c->stream));
     const int totalbits = bitlen ? (int)bitlen : (int)(8 * width);
     const int need_reduce = totalbits >= c->Q.bits;
-    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_ring_from_raw<N>, nblocks(n), kThreads, 0, raw.as<uint8_t>(), n, (int)width,
+    VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_ring_from_raw<N>, nblocks(n, codec_threads(width)), codec_threads(width), codec_smem(width), raw.as<uint8_t>(), n, (int)width,
                                    (int)bitlen, a->d, a->cap, c->Q.consts, need_reduce, c->Q.params<N>()));
     VMX_CHECK_LAUNCH();
     if (need_reduce) c->modmuls += 3 * n;
@@ -2172,7 +2193,7 @@ static int rarr_export(const vmx_rarr* a, int hdr, uint8_t* be_out) {
   DevBuf raw;
   const size_t bytes = a->n * (c->rb + hdr);
   VMX_TRY(raw.alloc(c, bytes));
-  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n, kCodecThreads), kCodecThreads, codec_smem(c->rb + hdr), a->d, a->cap, a->n, (int)c->rb, hdr, 1,
+  VMX_DISPATCH(c->nl, VMX_LAUNCH(c, k_to_bytes<N>, nblocks(a->n, codec_threads(c->rb + hdr)), codec_threads(c->rb + hdr), codec_smem(c->rb + hdr), a->d, a->cap, a->n, (int)c->rb, hdr, 1,
                                  raw.as<uint8_t>(), c->Q.params<N>()));
   VMX_CHECK_LAUNCH();
   VMX_CU(cudaMemcpyAsync(be_out, raw.p, bytes, cudaMemcpyDeviceToHost, c->stream));

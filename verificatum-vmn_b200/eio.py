@@ -223,10 +223,19 @@ def _skip_subtrees(buf, pos: int, count: int) -> int:
     equal-width leaves, the bulk of every proof file, are skipped arithmetically."""
     n = len(buf)
     stack = [count]
+    fresh = True      # the sibling list on top of the stack has not been tried as a run of equal-width leaves
     while stack:
         if stack[-1] == 0:
             stack.pop()
+            fresh = False
             continue
+        if fresh and stack[-1] > 1:
+            end = _uniform_leaves_end(buf, pos, stack[-1])
+            if end:
+                pos = end
+                stack[-1] = 0
+                continue
+        fresh = False
         stack[-1] -= 1
         if pos + 5 > n:
             raise EIOException("truncated header")
@@ -239,13 +248,10 @@ def _skip_subtrees(buf, pos: int, count: int) -> int:
         elif kind == NODE:
             if cnt == 0:
                 continue
-            end = _uniform_leaves_end(buf, pos, cnt)
-            if end:
-                pos = end
-                continue
             if len(stack) >= MAX_DEPTH:
                 raise EIOException("byte tree nested deeper than %d levels" % MAX_DEPTH)
             stack.append(cnt)
+            fresh = True
         else:
             raise EIOException("bad tag %d" % kind)
     return pos
@@ -260,12 +266,23 @@ def _uniform_leaves_end(buf, pos: int, cnt: int) -> int:
     end = pos + cnt * (5 + w)
     if end > n:
         return 0
-    if cnt > 1:
-        m = np.frombuffer(buf[pos:end], dtype=np.uint8).reshape(cnt, 5 + w)
-        hdr = np.frombuffer(struct.pack(">BI", LEAF, w), dtype=np.uint8)
-        if not (m[:, :5] == hdr).all():
-            return 0
+    if cnt > 1 and not _leaf_headers_uniform(buf, pos, cnt, w):
+        return 0
     return end
+
+
+def _leaf_headers_uniform(buf, pos: int, cnt: int, w: int) -> bool:
+    """True iff the `cnt` records of 5 + w bytes at `pos` all start with the header of a leaf of w bytes: one pass
+    in the engine's library (vmx_leaves_uniform, host memory only) for long arrays -- a (cnt, 5) byte-matrix
+    comparison in numpy took 170 ms per 10^6 leaves in round 2's end-to-end trace, with the GPU idle."""
+    rec = 5 + w
+    base = np.frombuffer(buf, dtype=np.uint8)
+    if cnt >= 4096:
+        from . import _native as nat
+        return bool(nat.load().vmx_leaves_uniform(base[pos:].ctypes.data, cnt, w))
+    m = base[pos:pos + cnt * rec].reshape(cnt, rec)
+    hdr = np.frombuffer(struct.pack(">BI", LEAF, w), dtype=np.uint8)
+    return bool((m[:, :5] == hdr).all())
 
 
 class ByteTreeReader:
@@ -354,7 +371,6 @@ class ByteTreeReader:
         if end > len(self.buf):
             raise EIOException("truncated array")
         m = np.frombuffer(self.buf[self.pos:end], dtype=np.uint8).reshape(size, 5 + width)
-        hdr = np.frombuffer(struct.pack(">BI", LEAF, width), dtype=np.uint8)
-        if size and not (m[:, :5] == hdr).all():
+        if size and not _leaf_headers_uniform(self.buf, self.pos, size, width):
             raise EIOException("array leaves of unexpected width")
         return np.ascontiguousarray(m[:, 5:])
