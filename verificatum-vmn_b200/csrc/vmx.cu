@@ -139,18 +139,68 @@ static void image_put(std::vector<uint32_t>& img, size_t cap, size_t idx, const 
 }
 
 // ------------------------------------------------------------------ device memory helpers
+constexpr size_t kBigBlock = (size_t)32 << 20;
+// Device memory of a context: small blocks from the stream-ordered pool, large ones through the context's
+// recycling list (vmx_ctx::big_free).  *granted = the size to hand back to dev_free.
+static cudaError_t dev_alloc(vmx_ctx* c, size_t bytes, void** p, size_t* granted) {
+  if (bytes < kBigBlock) {
+    *granted = bytes;
+    return cudaMallocAsync(p, bytes ? bytes : 16, c->stream);
+  }
+  {
+    std::lock_guard<std::mutex> lk(c->big_mu);
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < c->big_free.size(); i++) {
+      const size_t b = c->big_free[i].bytes;
+      if (b >= bytes && b <= bytes + bytes / 4 && (best == (size_t)-1 || b < c->big_free[best].bytes)) best = i;
+    }
+    if (best != (size_t)-1) {
+      *p = c->big_free[best].p;
+      *granted = c->big_free[best].bytes;
+      c->big_free_bytes -= *granted;
+      c->big_free.erase(c->big_free.begin() + (long)best);
+      return cudaSuccess;
+    }
+  }
+  const size_t rounded = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+  *granted = rounded;
+  cudaError_t e = cudaMallocAsync(p, rounded, c->stream);
+  if (e != cudaSuccess) {  // out of memory with blocks parked in the list: give them back and try once more
+    (void)cudaGetLastError();
+    std::lock_guard<std::mutex> lk(c->big_mu);
+    for (auto& b : c->big_free) cudaFreeAsync(b.p, c->stream);
+    c->big_free.clear();
+    c->big_free_bytes = 0;
+    e = cudaMallocAsync(p, rounded, c->stream);
+  }
+  return e;
+}
+static void dev_free(vmx_ctx* c, void* p, size_t granted) {
+  if (!p) return;
+  if (granted < kBigBlock) { cudaFreeAsync(p, c->stream); return; }
+  std::lock_guard<std::mutex> lk(c->big_mu);
+  c->big_free.push_back({p, granted});
+  c->big_free_bytes += granted;
+  while (c->big_free_bytes > c->big_cache_max && !c->big_free.empty()) {  // oldest first
+    cudaFreeAsync(c->big_free.front().p, c->stream);
+    c->big_free_bytes -= c->big_free.front().bytes;
+    c->big_free.erase(c->big_free.begin());
+  }
+}
+
 struct DevBuf {  // stream-ordered temporary
   vmx_ctx* c = nullptr;
   void* p = nullptr;
+  size_t granted = 0;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { reset(); }
-  void reset() { if (p) cudaFreeAsync(p, c->stream); p = nullptr; }
+  void reset() { if (p) dev_free(c, p, granted); p = nullptr; }
   int alloc(vmx_ctx* ctx, size_t bytes) {
     reset();
     c = ctx;
-    if (cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream) != cudaSuccess) {
+    if (dev_alloc(ctx, bytes, &p, &granted) != cudaSuccess) {
       p = nullptr;
       (void)cudaGetLastError();
       set_error("device allocation of %zu bytes failed", bytes);
@@ -175,7 +225,7 @@ static int new_garr(vmx_ctx* c, size_t n, vmx_garr** out) {
   auto* a = new (std::nothrow) vmx_garr{c, n, cap_for(n), nullptr};
   if (!a) return VMX_ENOMEM;
   void* p = nullptr;
-  if (cudaMallocAsync(&p, a->cap * c->gl * 4, c->stream) != cudaSuccess) {
+  if (dev_alloc(c, a->cap * c->gl * 4, &p, &a->granted) != cudaSuccess) {
     (void)cudaGetLastError();
     delete a;
     set_error("device allocation of %zu bytes failed", a->cap * c->gl * 4);
@@ -190,7 +240,7 @@ static int new_rarr(vmx_ctx* c, size_t n, vmx_rarr** out) {
   auto* a = new (std::nothrow) vmx_rarr{c, n, cap_for(n), nullptr, -1};
   if (!a) return VMX_ENOMEM;
   void* p = nullptr;
-  if (cudaMallocAsync(&p, a->cap * c->nl * 4, c->stream) != cudaSuccess) {
+  if (dev_alloc(c, a->cap * c->nl * 4, &p, &a->granted) != cudaSuccess) {
     (void)cudaGetLastError();
     delete a;
     set_error("device allocation of %zu bytes failed", a->cap * c->nl * 4);
@@ -306,7 +356,8 @@ static int seg_product(vmx_ctx* c, const Modulus& Mod, const uint32_t* V, size_t
     c->modmuls += cur_total;
     // next round: values = partial products, segments = chunk ranges
     std::swap(val_keep.p, part.p); std::swap(val_keep.c, part.c); std::swap(val_keep.cap, part.cap);
-    std::swap(off_keep.p, chunk_off.p); std::swap(off_keep.c, chunk_off.c);
+    std::swap(val_keep.granted, part.granted);
+    std::swap(off_keep.p, chunk_off.p); std::swap(off_keep.c, chunk_off.c); std::swap(off_keep.granted, chunk_off.granted);
     cur_V = val_keep.d();
     cur_vcap = val_keep.cap;
     cur_idx = nullptr;
@@ -789,7 +840,7 @@ static int ring_reduce_sum(vmx_ctx* c, const uint32_t* a, size_t acap, const uin
                bb ? tmp.d() : (uint32_t*)nullptr, bb ? tmp.cap : (size_t)0, M);
     VMX_CHECK_LAUNCH();
     if (bb) c->modmuls += m;
-    std::swap(cur.p, nxt.p); std::swap(cur.c, nxt.c); std::swap(cur.cap, nxt.cap);
+    std::swap(cur.p, nxt.p); std::swap(cur.c, nxt.c); std::swap(cur.cap, nxt.cap); std::swap(cur.granted, nxt.granted);
     src = cur.d(); scap = cur.cap; m = nch; bb = nullptr; first = false;
   }
   VMX_TRY(out.alloc_elems(c, 1));
@@ -1236,6 +1287,8 @@ void vmx_ctx_destroy(vmx_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& kv : c->tables) cudaFreeAsync(kv.second.d, c->stream);
+  for (auto& b : c->big_free) cudaFreeAsync(b.p, c->stream);
+  c->big_free.clear();
   cudaFreeAsync(c->P.consts, c->stream);
   cudaFreeAsync(c->Q.consts, c->stream);
   cudaFreeAsync(c->d_flag, c->stream);
@@ -1280,7 +1333,8 @@ int vmx_ctx_set_tuning(vmx_ctx* c, const char* key, long long value) {
   else if (k == "mexp_window") {
     if (value != 0 && (value % kSubDigit != 0 || value > 16)) { set_error("mexp_window must be 0, 4, 8, 12 or 16"); return VMX_EARG; }
     c->mexp_window = (int)value;
-  } else if (k == "table_max_bytes") c->table_max_bytes = (size_t)value;
+  } else if (k == "big_cache_max") c->big_cache_max = (size_t)value;
+  else if (k == "table_max_bytes") c->table_max_bytes = (size_t)value;
   else if (k == "table_budget") c->table_budget = (size_t)value;
   else if (k == "fixed_window") return vmx_ctx_set_fixed_window(c, (int)value);
   else { set_error("unknown tuning key %s", key); return VMX_EARG; }
@@ -1579,7 +1633,7 @@ int vmx_garr_fill(vmx_ctx* c, size_t n, const uint8_t* elem_be, vmx_garr** out) 
 void vmx_garr_free(vmx_garr* a) {
   if (!a) return;
   cudaSetDevice(a->ctx->device);
-  if (a->d) cudaFreeAsync(a->d, a->ctx->stream);
+  if (a->d) dev_free(a->ctx, a->d, a->granted);
   delete a;
 }
 size_t vmx_garr_size(const vmx_garr* a) { return a ? a->n : 0; }
@@ -2225,7 +2279,7 @@ int vmx_rarr_fill(vmx_ctx* c, size_t n, const uint8_t* elem_be, vmx_rarr** out) 
 void vmx_rarr_free(vmx_rarr* a) {
   if (!a) return;
   cudaSetDevice(a->ctx->device);
-  if (a->d) cudaFreeAsync(a->d, a->ctx->stream);
+  if (a->d) dev_free(a->ctx, a->d, a->granted);
   delete a;
 }
 size_t vmx_rarr_size(const vmx_rarr* a) { return a ? a->n : 0; }

@@ -317,7 +317,8 @@ static int ec_seg_sum(vmx_ctx* c, const uint32_t* V, size_t vcap, int vjac, cons
                chunks.as<Chunk>(), nch_dev, part.d(), part.cap, c->ecc);
     VMX_CHECK_LAUNCH();
     std::swap(val_keep.p, part.p); std::swap(val_keep.c, part.c); std::swap(val_keep.cap, part.cap);
-    std::swap(off_keep.p, chunk_off.p); std::swap(off_keep.c, chunk_off.c);
+    std::swap(val_keep.granted, part.granted);
+    std::swap(off_keep.p, chunk_off.p); std::swap(off_keep.c, chunk_off.c); std::swap(off_keep.granted, chunk_off.granted);
     cur_V = val_keep.d();
     cur_vcap = val_keep.cap;
     cur_jac = 1;
@@ -465,7 +466,7 @@ static int ec_candidates(vmx_ctx* c, const uint8_t* d_raw, size_t m, size_t widt
   VMX_TRY(cand.alloc_limbs(c, m, kAffLimbs));
   VMX_TRY(ok.alloc(c, (m + 1) * 4));
   VMX_TRY(pos.alloc(c, (m + 1) * 4));
-  VMX_LAUNCH(c, k_ring_from_raw<8>, nblocks(m), kThreads, 0, d_raw, m, (int)width, (int)bitlen, xs.d(), xs.cap,
+  VMX_LAUNCH(c, k_ring_from_raw<8>, nblocks(m, codec_threads(width)), codec_threads(width), codec_smem(width), d_raw, m, (int)width, (int)bitlen, xs.d(), xs.cap,
              c->P.consts, 1, c->P.params<8>());
   VMX_CHECK_LAUNCH();
   VMX_CU(cudaMemsetAsync(ok.p, 0, (m + 1) * 4, c->stream));

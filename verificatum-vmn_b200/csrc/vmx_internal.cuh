@@ -93,6 +93,16 @@ struct vmx_ctx {
   size_t table_budget = (size_t)100e9;            // all cached tables together; beyond it the least recently used go
   size_t table_bytes = 0;                         // currently cached
   uint64_t table_clock = 0;
+  // Large device blocks (arrays and scratch of 32 MB and more) are recycled here instead of going back to the
+  // stream-ordered pool: a step allocates and frees the same ~40 sizes (384 MB arrays, GBs of Pippenger and
+  // window-table scratch) in an order that fragments the pool, and a fragmented pool answers with fresh physical
+  // memory -- one expProd in three took 1.46 s instead of 0.13 s at N = 10^6 (gpurun_out/s4_trace_device.json).
+  // All work of a context is on one stream, so a block freed by the host may be handed out again at once.
+  struct BigBlock { void* p; size_t bytes; };
+  std::vector<BigBlock> big_free;
+  std::mutex big_mu;
+  size_t big_free_bytes = 0;
+  size_t big_cache_max = (size_t)48e9;
   int* d_flag = nullptr;                          // device scratch: 4 ints
   int* h_flag = nullptr;                          // pinned scratch: 4 ints
   std::atomic<uint64_t> launches{0}, modmuls{0};
@@ -104,6 +114,7 @@ struct vmx_garr {
   vmx_ctx* ctx;
   size_t n, cap;
   uint32_t* d;
+  size_t granted = 0;  // bytes behind d as the allocator counted them (dev_alloc / dev_free)
 };
 
 struct vmx_rarr {
@@ -111,4 +122,5 @@ struct vmx_rarr {
   size_t n, cap;
   uint32_t* d;
   mutable int bits;  // cached max bit length, -1 = unknown
+  size_t granted = 0;
 };
