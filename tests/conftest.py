@@ -34,6 +34,9 @@ def vmx():
 
 @pytest.fixture(scope="session")
 def emul_lib():
+    # tools/asan_emul.sh points this at an AddressSanitizer / UBSan build of the same sources
+    if os.environ.get("VMX_EMUL_LIBRARY"):
+        return os.environ["VMX_EMUL_LIBRARY"]
     import __graft_entry__ as ge
     return ge.build_host_emul()
 
