@@ -640,7 +640,7 @@ def run_shuffle(args, env):
 OTHER_CONFIGS = [
     ("config3_verify_mix_3072", dict(workload="verify-mix", bits=3072, group="modp", width=1, n=100000)),
     ("config4_width3_2048", dict(workload="shuffle", bits=2048, group="modp", width=3, n=100000)),
-    ("config5_p256", dict(workload="shuffle", bits=3072, group="P-256", width=1, n=1000000)),
+    ("config5_p256", dict(workload="shuffle", bits=3072, group="P-256", width=1, n=10000000)),
 ]
 
 
