@@ -169,10 +169,17 @@ def install(G, threads: int | None = None):
         return vals
 
     ar.parse_array = parse_array
+    # single elements (A', C', D', F' of a commitment): the same Legendre-symbol test instead of a Python pow(x, q, p)
+    # per element (0.11 s each at 3072 bits -- a constant 0.6 s per step of the CPU arm)
+    had_contains = "contains" in G.__dict__
+    if G.p == 2 * G.q + 1:
+        G.contains = lambda x: 0 < x < G.p and acc.members([x])[0]
 
     def undo():
         ar.g_exp, ar.g_exp_prod, ar.g_mul = orig
         ar.parse_array = orig_parse
+        if not had_contains:
+            G.__dict__.pop("contains", None)
     return undo
 
 
