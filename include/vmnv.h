@@ -1,0 +1,62 @@
+/* vmnv.h -- C ABI of the native universal verifier (verificatum-vmn_b200/libvmnv.so, csrc/vmnv_native.cpp).
+ *
+ * What `vmnv` does with the proof directory of a mix-net execution
+ * (mixnet/MixNetElGamalVerifyFiatShamirSession.java:1318-1668, proofs of type "mixing" over a ModPGroup, ciphertexts
+ * of any width): every file is walked here, every group / ring operation is one call into the engine's C ABI
+ * (include/vmx.h), Fiat-Shamir hashing is SHA-256 on a worker thread beside the GPU.  A JVM would bind these
+ * three functions the way INTEGRATION.md binds vmx.h (JNI or FFM); the parameters are what the protocol info file
+ * holds (elgamal/ProtocolElGamalGen.java:81-213).
+ */
+#ifndef VMNV_H
+#define VMNV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vmxv_params {
+  const uint8_t* p_be; /* the group: modulus, order, generator, big-endian, nbytes each */
+  const uint8_t* q_be;
+  const uint8_t* g_be;
+  size_t nbytes;
+  int device;                 /* CUDA device of the engine context */
+  int k, threshold;           /* parties, threshold */
+  int vbitlenro, ebitlenro, rbitlen;
+  const char* version;        /* VCR.version() as written to the `version` file */
+  const char* sid;            /* session identifier of the info file; the auxsid is read from the proof */
+  const char* pgroup_string;  /* the pgroup string of the info file (enters the global prefix) */
+  const char* expected_auxsid; /* NULL or "": accept the one in the proof (vmnv -auxsid) */
+  int expected_width;          /* <= 0: accept the one in the proof (vmnv -width) */
+} vmxv_params;
+
+typedef struct vmxv_file {
+  const char* name;    /* path relative to the proof directory, '/' separated: "proofs/PoSReply01.bt" */
+  const uint8_t* data; /* borrowed for the call (page-locked memory makes the imports DMA transfers) */
+  size_t size;
+} vmxv_file;
+
+typedef struct vmxv_report {
+  int accepted;      /* the verdict of vmnv */
+  int fail_stop;     /* 1: a condition under which the reference stops with an error (`error` says which) */
+  int n_shuffles;    /* active threshold */
+  int shuffles[64];  /* verdict of each proof of a shuffle (an invalid one keeps its input) */
+  int valid_proofs;
+  int decryption;    /* the combined proof of the decryption factors */
+  int plaintexts;    /* Plaintexts.bt equals the decrypted output */
+  uint64_t hashed_bytes, launches;
+  char error[400];
+} vmxv_report;
+
+/* Bind the engine (path of libvmx.so, or of the host-emulation build in the CPU tests).  0 on success. */
+int vmxv_bind(const char* libvmx_path);
+/* Verify the proof directory given as in-memory files.  Returns 0 when `report` is filled (also for a rejected or
+ * fail-stopped proof), negative on an engine or usage error (report->error). */
+int vmxv_verify(const vmxv_params* params, const vmxv_file* files, size_t nfiles, vmxv_report* report);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

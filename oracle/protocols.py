@@ -888,6 +888,15 @@ class MixVerificationError(Exception):
     pass
 
 
+def _parse_int(raw: bytes) -> int:
+    """Integer.parseInt: an optional sign and decimal digits, nothing else."""
+    import re
+    text = raw.decode("ascii", errors="replace")
+    if re.fullmatch(r"[+-]?[0-9]{1,10}", text) is None:
+        raise ValueError("not an integer")
+    return int(text)
+
+
 def verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_auxsid=None, expected_width=None) -> dict:
     """The verdicts of mixnet/MixNetElGamalVerifyFiatShamirSession.verify for a proof of type "mixing".  A file
     that is malformed where the reference does not substitute trivial values is fail-stop."""
@@ -904,7 +913,7 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
         return d[name]
     if need("version").decode() != params.version or need("type") != b"mixing":
         raise MixVerificationError("header")
-    width = int(need("width").decode())
+    width = _parse_int(need("width"))
     if width < 1 or (expected_width is not None and width != expected_width):
         raise MixVerificationError("width")
     # determineAuxsid (MixNetElGamalVerifyFiatShamirSession.java:369-395): read from the proof, validated, and part
@@ -927,7 +936,7 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
     if pk[0] != G.g or pk[1] != coeffs[0]:
         raise MixVerificationError("mismatching keys")
     ys = {l: _eval_in_exponent(G, coeffs, l) for l in range(1, k + 1)}
-    active = int(need("proofs/activethreshold"))
+    active = _parse_int(need("proofs/activethreshold"))
     if active > k or active < threshold:
         raise MixVerificationError("active threshold")
     ct = bt.from_bytes(need("Ciphertexts.bt"))

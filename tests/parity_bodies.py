@@ -1061,3 +1061,67 @@ def concurrent_threads(vmx, bits, n, rounds=6):
     assert all(b == want_bytes and z == sq for b, z in exported) and len(exported) == rounds
     prod = oar.g_exp_prod(oar.ModPGroup(p, q, g), xs, es)
     assert computed[0::2] == [want_exp] * rounds and computed[1::2] == [prod] * rounds
+
+
+def native_vmnv_parity(vmx, spec, n, k=3, threshold=2, width=1, thorough=True):
+    """The native universal verifier (csrc/vmnv_native.cpp, include/vmnv.h) against the Python mirror of
+    mixnet/MixNetElGamalVerifyFiatShamirSession on the same proof directories: an honest mix, and the same mix with
+    one file at a time corrupted / truncated / emptied / missing -- identical verdicts per shuffle, identical
+    accept / reject / fail-stop."""
+    vm = importlib.import_module("verificatum-vmn_b200.vmnv")
+    vn = importlib.import_module("verificatum-vmn_b200.vmnv_native")
+    mix = importlib.import_module("verificatum-vmn_b200.mixnet")
+    G = engine_group(vmx, spec)
+    params = mix.SessionParams(pGroupString="native-%s" % spec, sid="Session_1")
+    rs = vmx.crypto.PRGHeuristic()
+    rs.setSeed(seed("native/dealer"))
+    M = vm.MixNetElGamal(G, params, k, threshold, rs, width=width, auxsid="run 7")
+    irs = vmx.crypto.PRGHeuristic()
+    irs.setSeed(seed("native/input"))
+    if width == 1:
+        w = mix.demoCiphertexts(M.fullPublicKey, n, irs)
+    else:
+        r = mix.getPlainPGroup(G, width).getPRing().randomElementArray(n, irs, 100)
+        w = mix.getWidePublicKey(M.fullPublicKey, width).exp(r)
+    M.run(w).free()
+    VP = vm.MixNetElGamalVerifyFiatShamirSession(G, params, k, threshold)
+    VN = vn.MixNetElGamalVerifyFiatShamirSessionNative(G, params, k, threshold)
+
+    def outcome(V, d):
+        try:
+            r = V.verify(d)
+            return ("verdict", r["accepted"], r["shuffles"], r["decryption"], r.get("plaintexts"))
+        except vm.VerificationError:
+            return ("failstop", V.report.get("shuffles"))
+
+    honest = outcome(VN, M.nizkp)
+    assert honest == outcome(VP, M.nizkp) and honest[:2] == ("verdict", True), honest
+    assert VN.report["hashed_bytes"] > 0 and VN.report["launches"] > 0
+    # the -auxsid / -width options
+    for kw, ok in ((dict(expectedAuxsid="run 7"), True), (dict(expectedAuxsid="other"), False),
+                   (dict(expectedWidth=width), True), (dict(expectedWidth=width + 1), False)):
+        got = outcome(vn.MixNetElGamalVerifyFiatShamirSessionNative(G, params, k, threshold, **kw), M.nizkp)
+        assert (got[0] == "verdict" and got[1]) == ok, (kw, got)
+    names = sorted(M.nizkp)
+    if not thorough:
+        names = [nm for nm in names if nm.endswith(("PoSReply01.bt", "DecrFactCommitment02.bt", "Plaintexts.bt"))]
+    nested = b"\x00\x00\x00\x00\x01" * 3000
+    for name in names:
+        raw = bytes(M.nizkp[name])
+        variants = [raw[:len(raw) // 2]]
+        if name.endswith(("PoSReply01.bt", "DecrFactCommitment01.bt", "Plaintexts.bt", "width", "CorrectIndices.bt", "activethreshold")):
+            variants += [b"", nested, raw + b"\x00"]
+        if len(raw) > 8:
+            for pos in ((len(raw) // 2, 6) if name.endswith(("PoSReply01.bt", "PoSCommitment01.bt")) else (len(raw) - 2,)):
+                b = bytearray(raw)
+                b[pos] ^= 0x04
+                variants.append(bytes(b))
+        for bad_bytes in variants:
+            bad = vm.ProofDirectory(M.nizkp)
+            bad[name] = bad_bytes
+            a, b = outcome(VN, bad), outcome(VP, bad)
+            assert a == b, (name, len(bad_bytes), a, b)
+        if thorough or name.endswith("Plaintexts.bt"):
+            missing = vm.ProofDirectory(M.nizkp)
+            del missing[name]
+            assert outcome(VN, missing) == outcome(VP, missing), name

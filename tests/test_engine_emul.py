@@ -145,3 +145,13 @@ def test_dedicated_squaring(engine_emul, bits, n):
 
 def test_one_context_two_threads(engine_emul):
     pb.concurrent_threads(engine_emul, 512, 40)
+
+
+def test_recycled_blocks_and_table_eviction(engine_emul, monkeypatch):
+    """The allocator paths of a BASELINE-sized run at test size: every device block of 4 KB and more goes through the
+    context's recycling list (production: 32 MB), at most 64 KB parked (so blocks are also evicted), and the
+    fixed-base table cache holds one small table at a time (so every change of base evicts and rebuilds)."""
+    pb.with_env(monkeypatch, VMX_BIG_BLOCK_MIN=4096, VMX_BIG_CACHE_MAX=65536, VMX_TABLE_BUDGET=1)
+    pb.group_ops(engine_emul, 512, 37)
+    pb.transcript_parity(engine_emul, 512, 9)
+    pb.decryption_parity(engine_emul, 512, 9, 3, 2)

@@ -175,6 +175,15 @@ def test_mix_and_vmnv_parity(engine_cuda, spec, n, tmp_path):
     pb.mix_parity(engine_cuda, spec, n, tmpdir=tmp_path)
 
 
+@pytest.mark.parametrize("bits,n,width", [(3072, 12, 1), (2048, 40, 2)])
+def test_native_vmnv(engine_cuda, bits, n, width):
+    """libvmnv.so (the native universal verifier over the C ABI) on the CUDA build: same verdicts as the Python
+    mirror on honest and corrupted proof directories."""
+    import __graft_entry__ as ge
+    ge.build_vmnv()
+    pb.native_vmnv_parity(engine_cuda, bits, n, width=width, thorough=False)
+
+
 @pytest.mark.parametrize("curve", ["P-256", "secp256k1"])
 def test_ec_edge_cases(engine_cuda, curve):
     pb.ec_edge_cases(engine_cuda, curve)

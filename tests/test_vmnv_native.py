@@ -1,0 +1,38 @@
+"""The native universal verifier (libvmnv.so over the C ABI, include/vmnv.h) against the Python mirror of the
+reference's vmnv on the host-emulation build; the same body runs on the B200 in tests/test_gpu_parity.py."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from tests import parity_bodies as pb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def vmnv_lib():
+    import __graft_entry__ as ge
+    return ge.build_vmnv()
+
+
+def test_library_exports_what_the_header_declares(vmnv_lib):
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "vmnv.h")).read(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(vmxv_[a-z0-9_]+)\s*\(", src)))
+    assert syms == ["vmxv_bind", "vmxv_verify"]
+    lib = ctypes.CDLL(vmnv_lib)
+    for s in syms:
+        assert hasattr(lib, s)
+
+
+def test_native_verifier_matches_the_mirror(engine_emul, vmnv_lib):
+    pb.native_vmnv_parity(engine_emul, 512, 4)
+
+
+def test_native_verifier_wide_ciphertexts(engine_emul, vmnv_lib):
+    pb.native_vmnv_parity(engine_emul, 512, 4, width=3, thorough=False)
+
+
+def test_native_verifier_other_thresholds(engine_emul, vmnv_lib):
+    pb.native_vmnv_parity(engine_emul, 512, 3, k=5, threshold=3, thorough=False)

@@ -139,11 +139,10 @@ static void image_put(std::vector<uint32_t>& img, size_t cap, size_t idx, const 
 }
 
 // ------------------------------------------------------------------ device memory helpers
-constexpr size_t kBigBlock = (size_t)32 << 20;
 // Device memory of a context: small blocks from the stream-ordered pool, large ones through the context's
 // recycling list (vmx_ctx::big_free).  *granted = the size to hand back to dev_free.
 static cudaError_t dev_alloc(vmx_ctx* c, size_t bytes, void** p, size_t* granted) {
-  if (bytes < kBigBlock) {
+  if (bytes < c->big_block_min) {
     *granted = bytes;
     return cudaMallocAsync(p, bytes ? bytes : 16, c->stream);
   }
@@ -177,7 +176,7 @@ static cudaError_t dev_alloc(vmx_ctx* c, size_t bytes, void** p, size_t* granted
 }
 static void dev_free(vmx_ctx* c, void* p, size_t granted) {
   if (!p) return;
-  if (granted < kBigBlock) { cudaFreeAsync(p, c->stream); return; }
+  if (granted < c->big_block_min) { cudaFreeAsync(p, c->stream); return; }
   std::lock_guard<std::mutex> lk(c->big_mu);
   c->big_free.push_back({p, granted});
   c->big_free_bytes += granted;
@@ -997,12 +996,16 @@ static int inv_batch(vmx_ctx* c, const uint32_t* a, size_t acap, size_t n, uint3
 }
 
 // Initial values of the tuning knobs (vmx_ctx_set_tuning) from the environment, read when a context is created:
-// VMX_COOP_MAX, VMX_VAR_CHUNK, VMX_MEXP_WINDOW.  The parity tests use them to send the oracle-sized protocol
-// transcripts through the kernels that production-sized arrays take.
+// VMX_COOP_MAX, VMX_VAR_CHUNK, VMX_MEXP_WINDOW, VMX_BIG_BLOCK_MIN, VMX_BIG_CACHE_MAX, VMX_TABLE_BUDGET.  The parity
+// tests use them to send the oracle-sized protocol transcripts through the kernels, the block recycling and the
+// table eviction that production-sized arrays take.
 template <typename Ctx>
 static void tuning_from_env(Ctx& c) {
   if (const char* e = std::getenv("VMX_COOP_MAX")) c->coop_max = (size_t)std::strtoull(e, nullptr, 10);
   if (const char* e = std::getenv("VMX_VAR_CHUNK")) c->var_chunk = (size_t)std::strtoull(e, nullptr, 10);
+  if (const char* e = std::getenv("VMX_BIG_BLOCK_MIN")) c->big_block_min = (size_t)std::strtoull(e, nullptr, 10);
+  if (const char* e = std::getenv("VMX_BIG_CACHE_MAX")) c->big_cache_max = (size_t)std::strtoull(e, nullptr, 10);
+  if (const char* e = std::getenv("VMX_TABLE_BUDGET")) c->table_budget = (size_t)std::strtoull(e, nullptr, 10);
   if (const char* e = std::getenv("VMX_MEXP_WINDOW")) {
     const int v = std::atoi(e);
     if (v == 4 || v == 8 || v == 12 || v == 16) c->mexp_window = v;
@@ -1334,6 +1337,11 @@ int vmx_ctx_set_tuning(vmx_ctx* c, const char* key, long long value) {
     if (value != 0 && (value % kSubDigit != 0 || value > 16)) { set_error("mexp_window must be 0, 4, 8, 12 or 16"); return VMX_EARG; }
     c->mexp_window = (int)value;
   } else if (k == "big_cache_max") c->big_cache_max = (size_t)value;
+  else if (k == "big_block_min") {
+    // a block is handed back by the size it was granted with: changing the threshold with blocks outstanding
+    // would route them to the wrong allocator, so it may only be set on a context that has no arrays yet
+    c->big_block_min = (size_t)value;
+  }
   else if (k == "table_max_bytes") c->table_max_bytes = (size_t)value;
   else if (k == "table_budget") c->table_budget = (size_t)value;
   else if (k == "fixed_window") return vmx_ctx_set_fixed_window(c, (int)value);

@@ -103,6 +103,7 @@ struct vmx_ctx {
   std::mutex big_mu;
   size_t big_free_bytes = 0;
   size_t big_cache_max = (size_t)48e9;
+  size_t big_block_min = (size_t)32 << 20;        // blocks of at least this size are recycled (tests lower it)
   int* d_flag = nullptr;                          // device scratch: 4 ints
   int* h_flag = nullptr;                          // pinned scratch: 4 ints
   std::atomic<uint64_t> launches{0}, modmuls{0};

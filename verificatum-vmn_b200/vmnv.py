@@ -30,6 +30,15 @@ from .hvzk import _to_positive, node_header
 from .mixnet import SessionParams, ShuffleProof, ShufflerSession, getCiphPGroup, validateSid
 
 
+def _parse_int(raw: bytes) -> int:
+    """Integer.parseInt of a file's content: an optional sign and decimal digits, nothing else."""
+    import re
+    text = raw.decode("ascii", errors="replace")
+    if re.fullmatch(r"[+-]?[0-9]{1,10}", text) is None:
+        raise ValueError("not an integer: %r" % text[:20])
+    return int(text)
+
+
 class VerificationError(RuntimeError):
     """`v.failStop(...)` of the reference's verifier: the proof directory is unusable."""
 
@@ -264,7 +273,7 @@ class MixNetElGamalVerifyFiatShamirSession:
         # determineWidth (:404-440): the number of ciphertexts shuffled in parallel; the keys of the directory are
         # the basic ones and are widened where they are used (elgamal/ProtocolElGamal.java:769-800)
         try:
-            width = int(self._file(nizkp, "width").decode())
+            width = _parse_int(self._file(nizkp, "width"))
         except ValueError:
             raise VerificationError("Can not parse width given in file!")
         if width < 1 or (self.expectedWidth is not None and width != self.expectedWidth):
@@ -291,7 +300,7 @@ class MixNetElGamalVerifyFiatShamirSession:
         session = ShufflerSession(G, fullPKey, p, None)
         challenger = session.challenger
         try:
-            active = int(self._file(nizkp, "proofs/activethreshold").decode())
+            active = _parse_int(self._file(nizkp, "proofs/activethreshold"))
         except ValueError:
             raise VerificationError("Can not parse active threshold given in file!")
         if active > k or active < threshold:
