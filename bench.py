@@ -295,6 +295,27 @@ def run_verify_mix(args, env):
                 "modmul": {"executed_per_ciphertext": modmuls / (args.steps * max(1, n_local)),
                            "executed_frac_of_imad_peak": modmuls * macs / (ms_per_step * args.steps * 1e-3) / IMAD_PEAK_MAC_PER_S},
                 "prover_s": prove_s, "proof_directory_bytes": nbytes}
+        if world == 1 and not is_curve(args):
+            # the same verification by the native pipeline (libvmnv.so: C++ over the C ABI, include/vmnv.h) from the
+            # same host bytes -- a reported extra; a failure here never costs the line above
+            try:
+                vn = importlib.import_module("verificatum-vmn_b200.vmnv_native")
+                VN = vn.MixNetElGamalVerifyFiatShamirSessionNative(G, params, 3, 2)
+                if not VN.verify(nizkp)["accepted"]:
+                    raise RuntimeError("the native verifier rejected an honest mix")
+                torch.cuda.synchronize()
+                t0 = time.time()
+                for _ in range(args.steps):
+                    VN.verify(nizkp)
+                torch.cuda.synchronize()
+                dt = (time.time() - t0) / args.steps
+                line["native_verifier"] = {"value": n / dt, "unit": "ciphertexts/s", "ms_per_step": dt * 1e3,
+                                           "gpu_launches_per_step": VN.report["launches"],
+                                           "hashed_bytes_per_step": VN.report["hashed_bytes"],
+                                           "what": "libvmnv.so: the whole verification in C++ over include/vmx.h, "
+                                                   "from the proof directory's bytes in host memory (wall clock)"}
+            except Exception as ex:
+                line["native_verifier"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
         if world == 1 and not args.no_cpu:
             try:
                 from oracle import cpu_baseline
@@ -673,7 +694,7 @@ def run_other_configs(args, env):
             line = {"error": "%s: %s" % (type(ex).__name__, ex)}
         if env.rank == 0 and line is not None:
             keep = ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "n_gpus", "scaling", "gpu_launches",
-                    "e2e", "modmul", "cold_first_step_ms", "error")
+                    "e2e", "modmul", "cold_first_step_ms", "native_verifier", "error")
             sub = {k: line[k] for k in keep if k in line}
             if "config" in line:
                 sub["workload"] = line["config"]["workload"]

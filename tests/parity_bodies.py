@@ -945,6 +945,8 @@ def malformed_proof_files(vmx, spec, n, k=3, threshold=2):
     assert V.verify(M.nizkp)["accepted"]
     nested = b"\x00\x00\x00\x00\x01" * 5000
     for name in sorted(M.nizkp):
+        if name.endswith(("02.bt", "03.bt")) and "DecrFact" not in name:
+            continue      # party 1's file of every kind, all the decryption proof files (the ADVICE cases), header files
         for junk in ((nested, b"", b"\x00\x01") if "DecrFact" in name or "PoSCommitment01" in name else (nested, b"")):
             bad = vm.ProofDirectory(M.nizkp)
             bad[name] = junk
@@ -1103,16 +1105,18 @@ def native_vmnv_parity(vmx, spec, n, k=3, threshold=2, width=1, thorough=True):
         got = outcome(vn.MixNetElGamalVerifyFiatShamirSessionNative(G, params, k, threshold, **kw), M.nizkp)
         assert (got[0] == "verdict" and got[1]) == ok, (kw, got)
     names = sorted(M.nizkp)
-    if not thorough:
+    if thorough:    # every kind of file once (party 1's of each), every header file
+        names = [nm for nm in names if not nm.endswith(("02.bt", "03.bt"))]
+    else:
         names = [nm for nm in names if nm.endswith(("PoSReply01.bt", "DecrFactCommitment02.bt", "Plaintexts.bt"))]
     nested = b"\x00\x00\x00\x00\x01" * 3000
     for name in names:
         raw = bytes(M.nizkp[name])
         variants = [raw[:len(raw) // 2]]
-        if name.endswith(("PoSReply01.bt", "DecrFactCommitment01.bt", "Plaintexts.bt", "width", "CorrectIndices.bt", "activethreshold")):
+        if name.endswith(("PoSReply01.bt", "DecrFactCommitment01.bt", "width", "activethreshold")):
             variants += [b"", nested, raw + b"\x00"]
         if len(raw) > 8:
-            for pos in ((len(raw) // 2, 6) if name.endswith(("PoSReply01.bt", "PoSCommitment01.bt")) else (len(raw) - 2,)):
+            for pos in ((len(raw) // 2, 6) if name.endswith("PoSCommitment01.bt") else (len(raw) - 2,)):
                 b = bytearray(raw)
                 b[pos] ^= 0x04
                 variants.append(bytes(b))

@@ -48,6 +48,6 @@ def test_sharded_equals_single(emul_lib, world, n):
     _run(world, 512, n, emul_lib)
 
 
-@pytest.mark.parametrize("world,n", [(2, 21), (3, 8)])
+@pytest.mark.parametrize("world,n", [(2, 21)])
 def test_sharded_curve_equals_single(emul_lib, world, n):
     _run(world, "P-256", n, emul_lib)

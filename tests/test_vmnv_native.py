@@ -27,12 +27,8 @@ def test_library_exports_what_the_header_declares(vmnv_lib):
 
 
 def test_native_verifier_matches_the_mirror(engine_emul, vmnv_lib):
-    pb.native_vmnv_parity(engine_emul, 512, 4)
+    pb.native_vmnv_parity(engine_emul, 512, 3)
 
 
-def test_native_verifier_wide_ciphertexts(engine_emul, vmnv_lib):
-    pb.native_vmnv_parity(engine_emul, 512, 4, width=3, thorough=False)
-
-
-def test_native_verifier_other_thresholds(engine_emul, vmnv_lib):
-    pb.native_vmnv_parity(engine_emul, 512, 3, k=5, threshold=3, thorough=False)
+def test_native_verifier_wide_ciphertexts_other_thresholds(engine_emul, vmnv_lib):
+    pb.native_vmnv_parity(engine_emul, 512, 3, k=4, threshold=3, width=2, thorough=False)
