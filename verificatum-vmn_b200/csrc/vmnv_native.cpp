@@ -45,7 +45,7 @@ namespace {
   X(vmx_garr_prg_sha256) X(vmx_exp_fixed) X(vmx_elem_exp) X(vmx_elem_inv) X(vmx_exp_scalar_var) X(vmx_expprod)     \
   X(vmx_expprod_cols) X(vmx_mul) X(vmx_inv) X(vmx_prod) X(vmx_shift_push) X(vmx_equals) X(vmx_get)                 \
   X(vmx_rarr_from_leaves) X(vmx_rarr_from_bytes) X(vmx_rarr_to_bytes) X(vmx_rarr_prg_sha256) X(vmx_rarr_free)      \
-  X(vmx_rprod) X(vmx_rmul) X(vmx_radd) X(vmx_leaves_uniform) X(vmx_ctx_launch_count)
+  X(vmx_rprod) X(vmx_rmul) X(vmx_radd) X(vmx_leaves_uniform) X(vmx_ctx_launch_count) X(vmx_fixed_precompute)
 
 struct Api {
 #define X(name) decltype(&::name) name = nullptr;
@@ -521,7 +521,8 @@ std::vector<Elem> expprod_many(const Ctx& C, const std::vector<const Garr*>& arr
 
 // ------------------------------------------------------------------------------------------------ the session
 struct Session {
-  Ctx C;
+  Ctx& C;
+  explicit Session(Ctx& c) : C(c) {}
   const vmxv_params* P;
   std::map<std::string, Span> files;
   Bytes prefix;  // rho
@@ -539,8 +540,8 @@ struct Session {
   Bytes challenge_finish(Oracle& o) { Bytes r = o.finish(); hashed += o.hashed; return r; }
 
   // ---- hvzk/PoSTW.java:177-260 over hvzk/PoSBasicTW.java: one proof of a shuffle
-  bool verify_shuffle(const Garr& h, const Elem& h0, size_t n, const CiphArr& w, const CiphArr& wp, Span wFile, Span wpFile,
-                      Span pcFile, Span commitFile, Span replyFile, const Elem& y);
+  bool verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n, const CiphArr& w, const CiphArr& wp, Span wFile,
+                      Span wpFile, Span pcFile, Span commitFile, Span replyFile, const Elem& y);
 
   void run(vmxv_report* rep);
 };
@@ -556,8 +557,8 @@ bool parse_int_strict(const std::string& s, long* out) {
 
 std::string two(int l) { char b[16]; snprintf(b, sizeof b, "%02d", l); return b; }
 
-bool Session::verify_shuffle(const Garr& h, const Elem& h0, size_t n, const CiphArr& w, const CiphArr& wp, Span wFile,
-                             Span wpFile, Span pcFile, Span commitFile, Span replyFile, const Elem& y) {
+bool Session::verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n, const CiphArr& w, const CiphArr& wp,
+                             Span wFile, Span wpFile, Span pcFile, Span commitFile, Span replyFile, const Elem& y) {
   const int W = width, K = 2 * W;
   std::vector<std::unique_ptr<Bytes>> store;  // serialisations that must outlive the hashing
   // permutation commitment u (PoSBasicTW.java:505-514); malformed -> the generators themselves
@@ -576,7 +577,7 @@ bool Session::verify_shuffle(const Garr& h, const Elem& h0, size_t n, const Ciph
   Oracle seedO(prefix, 256);
   seedO.update_owned(header(NODE, 6));
   seedO.update_owned(elem_tree(C.g));
-  seedO.update(garr_tree(C, h, n, store));
+  seedO.update(hTree);
   if (u_from_file && pcFile.n == garr_tree_bytes(C, n)) seedO.update(pcFile); else seedO.update(garr_tree(C, u, n, store));
   seedO.update_owned(header(NODE, 2));
   {
@@ -808,6 +809,10 @@ void Session::run(vmxv_report* rep) {
     fail_stop("Unable to read polynomial in exponent from file!");
   }
   if (coeffs[0] != y) fail_stop("Mismatching public keys!");
+  // window tables of the bases every proof raises to full-length exponents: g (arrays and single elements), the
+  // public key y and h0 (single elements: a small table turns a 3071-step ladder on one warp, ~20 ms, into a few
+  // multiplications per thread); they stay with the cached context for the next verification
+  check(api.vmx_fixed_precompute(C.c, y.data(), 16), "vmx_fixed_precompute");
   std::vector<Elem> pkeys((size_t)k + 1);
   for (int l = 1; l <= k; l++) {  // PolynomialInExponent.evaluate(l)
     Elem acc = coeffs[0];
@@ -867,6 +872,35 @@ void Session::run(vmxv_report* rep) {
     h = Garr(a);
   }
   const Elem h0 = elem_get(C, h, 0);
+  check(api.vmx_fixed_precompute(C.c, C.g.data(), n), "vmx_fixed_precompute");
+  check(api.vmx_fixed_precompute(C.c, h0.data(), 16), "vmx_fixed_precompute");
+  std::vector<std::unique_ptr<Bytes>> hStore;
+  const Span hTree = garr_tree(C, h, n, hStore);   // the generators are hashed into the seed of every proof
+  // The seed of the decryption proof is RO(node(node(g, L_active), node(node(coeffs), node(f_1..f_k)))) (:1586-1600):
+  // it depends on files only, so it is hashed on its worker thread WHILE the shuffles are verified, on the premise
+  // that the last shuffle is valid and the files canonical; checked below, hashed again if it does not hold.
+  std::unique_ptr<Oracle> spec;
+  std::string lastName = "proofs/Ciphertexts" + two(active) + ".bt";
+  if (!has(lastName)) lastName = "ShuffledCiphertexts.bt";
+  {
+    bool all = has(lastName) && files[lastName].n == ciph_arr_tree_bytes(C, W, n);
+    for (int l = 1; l <= k && all; l++) {
+      const std::string nm = "proofs/DecryptionFactors" + two(l) + ".bt";
+      all = has(nm) && files[nm].n == plain_arr_tree_bytes(C, W, n);
+    }
+    if (all) {
+      spec = std::make_unique<Oracle>(prefix, 256);
+      spec->update_owned(header(NODE, 2));
+      spec->update_owned(header(NODE, 2));
+      spec->update_owned(elem_tree(C.g));
+      spec->update(files[lastName]);
+      spec->update_owned(header(NODE, 2));
+      spec->update_owned(header(NODE, (uint32_t)coeffs.size()));
+      for (const Elem& c : coeffs) spec->update_owned(elem_tree(c));
+      spec->update_owned(header(NODE, (uint32_t)k));
+      for (int l = 1; l <= k; l++) spec->update(files["proofs/DecryptionFactors" + two(l) + ".bt"]);
+    }
+  }
   // ---- shuffles (:1403-1520)
   const CiphArr* inp = &ciphertexts;
   Span inpFile = ctFile;
@@ -881,7 +915,7 @@ void Session::run(vmxv_report* rep) {
     const Span rp = file("proofs/PoSReply" + two(l) + ".bt");
     const Span outFile = file(name);
     outputs.push_back(read_ciph(outFile, name));   // fail-stop if malformed; an invalid PROOF keeps the input
-    const bool ok = verify_shuffle(h, h0, n, *inp, outputs.back(), inpFile, outFile, pc, cm, rp, y);
+    const bool ok = verify_shuffle(h, hTree, h0, n, *inp, outputs.back(), inpFile, outFile, pc, cm, rp, y);
     rep->shuffles[l - 1] = ok ? 1 : 0;
     rep->n_shuffles = l;
     valid += ok ? 1 : 0;
@@ -934,20 +968,26 @@ void Session::run(vmxv_report* rep) {
   }
   // seed = RO(rho || node(node(g, L), node(node(coeffs), node(f_1 .. f_k))))  (:1586-1600)
   std::vector<std::unique_ptr<Bytes>> store;
-  Oracle seedO(prefix, 256);
-  seedO.update_owned(header(NODE, 2));
-  seedO.update_owned(header(NODE, 2));
-  seedO.update_owned(elem_tree(C.g));
-  if (inpFile.n == ciph_arr_tree_bytes(C, W, n)) seedO.update(inpFile); else hash_ciph_arr(C, seedO, mixed, W, n, store);
-  seedO.update_owned(header(NODE, 2));
-  seedO.update_owned(header(NODE, (uint32_t)coeffs.size()));
-  for (const Elem& c : coeffs) seedO.update_owned(elem_tree(c));
-  seedO.update_owned(header(NODE, (uint32_t)k));
-  for (int l = 1; l <= k; l++) {
-    if (fFile[(size_t)l].n == plain_arr_tree_bytes(C, W, n)) seedO.update(fFile[(size_t)l]);
-    else hash_plain_arr(C, seedO, f[(size_t)l].c, 0, W, n, store);
+  Bytes prgSeed;
+  if (spec && inpFile.p == files[lastName].p) {   // the premise held: the mixed list IS the last output file
+    prgSeed = challenge_finish(*spec);
+  } else {
+    spec.reset();   // (joins its worker)
+    Oracle seedO(prefix, 256);
+    seedO.update_owned(header(NODE, 2));
+    seedO.update_owned(header(NODE, 2));
+    seedO.update_owned(elem_tree(C.g));
+    if (inpFile.n == ciph_arr_tree_bytes(C, W, n)) seedO.update(inpFile); else hash_ciph_arr(C, seedO, mixed, W, n, store);
+    seedO.update_owned(header(NODE, 2));
+    seedO.update_owned(header(NODE, (uint32_t)coeffs.size()));
+    for (const Elem& c : coeffs) seedO.update_owned(elem_tree(c));
+    seedO.update_owned(header(NODE, (uint32_t)k));
+    for (int l = 1; l <= k; l++) {
+      if (fFile[(size_t)l].n == plain_arr_tree_bytes(C, W, n)) seedO.update(fFile[(size_t)l]);
+      else hash_plain_arr(C, seedO, f[(size_t)l].c, 0, W, n, store);
+    }
+    prgSeed = challenge_finish(seedO);
   }
-  const Bytes prgSeed = challenge_finish(seedO);
   vmx_rarr* eh = nullptr;
   check(api.vmx_rarr_prg_sha256(C.c, prgSeed.data(), prgSeed.size(), 0, n, (unsigned)P->ebitlenro, &eh), "vmx_rarr_prg_sha256");
   Rarr e(eh);
@@ -1041,25 +1081,40 @@ int vmxv_verify(const vmxv_params* P, const vmxv_file* files, size_t nfiles, vmx
   std::memset(rep, 0, sizeof *rep);
   if (!api.handle) { snprintf(rep->error, sizeof rep->error, "vmxv_bind was not called"); return -1; }
   try {
-    Session S;
-    S.P = P;
-    vmx_ctx* c = nullptr;
-    if (api.vmx_ctx_create_modp(P->p_be, P->q_be, P->g_be, P->nbytes, P->device, &c) != VMX_OK) {
-      snprintf(rep->error, sizeof rep->error, "context: %s", api.vmx_last_error());
-      return -1;
+    // engine contexts are kept between calls (keyed by modulus and device): their fixed-base tables and recycled
+    // blocks serve the next verification over the same group, as one vmnv process verifying several proofs would
+    static std::mutex cache_mu;
+    // never destroyed: at process exit the CUDA runtime may already be gone when static destructors run
+    static auto& cache = *new std::map<std::string, std::unique_ptr<Ctx>>();
+    std::unique_lock<std::mutex> cache_lock(cache_mu);   // one verification at a time per process
+    const std::string key = std::string((const char*)P->p_be, P->nbytes) + std::string((const char*)P->g_be, P->nbytes) +
+                            "#" + std::to_string(P->device);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      vmx_ctx* c = nullptr;
+      if (api.vmx_ctx_create_modp(P->p_be, P->q_be, P->g_be, P->nbytes, P->device, &c) != VMX_OK) {
+        snprintf(rep->error, sizeof rep->error, "context: %s", api.vmx_last_error());
+        return -1;
+      }
+      auto ctx = std::make_unique<Ctx>();
+      ctx->c = c;
+      ctx->eb = api.vmx_ctx_elem_bytes(c);
+      ctx->rb = api.vmx_ctx_ring_bytes(c);
+      auto fit = [](const uint8_t* be, size_t nbytes, size_t w) {
+        Bytes out(w, 0);
+        for (size_t i = 0; i < nbytes && i < w; i++) out[w - 1 - i] = be[nbytes - 1 - i];
+        return out;
+      };
+      ctx->q = fit(P->q_be, P->nbytes, ctx->rb);
+      ctx->g = fit(P->g_be, P->nbytes, ctx->eb);
+      ctx->one = Bytes(ctx->eb, 0);
+      ctx->one.back() = 1;
+      if (cache.size() >= 4) cache.clear();   // a verifier sees one group, a test suite a few
+      it = cache.emplace(key, std::move(ctx)).first;
     }
-    S.C.c = c;
-    S.C.eb = api.vmx_ctx_elem_bytes(c);
-    S.C.rb = api.vmx_ctx_ring_bytes(c);
-    auto fit = [](const uint8_t* be, size_t nbytes, size_t w) {
-      Bytes out(w, 0);
-      for (size_t i = 0; i < nbytes && i < w; i++) out[w - 1 - i] = be[nbytes - 1 - i];
-      return out;
-    };
-    S.C.q = fit(P->q_be, P->nbytes, S.C.rb);
-    S.C.g = fit(P->g_be, P->nbytes, S.C.eb);
-    S.C.one = Bytes(S.C.eb, 0);
-    S.C.one.back() = 1;
+    Session S(*it->second);
+    S.P = P;
+    vmx_ctx* c = S.C.c;
     for (size_t i = 0; i < nfiles; i++) S.files[files[i].name] = Span(files[i].data, files[i].size);
     const uint64_t l0 = api.vmx_ctx_launch_count(c);
     try {
