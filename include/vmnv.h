@@ -1,8 +1,8 @@
 /* vmnv.h -- C ABI of the native universal verifier (verificatum-vmn_b200/libvmnv.so, csrc/vmnv_native.cpp).
  *
  * What `vmnv` does with the proof directory of a mix-net execution
- * (mixnet/MixNetElGamalVerifyFiatShamirSession.java:1318-1668, proofs of type "mixing" over a ModPGroup, ciphertexts
- * of any width): every file is walked here, every group / ring operation is one call into the engine's C ABI
+ * (mixnet/MixNetElGamalVerifyFiatShamirSession.java:1318-1668, proofs of type "mixing" over a ModPGroup or an ECqPGroup,
+ * ciphertexts of any width): every file is walked here, every group / ring operation is one call into the engine's C ABI
  * (include/vmx.h), Fiat-Shamir hashing is SHA-256 on a worker thread beside the GPU.  A JVM would bind these
  * three functions the way INTEGRATION.md binds vmx.h (JNI or FFM); the parameters are what the protocol info file
  * holds (elgamal/ProtocolElGamalGen.java:81-213).
@@ -18,9 +18,13 @@ extern "C" {
 #endif
 
 typedef struct vmxv_params {
-  const uint8_t* p_be; /* the group: modulus, order, generator, big-endian, nbytes each */
+  int kind;            /* 0: ModPGroup (p, q, g); 1: ECqPGroup y^2 = x^3 + a x + b over F_p, generator (g, gy) of order q */
+  const uint8_t* p_be; /* big-endian, nbytes each */
   const uint8_t* q_be;
-  const uint8_t* g_be;
+  const uint8_t* g_be; /* the generator (its x coordinate on a curve) */
+  const uint8_t* a_be; /* curve only (else NULL) */
+  const uint8_t* b_be;
+  const uint8_t* gy_be;
   size_t nbytes;
   int device;                 /* CUDA device of the engine context */
   int k, threshold;           /* parties, threshold */

@@ -13,6 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def vmnv_lib():
+    if os.environ.get("VMNV_LIBRARY_PATH"):   # tools/asan_emul.sh: the sanitizer build of the same source
+        return os.environ["VMNV_LIBRARY_PATH"]
     import __graft_entry__ as ge
     return ge.build_vmnv()
 
@@ -32,3 +34,9 @@ def test_native_verifier_matches_the_mirror(engine_emul, vmnv_lib):
 
 def test_native_verifier_wide_ciphertexts_other_thresholds(engine_emul, vmnv_lib):
     pb.native_vmnv_parity(engine_emul, 512, 3, k=4, threshold=3, width=2, thorough=False)
+
+
+def test_native_verifier_curve_group(engine_emul, vmnv_lib):
+    """ECqPGroup proofs: points as node(x, y), arrays as node(x leaves, y leaves), on-curve checks by the engine."""
+    pb.native_vmnv_parity(engine_emul, "P-256", 4, thorough=False)
+    pb.native_vmnv_parity(engine_emul, "P-256", 3, width=2, thorough=False)

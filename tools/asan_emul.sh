@@ -10,8 +10,11 @@ cd "$(dirname "$0")/.."
 mkdir -p build/asan
 ( cd verificatum-vmn_b200/csrc && g++ -std=c++17 -O1 -g -fno-omit-frame-pointer -fsanitize=address,undefined \
     -fno-sanitize-recover=undefined -DVMX_HOST_EMUL -x c++ -fPIC -shared -o ../../build/asan/libvmx_emul_asan.so vmx.cu )
+( cd verificatum-vmn_b200/csrc && g++ -std=c++17 -O1 -g -fno-omit-frame-pointer -fsanitize=address,undefined \
+    -fno-sanitize-recover=undefined -fPIC -shared -o ../../build/asan/libvmnv_asan.so vmnv_native.cpp -ldl -lcrypto -lpthread )
 export VMX_EMUL_LIBRARY=$PWD/build/asan/libvmx_emul_asan.so
+export VMNV_LIBRARY_PATH=$PWD/build/asan/libvmnv_asan.so
 export LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)"
 export ASAN_OPTIONS=detect_leaks=0:abort_on_error=0:halt_on_error=1
 export UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1
-python -m pytest tests/test_engine_emul.py -x -q -p no:cacheprovider "$@"
+python -m pytest tests/test_engine_emul.py tests/test_vmnv_native.py -x -q -p no:cacheprovider "$@"

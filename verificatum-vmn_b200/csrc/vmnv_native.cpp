@@ -4,7 +4,7 @@
 //     hvzk/PoSTW.java:177-260 + hvzk/PoSBasicTW.java:505-514,780-823,970-1066  (proof of a shuffle, verifier)
 //     elgamal/DistrElGamalSessionBasic.java:465-727                (combination and batched proof of decryption factors)
 //     hvzk/ChallengerRO.java:96-116, distr/IndependentGeneratorsRO.java:110-130, elgamal/ProtocolElGamal.java:659-683
-// do with a proof of type "mixing" over a ModPGroup, for ciphertexts of any width, written against nothing but
+// do with a proof of type "mixing" over a ModPGroup or an ECqPGroup, for ciphertexts of any width, written against nothing but
 // the engine's C entry points: byte trees are walked here (headers only -- the engine validates every leaf of an
 // array on the device), Fiat-Shamir hashing is OpenSSL's SHA-256 on a worker thread beside the GPU, every group
 // and ring operation is one vmx_* call.  The Python mirror (verificatum-vmn_b200/vmnv.py) is the specification it
@@ -40,11 +40,11 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------ engine binding
 #define VMXV_SYMBOLS(X)                                                                                             \
-  X(vmx_last_error) X(vmx_ctx_create_modp) X(vmx_ctx_destroy) X(vmx_ctx_elem_bytes) X(vmx_ctx_ring_bytes)          \
+  X(vmx_last_error) X(vmx_ctx_create_modp) X(vmx_ctx_create_ecq) X(vmx_ctx_destroy) X(vmx_ctx_elem_bytes) X(vmx_ctx_ring_bytes)          \
   X(vmx_garr_from_leaves) X(vmx_garr_to_leaves) X(vmx_garr_fill) X(vmx_garr_free) X(vmx_garr_size)                 \
   X(vmx_garr_prg_sha256) X(vmx_exp_fixed) X(vmx_elem_exp) X(vmx_elem_inv) X(vmx_exp_scalar_var) X(vmx_expprod)     \
   X(vmx_expprod_cols) X(vmx_mul) X(vmx_inv) X(vmx_prod) X(vmx_shift_push) X(vmx_equals) X(vmx_get)                 \
-  X(vmx_rarr_from_leaves) X(vmx_rarr_from_bytes) X(vmx_rarr_to_bytes) X(vmx_rarr_prg_sha256) X(vmx_rarr_free)      \
+  X(vmx_rarr_from_leaves) X(vmx_rarr_from_bytes) X(vmx_rarr_to_bytes) X(vmx_rarr_prg_sha256) X(vmx_rarr_prg_raw_sha256) X(vmx_rarr_free)      \
   X(vmx_rprod) X(vmx_rmul) X(vmx_radd) X(vmx_leaves_uniform) X(vmx_ctx_launch_count) X(vmx_fixed_precompute)
 
 struct Api {
@@ -262,6 +262,8 @@ class Oracle {
 struct Ctx {
   vmx_ctx* c = nullptr;
   size_t eb = 0, rb = 0;
+  bool curve = false;  // ECqPGroup: an element is a point x || y (two coordinates of cb = eb / 2 bytes, the unit
+  size_t cb = 0;       // element all 0xff); on the wire node(leaf x, leaf y), an array node(node(x leaves), node(y leaves))
   Bytes q, g, one;  // big-endian, rb / eb / eb bytes
   ~Ctx() { if (c) api.vmx_ctx_destroy(c); }
 };
@@ -397,15 +399,32 @@ Elem arr_prod(const Ctx& C, const Garr& a) {
   return r;
 }
 
-// a single group element out of a leaf: length, range and membership as PGroup.toElement (the engine's import of a
-// one-element array checks all three)
-Elem parse_elem(const Ctx& C, Span leaf) {
-  const Hdr h = read_hdr(leaf, 0);
-  if (h.kind != LEAF || h.count != C.eb || leaf.n < 5 + C.eb) throw Malformed("group element of wrong length");
+// a single group element: length, range and membership as PGroup.toElement (the engine's import of a one-element
+// array checks all three; a curve point arrives as node(leaf x, leaf y) and is checked against the curve equation)
+Elem parse_elem(const Ctx& C, Span t) {
+  if (C.curve) {
+    const std::vector<Span> xy = children(t, 2);
+    const Span x = leaf_payload(xy[0], C.cb), y = leaf_payload(xy[1], C.cb);
+    Bytes buf;   // the array form of one point: node(1 leaf x), node(1 leaf y)
+    for (Span c : {x, y}) {
+      const Bytes n1 = header(NODE, 1), lf = header(LEAF, (uint32_t)C.cb);
+      buf.insert(buf.end(), n1.begin(), n1.end());
+      buf.insert(buf.end(), lf.begin(), lf.end());
+      buf.insert(buf.end(), c.p, c.p + c.n);
+    }
+    vmx_garr* a = nullptr;
+    check(api.vmx_garr_from_leaves(C.c, 1, buf.data(), 1, &a), "point");
+    Garr g(a);
+    Elem e(x.p, x.p + x.n);
+    e.insert(e.end(), y.p, y.p + y.n);
+    return e;
+  }
+  const Hdr h = read_hdr(t, 0);
+  if (h.kind != LEAF || h.count != C.eb || t.n < 5 + C.eb) throw Malformed("group element of wrong length");
   vmx_garr* a = nullptr;
-  check(api.vmx_garr_from_leaves(C.c, 1, leaf.p, 1, &a), "element");
+  check(api.vmx_garr_from_leaves(C.c, 1, t.p, 1, &a), "element");
   Garr g(a);
-  return Elem(leaf.p + 5, leaf.p + 5 + C.eb);
+  return Elem(t.p + 5, t.p + 5 + C.eb);
 }
 Scalar parse_scalar(const Ctx& C, Span leaf) {
   const Span v = leaf_payload(leaf, C.rb);
@@ -413,11 +432,15 @@ Scalar parse_scalar(const Ctx& C, Span leaf) {
   if (cmp_be(s, C.q) >= 0) throw Malformed("ring element out of range");
   return s;
 }
-// an array of `n` group elements out of node(n leaves): headers, range and membership are checked on the device
+// bytes of the serialised leaves of an array of n elements as the engine reads / writes them
+size_t garr_leaves_bytes(const Ctx& C, size_t n) { return C.curve ? 2 * (5 + n * (5 + C.cb)) : n * (5 + C.eb); }
+// an array of `n` group elements out of node(n leaves) -- over a curve node(node(n x leaves), node(n y leaves)):
+// inner headers, leaf headers, range and membership are checked on the device
 Garr parse_garr(const Ctx& C, Span node, size_t n) {
   const Hdr h = read_hdr(node, 0);
-  if (h.kind != NODE || h.count != n) throw Malformed("array of the wrong size");
-  const size_t bytes = n * (5 + C.eb);
+  if (h.kind != NODE || h.count != (C.curve ? 2 : n)) throw Malformed("array of the wrong size");
+  if (C.curve && n > (node.n / 2)) throw Malformed("truncated array");
+  const size_t bytes = garr_leaves_bytes(C, n);
   if (node.n < 5 + bytes) throw Malformed("truncated array");
   vmx_garr* a = nullptr;
   check(api.vmx_garr_from_leaves(C.c, n, node.p + 5, 1, &a), "array");
@@ -432,22 +455,33 @@ Rarr parse_rarr(const Ctx& C, Span node, size_t n) {
   check(api.vmx_rarr_from_leaves(C.c, n, node.p + 5, &a), "ring array");
   return Rarr(a);
 }
-size_t garr_tree_bytes(const Ctx& C, size_t n) { return 5 + n * (5 + C.eb); }
+size_t garr_tree_bytes(const Ctx& C, size_t n) { return 5 + garr_leaves_bytes(C, n); }
 
 // serialisation of an array the way toByteTree() writes it (node header + leaves), kept in `store`
 Span garr_tree(const Ctx& C, const Garr& a, size_t n, std::vector<std::unique_ptr<Bytes>>& store) {
   auto buf = std::make_unique<Bytes>(garr_tree_bytes(C, n));
   (*buf)[0] = NODE;
-  put_be32(buf->data() + 1, (uint32_t)n);
-  if (n) check(api.vmx_garr_to_leaves(a.h, buf->data() + 5), "vmx_garr_to_leaves");
+  put_be32(buf->data() + 1, (uint32_t)(C.curve ? 2 : n));
+  if (n || C.curve) check(api.vmx_garr_to_leaves(a.h, buf->data() + 5), "vmx_garr_to_leaves");
   store.push_back(std::move(buf));
   return Span(store.back()->data(), store.back()->size());
 }
-Bytes elem_tree(const Elem& e) {
+Bytes leaf_tree(const Bytes& e) {
   Bytes t = header(LEAF, (uint32_t)e.size());
   t.insert(t.end(), e.begin(), e.end());
   return t;
 }
+Bytes elem_tree(const Ctx& C, const Elem& e) {
+  if (!C.curve) return leaf_tree(e);
+  Bytes t = header(NODE, 2);
+  for (int half = 0; half < 2; half++) {
+    const Bytes lf = header(LEAF, (uint32_t)C.cb);
+    t.insert(t.end(), lf.begin(), lf.end());
+    t.insert(t.end(), e.begin() + (long)(half * C.cb), e.begin() + (long)((half + 1) * C.cb));
+  }
+  return t;
+}
+size_t elem_tree_bytes(const Ctx& C) { return C.curve ? 5 + 2 * (5 + C.cb) : 5 + C.eb; }
 Garr garr_fill(const Ctx& C, size_t n, const Elem& e) {
   vmx_garr* a = nullptr;
   check(api.vmx_garr_fill(C.c, n, e.data(), &a), "vmx_garr_fill");
@@ -493,9 +527,9 @@ PlainElem parse_plain_elem(const Ctx& C, Span s, int width) {
 size_t plain_arr_tree_bytes(const Ctx& C, int width, size_t n) { return width == 1 ? garr_tree_bytes(C, n) : 5 + width * garr_tree_bytes(C, n); }
 size_t ciph_arr_tree_bytes(const Ctx& C, int width, size_t n) { return 5 + 2 * plain_arr_tree_bytes(C, width, n); }
 
-void hash_plain_elem(Oracle& o, const PlainElem& e) {
+void hash_plain_elem(const Ctx& C, Oracle& o, const PlainElem& e) {
   if (e.size() > 1) o.update_owned(header(NODE, (uint32_t)e.size()));
-  for (const Elem& x : e) o.update_owned(elem_tree(x));
+  for (const Elem& x : e) o.update_owned(elem_tree(C, x));
 }
 void hash_plain_arr(const Ctx& C, Oracle& o, const std::vector<Garr>& comps, size_t first, int width, size_t n,
                     std::vector<std::unique_ptr<Bytes>>& store) {
@@ -506,6 +540,17 @@ void hash_ciph_arr(const Ctx& C, Oracle& o, const CiphArr& a, int width, size_t 
   o.update_owned(header(NODE, 2));
   hash_plain_arr(C, o, a.c, 0, width, n, store);
   hash_plain_arr(C, o, a.c, (size_t)width, width, n, store);
+}
+
+// the batching vector of a proof: n integers of `bits` bits from PRG(seed) as elements of Z_q
+// (hvzk/PoSBasicTW.java:533-538); integers as wide as q (a 256-bit curve order) are reduced as they are drawn
+Rarr batch_vector(const Ctx& C, const Bytes& seed, size_t n, unsigned bits) {
+  size_t qbits = 8 * C.q.size();
+  for (size_t i = 0; i < C.q.size(); i++) if (C.q[i]) { qbits = 8 * (C.q.size() - i); for (uint8_t v = C.q[i]; !(v & 0x80); v <<= 1) qbits--; break; }
+  vmx_rarr* h = nullptr;
+  if (bits < qbits) check(api.vmx_rarr_prg_sha256(C.c, seed.data(), seed.size(), 0, n, bits, &h), "vmx_rarr_prg_sha256");
+  else check(api.vmx_rarr_prg_raw_sha256(C.c, seed.data(), seed.size(), 0, n, (bits + 7) / 8, bits, &h), "vmx_rarr_prg_raw_sha256");
+  return Rarr(h);
 }
 
 // prod_i arrays[j][i]^e[i] for every j in one engine call (the exponent digits are sorted once)
@@ -576,14 +621,14 @@ bool Session::verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n
   // seed = RO(rho || node(g, h, u, pk, w, w'))  (PoSTW.java:118-124), hashed beside the imports below
   Oracle seedO(prefix, 256);
   seedO.update_owned(header(NODE, 6));
-  seedO.update_owned(elem_tree(C.g));
+  seedO.update_owned(elem_tree(C, C.g));
   seedO.update(hTree);
   if (u_from_file && pcFile.n == garr_tree_bytes(C, n)) seedO.update(pcFile); else seedO.update(garr_tree(C, u, n, store));
   seedO.update_owned(header(NODE, 2));
   {
     PlainElem gs((size_t)W, C.g), ys((size_t)W, y);
-    hash_plain_elem(seedO, gs);
-    hash_plain_elem(seedO, ys);
+    hash_plain_elem(C, seedO, gs);
+    hash_plain_elem(C, seedO, ys);
   }
   // w and w' were parsed from these files (fail-stop otherwise); their trees are the files when canonical
   if (wFile.n == ciph_arr_tree_bytes(C, W, n)) seedO.update(wFile); else hash_ciph_arr(C, seedO, w, W, n, store);
@@ -656,28 +701,26 @@ bool Session::verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n
   const Bytes prgSeed = challenge_finish(seedO);
 
   // batching vector (:533-538) and challenge v = RO(rho || node(leaf(seed), commitment))  (PoSTW.java:146-147)
-  vmx_rarr* eh = nullptr;
-  check(api.vmx_rarr_prg_sha256(C.c, prgSeed.data(), prgSeed.size(), 0, n, (unsigned)P->ebitlenro, &eh), "vmx_rarr_prg_sha256");
-  Rarr e(eh);
+  Rarr e = batch_vector(C, prgSeed, n, (unsigned)P->ebitlenro);
   Oracle chalO(prefix, (unsigned)P->vbitlenro);
   chalO.update_owned(header(NODE, 2));
-  chalO.update_owned(elem_tree(prgSeed));
-  const size_t plainElemBytes = W == 1 ? 5 + C.eb : 5 + (size_t)W * (5 + C.eb);
+  chalO.update_owned(leaf_tree(prgSeed));
+  const size_t plainElemBytes = W == 1 ? elem_tree_bytes(C) : 5 + (size_t)W * elem_tree_bytes(C);
   const bool commit_canonical = !malformed && read_hdr(commitFile, 0).count == 6 &&
-      commitFile.n == 5 + 2 * garr_tree_bytes(C, n) + 3 * (5 + C.eb) + 5 + 2 * plainElemBytes;
+      commitFile.n == 5 + 2 * garr_tree_bytes(C, n) + 3 * elem_tree_bytes(C) + 5 + 2 * plainElemBytes;
   if (commit_canonical) {
     chalO.update(commitFile);
   } else {
     chalO.update_owned(header(NODE, 6));
     chalO.update(garr_tree(C, B, n, store));
-    chalO.update_owned(elem_tree(Ap));
+    chalO.update_owned(elem_tree(C, Ap));
     chalO.update(garr_tree(C, Bp, n, store));
-    chalO.update_owned(elem_tree(Cp));
-    chalO.update_owned(elem_tree(Dp));
+    chalO.update_owned(elem_tree(C, Cp));
+    chalO.update_owned(elem_tree(C, Dp));
     chalO.update_owned(header(NODE, 2));
     for (int half = 0; half < 2; half++) {
       PlainElem pe_(Fp.begin() + half * W, Fp.begin() + (half + 1) * W);
-      hash_plain_elem(chalO, pe_);
+      hash_plain_elem(C, chalO, pe_);
     }
   }
   // A = prod u^e, F = prod w^e  (:407-410), while the challenge is hashed
@@ -836,6 +879,7 @@ void Session::run(vmxv_report* rep) {
   try {
     Span s = children(ctFile, 2)[0];
     if (W > 1) s = children(s, W)[0];
+    if (C.curve) s = children(s, 2)[0];   // an array over a curve is node(x leaves, y leaves)
     const Hdr h = read_hdr(s, 0);
     if (h.kind != NODE) throw Malformed("array expected");
     n = h.count;
@@ -892,11 +936,11 @@ void Session::run(vmxv_report* rep) {
       spec = std::make_unique<Oracle>(prefix, 256);
       spec->update_owned(header(NODE, 2));
       spec->update_owned(header(NODE, 2));
-      spec->update_owned(elem_tree(C.g));
+      spec->update_owned(elem_tree(C, C.g));
       spec->update(files[lastName]);
       spec->update_owned(header(NODE, 2));
       spec->update_owned(header(NODE, (uint32_t)coeffs.size()));
-      for (const Elem& c : coeffs) spec->update_owned(elem_tree(c));
+      for (const Elem& c : coeffs) spec->update_owned(elem_tree(C, c));
       spec->update_owned(header(NODE, (uint32_t)k));
       for (int l = 1; l <= k; l++) spec->update(files["proofs/DecryptionFactors" + two(l) + ".bt"]);
     }
@@ -976,11 +1020,11 @@ void Session::run(vmxv_report* rep) {
     Oracle seedO(prefix, 256);
     seedO.update_owned(header(NODE, 2));
     seedO.update_owned(header(NODE, 2));
-    seedO.update_owned(elem_tree(C.g));
+    seedO.update_owned(elem_tree(C, C.g));
     if (inpFile.n == ciph_arr_tree_bytes(C, W, n)) seedO.update(inpFile); else hash_ciph_arr(C, seedO, mixed, W, n, store);
     seedO.update_owned(header(NODE, 2));
     seedO.update_owned(header(NODE, (uint32_t)coeffs.size()));
-    for (const Elem& c : coeffs) seedO.update_owned(elem_tree(c));
+    for (const Elem& c : coeffs) seedO.update_owned(elem_tree(C, c));
     seedO.update_owned(header(NODE, (uint32_t)k));
     for (int l = 1; l <= k; l++) {
       if (fFile[(size_t)l].n == plain_arr_tree_bytes(C, W, n)) seedO.update(fFile[(size_t)l]);
@@ -988,9 +1032,7 @@ void Session::run(vmxv_report* rep) {
     }
     prgSeed = challenge_finish(seedO);
   }
-  vmx_rarr* eh = nullptr;
-  check(api.vmx_rarr_prg_sha256(C.c, prgSeed.data(), prgSeed.size(), 0, n, (unsigned)P->ebitlenro, &eh), "vmx_rarr_prg_sha256");
-  Rarr e(eh);
+  Rarr e = batch_vector(C, prgSeed, n, (unsigned)P->ebitlenro);
   // A = prod u^e, combinedB = prod combined^e  (:524-526, :683-685)
   std::vector<const Garr*> arrs;
   for (int c = 0; c < W; c++) arrs.push_back(&mixed.c[(size_t)c]);
@@ -1012,12 +1054,12 @@ void Session::run(vmxv_report* rep) {
   }
   Oracle chalO(prefix, (unsigned)P->vbitlenro);
   chalO.update_owned(header(NODE, 2));
-  chalO.update_owned(elem_tree(prgSeed));
+  chalO.update_owned(leaf_tree(prgSeed));
   chalO.update_owned(header(NODE, (uint32_t)k));
   for (int l = 1; l <= k; l++) {
     chalO.update_owned(header(NODE, 2));
-    chalO.update_owned(elem_tree(yp[(size_t)l]));
-    hash_plain_elem(chalO, Bp[(size_t)l]);
+    chalO.update_owned(elem_tree(C, yp[(size_t)l]));
+    hash_plain_elem(C, chalO, Bp[(size_t)l]);
   }
   const Scalar v = scalar_from_bytes(C, challenge_finish(chalO));
   for (int l = 1; l <= k; l++) {
@@ -1087,12 +1129,16 @@ int vmxv_verify(const vmxv_params* P, const vmxv_file* files, size_t nfiles, vmx
     // never destroyed: at process exit the CUDA runtime may already be gone when static destructors run
     static auto& cache = *new std::map<std::string, std::unique_ptr<Ctx>>();
     std::unique_lock<std::mutex> cache_lock(cache_mu);   // one verification at a time per process
-    const std::string key = std::string((const char*)P->p_be, P->nbytes) + std::string((const char*)P->g_be, P->nbytes) +
-                            "#" + std::to_string(P->device);
+    std::string key = std::string((const char*)P->p_be, P->nbytes) + std::string((const char*)P->g_be, P->nbytes) +
+                      "#" + std::to_string(P->device) + "#" + std::to_string(P->kind);
+    if (P->kind == 1) key += std::string((const char*)P->a_be, P->nbytes) + std::string((const char*)P->b_be, P->nbytes);
     auto it = cache.find(key);
     if (it == cache.end()) {
       vmx_ctx* c = nullptr;
-      if (api.vmx_ctx_create_modp(P->p_be, P->q_be, P->g_be, P->nbytes, P->device, &c) != VMX_OK) {
+      const int st = P->kind == 1
+          ? api.vmx_ctx_create_ecq(P->p_be, P->a_be, P->b_be, P->g_be, P->gy_be, P->q_be, P->nbytes, P->device, &c)
+          : api.vmx_ctx_create_modp(P->p_be, P->q_be, P->g_be, P->nbytes, P->device, &c);
+      if (st != VMX_OK) {
         snprintf(rep->error, sizeof rep->error, "context: %s", api.vmx_last_error());
         return -1;
       }
@@ -1106,9 +1152,18 @@ int vmxv_verify(const vmxv_params* P, const vmxv_file* files, size_t nfiles, vmx
         return out;
       };
       ctx->q = fit(P->q_be, P->nbytes, ctx->rb);
-      ctx->g = fit(P->g_be, P->nbytes, ctx->eb);
-      ctx->one = Bytes(ctx->eb, 0);
-      ctx->one.back() = 1;
+      if (P->kind == 1) {
+        ctx->curve = true;
+        ctx->cb = ctx->eb / 2;
+        ctx->g = fit(P->g_be, P->nbytes, ctx->cb);
+        const Bytes gy = fit(P->gy_be, P->nbytes, ctx->cb);
+        ctx->g.insert(ctx->g.end(), gy.begin(), gy.end());
+        ctx->one = Bytes(ctx->eb, 0xff);
+      } else {
+        ctx->g = fit(P->g_be, P->nbytes, ctx->eb);
+        ctx->one = Bytes(ctx->eb, 0);
+        ctx->one.back() = 1;
+      }
       if (cache.size() >= 4) cache.clear();   // a verifier sees one group, a test suite a few
       it = cache.emplace(key, std::move(ctx)).first;
     }

@@ -4,7 +4,7 @@ stops with an error (mixnet/MixNetElGamalVerifyFiatShamirSession.java:1318-1668)
 
 The pipeline itself -- byte-tree walking, Fiat-Shamir hashing beside the GPU, the order of the engine calls -- is
 C++ over include/vmx.h; this module only marshals the protocol parameters and the files of the proof directory
-(zero-copy: bytes, bytearray, numpy arrays and HostBytes are passed by address).  ModPGroup, any width.
+(zero-copy: bytes, bytearray, numpy arrays and HostBytes are passed by address).  ModPGroup and ECqPGroup, any width.
 """
 from __future__ import annotations
 
@@ -23,7 +23,8 @@ DEFAULT_LIB = os.path.join(_HERE, "libvmnv.so")
 
 
 class _Params(C.Structure):
-    _fields_ = [("p_be", C.c_char_p), ("q_be", C.c_char_p), ("g_be", C.c_char_p), ("nbytes", C.c_size_t),
+    _fields_ = [("kind", C.c_int), ("p_be", C.c_char_p), ("q_be", C.c_char_p), ("g_be", C.c_char_p),
+                ("a_be", C.c_char_p), ("b_be", C.c_char_p), ("gy_be", C.c_char_p), ("nbytes", C.c_size_t),
                 ("device", C.c_int), ("k", C.c_int), ("threshold", C.c_int), ("vbitlenro", C.c_int),
                 ("ebitlenro", C.c_int), ("rbitlen", C.c_int), ("version", C.c_char_p), ("sid", C.c_char_p),
                 ("pgroup_string", C.c_char_p), ("expected_auxsid", C.c_char_p), ("expected_width", C.c_int)]
@@ -74,8 +75,6 @@ class MixNetElGamalVerifyFiatShamirSessionNative:
 
     def __init__(self, pGroup, params: SessionParams, k: int, threshold: int, expectedAuxsid: Optional[str] = None,
                  expectedWidth: Optional[int] = None):
-        if getattr(pGroup, "is_curve", False):
-            raise NotImplementedError("the native verifier handles ModPGroup proofs (curve proofs: vmnv.py)")
         if params.rohash != "SHA-256" or params.prghash != "SHA-256":
             raise NotImplementedError("the native verifier hashes with SHA-256")
         self.pGroup, self.params, self.k, self.threshold = pGroup, params, k, threshold
@@ -87,7 +86,11 @@ class MixNetElGamalVerifyFiatShamirSessionNative:
         G, p = self.pGroup, self.params
         nbytes = (G.p.bit_length() + 7) // 8
         be = lambda v: int(v).to_bytes(nbytes, "big")
-        P = _Params(be(G.p), be(G.q), be(G.g), nbytes, getattr(G, "device", 0), self.k, self.threshold, p.vbitlenro,
+        if getattr(G, "is_curve", False):
+            group = (1, be(G.p), be(G.q), be(G.gx), be(G.a), be(G.b), be(G.gy))
+        else:
+            group = (0, be(G.p), be(G.q), be(G.g), None, None, None)
+        P = _Params(*group, nbytes, getattr(G, "device", 0), self.k, self.threshold, p.vbitlenro,
                     p.ebitlenro, p.rbitlen, p.version.encode(), p.sid.encode(), p.pGroupString.encode(),
                     (self.expectedAuxsid or "").encode(), int(self.expectedWidth or 0))
         names = sorted(nizkp)
