@@ -212,13 +212,18 @@ class ByteTreeDeviceArray(ByteTreeBasic):
         return buf.reshape(-1)
 
     def update(self, digest) -> None:
-        if self._curve:
-            digest.update(struct.pack(">BI", 0, 2))
-            digest.update(self.arr.leaves().data)
+        digest.update(struct.pack(">BI", 0, 2 if self._curve else self._n))
+        if not self._n and not self._curve:
             return
-        digest.update(struct.pack(">BI", 0, self._n))
-        if self._n:
-            digest.update(self._stream().data)
+        arr = self.arr
+        reserve = getattr(digest, "reserve", None)
+        if reserve is not None and getattr(arr, "_leaves", 0) is None and getattr(arr, "h", None) is not None \
+                and getattr(arr, "_export_into_messages", False):
+            # a message is being assembled and this array has not been serialised yet: export into the message
+            nbytes = arr.getPGroup()._leaves_bytes(self._n) if hasattr(arr, "getPGroup") else self._n * (5 + self._w)
+            arr._export_leaves(reserve(nbytes))
+            return
+        digest.update(arr.leaves().data if self._curve else self._stream().data)
 
     def to_bytes(self) -> bytes:
         if self._curve:
@@ -370,6 +375,8 @@ class PFieldElement:
 class PRingElementArray:
     """Device-resident array over Z_q."""
 
+    _export_into_messages = True   # ByteTreeDeviceArray.update: serialise straight into a message being assembled
+
     def __init__(self, ring: PField, handle):
         self.ring = ring
         self.h = handle
@@ -487,9 +494,15 @@ class PRingElementArray:
             if self.h is None:
                 raise ArithmError("byte tree of a freed array")
             buf = _host_buffer(self.ring.group.device, self.size() * (5 + self.ring.byte_len))
-            nat.check(self._lib.vmx_rarr_to_leaves(self.h, _ptr(buf)))
-            self._leaves = buf
+            self._export_leaves(buf)
         return self._leaves
+
+    def _export_leaves(self, buf: np.ndarray) -> None:
+        """Serialise into `buf` (n * (5 + width) bytes) and keep it as this array's cached serialisation.  A message
+        being assembled (eio._Writer.reserve) hands its own slice in: the engine then exports straight into the
+        published message -- no second copy of the array's 390 MB per 10^6 elements."""
+        nat.check(self._lib.vmx_rarr_to_leaves(self.h, _ptr(buf)))
+        self._leaves = buf
 
     def to_matrix(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         n, w = self.size(), self.ring.byte_len
@@ -1003,6 +1016,8 @@ def expMany(elements: Sequence["PGroupElement"], exponents: Sequence[PFieldEleme
 class PGroupElementArray:
     """Device-resident array of ModPGroup elements (Montgomery form, limb-major)."""
 
+    _export_into_messages = True   # ByteTreeDeviceArray.update: serialise straight into a message being assembled
+
     def __init__(self, group: ModPGroup, handle):
         self.group = group
         self.h = handle
@@ -1108,9 +1123,13 @@ class PGroupElementArray:
             if self.h is None:
                 raise ArithmError("byte tree of a freed array")
             buf = _host_buffer(self.group.device, self.group._leaves_bytes(self.size()))
-            nat.check(self._lib.vmx_garr_to_leaves(self.h, _ptr(buf)))
-            self._leaves = buf
+            self._export_leaves(buf)
         return self._leaves
+
+    def _export_leaves(self, buf: np.ndarray) -> None:
+        """As PRingElementArray._export_leaves."""
+        nat.check(self._lib.vmx_garr_to_leaves(self.h, _ptr(buf)))
+        self._leaves = buf
 
     def to_matrix(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         n, w = self.size(), self.group.elem_bytes

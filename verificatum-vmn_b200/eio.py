@@ -121,6 +121,15 @@ class _Writer:
         self.buf[self.pos:self.pos + a.size] = a
         self.pos += a.size
 
+    def reserve(self, nbytes: int) -> np.ndarray:
+        """The next `nbytes` of the message, for a producer that writes them itself (the engine exporting an
+        array straight into the message it is published in)."""
+        view = self.buf[self.pos:self.pos + nbytes]
+        if view.size != nbytes:
+            raise AssertionError("message buffer too small")
+        self.pos += nbytes
+        return view
+
     def value(self):
         if self.pos != self.buf.size:
             raise AssertionError("total_bytes() disagrees with update(): %d != %d" % (self.buf.size, self.pos))

@@ -729,11 +729,13 @@ class PoSTW:
         ByteTreeLeaf(prgSeed).update(cd)
         cd.update(node_header(6))
         commitment = P.commit(prgSeed, on_B=lambda B: B.toByteTree().update(cd))
-        for child in commitment.children[1:]:
-            child.update(cd)
+        # the message is assembled BEFORE its remaining children are hashed: B' is then serialised by the engine
+        # straight into the message (ByteTreeDeviceArray.update / eio._Writer.reserve) and hashed from there
         commitmentBytes = commitment.to_buffer()
         if publish is not None:
             publish("commitment", commitmentBytes)
+        for child in commitment.children[1:]:
+            child.update(cd)
         challengeBytes = self.challenger.finish(cd)
         reply = P.reply(_to_positive(challengeBytes))
         replyBytes = reply.to_buffer()

@@ -262,6 +262,8 @@ class ShardedField(PField):
 
 
 class ShardedRingArray(PRingElementArray):
+    _export_into_messages = False   # the serialisation of a sharded array is a gather of all shards (leaves())
+
     def __init__(self, ring: ShardedField, handle, gsize: int):
         super().__init__(ring, handle)
         self.gsize = int(gsize)
@@ -566,6 +568,8 @@ class ShardedECqPGroup(_ShardedGroupMixin, ECqPGroup):
 
 
 class ShardedGroupArray(PGroupElementArray):
+    _export_into_messages = False
+
     def __init__(self, group: ShardedModPGroup, handle, gsize: int):
         super().__init__(group, handle)
         self.gsize = int(gsize)
