@@ -258,6 +258,20 @@ def transcript_parity(vmx, bits, n):
     raw[len(raw) // 2] ^= 0x04
     okb, outb = ov.finish(dataclasses.replace(proof3, commitment=bytes(raw)))
     assert okb is False and col_values(outb) == oc.w
+    # the output on the board differs from the one the proof is finally presented with (same length): the streamed
+    # seed hash covered other bytes and must not be used -- same verdicts as the offline order, both ways round
+    other_out = bytearray(proof.output)
+    other_out[len(other_out) // 3] ^= 0x01
+    other_out = bytes(other_out)
+    for board, final in ((other_out, proof), (proof.output, dataclasses.replace(proof, output=other_out))):
+        ov = verifier.beginVerify(1, ec.w, generators=h)
+        ov.publish("output", board)
+        ov.publish("permutationCommitment", proof.permutationCommitment)
+        ov.publish("commitment", proof.commitment)
+        got = ov.finish(final)
+        want = verifier.verify(1, ec.w, final, generators=h)
+        assert got[0] == want[0] and col_values(got[1]) == col_values(want[1])
+    assert verifier.verify(1, ec.w, proof, generators=h)[0] is True
     ov = verifier.beginVerify(1, ec.w, generators=h)
     ov.publish("output", proof.output)
     ov.publish("permutationCommitment", proof.permutationCommitment[:-2])      # a truncated message on the board

@@ -857,13 +857,10 @@ void Session::run(vmxv_report* rep) {
   // multiplications per thread); they stay with the cached context for the next verification
   check(api.vmx_fixed_precompute(C.c, y.data(), 16), "vmx_fixed_precompute");
   std::vector<Elem> pkeys((size_t)k + 1);
-  for (int l = 1; l <= k; l++) {  // PolynomialInExponent.evaluate(l)
-    Elem acc = coeffs[0];
-    uint64_t power = 1;
-    for (size_t i = 1; i < coeffs.size(); i++) {
-      power *= (uint64_t)l;
-      acc = elem_mul(C, acc, elem_exp(C, coeffs[i], scalar_from_u64(C, power)));
-    }
+  for (int l = 1; l <= k; l++) {  // PolynomialInExponent.evaluate(l) = prod_i coeffs[i]^(l^i), by Horner's rule in the
+    Elem acc = coeffs.back();     // exponent (l^i itself leaves 64 bits for a hundred parties and a threshold of 11)
+    const Scalar ls = scalar_from_u64(C, (uint64_t)l);
+    for (size_t i = coeffs.size() - 1; i-- > 0;) acc = elem_mul(C, elem_exp(C, acc, ls), coeffs[i]);
     pkeys[(size_t)l] = acc;
   }
   int active = 0;
@@ -951,7 +948,7 @@ void Session::run(vmxv_report* rep) {
   std::vector<CiphArr> outputs;
   outputs.reserve((size_t)active);
   int valid = 0;
-  for (int l = 1; l <= active && l <= 64; l++) {
+  for (int l = 1; l <= active; l++) {
     std::string name = "proofs/Ciphertexts" + two(l) + ".bt";
     if (l == active && !has(name)) name = "ShuffledCiphertexts.bt";
     const Span pc = file("proofs/PermutationCommitment" + two(l) + ".bt");
@@ -960,7 +957,7 @@ void Session::run(vmxv_report* rep) {
     const Span outFile = file(name);
     outputs.push_back(read_ciph(outFile, name));   // fail-stop if malformed; an invalid PROOF keeps the input
     const bool ok = verify_shuffle(h, hTree, h0, n, *inp, outputs.back(), inpFile, outFile, pc, cm, rp, y);
-    rep->shuffles[l - 1] = ok ? 1 : 0;
+    if (l <= (int)(sizeof rep->shuffles / sizeof rep->shuffles[0])) rep->shuffles[l - 1] = ok ? 1 : 0;   // (all are counted)
     rep->n_shuffles = l;
     valid += ok ? 1 : 0;
     if (ok) { inp = &outputs.back(); inpFile = outFile; }
@@ -1122,6 +1119,19 @@ int vmxv_verify(const vmxv_params* P, const vmxv_file* files, size_t nfiles, vmx
   if (!P || !rep || (nfiles && !files)) return -1;
   std::memset(rep, 0, sizeof *rep);
   if (!api.handle) { snprintf(rep->error, sizeof rep->error, "vmxv_bind was not called"); return -1; }
+  {  // usage errors: nothing of the directory is looked at
+    const char* bad = nullptr;
+    if (P->kind != 0 && P->kind != 1) bad = "kind must be 0 (ModPGroup) or 1 (ECqPGroup)";
+    else if (!P->p_be || !P->q_be || !P->g_be || P->nbytes == 0 || P->nbytes > (1u << 16)) bad = "group parameters missing";
+    else if (P->kind == 1 && (!P->a_be || !P->b_be || !P->gy_be)) bad = "curve parameters missing";
+    else if (P->k < 1 || P->k > kOddPrimeMax || P->threshold < 1 || P->threshold > P->k) bad = "parties / threshold out of range";
+    else if (P->vbitlenro < 1 || P->ebitlenro < 1 || P->rbitlen < 0 || P->vbitlenro > 4096 || P->ebitlenro > 4096 ||
+             P->rbitlen > 4096) bad = "bit lengths out of range";
+    else if (!P->version || !P->sid || !P->pgroup_string) bad = "version / sid / pgroup string missing";
+    for (size_t i = 0; i < nfiles && !bad; i++)
+      if (!files[i].name || (files[i].size && !files[i].data)) bad = "a file without name or data";
+    if (bad) { snprintf(rep->error, sizeof rep->error, "%s", bad); return -1; }
+  }
   try {
     // engine contexts are kept between calls (keyed by modulus and device): their fixed-base tables and recycled
     // blocks serve the next verification over the same group, as one vmnv process verifying several proofs would
@@ -1130,6 +1140,7 @@ int vmxv_verify(const vmxv_params* P, const vmxv_file* files, size_t nfiles, vmx
     static auto& cache = *new std::map<std::string, std::unique_ptr<Ctx>>();
     std::unique_lock<std::mutex> cache_lock(cache_mu);   // one verification at a time per process
     std::string key = std::string((const char*)P->p_be, P->nbytes) + std::string((const char*)P->g_be, P->nbytes) +
+                      std::string((const char*)P->q_be, P->nbytes) +
                       "#" + std::to_string(P->device) + "#" + std::to_string(P->kind);
     if (P->kind == 1) key += std::string((const char*)P->a_be, P->nbytes) + std::string((const char*)P->b_be, P->nbytes);
     auto it = cache.find(key);

@@ -780,7 +780,10 @@ class PoSTW:
         self._preSeed = self._preChallenge = None
 
     # -- :177-260
-    def verify(self, pkey, w, wp, permutationCommitment: bytes, commitment: bytes, reply: bytes) -> bool:
+    def verify(self, pkey, w, wp, permutationCommitment: bytes, commitment: bytes, reply: bytes,
+               outputBytes=None) -> bool:
+        """`outputBytes`: the published message `wp` was parsed from (only needed to validate a streamed seed hash:
+        the hash stands only if it covered these very bytes)."""
         V = self.V
         V.setInstance(pkey, w, wp)
         u_parsed = True
@@ -793,7 +796,7 @@ class PoSTW:
         # they are exactly the byte trees of the parsed arrays (well formed, no trailing bytes)
         pre, prc = getattr(self, "_preSeed", None), getattr(self, "_preChallenge", None)
         self._preSeed = self._preChallenge = None
-        pre_ok = pre is not None and u_parsed and pre[1] is permutationCommitment and \
+        pre_ok = pre is not None and u_parsed and pre[1] is permutationCommitment and pre[2] is outputBytes and \
             len(permutationCommitment) == V.u.toByteTree().total_bytes() and len(pre[2]) == wp.toByteTree().total_bytes()
         if pre is not None and not pre_ok:
             self._preSeed, self._preChallenge = pre, prc

@@ -207,9 +207,11 @@ class ShufflerSession:
         own_generators = generators is None
         if own_generators:
             generators = self.deriveGenerators(size)
+        outputBytes = None
         try:
             if output is None:
                 output = ciphPPGroup.toElementArray(size, ByteTreeReader(proof.output))
+                outputBytes = proof.output
         except Exception:
             if own_generators:
                 generators.free()
@@ -221,7 +223,7 @@ class ShufflerSession:
             V = self._pos()
             V.precompute(generators.getPGroup().getg(), generators)
         verdict = V.verify(widePublicKey, ciphertexts, output, proof.permutationCommitment, proof.commitment,
-                           proof.reply)
+                           proof.reply, outputBytes=outputBytes)
         V.free()
         if own_generators:
             generators.free()
