@@ -1,9 +1,10 @@
 /* vmnv.h -- C ABI of the native universal verifier (verificatum-vmn_b200/libvmnv.so, csrc/vmnv_native.cpp).
  *
  * What `vmnv` does with the proof directory of a mix-net execution
- * (mixnet/MixNetElGamalVerifyFiatShamirSession.java:1318-1668, proofs of type "mixing" over a ModPGroup or an ECqPGroup,
- * ciphertexts of any width): every file is walked here, every group / ring operation is one call into the engine's C ABI
- * (include/vmx.h), Fiat-Shamir hashing is SHA-256 on a worker thread beside the GPU.  A JVM would bind these
+ * (mixnet/MixNetElGamalVerifyFiatShamirSession.java:1318-1668: proofs of type "mixing", "shuffling" or "decryption",
+ * with or without pre-computation, over a ModPGroup or an ECqPGroup, ciphertexts of any width): every file is walked
+ * here, every group / ring operation is one call into the engine's C ABI (include/vmx.h), Fiat-Shamir hashing is
+ * SHA-256 on a worker thread beside the GPU.  A JVM would bind these
  * three functions the way INTEGRATION.md binds vmx.h (JNI or FFM); the parameters are what the protocol info file
  * holds (elgamal/ProtocolElGamalGen.java:81-213).
  */
@@ -34,6 +35,11 @@ typedef struct vmxv_params {
   const char* pgroup_string;  /* the pgroup string of the info file (enters the global prefix) */
   const char* expected_auxsid; /* NULL or "": accept the one in the proof (vmnv -auxsid) */
   int expected_width;          /* <= 0: accept the one in the proof (vmnv -width) */
+  const char* expected_type;   /* NULL or "": accept the type in the proof; else "mixing" | "shuffling" | "decryption"
+                                  (vmnv -mix / -shuffle / -decrypt; MixNetElGamalVerifyFiatShamirSession.java:329-358) */
+  int nodec, noposc, noccpos;  /* non-zero: do not verify the decryption / the proofs of shuffles of commitments / the
+                                  (commitment-consistent) proofs of shuffles (vmnv -nodec, -noposc, -noccpos;
+                                  mixnet/SessionParams.java) */
 } vmxv_params;
 
 typedef struct vmxv_file {
@@ -45,11 +51,17 @@ typedef struct vmxv_file {
 typedef struct vmxv_report {
   int accepted;      /* the verdict of vmnv */
   int fail_stop;     /* 1: a condition under which the reference stops with an error (`error` says which) */
-  int n_shuffles;    /* active threshold */
-  int shuffles[64];  /* verdict of each proof of a shuffle (an invalid one keeps its input) */
+  int type;          /* 0 "mixing", 1 "shuffling", 2 "decryption" (the `type` file) */
+  int n_shuffles;    /* index of the last party whose shuffle was looked at */
+  int shuffles[64];  /* party l - 1: 1 its shuffle is valid, -1 invalid (its output is replaced by its input), 0 the
+                        party took no part / shuffles are not verified.  After a pre-computation the verdict is that of
+                        the proof of a shuffle of commitments AND of the commitment-consistent proof of a shuffle */
+  int poscs[64];     /* pre-computation only: 1 / -1 / 0 for the proof of a shuffle of commitments alone (an invalid
+                        one replaces the permutation commitment by the generators) */
   int valid_proofs;
-  int decryption;    /* the combined proof of the decryption factors */
-  int plaintexts;    /* Plaintexts.bt equals the decrypted output */
+  int enough_valid_proofs; /* valid_proofs >= threshold (1 also when no shuffle is verified) */
+  int decryption;    /* the combined proof of the decryption factors: 1 valid, 0 invalid, -1 not verified */
+  int plaintexts;    /* Plaintexts.bt equals the decrypted output: 1 / 0 / -1 */
   uint64_t hashed_bytes, launches;
   char error[400];
 } vmxv_report;

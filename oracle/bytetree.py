@@ -116,6 +116,12 @@ def from_bytes(data: bytes) -> ByteTree:
     return t
 
 
+def read(data: bytes) -> ByteTree:
+    """The byte tree at the start of `data`, as a ByteTreeReaderF over a file sees it: what follows the tree is never
+    read (no caller in the reference checks for the end of the file)."""
+    return parse(data, 0)[0]
+
+
 # ---------------------------------------------------------------- integers
 def int_byte_length(x: int) -> int:
     """Length of BigInteger.toByteArray() for x >= 0 (two's complement, minimal)."""

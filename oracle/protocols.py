@@ -294,27 +294,27 @@ def verify_shuffle(G, params: Params, pkey, w, h, proof: dict) -> bool:
     n = ar.size_of(w)
     prefix = params.prefix()
     try:
-        wp = ar.parse_array(G, bt.from_bytes(proof["output"]), n, pkey)
+        wp = ar.parse_array(G, bt.read(proof["output"]), n, pkey)
     except (ar.FormatError, bt.EIOError):
         return False
     V = PoSBasicTW(G, params.vbitlenro, params.ebitlenro, params.rbitlen, params.prghash, None)
     V.precompute(G.g, h)
     V.set_instance(pkey, w, wp)
     try:
-        V.u = ar.parse_array(G, bt.from_bytes(proof["permutationCommitment"]), n)
+        V.u = ar.parse_array(G, bt.read(proof["permutationCommitment"]), n)
     except (ar.FormatError, bt.EIOError):
         V.u = list(h)
     seed = challenge(params.rohash, prefix, _seed_data(G, V, pkey, w, wp), 8 * PRGHeuristic(params.prghash).min_no_seed_bytes())
     V.set_batch_vector(seed)
     V.compute_AF()
     try:
-        ctree = V.set_commitment(bt.from_bytes(proof["commitment"]))
+        ctree = V.set_commitment(bt.read(proof["commitment"]))
     except bt.EIOError:
         ctree = V.set_commitment(bt.leaf(b""))
     cb = challenge(params.rohash, prefix, bt.node(bt.leaf(seed), ctree), params.vbitlenro)
     V.set_challenge(int.from_bytes(cb, "big"))
     try:
-        return V.verify(bt.from_bytes(proof["reply"]))
+        return V.verify(bt.read(proof["reply"]))
     except bt.EIOError:
         return False
 
@@ -703,13 +703,13 @@ def posc_verify(G, params: Params, g, h, u, commitment: bytes, reply: bytes) -> 
                      8 * PRGHeuristic(params.prghash).min_no_seed_bytes())
     V.set_batch_vector(seed)
     try:
-        ctree = V.set_commitment(bt.from_bytes(commitment))
+        ctree = V.set_commitment(bt.read(commitment))
     except bt.EIOError:
         ctree = V.set_commitment(bt.leaf(b""))
     cb = challenge(params.rohash, prefix, bt.node(bt.leaf(seed), ctree), params.vbitlenro)
     V.set_challenge(int.from_bytes(cb, "big"))
     try:
-        return V.verify(bt.from_bytes(reply))
+        return V.verify(bt.read(reply))
     except bt.EIOError:
         return False
 
@@ -740,13 +740,13 @@ def ccpos_verify(G, params: Params, g, h, u, pkey, w, wp, commitment: bytes, rep
     V.set_batch_vector(seed)
     V.compute_AB()
     try:
-        ctree = V.set_commitment(bt.from_bytes(commitment))
+        ctree = V.set_commitment(bt.read(commitment))
     except bt.EIOError:
         ctree = V.set_commitment(bt.leaf(b""))
     cb = challenge(params.rohash, params.prefix(), bt.node(bt.leaf(seed), ctree), params.vbitlenro)
     V.set_challenge(int.from_bytes(cb, "big"))
     try:
-        return V.verify(bt.from_bytes(reply))
+        return V.verify(bt.read(reply))
     except bt.EIOError:
         return False
 
@@ -826,31 +826,62 @@ def wide_key(pk, width: int):
     return pk if width == 1 else ((pk[0],) * width, (pk[1],) * width)
 
 
-def run_mix(G, params: Params, k: int, threshold: int, w, rs, auxsid=None, width: int = 1):
-    """Returns (proof directory as dict name -> bytes, plaintext elements)."""
+def run_mix(G, params: Params, k: int, threshold: int, w, rs, auxsid=None, width: int = 1, mode: str = "mixing",
+            maxciph=None):
+    """Returns (proof directory as dict name -> bytes, plaintext elements -- the shuffled list for mode
+    "shuffling").  `mode` is the type of the session (mixnet/MixNetElGamalSession.java:53-63): "mixing" (shuffle,
+    then decrypt: :345-358), "shuffling" (:208-245) or "decryption" (:268-325).  `maxciph`: pre-computation for that
+    many ciphertexts first (:161-187; ShufflerElGamalSession.java:534-672), so that the shuffle is the
+    commitment-consistent one (:972-1033) over commitments shrunk to the actual number of ciphertexts."""
     if auxsid is not None:
         params = params.with_auxsid(auxsid)
+    if mode not in ("mixing", "shuffling", "decryption"):
+        raise ValueError(mode)
     q = G.q
     poly = [ar.ring_random_element(G, rs, params.rbitlen) for _ in range(threshold)]
     xs = {l: sum(a * pow(l, i, q) for i, a in enumerate(poly)) % q for l in range(1, k + 1)}
     coeffs = [G.op_exp(G.g, a) for a in poly]
     pk = (G.g, coeffs[0])
     wpk = wide_key(pk, width)
-    d = {"version": params.version.encode(), "type": b"mixing", "auxsid": params.auxsid.encode(),
+    d = {"version": params.version.encode(), "type": mode.encode(), "auxsid": params.auxsid.encode(),
          "width": str(width).encode(),
          "FullPublicKey.bt": ar.elem_tree(G, pk).to_bytes(),
          "proofs/PolynomialInExponent.bt": bt.node([ar.elem_tree(G, c) for c in coeffs]).to_bytes(),
          "Ciphertexts.bt": ar.array_tree(G, w).to_bytes(), "proofs/activethreshold": str(threshold).encode()}
     n = ar.size_of(w)
-    h = independent_generators(G, params.rohash, params.prefix(), "generators", n, params.rbitlen)
     inp = w
-    for l in range(1, threshold + 1):
-        out, proof = shuffle_and_prove(G, params, wpk, inp, h, _party_source(rs))
-        d["ShuffledCiphertexts.bt" if l == threshold else "proofs/Ciphertexts%02d.bt" % l] = proof["output"]
-        d["proofs/PermutationCommitment%02d.bt" % l] = proof["permutationCommitment"]
-        d["proofs/PoSCommitment%02d.bt" % l] = proof["commitment"]
-        d["proofs/PoSReply%02d.bt" % l] = proof["reply"]
-        inp = out
+    if mode != "decryption" and maxciph is None:
+        h = independent_generators(G, params.rohash, params.prefix(), "generators", n, params.rbitlen)
+        for l in range(1, threshold + 1):
+            out, proof = shuffle_and_prove(G, params, wpk, inp, h, _party_source(rs))
+            d["ShuffledCiphertexts.bt" if l == threshold else "proofs/Ciphertexts%02d.bt" % l] = proof["output"]
+            d["proofs/PermutationCommitment%02d.bt" % l] = proof["permutationCommitment"]
+            d["proofs/PoSCommitment%02d.bt" % l] = proof["commitment"]
+            d["proofs/PoSReply%02d.bt" % l] = proof["reply"]
+            inp = out
+    elif mode != "decryption":
+        if maxciph < n:
+            raise ValueError("more ciphertexts than pre-computed for")
+        d["proofs/maxciph"] = str(maxciph).encode()
+        h = independent_generators(G, params.rohash, params.prefix(), "generators", maxciph, params.rbitlen)
+        states = {}
+        for l in range(1, threshold + 1):       # pre-computation: every active party commits and proves (PoSC)
+            states[l], (pc, c, r) = precomp(G, params, wpk, h, _party_source(rs))
+            d["proofs/PermutationCommitment%02d.bt" % l] = pc
+            d["proofs/PoSCCommitment%02d.bt" % l] = c
+            d["proofs/PoSCReply%02d.bt" % l] = r
+        for l in range(1, threshold + 1):       # shrink to the actual size, then the commitment-consistent shuffles
+            d["proofs/KeepList%02d.bt" % l] = shrink(G, states[l], n)
+        for l in range(1, threshold + 1):
+            out, proof = committed_shuffle(G, params, wpk, states[l], inp, _party_source(rs))
+            d["ShuffledCiphertexts.bt" if l == threshold else "proofs/Ciphertexts%02d.bt" % l] = proof["output"]
+            d["proofs/CCPoSCommitment%02d.bt" % l] = proof["commitment"]
+            d["proofs/CCPoSReply%02d.bt" % l] = proof["reply"]
+            inp = out
+    if mode == "shuffling":
+        return d, inp
+    if mode == "mixing":   # the output of the shuffle moves into the proofs (MixNetElGamalSession.java:294-303)
+        d["proofs/Ciphertexts%02d.bt" % threshold] = d.pop("ShuffledCiphertexts.bt")
     # decryption
     u = inp[0]
     inv_factor = pow(prod_factor(q, k), -1, q)
@@ -897,27 +928,45 @@ def _parse_int(raw: bytes) -> int:
     return int(text)
 
 
-def verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_auxsid=None, expected_width=None) -> dict:
-    """The verdicts of mixnet/MixNetElGamalVerifyFiatShamirSession.verify for a proof of type "mixing".  A file
-    that is malformed where the reference does not substitute trivial values is fail-stop."""
+def verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_auxsid=None, expected_width=None,
+               expected_type=None, dec: bool = True, posc: bool = True, ccpos: bool = True) -> dict:
+    """The verdicts of mixnet/MixNetElGamalVerifyFiatShamirSession.verify (:1318-1668) for a proof of type "mixing",
+    "shuffling" or "decryption", with or without pre-computation (`proofs/maxciph` present: proofs of shuffles of
+    commitments, keep lists, commitment-consistent proofs of shuffles).  `dec`, `posc`, `ccpos`: what is verified
+    (the -nodec / -noposc / -noccpos options of vmnv; mixnet/SessionParams.java).  A file that is malformed where the
+    reference does not substitute trivial values is fail-stop."""
     try:
-        return _verify_mix(G, params, k, threshold, d, expected_auxsid, expected_width)
+        return _verify_mix(G, params, k, threshold, d, expected_auxsid, expected_width, expected_type, dec, posc, ccpos)
     except (bt.EIOError, ar.FormatError, ValueError, IndexError, AttributeError, TypeError) as e:
         raise MixVerificationError("malformed proof directory: %s" % e)
 
 
-def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_auxsid=None, expected_width=None) -> dict:
+def _first_array_size(G, t, width: int) -> int:
+    """Number of elements of the ciphertext array serialised as `t` (readArray with size 0, :577-607)."""
+    first = t.children[0]
+    for _ in range((1 if width > 1 else 0) + (1 if hasattr(G, "coord_bytes") else 0)):
+        first = first.children[0]
+    if first.is_leaf():
+        raise ar.FormatError("array expected")
+    return len(first.children)
+
+
+def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_auxsid=None, expected_width=None,
+                expected_type=None, dec=True, posc=True, ccpos=True) -> dict:
     def need(name):
         if name not in d:
             raise MixVerificationError("missing " + name)
         return d[name]
-    if need("version").decode() != params.version or need("type") != b"mixing":
-        raise MixVerificationError("header")
-    width = _parse_int(need("width"))
-    if width < 1 or (expected_width is not None and width != expected_width):
-        raise MixVerificationError("width")
-    # determineAuxsid (MixNetElGamalVerifyFiatShamirSession.java:369-395): read from the proof, validated, and part
-    # of the global prefix (:160); [VCR-mem] Protocol.validateSid = letters, digits, underscores, spaces
+    if need("version").decode() != params.version:
+        raise MixVerificationError("version")
+    # determineType (:329-358), determineSessionParams (:984-1005)
+    typ = need("type").decode("ascii", errors="replace")
+    if typ not in ("mixing", "shuffling", "decryption"):
+        raise MixVerificationError("unknown type of proof")
+    if expected_type is not None and typ != expected_type:
+        raise MixVerificationError("type mismatch")
+    # determineAuxsid (:369-395): read from the proof, validated, and part of the global prefix (:160); [VCR-mem]
+    # Protocol.validateSid = letters, digits, underscores, spaces
     import re
     auxsid = need("auxsid").decode("ascii", errors="replace")
     if re.fullmatch(r"[A-Za-z0-9_ ]{1,1024}", auxsid) is None:
@@ -925,50 +974,129 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
     if expected_auxsid is not None and auxsid != expected_auxsid:
         raise MixVerificationError("auxsid mismatch")
     params = params.with_auxsid(auxsid)
+    if typ == "shuffling":
+        dec = False
+    elif typ == "decryption":
+        posc = ccpos = False
+    width = 1
+    if ccpos or dec:
+        width = _parse_int(need("width"))
+        if width < 1 or (expected_width is not None and width != expected_width):
+            raise MixVerificationError("width")
+    rep = {"type": typ, "shuffles": {}, "poscs": {}, "decryption": None}
     try:
-        pk = ar.parse_elem(G, bt.from_bytes(need("FullPublicKey.bt")), (None, None))
-        t = bt.from_bytes(need("proofs/PolynomialInExponent.bt"))
-        if t.is_leaf() or len(t.children) != threshold:
-            raise ar.FormatError("degree")
-        coeffs = [ar.parse_elem(G, c) for c in t.children]
+        pk = ar.parse_elem(G, bt.read(need("FullPublicKey.bt")), (None, None))
     except (ar.FormatError, bt.EIOError):
         raise MixVerificationError("keys")
-    if pk[0] != G.g or pk[1] != coeffs[0]:
-        raise MixVerificationError("mismatching keys")
-    ys = {l: _eval_in_exponent(G, coeffs, l) for l in range(1, k + 1)}
+    if pk[0] != G.g:
+        raise MixVerificationError("basic public key is not the standard generator")
+    coeffs, ys = None, None
+    if dec:   # readMixServerPKeys :228-266
+        try:
+            t = bt.read(need("proofs/PolynomialInExponent.bt"))
+            if t.is_leaf() or len(t.children) != threshold:
+                raise ar.FormatError("degree")
+            coeffs = [ar.parse_elem(G, c) for c in t.children]
+        except (ar.FormatError, bt.EIOError):
+            raise MixVerificationError("keys")
+        if pk[1] != coeffs[0]:
+            raise MixVerificationError("mismatching keys")
+        ys = {l: _eval_in_exponent(G, coeffs, l) for l in range(1, k + 1)}
+    precomp_ = "proofs/maxciph" in d
     active = _parse_int(need("proofs/activethreshold"))
     if active > k or active < threshold:
         raise MixVerificationError("active threshold")
-    ct = bt.from_bytes(need("Ciphertexts.bt"))
-    first = ct.children[0]
-    for _ in range((1 if width > 1 else 0) + (1 if hasattr(G, "coord_bytes") else 0)):
-        first = first.children[0]
-    n = len(first.children)
     basic_pk, pk = pk, wide_key(pk, width)
-    try:
-        w = ar.parse_array(G, ct, n, pk)
-    except (ar.FormatError, bt.EIOError):
-        raise MixVerificationError("ciphertexts")
-    h = independent_generators(G, params.rohash, params.prefix(), "generators", n, params.rbitlen)
-    rep = {"shuffles": {}}
-    inp, valid = w, 0
-    for l in range(1, active + 1):
-        name = "proofs/Ciphertexts%02d.bt" % l
-        if l == active and name not in d:
-            name = "ShuffledCiphertexts.bt"
-        proof = {"output": need(name), "permutationCommitment": need("proofs/PermutationCommitment%02d.bt" % l),
-                 "commitment": need("proofs/PoSCommitment%02d.bt" % l), "reply": need("proofs/PoSReply%02d.bt" % l)}
-        try:
-            out = ar.parse_array(G, bt.from_bytes(proof["output"]), n, pk)
-        except (ar.FormatError, bt.EIOError):
-            raise MixVerificationError("output of party %d" % l)
-        ok = verify_shuffle(G, params, pk, inp, h, proof)
-        rep["shuffles"][l] = ok
-        valid += 1 if ok else 0
-        inp = out if ok else inp
-    rep["validProofs"] = valid
-    rep["enoughValidProofs"] = valid >= threshold
-    flags = bt.from_bytes(need("proofs/CorrectIndices.bt"))
+    # readCiphertexts :1017-1046
+    w = None
+    if ccpos or dec:
+        if ccpos or typ == "decryption":
+            name = "Ciphertexts.bt"
+            raw = need(name)
+        else:
+            name = "proofs/Ciphertexts%02d.bt" % active
+            raw = d.get(name)
+        if raw is not None:
+            try:
+                ct = bt.read(raw)
+                w = ar.parse_array(G, ct, _first_array_size(G, ct, width), pk)
+            except (ar.FormatError, bt.EIOError, IndexError, AttributeError):
+                raise MixVerificationError("ciphertexts")
+            if ar.size_of(w) == 0:
+                raise MixVerificationError("no ciphertexts")
+    if posc or ccpos:
+        # getMaxciph :541-548, deriveGenerators :556-576, getShrunkGenerators :1059-1068
+        if precomp_:
+            maxciph = _parse_int(need("proofs/maxciph"))
+            if maxciph < 1 or maxciph > max(len(v) for v in d.values()):   # (no file could hold such a commitment)
+                raise MixVerificationError("maxciph")
+        else:
+            if w is None:
+                raise MixVerificationError("no ciphertexts")
+            maxciph = ar.size_of(w)
+        h = independent_generators(G, params.rohash, params.prefix(), "generators", maxciph, params.rbitlen)
+        shrunk = None
+        if ccpos and precomp_:
+            if ar.size_of(w) > maxciph:
+                raise MixVerificationError("more ciphertexts than generators")
+            shrunk = h[:ar.size_of(w)]
+        inp, valid = w, 0
+        for l in range(1, active + 1):
+            verdict = True
+            pcname = "proofs/PermutationCommitment%02d.bt" % l
+            if (posc and precomp_ and not ccpos and pcname in d) or \
+                    ("proofs/CCPoSCommitment%02d.bt" % l in d or "proofs/PoSCommitment%02d.bt" % l in d):
+                try:   # readPermutationCommitment :626-641: fail-stop when missing or malformed
+                    u = ar.parse_array(G, bt.read(need(pcname)), maxciph)
+                except (ar.FormatError, bt.EIOError):
+                    raise MixVerificationError("permutation commitment of party %d" % l)
+                if posc and precomp_:   # verifyPoSC :652-705
+                    ok = posc_verify(G, params, G.g, h, u, need("proofs/PoSCCommitment%02d.bt" % l),
+                                     need("proofs/PoSCReply%02d.bt" % l))
+                    rep["poscs"][l] = ok
+                    if not ok:
+                        verdict = False
+                        u = list(h)
+                if ccpos:
+                    n = ar.size_of(inp)
+                    name = "proofs/Ciphertexts%02d.bt" % l
+                    if l == active and name not in d:
+                        name = "ShuffledCiphertexts.bt"
+                    try:
+                        out = ar.parse_array(G, bt.read(need(name)), n, pk)
+                    except (ar.FormatError, bt.EIOError):
+                        raise MixVerificationError("output of party %d" % l)
+                    if precomp_:
+                        # shrinkPermComm :714-745: a keep list that cannot be read or keeps the wrong number is fail-stop
+                        kl = bt.read(need("proofs/KeepList%02d.bt" % l))
+                        if not kl.is_leaf() or len(kl.value) != maxciph or any(x > 1 for x in kl.value):
+                            raise MixVerificationError("keep list of party %d" % l)
+                        if sum(kl.value) != n:
+                            raise MixVerificationError("wrong number of true elements in keep list of party %d" % l)
+                        su = [x for x, keep in zip(u, kl.value) if keep]
+                        ok = ccpos_verify(G, params, G.g, shrunk, su, pk, inp, out,
+                                          need("proofs/CCPoSCommitment%02d.bt" % l), need("proofs/CCPoSReply%02d.bt" % l))
+                        verdict = verdict and ok
+                    else:
+                        proof = {"output": d[name], "permutationCommitment": d[pcname],
+                                 "commitment": need("proofs/PoSCommitment%02d.bt" % l),
+                                 "reply": need("proofs/PoSReply%02d.bt" % l)}
+                        verdict = verify_shuffle(G, params, pk, inp, h, proof)
+                    inp = out if verdict else inp
+                rep["shuffles"][l] = verdict
+                valid += 1 if verdict else 0
+        rep["validProofs"] = valid
+        rep["enoughValidProofs"] = valid >= threshold
+        if dec:
+            w = inp
+    if not dec:
+        rep["accepted"] = bool(rep.get("enoughValidProofs", True))
+        return rep
+    if w is None:
+        raise MixVerificationError("no ciphertexts to decrypt")
+    inp = w
+    n = ar.size_of(inp)
+    flags = bt.read(need("proofs/CorrectIndices.bt"))
     if not flags.is_leaf() or len(flags.value) != k + 1 or max(flags.value) > 1:
         raise MixVerificationError("correct indices")
     correct = [bool(x) for x in flags.value]
@@ -976,7 +1104,7 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
         raise MixVerificationError("too few correct decryption factors")
     u = inp[0]
     try:
-        f = {l: ar.parse_array(G, bt.from_bytes(need("proofs/DecryptionFactors%02d.bt" % l)), n, pk[0] if width > 1 else None)
+        f = {l: ar.parse_array(G, bt.read(need("proofs/DecryptionFactors%02d.bt" % l)), n, pk[0] if width > 1 else None)
              for l in range(1, k + 1)}
     except (ar.FormatError, bt.EIOError):
         raise MixVerificationError("decryption factors")
@@ -991,14 +1119,14 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
     V.batch_combined(combined)
     for l in range(1, k + 1):
         try:
-            V.set_commitment(l, bt.from_bytes(need("proofs/DecrFactCommitment%02d.bt" % l)))
+            V.set_commitment(l, bt.read(need("proofs/DecrFactCommitment%02d.bt" % l)))
         except bt.EIOError:
             V.set_commitment(l, bt.leaf(b""))
     cdata = bt.node(bt.leaf(seed), bt.node([V.commitment_tree(l) for l in range(1, k + 1)]))
     v = int.from_bytes(challenge(params.rohash, prefix, cdata, params.vbitlenro), "big")
     for l in range(1, k + 1):
         try:
-            V.set_reply(l, bt.from_bytes(need("proofs/DecrFactReply%02d.bt" % l)))
+            V.set_reply(l, bt.read(need("proofs/DecrFactReply%02d.bt" % l)))
         except bt.EIOError:
             V.set_reply(l, bt.node([]))
     V.combine(correct)
@@ -1007,11 +1135,11 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
         raise MixVerificationError("combined proof of decryption")
     computed = ar.g_mul(G, inp[1], combined)
     try:
-        plain = ar.parse_array(G, bt.from_bytes(need("Plaintexts.bt")), n, pk[0] if width > 1 else None)
+        plain = ar.parse_array(G, bt.read(need("Plaintexts.bt")), n, pk[0] if width > 1 else None)
     except (ar.FormatError, bt.EIOError):
         raise MixVerificationError("plaintexts")
     rep["plaintexts"] = plain == computed
     if not rep["plaintexts"]:
         raise MixVerificationError("plaintexts are incorrect")
-    rep["accepted"] = rep["enoughValidProofs"]
+    rep["accepted"] = bool(rep.get("enoughValidProofs", True))
     return rep

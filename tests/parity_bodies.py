@@ -653,7 +653,7 @@ def ec_group_ops(vmx, curve, n):
     assert vals(R.randomElementArray(n, prg, 100)) == oar.ring_random_array(OG, n, ors, 100)
 
 
-def mix_parity(vmx, spec, n, k=3, threshold=2, tmpdir=None, width=1):
+def mix_parity(vmx, spec, n, k=3, threshold=2, tmpdir=None, width=1, mode="mixing", maxciph=None, light=False):
     """A whole mix (keys, `threshold` shuffles, threshold decryption with proofs) on the engine and on the
     oracle from the same seeds: every file of the proof directory is byte-identical; the engine's vmnv
     (vmnv.MixNetElGamalVerifyFiatShamirSession) and the oracle's accept it, also after a round trip through a
@@ -680,9 +680,11 @@ def mix_parity(vmx, spec, n, k=3, threshold=2, tmpdir=None, width=1):
         w = mix.getWidePublicKey(M.fullPublicKey, width).exp(r)
         ors = SeededRandomSource(seed("mix/input"))
         ow = oar.g_exp(OG, opr.wide_key(opk, width), tuple(oar.ring_random_array(OG, n, ors, 100) for _ in range(width)))
-    plain = M.run(w)
+    plain = M.run(w, mode=mode, maxciph=maxciph)
     assert col_values(w) == ow
-    od, oplain = opr.run_mix(OG, oparams, k, threshold, ow, SeededRandomSource(seed("mix/dealer")), width=width)
+    od, oplain = opr.run_mix(OG, oparams, k, threshold, ow, SeededRandomSource(seed("mix/dealer")), width=width,
+                             mode=mode, maxciph=maxciph)
+    assert M.nizkp["type"] == mode.encode()
     assert set(od) == set(M.nizkp)
     for name in sorted(od):
         assert od[name] == M.nizkp[name], name
@@ -697,7 +699,13 @@ def mix_parity(vmx, spec, n, k=3, threshold=2, tmpdir=None, width=1):
     rep = V.verify(nizkp)
     orep = opr.verify_mix(OG, oparams, k, threshold, dict(nizkp))
     assert rep["accepted"] and orep["accepted"]
-    assert rep["shuffles"] == orep["shuffles"] == {l: True for l in range(1, threshold + 1)}
+    shuffled = mode != "decryption"
+    assert rep["shuffles"] == orep["shuffles"] == ({l: True for l in range(1, threshold + 1)} if shuffled else {})
+    assert rep["poscs"] == orep["poscs"] == ({l: True for l in range(1, threshold + 1)}
+                                             if shuffled and maxciph is not None else {})
+    assert rep["decryption"] == orep["decryption"] == (None if mode == "shuffling" else True)
+    if mode != "mixing" or maxciph is not None:
+        return _mix_variants(vmx, vm, V, G, OG, params, oparams, k, threshold, M.nizkp, mode, maxciph, light)
 
     def both_reject(bad):
         for fn, exc in ((lambda: V.verify(bad), vm.VerificationError),
@@ -721,6 +729,71 @@ def mix_parity(vmx, spec, n, k=3, threshold=2, tmpdir=None, width=1):
     missing = vm.ProofDirectory(M.nizkp)
     del missing["proofs/PoSCommitment02.bt"]
     both_reject(missing)
+
+
+def _mix_variants(vmx, vm, V, G, OG, params, oparams, k, threshold, honest, mode, maxciph, light=False):
+    """The engine's vmnv and the oracle's on variants of one honest directory of a shuffling / decryption /
+    pre-computed session: the options of vmnv (what is verified, the expected type) and one corruption per kind of
+    file -- same verdict per party, same accept / reject / fail-stop (MixNetElGamalVerifyFiatShamirSession.java:1318-1668)."""
+    def outcome_engine(d, **kw):
+        Vk = vm.MixNetElGamalVerifyFiatShamirSession(G, params, k, threshold, **kw) if kw else V
+        try:
+            r = Vk.verify(d)
+            return ("verdict", r["accepted"], r["shuffles"], r["poscs"], r["decryption"], r.get("plaintexts"))
+        except vm.VerificationError:
+            return ("failstop",)
+
+    def outcome_oracle(d, **kw):
+        okw = {{"expectedType": "expected_type"}.get(a, a): b for a, b in kw.items()}
+        try:
+            r = opr.verify_mix(OG, oparams, k, threshold, dict(d), **okw)
+            return ("verdict", r["accepted"], r["shuffles"], r["poscs"], r["decryption"], r.get("plaintexts"))
+        except opr.MixVerificationError:
+            return ("failstop",)
+
+    options = (dict(dec=False), dict(posc=False), dict(ccpos=False), dict(posc=False, ccpos=False),
+               dict(expectedType=mode), dict(expectedType="mixing" if mode != "mixing" else "shuffling"))
+    for kw in (options[2:3] + options[5:] if light else options):
+        a, b = outcome_engine(honest, **kw), outcome_oracle(honest, **kw)
+        assert a == b, (kw, a, b)
+    assert outcome_engine(honest, expectedType="mixing" if mode != "mixing" else "shuffling") == ("failstop",)
+    seen = set()
+    for name in sorted(honest):
+        kind = "".join(ch for ch in name if not ch.isdigit())
+        if kind in seen:       # one file of every kind (party 1's)
+            continue
+        seen.add(kind)
+        raw = bytes(honest[name])
+        variants = [raw[:len(raw) // 2]] if light else [raw[:len(raw) // 2], raw + b"\x00"]
+        if len(raw) > 8:
+            for pos in ((len(raw) - 2,) if light else (len(raw) - 2, 6)):
+                b_ = bytearray(raw)
+                b_[pos] ^= 0x04
+                variants.append(bytes(b_))
+        for bad_bytes in variants:
+            bad = vm.ProofDirectory(honest)
+            bad[name] = bad_bytes
+            a, b = outcome_engine(bad), outcome_oracle(bad)
+            assert a == b, (name, len(bad_bytes), a, b)
+            if len(bad_bytes) == len(raw) and name.endswith(".bt") and "PolynomialInExponent" not in name:
+                assert a == ("failstop",) or a[1] is False or not all(a[2].values()) or not all(a[3].values()), (name, a)
+        if light and name.endswith(".bt") and not name.endswith(("Commitment01.bt", "Reply01.bt")):
+            continue
+        missing = vm.ProofDirectory(honest)
+        del missing[name]
+        a, b = outcome_engine(missing), outcome_oracle(missing)
+        assert a == b, (name, "missing", a, b)
+    if maxciph is not None:   # a keep list that keeps the wrong elements (right number): the CCPoS is rejected
+        import numpy as np
+        bad = vm.ProofDirectory(honest)
+        kl = bytearray(bad["proofs/KeepList01.bt"])
+        flags = np.frombuffer(bytes(kl[5:]), dtype=np.uint8).copy()
+        i, j = int(np.flatnonzero(flags == 1)[0]), int(np.flatnonzero(flags == 0)[0])
+        flags[i], flags[j] = 0, 1
+        bad["proofs/KeepList01.bt"] = bytes(kl[:5]) + flags.tobytes()
+        a, b = outcome_engine(bad), outcome_oracle(bad)
+        # (in a mixing session the decryption proof then speaks of another list: fail-stop)
+        assert a == b and (a == ("failstop",) if mode == "mixing" else a[2][1] is False and a[1] is False), (a, b)
 
 
 def ec_edge_cases(vmx, curve):
@@ -1079,7 +1152,7 @@ def concurrent_threads(vmx, bits, n, rounds=6):
     assert computed[0::2] == [want_exp] * rounds and computed[1::2] == [prod] * rounds
 
 
-def native_vmnv_parity(vmx, spec, n, k=3, threshold=2, width=1, thorough=True):
+def native_vmnv_parity(vmx, spec, n, k=3, threshold=2, width=1, thorough=True, mode="mixing", maxciph=None):
     """The native universal verifier (csrc/vmnv_native.cpp, include/vmnv.h) against the Python mirror of
     mixnet/MixNetElGamalVerifyFiatShamirSession on the same proof directories: an honest mix, and the same mix with
     one file at a time corrupted / truncated / emptied / missing -- identical verdicts per shuffle, identical
@@ -1099,35 +1172,43 @@ def native_vmnv_parity(vmx, spec, n, k=3, threshold=2, width=1, thorough=True):
     else:
         r = mix.getPlainPGroup(G, width).getPRing().randomElementArray(n, irs, 100)
         w = mix.getWidePublicKey(M.fullPublicKey, width).exp(r)
-    M.run(w).free()
+    M.run(w, mode=mode, maxciph=maxciph).free()
     VP = vm.MixNetElGamalVerifyFiatShamirSession(G, params, k, threshold)
     VN = vn.MixNetElGamalVerifyFiatShamirSessionNative(G, params, k, threshold)
 
     def outcome(V, d):
         try:
             r = V.verify(d)
-            return ("verdict", r["accepted"], r["shuffles"], r["decryption"], r.get("plaintexts"))
+            return ("verdict", r["type"], r["accepted"], r["shuffles"], r["poscs"], r["decryption"], r.get("plaintexts"))
         except vm.VerificationError:
-            return ("failstop", V.report.get("shuffles"))
+            return ("failstop", V.report.get("shuffles"), V.report.get("poscs"))
 
     honest = outcome(VN, M.nizkp)
-    assert honest == outcome(VP, M.nizkp) and honest[:2] == ("verdict", True), honest
+    assert honest == outcome(VP, M.nizkp) and honest[:3] == ("verdict", mode, True), honest
     assert VN.report["hashed_bytes"] > 0 and VN.report["launches"] > 0
+    # what is verified (-nodec, -noposc, -noccpos) and the expected type (-mix, -shuffle, -decrypt)
+    for kw in (dict(dec=False), dict(posc=False), dict(ccpos=False), dict(posc=False, ccpos=False),
+               dict(expectedType=mode), dict(expectedType="shuffling" if mode == "mixing" else "mixing")):
+        a = outcome(vn.MixNetElGamalVerifyFiatShamirSessionNative(G, params, k, threshold, **kw), M.nizkp)
+        b = outcome(vm.MixNetElGamalVerifyFiatShamirSession(G, params, k, threshold, **kw), M.nizkp)
+        assert a == b, (kw, a, b)
     # the -auxsid / -width options
     for kw, ok in ((dict(expectedAuxsid="run 7"), True), (dict(expectedAuxsid="other"), False),
                    (dict(expectedWidth=width), True), (dict(expectedWidth=width + 1), False)):
         got = outcome(vn.MixNetElGamalVerifyFiatShamirSessionNative(G, params, k, threshold, **kw), M.nizkp)
-        assert (got[0] == "verdict" and got[1]) == ok, (kw, got)
+        assert (got[0] == "verdict" and got[2]) == ok, (kw, got)
     names = sorted(M.nizkp)
     if thorough:    # every kind of file once (party 1's of each), every header file
         names = [nm for nm in names if not nm.endswith(("02.bt", "03.bt"))]
     else:
-        names = [nm for nm in names if nm.endswith(("PoSReply01.bt", "DecrFactCommitment02.bt", "Plaintexts.bt"))]
+        names = [nm for nm in names if nm.endswith(("PoSReply01.bt", "DecrFactCommitment02.bt", "Plaintexts.bt",
+                                                    "CCPoSReply01.bt", "KeepList02.bt", "PoSCCommitment02.bt"))]
     nested = b"\x00\x00\x00\x00\x01" * 3000
     for name in names:
         raw = bytes(M.nizkp[name])
         variants = [raw[:len(raw) // 2]]
-        if name.endswith(("PoSReply01.bt", "DecrFactCommitment01.bt", "width", "activethreshold")):
+        if name.endswith(("PoSReply01.bt", "DecrFactCommitment01.bt", "width", "activethreshold", "maxciph", "type",
+                          "KeepList01.bt", "CCPoSCommitment01.bt", "PermutationCommitment01.bt")):
             variants += [b"", nested, raw + b"\x00"]
         if len(raw) > 8:
             for pos in ((len(raw) // 2, 6) if name.endswith("PoSCommitment01.bt") else (len(raw) - 2,)):
@@ -1143,3 +1224,125 @@ def native_vmnv_parity(vmx, spec, n, k=3, threshold=2, width=1, thorough=True):
             missing = vm.ProofDirectory(M.nizkp)
             del missing[name]
             assert outcome(VN, missing) == outcome(VP, missing), name
+
+
+def _fuzz_mutation(rng, nizkp, names):
+    """One random structure-aware mutation of a proof directory: (description, {name: bytes or None})."""
+    name = names[rng.randrange(len(names))]
+    raw = bytes(nizkp[name])
+    kind = rng.randrange(11)
+    if kind == 0 and raw:                                   # flip one bit anywhere
+        pos = rng.randrange(len(raw))
+        b = bytearray(raw)
+        b[pos] ^= 1 << rng.randrange(8)
+        return "%s: bit flip at %d" % (name, pos), {name: bytes(b)}
+    if kind == 1 and len(raw) >= 5:                         # damage a byte-tree header (tag, count or length)
+        heads = [i for i in range(0, len(raw) - 4) if raw[i] in (0, 1) and raw[i + 1] == 0 and raw[i + 2] == 0][:64]
+        pos = heads[rng.randrange(len(heads))] if heads else 0
+        b = bytearray(raw)
+        field = rng.randrange(3)
+        if field == 0:
+            b[pos] = rng.choice([0, 1, 2, 0xFF])
+        else:
+            b[pos + 1:pos + 5] = rng.choice([0, 1, 2, 3, 0x7FFFFFFF, 0xFFFFFFFF, len(raw), rng.randrange(1 << 32),
+                                             max(0, int.from_bytes(raw[pos + 1:pos + 5], "big") + rng.choice([-1, 1]))
+                                             ]).to_bytes(4, "big")
+        return "%s: header at %d" % (name, pos), {name: bytes(b)}
+    if kind == 2:                                           # truncate anywhere
+        cut = rng.randrange(len(raw) + 1)
+        return "%s: truncated to %d" % (name, cut), {name: raw[:cut]}
+    if kind == 3:                                           # trailing bytes
+        extra = bytes(rng.randrange(256) for _ in range(rng.randrange(1, 9)))
+        return "%s: %d trailing bytes" % (name, len(extra)), {name: raw + extra}
+    if kind == 4 and len(raw) > 12:                         # overwrite a run with 0x00 / 0xff / random
+        pos = rng.randrange(len(raw) - 4)
+        ln = rng.randrange(1, min(64, len(raw) - pos))
+        fill = rng.choice([b"\x00", b"\xff", None])
+        b = bytearray(raw)
+        b[pos:pos + ln] = (fill * ln) if fill else bytes(rng.randrange(256) for _ in range(ln))
+        return "%s: run of %d at %d" % (name, ln, pos), {name: bytes(b)}
+    if kind == 5:                                           # swap with another file of the directory
+        other = names[rng.randrange(len(names))]
+        return "%s <-> %s" % (name, other), {name: bytes(nizkp[other]), other: raw}
+    if kind == 6:                                           # missing
+        return "%s: missing" % name, {name: None}
+    if kind == 7:                                           # deep nesting / empty node / empty leaf / empty file
+        v = rng.choice([b"", b"\x00\x00\x00\x00\x00", b"\x01\x00\x00\x00\x00", b"\x00\x00\x00\x00\x01" * 5000,
+                        b"\x00\xff\xff\xff\xff", b"\x01\xff\xff\xff\xff", b"\x00\x00\x00\x00\x02" + raw + raw])
+        return "%s: replaced by %d special bytes" % (name, len(v)), {name: v}
+    if kind == 8 and len(raw) > 16:                         # delete or duplicate a slice (shifts everything behind it)
+        pos = rng.randrange(len(raw) - 8)
+        ln = rng.randrange(1, min(600, len(raw) - pos))
+        if rng.randrange(2):
+            return "%s: %d bytes deleted at %d" % (name, ln, pos), {name: raw[:pos] + raw[pos + ln:]}
+        return "%s: %d bytes doubled at %d" % (name, ln, pos), {name: raw[:pos + ln] + raw[pos:]}
+    if kind == 9 and len(raw) > 40:                         # an element set to 0, 1, p - 1 style patterns: last bytes of a leaf
+        pos = rng.randrange(len(raw) - 8)
+        b = bytearray(raw)
+        b[pos:pos + 8] = rng.choice([b"\x00" * 8, b"\x00" * 7 + b"\x01", b"\xff" * 8, b"\x80" + b"\x00" * 7])
+        return "%s: word pattern at %d" % (name, pos), {name: bytes(b)}
+    # text files: other integers and junk
+    v = rng.choice([b"0", b"-1", b"1", b"2", b"3", b"64", b"65", b"1025", b"99999999999", b" 1", b"1\n", b"+1", b"0x1",
+                    b"mixing", b"shuffling", b"", b"\xff\xfe", b"1e3"])
+    return "%s: text %r" % (name, v), {name: v}
+
+
+def native_vmnv_fuzz(vmx, spec, n, rounds, seed_label="fuzz", k=3, threshold=2, width=1, log=None, mode="mixing",
+                     maxciph=None):
+    """Differential fuzzing of the native universal verifier against the Python mirror: `rounds` random
+    structure-aware mutations of an honest proof directory (bit flips, damaged headers, truncations, trailing
+    bytes, swapped / missing / deeply nested files, junk in the text files); both must reach the same outcome --
+    verdict per shuffle, decryption, plaintexts, accept / reject / fail-stop -- and neither may raise anything but
+    VerificationError (mixnet/MixNetElGamalVerifyFiatShamirSession.java:1318-1668 never aborts on a bad proof)."""
+    import random as _random
+    vm = importlib.import_module("verificatum-vmn_b200.vmnv")
+    vn = importlib.import_module("verificatum-vmn_b200.vmnv_native")
+    mix = importlib.import_module("verificatum-vmn_b200.mixnet")
+    G = engine_group(vmx, spec)
+    params = mix.SessionParams(pGroupString="fuzz-%s" % spec, sid="Session_1")
+    rs = vmx.crypto.PRGHeuristic()
+    rs.setSeed(seed("fuzz/dealer"))
+    M = vm.MixNetElGamal(G, params, k, threshold, rs, width=width, auxsid="fuzz")
+    irs = vmx.crypto.PRGHeuristic()
+    irs.setSeed(seed("fuzz/input"))
+    if width == 1:
+        w = mix.demoCiphertexts(M.fullPublicKey, n, irs)
+    else:
+        r = mix.getPlainPGroup(G, width).getPRing().randomElementArray(n, irs, 100)
+        w = mix.getWidePublicKey(M.fullPublicKey, width).exp(r)
+    M.run(w, mode=mode, maxciph=maxciph).free()
+    VP = vm.MixNetElGamalVerifyFiatShamirSession(G, params, k, threshold)
+    VN = vn.MixNetElGamalVerifyFiatShamirSessionNative(G, params, k, threshold)
+
+    def outcome(V, d):
+        try:
+            r = V.verify(d)
+            return ("verdict", r["accepted"], r["shuffles"], r["poscs"], r["decryption"], r.get("plaintexts"))
+        except vm.VerificationError:
+            return ("failstop", V.report.get("shuffles"), V.report.get("poscs"))
+
+    rng = _random.Random(seed_label)
+    names = sorted(M.nizkp)
+    tally = {}
+    for i in range(rounds):
+        muts = {}
+        what = []
+        for _ in range(1 if rng.randrange(4) else 2):      # one mutation, sometimes two at once
+            d, m = _fuzz_mutation(rng, M.nizkp, names)
+            what.append(d)
+            muts.update(m)
+        bad = vm.ProofDirectory(M.nizkp)
+        for nm, v in muts.items():
+            if v is None:
+                if nm in bad:
+                    del bad[nm]
+            else:
+                bad[nm] = v
+        a, b = outcome(VN, bad), outcome(VP, bad)
+        assert a == b, (i, what, a, b)
+        key = a[0] if a[0] == "failstop" else ("accepted" if a[1] else "rejected")
+        tally[key] = tally.get(key, 0) + 1
+        if log is not None:
+            log("%4d %-9s %s" % (i, key, "; ".join(what)))
+    assert outcome(VN, M.nizkp)[:2] == ("verdict", True)   # and the honest directory still verifies afterwards
+    return tally

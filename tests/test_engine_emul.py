@@ -133,6 +133,16 @@ def test_mix_and_vmnv_parity_wide(engine_emul, spec, width, n, tmp_path):
     pb.mix_parity(engine_emul, spec, n, tmpdir=tmp_path, width=width)
 
 
+@pytest.mark.parametrize("mode,maxciph,width,light", [("mixing", 6, 1, True), ("shuffling", None, 1, True),
+                                                      ("shuffling", 5, 2, True), ("decryption", None, 2, False)])
+def test_mix_session_types(engine_emul, mode, maxciph, width, light):
+    """Sessions of type "shuffling" and "decryption", and sessions after a pre-computation (proofs of shuffles of
+    commitments, keep lists, commitment-consistent proofs of shuffles): proof directories byte-identical to the
+    oracle's, same verdicts on honest and corrupted directories and under every option of vmnv
+    (mixnet/MixNetElGamalSession.java:161-358, mixnet/MixNetElGamalVerifyFiatShamirSession.java:1318-1668)."""
+    pb.mix_parity(engine_emul, 512, 3, width=width, mode=mode, maxciph=maxciph, light=light)
+
+
 def test_malformed_proof_files_are_verdicts_not_crashes(engine_emul):
     pb.malformed_proof_files(engine_emul, 512, 3)
 

@@ -40,3 +40,20 @@ def test_native_verifier_curve_group(engine_emul, vmnv_lib):
     """ECqPGroup proofs: points as node(x, y), arrays as node(x leaves, y leaves), on-curve checks by the engine."""
     pb.native_vmnv_parity(engine_emul, "P-256", 4, thorough=False)
     pb.native_vmnv_parity(engine_emul, "P-256", 3, width=2, thorough=False)
+
+
+@pytest.mark.parametrize("mode,maxciph,width,thorough", [("mixing", 6, 1, False), ("shuffling", 5, 2, False),
+                                                         ("shuffling", None, 1, False), ("decryption", None, 1, True)])
+def test_native_verifier_session_types(engine_emul, vmnv_lib, mode, maxciph, width, thorough):
+    """Proofs of type "shuffling" / "decryption" and proofs after a pre-computation (PoSC, keep lists, CCPoS), the
+    options -nodec / -noposc / -noccpos and the expected type: same outcome as the mirror."""
+    pb.native_vmnv_parity(engine_emul, 512, 3, width=width, mode=mode, maxciph=maxciph, thorough=thorough)
+
+
+def test_native_verifier_differential_fuzz(engine_emul, vmnv_lib):
+    """A seeded sample of the differential fuzzer (tools/fuzz_vmnv.py runs thousands of rounds under ASan)."""
+    rounds = int(os.environ.get("VMNV_FUZZ_ROUNDS", "15"))
+    tally = pb.native_vmnv_fuzz(engine_emul, 512, 3, rounds=rounds)
+    assert sum(tally.values()) == rounds and tally.get("failstop", 0) > 0
+    tally = pb.native_vmnv_fuzz(engine_emul, 512, 3, rounds=rounds, mode="mixing", maxciph=5, seed_label="fuzz/precomp")
+    assert sum(tally.values()) == rounds and tally.get("failstop", 0) > 0

@@ -45,7 +45,8 @@ namespace {
   X(vmx_garr_prg_sha256) X(vmx_exp_fixed) X(vmx_elem_exp) X(vmx_elem_inv) X(vmx_exp_scalar_var) X(vmx_expprod)     \
   X(vmx_expprod_cols) X(vmx_mul) X(vmx_inv) X(vmx_prod) X(vmx_shift_push) X(vmx_equals) X(vmx_get)                 \
   X(vmx_rarr_from_leaves) X(vmx_rarr_from_bytes) X(vmx_rarr_to_bytes) X(vmx_rarr_prg_sha256) X(vmx_rarr_prg_raw_sha256) X(vmx_rarr_free)      \
-  X(vmx_rprod) X(vmx_rmul) X(vmx_radd) X(vmx_leaves_uniform) X(vmx_ctx_launch_count) X(vmx_fixed_precompute)
+  X(vmx_rprod) X(vmx_rmul) X(vmx_radd) X(vmx_leaves_uniform) X(vmx_ctx_launch_count) X(vmx_fixed_precompute)   \
+  X(vmx_extract) X(vmx_slice)
 
 struct Api {
 #define X(name) decltype(&::name) name = nullptr;
@@ -585,8 +586,12 @@ struct Session {
   Bytes challenge_finish(Oracle& o) { Bytes r = o.finish(); hashed += o.hashed; return r; }
 
   // ---- hvzk/PoSTW.java:177-260 over hvzk/PoSBasicTW.java: one proof of a shuffle
-  bool verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n, const CiphArr& w, const CiphArr& wp, Span wFile,
-                      Span wpFile, Span pcFile, Span commitFile, Span replyFile, const Elem& y);
+  // (w == nullptr: hvzk/PoSCTW.java:137-210 over hvzk/PoSCBasicTW.java -- the same proof without the ciphertexts)
+  bool verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n, const Garr& u, Span uTree, const CiphArr* w,
+                      const CiphArr* wp, Span wFile, Span wpFile, Span commitFile, Span replyFile, const Elem& y);
+  // ---- hvzk/CCPoSW.java:160-260 over hvzk/CCPoSBasicW.java: one commitment-consistent proof of a shuffle
+  bool verify_ccpos(const Garr& h, Span hTree, size_t n, const Garr& u, Span uTree, const CiphArr& w, const CiphArr& wp,
+                    Span wFile, Span wpFile, Span commitFile, Span replyFile, const Elem& y);
 
   void run(vmxv_report* rep);
 };
@@ -602,37 +607,28 @@ bool parse_int_strict(const std::string& s, long* out) {
 
 std::string two(int l) { char b[16]; snprintf(b, sizeof b, "%02d", l); return b; }
 
-bool Session::verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n, const CiphArr& w, const CiphArr& wp,
-                             Span wFile, Span wpFile, Span pcFile, Span commitFile, Span replyFile, const Elem& y) {
-  const int W = width, K = 2 * W;
+bool Session::verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n, const Garr& u, Span uTree,
+                             const CiphArr* wq, const CiphArr* wpq, Span wFile, Span wpFile, Span commitFile,
+                             Span replyFile, const Elem& y) {
+  const bool ciph = wq != nullptr;   // PoS (ciphertexts) or PoSC (commitments only)
+  const int W = width, K = ciph ? 2 * W : 0;
   std::vector<std::unique_ptr<Bytes>> store;  // serialisations that must outlive the hashing
-  // permutation commitment u (PoSBasicTW.java:505-514); malformed -> the generators themselves
-  Garr u;
-  bool u_from_file = true;
-  try {
-    u = parse_garr(C, pcFile, n);
-  } catch (const Malformed&) {
-    vmx_garr* cp = nullptr;
-    Garr one = garr_fill(C, n, C.one);
-    check(api.vmx_mul(h.h, one.h, &cp), "vmx_mul");   // a copy of h
-    u = Garr(cp);
-    u_from_file = false;
-  }
-  // seed = RO(rho || node(g, h, u, pk, w, w'))  (PoSTW.java:118-124), hashed beside the imports below
+  // seed = RO(rho || node(g, h, u, pk, w, w'))  (PoSTW.java:118-124), hashed beside the imports below;
+  //        RO(rho || node(g, h, u)) for a proof of a shuffle of commitments (PoSCTW.java:90-92)
   Oracle seedO(prefix, 256);
-  seedO.update_owned(header(NODE, 6));
+  seedO.update_owned(header(NODE, ciph ? 6 : 3));
   seedO.update_owned(elem_tree(C, C.g));
   seedO.update(hTree);
-  if (u_from_file && pcFile.n == garr_tree_bytes(C, n)) seedO.update(pcFile); else seedO.update(garr_tree(C, u, n, store));
-  seedO.update_owned(header(NODE, 2));
-  {
+  seedO.update(uTree);
+  if (ciph) {
+    seedO.update_owned(header(NODE, 2));
     PlainElem gs((size_t)W, C.g), ys((size_t)W, y);
     hash_plain_elem(C, seedO, gs);
     hash_plain_elem(C, seedO, ys);
+    // w and w' were parsed from these files (fail-stop otherwise); their trees are the files when canonical
+    if (wFile.n == ciph_arr_tree_bytes(C, W, n)) seedO.update(wFile); else hash_ciph_arr(C, seedO, *wq, W, n, store);
+    if (wpFile.n == ciph_arr_tree_bytes(C, W, n)) seedO.update(wpFile); else hash_ciph_arr(C, seedO, *wpq, W, n, store);
   }
-  // w and w' were parsed from these files (fail-stop otherwise); their trees are the files when canonical
-  if (wFile.n == ciph_arr_tree_bytes(C, W, n)) seedO.update(wFile); else hash_ciph_arr(C, seedO, w, W, n, store);
-  if (wpFile.n == ciph_arr_tree_bytes(C, W, n)) seedO.update(wpFile); else hash_ciph_arr(C, seedO, wp, W, n, store);
 
   // commitment (:780-823): node(B, A', B', C', D', F'); anything malformed -> all trivial
   Garr B, Bp;
@@ -640,14 +636,15 @@ bool Session::verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n
   std::vector<Elem> Fp;  // 2 * width components
   bool malformed = false;
   try {
-    const std::vector<Span> ch = first_children(commitFile, 6);
+    const std::vector<Span> ch = first_children(commitFile, ciph ? 6 : 5);
     B = parse_garr(C, ch[0], n);
     Ap = parse_elem(C, ch[1]);
     Bp = parse_garr(C, ch[2], n);
     Cp = parse_elem(C, ch[3]);
     Dp = parse_elem(C, ch[4]);
-    for (Span half : children(ch[5], 2))
-      for (Span part : plain_parts(half, W)) Fp.push_back(parse_elem(C, part));
+    if (ciph)
+      for (Span half : children(ch[5], 2))
+        for (Span part : plain_parts(half, W)) Fp.push_back(parse_elem(C, part));
   } catch (const Malformed&) {
     malformed = true;
   }
@@ -663,13 +660,14 @@ bool Session::verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n
   Rarr kB, kE;
   bool parsed = true;
   try {
-    const std::vector<Span> ch = first_children(replyFile, 6);
+    const std::vector<Span> ch = first_children(replyFile, ciph ? 6 : 5);
     kA = parse_scalar(C, ch[0]);
     kB = parse_rarr(C, ch[1], n);
     kC = parse_scalar(C, ch[2]);
     kD = parse_scalar(C, ch[3]);
     kE = parse_rarr(C, ch[4], n);
-    for (Span part : plain_parts(ch[5], W)) kF.push_back(parse_scalar(C, part));
+    if (ciph)
+      for (Span part : plain_parts(ch[5], W)) kF.push_back(parse_scalar(C, part));
   } catch (const Malformed&) {
     parsed = false;
   }
@@ -681,7 +679,7 @@ bool Session::verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n
   if (parsed) {
     Cc = elem_mul(C, arr_prod(C, u), elem_inv(C, arr_prod(C, h)));                      // :1013
     std::vector<const Garr*> arrs{&h};
-    for (const Garr& a : wp.c) arrs.push_back(&a);
+    if (ciph) for (const Garr& a : wpq->c) arrs.push_back(&a);
     const std::vector<Elem> pe = expprod_many(C, arrs, kE);                              // :1021, :1063
     rightA = elem_mul(C, elem_exp(C, C.g, kA), pe[0]);
     vmx_garr* t = nullptr;
@@ -706,26 +704,28 @@ bool Session::verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n
   chalO.update_owned(header(NODE, 2));
   chalO.update_owned(leaf_tree(prgSeed));
   const size_t plainElemBytes = W == 1 ? elem_tree_bytes(C) : 5 + (size_t)W * elem_tree_bytes(C);
-  const bool commit_canonical = !malformed && read_hdr(commitFile, 0).count == 6 &&
-      commitFile.n == 5 + 2 * garr_tree_bytes(C, n) + 3 * elem_tree_bytes(C) + 5 + 2 * plainElemBytes;
+  const bool commit_canonical = !malformed && read_hdr(commitFile, 0).count == (ciph ? 6u : 5u) &&
+      commitFile.n == 5 + 2 * garr_tree_bytes(C, n) + 3 * elem_tree_bytes(C) + (ciph ? 5 + 2 * plainElemBytes : 0);
   if (commit_canonical) {
     chalO.update(commitFile);
   } else {
-    chalO.update_owned(header(NODE, 6));
+    chalO.update_owned(header(NODE, ciph ? 6 : 5));
     chalO.update(garr_tree(C, B, n, store));
     chalO.update_owned(elem_tree(C, Ap));
     chalO.update(garr_tree(C, Bp, n, store));
     chalO.update_owned(elem_tree(C, Cp));
     chalO.update_owned(elem_tree(C, Dp));
-    chalO.update_owned(header(NODE, 2));
-    for (int half = 0; half < 2; half++) {
-      PlainElem pe_(Fp.begin() + half * W, Fp.begin() + (half + 1) * W);
-      hash_plain_elem(C, chalO, pe_);
+    if (ciph) {
+      chalO.update_owned(header(NODE, 2));
+      for (int half = 0; half < 2; half++) {
+        PlainElem pe_(Fp.begin() + half * W, Fp.begin() + (half + 1) * W);
+        hash_plain_elem(C, chalO, pe_);
+      }
     }
   }
   // A = prod u^e, F = prod w^e  (:407-410), while the challenge is hashed
   std::vector<const Garr*> arrs{&u};
-  for (const Garr& a : w.c) arrs.push_back(&a);
+  if (ciph) for (const Garr& a : wq->c) arrs.push_back(&a);
   const std::vector<Elem> AF = expprod_many(C, arrs, e);
   const Bytes vBytes = challenge_finish(chalO);
   if (!parsed) return false;
@@ -746,6 +746,86 @@ bool Session::verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n
   bool okF = true;
   for (int i = 0; i < K; i++) okF = okF && elem_mul(C, elem_exp(C, AF[(size_t)(1 + i)], v), Fp[(size_t)i]) == rightF[(size_t)i];   // :1062-1063
   return okA && okB && okC && okD && okF;
+}
+
+bool Session::verify_ccpos(const Garr& h, Span hTree, size_t n, const Garr& u, Span uTree, const CiphArr& w, const CiphArr& wp,
+                           Span wFile, Span wpFile, Span commitFile, Span replyFile, const Elem& y) {
+  const int W = width, K = 2 * W;
+  std::vector<std::unique_ptr<Bytes>> store;
+  // seed = RO(rho || node(g, h, u, pk, w, w'))  (CCPoSW.java:92-98)
+  Oracle seedO(prefix, 256);
+  seedO.update_owned(header(NODE, 6));
+  seedO.update_owned(elem_tree(C, C.g));
+  seedO.update(hTree);
+  seedO.update(uTree);
+  seedO.update_owned(header(NODE, 2));
+  {
+    PlainElem gs((size_t)W, C.g), ys((size_t)W, y);
+    hash_plain_elem(C, seedO, gs);
+    hash_plain_elem(C, seedO, ys);
+  }
+  if (wFile.n == ciph_arr_tree_bytes(C, W, n)) seedO.update(wFile); else hash_ciph_arr(C, seedO, w, W, n, store);
+  if (wpFile.n == ciph_arr_tree_bytes(C, W, n)) seedO.update(wpFile); else hash_ciph_arr(C, seedO, wp, W, n, store);
+  // commitment (CCPoSBasicW.java:408-431): node(A', B'), B' a ciphertext; malformed -> both trivial
+  Elem Ap;
+  std::vector<Elem> Bp;  // 2 * width components
+  try {
+    const std::vector<Span> ch = first_children(commitFile, 2);
+    Ap = parse_elem(C, ch[0]);
+    for (Span half : children(ch[1], 2))
+      for (Span part : plain_parts(half, W)) Bp.push_back(parse_elem(C, part));
+  } catch (const Malformed&) {
+    Ap = C.one;
+    Bp.assign((size_t)K, C.one);
+  }
+  // reply (:519-552): node(k_A, k_B, k_E); malformed -> reject once the challenge is derived
+  Scalar kA;
+  std::vector<Scalar> kB;  // width components
+  Rarr kE;
+  bool parsed = true;
+  try {
+    const std::vector<Span> ch = first_children(replyFile, 3);
+    kA = parse_scalar(C, ch[0]);
+    for (Span part : plain_parts(ch[1], W)) kB.push_back(parse_scalar(C, part));
+    kE = parse_rarr(C, ch[2], n);
+  } catch (const Malformed&) {
+    parsed = false;
+  }
+  // the right-hand sides g^k_A * prod h^k_E and pk^-k_B * prod w'^k_E (:554-579), queued while the seed is hashed
+  Elem rightA;
+  std::vector<Elem> rightB;
+  if (parsed) {
+    std::vector<const Garr*> arrs{&h};
+    for (const Garr& a : wp.c) arrs.push_back(&a);
+    const std::vector<Elem> pe = expprod_many(C, arrs, kE);
+    rightA = elem_mul(C, elem_exp(C, C.g, kA), pe[0]);
+    for (int i = 0; i < K; i++) {
+      const Scalar nk = scalar_neg(C, kB[(size_t)(i % W)]);
+      rightB.push_back(elem_mul(C, elem_exp(C, i < W ? C.g : y, nk), pe[(size_t)(1 + i)]));
+    }
+  }
+  const Bytes prgSeed = challenge_finish(seedO);
+  Rarr e = batch_vector(C, prgSeed, n, (unsigned)P->ebitlenro);
+  Oracle chalO(prefix, (unsigned)P->vbitlenro);
+  chalO.update_owned(header(NODE, 2));
+  chalO.update_owned(leaf_tree(prgSeed));
+  chalO.update_owned(header(NODE, 2));
+  chalO.update_owned(elem_tree(C, Ap));
+  chalO.update_owned(header(NODE, 2));
+  for (int half = 0; half < 2; half++) {
+    PlainElem pe_(Bp.begin() + half * W, Bp.begin() + (half + 1) * W);
+    hash_plain_elem(C, chalO, pe_);
+  }
+  // A = prod u^e, B = prod w^e  (:493-506), while the challenge is hashed
+  std::vector<const Garr*> arrs{&u};
+  for (const Garr& a : w.c) arrs.push_back(&a);
+  const std::vector<Elem> AB = expprod_many(C, arrs, e);
+  const Bytes vBytes = challenge_finish(chalO);
+  if (!parsed) return false;
+  const Scalar v = scalar_from_bytes(C, vBytes);
+  bool ok = elem_mul(C, elem_exp(C, AB[0], v), Ap) == rightA;
+  for (int i = 0; i < K; i++) ok = ok && elem_mul(C, elem_exp(C, AB[(size_t)(1 + i)], v), Bp[(size_t)i]) == rightB[(size_t)i];
+  return ok;
 }
 
 // modified Lagrange coefficients (elgamal/DistrElGamalSessionBasic.java:290-452): small signed integers
@@ -808,16 +888,26 @@ std::vector<Scalar> lagrange(const Ctx& C, const std::vector<bool>& correct, int
 
 void Session::run(vmxv_report* rep) {
   const int k = P->k, threshold = P->threshold;
+  const size_t kVerdicts = sizeof rep->shuffles / sizeof rep->shuffles[0];
   // ---- header files (MixNetElGamalVerifyFiatShamirSession.java:1318-1360)
   if (text("version") != P->version) fail_stop("Mismatching versions!");
-  if (text("type") != "mixing") fail_stop("Unsupported proof type");
+  // determineType :329-358, determineSessionParams :984-1005
+  const std::string type = text("type");
+  if (type != "mixing" && type != "shuffling" && type != "decryption") fail_stop("Unknown type of proof!");
+  if (P->expected_type && P->expected_type[0] && type != P->expected_type)
+    fail_stop("Attempting to verify proof of %s, but proof is a proof of %s!", P->expected_type, type.c_str());
+  rep->type = type == "mixing" ? 0 : type == "shuffling" ? 1 : 2;
   const std::string auxsid = text("auxsid");
   bool sid_ok = !auxsid.empty() && auxsid.size() <= 1024;
   for (char ch : auxsid) sid_ok = sid_ok && (std::isalnum((unsigned char)ch) || ch == '_' || ch == ' ') && (unsigned char)ch < 128;
   if (!sid_ok) fail_stop("Can not read auxsid from file!");
   if (P->expected_auxsid && P->expected_auxsid[0] && auxsid != P->expected_auxsid)
     fail_stop("The given auxiliary session identifier does not match the one in the proof!");
-  {
+  bool dec = !P->nodec, posc = !P->noposc, ccpos = !P->noccpos;
+  if (type == "shuffling") dec = false;
+  else if (type == "decryption") posc = ccpos = false;
+  width = 1;
+  if (ccpos || dec) {
     long wv = 0;
     if (!parse_int_strict(text("width"), &wv)) fail_stop("Can not parse width given in file!");
     if (wv < 1 || wv > 1024 || (P->expected_width > 0 && wv != P->expected_width)) fail_stop("Mismatching or invalid width!");
@@ -846,23 +936,26 @@ void Session::run(vmxv_report* rep) {
   } catch (const Malformed&) {
     fail_stop("Could not read full El Gamal public key from file!");
   }
-  try {
-    for (Span c : children(file("proofs/PolynomialInExponent.bt"), threshold)) coeffs.push_back(parse_elem(C, c));
-  } catch (const Malformed&) {
-    fail_stop("Unable to read polynomial in exponent from file!");
-  }
-  if (coeffs[0] != y) fail_stop("Mismatching public keys!");
   // window tables of the bases every proof raises to full-length exponents: g (arrays and single elements), the
   // public key y and h0 (single elements: a small table turns a 3071-step ladder on one warp, ~20 ms, into a few
   // multiplications per thread); they stay with the cached context for the next verification
   check(api.vmx_fixed_precompute(C.c, y.data(), 16), "vmx_fixed_precompute");
-  std::vector<Elem> pkeys((size_t)k + 1);
-  for (int l = 1; l <= k; l++) {  // PolynomialInExponent.evaluate(l) = prod_i coeffs[i]^(l^i), by Horner's rule in the
-    Elem acc = coeffs.back();     // exponent (l^i itself leaves 64 bits for a hundred parties and a threshold of 11)
-    const Scalar ls = scalar_from_u64(C, (uint64_t)l);
-    for (size_t i = coeffs.size() - 1; i-- > 0;) acc = elem_mul(C, elem_exp(C, acc, ls), coeffs[i]);
-    pkeys[(size_t)l] = acc;
+  if (dec) {   // readMixServerPKeys :228-266
+    try {
+      for (Span c : children(file("proofs/PolynomialInExponent.bt"), threshold)) coeffs.push_back(parse_elem(C, c));
+    } catch (const Malformed&) {
+      fail_stop("Unable to read polynomial in exponent from file!");
+    }
+    if (coeffs[0] != y) fail_stop("Mismatching public keys!");
+    std::vector<Elem> pkeys((size_t)k + 1);
+    for (int l = 1; l <= k; l++) {  // PolynomialInExponent.evaluate(l) = prod_i coeffs[i]^(l^i), by Horner's rule in the
+      Elem acc = coeffs.back();     // exponent (l^i itself leaves 64 bits for a hundred parties and a threshold of 11)
+      const Scalar ls = scalar_from_u64(C, (uint64_t)l);
+      for (size_t i = coeffs.size() - 1; i-- > 0;) acc = elem_mul(C, elem_exp(C, acc, ls), coeffs[i]);
+      pkeys[(size_t)l] = acc;
+    }
   }
+  const bool precomp = has("proofs/maxciph");                                                     // :946-948
   int active = 0;
   {
     long a = 0;
@@ -870,61 +963,54 @@ void Session::run(vmxv_report* rep) {
     if (a > k || a < threshold) fail_stop("Active threshold out of range!");
     active = (int)a;
   }
-  // ---- input ciphertexts
-  const Span ctFile = file("Ciphertexts.bt");
-  size_t n = 0;
-  try {
-    Span s = children(ctFile, 2)[0];
-    if (W > 1) s = children(s, W)[0];
-    if (C.curve) s = children(s, 2)[0];   // an array over a curve is node(x leaves, y leaves)
-    const Hdr h = read_hdr(s, 0);
-    if (h.kind != NODE) throw Malformed("array expected");
-    n = h.count;
-  } catch (const Malformed&) {
-    fail_stop("Unable to read ciphertexts!");
-  }
-  if (n == 0) fail_stop("No ciphertexts!");
-  auto read_ciph = [&](Span s, const std::string& name) {
+  // ---- input ciphertexts (readCiphertexts :1017-1046; readArray with size 0: the size is that of the first array)
+  auto read_ciph = [&](Span s, const std::string& name, size_t n) {
     try {
       return parse_ciph_arr(C, s, W, n);
     } catch (const Malformed& e) {
       fail_stop("Unable to read array %s! (%s)", name.c_str(), e.what());
     }
   };
-  CiphArr ciphertexts = read_ciph(ctFile, "Ciphertexts.bt");
-  // ---- independent generators (distr/IndependentGeneratorsRO.java:110-130)
-  Garr h;
-  {
-    Sha256 d;
-    uint8_t b4[4];
-    put_be32(b4, 256);
-    d.update(b4, 4);
-    d.update(prefix.data(), prefix.size());
-    const std::string sid = "generators";
-    Bytes leaf = header(LEAF, (uint32_t)sid.size());
-    leaf.insert(leaf.end(), sid.begin(), sid.end());
-    d.update(leaf.data(), leaf.size());
-    const Bytes seed = prg_bytes(d.digest(), 32);
-    size_t pbits = 0;
-    for (size_t i = 0; i < P->nbytes; i++) if (P->p_be[i]) { pbits = 8 * (P->nbytes - i); for (uint8_t v = P->p_be[i]; !(v & 0x80); v <<= 1) pbits--; break; }
-    const size_t bits = pbits + (size_t)P->rbitlen;
-    vmx_garr* a = nullptr;
-    check(api.vmx_garr_prg_sha256(C.c, seed.data(), seed.size(), 0, n, (bits + 7) / 8, (unsigned)bits, &a), "vmx_garr_prg_sha256");
-    h = Garr(a);
+  std::unique_ptr<CiphArr> ciphertexts;
+  std::string ctName;
+  Span ctFile;
+  size_t n = 0;
+  if (ccpos || dec) {
+    if (ccpos || type == "decryption") {
+      ctName = "Ciphertexts.bt";
+      file(ctName);
+    } else if (has("proofs/Ciphertexts" + two(active) + ".bt")) {
+      ctName = "proofs/Ciphertexts" + two(active) + ".bt";
+    }
+    if (!ctName.empty()) {
+      ctFile = file(ctName);
+      try {
+        Span s = children(ctFile, 2)[0];
+        if (W > 1) s = children(s, W)[0];
+        if (C.curve) s = children(s, 2)[0];   // an array over a curve is node(x leaves, y leaves)
+        const Hdr h = read_hdr(s, 0);
+        if (h.kind != NODE) throw Malformed("array expected");
+        n = h.count;
+      } catch (const Malformed&) {
+        fail_stop("Unable to read ciphertexts!");
+      }
+      if (n == 0) fail_stop("No ciphertexts!");
+      ciphertexts = std::make_unique<CiphArr>(read_ciph(ctFile, ctName, n));
+    }
   }
-  const Elem h0 = elem_get(C, h, 0);
-  check(api.vmx_fixed_precompute(C.c, C.g.data(), n), "vmx_fixed_precompute");
-  check(api.vmx_fixed_precompute(C.c, h0.data(), 16), "vmx_fixed_precompute");
-  std::vector<std::unique_ptr<Bytes>> hStore;
-  const Span hTree = garr_tree(C, h, n, hStore);   // the generators are hashed into the seed of every proof
-  // The seed of the decryption proof is RO(node(node(g, L_active), node(node(coeffs), node(f_1..f_k)))) (:1586-1600):
-  // it depends on files only, so it is hashed on its worker thread WHILE the shuffles are verified, on the premise
-  // that the last shuffle is valid and the files canonical; checked below, hashed again if it does not hold.
+  // The seed of the decryption proof is RO(node(node(g, L), node(node(coeffs), node(f_1..f_k)))) (:1586-1600), L the list
+  // that is decrypted: it depends on files only, so it is hashed on its worker thread WHILE the shuffles are verified,
+  // on the premise that L is the last output file (the last shuffle is valid) and the files canonical; checked
+  // below, hashed again if it does not hold.
   std::unique_ptr<Oracle> spec;
-  std::string lastName = "proofs/Ciphertexts" + two(active) + ".bt";
-  if (!has(lastName)) lastName = "ShuffledCiphertexts.bt";
-  {
-    bool all = has(lastName) && files[lastName].n == ciph_arr_tree_bytes(C, W, n);
+  std::string lastName;
+  if (dec) {
+    lastName = ctName;
+    if (ccpos) {
+      lastName = "proofs/Ciphertexts" + two(active) + ".bt";
+      if (!has(lastName)) lastName = "ShuffledCiphertexts.bt";
+    }
+    bool all = !lastName.empty() && has(lastName) && n > 0 && files[lastName].n == ciph_arr_tree_bytes(C, W, n);
     for (int l = 1; l <= k && all; l++) {
       const std::string nm = "proofs/DecryptionFactors" + two(l) + ".bt";
       all = has(nm) && files[nm].n == plain_arr_tree_bytes(C, W, n);
@@ -942,27 +1028,139 @@ void Session::run(vmxv_report* rep) {
       for (int l = 1; l <= k; l++) spec->update(files["proofs/DecryptionFactors" + two(l) + ".bt"]);
     }
   }
-  // ---- shuffles (:1403-1520)
-  const CiphArr* inp = &ciphertexts;
+  // ---- shuffles (:1378-1530)
+  const CiphArr* inp = ciphertexts.get();
   Span inpFile = ctFile;
-  std::vector<CiphArr> outputs;
-  outputs.reserve((size_t)active);
+  std::vector<std::unique_ptr<CiphArr>> outputs;
   int valid = 0;
-  for (int l = 1; l <= active; l++) {
-    std::string name = "proofs/Ciphertexts" + two(l) + ".bt";
-    if (l == active && !has(name)) name = "ShuffledCiphertexts.bt";
-    const Span pc = file("proofs/PermutationCommitment" + two(l) + ".bt");
-    const Span cm = file("proofs/PoSCommitment" + two(l) + ".bt");
-    const Span rp = file("proofs/PoSReply" + two(l) + ".bt");
-    const Span outFile = file(name);
-    outputs.push_back(read_ciph(outFile, name));   // fail-stop if malformed; an invalid PROOF keeps the input
-    const bool ok = verify_shuffle(h, hTree, h0, n, *inp, outputs.back(), inpFile, outFile, pc, cm, rp, y);
-    if (l <= (int)(sizeof rep->shuffles / sizeof rep->shuffles[0])) rep->shuffles[l - 1] = ok ? 1 : 0;   // (all are counted)
-    rep->n_shuffles = l;
-    valid += ok ? 1 : 0;
-    if (ok) { inp = &outputs.back(); inpFile = outFile; }
+  if (posc || ccpos) {
+    size_t maxciph = n;
+    if (precomp) {                                                                                // getMaxciph :541-548
+      long mc = 0;
+      if (!parse_int_strict(text("proofs/maxciph"), &mc)) fail_stop("Can not parse maxciph file!");
+      if (mc < 1) fail_stop("Invalid maxciph!");
+      maxciph = (size_t)mc;
+    } else if (!ciphertexts) {
+      fail_stop("No ciphertexts!");
+    }
+    // independent generators (distr/IndependentGeneratorsRO.java:110-130)
+    Garr h;
+    {
+      // the serialisation of the generators is hashed into the seed of every proof: a maxciph no file of the
+      // directory can answer to is refused before anything of that size is allocated
+      size_t largest = 0;
+      for (const auto& f : files) largest = f.second.n > largest ? f.second.n : largest;
+      if (maxciph > largest) fail_stop("maxciph exceeds what the proof directory can hold!");
+      Sha256 d;
+      uint8_t b4[4];
+      put_be32(b4, 256);
+      d.update(b4, 4);
+      d.update(prefix.data(), prefix.size());
+      const std::string sid = "generators";
+      Bytes leaf = header(LEAF, (uint32_t)sid.size());
+      leaf.insert(leaf.end(), sid.begin(), sid.end());
+      d.update(leaf.data(), leaf.size());
+      const Bytes seed = prg_bytes(d.digest(), 32);
+      size_t pbits = 0;
+      for (size_t i = 0; i < P->nbytes; i++) if (P->p_be[i]) { pbits = 8 * (P->nbytes - i); for (uint8_t v = P->p_be[i]; !(v & 0x80); v <<= 1) pbits--; break; }
+      const size_t bits = pbits + (size_t)P->rbitlen;
+      vmx_garr* a = nullptr;
+      check(api.vmx_garr_prg_sha256(C.c, seed.data(), seed.size(), 0, maxciph, (bits + 7) / 8, (unsigned)bits, &a), "vmx_garr_prg_sha256");
+      h = Garr(a);
+    }
+    const Elem h0 = elem_get(C, h, 0);
+    check(api.vmx_fixed_precompute(C.c, C.g.data(), maxciph), "vmx_fixed_precompute");
+    check(api.vmx_fixed_precompute(C.c, h0.data(), 16), "vmx_fixed_precompute");
+    std::vector<std::unique_ptr<Bytes>> hStore;
+    const Span hTree = garr_tree(C, h, maxciph, hStore);   // the generators are hashed into the seed of every proof
+    Garr shrunkH;                                          // getShrunkGenerators :1059-1068
+    Span shrunkHTree;
+    if (ccpos && precomp) {
+      if (n > maxciph) fail_stop("Too few generators have been derived!");
+      vmx_garr* a = nullptr;
+      check(api.vmx_slice(h.h, 0, n, &a), "vmx_slice");
+      shrunkH = Garr(a);
+      shrunkHTree = garr_tree(C, shrunkH, n, hStore);
+    }
+    for (int l = 1; l <= active; l++) {
+      bool verdict = true;
+      const std::string pcName = "proofs/PermutationCommitment" + two(l) + ".bt";
+      if (!((posc && precomp && !ccpos && has(pcName))                                            // getPoSCActive :958
+            || has("proofs/CCPoSCommitment" + two(l) + ".bt") || has("proofs/PoSCommitment" + two(l) + ".bt")))   // :972-976
+        continue;
+      rep->n_shuffles = l;
+      // readPermutationCommitment :626-641: fail-stop when missing or malformed
+      const Span pcFile = file(pcName);
+      Garr u;
+      try {
+        u = parse_garr(C, pcFile, maxciph);
+      } catch (const Malformed& e) {
+        fail_stop("Unable to read array %s! (%s)", pcName.c_str(), e.what());
+      }
+      std::vector<std::unique_ptr<Bytes>> uStore;
+      Span uTree = pcFile.n == garr_tree_bytes(C, maxciph) ? pcFile : garr_tree(C, u, maxciph, uStore);
+      if (posc && precomp) {                                                                      // verifyPoSC :652-705
+        const bool ok = verify_shuffle(h, hTree, h0, maxciph, u, uTree, nullptr, nullptr, Span(), Span(),
+                                       file("proofs/PoSCCommitment" + two(l) + ".bt"), file("proofs/PoSCReply" + two(l) + ".bt"), y);
+        if ((size_t)l <= kVerdicts) rep->poscs[l - 1] = ok ? 1 : -1;
+        if (!ok) {   // "Setting permutation commitment to list of generators."
+          verdict = false;
+          vmx_garr* cp = nullptr;
+          check(api.vmx_slice(h.h, 0, maxciph, &cp), "vmx_slice");
+          u = Garr(cp);
+          uTree = hTree;
+        }
+      }
+      if (ccpos) {
+        std::string name = "proofs/Ciphertexts" + two(l) + ".bt";
+        if (l == active && !has(name)) name = "ShuffledCiphertexts.bt";
+        const Span outFile = file(name);
+        // fail-stop if malformed; an invalid PROOF keeps the input
+        outputs.push_back(std::make_unique<CiphArr>(read_ciph(outFile, name, n)));
+        bool ok;
+        if (precomp) {
+          // shrinkPermComm :714-745: a keep list that cannot be read or keeps the wrong number is fail-stop
+          Span flags;
+          try {
+            flags = leaf_payload(file("proofs/KeepList" + two(l) + ".bt"), maxciph);
+            for (size_t i = 0; i < maxciph; i++) if (flags.p[i] > 1) throw Malformed("boolean");
+          } catch (const Malformed&) {
+            fail_stop("Unable to open keeplist of Party %d!", l);
+          }
+          size_t total = 0;
+          for (size_t i = 0; i < maxciph; i++) total += flags.p[i];
+          if (total != n) fail_stop("Wrong number of true elements in keep list of Party %d!", l);
+          vmx_garr* a = nullptr;
+          check(api.vmx_extract(u.h, flags.p, &a), "vmx_extract");
+          Garr shrunkU(a);
+          u.reset();
+          std::vector<std::unique_ptr<Bytes>> suStore;
+          const Span suTree = garr_tree(C, shrunkU, n, suStore);
+          ok = verify_ccpos(shrunkH, shrunkHTree, n, shrunkU, suTree, *inp, *outputs.back(), inpFile, outFile,
+                            file("proofs/CCPoSCommitment" + two(l) + ".bt"), file("proofs/CCPoSReply" + two(l) + ".bt"), y);
+          verdict = verdict && ok;
+        } else {
+          verdict = verify_shuffle(h, hTree, h0, n, u, uTree, inp, outputs.back().get(), inpFile, outFile,
+                                   file("proofs/PoSCommitment" + two(l) + ".bt"), file("proofs/PoSReply" + two(l) + ".bt"), y);
+        }
+        if (verdict) { inp = outputs.back().get(); inpFile = outFile; }
+        else outputs.pop_back();
+      }
+      if ((size_t)l <= kVerdicts) rep->shuffles[l - 1] = verdict ? 1 : -1;   // (all are counted; 0: the party took no part)
+      valid += verdict ? 1 : 0;
+    }
+    rep->valid_proofs = valid;
+    rep->enough_valid_proofs = valid >= threshold ? 1 : 0;
+  } else {
+    rep->enough_valid_proofs = 1;
   }
-  rep->valid_proofs = valid;
+  if (!dec) {
+    rep->decryption = -1;
+    rep->plaintexts = -1;
+    rep->accepted = rep->enough_valid_proofs;
+    return;
+  }
+  if (!inp) fail_stop("No ciphertexts to decrypt!");
   const CiphArr& mixed = *inp;
   // ---- decryption (:1535-1665)
   std::vector<bool> correct((size_t)k + 1, false);
@@ -1076,11 +1274,11 @@ void Session::run(vmxv_report* rep) {
     for (int c = 0; c < W; c++) cBp[(size_t)c] = elem_mul(C, cBp[(size_t)c], elem_exp(C, Bp[(size_t)l][(size_t)c], lam[t]));
     ckx = scalar_add(C, ckx, scalar_mul(C, kx[(size_t)l], lam[t]));
   }
-  bool dec = elem_mul(C, elem_exp(C, elem_inv(C, y), v), cyp) == elem_exp(C, C.g, ckx);
+  bool decOk = elem_mul(C, elem_exp(C, elem_inv(C, y), v), cyp) == elem_exp(C, C.g, ckx);
   for (int c = 0; c < W; c++)
-    dec = dec && elem_mul(C, elem_exp(C, AB[(size_t)(W + c)], v), cBp[(size_t)c]) == elem_exp(C, AB[(size_t)c], ckx);
-  rep->decryption = dec ? 1 : 0;
-  if (!dec) fail_stop("Verify combined proof of decryption... failed!");
+    decOk = decOk && elem_mul(C, elem_exp(C, AB[(size_t)(W + c)], v), cBp[(size_t)c]) == elem_exp(C, AB[(size_t)c], ckx);
+  rep->decryption = decOk ? 1 : 0;
+  if (!decOk) fail_stop("Verify combined proof of decryption... failed!");
   // ---- plaintexts (:1267-1275)
   PlainArr plain;
   try {
@@ -1095,7 +1293,7 @@ void Session::run(vmxv_report* rep) {
   }
   rep->plaintexts = match ? 1 : 0;
   if (!match) fail_stop("Plaintexts are incorrect!");
-  rep->accepted = valid >= threshold ? 1 : 0;
+  rep->accepted = rep->enough_valid_proofs;
 }
 
 }  // namespace
@@ -1118,6 +1316,7 @@ int vmxv_bind(const char* libvmx_path) {
 int vmxv_verify(const vmxv_params* P, const vmxv_file* files, size_t nfiles, vmxv_report* rep) {
   if (!P || !rep || (nfiles && !files)) return -1;
   std::memset(rep, 0, sizeof *rep);
+  rep->decryption = rep->plaintexts = -1;
   if (!api.handle) { snprintf(rep->error, sizeof rep->error, "vmxv_bind was not called"); return -1; }
   {  // usage errors: nothing of the directory is looked at
     const char* bad = nullptr;

@@ -794,6 +794,7 @@ class PoSTW:
             u_parsed = False
         # online verification (prehashSeed): the seed hash was started from the published bytes; it stands if
         # they are exactly the byte trees of the parsed arrays (well formed, no trailing bytes)
+        self.u_parsed = u_parsed   # (vmnv reads the commitment itself first and fail-stops when it is malformed)
         pre, prc = getattr(self, "_preSeed", None), getattr(self, "_preChallenge", None)
         self._preSeed = self._preChallenge = None
         pre_ok = pre is not None and u_parsed and pre[1] is permutationCommitment and pre[2] is outputBytes and \

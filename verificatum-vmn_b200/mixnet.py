@@ -224,6 +224,7 @@ class ShufflerSession:
             V.precompute(generators.getPGroup().getg(), generators)
         verdict = V.verify(widePublicKey, ciphertexts, output, proof.permutationCommitment, proof.commitment,
                            proof.reply, outputBytes=outputBytes)
+        self.last_u_parsed = V.u_parsed
         V.free()
         if own_generators:
             generators.free()

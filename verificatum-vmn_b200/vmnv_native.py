@@ -27,7 +27,8 @@ class _Params(C.Structure):
                 ("a_be", C.c_char_p), ("b_be", C.c_char_p), ("gy_be", C.c_char_p), ("nbytes", C.c_size_t),
                 ("device", C.c_int), ("k", C.c_int), ("threshold", C.c_int), ("vbitlenro", C.c_int),
                 ("ebitlenro", C.c_int), ("rbitlen", C.c_int), ("version", C.c_char_p), ("sid", C.c_char_p),
-                ("pgroup_string", C.c_char_p), ("expected_auxsid", C.c_char_p), ("expected_width", C.c_int)]
+                ("pgroup_string", C.c_char_p), ("expected_auxsid", C.c_char_p), ("expected_width", C.c_int),
+                ("expected_type", C.c_char_p), ("nodec", C.c_int), ("noposc", C.c_int), ("noccpos", C.c_int)]
 
 
 class _File(C.Structure):
@@ -35,8 +36,9 @@ class _File(C.Structure):
 
 
 class _Report(C.Structure):
-    _fields_ = [("accepted", C.c_int), ("fail_stop", C.c_int), ("n_shuffles", C.c_int), ("shuffles", C.c_int * 64),
-                ("valid_proofs", C.c_int), ("decryption", C.c_int), ("plaintexts", C.c_int),
+    _fields_ = [("accepted", C.c_int), ("fail_stop", C.c_int), ("type", C.c_int), ("n_shuffles", C.c_int),
+                ("shuffles", C.c_int * 64), ("poscs", C.c_int * 64), ("valid_proofs", C.c_int),
+                ("enough_valid_proofs", C.c_int), ("decryption", C.c_int), ("plaintexts", C.c_int),
                 ("hashed_bytes", C.c_uint64), ("launches", C.c_uint64), ("error", C.c_char * 400)]
 
 
@@ -71,14 +73,16 @@ def _address(data):
 
 
 class MixNetElGamalVerifyFiatShamirSessionNative:
-    """Drop-in for vmnv.MixNetElGamalVerifyFiatShamirSession on ModPGroup proofs."""
+    """Drop-in for vmnv.MixNetElGamalVerifyFiatShamirSession (same options, same report)."""
 
     def __init__(self, pGroup, params: SessionParams, k: int, threshold: int, expectedAuxsid: Optional[str] = None,
-                 expectedWidth: Optional[int] = None):
+                 expectedWidth: Optional[int] = None, expectedType: Optional[str] = None, dec: bool = True,
+                 posc: bool = True, ccpos: bool = True):
         if params.rohash != "SHA-256" or params.prghash != "SHA-256":
             raise NotImplementedError("the native verifier hashes with SHA-256")
         self.pGroup, self.params, self.k, self.threshold = pGroup, params, k, threshold
-        self.expectedAuxsid, self.expectedWidth = expectedAuxsid, expectedWidth
+        self.expectedAuxsid, self.expectedWidth, self.expectedType = expectedAuxsid, expectedWidth, expectedType
+        self.dec, self.posc, self.ccpos = dec, posc, ccpos
         self.report: Dict[str, object] = {}
 
     def verify(self, nizkp) -> Dict[str, object]:
@@ -92,7 +96,8 @@ class MixNetElGamalVerifyFiatShamirSessionNative:
             group = (0, be(G.p), be(G.q), be(G.g), None, None, None)
         P = _Params(*group, nbytes, getattr(G, "device", 0), self.k, self.threshold, p.vbitlenro,
                     p.ebitlenro, p.rbitlen, p.version.encode(), p.sid.encode(), p.pGroupString.encode(),
-                    (self.expectedAuxsid or "").encode(), int(self.expectedWidth or 0))
+                    (self.expectedAuxsid or "").encode(), int(self.expectedWidth or 0),
+                    (self.expectedType or "").encode(), int(not self.dec), int(not self.posc), int(not self.ccpos))
         names = sorted(nizkp)
         files = (_File * len(names))()
         keep = []
@@ -104,17 +109,17 @@ class MixNetElGamalVerifyFiatShamirSessionNative:
         rc = lib.vmxv_verify(C.byref(P), files, len(names), C.byref(R))
         if rc != 0:
             raise nat.VmxError(nat.VMX_ECUDA, "native verifier: %s" % R.error.decode("utf-8", "replace"))
-        rep = {"shuffles": {l + 1: bool(R.shuffles[l]) for l in range(R.n_shuffles)}, "decryption": None,
-               "hashed_bytes": int(R.hashed_bytes), "launches": int(R.launches)}
-        if R.n_shuffles:
-            rep["validProofs"] = int(R.valid_proofs)
-            rep["enoughValidProofs"] = R.valid_proofs >= self.threshold
+        tri = lambda v: None if v < 0 else bool(v)
+        span = min(R.n_shuffles, 64)
+        rep = {"type": ("mixing", "shuffling", "decryption")[R.type],
+               "shuffles": {l + 1: R.shuffles[l] > 0 for l in range(span) if R.shuffles[l]},
+               "poscs": {l + 1: R.poscs[l] > 0 for l in range(span) if R.poscs[l]},
+               "decryption": tri(R.decryption), "hashed_bytes": int(R.hashed_bytes), "launches": int(R.launches),
+               "validProofs": int(R.valid_proofs), "enoughValidProofs": bool(R.enough_valid_proofs)}
         self.report = rep
         if R.fail_stop:
-            if R.decryption or b"decryption" in R.error:
-                rep["decryption"] = bool(R.decryption)
             raise VerificationError(R.error.decode("utf-8", "replace"))
-        rep["decryption"] = bool(R.decryption)
-        rep["plaintexts"] = bool(R.plaintexts)
+        if R.plaintexts >= 0:
+            rep["plaintexts"] = bool(R.plaintexts)
         rep["accepted"] = bool(R.accepted)
         return rep
