@@ -329,6 +329,102 @@ def run_verify_mix(args, env):
     return line
 
 
+def run_committed_shuffle(args, env):
+    """BASELINE.json config 4's protocol: "re-encryption and expProd-heavy CCPoS verify" over multi-block
+    ciphertexts.  After a pre-computation for N ciphertexts (permutation commitment + its proof of a shuffle of
+    commitments; untimed, reported as `precomp_s`), one step = re-encryption factors pk^s for fresh exponents
+    (2 omega fixed-base exponentiations per ciphertext), re-encryption + permutation, the commitment-consistent proof of
+    a shuffle (hvzk/CCPoSW.java:75-150) and its verification (:160-260; mixnet/ShufflerElGamalSession.java:771-960)
+    through the session API: published byte trees out of the prover, imported with membership checks by the
+    verifier, Fiat-Shamir hashing on the host -- so `value` and `e2e` are the same end-to-end measurement.  One GPU."""
+    torch = env.torch
+    if env.world != 1:
+        raise SystemExit("bench: --workload committed-shuffle runs on one GPU")
+    vmx = importlib.import_module("verificatum-vmn_b200")
+    A = vmx.arithm
+    mixnet = importlib.import_module("verificatum-vmn_b200.mixnet")
+    G = make_group(args, env)
+    stream = torch.cuda.ExternalStream(G._lib.vmx_ctx_stream(G.ctx), device=torch.device("cuda", env.local_rank))
+    n, width = args.n, args.width
+    setup_rs = make_prg("setup")
+    x = G.getPRing().randomElement(setup_rs, 100)
+    basic_pk = A.PPGroup(G, 2).product(G.getg(), G.getg().exp(x))
+    exponentsRing = mixnet.getPlainPGroup(G, width).getPRing()
+    widePk = mixnet.getWidePublicKey(basic_pk, width)
+    if width == 1:
+        ciphertexts = mixnet.demoCiphertexts(basic_pk, n, setup_rs)
+    else:
+        r0 = exponentsRing.randomElementArray(n, setup_rs, 100)
+        ciphertexts = widePk.exp(r0)
+        r0.free()
+    params = mixnet.SessionParams(pGroupString=group_label(args))
+    prover = mixnet.ShufflerSession(G, basic_pk, params, make_prg("prover"))
+    verifier = mixnet.ShufflerSession(G, basic_pk, params, None)
+    G.membership_check = True
+    # ---- pre-computation (ShufflerElGamalSession.precomp :534-672) and its verification, untimed
+    t0 = time.time()
+    cs = mixnet.CommittedShuffler(prover, width, n)
+    pub = cs.precomp()
+    gens = verifier.deriveGenerators(n)
+    pcv = mixnet.PermutationCommitment(verifier, gens)
+    if not pcv.verify(*pub):
+        raise SystemExit("bench: the proof of a shuffle of commitments was rejected")
+    keep = cs.shrink(n)
+    pcv.shrink(n, keep)
+    G.sync()
+    precomp_s = time.time() - t0
+
+    def step(i: int):
+        rs = make_prg("step%d" % i)
+        prover.randomSource = rs
+        for a in (cs.reencExponents, cs.reencFactors):
+            a.free()
+        cs.reencExponents = exponentsRing.randomElementArray(n, rs, params.rbitlen)
+        cs.reencFactors = widePk.exp(cs.reencExponents)
+        proof, _ = cs.shuffle(ciphertexts)
+        ok, out = mixnet.verifyCommittedShuffle(verifier, width, gens, pcv.commitment, ciphertexts, proof)
+        out.free()
+        if not ok:
+            raise SystemExit("bench: the verifier rejected an honest commitment-consistent proof of a shuffle")
+        return len(proof.output) + len(proof.commitment) + len(proof.reply)
+
+    for i in range(max(1, args.warmup)):
+        nbytes = step(i)
+    sampler = ClockSampler(env.local_rank)
+    sampler.start()
+    launches0, modmuls0 = G.launch_count(), G.modmul_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    t0 = time.time()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record(stream)
+    e1.synchronize()
+    wall = time.time() - t0
+    sampler.stop_flag.set()
+    sampler.join()
+    ms_per_step = e0.elapsed_time(e1) / args.steps
+    macs = 136 if is_curve(args) else macs_per_modmul(args.bits)
+    modmuls = G.modmul_count() - modmuls0
+    return {"metric": "ciphertexts/s: re-encrypt + CCPoS prove+verify after pre-computation, %s, width %d"
+                      % (group_label(args), width),
+            "value": n / (ms_per_step * 1e-3), "unit": "ciphertexts/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32 limbs (exact integer)", "data": "synthetic",
+            "config": {"workload": "%s, width %d, N=%d ciphertexts: re-encryption + commitment-consistent proof of a "
+                                   "shuffle, prove + verify, after a pre-computation for N (BASELINE.json config 4's protocol)"
+                                   % (group_label(args), width, n), "n_total": n, "width": width},
+            "clocks": sampler.summary(), "gpu_launches": int(G.launch_count() - launches0),
+            "e2e": {"value": n / (wall / args.steps), "unit": "ciphertexts/s", "h2d_bytes_per_step": nbytes,
+                    "d2h_bytes_per_step": nbytes, "ms_per_step": wall / args.steps * 1e3,
+                    "includes": "byte-tree encode/decode, D2H/H2D, membership checks, Fiat-Shamir SHA-256 on the host"},
+            "modmul": {"executed_per_ciphertext": modmuls / (args.steps * n),
+                       "executed_frac_of_imad_peak": modmuls * macs / (ms_per_step * args.steps * 1e-3) / IMAD_PEAK_MAC_PER_S},
+            "precomp_s": precomp_s}
+
+
 class _Null:
     def __enter__(self):
         return self
@@ -670,6 +766,27 @@ OTHER_CONFIGS = [
 ]
 
 
+def run_isolated(extra, timeout_s: float):
+    """A side run in its own process (own CUDA context): whatever happens to it cannot cost the headline line."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--no-other", "--no-cpu", "--steps", "2", "--warmup", "2"] + extra
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    t0 = time.time()
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+    except subprocess.TimeoutExpired:
+        return {"error": "no result within %d s" % timeout_s}
+    for ln in reversed(p.stdout.splitlines()):
+        if ln.startswith("{"):
+            try:
+                line = json.loads(ln)
+                line["wall_s"] = time.time() - t0
+                return line
+            except ValueError:
+                break
+    return {"error": "rc=%d: %s" % (p.returncode, (p.stderr or p.stdout)[-300:])}
+
+
 def run_other_configs(args, env):
     import copy
     import gc
@@ -702,6 +819,14 @@ def run_other_configs(args, env):
                 sub["roofline"] = {k: line["roofline"][k] for k in ("kernel", "achieved", "peak", "unit", "frac")}
             sub["wall_s"] = time.time() - t0
             out[name] = sub
+    if env.world == 1:
+        # config 4's own protocol (pre-computation, then re-encryption + commitment-consistent proof of a shuffle),
+        # in a process of its own
+        gc.collect()
+        line = run_isolated(["--workload", "committed-shuffle", "--bits", "2048", "--width", "3", "--n", "100000"], 240)
+        keep = ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "gpu_launches", "e2e", "modmul", "precomp_s",
+                "wall_s", "error")
+        out["config4_ccpos_2048_width3"] = {k: line[k] for k in keep if k in line}
     return out
 
 
@@ -727,7 +852,7 @@ def main():
     ap.add_argument("--phases", action="store_true", help="print per-phase device times to stderr")
     ap.add_argument("--trace", default="", help="write the host timeline (ABI calls, hashing) of one extra untimed "
                                                 "end-to-end step to this JSON file")
-    ap.add_argument("--workload", default="shuffle", choices=["shuffle", "verify-mix"],
+    ap.add_argument("--workload", default="shuffle", choices=["shuffle", "verify-mix", "committed-shuffle"],
                     help="shuffle: re-encrypt + PoS prove + verify (BASELINE.json's metric, the default); "
                          "verify-mix: vmnv-style verification of a 3-party mix, threshold 2 (config 3)")
     args = ap.parse_args()
@@ -751,7 +876,10 @@ def main():
     env = Env(torch, dist, world, rank, local_rank)
 
     headline = (args.workload == "shuffle" and args.group == "modp" and args.bits == 3072 and args.width == 1)
-    line = run_verify_mix(args, env) if args.workload == "verify-mix" else run_shuffle(args, env)
+    if args.workload == "committed-shuffle":
+        line = run_committed_shuffle(args, env)
+    else:
+        line = run_verify_mix(args, env) if args.workload == "verify-mix" else run_shuffle(args, env)
     if headline and not args.no_other:
         other = run_other_configs(args, env)
         if rank == 0:

@@ -653,14 +653,29 @@ def ec_group_ops(vmx, curve, n):
     assert vals(R.randomElementArray(n, prg, 100)) == oar.ring_random_array(OG, n, ors, 100)
 
 
-def mix_parity(vmx, spec, n, k=3, threshold=2, tmpdir=None, width=1, mode="mixing", maxciph=None, light=False):
+def mix_parity(vmx, spec, n, k=3, threshold=2, tmpdir=None, width=1, mode="mixing", maxciph=None, light=False,
+               gmp=False):
+    """`gmp`: the oracle's array operations on its GMP back end (oracle/accel.py, pinned to Python integers in
+    tests/test_oracle_accel.py) -- what lets the 2048-bit cases of the GPU suite run in seconds."""
+    OG = oracle_group(spec)
+    if not gmp:
+        return _mix_parity(vmx, spec, OG, n, k, threshold, tmpdir, width, mode, maxciph, light)
+    from oracle import accel
+    undo = accel.install(OG, accel.cores())
+    try:
+        return _mix_parity(vmx, spec, OG, n, k, threshold, tmpdir, width, mode, maxciph, light)
+    finally:
+        undo()
+
+
+def _mix_parity(vmx, spec, OG, n, k=3, threshold=2, tmpdir=None, width=1, mode="mixing", maxciph=None, light=False):
     """A whole mix (keys, `threshold` shuffles, threshold decryption with proofs) on the engine and on the
     oracle from the same seeds: every file of the proof directory is byte-identical; the engine's vmnv
     (vmnv.MixNetElGamalVerifyFiatShamirSession) and the oracle's accept it, also after a round trip through a
     directory on disk; corrupted files are rejected by both (BASELINE.json config 3 at test size)."""
     vm = importlib.import_module("verificatum-vmn_b200.vmnv")
     mix = importlib.import_module("verificatum-vmn_b200.mixnet")
-    G, OG = engine_group(vmx, spec), oracle_group(spec)
+    G = engine_group(vmx, spec)
     params = mix.SessionParams(pGroupString="mix-%s" % spec)
     oparams = opr.Params(pgroup_string="mix-%s" % spec)
     rs = vmx.crypto.PRGHeuristic()
@@ -758,11 +773,14 @@ def _mix_variants(vmx, vm, V, G, OG, params, oparams, k, threshold, honest, mode
         assert a == b, (kw, a, b)
     assert outcome_engine(honest, expectedType="mixing" if mode != "mixing" else "shuffling") == ("failstop",)
     seen = set()
+    few = ("Reply01.bt", "KeepList01.bt", "Plaintexts.bt", "ShuffledCiphertexts.bt", "DecryptionFactors01.bt")
     for name in sorted(honest):
         kind = "".join(ch for ch in name if not ch.isdigit())
         if kind in seen:       # one file of every kind (party 1's)
             continue
         seen.add(kind)
+        if light == "min" and not name.endswith(few):   # (the GPU tests: the variants are host logic, tested on the CPU)
+            continue
         raw = bytes(honest[name])
         variants = [raw[:len(raw) // 2]] if light else [raw[:len(raw) // 2], raw + b"\x00"]
         if len(raw) > 8:
@@ -1152,7 +1170,8 @@ def concurrent_threads(vmx, bits, n, rounds=6):
     assert computed[0::2] == [want_exp] * rounds and computed[1::2] == [prod] * rounds
 
 
-def native_vmnv_parity(vmx, spec, n, k=3, threshold=2, width=1, thorough=True, mode="mixing", maxciph=None):
+def native_vmnv_parity(vmx, spec, n, k=3, threshold=2, width=1, thorough=True, mode="mixing", maxciph=None,
+                       minimal=False):
     """The native universal verifier (csrc/vmnv_native.cpp, include/vmnv.h) against the Python mirror of
     mixnet/MixNetElGamalVerifyFiatShamirSession on the same proof directories: an honest mix, and the same mix with
     one file at a time corrupted / truncated / emptied / missing -- identical verdicts per shuffle, identical
@@ -1187,18 +1206,21 @@ def native_vmnv_parity(vmx, spec, n, k=3, threshold=2, width=1, thorough=True, m
     assert honest == outcome(VP, M.nizkp) and honest[:3] == ("verdict", mode, True), honest
     assert VN.report["hashed_bytes"] > 0 and VN.report["launches"] > 0
     # what is verified (-nodec, -noposc, -noccpos) and the expected type (-mix, -shuffle, -decrypt)
-    for kw in (dict(dec=False), dict(posc=False), dict(ccpos=False), dict(posc=False, ccpos=False),
-               dict(expectedType=mode), dict(expectedType="shuffling" if mode == "mixing" else "mixing")):
+    options = (dict(dec=False), dict(posc=False), dict(ccpos=False), dict(posc=False, ccpos=False),
+               dict(expectedType=mode), dict(expectedType="shuffling" if mode == "mixing" else "mixing"))
+    for kw in (options[1:2] if minimal else options):
         a = outcome(vn.MixNetElGamalVerifyFiatShamirSessionNative(G, params, k, threshold, **kw), M.nizkp)
         b = outcome(vm.MixNetElGamalVerifyFiatShamirSession(G, params, k, threshold, **kw), M.nizkp)
         assert a == b, (kw, a, b)
     # the -auxsid / -width options
     for kw, ok in ((dict(expectedAuxsid="run 7"), True), (dict(expectedAuxsid="other"), False),
-                   (dict(expectedWidth=width), True), (dict(expectedWidth=width + 1), False)):
+                   (dict(expectedWidth=width), True), (dict(expectedWidth=width + 1), False))[:1 if minimal else 4]:
         got = outcome(vn.MixNetElGamalVerifyFiatShamirSessionNative(G, params, k, threshold, **kw), M.nizkp)
         assert (got[0] == "verdict" and got[2]) == ok, (kw, got)
     names = sorted(M.nizkp)
-    if thorough:    # every kind of file once (party 1's of each), every header file
+    if minimal:     # (the GPU tests of the pre-computed sessions: the variants are host logic, tested on the CPU)
+        names = [nm for nm in names if nm.endswith(("CCPoSReply01.bt", "KeepList02.bt", "PoSCCommitment02.bt", "PoSReply01.bt"))]
+    elif thorough:    # every kind of file once (party 1's of each), every header file
         names = [nm for nm in names if not nm.endswith(("02.bt", "03.bt"))]
     else:
         names = [nm for nm in names if nm.endswith(("PoSReply01.bt", "DecrFactCommitment02.bt", "Plaintexts.bt",
