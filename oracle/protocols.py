@@ -1028,7 +1028,8 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
         # getMaxciph :541-548, deriveGenerators :556-576, getShrunkGenerators :1059-1068
         if precomp_:
             maxciph = _parse_int(need("proofs/maxciph"))
-            if maxciph < 1 or maxciph > max(len(v) for v in d.values()):   # (no file could hold such a commitment)
+            # (no file of the directory could hold a commitment of that many elements)
+            if maxciph < 1 or maxciph > max(len(v) for v in d.values()) // (5 + (G.p.bit_length() + 7) // 8):
                 raise MixVerificationError("maxciph")
         else:
             if w is None:

@@ -225,18 +225,24 @@ def main():
     assert c1 == c2, "sharded committed shuffle differs from the single-process one on rank %d" % rank
 
     # ---- a whole 3-party mix and its vmnv-style verification on shards
-    def whole_mix(Gx):
+    def whole_mix(Gx, mode="mixing", maxciph=None):
         vm = importlib.import_module("verificatum-vmn_b200.vmnv")
         mix = importlib.import_module("verificatum-vmn_b200.mixnet")
         params = mix.SessionParams(pGroupString="par-mix")
         M = vm.MixNetElGamal(Gx, params, 3, 2, rs("mix/dealer"))
         w = mix.demoCiphertexts(M.fullPublicKey, n, rs("mix/input"))
-        M.run(w)
+        M.run(w, mode=mode, maxciph=maxciph)
         rep = vm.MixNetElGamalVerifyFiatShamirSession(Gx, params, 3, 2).verify(M.nizkp)
         return dict(M.nizkp), rep
 
     m1, m2 = whole_mix(G1), whole_mix(GS)
     assert m1[1]["accepted"] and m1 == m2, "sharded mix differs from the single-process one on rank %d" % rank
+    # ... and a pre-computed session (PoSC over maxciph generators, keep lists, CCPoS over the shrunk commitments:
+    # extract / copyOfRange move elements between shards), mixnet/MixNetElGamalVerifyFiatShamirSession.java:1378-1530
+    if n >= 2 and not (isinstance(bits, str) and world > 2):
+        m1, m2 = whole_mix(G1, maxciph=n + 3), whole_mix(GS, maxciph=n + 3)
+        assert m1[1]["accepted"] and m1[1]["poscs"] == {1: True, 2: True} and m1 == m2, \
+            "sharded pre-computed mix differs from the single-process one on rank %d" % rank
 
     stats = (GS.comm.collectives, GS.comm.bytes_exchanged)
     dist.barrier()

@@ -1048,9 +1048,10 @@ void Session::run(vmxv_report* rep) {
     {
       // the serialisation of the generators is hashed into the seed of every proof: a maxciph no file of the
       // directory can answer to is refused before anything of that size is allocated
-      size_t largest = 0;
+      size_t largest = 0, pbits0 = 0;
       for (const auto& f : files) largest = f.second.n > largest ? f.second.n : largest;
-      if (maxciph > largest) fail_stop("maxciph exceeds what the proof directory can hold!");
+      for (size_t i = 0; i < P->nbytes; i++) if (P->p_be[i]) { pbits0 = 8 * (P->nbytes - i); for (uint8_t v = P->p_be[i]; !(v & 0x80); v <<= 1) pbits0--; break; }
+      if (maxciph > largest / (5 + (pbits0 + 7) / 8)) fail_stop("maxciph exceeds what the proof directory can hold!");
       Sha256 d;
       uint8_t b4[4];
       put_be32(b4, 256);

@@ -461,9 +461,9 @@ class MixNetElGamalVerifyFiatShamirSession:
                 if maxciph < 1:
                     raise VerificationError("Invalid maxciph!")
                 # every party that counts published a permutation commitment of maxciph elements (else
-                # readPermutationCommitment :626-641 stops): a maxciph no file of the directory can answer to is
-                # refused before that many generators are derived
-                if maxciph > max(len(v) for v in nizkp.values()):
+                # readPermutationCommitment :626-641 stops), maxciph leaves of at least a coordinate's length each:
+                # a maxciph no file of the directory can answer to is refused before that many generators are derived
+                if maxciph > max(len(v) for v in nizkp.values()) // (5 + (G.p.bit_length() + 7) // 8):
                     raise VerificationError("maxciph exceeds what the proof directory can hold!")
             else:
                 if ciphertexts is None:
