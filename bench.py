@@ -381,8 +381,13 @@ def run_committed_shuffle(args, env):
             a.free()
         cs.reencExponents = exponentsRing.randomElementArray(n, rs, params.rbitlen)
         cs.reencFactors = widePk.exp(cs.reencExponents)
-        proof, _ = cs.shuffle(ciphertexts)
-        ok, out = mixnet.verifyCommittedShuffle(verifier, width, gens, pcv.commitment, ciphertexts, proof)
+        if args.offline_verify:
+            proof, _ = cs.shuffle(ciphertexts)
+            ok, out = mixnet.verifyCommittedShuffle(verifier, width, gens, pcv.commitment, ciphertexts, proof)
+        else:   # the verifier reads the output from the board when it is published and hashes beside the prover
+            ov = mixnet.OnlineCommittedVerification(verifier, width, gens, pcv.commitment, ciphertexts)
+            proof, _ = cs.shuffle(ciphertexts, publish=ov.publish)
+            ok, out = ov.finish(proof)
         out.free()
         if not ok:
             raise SystemExit("bench: the verifier rejected an honest commitment-consistent proof of a shuffle")
@@ -419,7 +424,9 @@ def run_committed_shuffle(args, env):
             "clocks": sampler.summary(), "gpu_launches": int(G.launch_count() - launches0),
             "e2e": {"value": n / (wall / args.steps), "unit": "ciphertexts/s", "h2d_bytes_per_step": nbytes,
                     "d2h_bytes_per_step": nbytes, "ms_per_step": wall / args.steps * 1e3,
-                    "includes": "byte-tree encode/decode, D2H/H2D, membership checks, Fiat-Shamir SHA-256 on the host"},
+                    "includes": "byte-tree encode/decode, D2H/H2D, membership checks, Fiat-Shamir SHA-256 on the host",
+                    "verifier": "offline" if args.offline_verify else
+                                "online: the verifier hashes the output as the prover publishes it"},
             "modmul": {"executed_per_ciphertext": modmuls / (args.steps * n),
                        "executed_frac_of_imad_peak": modmuls * macs / (ms_per_step * args.steps * 1e-3) / IMAD_PEAK_MAC_PER_S},
             "precomp_s": precomp_s}

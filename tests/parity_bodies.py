@@ -544,6 +544,25 @@ def committed_shuffle_parity(vmx, bits, maxciph, n):
     sgens = gens.copyOfRange(0, n)
     ok, out2 = mix.verifyCommittedShuffle(verifier, 1, sgens, pcv.commitment, ec.w, proof)
     assert ok is True and col_values(out2) == owp
+    # online verification (the verifier's seed hash starts when the output is published, beside the prover's): same
+    # verdict and output; a board message other than the output finally presented is hashed again, not trusted
+    prover.randomSource.setSeed(seed("committed/prove2"))
+    ov = mix.OnlineCommittedVerification(verifier, 1, sgens, pcv.commitment, ec.w)
+    proof_on, _ = cs.shuffle(ec.w, publish=ov.publish)
+    assert dataclasses.asdict(proof_on) == oproof
+    ok_on, out_on = ov.finish(proof_on)
+    assert ok_on is True and col_values(out_on) == owp
+    ov = mix.OnlineCommittedVerification(verifier, 1, sgens, pcv.commitment, ec.w)
+    other = bytearray(proof.output)
+    other[len(other) // 2] ^= 1
+    ov.publish("output", bytes(other))
+    ok_on, out_on = ov.finish(proof)
+    assert ok_on is True and col_values(out_on) == owp
+    ov = mix.OnlineCommittedVerification(verifier, 1, sgens, pcv.commitment, ec.w)
+    ov.publish("output", proof.output)
+    ok_on, out_on = ov.finish(dataclasses.replace(proof, output=bytes(other)))
+    want = mix.verifyCommittedShuffle(verifier, 1, sgens, pcv.commitment, ec.w, dataclasses.replace(proof, output=bytes(other)))
+    assert ok_on is want[0] is False and col_values(out_on) == col_values(want[1]) == oc.w
     # oracle verifier on the engine's bytes
     ou = oar.parse_array(OG, obt.from_bytes(pub[0]), maxciph)
     assert opr.posc_verify(OG, oc.params, OG.g, oh, ou, pub[1], pub[2]) is True

@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--threshold", type=int, default=2)
     ap.add_argument("--width", type=int, default=1)
     ap.add_argument("--seed", default="fuzz")
+    ap.add_argument("--mode", default="mixing", choices=["mixing", "shuffling", "decryption"])
+    ap.add_argument("--maxciph", type=int, default=0, help="pre-compute for this many ciphertexts first (0: no pre-computation)")
     ap.add_argument("--asan", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
@@ -58,9 +60,12 @@ def main():
     spec = int(args.spec) if args.spec.isdigit() else args.spec
     t0 = time.time()
     tally = pb.native_vmnv_fuzz(vmx, spec, args.n, args.rounds, seed_label=args.seed, k=args.k, threshold=args.threshold,
-                                width=args.width, log=print if args.verbose else None)
-    print("spec=%s n=%d k=%d threshold=%d width=%d seed=%r rounds=%d: native == mirror on every round; outcomes %s; %.0f s%s"
-          % (args.spec, args.n, args.k, args.threshold, args.width, args.seed, args.rounds, dict(sorted(tally.items())),
+                                width=args.width, log=(lambda m: print(m, flush=True)) if args.verbose else None,
+                                mode=args.mode, maxciph=args.maxciph or None)
+    print("spec=%s n=%d k=%d threshold=%d width=%d mode=%s maxciph=%s seed=%r rounds=%d: native == mirror on every round; "
+          "outcomes %s; %.0f s%s"
+          % (args.spec, args.n, args.k, args.threshold, args.width, args.mode, args.maxciph or None, args.seed, args.rounds,
+             dict(sorted(tally.items())),
              time.time() - t0, " (ASan + UBSan builds)" if os.environ.get("VMNV_FUZZ_CHILD") else ""))
 
 

@@ -555,19 +555,27 @@ class CCPoSBasicW:
         self.e = self.pField.unsafeToElementArray(lia)
 
     # -- :344-396
-    def commit(self, prgSeed: bytes, randomSource) -> ByteTreeBasic:
-        self.setBatchVector(prgSeed)
-        piinv = self.pi.inv()
-        self.ipe = self.e.permute(piinv)
+    def commitIndependent(self, randomSource) -> None:
+        """A' and B' (:365-393): functions of the prover's randomness alone (alpha, epsilon, beta, drawn in the
+        reference's order) -- the two multi-exponentiations that are nearly all of a CCPoS proof.  CCPoSW.prove
+        queues them while the seed of the batching vector is being hashed."""
         self.alpha = self.pRing.randomElement(randomSource, self.rbitlen)
         epsilonBitLength = self.ebitlen + self.vbitlen + self.rbitlen
         epsilonIntegers = LargeIntegerArray.random(self.size, epsilonBitLength, randomSource, self.pField)
         self.epsilon = self.pField.toElementArray(epsilonIntegers)
         epsilonIntegers.free()
-        self.Ap = self.g.exp(self.alpha).mul(self.h.expProd(self.epsilon))
+        h_eps, wp_eps = expProdTogether([self.h, self.wp], self.epsilon)
+        self.Ap = self.g.exp(self.alpha).mul(h_eps)
         ciphPRing = self.pkey.project(0).getPGroup().getPRing()
         self.beta = ciphPRing.randomElement(randomSource, self.rbitlen)
-        self.Bp = self.pkey.exp(self.beta.neg()).mul(self.wp.expProd(self.epsilon))
+        self.Bp = self.pkey.exp(self.beta.neg()).mul(wp_eps)
+
+    def commit(self, prgSeed: bytes, randomSource) -> ByteTreeBasic:
+        self.setBatchVector(prgSeed)
+        piinv = self.pi.inv()
+        self.ipe = self.e.permute(piinv)
+        if self.epsilon is None:
+            self.commitIndependent(randomSource)
         return ByteTreeContainer(self.Ap.toByteTree(), self.Bp.toByteTree())
 
     # -- :406-428
@@ -917,7 +925,13 @@ class CCPoSW:
     def prove(self, g, h, u, pkey, w, wp, r, pi, s):
         P = CCPoSBasicW(self.vbitlen, self.ebitlen, self.rbitlen, self.prg)
         P.setInstance(g, h, u, pkey, w, wp, r, pi, s)
-        prgSeed = self._seed(g, h, u, pkey, w, wp)
+        # the seed RO(g, h, u, pk, w, w') is hashed on the worker thread (370 MB per 10^5 ciphertexts of width 3)
+        # while the device computes the commitment, which does not depend on it
+        d = self.challenger.begin(8 * self.prg.minNoSeedBytes())
+        ByteTreeContainer(g.toByteTree(), h.toByteTree(), u.toByteTree(), pkey.toByteTree(), w.toByteTree(),
+                          wp.toByteTree()).update(d)                                                # :92-98
+        P.commitIndependent(self.randomSource)
+        prgSeed = self.challenger.finish(d)
         commitment = P.commit(prgSeed, self.randomSource)
         challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitment)
         challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
@@ -926,15 +940,41 @@ class CCPoSW:
         P.free()
         return out
 
+    # -- verifier, online (cf. PoSTW.prehashSeed): the other mix-servers read a party's output from the bulletin board
+    # as soon as it is published (mixnet/ShufflerElGamalSession.java:875-890) -- the seed hash starts then, on the
+    # premise that the message is well formed (its bytes ARE the byte tree of the parsed array); `verify` checks the
+    # premise and hashes again if it does not hold, so verdicts are those of the offline order.
+    def prehashSeed(self, g, h, u, pkey, w, output) -> None:
+        d = self.challenger.begin(8 * self.prg.minNoSeedBytes())
+        d.update(node_header(6))
+        for t in (g, h, u, pkey, w):
+            t.toByteTree().update(d)
+        d.update(output)
+        self._preSeed = (d, output)
+
+    def _abandon_prehash(self) -> None:
+        pre, self._preSeed = getattr(self, "_preSeed", None), None
+        if pre is not None:
+            pre[0].abandon()
+
     # -- :160-260
-    def verify(self, g, h, u, pkey, w, wp, commitment: bytes, reply: bytes) -> bool:
+    def verify(self, g, h, u, pkey, w, wp, commitment: bytes, reply: bytes, outputBytes=None) -> bool:
+        """`outputBytes`: the published message `wp` was parsed from (validates a streamed seed hash: it stands only
+        if it covered these very bytes and they are the canonical serialisation of `wp`)."""
         V = CCPoSBasicW(self.vbitlen, self.ebitlen, self.rbitlen, self.prg)
         V.setInstance(g, h, u, pkey, w, wp)
-        # as in PoSTW.verify: the seed RO(g, h, u, pk, w, w') is hashed on the worker thread while the device
-        # computes what depends on the proof alone (the two multi-exponentiations with k_E)
-        d = self.challenger.begin(8 * self.prg.minNoSeedBytes())
-        ByteTreeContainer(g.toByteTree(), h.toByteTree(), u.toByteTree(), pkey.toByteTree(), w.toByteTree(),
-                          wp.toByteTree()).update(d)                                                # :92-98
+        pre, self._preSeed = getattr(self, "_preSeed", None), None
+        if pre is not None and not (pre[1] is outputBytes and len(outputBytes) == wp.toByteTree().total_bytes()):
+            pre[0].abandon()
+            pre = None
+        if pre is not None:
+            d = pre[0]
+        else:
+            # as in PoSTW.verify: the seed RO(g, h, u, pk, w, w') is hashed on the worker thread while the device
+            # computes what depends on the proof alone (the two multi-exponentiations with k_E)
+            d = self.challenger.begin(8 * self.prg.minNoSeedBytes())
+            ByteTreeContainer(g.toByteTree(), h.toByteTree(), u.toByteTree(), pkey.toByteTree(), w.toByteTree(),
+                              wp.toByteTree()).update(d)                                            # :92-98
         try:
             commitmentTree = V.setCommitment(ByteTreeReader(commitment))
         except EIOException:

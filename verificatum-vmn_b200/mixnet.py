@@ -416,13 +416,17 @@ class CommittedShuffler:
         return self.permutationCommitment.shrink(noCiphertexts)
 
     # -- :771-822
-    def shuffle(self, ciphertexts, keep_output: bool = False):
+    def shuffle(self, ciphertexts, keep_output: bool = False, publish=None):
+        """`publish(name, message)` is called as the output goes to the bulletin board (:795), before it is proved
+        (an OnlineCommittedVerification's `publish`)."""
         pc = self.permutationCommitment
         reenc = ciphertexts.mul(self.reencFactors)                                                   # :789
         inverse = pc.permutation.inv()
         output = reenc.permute(inverse)                                                              # :792
         reenc.free()
         output_bytes = output.toByteTree().to_buffer()
+        if publish is not None:
+            publish("output", output_bytes)
         c, r = self._ccpos().prove(self.generators.getPGroup().getg(), self.generators, pc.commitment,
                                    self.widePublicKey, ciphertexts, output, pc.exponents, pc.permutation,
                                    self.reencExponents)                                              # :808-819
@@ -440,22 +444,49 @@ def _copy_of_range(arr, a: int, b: int):
     return arr.copyOfRange(a, b)
 
 
+class OnlineCommittedVerification:
+    """One commitment-consistent shuffle being verified as its messages are published: the verifier's seed hash
+    (h, u, pk, w, w' -- 370 MB per 10^5 ciphertexts of width 3) starts when the output appears on the board and
+    runs beside the prover's (mixnet/ShufflerElGamalSession.java:875-960: the other parties read the output as soon
+    as it is published).  `publish` goes to `CommittedShuffler.shuffle(..., publish=...)`; `finish(proof)` gives
+    (verdict, output array) exactly as `verifyCommittedShuffle` would."""
+
+    def __init__(self, session: "ShufflerSession", width: int, generators, commitment, ciphertexts):
+        self.session, self.width, self.generators = session, width, generators
+        self.commitment, self.ciphertexts = commitment, ciphertexts
+        p = session.params
+        self.V = CCPoSW(p.vbitlenro, p.ebitlenro, p.rbitlen, session.prg, session.randomSource, session.challenger)
+
+    def publish(self, name: str, message) -> None:
+        if name == "output":
+            self.V.prehashSeed(self.generators.getPGroup().getg(), self.generators, self.commitment,
+                               getWidePublicKey(self.session.publicKey, self.width), self.ciphertexts, message)
+
+    def finish(self, proof: CommittedShuffleProof):
+        return verifyCommittedShuffle(self.session, self.width, self.generators, self.commitment, self.ciphertexts,
+                                      proof, _ccpos=self.V)
+
+
 def verifyCommittedShuffle(session: "ShufflerSession", width: int, generators, commitment, ciphertexts,
-                           proof: CommittedShuffleProof):
+                           proof: CommittedShuffleProof, _ccpos=None):
     """ShufflerElGamalSession.committedShuffleVerify (:875-960) without the raised-commitment
     optimisation: read the output, verify the CCPoS against the (shrunk) permutation commitment; on
     failure the output is replaced by the input.  Returns (verdict, output)."""
     ciphPPGroup = ciphertexts.getPGroup()
     size = ciphertexts.size()
     widePublicKey = getWidePublicKey(session.publicKey, width)
+    V = _ccpos
     try:
         output = ciphPPGroup.toElementArray(size, ByteTreeReader(proof.output))
     except Exception:
+        if V is not None:
+            V._abandon_prehash()
         return False, ciphertexts.copyOfRange(0, size)
     p = session.params
-    V = CCPoSW(p.vbitlenro, p.ebitlenro, p.rbitlen, session.prg, session.randomSource, session.challenger)
+    if V is None:
+        V = CCPoSW(p.vbitlenro, p.ebitlenro, p.rbitlen, session.prg, session.randomSource, session.challenger)
     verdict = V.verify(generators.getPGroup().getg(), generators, commitment, widePublicKey, ciphertexts, output,
-                       proof.commitment, proof.reply)
+                       proof.commitment, proof.reply, outputBytes=proof.output)
     if not verdict:
         output.free()
         output = ciphertexts.copyOfRange(0, size)
