@@ -107,6 +107,24 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "committed-shuffle":
+        res = cpu_baseline.run_committed_shuffle(bits=args.bits, n_total=args.n, sample=cpu_sample_size(args),
+                                                 steps=args.steps, warmup=min(args.warmup, 1), group=args.group,
+                                                 width=args.width)
+        line = {"metric": "ciphertexts/s: re-encrypt + CCPoS prove+verify after pre-computation, %s, width %d"
+                          % (group_label(args), args.width), "impl": "reference",
+                "value": res["value"], "unit": "ciphertexts/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u32 limbs (exact integer)", "data": "synthetic",
+                "config": {"workload": "%s, width %d, N=%d ciphertexts: re-encryption + commitment-consistent proof of "
+                                       "a shuffle, prove + verify, after a pre-computation for N (BASELINE.json config 4's "
+                                       "protocol)" % (group_label(args), args.width, args.n), "n_total": args.n,
+                           "width": args.width, "cpu_sample": res["sample_n"]},
+                "cpu_baseline": {"value": res["value"], "unit": "ciphertexts/s", "cores": res["cores"], "kind": "port",
+                                 "sample": res["sample"]},
+                "e2e": {"value": res["value"], "unit": "ciphertexts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
     if args.workload == "verify-mix":
         res = cpu_baseline.run_verify_mix(bits=args.bits, n_total=args.n, sample=cpu_sample_size(args), steps=args.steps,
                                           warmup=min(args.warmup, 1), group=args.group)
@@ -138,7 +156,9 @@ def cpu_sample_size(args) -> int:
     except AttributeError:
         cores = os.cpu_count() or 1
     mix = args.workload == "verify-mix"
-    if is_curve(args):
+    if args.workload == "committed-shuffle":
+        per_ct = 0.02 * args.width * (args.bits / 3072.0) ** 2
+    elif is_curve(args):
         per_ct = 0.016 if mix else 0.0125
     else:
         per_ct = (0.055 if mix else 0.046) * (args.bits / 3072.0) ** 2
@@ -420,7 +440,8 @@ def run_committed_shuffle(args, env):
             "vs_baseline": None, "dtype": "u32 limbs (exact integer)", "data": "synthetic",
             "config": {"workload": "%s, width %d, N=%d ciphertexts: re-encryption + commitment-consistent proof of a "
                                    "shuffle, prove + verify, after a pre-computation for N (BASELINE.json config 4's protocol)"
-                                   % (group_label(args), width, n), "n_total": n, "width": width},
+                                   % (group_label(args), width, n), "n_total": n, "width": width,
+                       "cpu_sample": cpu_sample_size(args)},
             "clocks": sampler.summary(), "gpu_launches": int(G.launch_count() - launches0),
             "e2e": {"value": n / (wall / args.steps), "unit": "ciphertexts/s", "h2d_bytes_per_step": nbytes,
                     "d2h_bytes_per_step": nbytes, "ms_per_step": wall / args.steps * 1e3,
@@ -429,7 +450,20 @@ def run_committed_shuffle(args, env):
                                 "online: the verifier hashes the output as the prover publishes it"},
             "modmul": {"executed_per_ciphertext": modmuls / (args.steps * n),
                        "executed_frac_of_imad_peak": modmuls * macs / (ms_per_step * args.steps * 1e-3) / IMAD_PEAK_MAC_PER_S},
-            "precomp_s": precomp_s}
+            "precomp_s": precomp_s, "cpu_baseline": _cpu_committed(args)}
+
+
+def _cpu_committed(args):
+    if args.no_cpu or is_curve(args):
+        return None
+    try:
+        from oracle import cpu_baseline
+        res = cpu_baseline.run_committed_shuffle(bits=args.bits, n_total=args.n, sample=cpu_sample_size(args),
+                                                 group=args.group, width=args.width)
+        return {"value": res["value"], "unit": "ciphertexts/s", "cores": res["cores"], "kind": "port",
+                "sample": res["sample"]}
+    except Exception as ex:  # a reported number, never a reason to lose the GPU line
+        return {"value": None, "unit": "ciphertexts/s", "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
 
 
 class _Null:

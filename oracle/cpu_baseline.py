@@ -116,3 +116,51 @@ def run_verify_mix(bits: int = 3072, n_total: int = 100000, sample: int = 0, ste
             "sample": "%d of %d ciphertexts (verification of a %d-party mix, threshold %d, from its proof directory "
                       "incl. Fiat-Shamir hashing and membership checks), GMP 6 via %s, %d threads"
                       % (sample, n_total, k, threshold, lib_note, cores)}
+
+
+def run_committed_shuffle(bits: int = 2048, n_total: int = 100000, sample: int = 0, steps: int = 1, warmup: int = 0,
+                          group: str = "modp", width: int = 3):
+    """The same baseline for `bench.py --workload committed-shuffle` (BASELINE.json config 4's protocol): after an
+    untimed pre-computation for `sample` ciphertexts (protocols.precomp / shrink), one step = re-encryption factors for
+    fresh exponents, re-encryption + permutation, the commitment-consistent proof of a shuffle and its verification
+    (protocols.committed_shuffle / ccpos_verify), ModPGroup only."""
+    if group != "modp":
+        raise ValueError("the CPU arm of the committed shuffle is written for ModPGroup")
+    cores = accel.cores()
+    groups = importlib.import_module("verificatum-vmn_b200.groups")  # constants only
+    p, q, g = groups.rfc3526(bits) if bits != 512 else groups.test512()
+    G = ar.ModPGroup(p, q, g)
+    if sample <= 0:
+        sample = max(8 * cores, min(n_total, int(15.0 * cores / (0.02 * width * (bits / 3072.0) ** 2))))
+    undo = accel.install(G, cores)
+    try:
+        params = pr.Params(pgroup_string="ModPGroup(RFC3526-%d)" % bits)
+        rs = SeededRandomSource(hashlib.sha256(b"cpu-baseline/committed").digest())
+        pk = pr.wide_key((G.g, ar.g_exp(G, G.g, ar.ring_random_element(G, rs, 100))), width)
+
+        def exponents(src):
+            cols = tuple(ar.ring_random_array(G, sample, src, params.rbitlen) for _ in range(width))
+            return cols if width > 1 else cols[0]
+        w = ar.g_exp(G, pk, exponents(rs))
+        h = pr.independent_generators(G, "sha256", params.prefix(), "generators", sample, params.rbitlen)
+        state, _pub = pr.precomp(G, params, pk, h, rs)
+        pr.shrink(G, state, sample)
+        times = []
+        for i in range(warmup + steps):
+            prs = SeededRandomSource(hashlib.sha256(b"cpu-baseline/committed/step%d" % i).digest())
+            t0 = time.time()
+            state["s"] = exponents(prs)
+            state["factors"] = ar.g_exp(G, pk, state["s"])
+            wp, proof = pr.committed_shuffle(G, params, pk, state, w, prs)
+            ok = pr.ccpos_verify(G, params, G.g, state["h"], state["u"], pk, w, wp, proof["commitment"], proof["reply"])
+            dt = time.time() - t0
+            if not ok:
+                raise RuntimeError("cpu baseline: the verifier rejected an honest commitment-consistent proof")
+            if i >= warmup:
+                times.append(dt)
+        t = sum(times) / len(times)
+    finally:
+        undo()
+    return {"value": sample / t, "ms_per_step": t * 1e3, "cores": cores, "sample_n": sample,
+            "sample": "%d of %d ciphertexts of width %d (re-encryption factors, re-encryption, CCPoS prove + verify incl. "
+                      "Fiat-Shamir hashing), GMP 6 via oracle/cpu_ref.c, %d threads" % (sample, n_total, width, cores)}

@@ -40,6 +40,13 @@ def test_reference_arm_verify_mix_line():
     assert line["config"]["cpu_sample"] == 24 and line["value"] > 0
 
 
+def test_reference_arm_committed_shuffle_line():
+    line = _run("--workload", "committed-shuffle", "--width", "3")
+    assert line["impl"] == "reference" and "commitment-consistent proof of a shuffle" in line["config"]["workload"]
+    assert line["config"]["cpu_sample"] == 24 and line["config"]["width"] == 3 and line["value"] > 0
+    assert line["cpu_baseline"]["sample"].startswith("24 of 300 ciphertexts of width 3")
+
+
 def test_other_ranks_of_the_reference_arm_do_nothing():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
