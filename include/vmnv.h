@@ -64,6 +64,10 @@ typedef struct vmxv_report {
   int plaintexts;    /* Plaintexts.bt equals the decrypted output: 1 / 0 / -1 */
   uint64_t hashed_bytes, launches;
   char error[400];
+  char test_vectors[16384]; /* the scalar test vectors of `vmnv -t` (mixnet/MixNetElGamalVerifyFiatShamirTool.java:82-224:
+                               par.*, der.rho, PoS.s / PoS.v, PoSC.*, CCPoS.*, Dec.s / Dec.v) in the order the reference
+                               prints them, one per line: name '@' party (0: none) '=' value (seeds and rho in
+                               hexadecimal, challenges and parameters in decimal); cut off when the buffer is full */
 } vmxv_report;
 
 /* Bind the engine (path of libvmx.so, or of the host-emulation build in the CPU tests).  0 on success. */

@@ -289,8 +289,9 @@ def shuffle_and_prove(G, params: Params, pkey, w, h, rs):
                 "commitment": commitment.to_bytes(), "reply": reply.to_bytes()}
 
 
-def verify_shuffle(G, params: Params, pkey, w, h, proof: dict) -> bool:
-    """mixnet/ShufflerElGamalSession.java:195-210,301-330 + hvzk/PoSTW.java:177-260."""
+def verify_shuffle(G, params: Params, pkey, w, h, proof: dict, tv=None) -> bool:
+    """mixnet/ShufflerElGamalSession.java:195-210,301-330 + hvzk/PoSTW.java:177-260.  `tv`: a dict that receives the
+    seed ("s") and the challenge ("v"), the test vectors PoS.s / PoS.v of `vmnv -t`."""
     n = ar.size_of(w)
     prefix = params.prefix()
     try:
@@ -312,6 +313,8 @@ def verify_shuffle(G, params: Params, pkey, w, h, proof: dict) -> bool:
     except bt.EIOError:
         ctree = V.set_commitment(bt.leaf(b""))
     cb = challenge(params.rohash, prefix, bt.node(bt.leaf(seed), ctree), params.vbitlenro)
+    if tv is not None:
+        tv["s"], tv["v"] = seed, int.from_bytes(cb, "big")
     V.set_challenge(int.from_bytes(cb, "big"))
     try:
         return V.verify(bt.read(proof["reply"]))
@@ -694,7 +697,7 @@ def posc_prove(G, params: Params, g, h, u, r, pi, rs):
     return commitment.to_bytes(), reply.to_bytes()
 
 
-def posc_verify(G, params: Params, g, h, u, commitment: bytes, reply: bytes) -> bool:
+def posc_verify(G, params: Params, g, h, u, commitment: bytes, reply: bytes, tv=None) -> bool:
     """hvzk/PoSCTW.java:137-210; mixnet/MixNetElGamalVerifyFiatShamirSession.java:652-705."""
     prefix = params.prefix()
     V = PoSCBasicTW(G, params.vbitlenro, params.ebitlenro, params.rbitlen, params.prghash, None)
@@ -707,6 +710,8 @@ def posc_verify(G, params: Params, g, h, u, commitment: bytes, reply: bytes) -> 
     except bt.EIOError:
         ctree = V.set_commitment(bt.leaf(b""))
     cb = challenge(params.rohash, prefix, bt.node(bt.leaf(seed), ctree), params.vbitlenro)
+    if tv is not None:
+        tv["s"], tv["v"] = seed, int.from_bytes(cb, "big")
     V.set_challenge(int.from_bytes(cb, "big"))
     try:
         return V.verify(bt.read(reply))
@@ -732,7 +737,7 @@ def ccpos_prove(G, params: Params, g, h, u, pkey, w, wp, r, pi, s, rs):
     return commitment.to_bytes(), reply.to_bytes()
 
 
-def ccpos_verify(G, params: Params, g, h, u, pkey, w, wp, commitment: bytes, reply: bytes) -> bool:
+def ccpos_verify(G, params: Params, g, h, u, pkey, w, wp, commitment: bytes, reply: bytes, tv=None) -> bool:
     """hvzk/CCPoSW.java:160-260 with raisedu == null; mixnet/MixNetElGamalVerifyFiatShamirSession.java:757-841."""
     V = CCPoSBasicW(G, params.vbitlenro, params.ebitlenro, params.rbitlen, params.prghash)
     V.set_instance(g, h, u, pkey, w, wp)
@@ -744,6 +749,8 @@ def ccpos_verify(G, params: Params, g, h, u, pkey, w, wp, commitment: bytes, rep
     except bt.EIOError:
         ctree = V.set_commitment(bt.leaf(b""))
     cb = challenge(params.rohash, params.prefix(), bt.node(bt.leaf(seed), ctree), params.vbitlenro)
+    if tv is not None:
+        tv["s"], tv["v"] = seed, int.from_bytes(cb, "big")
     V.set_challenge(int.from_bytes(cb, "big"))
     try:
         return V.verify(bt.read(reply))
@@ -983,7 +990,20 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
         width = _parse_int(need("width"))
         if width < 1 or (expected_width is not None and width != expected_width):
             raise MixVerificationError("width")
-    rep = {"type": typ, "shuffles": {}, "poscs": {}, "decryption": None}
+    # the scalar test vectors of `vmnv -t` (mixnet/MixNetElGamalVerifyFiatShamirTool.java:82-224), in the order the
+    # reference prints them: (name, party or None, value)
+    vectors = []
+    rep = {"type": typ, "shuffles": {}, "poscs": {}, "decryption": None, "vectors": vectors}
+
+    def record(name, value, party=None):
+        vectors.append((name, party, value.hex() if isinstance(value, (bytes, bytearray)) else str(value)))
+    for name, value in (("par.k", k), ("par.lambda", threshold), ("par.n_e", params.ebitlenro), ("par.n_r", params.rbitlen),
+                        ("par.n_v", params.vbitlenro), ("par.s_Gq", params.pgroup_string), ("par.version", params.version)):
+        record(name, value)
+    if ccpos or dec:
+        record("par.omega", width)
+    record("par.sid", params.sid)
+    record("der.rho", params.prefix())
     try:
         pk = ar.parse_elem(G, bt.read(need("FullPublicKey.bt")), (None, None))
     except (ar.FormatError, bt.EIOError):
@@ -1006,6 +1026,7 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
     active = _parse_int(need("proofs/activethreshold"))
     if active > k or active < threshold:
         raise MixVerificationError("active threshold")
+    record("par.lambda", active)
     basic_pk, pk = pk, wide_key(pk, width)
     # readCiphertexts :1017-1046
     w = None
@@ -1029,6 +1050,7 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
         if precomp_:
             maxciph = _parse_int(need("proofs/maxciph"))
             # (no file of the directory could hold a commitment of that many elements)
+            record("par.N_0", maxciph)
             if maxciph < 1 or maxciph > max(len(v) for v in d.values()) // (5 + (G.p.bit_length() + 7) // 8):
                 raise MixVerificationError("maxciph")
         else:
@@ -1052,8 +1074,11 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
                 except (ar.FormatError, bt.EIOError):
                     raise MixVerificationError("permutation commitment of party %d" % l)
                 if posc and precomp_:   # verifyPoSC :652-705
+                    tv = {}
                     ok = posc_verify(G, params, G.g, h, u, need("proofs/PoSCCommitment%02d.bt" % l),
-                                     need("proofs/PoSCReply%02d.bt" % l))
+                                     need("proofs/PoSCReply%02d.bt" % l), tv)
+                    record("PoSC.s", tv["s"], l)
+                    record("PoSC.v", tv["v"], l)
                     rep["poscs"][l] = ok
                     if not ok:
                         verdict = False
@@ -1075,14 +1100,20 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
                         if sum(kl.value) != n:
                             raise MixVerificationError("wrong number of true elements in keep list of party %d" % l)
                         su = [x for x, keep in zip(u, kl.value) if keep]
+                        tv = {}
                         ok = ccpos_verify(G, params, G.g, shrunk, su, pk, inp, out,
-                                          need("proofs/CCPoSCommitment%02d.bt" % l), need("proofs/CCPoSReply%02d.bt" % l))
+                                          need("proofs/CCPoSCommitment%02d.bt" % l), need("proofs/CCPoSReply%02d.bt" % l), tv)
+                        record("CCPoS.s", tv["s"], l)
+                        record("CCPoS.v", tv["v"], l)
                         verdict = verdict and ok
                     else:
                         proof = {"output": d[name], "permutationCommitment": d[pcname],
                                  "commitment": need("proofs/PoSCommitment%02d.bt" % l),
                                  "reply": need("proofs/PoSReply%02d.bt" % l)}
-                        verdict = verify_shuffle(G, params, pk, inp, h, proof)
+                        tv = {}
+                        verdict = verify_shuffle(G, params, pk, inp, h, proof, tv)
+                        record("PoS.s", tv["s"], l)
+                        record("PoS.v", tv["v"], l)
                     inp = out if verdict else inp
                 rep["shuffles"][l] = verdict
                 valid += 1 if verdict else 0
@@ -1113,6 +1144,7 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
     prefix = params.prefix()
     seed = challenge(params.rohash, prefix, _dec_seed_data(G, G.g, inp, coeffs, f, k),
                      8 * PRGHeuristic(params.prghash).min_no_seed_bytes())
+    record("Dec.s", seed)
     V = DistrElGamalSessionBasic(G, 0, k, threshold, params.ebitlenro, params.rbitlen, params.prghash, G.g, ys, u)
     V.f = f
     V.set_batch_vector(seed)
@@ -1125,6 +1157,7 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
             V.set_commitment(l, bt.leaf(b""))
     cdata = bt.node(bt.leaf(seed), bt.node([V.commitment_tree(l) for l in range(1, k + 1)]))
     v = int.from_bytes(challenge(params.rohash, prefix, cdata, params.vbitlenro), "big")
+    record("Dec.v", v)
     for l in range(1, k + 1):
         try:
             V.set_reply(l, bt.read(need("proofs/DecrFactReply%02d.bt" % l)))

@@ -738,6 +738,8 @@ def _mix_parity(vmx, spec, OG, n, k=3, threshold=2, tmpdir=None, width=1, mode="
     assert rep["poscs"] == orep["poscs"] == ({l: True for l in range(1, threshold + 1)}
                                              if shuffled and maxciph is not None else {})
     assert rep["decryption"] == orep["decryption"] == (None if mode == "shuffling" else True)
+    # the scalar test vectors of `vmnv -t` (global prefix, seeds, challenges, parameters), in the reference's order
+    assert rep["vectors"] == orep["vectors"] and any(nm == "der.rho" for nm, _, _ in rep["vectors"])
     if mode != "mixing" or maxciph is not None:
         return _mix_variants(vmx, vm, V, G, OG, params, oparams, k, threshold, M.nizkp, mode, maxciph, light)
 
@@ -1223,6 +1225,7 @@ def native_vmnv_parity(vmx, spec, n, k=3, threshold=2, width=1, thorough=True, m
 
     honest = outcome(VN, M.nizkp)
     assert honest == outcome(VP, M.nizkp) and honest[:3] == ("verdict", mode, True), honest
+    assert VN.report["vectors"] == VP.report["vectors"] and len(VN.report["vectors"]) > 10   # `vmnv -t` test vectors
     assert VN.report["hashed_bytes"] > 0 and VN.report["launches"] > 0
     # what is verified (-nodec, -noposc, -noccpos) and the expected type (-mix, -shuffle, -decrypt)
     options = (dict(dec=False), dict(posc=False), dict(ccpos=False), dict(posc=False, ccpos=False),

@@ -13,6 +13,7 @@ import pytest
 from oracle import arithm as oar
 from oracle import bytetree as bt
 from oracle import protocols as opr
+from oracle import testvectors
 
 REF = os.path.join(os.path.dirname(__file__), "golden", "nizkp_ref")
 needs_ref = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "nizkp")),
@@ -30,9 +31,25 @@ def _load():
     vectors = {}
     tv = os.path.join(REF, "vmnv_testvectors.txt")
     if os.path.exists(tv):
-        for m in re.finditer(r"^\s*([A-Za-z]+\.[A-Za-z0-9_.\[\]]+)\s*[=:]\s*(\S+)\s*$", open(tv).read(), flags=re.M):
-            vectors[m.group(1)] = m.group(2)
+        vectors = testvectors.parse(open(tv).read())   # {(name, party or None): [values]}, the format of `vmnv -t`
     return params, d, vectors
+
+
+def _check_vectors(ours, theirs):
+    """Every scalar test vector we derive that the reference's dump also holds must agree (same party, same order
+    of appearance).  Returns how many were compared."""
+    seen, compared = {}, 0
+    for name, party, value in ours:
+        if name not in testvectors.SCALAR_NAMES:
+            continue
+        idx = seen.get((name, party), 0)
+        seen[(name, party)] = idx + 1
+        ref = theirs.get((name, party))
+        if ref is None or idx >= len(ref):
+            continue
+        assert testvectors.same_value(name, value, ref[idx]), (name, party, value, ref[idx])
+        compared += 1
+    return compared
 
 
 def marshalled_group(pgroup: str):
@@ -57,9 +74,10 @@ def test_oracle_accepts_the_reference_proof_directory():
     P = _oracle_params(params)
     rep = opr.verify_mix(G, P, params["k"], params["threshold"], d)
     assert rep["accepted"], rep
-    rho = P.with_auxsid(d["auxsid"].decode()).prefix().hex()
-    if "der.rho" in vectors:
-        assert vectors["der.rho"].lower() == rho
+    # the global prefix, every seed and every challenge derived on the way against the `vmnv -t` dump
+    if vectors:
+        assert ("der.rho", None) in vectors, "the dump holds no der.rho: was vmnv run with -t par,der,bas,PoS,Dec,PoSC,CCPoS?"
+        assert _check_vectors(rep["vectors"], vectors) >= 3
 
 
 @needs_ref
@@ -77,7 +95,7 @@ def test_engine_accepts_the_reference_proof_directory(engine_cuda):
     rep = V.verify(vm.ProofDirectory(d))
     orep = opr.verify_mix(oar.ModPGroup(*marshalled_group(params["pgroup"])), _oracle_params(params), params["k"],
                           params["threshold"], d)
-    assert rep["accepted"] and rep["shuffles"] == orep["shuffles"]
+    assert rep["accepted"] and rep["shuffles"] == orep["shuffles"] and rep["vectors"] == orep["vectors"]
 
 
 def test_the_loader_reads_what_the_engine_writes(tmp_path, monkeypatch):
@@ -104,9 +122,22 @@ def test_the_loader_reads_what_the_engine_writes(tmp_path, monkeypatch):
         f.parent.mkdir(parents=True, exist_ok=True)
         f.write_bytes(data)
     (root / "params.json").write_text(json.dumps(params))
-    (root / "vmnv_testvectors.txt").write_text("der.rho = %s\n" % P.with_auxsid("default").prefix().hex())
+    # the dump `vmnv -v -t ...` would print for it, in the reference's format, between other output
+    honest = opr.verify_mix(G, P, 3, 2, d)
+    dump = "Prepare to verify proof.\n" + testvectors.render(honest["vectors"]) + "\nVerification completed SUCCESSFULLY\n"
+    (root / "vmnv_testvectors.txt").write_text(dump)
     monkeypatch.setattr(importlib.import_module(__name__), "REF", str(root))
     params2, d2, vectors = _load()
-    assert marshalled_group(params2["pgroup"]) == (p, q, g) and d2 == d and "der.rho" in vectors
+    assert marshalled_group(params2["pgroup"]) == (p, q, g) and d2 == d and ("der.rho", None) in vectors
+    assert vectors[("PoS.s", 2)] and vectors[("Dec.v", None)] and len(vectors[("par.lambda", None)]) == 2
     rep = opr.verify_mix(G, _oracle_params(params2), 3, 2, d2)
     assert rep["accepted"]
+    scalars = [v for v in rep["vectors"] if v[0] in testvectors.SCALAR_NAMES]
+    assert _check_vectors(rep["vectors"], vectors) == len(scalars) >= 15
+    # a dump that disagrees anywhere is caught (a challenge printed in hexadecimal is accepted)
+    name, party, value = next(v for v in rep["vectors"] if v[0] == "PoS.v")
+    vectors[(name, party)][0] = "%x" % int(value)
+    assert _check_vectors(rep["vectors"], vectors) == len(scalars)
+    vectors[(name, party)][0] = str(int(value) + 1)
+    with pytest.raises(AssertionError):
+        _check_vectors(rep["vectors"], vectors)

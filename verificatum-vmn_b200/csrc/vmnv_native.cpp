@@ -573,6 +573,7 @@ struct Session {
   std::map<std::string, Span> files;
   Bytes prefix;  // rho
   int width = 1;
+  int party = 0;   // the party whose proof is being verified (test vectors)
   uint64_t hashed = 0;
 
   Span file(const std::string& name) const {
@@ -584,6 +585,31 @@ struct Session {
   std::string text(const std::string& name) const { const Span s = file(name); return std::string((const char*)s.p, s.n); }
 
   Bytes challenge_finish(Oracle& o) { Bytes r = o.finish(); hashed += o.hashed; return r; }
+
+  // the scalar test vectors of `vmnv -t` (mixnet/MixNetElGamalVerifyFiatShamirTool.java:82-224) in the order the
+  // reference prints them, one per line: name '@' party (0: none) '=' value
+  std::string vectors;
+  void record(const char* name, int party, const std::string& value) {
+    vectors += std::string(name) + "@" + std::to_string(party) + "=" + value + "\n";
+  }
+  static std::string hex_of(const Bytes& b) {
+    static const char* d = "0123456789abcdef";
+    std::string o;
+    for (uint8_t v : b) { o += d[v >> 4]; o += d[v & 15]; }
+    return o;
+  }
+  static std::string decimal_of(Bytes b) {   // a non-negative big-endian integer (LargeInteger.toString)
+    std::string o;
+    size_t first = 0;
+    while (first < b.size()) {
+      unsigned rem = 0;
+      for (size_t i = first; i < b.size(); i++) { const unsigned cur = rem * 256 + b[i]; b[i] = (uint8_t)(cur / 10); rem = cur % 10; }
+      o += (char)('0' + rem);
+      while (first < b.size() && b[first] == 0) first++;
+    }
+    if (o.empty()) o = "0";
+    return std::string(o.rbegin(), o.rend());
+  }
 
   // ---- hvzk/PoSTW.java:177-260 over hvzk/PoSBasicTW.java: one proof of a shuffle
   // (w == nullptr: hvzk/PoSCTW.java:137-210 over hvzk/PoSCBasicTW.java -- the same proof without the ciphertexts)
@@ -728,6 +754,8 @@ bool Session::verify_shuffle(const Garr& h, Span hTree, const Elem& h0, size_t n
   if (ciph) for (const Garr& a : wq->c) arrs.push_back(&a);
   const std::vector<Elem> AF = expprod_many(C, arrs, e);
   const Bytes vBytes = challenge_finish(chalO);
+  record(ciph ? "PoS.s" : "PoSC.s", party, hex_of(prgSeed));
+  record(ciph ? "PoS.v" : "PoSC.v", party, decimal_of(vBytes));
   if (!parsed) return false;
   const Scalar v = scalar_from_bytes(C, vBytes);
 
@@ -821,6 +849,8 @@ bool Session::verify_ccpos(const Garr& h, Span hTree, size_t n, const Garr& u, S
   for (const Garr& a : w.c) arrs.push_back(&a);
   const std::vector<Elem> AB = expprod_many(C, arrs, e);
   const Bytes vBytes = challenge_finish(chalO);
+  record("CCPoS.s", party, hex_of(prgSeed));
+  record("CCPoS.v", party, decimal_of(vBytes));
   if (!parsed) return false;
   const Scalar v = scalar_from_bytes(C, vBytes);
   bool ok = elem_mul(C, elem_exp(C, AB[0], v), Ap) == rightA;
@@ -903,6 +933,13 @@ void Session::run(vmxv_report* rep) {
   if (!sid_ok) fail_stop("Can not read auxsid from file!");
   if (P->expected_auxsid && P->expected_auxsid[0] && auxsid != P->expected_auxsid)
     fail_stop("The given auxiliary session identifier does not match the one in the proof!");
+  record("par.k", 0, std::to_string(k));
+  record("par.lambda", 0, std::to_string(threshold));
+  record("par.n_e", 0, std::to_string(P->ebitlenro));
+  record("par.n_r", 0, std::to_string(P->rbitlen));
+  record("par.n_v", 0, std::to_string(P->vbitlenro));
+  record("par.s_Gq", 0, P->pgroup_string);
+  record("par.version", 0, P->version);
   bool dec = !P->nodec, posc = !P->noposc, ccpos = !P->noccpos;
   if (type == "shuffling") dec = false;
   else if (type == "decryption") posc = ccpos = false;
@@ -912,6 +949,7 @@ void Session::run(vmxv_report* rep) {
     if (!parse_int_strict(text("width"), &wv)) fail_stop("Can not parse width given in file!");
     if (wv < 1 || wv > 1024 || (P->expected_width > 0 && wv != P->expected_width)) fail_stop("Mismatching or invalid width!");
     width = (int)wv;
+    record("par.omega", 0, std::to_string(width));
   }
   const int W = width;
   // ---- global prefix (:158-189)
@@ -955,6 +993,8 @@ void Session::run(vmxv_report* rep) {
       pkeys[(size_t)l] = acc;
     }
   }
+  record("par.sid", 0, P->sid);
+  record("der.rho", 0, hex_of(prefix));
   const bool precomp = has("proofs/maxciph");                                                     // :946-948
   int active = 0;
   {
@@ -962,6 +1002,7 @@ void Session::run(vmxv_report* rep) {
     if (!parse_int_strict(text("proofs/activethreshold"), &a)) fail_stop("Can not parse active threshold given in file!");
     if (a > k || a < threshold) fail_stop("Active threshold out of range!");
     active = (int)a;
+    record("par.lambda", 0, std::to_string(active));
   }
   // ---- input ciphertexts (readCiphertexts :1017-1046; readArray with size 0: the size is that of the first array)
   auto read_ciph = [&](Span s, const std::string& name, size_t n) {
@@ -1038,6 +1079,7 @@ void Session::run(vmxv_report* rep) {
     if (precomp) {                                                                                // getMaxciph :541-548
       long mc = 0;
       if (!parse_int_strict(text("proofs/maxciph"), &mc)) fail_stop("Can not parse maxciph file!");
+      record("par.N_0", 0, std::to_string(mc));
       if (mc < 1) fail_stop("Invalid maxciph!");
       maxciph = (size_t)mc;
     } else if (!ciphertexts) {
@@ -1090,6 +1132,7 @@ void Session::run(vmxv_report* rep) {
             || has("proofs/CCPoSCommitment" + two(l) + ".bt") || has("proofs/PoSCommitment" + two(l) + ".bt")))   // :972-976
         continue;
       rep->n_shuffles = l;
+      party = l;
       // readPermutationCommitment :626-641: fail-stop when missing or malformed
       const Span pcFile = file(pcName);
       Garr u;
@@ -1228,6 +1271,7 @@ void Session::run(vmxv_report* rep) {
     }
     prgSeed = challenge_finish(seedO);
   }
+  record("Dec.s", 0, hex_of(prgSeed));
   Rarr e = batch_vector(C, prgSeed, n, (unsigned)P->ebitlenro);
   // A = prod u^e, combinedB = prod combined^e  (:524-526, :683-685)
   std::vector<const Garr*> arrs;
@@ -1257,7 +1301,9 @@ void Session::run(vmxv_report* rep) {
     chalO.update_owned(elem_tree(C, yp[(size_t)l]));
     hash_plain_elem(C, chalO, Bp[(size_t)l]);
   }
-  const Scalar v = scalar_from_bytes(C, challenge_finish(chalO));
+  const Bytes decV = challenge_finish(chalO);
+  record("Dec.v", 0, decimal_of(decV));
+  const Scalar v = scalar_from_bytes(C, decV);
   for (int l = 1; l <= k; l++) {
     try {
       kx[(size_t)l] = parse_scalar(C, file("proofs/DecrFactReply" + two(l) + ".bt"));
@@ -1394,6 +1440,7 @@ int vmxv_verify(const vmxv_params* P, const vmxv_file* files, size_t nfiles, vmx
       rep->accepted = 0;
       snprintf(rep->error, sizeof rep->error, "Malformed proof directory: %s", e.what());
     }
+    snprintf(rep->test_vectors, sizeof rep->test_vectors, "%s", S.vectors.c_str());
     rep->hashed_bytes = S.hashed;
     rep->launches = api.vmx_ctx_launch_count(c) - l0;
     return 0;

@@ -844,6 +844,7 @@ class PoSTW:
             ByteTreeContainer(ByteTreeLeaf(prgSeed), commitmentTree).update(cd)
         V.computeAF()
         challengeBytes = self.challenger.finish(cd)
+        self.testVector = {"s": prgSeed, "v": _to_positive(challengeBytes)}   # PoS.s / PoS.v of `vmnv -t`
         V.setChallenge(_to_positive(challengeBytes))
         return V.verifyParsed() if parsed else False
 
@@ -901,6 +902,7 @@ class PoSCTW:
         V.setBatchVector(prgSeed)
         challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), commitmentTree)
         challengeBytes = self.challenger.challenge(challengeData, self.vbitlen, self.rbitlen)
+        self.testVector = {"s": prgSeed, "v": _to_positive(challengeBytes)}   # PoSC.s / PoSC.v of `vmnv -t`
         V.setChallenge(_to_positive(challengeBytes))
         verdict = V.verifyParsed() if parsed else False
         V.free()
@@ -991,6 +993,7 @@ class CCPoSW:
         ByteTreeContainer(ByteTreeLeaf(prgSeed), commitmentTree).update(cd)
         V.computeAB()
         challengeBytes = self.challenger.finish(cd)
+        self.testVector = {"s": prgSeed, "v": _to_positive(challengeBytes)}   # CCPoS.s / CCPoS.v of `vmnv -t`
         V.setChallenge(_to_positive(challengeBytes))
         verdict = V.verifyParsed() if parsed else False
         V.free()

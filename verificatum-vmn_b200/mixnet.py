@@ -225,6 +225,7 @@ class ShufflerSession:
         verdict = V.verify(widePublicKey, ciphertexts, output, proof.permutationCommitment, proof.commitment,
                            proof.reply, outputBytes=outputBytes)
         self.last_u_parsed = V.u_parsed
+        self.last_test_vector = V.testVector
         V.free()
         if own_generators:
             generators.free()

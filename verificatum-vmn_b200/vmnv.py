@@ -349,7 +349,14 @@ class MixNetElGamalVerifyFiatShamirSession:
 
     def _verify(self, nizkp: ProofDirectory) -> Dict[str, object]:
         p, k, threshold, G = self.params, self.k, self.threshold, self.pGroup
-        rep = self.report = {"shuffles": {}, "poscs": {}, "decryption": None}
+        # the scalar test vectors of `vmnv -t` (mixnet/MixNetElGamalVerifyFiatShamirTool.java:82-224), in the order the
+        # reference prints them: (name, party or None, value)
+        vectors = []
+        rep = self.report = {"shuffles": {}, "poscs": {}, "decryption": None, "vectors": vectors}
+
+        def record(name, value, party=None):
+            vectors.append((name, party, bytes(value).hex() if isinstance(value, (bytes, bytearray, memoryview))
+                            else str(value)))
         if self._file(nizkp, "version").decode() != p.version:
             raise VerificationError("Mismatching versions!")
         # determineType :329-358, determineSessionParams :984-1005
@@ -368,6 +375,9 @@ class MixNetElGamalVerifyFiatShamirSession:
         if self.expectedAuxsid is not None and auxsid != self.expectedAuxsid:
             raise VerificationError("The given auxiliary session identifier does not match the one in the proof!")
         p = dataclasses.replace(p, auxsid=auxsid)
+        for name, value in (("par.k", k), ("par.lambda", threshold), ("par.n_e", p.ebitlenro), ("par.n_r", p.rbitlen),
+                            ("par.n_v", p.vbitlenro), ("par.s_Gq", p.pGroupString), ("par.version", p.version)):
+            record(name, value)
         dec, posc, ccpos = self.dec, self.posc, self.ccpos
         if typ == "shuffling":
             dec = False
@@ -383,6 +393,7 @@ class MixNetElGamalVerifyFiatShamirSession:
                 raise VerificationError("Can not parse width given in file!")
             if width < 1 or (self.expectedWidth is not None and width != self.expectedWidth):
                 raise VerificationError("Mismatching or invalid width!")
+            record("par.omega", width)
         ciphPGroup = getCiphPGroup(G, width)
         # readFullPKey :195-226
         try:
@@ -405,6 +416,8 @@ class MixNetElGamalVerifyFiatShamirSession:
                 raise VerificationError("Mismatching public keys!")
         session = ShufflerSession(G, fullPKey, p, None)
         challenger = session.challenger
+        record("par.sid", p.sid)
+        record("der.rho", challenger.globalPrefix)
         precomp = "proofs/maxciph" in nizkp                                                           # :946-948
         try:
             active = _parse_int(self._file(nizkp, "proofs/activethreshold"))
@@ -412,6 +425,7 @@ class MixNetElGamalVerifyFiatShamirSession:
             raise VerificationError("Can not parse active threshold given in file!")
         if active > k or active < threshold:
             raise VerificationError("Active threshold out of range!")
+        record("par.lambda", active)
         # readCiphertexts :1017-1046
         ciphertexts, ctName = None, None
         if ccpos or dec:
@@ -458,6 +472,7 @@ class MixNetElGamalVerifyFiatShamirSession:
                     maxciph = _parse_int(self._file(nizkp, "proofs/maxciph"))
                 except ValueError:
                     raise VerificationError("Can not parse maxciph file!")
+                record("par.N_0", maxciph)
                 if maxciph < 1:
                     raise VerificationError("Invalid maxciph!")
                 # every party that counts published a permutation commitment of maxciph elements (else
@@ -491,6 +506,8 @@ class MixNetElGamalVerifyFiatShamirSession:
                     V = PoSCTW(p.vbitlenro, p.ebitlenro, p.rbitlen, session.prg, None, challenger)
                     ok = V.verify(G.getg(), generators, pc, self._file(nizkp, ProofDirectory.PoSCCfile(l)),
                                   self._file(nizkp, ProofDirectory.PoSCRfile(l)))
+                    record("PoSC.s", V.testVector["s"], l)
+                    record("PoSC.v", V.testVector["v"], l)
                     rep["poscs"][l] = ok
                     if not ok:
                         verdict = False
@@ -519,6 +536,8 @@ class MixNetElGamalVerifyFiatShamirSession:
                                       self._file(nizkp, ProofDirectory.CCPoSCfile(l)),
                                       self._file(nizkp, ProofDirectory.CCPoSRfile(l)))
                         shrunk.free()
+                        record("CCPoS.s", V.testVector["s"], l)
+                        record("CCPoS.v", V.testVector["v"], l)
                         verdict = verdict and ok
                         if not verdict:
                             output.free()
@@ -532,6 +551,8 @@ class MixNetElGamalVerifyFiatShamirSession:
                         if not session.last_u_parsed:   # readPermutationCommitment :626-641 is fail-stop
                             output.free()
                             raise VerificationError("Unable to read array %s!" % pcName)
+                        record("PoS.s", session.last_test_vector["s"], l)
+                        record("PoS.v", session.last_test_vector["v"], l)
                     if inp is not ciphertexts:
                         inp.free()
                     inp = output
@@ -583,6 +604,7 @@ class MixNetElGamalVerifyFiatShamirSession:
                 spec.abandon()
             seedData = _decryption_seed_data(G.getg(), mixed, coeffs, f, k)
             prgSeed = challenger.challenge(seedData, 8 * PRGHeuristic().minNoSeedBytes(), p.rbitlen)
+        record("Dec.s", prgSeed)
         basic.setBatchVector(prgSeed)
         basic.batchInput()
         basic.batchCombined()
@@ -590,6 +612,7 @@ class MixNetElGamalVerifyFiatShamirSession:
             basic.setCommitment(l, self._file(nizkp, ProofDirectory.DFCfile(l)))
         challengeData = ByteTreeContainer(ByteTreeLeaf(prgSeed), basic.getCommitment())
         v = _to_positive(challenger.challenge(challengeData, p.vbitlenro, p.rbitlen))
+        record("Dec.v", v)
         for l in range(1, k + 1):
             basic.setReply(l, self._file(nizkp, ProofDirectory.DFRfile(l)))
         basic.combine(correct)

@@ -39,7 +39,8 @@ class _Report(C.Structure):
     _fields_ = [("accepted", C.c_int), ("fail_stop", C.c_int), ("type", C.c_int), ("n_shuffles", C.c_int),
                 ("shuffles", C.c_int * 64), ("poscs", C.c_int * 64), ("valid_proofs", C.c_int),
                 ("enough_valid_proofs", C.c_int), ("decryption", C.c_int), ("plaintexts", C.c_int),
-                ("hashed_bytes", C.c_uint64), ("launches", C.c_uint64), ("error", C.c_char * 400)]
+                ("hashed_bytes", C.c_uint64), ("launches", C.c_uint64), ("error", C.c_char * 400),
+                ("test_vectors", C.c_char * 16384)]
 
 
 _lib = None
@@ -116,6 +117,11 @@ class MixNetElGamalVerifyFiatShamirSessionNative:
                "poscs": {l + 1: R.poscs[l] > 0 for l in range(span) if R.poscs[l]},
                "decryption": tri(R.decryption), "hashed_bytes": int(R.hashed_bytes), "launches": int(R.launches),
                "validProofs": int(R.valid_proofs), "enoughValidProofs": bool(R.enough_valid_proofs)}
+        rep["vectors"] = []
+        for ln in R.test_vectors.decode("utf-8", "replace").splitlines():
+            head, _, value = ln.partition("=")
+            name, _, party = head.partition("@")
+            rep["vectors"].append((name, int(party) or None, value))
         self.report = rep
         if R.fail_stop:
             raise VerificationError(R.error.decode("utf-8", "replace"))
