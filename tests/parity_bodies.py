@@ -1360,8 +1360,8 @@ def native_vmnv_fuzz(vmx, spec, n, rounds, seed_label="fuzz", k=3, threshold=2, 
 
     def outcome(V, d):
         try:
-            r = V.verify(d)
-            return ("verdict", r["accepted"], r["shuffles"], r["poscs"], r["decryption"], r.get("plaintexts"))
+            r = V.verify(d)   # (with the seeds and challenges derived on the way: the test vectors of `vmnv -t`)
+            return ("verdict", r["accepted"], r["shuffles"], r["poscs"], r["decryption"], r.get("plaintexts"), r["vectors"])
         except vm.VerificationError:
             return ("failstop", V.report.get("shuffles"), V.report.get("poscs"))
 

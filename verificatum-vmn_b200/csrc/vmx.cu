@@ -219,8 +219,12 @@ struct ElemBuf : DevBuf {
   uint32_t* d() const { return as<uint32_t>(); }
 };
 
+// Element counts are bounded well below where cap * limbs * 4 leaves 64 bits (indices of permutations and the launch
+// geometry are 32-bit); the reference's arrays are Java arrays, int-indexed.
+static constexpr size_t kMaxElems = (size_t)1 << 31;
 static int new_garr(vmx_ctx* c, size_t n, vmx_garr** out) {
   *out = nullptr;
+  if (n > kMaxElems) { set_error("array of %zu elements is beyond the engine's limit of 2^31", n); return VMX_ESIZE; }
   auto* a = new (std::nothrow) vmx_garr{c, n, cap_for(n), nullptr};
   if (!a) return VMX_ENOMEM;
   void* p = nullptr;
@@ -236,6 +240,7 @@ static int new_garr(vmx_ctx* c, size_t n, vmx_garr** out) {
 }
 static int new_rarr(vmx_ctx* c, size_t n, vmx_rarr** out) {
   *out = nullptr;
+  if (n > kMaxElems) { set_error("array of %zu elements is beyond the engine's limit of 2^31", n); return VMX_ESIZE; }
   auto* a = new (std::nothrow) vmx_rarr{c, n, cap_for(n), nullptr, -1};
   if (!a) return VMX_ENOMEM;
   void* p = nullptr;
@@ -1724,6 +1729,7 @@ int vmx_elem_inv(vmx_ctx* c, const uint8_t* in_be, uint8_t* out_be) {
 
 int vmx_fixed_precompute(vmx_ctx* c, const uint8_t* base_be, size_t n_hint) {
   VMX_ENTER(c);
+  if (!base_be) { set_error("null base"); return VMX_EARG; }
   FixedTable T;
   return get_table(c, base_be, n_hint, &T);
 }
