@@ -778,7 +778,7 @@ def run_shuffle(args, env):
                            "nominal_frac_of_imad_peak": value / world * nominal["total"] * macs / IMAD_PEAK_MAC_PER_S,
                            "executed_frac_of_imad_peak": modmuls * macs / (dev_ms * 1e-3) / IMAD_PEAK_MAC_PER_S,
                            "note": "fractions are per GPU (rank 0's kernels against one GPU's peak); a squaring "
-                                   "counts as one modmul although it executes ~0.79 of a multiplication's MACs"},
+                                   "counts as one modmul although it executes ~0.83 of a multiplication's MACs"},
                 "host_wall_ms_per_step": t_host * 1e3 / args.steps,
                 "step_ms": {"min": min(step_ms), "max": max(step_ms), "all": step_ms[:32]}}
         if args.phases:

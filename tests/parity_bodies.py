@@ -822,11 +822,11 @@ def _mix_variants(vmx, vm, V, G, OG, params, oparams, k, threshold, honest, mode
         del missing[name]
         a, b = outcome_engine(missing), outcome_oracle(missing)
         assert a == b, (name, "missing", a, b)
-    if maxciph is not None:   # a keep list that keeps the wrong elements (right number): the CCPoS is rejected
-        import numpy as np
+    import numpy as np
+    flags = np.frombuffer(bytes(honest["proofs/KeepList01.bt"][5:]), dtype=np.uint8).copy() if maxciph is not None else None
+    if flags is not None and (flags == 0).any():   # a keep list that keeps the wrong elements (right number): the CCPoS is rejected
         bad = vm.ProofDirectory(honest)
         kl = bytearray(bad["proofs/KeepList01.bt"])
-        flags = np.frombuffer(bytes(kl[5:]), dtype=np.uint8).copy()
         i, j = int(np.flatnonzero(flags == 1)[0]), int(np.flatnonzero(flags == 0)[0])
         flags[i], flags[j] = 0, 1
         bad["proofs/KeepList01.bt"] = bytes(kl[:5]) + flags.tobytes()

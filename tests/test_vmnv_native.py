@@ -50,6 +50,15 @@ def test_native_verifier_session_types(engine_emul, vmnv_lib, mode, maxciph, wid
     pb.native_vmnv_parity(engine_emul, 512, 3, width=width, mode=mode, maxciph=maxciph, thorough=thorough)
 
 
+@pytest.mark.parametrize("k,threshold,n,mode,maxciph", [(1, 1, 2, "mixing", 2), (2, 1, 3, "shuffling", 3),
+                                                        (3, 3, 1, "decryption", None)])
+def test_edge_sizes(engine_emul, vmnv_lib, k, threshold, n, mode, maxciph):
+    """A single party, one ciphertext, a pre-computation for exactly the number of ciphertexts (keep lists of ones), a
+    threshold equal to the number of parties: oracle, mirror and libvmnv agree."""
+    pb.mix_parity(engine_emul, 512, n, k=k, threshold=threshold, mode=mode, maxciph=maxciph, light="min")
+    pb.native_vmnv_parity(engine_emul, 512, n, k=k, threshold=threshold, mode=mode, maxciph=maxciph, minimal=True)
+
+
 def test_native_verifier_differential_fuzz(engine_emul, vmnv_lib):
     """A seeded sample of the differential fuzzer (tools/fuzz_vmnv.py runs thousands of rounds under ASan)."""
     rounds = int(os.environ.get("VMNV_FUZZ_ROUNDS", "15"))
