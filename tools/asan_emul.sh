@@ -17,4 +17,4 @@ export VMNV_LIBRARY_PATH=$PWD/build/asan/libvmnv_asan.so
 export LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)"
 export ASAN_OPTIONS=detect_leaks=0:abort_on_error=0:halt_on_error=1
 export UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1
-python -m pytest tests/test_engine_emul.py tests/test_vmnv_native.py -x -q -p no:cacheprovider "$@"
+python -m pytest tests/test_engine_emul.py tests/test_vmnv_native.py tests/test_abi_misuse.py -x -q -p no:cacheprovider "$@"
