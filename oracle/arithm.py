@@ -69,7 +69,7 @@ class ModPGroup:
         return x
 
     def parse_leaf_array(self, t: bt.ByteTree, size: int):
-        if t.is_leaf() or len(t.children) != size:
+        if t.is_leaf() or t.declared != size or len(t.children) != size:
             raise FormatError("array size")
         return [self.parse_leaf(c) for c in t.children]
 
@@ -137,7 +137,7 @@ class FormatError(ValueError):
 
 def parse_elem(G: ModPGroup, t: bt.ByteTree, shape=None) -> int:
     if isinstance(shape, tuple):
-        if t.is_leaf() or len(t.children) != len(shape):
+        if t.is_leaf() or t.declared != len(shape) or len(t.children) != len(shape):
             raise FormatError("arity")
         return tuple(parse_elem(G, c, s) for c, s in zip(t.children, shape))
     return G.parse_leaf(t)
@@ -145,7 +145,7 @@ def parse_elem(G: ModPGroup, t: bt.ByteTree, shape=None) -> int:
 
 def parse_array(G: ModPGroup, t: bt.ByteTree, size: int, shape=None):
     if isinstance(shape, tuple):
-        if t.is_leaf() or len(t.children) != len(shape):
+        if t.is_leaf() or t.declared != len(shape) or len(t.children) != len(shape):
             raise FormatError("arity")
         return tuple(parse_array(G, c, size, s) for c, s in zip(t.children, shape))
     return G.parse_leaf_array(t, size)
@@ -153,7 +153,7 @@ def parse_array(G: ModPGroup, t: bt.ByteTree, size: int, shape=None):
 
 def parse_ring(G: ModPGroup, t: bt.ByteTree, shape=None):
     if isinstance(shape, tuple):
-        if t.is_leaf() or len(t.children) != len(shape):
+        if t.is_leaf() or t.declared != len(shape) or len(t.children) != len(shape):
             raise FormatError("arity")
         return tuple(parse_ring(G, c, s) for c, s in zip(t.children, shape))
     if not t.is_leaf() or len(t.value) != G.ring_bytes:
@@ -165,7 +165,7 @@ def parse_ring(G: ModPGroup, t: bt.ByteTree, shape=None):
 
 
 def parse_ring_array(G: ModPGroup, t: bt.ByteTree, size: int):
-    if t.is_leaf() or len(t.children) != size:
+    if t.is_leaf() or t.declared != size or len(t.children) != size:
         raise FormatError("array size")
     return [parse_ring(G, c) for c in t.children]
 

@@ -26,15 +26,19 @@ LEAF = 1
 class ByteTree:
     """Immutable byte tree: either a leaf (bytes) or a node (list of ByteTree)."""
 
-    __slots__ = ("value", "children")
+    __slots__ = ("value", "children", "declared")
 
-    def __init__(self, value: Union[bytes, Sequence["ByteTree"]]):
+    def __init__(self, value: Union[bytes, Sequence["ByteTree"]], declared: int | None = None):
         if isinstance(value, (bytes, bytearray, memoryview)):
             self.value = bytes(value)
             self.children = None
+            self.declared = None
         else:
             self.value = None
             self.children = list(value)
+            # the number of children the node's header announces: more than len(children) only for the root of a
+            # tree obtained with read() whose later children are missing or malformed
+            self.declared = len(self.children) if declared is None else declared
 
     def is_leaf(self) -> bool:
         return self.children is None
@@ -117,9 +121,39 @@ def from_bytes(data: bytes) -> ByteTree:
 
 
 def read(data: bytes) -> ByteTree:
-    """The byte tree at the start of `data`, as a ByteTreeReaderF over a file sees it: what follows the tree is never
-    read (no caller in the reference checks for the end of the file)."""
-    return parse(data, 0)[0]
+    """The byte tree at the start of `data`, as the reference's code sees a file or a message through a ByteTreeReader:
+    what follows the tree is never read (no caller checks for the end of the file), and the children of the ROOT are
+    reached one getNextChild() at a time -- a parser that takes the first k children of a node never learns that a
+    later one is missing or malformed.  The root therefore keeps the longest prefix of well-formed children, with the
+    count its header announces in `declared`; `first(t, k)` / `exact(t, k)` are the two ways the reference's parsers
+    consume a node.  Everything below the root is parsed strictly (getNextChild skips over the whole child)."""
+    if len(data) < 5:
+        raise EIOError("truncated header")
+    kind, n = struct.unpack_from(">BI", data, 0)
+    if kind != NODE:
+        return parse(data, 0)[0]
+    kids, offset = [], 5
+    for _ in range(n):
+        try:
+            c, offset = parse(data, offset, 1)
+        except EIOError:
+            break
+        kids.append(c)
+    return ByteTree(kids, declared=n)
+
+
+def first(t: ByteTree, k: int) -> List[ByteTree]:
+    """getNextChild() k times: the node announces at least k children and the first k are well formed."""
+    if t.is_leaf() or t.declared < k or len(t.children) < k:
+        raise EIOError("expected a node of at least %d children" % k)
+    return t.children[:k]
+
+
+def exact(t: ByteTree, k: int) -> List[ByteTree]:
+    """A node that announces exactly k children (getRemaining() == k), all of them well formed."""
+    if t.is_leaf() or t.declared != k or len(t.children) != k:
+        raise EIOError("expected a node of %d children" % k)
+    return t.children
 
 
 # ---------------------------------------------------------------- integers

@@ -163,7 +163,7 @@ class ECqPGroup:
         return P
 
     def parse_leaf(self, t: bt.ByteTree) -> ECPoint:
-        if t.is_leaf() or len(t.children) != 2 or not t.children[0].is_leaf() or not t.children[1].is_leaf():
+        if t.is_leaf() or t.declared != 2 or len(t.children) != 2 or not t.children[0].is_leaf() or not t.children[1].is_leaf():
             raise FormatError("point arity")
         return self._decode(t.children[0].value, t.children[1].value)
 

@@ -159,16 +159,14 @@ class PoSBasicTW:
     def set_commitment(self, t: bt.ByteTree) -> bt.ByteTree:
         G = self.G
         try:
-            if t.is_leaf() or len(t.children) != 6:
-                raise ar.FormatError("commitment arity")
-            c = t.children
+            c = bt.first(t, 6)   # btr.getNextChild() six times (:787-805); a seventh child is never looked at
             self.B = ar.parse_array(G, c[0], self.size)
             self.Ap = ar.parse_elem(G, c[1])
             self.Bp = ar.parse_array(G, c[2], self.size)
             self.Cp = ar.parse_elem(G, c[3])
             self.Dp = ar.parse_elem(G, c[4])
             self.Fp = ar.parse_elem(G, c[5], self.pkey)
-        except ar.FormatError:
+        except (ar.FormatError, bt.EIOError):
             self.B = [G.one] * self.size
             self.Bp = [G.one] * self.size
             self.Ap = self.Cp = self.Dp = G.one
@@ -204,16 +202,14 @@ class PoSBasicTW:
     def verify(self, t: bt.ByteTree) -> bool:
         G, g, h, u = self.G, self.g, self.h, self.u
         try:
-            if t.is_leaf() or len(t.children) != 6:
-                raise ar.FormatError("reply arity")
-            c = t.children
+            c = bt.first(t, 6)   # (:975-986)
             self.k_A = ar.parse_ring(G, c[0])
             self.k_B = ar.parse_ring_array(G, c[1], self.size)
             self.k_C = ar.parse_ring(G, c[2])
             self.k_D = ar.parse_ring(G, c[3])
             self.k_E = ar.parse_ring_array(G, c[4], self.size)
             self.k_F = ar.parse_ring(G, c[5], _ring_shape(self.pkey))
-        except ar.FormatError:
+        except (ar.FormatError, bt.EIOError):
             return False
         v = self.v
         h0 = h[0]
@@ -1014,7 +1010,7 @@ def _verify_mix(G, params: Params, k: int, threshold: int, d: dict, expected_aux
     if dec:   # readMixServerPKeys :228-266
         try:
             t = bt.read(need("proofs/PolynomialInExponent.bt"))
-            if t.is_leaf() or len(t.children) != threshold:
+            if t.is_leaf() or t.declared != threshold or len(t.children) != threshold:
                 raise ar.FormatError("degree")
             coeffs = [ar.parse_elem(G, c) for c in t.children]
         except (ar.FormatError, bt.EIOError):

@@ -1332,7 +1332,7 @@ def _fuzz_mutation(rng, nizkp, names):
 
 
 def native_vmnv_fuzz(vmx, spec, n, rounds, seed_label="fuzz", k=3, threshold=2, width=1, log=None, mode="mixing",
-                     maxciph=None):
+                     maxciph=None, oracle=False):
     """Differential fuzzing of the native universal verifier against the Python mirror: `rounds` random
     structure-aware mutations of an honest proof directory (bit flips, damaged headers, truncations, trailing
     bytes, swapped / missing / deeply nested files, junk in the text files); both must reach the same outcome --
@@ -1365,6 +1365,16 @@ def native_vmnv_fuzz(vmx, spec, n, rounds, seed_label="fuzz", k=3, threshold=2, 
         except vm.VerificationError:
             return ("failstop", V.report.get("shuffles"), V.report.get("poscs"))
 
+    OG = oracle_group(spec) if oracle else None
+    oparams = opr.Params(pgroup_string="fuzz-%s" % spec, sid="Session_1")
+
+    def outcome_oracle(d):   # the oracle's vmnv as a third party (`oracle=True`): same outcome, same derived values
+        try:
+            r = opr.verify_mix(OG, oparams, k, threshold, {nm: bytes(v) for nm, v in d.items()})
+            return ("verdict", r["accepted"], r["shuffles"], r["poscs"], r["decryption"], r.get("plaintexts"), r["vectors"])
+        except opr.MixVerificationError:
+            return ("failstop",)
+
     rng = _random.Random(seed_label)
     names = sorted(M.nizkp)
     tally = {}
@@ -1384,6 +1394,9 @@ def native_vmnv_fuzz(vmx, spec, n, rounds, seed_label="fuzz", k=3, threshold=2, 
                 bad[nm] = v
         a, b = outcome(VN, bad), outcome(VP, bad)
         assert a == b, (i, what, a, b)
+        if oracle:
+            c = outcome_oracle(bad)
+            assert c == (a if a[0] == "verdict" else a[:1]), (i, what, a, c)
         key = a[0] if a[0] == "failstop" else ("accepted" if a[1] else "rejected")
         tally[key] = tally.get(key, 0) + 1
         if log is not None:

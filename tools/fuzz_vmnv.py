@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--mode", default="mixing", choices=["mixing", "shuffling", "decryption"])
     ap.add_argument("--maxciph", type=int, default=0, help="pre-compute for this many ciphertexts first (0: no pre-computation)")
     ap.add_argument("--asan", action="store_true")
+    ap.add_argument("--oracle", action="store_true", help="the oracle's vmnv (oracle/protocols.py) as a third party")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
 
@@ -61,11 +62,11 @@ def main():
     t0 = time.time()
     tally = pb.native_vmnv_fuzz(vmx, spec, args.n, args.rounds, seed_label=args.seed, k=args.k, threshold=args.threshold,
                                 width=args.width, log=(lambda m: print(m, flush=True)) if args.verbose else None,
-                                mode=args.mode, maxciph=args.maxciph or None)
-    print("spec=%s n=%d k=%d threshold=%d width=%d mode=%s maxciph=%s seed=%r rounds=%d: native == mirror on every round; "
+                                mode=args.mode, maxciph=args.maxciph or None, oracle=args.oracle)
+    print("spec=%s n=%d k=%d threshold=%d width=%d mode=%s maxciph=%s seed=%r rounds=%d: native == mirror%s on every round; "
           "outcomes %s; %.0f s%s"
           % (args.spec, args.n, args.k, args.threshold, args.width, args.mode, args.maxciph or None, args.seed, args.rounds,
-             dict(sorted(tally.items())),
+             " == oracle" if args.oracle else "", dict(sorted(tally.items())),
              time.time() - t0, " (ASan + UBSan builds)" if os.environ.get("VMNV_FUZZ_CHILD") else ""))
 
 
