@@ -217,6 +217,17 @@ def main():
         raw[-2] ^= 8
         rej, _ = mix.verifyCommittedShuffle(verifier, 1, gens.copyOfRange(0, n), pcv.commitment, w,
                                             dataclasses.replace(proof, reply=bytes(raw)))
+        # the verifier that follows the bulletin board (its seed hash starts when the output is published; on shards
+        # the root rank alone hashes): same proof bytes from a prover with the same randomness, same verdict
+        prover2 = mix.ShufflerSession(Gx, pk, params, rs("cs/prover"))
+        cs2 = mix.CommittedShuffler(prover2, 1, maxciph)
+        cs2.precomp()
+        cs2.shrink(n)
+        sg = gens.copyOfRange(0, n)
+        ov = mix.OnlineCommittedVerification(verifier, 1, sg, pcv.commitment, w)
+        proof2, _ = cs2.shuffle(w, publish=ov.publish)
+        ok_on, out_on = ov.finish(proof2)
+        assert dataclasses.astuple(proof2) == dataclasses.astuple(proof) and ok_on is True and out_on.equals(out)
         return tuple(bytes(b) for b in pub), bytes(keep), dataclasses.astuple(proof), okc, bytes(keep2), ok, \
             out2.equals(out), rej
 
