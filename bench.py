@@ -15,6 +15,10 @@ PoSBasicTW verification of that proof.
   roofline  IMAD-pipe modmul roofline of the dominant kernel (fixed-base exponentiation).
   cpu_baseline  the oracle's GMP-backed C restatement on the host cores (bounded sample).
 
+Other workloads (`--workload`): verify-mix = vmnv over the proof directory of a 3-party mix (BASELINE.json config 3);
+committed-shuffle = pre-computation, then re-encryption + commitment-consistent proof of a shuffle, prove + verify
+(config 4's protocol).  The default run reports configs 3, 4, 5 as `other_configs`.
+
 `--impl reference` times that CPU restatement alone (the reference is Java + GMP natives; no JVM
 exists in this image) on the same config.
 """
