@@ -1230,7 +1230,7 @@ def native_vmnv_parity(vmx, spec, n, k=3, threshold=2, width=1, thorough=True, m
     # what is verified (-nodec, -noposc, -noccpos) and the expected type (-mix, -shuffle, -decrypt)
     options = (dict(dec=False), dict(posc=False), dict(ccpos=False), dict(posc=False, ccpos=False),
                dict(expectedType=mode), dict(expectedType="shuffling" if mode == "mixing" else "mixing"))
-    for kw in (options[1:2] if minimal else options):
+    for kw in (options[1:2] if minimal else options if thorough else options[2:3] + options[5:]):
         a = outcome(vn.MixNetElGamalVerifyFiatShamirSessionNative(G, params, k, threshold, **kw), M.nizkp)
         b = outcome(vm.MixNetElGamalVerifyFiatShamirSession(G, params, k, threshold, **kw), M.nizkp)
         assert a == b, (kw, a, b)
