@@ -34,7 +34,9 @@ typedef struct vmxv_params {
   const char* sid;            /* session identifier of the info file; the auxsid is read from the proof */
   const char* pgroup_string;  /* the pgroup string of the info file (enters the global prefix) */
   const char* expected_auxsid; /* NULL or "": accept the one in the proof (vmnv -auxsid) */
-  int expected_width;          /* <= 0: accept the one in the proof (vmnv -width) */
+  int expected_width;          /* > 0: the width the proof must have -- vmnv's `-width w`, or, for its default behaviour,
+                                  the `width` of the protocol info file (determineWidth :404-440: without the option the
+                                  proof's width must equal the info file's); <= 0: accept the one in the proof */
   const char* expected_type;   /* NULL or "": accept the type in the proof; else "mixing" | "shuffling" | "decryption"
                                   (vmnv -mix / -shuffle / -decrypt; MixNetElGamalVerifyFiatShamirSession.java:329-358) */
   int nodec, noposc, noccpos;  /* non-zero: do not verify the decryption / the proofs of shuffles of commitments / the

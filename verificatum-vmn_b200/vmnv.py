@@ -303,7 +303,8 @@ class MixNetElGamalVerifyFiatShamirSession:
                  expectedWidth: Optional[int] = None, expectedType: Optional[str] = None, dec: bool = True,
                  posc: bool = True, ccpos: bool = True):
         """`expectedAuxsid`, `expectedWidth`, `expectedType`: the `-auxsid` / `-width` / `-mix|-shuffle|-decrypt`
-        options of vmnv; None accepts whatever the proof directory names.  `dec`, `posc`, `ccpos`: what is verified
+        options of vmnv; None accepts whatever the proof directory names (vmnv without `-width` compares with the
+        width of the protocol info file, determineWidth :404-440: pass that width to get its default behaviour).  `dec`, `posc`, `ccpos`: what is verified
         (`-nodec`, `-noposc`, `-noccpos`; mixnet/SessionParams.java)."""
         self.pGroup, self.params, self.k, self.threshold = pGroup, params, k, threshold
         self.expectedAuxsid, self.expectedWidth, self.expectedType = expectedAuxsid, expectedWidth, expectedType
