@@ -1,9 +1,11 @@
 """A whole mix on the engine, and its universal verification: the array work of
 
-    mixnet/MixNetElGamalSession (shuffle by the first `activeThreshold` parties, then decryption),
+    mixnet/MixNetElGamalSession.java:161-358 (pre-computation, shuffling by the first `activeThreshold` parties --
+    plain or commitment-consistent --, decryption; sessions of type "mixing", "shuffling", "decryption"),
     elgamal/DistrElGamalSession.java:361-545 (decryption factors, their exchange, the batched proof),
-    mixnet/MixNetElGamalVerifyFiatShamirSession.java:1318-1668 (what `vmnv` does with a proof directory:
-    2 x verifyPoS + verification of the decryption, BASELINE.json config 3)
+    mixnet/MixNetElGamalVerifyFiatShamirSession.java:1318-1668 (what `vmnv` does with a proof directory of any of
+    those types: verifyPoS / verifyPoSC + shrinkPermComm + verifyCCPoS per party, the verification of the decryption;
+    2 x verifyPoS + decryption is BASELINE.json config 3)
 
 in the order and with the Fiat-Shamir inputs of the reference, on in-memory byte trees named like the
 files of the proof directory (mixnet/MixNetElGamalSession.java:381-446, mixnet/ShufflerElGamalSession.java:1077-1101,
